@@ -1,0 +1,363 @@
+"""Oracle (test infrastructure): univariate IHT, numpy restatement of the reference.
+
+Follows, function by function (all paths under /root/reference):
+  `fit_iht`            src/fit.jl:60-118
+  `fit_iht!`           src/fit.jl:145-207
+  `iht_one_step!`      src/fit.jl:213-263
+  `init_iht_indices!`  src/utilities.jl:366-438
+  `iht_stepsize!`      src/utilities.jl:722-764
+  `_iht_gradstep!`     src/utilities.jl:252-280  (+ vectorize!/unvectorize! :291-354,
+                        project_k! :553-559, _choose! :444-458)
+  `update_xb!`         src/utilities.jl:93-118
+  `update_mu!`         src/utilities.jl:74-82
+  `loglikelihood` / `deviance`  src/utilities.jl:9-61
+  `score!`             src/utilities.jl:126-135
+  `save_prev!`         src/utilities.jl:702-712
+  `check_convergence`  src/utilities.jl:953-957
+  `backtrack!`         src/utilities.jl:959-973
+  `save_best_model!`   src/utilities.jl:995-1006
+  `mle_for_r`          src/utilities.jl:141-247
+  `pve`                src/pve.jl:22-37
+
+Documented deviation (shared with the CUDA path): when the k-th magnitude is tied, the reference
+keeps every tie and then drops random entries of the support with the global RNG
+(`_choose!`, src/utilities.jl:444-458).  Both the oracle and the product instead drop the tied
+entries with the HIGHEST index, which is deterministic and identical whenever there is no tie.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+from scipy.special import digamma, polygamma
+
+from . import glm
+
+
+def project_k(x: np.ndarray, k: int) -> None:
+    """`project_k!(x, k)` (src/utilities.jl:553-559): zero everything with |x| < k-th largest |x|."""
+    if k < 0:
+        raise ValueError(f"Attempted to project to sparsity level {k}")
+    ax = np.abs(x)
+    a = np.partition(ax, ax.size - k)[ax.size - k]
+    x[ax < a] = 0.0
+
+
+def prune_ties(vals: np.ndarray, nz_mask: np.ndarray, excess: int) -> None:
+    """Deterministic replacement for `_choose!`: drop `excess` smallest-magnitude support entries,
+    highest index first (only ties at the threshold can be in excess)."""
+    pos = np.flatnonzero(nz_mask)
+    order = sorted(pos, key=lambda j: (abs(vals[j]), -j))
+    for j in order[:excess]:
+        vals[j] = 0.0
+        nz_mask[j] = False
+
+
+@dataclass
+class IHTTrace:
+    logl: list = field(default_factory=list)
+    backtracks: list = field(default_factory=list)
+    tol: list = field(default_factory=list)
+    eta: list = field(default_factory=list)
+    support: list = field(default_factory=list)
+
+
+@dataclass
+class IHTResult:
+    """`IHTResult` (src/data_structures.jl:245-258)."""
+    time: float
+    logl: float
+    iter: int
+    beta: np.ndarray
+    c: np.ndarray
+    J: int
+    k: int
+    group: list
+    d: str
+    sigma_g: float
+    trace: IHTTrace = None
+    r: float = 1.0   # NegativeBinomial nuisance parameter at exit
+
+
+class IHTVariable:
+    """`IHTVariable` (src/data_structures.jl:4-43), memory_efficient=true branch."""
+
+    def __init__(self, x, z, y, k, d, l, zkeep=None, est_r="None", nb_r=1.0):
+        self.x, self.y = x, np.asarray(y, dtype=np.float64)
+        z = np.asarray(z, dtype=np.float64)
+        self.z = z.reshape(-1, 1) if z.ndim == 1 else z
+        n, p = x.shape
+        q = self.z.shape[1]
+        if not (self.y.shape[0] == n == self.z.shape[0]):
+            raise ValueError(f"row dimension of y, x, and z ({self.y.shape[0]}, {n}, {self.z.shape[0]}) are not equal")
+        self.n, self.p, self.q = n, p, q
+        self.k, self.d, self.l, self.est_r, self.nb_r = int(k), d, l, est_r, float(nb_r)
+        self.zkeep = np.ones(q, dtype=bool) if zkeep is None else np.asarray(zkeep, dtype=bool)
+        if self.zkeep.shape[0] != q:
+            raise ValueError(f"zkeep must have length {q} but was {self.zkeep.shape[0]}")
+        self.zkeepn = int(self.zkeep.sum())
+        self.b = np.zeros(p); self.b0 = np.zeros(p); self.best_b = np.zeros(p)
+        self.xb = np.zeros(n); self.xgk = np.zeros(n)
+        self.idx = np.zeros(p, bool); self.idx0 = np.zeros(p, bool)
+        self.idc = self.zkeep.copy(); self.idc0 = self.zkeep.copy()
+        self.r = np.zeros(n); self.df = np.zeros(p); self.df2 = np.zeros(q)
+        self.c = np.zeros(q); self.c0 = np.zeros(q); self.best_c = np.zeros(q)
+        self.zc = np.zeros(n); self.mu = np.zeros(n); self.cv_wts = np.zeros(n)
+
+    # -- src/utilities.jl:74-82
+    def update_mu(self):
+        self.mu = glm.linkinv(self.l, self.xb + self.zc)
+
+    # -- src/utilities.jl:93-118
+    def update_xb(self):
+        idx = np.flatnonzero(self.idx)
+        self.xb = self.x.support_xb(idx, self.b[idx])
+        self.zc = self.z @ self.c
+        if self.d != glm.NORMAL:
+            np.clip(self.xb, -20, 20, out=self.xb)
+            np.clip(self.zc, -20, 20, out=self.zc)
+
+    # -- src/utilities.jl:52-61, 9-20
+    def deviance(self):
+        return glm.deviance(self.d, self.y, self.mu, self.cv_wts, self.nb_r)
+
+    def loglikelihood(self):
+        return glm.loglikelihood(self.d, self.y, self.mu, self.cv_wts, self.nb_r)
+
+    # -- src/utilities.jl:126-135
+    def score(self):
+        eta = self.xb + self.zc
+        with np.errstate(divide="ignore", invalid="ignore"):
+            w = glm.mueta(self.l, eta) / glm.glmvar(self.d, self.mu, self.nb_r)
+            self.r = w * (self.y - self.mu) * self.cv_wts
+        self.df = self.x.xt_v(self.r)
+        self.df2 = self.z.T @ self.r
+
+    # -- src/utilities.jl:291-354 + 553-559 + 444-458 (no weights / groups)
+    def _project_full(self, b, c):
+        """vectorize! -> project_k!(k + zkeepn) -> unvectorize!; returns nothing (in place)."""
+        full = np.concatenate([b, np.where(self.zkeep, np.inf, c)])
+        project_k(full, self.k + self.zkeepn)
+        b[:] = full[: self.p]
+        cpart = full[self.p:]
+        c[~self.zkeep] = cpart[~self.zkeep]
+
+    def _choose(self):
+        sparsity = self.k + self.zkeepn
+        nonzero = int(self.idx.sum()) + int(self.idc.sum()) - self.zkeepn
+        if nonzero > sparsity:
+            prune_ties(self.b, self.idx, nonzero - sparsity)
+
+    # -- src/utilities.jl:366-438
+    def init_iht_indices(self, cv_idx: np.ndarray):
+        for a in (self.b, self.b0, self.best_b, self.xb, self.xgk, self.r, self.df, self.df2, self.c,
+                  self.best_c, self.c0, self.zc, self.mu, self.cv_wts):
+            a[...] = 0
+        self.idx[:] = False; self.idx0[:] = False
+        self.idc = self.zkeep.copy(); self.idc0 = self.zkeep.copy()
+        self.cv_wts[np.asarray(cv_idx, dtype=bool)] = 1.0
+        # intercept by (clamped) Newton, :394-405
+        ybar = float(np.sum(self.y * self.cv_wts)) / int(np.count_nonzero(self.cv_wts))
+        for _ in range(20):
+            g1 = float(glm.linkinv(self.l, self.c[0]))
+            g2 = float(glm.mueta(self.l, self.c[0]))
+            self.c[0] = self.c[0] - min(max((g1 - ybar) / g2, -1.0), 1.0)
+            if abs(g1 - ybar) < 1e-10:
+                break
+        self.zc = self.z @ self.c
+        self.update_mu()
+        self.score()
+        # first k non-zero entries chosen from largest gradient; df itself is projected (:417-425)
+        self._project_full(self.df, self.df2)
+        self.idx = self.df != 0
+        self.idc = self.zkeep.copy()
+        sparsity = self.k + self.zkeepn
+        nonzero = int(self.idx.sum()) + int(self.idc.sum()) - self.zkeepn
+        if nonzero > sparsity:
+            # `_choose!` zeroes v.b (already 0) and clears idx; df keeps its value (:450-456)
+            tmp = self.df.copy()
+            prune_ties(tmp, self.idx, nonzero - sparsity)
+
+    # -- src/utilities.jl:722-764
+    def iht_stepsize(self):
+        idx = np.flatnonzero(self.idx)
+        self.xgk = self.x.support_xb(idx, self.df[idx])
+        zdf2 = self.z[:, self.idc] @ self.df2[self.idc]
+        self.xgk = self.xgk + zdf2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            sw = np.sqrt(glm.mueta(self.l, self.xb + self.zc) ** 2 / glm.glmvar(self.d, self.mu, self.nb_r)) * self.cv_wts
+            self.xgk = self.xgk * sw
+            numer = float(np.sum(self.df[idx] ** 2)) + float(np.sum(self.df2[self.idc] ** 2))
+            denom = float(np.dot(self.xgk, self.xgk))
+            eta = numer / denom if denom != 0 else (np.inf if numer > 0 else np.nan)
+        if np.isinf(eta) or np.isnan(eta):
+            eta = 1e-8
+        return eta
+
+    # -- src/utilities.jl:252-280
+    def iht_gradstep(self, eta):
+        self.b += eta * self.df
+        self.c += eta * self.df2
+        self._project_full(self.b, self.c)
+        self.idx = self.b != 0
+        self.idc = self.c != 0
+        self._choose()
+
+    # -- src/utilities.jl:702-712
+    def save_prev(self, cur_logl, best_logl):
+        self.b0 = self.b.copy(); self.idx0 = self.idx.copy()
+        self.idc0 = self.idc.copy(); self.c0 = self.c.copy()
+        if cur_logl > best_logl:
+            self.best_b = self.b.copy(); self.best_c = self.c.copy()
+        return max(cur_logl, best_logl)
+
+    # -- src/utilities.jl:953-957
+    def check_convergence(self):
+        the_norm = max(np.max(np.abs(self.b - self.b0)), np.max(np.abs(self.c - self.c0)))
+        return the_norm / (max(np.max(np.abs(self.b0)), np.max(np.abs(self.c0))) + 1.0)
+
+    # -- src/utilities.jl:959-973
+    def backtrack(self, eta):
+        self.b = self.b0.copy(); self.c = self.c0.copy()
+        self.iht_gradstep(eta)
+        self.update_xb(); self.update_mu()
+        if self.est_r != "None":
+            self.mle_for_r()
+        return self.loglikelihood()
+
+    # -- src/utilities.jl:995-1006
+    def save_best_model(self):
+        self.b = self.best_b.copy(); self.c = self.best_c.copy()
+        self.idx = self.b != 0; self.idc = self.c != 0
+        self.update_xb()
+        self.mu = glm.linkinv(self.l, self.xb)   # genotype predictors only
+
+    # -- src/utilities.jl:141-247
+    def mle_for_r(self):
+        if self.est_r == "MM":
+            self.nb_r = self._update_r_mm()
+        elif self.est_r == "Newton":
+            self.nb_r = self._update_r_newton()
+        else:
+            raise ValueError(f"Only support method is Newton or MM, but got {self.est_r}")
+
+    def _update_r_mm(self):
+        r = self.nb_r
+        num = 0.0
+        for yi in self.y:
+            j = np.arange(0, int(yi))
+            num += float(np.sum(r / (r + j)))
+        den = float(np.sum(np.log(r / (r + self.mu))))
+        return -num / den
+
+    def _update_r_newton(self, max_iter=100, conv_tol=1e-6):
+        y, mu = self.y, self.mu
+        r = self.nb_r
+
+        def d1(r):
+            return float(np.sum(-(y + r) / (mu + r) - np.log(mu + r) + 1 + np.log(r) + digamma(r + y) - digamma(r)))
+
+        def d2(r):
+            return float(np.sum((y + r) / (mu + r) ** 2 - 2 / (mu + r) + 1 / r + polygamma(1, r + y) - polygamma(1, r)))
+
+        def nb_logl(r):
+            self.nb_r = r
+            return self.loglikelihood()
+
+        new_r, stepsize = 1.0, 1.0
+        for _ in range(max_iter):
+            dx, dx2 = d1(r), d2(r)
+            increment = dx / dx2 if dx2 < 0 else dx
+            new_r = r - stepsize * increment
+            old_logl = nb_logl(r)
+            for _ in range(20):
+                if new_r <= 0:
+                    stepsize /= 2
+                    new_r = r - stepsize * increment
+                else:
+                    new_logl = nb_logl(new_r)
+                    if old_logl >= new_logl:
+                        stepsize /= 2
+                        new_r = r - stepsize * increment
+                    else:
+                        break
+            if abs(r - new_r) <= conv_tol:
+                self.nb_r = new_r
+                return new_r
+            r = new_r
+        self.nb_r = r
+        return r
+
+
+def iht_one_step(v: IHTVariable, old_logl: float, nstep: int):
+    """`iht_one_step!` (src/fit.jl:213-263)."""
+    eta = v.iht_stepsize()
+    v.iht_gradstep(eta)
+    v.update_xb(); v.update_mu()
+    if v.est_r != "None":
+        v.mle_for_r()
+    new_logl = v.loglikelihood()
+    eta_step = 0
+    while (old_logl > new_logl) and (eta_step < nstep):      # `_iht_backtrack_` :484-486
+        eta /= 2
+        new_logl = v.backtrack(eta)
+        eta_step += 1
+    v.score()
+    if np.isnan(new_logl):
+        raise FloatingPointError("Loglikelihood function is NaN, aborting...")
+    if np.isinf(new_logl):
+        raise FloatingPointError("Loglikelihood function is Inf, aborting...")
+    return eta, eta_step, new_logl
+
+
+def fit_iht_loop(v: IHTVariable, tol=1e-4, max_iter=200, min_iter=5, max_step=3, trace: IHTTrace = None):
+    """`fit_iht!` (src/fit.jl:145-207).  Returns (best_logl, mm_iter)."""
+    mm_iter = 0
+    next_logl = -np.inf
+    best_logl = -np.inf
+    for it in range(1, max_iter + 1):
+        if it >= max_iter:
+            best_logl = v.save_prev(next_logl, best_logl)
+            v.save_best_model()
+            mm_iter = it
+            break
+        best_logl = v.save_prev(next_logl, best_logl)
+        eta, eta_step, next_logl = iht_one_step(v, next_logl, max_step)
+        scaled_norm = v.check_convergence()
+        if trace is not None:
+            trace.logl.append(next_logl); trace.backtracks.append(eta_step)
+            trace.tol.append(scaled_norm); trace.eta.append(eta)
+            trace.support.append(np.flatnonzero(v.idx).copy())
+        if it >= min_iter and scaled_norm < tol:
+            best_logl = v.save_prev(next_logl, best_logl)
+            v.save_best_model()
+            mm_iter = it
+            break
+    return best_logl, mm_iter
+
+
+def pve(y, mu):
+    """`_pve` (src/pve.jl:22-24): var(mu)/var(y), sample variances."""
+    return float(np.var(mu, ddof=1) / np.var(y, ddof=1))
+
+
+def fit_iht(y, x, z=None, k=10, d=glm.NORMAL, l=None, zkeep=None, est_r="None", nb_r=1.0,
+            tol=1e-4, max_iter=200, min_iter=5, max_step=3, cv_train_idx=None) -> IHTResult:
+    """`fit_iht` (src/fit.jl:60-118) on an oracle SnpLinAlg `x` (see oracle/snp.py)."""
+    if z is None:
+        z = np.ones(x.shape[0])
+    if l is None:
+        l = glm.IDENTITY
+    if max_iter < 0 or max_step < 0 or k < 0:
+        raise AssertionError("max_iter, max_step and k must be nonnegative")
+    if not tol > np.finfo(np.float64).eps:
+        raise AssertionError("Value of global tol must exceed machine precision!")
+    v = IHTVariable(x, z, y, k, d, l, zkeep=zkeep, est_r=est_r, nb_r=nb_r)
+    v.init_iht_indices(np.ones(v.n, bool) if cv_train_idx is None else cv_train_idx)
+    trace = IHTTrace()
+    best_logl, mm_iter = fit_iht_loop(v, tol=tol, max_iter=max_iter, min_iter=min_iter,
+                                      max_step=max_step, trace=trace)
+    res = IHTResult(0.0, best_logl, mm_iter, v.best_b.copy(), v.best_c.copy(), 1, k, [], d,
+                    pve(v.y, v.mu), trace, v.nb_r)
+    res.v = v
+    return res
