@@ -1,0 +1,128 @@
+/*
+ * ihtb200.h — C ABI of libihtb200.so: the B200 (sm_100a) implementation of MendelIHT.jl's
+ * iterative-hard-thresholding hot path over 2-bit PLINK genotypes.
+ *
+ * The reference (OpenMendel/MendelIHT.jl v1.4.11) has no FFI of its own: its extension point is
+ * Julia dispatch on the matrix type M of IHTVariable{T,M} (src/data_structures.jl:4-6).  Each entry
+ * point below names the reference call it replaces; julia/MendelIHTB200.jl and INTEGRATION.md show the
+ * `ccall` binding a maintainer adds.  All functions return 0 on success or a negative IHTB_E* code;
+ * ihtb_last_error() returns the message for the calling thread.  Plain pointers and sizes only.
+ *
+ * Ownership: the caller owns every host array; the library copies inputs to the device during the
+ * call and never retains host pointers.  Handles are opaque and freed by the *_destroy functions.
+ * Threading: a genotype handle is immutable and may be shared; a fit handle is single-owner.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with IHTB_ECUDA.
+ */
+#ifndef IHTB200_H
+#define IHTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (the Julia shim rethrows the reference's exception types) ------------------- */
+#define IHTB_OK          0
+#define IHTB_EINVAL     -1   /* AssertionError / ArgumentError  (src/fit.jl:87-90, cross_validation.jl:81-85) */
+#define IHTB_EDIM       -2   /* DimensionMismatch               (src/data_structures.jl:63-85) */
+#define IHTB_EDOMAIN    -3   /* DomainError                     (src/utilities.jl:554) */
+#define IHTB_ENUMERIC   -4   /* ErrorException("Loglikelihood function is NaN|Inf, aborting...") (src/fit.jl:259-260) */
+#define IHTB_ECUDA      -5   /* CUDA / NCCL failure, or no device (no CPU fallback) */
+#define IHTB_ENOMEM     -6
+#define IHTB_EUNSUPPORTED -7
+
+/* ---- enums ------------------------------------------------------------------------------------ */
+enum { IHTB_NORMAL = 0, IHTB_BERNOULLI = 1, IHTB_POISSON = 2, IHTB_NEGBIN = 3 };
+enum { IHTB_LINK_IDENTITY = 0, IHTB_LINK_LOGIT = 1, IHTB_LINK_LOG = 2, IHTB_LINK_PROBIT = 3,
+       IHTB_LINK_CLOGLOG = 4, IHTB_LINK_CAUCHIT = 5, IHTB_LINK_SQRT = 6, IHTB_LINK_INVERSE = 7,
+       IHTB_LINK_INVSQ = 8 };
+/* X'v sweep arithmetic.  FAST = FP32 byte-LUT partial sums + FP64 cross-slab sums; the fit then
+ * re-scores every top-k candidate exactly in FP64, so support / iteration counts do not depend on it.
+ * EXACT = FP64 accumulation throughout (slower kernel; what ihtb_xt_v uses for parity checks). */
+enum { IHTB_SWEEP_FAST = 0, IHTB_SWEEP_EXACT = 1 };
+
+typedef struct ihtb_geno ihtb_geno;     /* replaces SnpLinAlg{Float64}(s; center, scale, impute) */
+typedef struct ihtb_fit ihtb_fit;       /* replaces IHTVariable{Float64, SnpLinAlg} (src/data_structures.jl:4-43) */
+typedef struct ihtb_mvfit ihtb_mvfit;   /* replaces mIHTVariable (src/data_structures.jl:140-180) */
+typedef struct ihtb_comm ihtb_comm;     /* NCCL communicator for SNP-sharded fits (no reference equivalent) */
+
+/* kwargs of fit_iht / fit_iht! (src/fit.jl:60-82, 145-154) */
+typedef struct ihtb_cfg {
+    int32_t dist;        /* IHTB_NORMAL ...                                   `d`        */
+    int32_t link;        /* IHTB_LINK_*                                       `l`        */
+    int64_t k;           /* sparsity                                          `k`        */
+    double  nb_r;        /* NegativeBinomial r (fixed; est_r = :None)         `d.r`      */
+    double  tol;         /* 1e-4                                              `tol`      */
+    int32_t max_iter;    /* 200 (100 in cv_iht)                               `max_iter` */
+    int32_t min_iter;    /* 5                                                 `min_iter` */
+    int32_t max_step;    /* 3                                                 `max_step` */
+    int32_t sweep_mode;  /* IHTB_SWEEP_FAST | IHTB_SWEEP_EXACT                           */
+} ihtb_cfg;
+
+/* IHTResult (src/data_structures.jl:245-258); beta/c are written through ihtb_fit_get */
+typedef struct ihtb_result {
+    double  time;        /* seconds inside the fit loop (src/fit.jl:157,174,200) */
+    double  logl;        /* best loglikelihood                                   */
+    int64_t iter;        /* iterations                                           */
+    double  sigma_g;     /* PVE  (src/pve.jl:31-33)                              */
+    int64_t n_sweeps;    /* full X'r sweeps executed (init + one per iteration)  */
+    int64_t n_backtracks;
+    double  sweep_seconds; /* device time spent inside the sweep kernels (CUDA events) */
+    int64_t n_launches;  /* kernels launched by this fit                         */
+    int64_t n_steps;     /* IHT steps taken = trace lines written (iter, or iter-1 on a max_iter exit) */
+} ihtb_result;
+
+/* one line of the verbose trace "Iteration i: loglikelihood = .., backtracks = .., tol = .." (src/fit.jl:194) */
+typedef struct ihtb_iter_trace {
+    double  logl;
+    double  tol;
+    double  eta;
+    int32_t backtracks;
+    int32_t n_candidates;  /* columns re-scored exactly by the projection of this iteration */
+} ihtb_iter_trace;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int32_t ihtb_version(void);
+int32_t ihtb_last_error(char* buf, int64_t cap);
+int32_t ihtb_device_count(int32_t* count);
+int32_t ihtb_set_device(int32_t device);
+int32_t ihtb_launch_count(int64_t* count);   /* kernels launched by this library in this process */
+
+/* ---- genotype operator (SnpArrays.jl SnpLinAlg; constructed at src/wrapper.jl:68-69,318-319) ---- */
+/* bed_cols: SNP-major packed columns WITHOUT the 3 magic bytes; column j starts at bed_cols + j*col_stride_bytes. */
+int32_t ihtb_geno_create(const uint8_t* bed_cols, int64_t n, int64_t p, int64_t col_stride_bytes,
+                         int32_t center, int32_t scale, int32_t impute, ihtb_geno** out);
+/* Synthetic PLINK matrix generated on the device (mirrors simulate_random_snparray, src/simulate_utilities.jl:23-51):
+ * maf_j = clip(0.5*U, 0.01, 0.5), genotype = Bern(maf)+Bern(maf), optional missing rate; counter-based hash keyed by
+ * (seed, global column, sample).  Columns [j0, j0+p_local) of a p_global-column matrix (j0=0, p_local=p for one GPU). */
+int32_t ihtb_geno_create_synthetic(int64_t n, int64_t p_local, int64_t j0, uint64_t seed, double missing_rate,
+                                   ihtb_geno** out);
+int32_t ihtb_geno_dims(const ihtb_geno* g, int64_t* n, int64_t* p);
+int32_t ihtb_geno_stats(const ihtb_geno* g, double* mu, double* sigma_inv, int64_t* n_missing);
+/* bit-exact getindex: out[(j-j0)*(i1-i0) + (i-i0)] = x[i, j] for i in [i0,i1), j in [j0,j1)  (src/utilities.jl:102,735) */
+int32_t ihtb_geno_decode(const ihtb_geno* g, int64_t i0, int64_t i1, int64_t j0, int64_t j1, double* out_colmajor);
+/* packed bytes of columns [j0,j1), ceil(n/4) bytes each (for generator parity and .bed export) */
+int32_t ihtb_geno_packed(const ihtb_geno* g, int64_t j0, int64_t j1, uint8_t* out);
+/* mul!(out, Transpose(x), V): V is n x m column-major, out is p x m column-major  (src/utilities.jl:133, src/multivariate.jl:85) */
+int32_t ihtb_xt_v(const ihtb_geno* g, const double* V, int64_t m, double* out, int32_t sweep_mode);
+/* x[:, idx] * coef: idx are 0-based columns, coef is k x m column-major, out is n x m  (src/utilities.jl:95-111,728-743) */
+int32_t ihtb_x_support(const ihtb_geno* g, const int64_t* idx, int64_t k, const double* coef, int64_t m, double* out);
+int32_t ihtb_geno_destroy(ihtb_geno* g);
+
+/* ---- univariate fit (fit_iht / fit_iht! / init_iht_indices!, src/fit.jl:60-207, src/utilities.jl:366-438) ---- */
+/* y[n]; z is n x q column-major with the intercept in column 0; zkeep[q] (0/1) or NULL for all kept. */
+int32_t ihtb_fit_create(const ihtb_geno* g, const double* y, const double* z, int64_t q, const uint8_t* zkeep,
+                        const ihtb_cfg* cfg, ihtb_fit** out);
+int32_t ihtb_fit_set_k(ihtb_fit* f, int64_t k);                       /* v.k = sparsity (src/cross_validation.jl:110) */
+int32_t ihtb_fit_init(ihtb_fit* f, const uint8_t* train_mask);         /* init_iht_indices!; NULL = all samples */
+int32_t ihtb_fit_run(ihtb_fit* f, ihtb_result* result, ihtb_iter_trace* trace, int64_t trace_cap);   /* fit_iht! + pve */
+/* any pointer may be NULL; beta[p], c[q], mu[n], xb[n] */
+int32_t ihtb_fit_get(const ihtb_fit* f, double* beta, double* c, double* mu, double* xb);
+int32_t ihtb_fit_predict(ihtb_fit* f, const uint8_t* test_mask, double* deviance);   /* predict! (src/cross_validation.jl:279-286) */
+int32_t ihtb_fit_destroy(ihtb_fit* f);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IHTB200_H */

@@ -1,0 +1,310 @@
+"""Host-side mirror of MendelIHT.jl's public API over libihtb200.so.
+
+Same names, argument meaning and error behaviour as the reference (all paths under /root/reference):
+  `B200SnpLinAlg`  <- `SnpLinAlg{Float64}(s; model=ADDITIVE_MODEL, center, scale, impute)`  src/wrapper.jl:68-69
+  `fit_iht`        <- src/fit.jl:60-118        `IHTResult` <- src/data_structures.jl:245-258
+  `cv_iht`         <- src/cross_validation.jl:60-131
+  `iht`            <- src/wrapper.jl:52-120    `cross_validate` <- src/wrapper.jl:301-349
+Julia is not available in this image, so this Python layer plays the role of julia/MendelIHTB200.jl (which binds
+the very same C entry points with ccall); every numerical step happens inside the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import Cfg, IterTrace, Result, check, f64, load, ptr
+
+NORMAL, BERNOULLI, POISSON, NEGBIN = "Normal", "Bernoulli", "Poisson", "NegativeBinomial"
+DIST_ID = {NORMAL: 0, BERNOULLI: 1, POISSON: 2, NEGBIN: 3}
+LINK_ID = {"IdentityLink": 0, "LogitLink": 1, "LogLink": 2, "ProbitLink": 3, "CloglogLink": 4, "CauchitLink": 5,
+           "SqrtLink": 6, "InverseLink": 7, "InverseSquareLink": 8}
+
+
+def canonicallink(d: str) -> str:
+    """`canonicallink(d())`, LogLink for NegativeBinomial (src/wrapper.jl:87)."""
+    return {NORMAL: "IdentityLink", BERNOULLI: "LogitLink", POISSON: "LogLink", NEGBIN: "LogLink"}[d]
+
+
+class B200SnpLinAlg:
+    """Device-resident 2-bit genotype matrix with SnpLinAlg semantics (n samples x p SNPs)."""
+
+    def __init__(self, handle, n, p, j0=0):
+        self._h = handle
+        self.n, self.p, self.j0 = int(n), int(p), int(j0)
+        self.center = self.scale = self.impute = True
+
+    @classmethod
+    def from_bed_columns(cls, bed_cols: np.ndarray, n: int, center=True, scale=True, impute=True):
+        """bed_cols: uint8 [p, stride>=ceil(n/4)] SNP-major packed columns (PLINK .bed without the 3 magic bytes)."""
+        bed_cols = np.ascontiguousarray(bed_cols, dtype=np.uint8)
+        if bed_cols.ndim != 2:
+            raise _lib.DimensionMismatch(_lib.IHTB_EDIM, "bed_cols must be [p, ceil(n/4)]")
+        h = C.c_void_p()
+        check(load().ihtb_geno_create(ptr(bed_cols, C.c_uint8), n, bed_cols.shape[0], bed_cols.shape[1],
+                                      int(center), int(scale), int(impute), C.byref(h)))
+        obj = cls(h, n, bed_cols.shape[0])
+        obj.center, obj.scale, obj.impute = bool(center), bool(scale), bool(impute)
+        return obj
+
+    @classmethod
+    def from_bed_file(cls, path: str, n: int, **kw):
+        raw = np.fromfile(path, dtype=np.uint8)
+        if raw[:3].tobytes() != bytes([0x6C, 0x1B, 0x01]):
+            raise ValueError("not a SNP-major PLINK .bed file")
+        stride = (n + 3) // 4
+        return cls.from_bed_columns(raw[3:].reshape(-1, stride), n, **kw)
+
+    @classmethod
+    def synthetic(cls, n: int, p: int, seed: int, missing_rate: float = 0.0, j0: int = 0):
+        h = C.c_void_p()
+        check(load().ihtb_geno_create_synthetic(n, p, j0, seed, missing_rate, C.byref(h)))
+        return cls(h, n, p, j0)
+
+    @property
+    def shape(self):
+        return (self.n, self.p)
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim - 1]
+
+    def stats(self):
+        mu = np.empty(self.p); sinv = np.empty(self.p); nm = np.empty(self.p, dtype=np.int64)
+        check(load().ihtb_geno_stats(self._h, ptr(mu, C.c_double), ptr(sinv, C.c_double), ptr(nm, C.c_int64)))
+        return mu, sinv, nm
+
+    def decode(self, i0=0, i1=None, j0=0, j1=None) -> np.ndarray:
+        """x[i0:i1, j0:j1] through the getindex formula, float64 [i1-i0, j1-j0]."""
+        i1 = self.n if i1 is None else i1
+        j1 = self.p if j1 is None else j1
+        out = np.empty((max(j1 - j0, 0), max(i1 - i0, 0)))
+        check(load().ihtb_geno_decode(self._h, i0, i1, j0, j1, ptr(out, C.c_double)))
+        return out.T
+
+    def packed(self, j0=0, j1=None) -> np.ndarray:
+        j1 = self.p if j1 is None else j1
+        out = np.empty((max(j1 - j0, 0), (self.n + 3) // 4), dtype=np.uint8)
+        check(load().ihtb_geno_packed(self._h, j0, j1, ptr(out, C.c_uint8)))
+        return out
+
+    def xt_v(self, v: np.ndarray, mode: int = _lib.SWEEP_FAST) -> np.ndarray:
+        """mul!(out, Transpose(x), v) for v [n] or [n, m]."""
+        v = np.asarray(v, dtype=np.float64)
+        one = v.ndim == 1
+        vm = np.asfortranarray(v.reshape(self.n, -1))
+        if vm.shape[0] != self.n:
+            raise _lib.DimensionMismatch(_lib.IHTB_EDIM, "length(v) != size(x, 1)")
+        m = vm.shape[1]
+        out = np.empty((self.p, m), order="F")
+        check(load().ihtb_xt_v(self._h, vm.ctypes.data_as(C.POINTER(C.c_double)), m,
+                               out.ctypes.data_as(C.POINTER(C.c_double)), mode))
+        return out[:, 0].copy() if one else out
+
+    def x_support(self, idx, coef) -> np.ndarray:
+        """x[:, idx] * coef for coef [k] or [k, m]."""
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        coef = np.asarray(coef, dtype=np.float64)
+        one = coef.ndim == 1
+        cm = np.asfortranarray(coef.reshape(idx.shape[0], -1))
+        m = cm.shape[1]
+        out = np.empty((self.n, m), order="F")
+        check(load().ihtb_x_support(self._h, ptr(idx, C.c_int64), idx.shape[0],
+                                    cm.ctypes.data_as(C.POINTER(C.c_double)), m,
+                                    out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out[:, 0].copy() if one else out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().ihtb_geno_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class IHTResult:
+    """`IHTResult` (src/data_structures.jl:245-258) + device-side counters."""
+    time: float
+    logl: float
+    iter: int
+    beta: np.ndarray
+    c: np.ndarray
+    J: int
+    k: int
+    group: list
+    d: str
+    sigma_g: float
+    trace: list = field(default_factory=list)   # [(logl, backtracks, tol, eta, n_candidates)] per iteration
+    n_sweeps: int = 0
+    n_backtracks: int = 0
+    sweep_seconds: float = 0.0
+    n_launches: int = 0
+
+
+class IHTVariable:
+    """`IHTVariable` (src/data_structures.jl:4-43): one fit's device workspace."""
+
+    def __init__(self, x: B200SnpLinAlg, z, y, k, d=NORMAL, l="IdentityLink", zkeep=None, nb_r=1.0, tol=1e-4,
+                 max_iter=200, min_iter=5, max_step=3, sweep_mode=_lib.SWEEP_FAST):
+        y = f64(y)
+        z = np.asarray(z, dtype=np.float64)
+        if z.ndim == 1:
+            z = z.reshape(-1, 1)
+        n = x.n
+        if not (y.shape[0] == n == z.shape[0]):
+            raise _lib.DimensionMismatch(
+                _lib.IHTB_EDIM, f"row dimension of y, x, and z ({y.shape[0]}, {n}, {z.shape[0]}) are not equal")
+        q = z.shape[1]
+        zk = None
+        if zkeep is not None:
+            zk = np.ascontiguousarray(zkeep, dtype=np.uint8)
+            if zk.shape[0] != q:
+                raise _lib.DimensionMismatch(_lib.IHTB_EDIM, f"zkeep must have length {q} but was {zk.shape[0]}")
+        self.x, self.n, self.p, self.q, self.d = x, n, x.p, q, d
+        self.cfg = Cfg(DIST_ID[d], LINK_ID[l], int(k), float(nb_r), float(tol), int(max_iter), int(min_iter),
+                       int(max_step), int(sweep_mode))
+        zf = np.asfortranarray(z)
+        self._h = C.c_void_p()
+        check(load().ihtb_fit_create(x._h, ptr(y, C.c_double), zf.ctypes.data_as(C.POINTER(C.c_double)), q,
+                                     ptr(zk, C.c_uint8) if zk is not None else None, C.byref(self.cfg),
+                                     C.byref(self._h)))
+
+    def set_k(self, k):
+        check(load().ihtb_fit_set_k(self._h, int(k)))
+        self.cfg.k = int(k)
+
+    def init_iht_indices(self, train_mask=None):
+        m = None if train_mask is None else np.ascontiguousarray(train_mask, dtype=np.uint8)
+        check(load().ihtb_fit_init(self._h, ptr(m, C.c_uint8) if m is not None else None))
+
+    def fit(self, trace_cap=None):
+        cap = int(self.cfg.max_iter) if trace_cap is None else trace_cap
+        res = Result()
+        tr = (IterTrace * max(cap, 1))()
+        check(load().ihtb_fit_run(self._h, C.byref(res), tr, cap))
+        n_it = min(int(res.n_steps), cap)
+        trace = [(tr[i].logl, tr[i].backtracks, tr[i].tol, tr[i].eta, tr[i].n_candidates) for i in range(n_it)]
+        return res, trace
+
+    def get(self, mu=False, xb=False):
+        beta = np.empty(self.p); c = np.empty(self.q)
+        m = np.empty(self.n) if mu else None
+        x = np.empty(self.n) if xb else None
+        check(load().ihtb_fit_get(self._h, ptr(beta, C.c_double), ptr(c, C.c_double),
+                                  ptr(m, C.c_double) if mu else None, ptr(x, C.c_double) if xb else None))
+        return beta, c, m, x
+
+    def predict(self, test_mask=None) -> float:
+        m = None if test_mask is None else np.ascontiguousarray(test_mask, dtype=np.uint8)
+        dev = C.c_double(0.0)
+        check(load().ihtb_fit_predict(self._h, ptr(m, C.c_uint8) if m is not None else None, C.byref(dev)))
+        return float(dev.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().ihtb_fit_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _check_args(k, max_iter, max_step, tol):
+    # the reference's @assert lines (src/fit.jl:87-90, src/utilities.jl:913)
+    if max_iter < 0:
+        raise AssertionError("Value of max_iter must be nonnegative!\n")
+    if max_step < 0:
+        raise AssertionError("Value of max_step must be nonnegative!\n")
+    if not tol > np.finfo(np.float64).eps:
+        raise AssertionError("Value of global tol must exceed machine precision!\n")
+    if k < 0:
+        raise AssertionError("Value of k (max predictors per group) must be nonnegative!\n")
+
+
+def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est_r="None", nb_r=1.0, tol=1e-4,
+            max_iter=200, min_iter=5, max_step=3, sweep_mode=_lib.SWEEP_FAST, verbose=False, io=None) -> IHTResult:
+    """`fit_iht(y, x, z; k, d, l, zkeep, tol, max_iter, min_iter, max_step)` (src/fit.jl:60-118)."""
+    _check_args(k, max_iter, max_step, tol)
+    if est_r != "None":
+        raise NotImplementedError("est_r = :MM / :Newton is not implemented on the device path yet")
+    if not x.center:
+        raise _lib.IHTBError(_lib.IHTB_EUNSUPPORTED, "x is not centered! Please construct SnpLinAlg{Float64}"
+                                                     "(::SnpArray, center=true, scale=true)")
+    if z is None:
+        z = np.ones(x.n)
+    l = l or "IdentityLink"
+    v = IHTVariable(x, z, y, k, d, l, zkeep, nb_r, tol, max_iter, min_iter, max_step, sweep_mode)
+    try:
+        v.init_iht_indices(None)
+        res, trace = v.fit()
+        beta, c, _, _ = v.get()
+    finally:
+        v.close()
+    if verbose:
+        import sys
+        out = io or sys.stdout
+        for i, t in enumerate(trace):
+            print(f"Iteration {i + 1}: loglikelihood = {t[0]}, backtracks = {t[1]}, tol = {t[2]}", file=out)
+    return IHTResult(res.time, res.logl, int(res.iter), beta, c, 1, k, [], d, res.sigma_g, trace, int(res.n_sweeps),
+                     int(res.n_backtracks), res.sweep_seconds, int(res.n_launches))
+
+
+def allocate_fold_and_k(q: int, path):
+    """Fold-major (fold, k) list, folds numbered 1..q (src/cross_validation.jl:217-223)."""
+    return [(fold, int(k)) for fold in range(1, q + 1) for k in path]
+
+
+def meanloss(fitloss, q: int, folds):
+    """Fold-size weighted sum of the per-fold losses (src/cross_validation.jl:304-320)."""
+    folds = np.asarray(folds)
+    ninfold = np.array([(folds == f).sum() for f in range(1, q + 1)])
+    pathsize = len(fitloss) // q
+    loss = np.zeros(pathsize)
+    for j in range(q):
+        wfold = ninfold[j] / folds.shape[0]
+        for i in range(pathsize):
+            loss[i] += fitloss[i + j * pathsize] * wfold
+    return loss
+
+
+def cv_iht(y, x: B200SnpLinAlg, z=None, d=NORMAL, l=None, path=range(1, 21), q=5, folds=None, zkeep=None,
+           nb_r=1.0, max_iter=100, min_iter=5, sweep_mode=_lib.SWEEP_FAST, combos=None, return_grid=False):
+    """`cv_iht` (src/cross_validation.jl:60-131).  `folds` in 1..q (drawn with numpy's default_rng if omitted).
+    `combos`: optional subset of grid positions to run (used by the multi-GPU farm, parallel.py)."""
+    path = [int(k) for k in path]
+    if max(path) > x.p:
+        raise ValueError("Sparsity level in `path` cannot be larger than total number of variables")
+    if folds is None:
+        folds = np.random.default_rng().integers(1, q + 1, size=x.n)
+    folds = np.asarray(folds)
+    if z is None:
+        z = np.ones(x.n)
+    l = l or "IdentityLink"
+    grid = allocate_fold_and_k(q, path)
+    todo = range(len(grid)) if combos is None else combos
+    mses = np.zeros(len(grid)); iters = np.zeros(len(grid), dtype=np.int64)
+    v = IHTVariable(x, z, y, max(path), d, l, zkeep, nb_r, 1e-4, max_iter, min_iter, 3, sweep_mode)
+    try:
+        for i in todo:
+            fold, k = grid[i]
+            test = folds == fold
+            v.set_k(k)
+            v.init_iht_indices(~test)
+            res, _ = v.fit(trace_cap=0)
+            iters[i] = res.iter
+            mses[i] = v.predict(test)
+    finally:
+        v.close()
+    if return_grid:
+        return mses, iters
+    return meanloss(mses, q, folds)

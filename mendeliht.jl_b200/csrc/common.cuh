@@ -1,0 +1,189 @@
+// Shared internals of libihtb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "../../include/ihtb200.h"
+
+namespace ihtb {
+
+// ---- error plumbing: C++ exceptions inside, status codes at the C boundary -------------------
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+void set_last_error(const std::string& m);
+const std::string& last_error();
+int64_t& launch_counter();
+
+#define IHTB_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            throw ::ihtb::Error(IHTB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+#define IHTB_CHECK(cond, code, msg)                                  \
+    do {                                                             \
+        if (!(cond)) throw ::ihtb::Error((code), (msg));             \
+    } while (0)
+
+// every kernel launch goes through this so `gpu_launches` in bench.py is a real count
+#define IHTB_LAUNCH(kernel, grid, block, smem, stream, ...)          \
+    do {                                                             \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);  \
+        ::ihtb::launch_counter()++;                                  \
+        IHTB_CUDA(cudaGetLastError());                               \
+    } while (0)
+
+template <typename F>
+static inline int32_t guard(F&& f) {
+    try {
+        f();
+        return IHTB_OK;
+    } catch (const Error& e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        set_last_error("out of host memory");
+        return IHTB_ENOMEM;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return IHTB_EINVAL;
+    }
+}
+
+// ---- device buffer RAII --------------------------------------------------------------------
+template <typename T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DBuf() = default;
+    explicit DBuf(size_t count) { alloc(count); }
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    ~DBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) {
+            cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+            if (e != cudaSuccess) {
+                p = nullptr; n = 0;
+                throw Error(IHTB_ENOMEM, std::string("cudaMalloc of ") + std::to_string(count * sizeof(T)) +
+                                             " bytes failed: " + cudaGetErrorString(e));
+            }
+        }
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    void zero(cudaStream_t s) { if (n) IHTB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+};
+
+// pinned host buffer for scalar read-backs
+template <typename T>
+struct HBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    HBuf() = default;
+    HBuf(const HBuf&) = delete;
+    HBuf& operator=(const HBuf&) = delete;
+    ~HBuf() { if (p) cudaFreeHost(p); }
+    void alloc(size_t count) {
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = count;
+        if (count) IHTB_CUDA(cudaMallocHost((void**)&p, count * sizeof(T)));
+    }
+};
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- genotype handle -----------------------------------------------------------------------
+}  // namespace ihtb
+
+struct ihtb_geno {
+    int device = 0;
+    int64_t n = 0;            // samples
+    int64_t p = 0;            // local SNP columns
+    int64_t j0 = 0;           // global index of local column 0 (SNP-sharded fits)
+    int64_t nbytes = 0;       // ceil(n/4)
+    int64_t stride = 0;       // padded bytes per column: multiple of 128 (= 512-sample slabs), zero padded
+    // Byte b of column j lives at bed + j*cs_j + (b>>7)*cs_s + (b&127):
+    //   column-major: cs_j = stride, cs_s = 128        slab-major tiles: cs_j = 128, cs_s = p*128
+    int64_t cs_j = 0, cs_s = 0;
+    int center = 1, scale = 1, impute = 1;
+    int sm_count = 148;
+    ihtb::DBuf<uint8_t> bed;  // p * stride bytes
+    ihtb::DBuf<double> mu, sinv;
+    ihtb::DBuf<int32_t> nmiss;
+    // CSR of missing samples per column (sparse imputation correction of the sweep)
+    ihtb::DBuf<int64_t> miss_ptr;   // [p+1]
+    ihtb::DBuf<int32_t> miss_idx;   // sample indices
+    int64_t total_missing = 0;
+};
+
+// what kernels see of a genotype handle
+struct GenoView {
+    const uint8_t* bed;
+    int64_t cs_j, cs_s, nbytes, stride, n, p;
+    const double* mu;
+    const double* sinv;
+    const int32_t* nmiss;
+    int impute;
+};
+static inline GenoView geno_view(const ihtb_geno* g) {
+    return GenoView{g->bed.p, g->cs_j, g->cs_s, g->nbytes, g->stride, g->n, g->p, g->mu.p, g->sinv.p, g->nmiss.p,
+                    g->impute};
+}
+__device__ __forceinline__ const uint8_t* gv_ptr(const GenoView& g, int64_t j, int64_t b) {
+    return g.bed + j * g.cs_j + (b >> 7) * g.cs_s + (b & 127);
+}
+
+namespace ihtb {
+
+// ---- device helpers --------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block reduction (fixed tree); result valid in thread 0. `sh` needs 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+    if (w == 0) v = warp_sum(v);
+    return v;
+}
+
+// ---- kernels implemented in other translation units -------------------------------------------
+// sweep.cu
+void sweep_xt_v(const ihtb_geno* g, const double* dV, int64_t m, double* dOut, int mode, cudaStream_t s,
+                double* sweep_seconds);
+// support.cu
+void x_support(const ihtb_geno* g, const int64_t* d_idx_local, int64_t k, const double* d_coef, int64_t m,
+               double* d_out, cudaStream_t s);
+void xt_gather(const ihtb_geno* g, const int64_t* d_cols_local, int64_t ncols, const double* d_v, int64_t m,
+               const double* d_vsum /*[m] device*/, double* d_out /*[ncols*m]*/, cudaStream_t s);
+
+}  // namespace ihtb

@@ -1,0 +1,568 @@
+// Univariate IHT driver: the whole fit_iht! loop (reference src/fit.jl:145-263) runs inside one C call.
+// O(n), O(p) and O(np) work is on the device; the k-sparse model (b, b0, best_b, supports, c) and the loop control
+// live on the host, which reads back a handful of scalars per iteration.
+//
+// Reference function -> where it is here
+//   init_iht_indices!  src/utilities.jl:366-438  -> ihtb_fit::init
+//   fit_iht!           src/fit.jl:145-207        -> ihtb_fit::run
+//   iht_one_step!      src/fit.jl:213-263        -> ihtb_fit::one_step
+//   iht_stepsize!      src/utilities.jl:722-764  -> ihtb_fit::stepsize   (x_support + k_stepsize)
+//   _iht_gradstep!     src/utilities.jl:252-280  -> ihtb_fit::gradstep   (topk_candidates + xt_gather + host top-k)
+//   update_xb!/update_mu!/loglikelihood          -> ihtb_fit::update_xb / glm_update (k_glm_mu)
+//   score!             src/utilities.jl:126-135  -> ihtb_fit::score_and_sweep (k_score + sweep)
+//   save_prev!/check_convergence/backtrack!/save_best_model!  -> same names below
+//   pve                src/pve.jl:31-33          -> ihtb_fit::compute_pve
+#include "glm.cuh"
+#include "topk.cuh"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <memory>
+#include <unordered_map>
+
+namespace ihtb {
+void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* vbar_host, int64_t m, double* dOut,
+                           int mode, cudaStream_t s, void* scratch_any, float* sweep_ms);
+void* sweep_scratch_create();
+void sweep_scratch_destroy(void* p);
+}  // namespace ihtb
+
+using namespace ihtb;
+
+// worst-case absolute error of the FAST sweep's sum_i dosage_ij u_i, as a multiple of ||u||_1 :
+// 1 rounding of u to FP32 + 3 adds in the table + 3 adds per lane + 5 butterfly adds = 12 roundings of at most
+// 2^-24 relative on partial sums bounded by 2*||u||_1 (dosage <= 2)  ->  12 * 2^-24 * 2 = 1.43e-6 ;
+// we use 2^-18 = 3.8e-6 (2.7x margin).  The FP64 cross-slab sums add < 1e-13.
+static const double kFastBound = 1.0 / 262144.0;
+static const double kExactBound = 1e-13;
+
+struct ihtb_fit {
+    const ihtb_geno* g = nullptr;
+    int64_t n = 0, p = 0, q = 0;
+    ihtb_cfg cfg{};
+    cudaStream_t s = nullptr;
+    std::vector<uint8_t> zkeep;
+    int zkeepn = 0;
+    int cap = 4096;
+
+    // device state
+    DBuf<double> d_y, d_z, d_w, d_xb, d_zc, d_mu, d_r, d_xs, d_dfa, d_b0d, d_part, d_scal, d_small, d_coef, d_gout,
+        d_vbar, d_sval;
+    DBuf<uint8_t> d_mask;
+    DBuf<uint32_t> d_keyL, d_keyU;
+    DBuf<int> d_hist;
+    DBuf<int64_t> d_sel;   // [TopkState (2 x int64) | cand[cap]]
+    DBuf<int64_t> d_idx, d_cols, d_sidx;
+    HBuf<double> h_scal, h_gout;
+    HBuf<int64_t> h_sel;
+    void* sweep_scratch = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool sweep_pending = false;
+    GlmCtx glm{};
+    TopkCtx tk{};
+
+    // host model state (k-sparse)
+    std::vector<int64_t> idx, idx0, best_idx, b0d_idx;
+    std::vector<double> b, b0, best_b;
+    std::vector<double> c, c0, best_c, df2;
+    std::vector<uint8_t> idc, idc0;
+    std::unordered_map<int64_t, double> df_exact;
+    bool df_sparse = false;
+    std::vector<int64_t> dfs_idx;
+    std::vector<double> dfs_val;
+    double rbar = 0.0, bound = 0.0, sum_w = 0.0, last_dev = 0.0;
+    bool inited = false;
+
+    // statistics
+    int64_t n_sweeps = 0, n_backtracks = 0, n_cand_iter = 0;
+    double sweep_ms_total = 0.0;
+    double pve = 0.0;
+
+    ~ihtb_fit() {
+        if (sweep_scratch) sweep_scratch_destroy(sweep_scratch);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (s) cudaStreamDestroy(s);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    void sync() { IHTB_CUDA(cudaStreamSynchronize(s)); }
+    void readback_scal(int nv) {
+        IHTB_CUDA(cudaMemcpyAsync(h_scal.p, d_scal.p, nv * sizeof(double), cudaMemcpyDeviceToHost, s));
+        sync();
+        if (sweep_pending) {
+            float ms = 0.f;
+            IHTB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+            sweep_ms_total += ms;
+            sweep_pending = false;
+        }
+    }
+    template <typename T>
+    void upload(T* dst, const T* src, size_t count) {
+        if (count) IHTB_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+
+    // ---- update_xb! genetic part: xb = x[:, idx] * b[idx]  (src/utilities.jl:95-111) ------------
+    void update_xb() {
+        std::vector<int64_t> ii; std::vector<double> vv;
+        for (size_t t = 0; t < idx.size(); ++t)
+            if (b[t] != 0.0) { ii.push_back(idx[t]); vv.push_back(b[t]); }
+        if (ii.empty()) { d_xb.zero(s); return; }
+        upload(d_idx.p, ii.data(), ii.size());
+        upload(d_coef.p, vv.data(), vv.size());
+        x_support(g, d_idx.p, (int64_t)ii.size(), d_coef.p, 1, d_xb.p, s);
+    }
+
+    // ---- zc = Z c, clamp, mu = linkinv, deviance, loglikelihood (src/utilities.jl:9-20,52-61,74-82,113-117) ----
+    double glm_update(int add_zc) {
+        upload(d_small.p, c.data(), (size_t)q);
+        glm_mu(glm, d_small.p, add_zc, s);
+        readback_scal(3);
+        double dev = h_scal.p[0], lp = h_scal.p[1], sw = h_scal.p[2];
+        last_dev = dev;
+        if (cfg.dist == IHTB_NORMAL) {
+            double phi = dev / (double)n;               // deviance / length(y), even under CV masks
+            double sigma = std::sqrt(phi);
+            return -0.5 * (dev / phi) - sw * (0.5 * std::log(2.0 * M_PI) + std::log(sigma));
+        }
+        return lp;
+    }
+
+    // ---- exact df_j for a list of columns (cached until the next sweep) --------------------------
+    void exact_df(const std::vector<int64_t>& cols) {
+        std::vector<int64_t> need;
+        for (int64_t j : cols)
+            if (!df_exact.count(j)) need.push_back(j);
+        if (need.empty()) return;
+        IHTB_CHECK((int64_t)need.size() <= (int64_t)d_cols.n, IHTB_ENUMERIC, "too many columns to re-score");
+        upload(d_cols.p, need.data(), need.size());
+        upload(d_vbar.p, &rbar, 1);
+        xt_gather(g, d_cols.p, (int64_t)need.size(), d_r.p, 1, d_vbar.p, d_gout.p, s);
+        IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_gout.p, need.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        sync();
+        for (size_t t = 0; t < need.size(); ++t) df_exact[need[t]] = h_gout.p[t];
+        n_cand_iter += (int64_t)need.size();
+    }
+
+    // ---- score! : r, df2 = Z'r, df = X'r (src/utilities.jl:126-135) ------------------------------
+    void score_and_sweep() {
+        glm_score(glm, s);
+        readback_scal(2 + (int)q);
+        double rsum = h_scal.p[0], rl1 = h_scal.p[1];
+        for (int64_t l = 0; l < q; ++l) df2[l] = h_scal.p[2 + l];
+        rbar = rsum / (double)n;
+        double ul1 = rl1 + (double)n * std::fabs(rbar);    // >= ||r - rbar||_1
+        bound = (cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound) * ul1;
+        IHTB_CUDA(cudaEventRecord(ev0, s));
+        sweep_xt_v_with_means(g, d_r.p, &rbar, 1, d_dfa.p, cfg.sweep_mode, s, sweep_scratch, nullptr);
+        IHTB_CUDA(cudaEventRecord(ev1, s));
+        sweep_pending = true;
+        ++n_sweeps;
+        df_exact.clear();
+        df_sparse = false;
+        exact_df(idx);
+    }
+
+    double df_at(int64_t j) const {
+        if (df_sparse) {
+            auto it = std::lower_bound(dfs_idx.begin(), dfs_idx.end(), j);
+            return (it != dfs_idx.end() && *it == j) ? dfs_val[it - dfs_idx.begin()] : 0.0;
+        }
+        return df_exact.at(j);
+    }
+
+    // ---- iht_stepsize! (src/utilities.jl:722-764) -------------------------------------------------
+    double stepsize() {
+        std::vector<double> coef(idx.size());
+        double numer = 0.0;
+        for (size_t t = 0; t < idx.size(); ++t) { coef[t] = df_at(idx[t]); numer += coef[t] * coef[t]; }
+        if (idx.empty()) {
+            d_xs.zero(s);
+        } else {
+            upload(d_idx.p, idx.data(), idx.size());
+            upload(d_coef.p, coef.data(), coef.size());
+            x_support(g, d_idx.p, (int64_t)idx.size(), d_coef.p, 1, d_xs.p, s);
+        }
+        std::vector<double> d2((size_t)q);
+        for (int64_t l = 0; l < q; ++l) {
+            d2[l] = idc[l] ? df2[l] : 0.0;
+            if (idc[l]) numer += df2[l] * df2[l];
+        }
+        upload(d_small.p + q, d2.data(), (size_t)q);
+        glm_stepsize(glm, d_small.p + q, d_xs.p, s);
+        readback_scal(1);
+        double denom = h_scal.p[0];
+        double eta = numer / denom;
+        if (std::isinf(eta) || std::isnan(eta)) eta = 1e-8;
+        return eta;
+    }
+
+    void sync_b0d() {   // device dense copy of b0 used by the candidate selection
+        if (!b0d_idx.empty()) {
+            upload(d_sidx.p, b0d_idx.data(), b0d_idx.size());
+            scatter_dense(d_b0d.p, d_sidx.p, nullptr, (int64_t)b0d_idx.size(), 1, s);
+        }
+        b0d_idx.clear();
+        std::vector<double> vals;
+        for (size_t t = 0; t < idx0.size(); ++t)
+            if (b0[t] != 0.0) { b0d_idx.push_back(idx0[t]); vals.push_back(b0[t]); }
+        if (!b0d_idx.empty()) {
+            upload(d_sidx.p, b0d_idx.data(), b0d_idx.size());
+            upload(d_sval.p, vals.data(), vals.size());
+            scatter_dense(d_b0d.p, d_sidx.p, d_sval.p, (int64_t)b0d_idx.size(), 0, s);
+        }
+    }
+
+    // candidates of the device selection over |b0 + eta*df| (dense df from the last sweep)
+    std::vector<int64_t> device_candidates(double eta) {
+        std::vector<int64_t> out;
+        if (cfg.k <= 0) return out;
+        topk_candidates(tk, d_dfa.p, d_b0d.p, g->sinv.p, eta, bound, cfg.k, s);
+        IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + cap) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        sync();
+        const TopkState* st = reinterpret_cast<const TopkState*>(h_sel.p);
+        IHTB_CHECK(st->count <= cap, IHTB_ENUMERIC,
+                   "degenerate projection: more than " + std::to_string(cap) +
+                       " entries lie within the sweep error bound of the k-th largest magnitude");
+        out.assign(h_sel.p + 2, h_sel.p + 2 + st->count);
+        return out;
+    }
+
+    static double b_lookup(const std::vector<int64_t>& ii, const std::vector<double>& vv, int64_t j) {
+        auto it = std::lower_bound(ii.begin(), ii.end(), j);
+        return (it != ii.end() && *it == j) ? vv[it - ii.begin()] : 0.0;
+    }
+
+    // ---- _iht_gradstep! : b = P_k(b0 + eta*df), c = c0 + eta*df2 (src/utilities.jl:252-280) --------
+    // Ties at the k-th magnitude: lowest position in [b; c] wins (the reference prunes at random, :444-458).
+    void gradstep(double eta) {
+        std::vector<int64_t> cand;
+        if (df_sparse) {
+            cand = dfs_idx;
+        } else {
+            cand = device_candidates(eta);
+        }
+        cand.insert(cand.end(), idx0.begin(), idx0.end());
+        std::sort(cand.begin(), cand.end());
+        cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+        if (!df_sparse) exact_df(cand);
+
+        struct Item { double a; int64_t pos; double v; };
+        std::vector<Item> items;
+        items.reserve(cand.size() + (size_t)q);
+        for (int64_t j : cand) {
+            double v = b_lookup(idx0, b0, j) + eta * df_at(j);
+            items.push_back({std::fabs(v), j, v});
+        }
+        for (int64_t l = 0; l < q; ++l) {
+            c[l] = c0[l] + eta * df2[l];
+            if (!zkeep[l]) items.push_back({std::fabs(c[l]), p + l, c[l]});
+        }
+        int64_t k = cfg.k;
+        std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) {
+            return x.a > y.a || (x.a == y.a && x.pos < y.pos);
+        });
+        idx.clear(); b.clear();
+        std::vector<std::pair<int64_t, double>> keep;
+        for (size_t t = 0; t < items.size(); ++t) {
+            bool kept = (int64_t)t < k;
+            if (items[t].pos >= p) {
+                if (!kept) c[items[t].pos - p] = 0.0;
+            } else if (kept && items[t].v != 0.0) {
+                keep.push_back({items[t].pos, items[t].v});
+            }
+        }
+        std::sort(keep.begin(), keep.end());
+        for (auto& kv : keep) { idx.push_back(kv.first); b.push_back(kv.second); }
+        for (int64_t l = 0; l < q; ++l) idc[l] = c[l] != 0.0;
+    }
+
+    // ---- save_prev! (src/utilities.jl:702-712) ----------------------------------------------------
+    double save_prev(double cur, double best) {
+        idx0 = idx; b0 = b; c0 = c; idc0 = idc;
+        if (cur > best) { best_idx = idx; best_b = b; best_c = c; }
+        sync_b0d();
+        return std::max(cur, best);
+    }
+
+    // ---- check_convergence (src/utilities.jl:953-957) ---------------------------------------------
+    double check_convergence() const {
+        double the_norm = 0.0, b0max = 0.0;
+        size_t i = 0, j = 0;
+        while (i < idx.size() || j < idx0.size()) {
+            double x = 0.0, y = 0.0;
+            if (j >= idx0.size() || (i < idx.size() && idx[i] < idx0[j])) x = b[i++];
+            else if (i >= idx.size() || idx0[j] < idx[i]) y = b0[j++];
+            else { x = b[i++]; y = b0[j++]; }
+            the_norm = std::max(the_norm, std::fabs(x - y));
+            b0max = std::max(b0max, std::fabs(y));
+        }
+        for (int64_t l = 0; l < q; ++l) {
+            the_norm = std::max(the_norm, std::fabs(c[l] - c0[l]));
+            b0max = std::max(b0max, std::fabs(c0[l]));
+        }
+        return the_norm / (b0max + 1.0);
+    }
+
+    // ---- save_best_model! (src/utilities.jl:995-1006) ---------------------------------------------
+    void save_best_model() {
+        idx.clear(); b.clear();
+        for (size_t t = 0; t < best_idx.size(); ++t)
+            if (best_b[t] != 0.0) { idx.push_back(best_idx[t]); b.push_back(best_b[t]); }
+        c = best_c;
+        for (int64_t l = 0; l < q; ++l) idc[l] = c[l] != 0.0;
+        update_xb();
+        glm_update(/*add_zc=*/0);     // mu = linkinv(xb): genotype predictors only
+    }
+
+    void compute_pve() {   // var(mu) / var(y), two-pass like Statistics.var
+        glm_sum2(glm, d_mu.p, d_y.p, s);
+        readback_scal(2);
+        double mm = h_scal.p[0] / (double)n, my = h_scal.p[1] / (double)n;
+        glm_ssq2(glm, d_mu.p, mm, d_y.p, my, s);
+        readback_scal(2);
+        pve = h_scal.p[0] / h_scal.p[1];
+    }
+
+    // ---- init_iht_indices! (src/utilities.jl:366-438) ----------------------------------------------
+    void init(const uint8_t* train_mask) {
+        idx.clear(); b.clear(); idx0.clear(); b0.clear(); best_idx.clear(); best_b.clear();
+        c.assign((size_t)q, 0.0); c0 = c; best_c = c; df2.assign((size_t)q, 0.0);
+        idc.assign(zkeep.begin(), zkeep.end()); idc0 = idc;
+        df_exact.clear(); dfs_idx.clear(); dfs_val.clear(); df_sparse = false;
+        d_xb.zero(s);
+        sync_b0d();     // idx0 empty -> clears the dense copy
+        const uint8_t* dm = nullptr;
+        if (train_mask) {
+            upload(d_mask.p, train_mask, (size_t)n);
+            dm = d_mask.p;
+        }
+        glm_set_weights(glm, dm, s);
+        readback_scal(2);
+        sum_w = h_scal.p[0];
+        double ybar = h_scal.p[1] / sum_w;
+        // intercept by Newton's method with the step clamped to +-1 (:394-405)
+        for (int it = 0; it < 20; ++it) {
+            double g1 = glm_linkinv(cfg.link, c[0]);
+            double g2 = glm_mueta(cfg.link, c[0]);
+            double step = (g1 - ybar) / g2;
+            step = std::min(std::max(step, -1.0), 1.0);
+            c[0] = c[0] - step;
+            if (std::fabs(g1 - ybar) < 1e-10) break;
+        }
+        glm_update(1);        // zc = Z c, mu (the reference does not clamp here; xb = 0 and |c1| is small)
+        score_and_sweep();
+        // first k entries chosen from the largest gradient; df itself becomes its projection (:417-425)
+        std::vector<int64_t> cand = device_candidates(1.0);
+        std::sort(cand.begin(), cand.end());
+        exact_df(cand);
+        struct Item { double a; int64_t pos; double v; };
+        std::vector<Item> items;
+        for (int64_t j : cand) { double v = df_exact.at(j); items.push_back({std::fabs(v), j, v}); }
+        for (int64_t l = 0; l < q; ++l)
+            if (!zkeep[l]) items.push_back({std::fabs(df2[l]), p + l, df2[l]});
+        std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) {
+            return x.a > y.a || (x.a == y.a && x.pos < y.pos);
+        });
+        std::vector<std::pair<int64_t, double>> keep;
+        for (size_t t = 0; t < items.size(); ++t) {
+            bool kept = (int64_t)t < cfg.k;
+            if (items[t].pos >= p) {
+                if (!kept) df2[items[t].pos - p] = 0.0;
+            } else if (kept && items[t].v != 0.0) {
+                keep.push_back({items[t].pos, items[t].v});
+            }
+        }
+        std::sort(keep.begin(), keep.end());
+        for (auto& kv : keep) { dfs_idx.push_back(kv.first); dfs_val.push_back(kv.second); }
+        df_sparse = true;
+        idx = dfs_idx;
+        b.assign(idx.size(), 0.0);
+        for (int64_t l = 0; l < q; ++l) idc[l] = zkeep[l];
+        inited = true;
+    }
+
+    // ---- iht_one_step! (src/fit.jl:213-263) --------------------------------------------------------
+    void one_step(double old_logl, double& eta, int& eta_step, double& new_logl) {
+        eta = stepsize();
+        gradstep(eta);
+        update_xb();
+        new_logl = glm_update(1);
+        eta_step = 0;
+        while (old_logl > new_logl && eta_step < cfg.max_step) {    // _iht_backtrack_ (src/utilities.jl:484-486)
+            eta /= 2;
+            idx = idx0; b = b0; c = c0;                              // backtrack! (src/utilities.jl:959-973)
+            gradstep(eta);
+            update_xb();
+            new_logl = glm_update(1);
+            ++eta_step;
+            ++n_backtracks;
+        }
+        score_and_sweep();
+        IHTB_CHECK(!std::isnan(new_logl), IHTB_ENUMERIC, "Loglikelihood function is NaN, aborting...");
+        IHTB_CHECK(!std::isinf(new_logl), IHTB_ENUMERIC, "Loglikelihood function is Inf, aborting...");
+    }
+
+    // ---- fit_iht! (src/fit.jl:145-207) -------------------------------------------------------------
+    void run(ihtb_result* res, ihtb_iter_trace* trace, int64_t trace_cap) {
+        IHTB_CHECK(inited, IHTB_EINVAL, "ihtb_fit_init must be called before ihtb_fit_run");
+        auto t0 = std::chrono::steady_clock::now();
+        int64_t launches0 = launch_counter();
+        int64_t mm_iter = 0, n_steps = 0;
+        double next_logl = -INFINITY, best_logl = -INFINITY;
+        n_backtracks = 0;
+        int64_t sweeps0 = n_sweeps;
+        double sweep_ms0 = sweep_ms_total;
+        for (int64_t iter = 1; iter <= cfg.max_iter; ++iter) {
+            if (iter >= cfg.max_iter) {
+                best_logl = save_prev(next_logl, best_logl);
+                save_best_model();
+                mm_iter = iter;
+                break;
+            }
+            best_logl = save_prev(next_logl, best_logl);
+            double eta; int eta_step;
+            n_cand_iter = 0;
+            one_step(next_logl, eta, eta_step, next_logl);
+            ++n_steps;
+            double scaled_norm = check_convergence();
+            if (trace && iter - 1 < trace_cap)
+                trace[iter - 1] = ihtb_iter_trace{next_logl, scaled_norm, eta, eta_step, (int32_t)n_cand_iter};
+            if (iter >= cfg.min_iter && scaled_norm < cfg.tol) {
+                best_logl = save_prev(next_logl, best_logl);
+                save_best_model();
+                mm_iter = iter;
+                break;
+            }
+        }
+        compute_pve();
+        inited = false;   // like the reference, a fitted variable must be re-initialised before another fit
+        if (res) {
+            res->time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            res->logl = best_logl;
+            res->iter = mm_iter;
+            res->sigma_g = pve;
+            res->n_sweeps = n_sweeps - sweeps0 + 1;   // + the sweep of init_iht_indices!
+            res->n_backtracks = n_backtracks;
+            res->sweep_seconds = (sweep_ms_total - sweep_ms0) * 1e-3;
+            res->n_launches = launch_counter() - launches0;
+            res->n_steps = n_steps;
+        }
+    }
+};
+
+extern "C" {
+
+int32_t ihtb_fit_create(const ihtb_geno* g, const double* y, const double* z, int64_t q, const uint8_t* zkeep,
+                        const ihtb_cfg* cfg, ihtb_fit** out) {
+    return guard([&] {
+        IHTB_CHECK(g && y && z && cfg && out, IHTB_EINVAL, "NULL argument");
+        IHTB_CHECK(q >= 1, IHTB_EDIM, "z must have at least the intercept column");
+        IHTB_CHECK(cfg->k >= 0, IHTB_EINVAL, "Value of k (max predictors per group) must be nonnegative!");
+        IHTB_CHECK(cfg->max_iter >= 0, IHTB_EINVAL, "Value of max_iter must be nonnegative!");
+        IHTB_CHECK(cfg->max_step >= 0, IHTB_EINVAL, "Value of max_step must be nonnegative!");
+        IHTB_CHECK(cfg->tol > 2.220446049250313e-16, IHTB_EINVAL, "Value of global tol must exceed machine precision!");
+        IHTB_CHECK(cfg->dist >= IHTB_NORMAL && cfg->dist <= IHTB_NEGBIN, IHTB_EINVAL, "unknown distribution");
+        IHTB_CHECK(cfg->link >= IHTB_LINK_IDENTITY && cfg->link <= IHTB_LINK_INVSQ, IHTB_EINVAL, "unknown link");
+        IHTB_CHECK(cfg->sweep_mode == IHTB_SWEEP_FAST || cfg->sweep_mode == IHTB_SWEEP_EXACT, IHTB_EINVAL,
+                   "bad sweep_mode");
+        IHTB_CHECK(cfg->k <= g->p, IHTB_EINVAL, "k cannot exceed the number of SNPs");
+        IHTB_CUDA(cudaSetDevice(g->device));
+        std::unique_ptr<ihtb_fit> f(new ihtb_fit());
+        f->g = g; f->n = g->n; f->p = g->p; f->q = q; f->cfg = *cfg;
+        f->zkeep.assign((size_t)q, 1);
+        if (zkeep) for (int64_t l = 0; l < q; ++l) f->zkeep[l] = zkeep[l] ? 1 : 0;
+        f->zkeepn = 0;
+        for (auto v : f->zkeep) f->zkeepn += v;
+        int64_t n = g->n, p = g->p;
+        f->cap = (int)std::max<int64_t>(4096, 4 * cfg->k + 1024);
+        IHTB_CUDA(cudaStreamCreateWithFlags(&f->s, cudaStreamNonBlocking));
+        IHTB_CUDA(cudaEventCreate(&f->ev0));
+        IHTB_CUDA(cudaEventCreate(&f->ev1));
+        f->d_y.alloc(n); f->d_z.alloc(n * q); f->d_w.alloc(n); f->d_xb.alloc(n); f->d_zc.alloc(n); f->d_mu.alloc(n);
+        f->d_r.alloc(n); f->d_xs.alloc(n); f->d_dfa.alloc(p); f->d_b0d.alloc(p); f->d_mask.alloc(n);
+        f->d_part.alloc((size_t)GLM_MAX_BLOCKS * (2 + q)); f->d_scal.alloc(2 + q + 8); f->d_small.alloc(2 * q);
+        size_t cols_cap = 2 * (size_t)f->cap + 64;
+        f->d_coef.alloc(cols_cap); f->d_gout.alloc(cols_cap); f->d_vbar.alloc(1); f->d_sval.alloc(cols_cap);
+        f->d_idx.alloc(cols_cap); f->d_cols.alloc(cols_cap); f->d_sidx.alloc(cols_cap);
+        f->d_keyL.alloc(p); f->d_keyU.alloc(p); f->d_hist.alloc(2048); f->d_sel.alloc(2 + f->cap);
+        f->h_scal.alloc(2 + q + 8); f->h_gout.alloc(cols_cap); f->h_sel.alloc(2 + f->cap);
+        f->sweep_scratch = sweep_scratch_create();
+        IHTB_CUDA(cudaMemcpyAsync(f->d_y.p, y, n * sizeof(double), cudaMemcpyHostToDevice, f->s));
+        IHTB_CUDA(cudaMemcpyAsync(f->d_z.p, z, n * q * sizeof(double), cudaMemcpyHostToDevice, f->s));
+        f->d_b0d.zero(f->s); f->d_hist.zero(f->s); f->d_xb.zero(f->s); f->d_zc.zero(f->s);
+        f->glm = GlmCtx{n, q, f->d_z.p, f->d_y.p, f->d_w.p, f->d_xb.p, f->d_zc.p, f->d_mu.p, f->d_r.p, f->d_part.p,
+                        f->d_scal.p, cfg->dist, cfg->link, cfg->nb_r};
+        f->tk = TopkCtx{p, f->d_keyL.p, f->d_keyU.p, f->d_hist.p, reinterpret_cast<TopkState*>(f->d_sel.p),
+                        f->d_sel.p + 2, f->cap};
+        f->sync();
+        *out = f.release();
+    });
+}
+
+int32_t ihtb_fit_set_k(ihtb_fit* f, int64_t k) {
+    return guard([&] {
+        IHTB_CHECK(f, IHTB_EINVAL, "NULL fit handle");
+        IHTB_CHECK(k >= 0 && k <= f->p, IHTB_EINVAL, "Sparsity level cannot be larger than total number of variables");
+        IHTB_CHECK(4 * k + 1024 <= f->cap, IHTB_EINVAL,
+                   "k exceeds the candidate capacity this fit handle was created with (create it with the largest k)");
+        f->cfg.k = k;
+    });
+}
+
+int32_t ihtb_fit_init(ihtb_fit* f, const uint8_t* train_mask) {
+    return guard([&] {
+        IHTB_CHECK(f, IHTB_EINVAL, "NULL fit handle");
+        IHTB_CUDA(cudaSetDevice(f->g->device));
+        f->init(train_mask);
+    });
+}
+
+int32_t ihtb_fit_run(ihtb_fit* f, ihtb_result* result, ihtb_iter_trace* trace, int64_t trace_cap) {
+    return guard([&] {
+        IHTB_CHECK(f, IHTB_EINVAL, "NULL fit handle");
+        IHTB_CUDA(cudaSetDevice(f->g->device));
+        f->run(result, trace, trace_cap);
+    });
+}
+
+int32_t ihtb_fit_get(const ihtb_fit* f, double* beta, double* c, double* mu, double* xb) {
+    return guard([&] {
+        IHTB_CHECK(f, IHTB_EINVAL, "NULL fit handle");
+        IHTB_CUDA(cudaSetDevice(f->g->device));
+        if (beta) {
+            std::fill(beta, beta + f->p, 0.0);
+            for (size_t t = 0; t < f->best_idx.size(); ++t) beta[f->best_idx[t]] = f->best_b[t];
+        }
+        if (c) std::copy(f->best_c.begin(), f->best_c.end(), c);
+        if (mu) IHTB_CUDA(cudaMemcpy(mu, f->d_mu.p, f->n * sizeof(double), cudaMemcpyDeviceToHost));
+        if (xb) IHTB_CUDA(cudaMemcpy(xb, f->d_xb.p, f->n * sizeof(double), cudaMemcpyDeviceToHost));
+    });
+}
+
+int32_t ihtb_fit_predict(ihtb_fit* f, const uint8_t* test_mask, double* deviance) {
+    return guard([&] {
+        IHTB_CHECK(f && deviance, IHTB_EINVAL, "NULL argument");
+        IHTB_CUDA(cudaSetDevice(f->g->device));
+        const uint8_t* dm = nullptr;
+        if (test_mask) {
+            f->upload(f->d_mask.p, test_mask, (size_t)f->n);
+            dm = f->d_mask.p;
+        }
+        glm_set_weights(f->glm, dm, f->s);     // predict! (src/cross_validation.jl:279-286)
+        f->update_xb();
+        f->glm_update(1);
+        *deviance = f->last_dev;
+    });
+}
+
+int32_t ihtb_fit_destroy(ihtb_fit* f) {
+    return guard([&] {
+        if (f) {
+            cudaSetDevice(f->g->device);
+            delete f;
+        }
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,371 @@
+// Genotype handle: device-resident 2-bit PLINK matrix + per-SNP statistics.
+// Replaces SnpLinAlg{Float64}(s; model=ADDITIVE_MODEL, center, scale, impute) (constructed at reference
+// src/wrapper.jl:68-69,318-319; SnpArrays.jl itself is an external dependency, semantics in SURVEY.md App. A.1).
+#include "common.cuh"
+#include "synth.cuh"
+#include <mutex>
+#include <stdlib.h>
+#include <string.h>
+
+namespace ihtb {
+
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& m) { t_last_error = m; }
+const std::string& last_error() { return t_last_error; }
+int64_t& launch_counter() {
+    static int64_t c = 0;
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernels
+// ---------------------------------------------------------------------------------------------
+
+// zero the unused high bits of the last data byte of every column (n % 4 != 0)
+__global__ void k_mask_tail(GenoView g, int n_rem) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= g.p) return;
+    uint8_t mask = (uint8_t)((1u << (2 * n_rem)) - 1u);
+    *const_cast<uint8_t*>(gv_ptr(g, j, g.nbytes - 1)) &= mask;
+}
+
+// repack a column-major staging block (columns [j0, j0+ncols), `nbytes` bytes each, pitch `pitch`) into the handle's
+// layout, 16 bytes per thread; the tail of the last 16-byte vector of a column is zero-filled
+__global__ void k_repack(const uint8_t* __restrict__ staging, int64_t pitch, int64_t j0, int64_t ncols, GenoView g) {
+    int64_t vec_per_col = (g.nbytes + 15) >> 4;
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= ncols * vec_per_col) return;
+    int64_t c = t / vec_per_col, v = t % vec_per_col;
+    const uint8_t* src = staging + c * pitch + 16 * v;
+    uint8_t tmp[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) tmp[k] = (16 * v + k < g.nbytes) ? src[k] : (uint8_t)0;
+    uint4 q;
+    memcpy(&q, tmp, 16);
+    *reinterpret_cast<uint4*>(const_cast<uint8_t*>(gv_ptr(g, j0 + c, 16 * v))) = q;
+}
+
+// inverse of k_repack for export: out[c][b] = byte b of column j0 + c
+__global__ void k_export(GenoView g, int64_t j0, int64_t ncols, uint8_t* __restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= ncols * g.nbytes) return;
+    int64_t c = t / g.nbytes, b = t % g.nbytes;
+    out[t] = *gv_ptr(g, j0 + c, b);
+}
+
+// one warp per column: counts of het (10), hom2 (11), missing (01) -> mu, sigma_inv
+// mu_j = (n1 + 2 n2) / n_obs ; sigma_inv_j = 1/sqrt(mu_j (1 - mu_j/2)) or 1 (same statistic as the
+// reference's standardize_genotypes!, src/wrapper.jl:409-416)
+__global__ void k_col_stats(GenoView g, int scale, double* __restrict__ mu, double* __restrict__ sinv,
+                            int32_t* __restrict__ nmiss) {
+    int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (j >= g.p) return;
+    const int64_t n = g.n;
+    int64_t nvec = g.stride >> 4;
+    int c1 = 0, c2 = 0, cm = 0;
+    for (int64_t v = lane; v < nvec; v += 32) {
+        uint4 q = *reinterpret_cast<const uint4*>(gv_ptr(g, j, 16 * v));
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            uint32_t lo = w[t] & 0x55555555u, hi = (w[t] >> 1) & 0x55555555u;
+            cm += __popc(lo & ~hi);
+            c1 += __popc(hi & ~lo);
+            c2 += __popc(hi & lo);
+        }
+    }
+    c1 = warp_sum(c1); c2 = warp_sum(c2); cm = warp_sum(cm);
+    if (lane == 0) {
+        double nobs = (double)(n - cm);
+        double m = (double)((int64_t)c1 + 2 * (int64_t)c2) / nobs;
+        double s = sqrt(__dmul_rn(m, __dsub_rn(1.0, m / 2.0)));
+        mu[j] = m;
+        sinv[j] = (scale && s > 0.0) ? 1.0 / s : 1.0;
+        nmiss[j] = cm;
+    }
+}
+
+// CSR fill of missing sample indices: one warp per column, ordered by sample index
+__global__ void k_fill_missing(GenoView g, const int64_t* __restrict__ ptr, int32_t* __restrict__ idx) {
+    int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (j >= g.p) return;
+    int64_t base = ptr[j];
+    if (ptr[j + 1] == base) return;
+    const int64_t nbytes = g.nbytes;
+    int64_t off = 0;
+    for (int64_t b0 = 0; b0 < nbytes; b0 += 32) {
+        int64_t b = b0 + lane;
+        uint32_t byte = (b < nbytes) ? *gv_ptr(g, j, b) : 0u;
+        uint32_t lo = byte & 0x55u, hi = (byte >> 1) & 0x55u;
+        uint32_t mm = lo & ~hi;  // bit 2t set if sample t of this byte is missing
+        int cnt = __popc(mm);
+        // exclusive prefix over lanes
+        int pre = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += t;
+        }
+        int total = __shfl_sync(0xffffffffu, pre, 31);
+        pre -= cnt;
+        int w = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (mm & (1u << (2 * t))) idx[base + off + pre + (w++)] = (int32_t)(4 * b + t);
+        off += total;
+    }
+}
+
+// bit-exact getindex: x_ij = ((missing ? mu_j : g_ij) - mu_j) * sigma_inv_j
+__global__ void k_decode(GenoView gv, int center, int64_t i0, int64_t i1, int64_t j0, int64_t j1,
+                         double* __restrict__ out) {
+    int64_t ni = i1 - i0;
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= ni * (j1 - j0)) return;
+    int64_t j = j0 + t / ni, i = i0 + t % ni;
+    uint32_t code = (*gv_ptr(gv, j, i >> 2) >> (2 * (i & 3))) & 3u;
+    double m = gv.mu[j];
+    double g = (code == 2) ? 1.0 : (code == 3) ? 2.0 : (code == 1) ? (gv.impute ? m : 0.0) : 0.0;
+    if (center) g = __dsub_rn(g, m);
+    out[t] = __dmul_rn(g, gv.sinv[j]);
+}
+
+// synthetic generator: one thread per 32-bit word (16 samples) of a column
+__global__ void k_synth(GenoView g, int64_t j0, uint64_t seed, uint32_t miss_thr) {
+    const int64_t n = g.n;
+    int64_t words = g.stride >> 2;
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= g.p * words) return;
+    int64_t j = t / words, w = t % words;
+    uint64_t key = synth_col_key(seed, (uint64_t)(j0 + j));
+    uint64_t thr = synth_maf_threshold(key);
+    uint32_t out = 0;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        int64_t i = 16 * w + s;
+        if (i < n) out |= synth_code(key, thr, miss_thr, (uint64_t)i) << (2 * s);
+    }
+    *reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(gv_ptr(g, j, 4 * w))) = out;
+}
+
+__global__ void k_prefix_ptr(const int32_t* __restrict__ nmiss, int64_t p, int64_t* __restrict__ ptr) {
+    // single-thread exclusive scan (p <= a few million; runs once per handle)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int64_t acc = 0;
+        for (int64_t j = 0; j < p; ++j) { ptr[j] = acc; acc += nmiss[j]; }
+        ptr[p] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+static void finish_handle(ihtb_geno* g) {
+    cudaStream_t s = 0;
+    g->mu.alloc(g->p); g->sinv.alloc(g->p); g->nmiss.alloc(g->p);
+    int64_t threads = g->p * 32;
+    IHTB_LAUNCH(k_col_stats, (unsigned)ceil_div(threads, 256), 256, 0, s, geno_view(g), g->scale, g->mu.p, g->sinv.p,
+                g->nmiss.p);
+    g->miss_ptr.alloc(g->p + 1);
+    IHTB_LAUNCH(k_prefix_ptr, 1, 32, 0, s, g->nmiss.p, g->p, g->miss_ptr.p);
+    int64_t total = 0;
+    IHTB_CUDA(cudaMemcpy(&total, g->miss_ptr.p + g->p, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    g->total_missing = total;
+    if (total > 0) {
+        g->miss_idx.alloc(total);
+        IHTB_LAUNCH(k_fill_missing, (unsigned)ceil_div(threads, 256), 256, 0, s, geno_view(g), g->miss_ptr.p,
+                    g->miss_idx.p);
+    }
+    IHTB_CUDA(cudaStreamSynchronize(s));
+}
+
+static ihtb_geno* new_handle(int64_t n, int64_t p, int center, int scale, int impute) {
+    IHTB_CHECK(n > 0 && p > 0, IHTB_EDIM, "genotype matrix must have n > 0 and p > 0");
+    IHTB_CHECK(n < (int64_t(1) << 31), IHTB_EDIM, "n must be < 2^31");
+    IHTB_CHECK(center == 1, IHTB_EUNSUPPORTED,
+               "x is not centered! Please construct SnpLinAlg{Float64}(::SnpArray, center=true, scale=true)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw Error(IHTB_ECUDA, "no CUDA device available (libihtb200 has no CPU fallback)");
+    ihtb_geno* g = new ihtb_geno();
+    IHTB_CUDA(cudaGetDevice(&g->device));
+    IHTB_CUDA(cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, g->device));
+    g->n = n; g->p = p;
+    g->nbytes = (n + 3) / 4;
+    g->stride = ceil_div(g->nbytes, 128) * 128;
+    // HBM layout: slab-major 128-byte tiles by default (the sweep then streams contiguous memory);
+    // IHTB_LAYOUT=colmajor keeps PLINK's column-major order (padded stride)
+    const char* lay = getenv("IHTB_LAYOUT");
+    if (lay && std::string(lay) == "colmajor") { g->cs_j = g->stride; g->cs_s = 128; }
+    else { g->cs_j = 128; g->cs_s = g->p * 128; }
+    g->center = center; g->scale = scale; g->impute = impute;
+    try {
+        g->bed.alloc((size_t)(g->p * g->stride));
+    } catch (...) {
+        delete g;
+        throw;
+    }
+    return g;
+}
+
+}  // namespace ihtb
+
+using namespace ihtb;
+
+extern "C" {
+
+int32_t ihtb_version(void) { return 100; }
+
+int32_t ihtb_last_error(char* buf, int64_t cap) {
+    if (!buf || cap <= 0) return IHTB_EINVAL;
+    const std::string& m = ihtb::last_error();
+    int64_t k = (int64_t)m.size() < cap - 1 ? (int64_t)m.size() : cap - 1;
+    memcpy(buf, m.data(), (size_t)k);
+    buf[k] = 0;
+    return IHTB_OK;
+}
+
+int32_t ihtb_device_count(int32_t* count) {
+    return guard([&] {
+        IHTB_CHECK(count, IHTB_EINVAL, "count is NULL");
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        *count = (e == cudaSuccess) ? n : 0;
+        if (e != cudaSuccess) cudaGetLastError();
+    });
+}
+
+int32_t ihtb_set_device(int32_t device) {
+    return guard([&] { IHTB_CUDA(cudaSetDevice(device)); });
+}
+
+int32_t ihtb_launch_count(int64_t* count) {
+    return guard([&] {
+        IHTB_CHECK(count, IHTB_EINVAL, "count is NULL");
+        *count = launch_counter();
+    });
+}
+
+int32_t ihtb_geno_create(const uint8_t* bed_cols, int64_t n, int64_t p, int64_t col_stride_bytes, int32_t center,
+                         int32_t scale, int32_t impute, ihtb_geno** out) {
+    return guard([&] {
+        IHTB_CHECK(bed_cols && out, IHTB_EINVAL, "NULL argument");
+        IHTB_CHECK(col_stride_bytes >= (n + 3) / 4, IHTB_EDIM, "col_stride_bytes is smaller than ceil(n/4)");
+        ihtb_geno* g = new_handle(n, p, center, scale, impute);
+        try {
+            IHTB_CUDA(cudaMemset(g->bed.p, 0, (size_t)(g->p * g->stride)));
+            // H2D in column blocks of <= 256 MiB through a staging buffer, then repack into the device layout
+            int64_t pitch = ceil_div(g->nbytes, 16) * 16;
+            int64_t cols_per = (int64_t(256) << 20) / pitch;
+            if (cols_per < 1) cols_per = 1;
+            if (cols_per > p) cols_per = p;
+            DBuf<uint8_t> staging((size_t)(cols_per * pitch));
+            GenoView gv = geno_view(g);
+            int64_t vec_per_col = (g->nbytes + 15) >> 4;
+            for (int64_t j = 0; j < p; j += cols_per) {
+                int64_t h = (p - j < cols_per) ? p - j : cols_per;
+                IHTB_CUDA(cudaMemcpy2D(staging.p, (size_t)pitch, bed_cols + j * col_stride_bytes,
+                                       (size_t)col_stride_bytes, (size_t)g->nbytes, (size_t)h,
+                                       cudaMemcpyHostToDevice));
+                IHTB_LAUNCH(k_repack, (unsigned)ceil_div(h * vec_per_col, 256), 256, 0, 0, staging.p, pitch, j, h, gv);
+                IHTB_CUDA(cudaDeviceSynchronize());
+            }
+            if (n % 4) IHTB_LAUNCH(k_mask_tail, (unsigned)ceil_div(p, 256), 256, 0, 0, gv, (int)(n % 4));
+            finish_handle(g);
+        } catch (...) {
+            delete g;
+            throw;
+        }
+        *out = g;
+    });
+}
+
+int32_t ihtb_geno_create_synthetic(int64_t n, int64_t p_local, int64_t j0, uint64_t seed, double missing_rate,
+                                   ihtb_geno** out) {
+    return guard([&] {
+        IHTB_CHECK(out, IHTB_EINVAL, "NULL argument");
+        IHTB_CHECK(missing_rate >= 0.0 && missing_rate < 1.0, IHTB_EINVAL, "missing_rate must be in [0, 1)");
+        ihtb_geno* g = new_handle(n, p_local, 1, 1, 1);
+        try {
+            g->j0 = j0;
+            uint32_t miss_thr = synth_missing_threshold(missing_rate);
+            int64_t words = g->stride >> 2;
+            int64_t total = g->p * words;
+            IHTB_LAUNCH(k_synth, (unsigned)ceil_div(total, 256), 256, 0, 0, geno_view(g), j0, seed, miss_thr);
+            finish_handle(g);
+        } catch (...) {
+            delete g;
+            throw;
+        }
+        *out = g;
+    });
+}
+
+int32_t ihtb_geno_dims(const ihtb_geno* g, int64_t* n, int64_t* p) {
+    return guard([&] {
+        IHTB_CHECK(g, IHTB_EINVAL, "NULL genotype handle");
+        if (n) *n = g->n;
+        if (p) *p = g->p;
+    });
+}
+
+int32_t ihtb_geno_stats(const ihtb_geno* g, double* mu, double* sigma_inv, int64_t* n_missing) {
+    return guard([&] {
+        IHTB_CHECK(g, IHTB_EINVAL, "NULL genotype handle");
+        IHTB_CUDA(cudaSetDevice(g->device));
+        if (mu) IHTB_CUDA(cudaMemcpy(mu, g->mu.p, g->p * sizeof(double), cudaMemcpyDeviceToHost));
+        if (sigma_inv) IHTB_CUDA(cudaMemcpy(sigma_inv, g->sinv.p, g->p * sizeof(double), cudaMemcpyDeviceToHost));
+        if (n_missing) {
+            std::vector<int32_t> tmp(g->p);
+            IHTB_CUDA(cudaMemcpy(tmp.data(), g->nmiss.p, g->p * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            for (int64_t j = 0; j < g->p; ++j) n_missing[j] = tmp[j];
+        }
+    });
+}
+
+int32_t ihtb_geno_decode(const ihtb_geno* g, int64_t i0, int64_t i1, int64_t j0, int64_t j1, double* out) {
+    return guard([&] {
+        IHTB_CHECK(g && out, IHTB_EINVAL, "NULL argument");
+        IHTB_CHECK(0 <= i0 && i0 <= i1 && i1 <= g->n && 0 <= j0 && j0 <= j1 && j1 <= g->p, IHTB_EDIM,
+                   "decode block out of bounds");
+        IHTB_CUDA(cudaSetDevice(g->device));
+        int64_t total = (i1 - i0) * (j1 - j0);
+        if (total == 0) return;
+        DBuf<double> d((size_t)total);
+        IHTB_LAUNCH(k_decode, (unsigned)ceil_div(total, 256), 256, 0, 0, geno_view(g), g->center, i0, i1, j0, j1, d.p);
+        IHTB_CUDA(cudaMemcpy(out, d.p, total * sizeof(double), cudaMemcpyDeviceToHost));
+    });
+}
+
+int32_t ihtb_geno_packed(const ihtb_geno* g, int64_t j0, int64_t j1, uint8_t* out) {
+    return guard([&] {
+        IHTB_CHECK(g && out, IHTB_EINVAL, "NULL argument");
+        IHTB_CHECK(0 <= j0 && j0 <= j1 && j1 <= g->p, IHTB_EDIM, "column range out of bounds");
+        IHTB_CUDA(cudaSetDevice(g->device));
+        if (j1 == j0) return;
+        int64_t cols_per = (int64_t(256) << 20) / g->nbytes;
+        if (cols_per < 1) cols_per = 1;
+        if (cols_per > j1 - j0) cols_per = j1 - j0;
+        DBuf<uint8_t> staging((size_t)(cols_per * g->nbytes));
+        for (int64_t j = j0; j < j1; j += cols_per) {
+            int64_t h = (j1 - j < cols_per) ? j1 - j : cols_per;
+            IHTB_LAUNCH(k_export, (unsigned)ceil_div(h * g->nbytes, 256), 256, 0, 0, geno_view(g), j, h, staging.p);
+            IHTB_CUDA(cudaMemcpy(out + (j - j0) * g->nbytes, staging.p, (size_t)(h * g->nbytes),
+                                 cudaMemcpyDeviceToHost));
+        }
+    });
+}
+
+int32_t ihtb_geno_destroy(ihtb_geno* g) {
+    return guard([&] {
+        if (g) {
+            cudaSetDevice(g->device);
+            delete g;
+        }
+    });
+}
+
+}  // extern "C"

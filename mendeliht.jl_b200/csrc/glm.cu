@@ -1,0 +1,192 @@
+// Fused elementwise GLM kernels + deterministic reductions over the n-vectors of one fit.
+// Replace update_mu! (reference src/utilities.jl:74-82), the clamp and z*c of update_xb! (:113-117),
+// deviance / loglikelihood (:9-61), the residual loop of score! (:128-134, incl. df2 = Z'r) and the
+// sqrt(W) weighting + dot of iht_stepsize! (:744-756).  Link / variance / deviance / logpdf formulas are those
+// of GLM.jl 1.x and Distributions.jl 0.25.
+#include "glm.cuh"
+
+namespace ihtb {
+
+constexpr int GLM_THREADS = 256;
+
+static inline int glm_grid(int64_t n) {
+    int64_t b = ceil_div(n, GLM_THREADS);
+    return (int)(b < 1 ? 1 : (b > GLM_MAX_BLOCKS ? GLM_MAX_BLOCKS : b));
+}
+
+// xb (clamped in place unless Normal), zc = Z c (clamped), mu = linkinv(xb + zc) [or linkinv(xb) when !add_zc],
+// partial sums: [0] sum w*devresid, [1] sum w*logpdf (phi-free part; unused for Normal), [2] sum w
+__global__ void __launch_bounds__(GLM_THREADS)
+k_glm_mu(int64_t n, int64_t q, const double* __restrict__ Z, const double* __restrict__ c, double* __restrict__ xb,
+         double* __restrict__ zc, double* __restrict__ mu, const double* __restrict__ y, const double* __restrict__ w,
+         int dist, int link, double nb_r, int add_zc, double* __restrict__ part) {
+    __shared__ double sh[32];
+    double a_dev = 0.0, a_lp = 0.0, a_w = 0.0;
+    const bool clampit = dist != IHTB_NORMAL;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double z = 0.0;
+        for (int64_t l = 0; l < q; ++l) z += Z[i + l * n] * c[l];
+        double x = xb[i];
+        if (clampit) {
+            x = fmin(fmax(x, -20.0), 20.0);
+            z = fmin(fmax(z, -20.0), 20.0);
+            xb[i] = x;
+        }
+        zc[i] = z;
+        double m = glm_linkinv(link, add_zc ? x + z : x);
+        mu[i] = m;
+        double wi = w[i], yi = y[i];
+        a_dev += wi * glm_devresid(dist, yi, m, nb_r);
+        if (dist != IHTB_NORMAL) a_lp += wi * glm_logpdf_nophi(dist, yi, m, nb_r);
+        a_w += wi;
+    }
+    a_dev = block_sum(a_dev, sh);
+    a_lp = block_sum(a_lp, sh);
+    a_w = block_sum(a_w, sh);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x * 3 + 0] = a_dev;
+        part[blockIdx.x * 3 + 1] = a_lp;
+        part[blockIdx.x * 3 + 2] = a_w;
+    }
+}
+
+// r_i = mueta(eta_i)/glmvar(mu_i) * (y_i - mu_i) * w_i ; partials [0] sum r, [1] sum |r|, [2..2+q) Z'r
+__global__ void __launch_bounds__(GLM_THREADS)
+k_score(int64_t n, int64_t q, const double* __restrict__ Z, const double* __restrict__ xb,
+        const double* __restrict__ zc, const double* __restrict__ mu, const double* __restrict__ y,
+        const double* __restrict__ w, int dist, int link, double nb_r, double* __restrict__ r,
+        double* __restrict__ part) {
+    __shared__ double sh[32];
+    const int nv = 2 + (int)q;
+    double a_r = 0.0, a_abs = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double eta = xb[i] + zc[i];
+        double m = mu[i];
+        double ri = glm_mueta(link, eta) / glm_var(dist, m, nb_r) * (y[i] - m) * w[i];
+        r[i] = ri;
+        a_r += ri;
+        a_abs += fabs(ri);
+    }
+    a_r = block_sum(a_r, sh);
+    a_abs = block_sum(a_abs, sh);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x * nv + 0] = a_r;
+        part[blockIdx.x * nv + 1] = a_abs;
+    }
+    // df2 = Z'r (second pass over this block's rows; r was just written by the same threads)
+    for (int64_t l = 0; l < q; ++l) {
+        double a = 0.0;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+            a += Z[i + l * n] * r[i];
+        a = block_sum(a, sh);
+        if (threadIdx.x == 0) part[blockIdx.x * nv + 2 + l] = a;
+    }
+}
+
+// xgk_i = (xs_i + sum_l Z[i,l] d2_l) * sqrt(mueta^2 / glmvar) * w_i ; partial [0] = sum xgk_i^2
+__global__ void __launch_bounds__(GLM_THREADS)
+k_stepsize(int64_t n, int64_t q, const double* __restrict__ Z, const double* __restrict__ d2,
+           const double* __restrict__ xs, const double* __restrict__ xb, const double* __restrict__ zc,
+           const double* __restrict__ mu, const double* __restrict__ w, int dist, int link, double nb_r,
+           double* __restrict__ part) {
+    __shared__ double sh[32];
+    double a = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double zd = 0.0;
+        for (int64_t l = 0; l < q; ++l) zd += Z[i + l * n] * d2[l];
+        double g = glm_mueta(link, xb[i] + zc[i]);
+        double sw = sqrt(g * g / glm_var(dist, mu[i], nb_r)) * w[i];
+        double v = (xs[i] + zd) * sw;
+        a += v * v;
+    }
+    a = block_sum(a, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = a;
+}
+
+// partials [0] sum a_i, [1] sum b_i   (means for pve)
+__global__ void __launch_bounds__(GLM_THREADS)
+k_sum2(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ part) {
+    __shared__ double sh[32];
+    double sa = 0.0, sb = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        sa += a[i]; sb += b[i];
+    }
+    sa = block_sum(sa, sh); sb = block_sum(sb, sh);
+    if (threadIdx.x == 0) { part[blockIdx.x * 2] = sa; part[blockIdx.x * 2 + 1] = sb; }
+}
+// partials [0] sum (a_i - ma)^2, [1] sum (b_i - mb)^2
+__global__ void __launch_bounds__(GLM_THREADS)
+k_ssq2(int64_t n, const double* __restrict__ a, double ma, const double* __restrict__ b, double mb,
+       double* __restrict__ part) {
+    __shared__ double sh[32];
+    double sa = 0.0, sb = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double da = a[i] - ma, db = b[i] - mb;
+        sa += da * da; sb += db * db;
+    }
+    sa = block_sum(sa, sh); sb = block_sum(sb, sh);
+    if (threadIdx.x == 0) { part[blockIdx.x * 2] = sa; part[blockIdx.x * 2 + 1] = sb; }
+}
+
+// w_i = mask_i ? 1 : 0 ; partials [0] sum w, [1] sum y*w
+__global__ void __launch_bounds__(GLM_THREADS)
+k_set_weights(int64_t n, const uint8_t* __restrict__ mask, const double* __restrict__ y, double* __restrict__ w,
+              double* __restrict__ part) {
+    __shared__ double sh[32];
+    double sw = 0.0, sy = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double wi = (mask == nullptr || mask[i]) ? 1.0 : 0.0;
+        w[i] = wi;
+        sw += wi;
+        sy += y[i] * wi;
+    }
+    sw = block_sum(sw, sh); sy = block_sum(sy, sh);
+    if (threadIdx.x == 0) { part[blockIdx.x * 2] = sw; part[blockIdx.x * 2 + 1] = sy; }
+}
+
+// out[v] = sum_b part[b*nv + v], blocks in order (deterministic)
+__global__ void k_finalize(const double* __restrict__ part, int nblocks, int nv, double* __restrict__ out) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    double a = 0.0;
+    for (int b = 0; b < nblocks; ++b) a += part[b * nv + v];
+    out[v] = a;
+}
+
+// ---- launchers ------------------------------------------------------------------------------------
+void glm_mu(GlmCtx& c, const double* d_c, int add_zc, cudaStream_t s) {
+    int grid = glm_grid(c.n);
+    IHTB_LAUNCH(k_glm_mu, grid, GLM_THREADS, 0, s, c.n, c.q, c.Z, d_c, c.xb, c.zc, c.mu, c.y, c.w, c.dist, c.link,
+                c.nb_r, add_zc, c.part);
+    IHTB_LAUNCH(k_finalize, 1, 32, 0, s, c.part, grid, 3, c.scal);
+}
+void glm_score(GlmCtx& c, cudaStream_t s) {
+    int grid = glm_grid(c.n);
+    int nv = 2 + (int)c.q;
+    IHTB_LAUNCH(k_score, grid, GLM_THREADS, 0, s, c.n, c.q, c.Z, c.xb, c.zc, c.mu, c.y, c.w, c.dist, c.link, c.nb_r,
+                c.r, c.part);
+    IHTB_LAUNCH(k_finalize, (unsigned)ceil_div(nv, 32), 32, 0, s, c.part, grid, nv, c.scal);
+}
+void glm_stepsize(GlmCtx& c, const double* d_d2, const double* d_xs, cudaStream_t s) {
+    int grid = glm_grid(c.n);
+    IHTB_LAUNCH(k_stepsize, grid, GLM_THREADS, 0, s, c.n, c.q, c.Z, d_d2, d_xs, c.xb, c.zc, c.mu, c.w, c.dist, c.link,
+                c.nb_r, c.part);
+    IHTB_LAUNCH(k_finalize, 1, 32, 0, s, c.part, grid, 1, c.scal);
+}
+void glm_sum2(GlmCtx& c, const double* a, const double* b, cudaStream_t s) {
+    int grid = glm_grid(c.n);
+    IHTB_LAUNCH(k_sum2, grid, GLM_THREADS, 0, s, c.n, a, b, c.part);
+    IHTB_LAUNCH(k_finalize, 1, 32, 0, s, c.part, grid, 2, c.scal);
+}
+void glm_ssq2(GlmCtx& c, const double* a, double ma, const double* b, double mb, cudaStream_t s) {
+    int grid = glm_grid(c.n);
+    IHTB_LAUNCH(k_ssq2, grid, GLM_THREADS, 0, s, c.n, a, ma, b, mb, c.part);
+    IHTB_LAUNCH(k_finalize, 1, 32, 0, s, c.part, grid, 2, c.scal);
+}
+void glm_set_weights(GlmCtx& c, const uint8_t* d_mask, cudaStream_t s) {
+    int grid = glm_grid(c.n);
+    IHTB_LAUNCH(k_set_weights, grid, GLM_THREADS, 0, s, c.n, d_mask, c.y, c.w, c.part);
+    IHTB_LAUNCH(k_finalize, 1, 32, 0, s, c.part, grid, 2, c.scal);
+}
+
+}  // namespace ihtb

@@ -1,0 +1,176 @@
+// Support-only kernels: x[:, idx] * coef (gather matvec) and exact FP64 column dots x[:, cols]' * V.
+// Replace the getindex loops of the reference: update_xb! (src/utilities.jl:95-111), iht_stepsize!
+// (src/utilities.jl:728-743) and their multivariate forms (src/multivariate.jl:24,234); the column dots
+// re-score top-k candidates exactly (same value mul!(df, Transpose(x), r) gives for those columns).
+#include "common.cuh"
+
+namespace ihtb {
+
+constexpr int XS_CHUNK = 32;  // columns staged per shared-memory table refill
+
+// out[i, t] = sum_c x[i, idx_c] * coef[c, t], ascending c (the order the reference's single-thread loop uses).
+// One thread per packed byte (4 samples). tab[c][code][t] = ((dos(code) - mu) * sinv) * coef[c, t].
+template <int M>
+__global__ void __launch_bounds__(256)
+k_x_support(GenoView gv, const int64_t* __restrict__ idx, int64_t k, const double* __restrict__ coef,
+            double* __restrict__ out) {
+    const int64_t nbytes = gv.nbytes, n = gv.n;
+    const double* __restrict__ mu = gv.mu;
+    const double* __restrict__ sinv = gv.sinv;
+    const int impute = gv.impute;
+    __shared__ double tab[XS_CHUNK][4][M];
+    __shared__ int64_t cols[XS_CHUNK];
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double acc[4][M];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int t = 0; t < M; ++t) acc[s][t] = 0.0;
+
+    for (int64_t c0 = 0; c0 < k; c0 += XS_CHUNK) {
+        int nc = (int)((k - c0 < XS_CHUNK) ? (k - c0) : XS_CHUNK);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nc * 4 * M; e += blockDim.x) {
+            int c = e / (4 * M), code = (e / M) & 3, t = e % M;
+            int64_t j = idx[c0 + c];
+            double m = mu[j];
+            double g = (code == 2) ? 1.0 : (code == 3) ? 2.0 : (code == 1) ? (impute ? m : 0.0) : 0.0;
+            double x = __dmul_rn(__dsub_rn(g, m), sinv[j]);
+            tab[c][code][t] = __dmul_rn(x, coef[(c0 + c) + (int64_t)t * k]);
+            if (code == 0 && t == 0) cols[c] = j;
+        }
+        __syncthreads();
+        if (b < nbytes) {
+            for (int c = 0; c < nc; ++c) {
+                uint32_t byte = *gv_ptr(gv, cols[c], b);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    uint32_t code = (byte >> (2 * s)) & 3u;
+#pragma unroll
+                    for (int t = 0; t < M; ++t) acc[s][t] = __dadd_rn(acc[s][t], tab[c][code][t]);
+                }
+            }
+        }
+    }
+    if (b < nbytes) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            int64_t i = 4 * b + s;
+            if (i < n)
+#pragma unroll
+                for (int t = 0; t < M; ++t) out[i + (int64_t)t * n] = acc[s][t];
+        }
+    }
+}
+
+template <int M>
+static void launch_x_support(const ihtb_geno* g, const int64_t* d_idx, int64_t k, const double* d_coef, double* d_out,
+                             cudaStream_t s) {
+    IHTB_LAUNCH((k_x_support<M>), (unsigned)ceil_div(g->nbytes, 256), 256, 0, s, geno_view(g), d_idx, k, d_coef, d_out);
+}
+
+void x_support(const ihtb_geno* g, const int64_t* d_idx, int64_t k, const double* d_coef, int64_t m, double* d_out,
+               cudaStream_t s) {
+    // m right-hand sides in groups of <= 4 (coef is k x m column-major, out is n x m column-major)
+    for (int64_t t0 = 0; t0 < m;) {
+        int64_t mm = m - t0;
+        const double* cf = d_coef + t0 * k;
+        double* o = d_out + t0 * g->n;
+        if (mm >= 4) { launch_x_support<4>(g, d_idx, k, cf, o, s); t0 += 4; }
+        else if (mm == 3) { launch_x_support<3>(g, d_idx, k, cf, o, s); t0 += 3; }
+        else if (mm == 2) { launch_x_support<2>(g, d_idx, k, cf, o, s); t0 += 2; }
+        else { launch_x_support<1>(g, d_idx, k, cf, o, s); t0 += 1; }
+    }
+}
+
+// Exact column dots. out[c + t*ncols] = sinv_j * (A + mu_j * (impute ? Mm : -vbar_t * nmiss_j)),
+//   A = sum_{obs i} dos_ij (v_it - vbar_t), Mm = sum_{missing i} (v_it - vbar_t), j = cols[c].
+// One CTA per column, one thread per packed byte per step, fixed-tree reduction (deterministic).
+template <int M>
+__global__ void __launch_bounds__(256)
+k_xt_gather(GenoView gv, const int64_t* __restrict__ cols, int64_t ncols, const double* __restrict__ v,
+            const double* __restrict__ vbar, double* __restrict__ out) {
+    __shared__ double sh[32];
+    const int64_t nbytes = gv.nbytes, n = gv.n;
+    const int impute = gv.impute;
+    int64_t c = blockIdx.x;
+    int64_t j = cols[c];
+    double a[M], mm[M], vb[M];
+#pragma unroll
+    for (int t = 0; t < M; ++t) { a[t] = 0.0; mm[t] = 0.0; vb[t] = vbar[t]; }
+    for (int64_t b = threadIdx.x; b < nbytes; b += blockDim.x) {
+        uint32_t byte = *gv_ptr(gv, j, b);
+        if (byte == 0) continue;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            uint32_t code = (byte >> (2 * s)) & 3u;
+            int64_t i = 4 * b + s;
+            if (code != 0 && i < n) {
+#pragma unroll
+                for (int t = 0; t < M; ++t) {
+                    double u = __dsub_rn(v[i + (int64_t)t * n], vb[t]);
+                    if (code == 1) mm[t] = __dadd_rn(mm[t], u);
+                    else a[t] = __dadd_rn(a[t], (code == 3) ? __dadd_rn(u, u) : u);
+                }
+            }
+        }
+    }
+    double m = gv.mu[j], si = gv.sinv[j];
+    double nm = (double)gv.nmiss[j];
+#pragma unroll
+    for (int t = 0; t < M; ++t) {
+        double at = block_sum(a[t], sh);
+        double mt = block_sum(mm[t], sh);
+        if (threadIdx.x == 0) {
+            double corr = impute ? mt : __dmul_rn(-vb[t], nm);
+            out[c + (int64_t)t * ncols] = __dmul_rn(si, __dadd_rn(at, __dmul_rn(m, corr)));
+        }
+    }
+}
+
+template <int M>
+static void launch_xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t ncols, const double* d_v,
+                             const double* d_vbar, double* d_out, cudaStream_t s) {
+    IHTB_LAUNCH((k_xt_gather<M>), (unsigned)ncols, 256, 0, s, geno_view(g), d_cols, ncols, d_v, d_vbar, d_out);
+}
+
+void xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t ncols, const double* d_v, int64_t m,
+               const double* d_vbar, double* d_out, cudaStream_t s) {
+    if (ncols == 0) return;
+    for (int64_t t0 = 0; t0 < m;) {
+        int64_t mm = m - t0;
+        const double* vv = d_v + t0 * g->n;
+        const double* vb = d_vbar + t0;
+        double* o = d_out + t0 * ncols;
+        if (mm >= 4) { launch_xt_gather<4>(g, d_cols, ncols, vv, vb, o, s); t0 += 4; }
+        else if (mm == 3) { launch_xt_gather<3>(g, d_cols, ncols, vv, vb, o, s); t0 += 3; }
+        else if (mm == 2) { launch_xt_gather<2>(g, d_cols, ncols, vv, vb, o, s); t0 += 2; }
+        else { launch_xt_gather<1>(g, d_cols, ncols, vv, vb, o, s); t0 += 1; }
+    }
+}
+
+}  // namespace ihtb
+
+using namespace ihtb;
+
+extern "C" int32_t ihtb_x_support(const ihtb_geno* g, const int64_t* idx, int64_t k, const double* coef, int64_t m,
+                                  double* out) {
+    return guard([&] {
+        IHTB_CHECK(g && out && m >= 1 && k >= 0, IHTB_EINVAL, "bad argument");
+        IHTB_CHECK(k == 0 || (idx && coef), IHTB_EINVAL, "NULL idx/coef");
+        IHTB_CUDA(cudaSetDevice(g->device));
+        for (int64_t c = 0; c < k; ++c)
+            IHTB_CHECK(idx[c] >= 0 && idx[c] < g->p, IHTB_EDIM, "support index out of range");
+        DBuf<double> d_out((size_t)(g->n * m));
+        if (k == 0) {
+            d_out.zero(0);
+        } else {
+            DBuf<int64_t> d_idx((size_t)k);
+            DBuf<double> d_coef((size_t)(k * m));
+            IHTB_CUDA(cudaMemcpy(d_idx.p, idx, k * sizeof(int64_t), cudaMemcpyHostToDevice));
+            IHTB_CUDA(cudaMemcpy(d_coef.p, coef, k * m * sizeof(double), cudaMemcpyHostToDevice));
+            x_support(g, d_idx.p, k, d_coef.p, m, d_out.p, 0);
+        }
+        IHTB_CUDA(cudaMemcpy(out, d_out.p, g->n * m * sizeof(double), cudaMemcpyDeviceToHost));
+    });
+}

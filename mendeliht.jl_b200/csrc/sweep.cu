@@ -1,0 +1,177 @@
+// The dominant kernel: transpose matvec X'v over the 2-bit packed matrix.
+// Replaces mul!(v.df, Transpose(x), v.r) (reference src/utilities.jl:133, executed inside SnpArrays.jl) and the
+// skinny multi-RHS SnpArrays.mul!(v.p_by_r, Transpose(sla), v.n_by_r) (src/multivariate.jl:85).
+//
+// All variants compute, per column j and right-hand side t, with u = v - mean(v):
+//     A_jt = sum_{observed i} dosage_ij * u_it            (dense pass over the packed bytes; code 01 counts 0)
+// and an epilogue adds the sparse mean-imputation term and scales:
+//     out_jt = sinv_j * (A_jt + mu_j * sum_{missing i} u_it)
+// which equals sinv_j * (sum_i gimp_ij v_it - mu_j sum_i v_it) because mean imputation keeps sum_i gimp_ij = n mu_j.
+//
+//  EXACT: FP64 FMA per genotype, slab partials in FP64 (this file, k_sweep_exact).
+//  FAST : FP32 byte-indexed lookup tables in shared memory (sweep_lut.cu).
+#include "common.cuh"
+
+namespace ihtb {
+
+void sweep_fast_partials(const ihtb_geno* g, const double* d_v, double vbar, float* d_part, int64_t* n_slabs,
+                         cudaStream_t s);
+int64_t sweep_fast_num_slabs(const ihtb_geno* g);
+
+constexpr int EX_THREADS = 128;          // one 32-bit word (16 samples) per thread -> 2048 samples per slab
+constexpr int EX_CB = 8;                 // columns per register tile
+constexpr int EX_COLS_PER_CTA = 512;
+
+__global__ void __launch_bounds__(EX_THREADS)
+k_sweep_exact(GenoView gv, const double* __restrict__ v, double vbar, double* __restrict__ part /*[n_slabs][p]*/) {
+    __shared__ double red[EX_THREADS / 32][EX_CB];
+    const int64_t p = gv.p, n = gv.n;
+    const int64_t words = gv.stride >> 2;
+    const int64_t slab = blockIdx.y;
+    const int64_t w = slab * EX_THREADS + threadIdx.x;
+    const bool live = w < words;
+    double u[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        int64_t i = 16 * w + s;
+        u[s] = (live && i < n) ? __dsub_rn(v[i], vbar) : 0.0;
+    }
+    const int64_t jbeg = blockIdx.x * (int64_t)EX_COLS_PER_CTA;
+    const int64_t jend = (jbeg + EX_COLS_PER_CTA < p) ? jbeg + EX_COLS_PER_CTA : p;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t j0 = jbeg; j0 < jend; j0 += EX_CB) {
+        uint32_t wd[EX_CB];
+#pragma unroll
+        for (int c = 0; c < EX_CB; ++c) {
+            int64_t j = j0 + c;
+            wd[c] = (live && j < jend) ? *reinterpret_cast<const uint32_t*>(gv_ptr(gv, j, 4 * w)) : 0u;
+        }
+        double acc[EX_CB];
+#pragma unroll
+        for (int c = 0; c < EX_CB; ++c) {
+            double a = 0.0;
+            uint32_t x = wd[c];
+#pragma unroll
+            for (int s = 0; s < 16; ++s) {
+                uint32_t code = (x >> (2 * s)) & 3u;
+                double dos = (code == 2) ? 1.0 : ((code == 3) ? 2.0 : 0.0);
+                a = fma(u[s], dos, a);
+            }
+            acc[c] = warp_sum(a);
+        }
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < EX_CB; ++c) red[warp][c] = acc[c];
+        }
+        __syncthreads();
+        if (threadIdx.x < EX_CB && j0 + threadIdx.x < jend) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < EX_THREADS / 32; ++q) t += red[q][threadIdx.x];
+            part[slab * p + j0 + threadIdx.x] = t;
+        }
+    }
+}
+
+// out_j = sinv_j * (sum_s part[s][j] + mu_j * (impute ? sum_{i in miss_j} u_i : -vbar * nmiss_j))
+template <typename T>
+__global__ void k_sweep_epilogue(const T* __restrict__ part, int64_t n_slabs, int64_t p,
+                                 const double* __restrict__ mu, const double* __restrict__ sinv,
+                                 const int32_t* __restrict__ nmiss, const int64_t* __restrict__ miss_ptr,
+                                 const int32_t* __restrict__ miss_idx, const double* __restrict__ v, double vbar,
+                                 int impute, double* __restrict__ out) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    double a = 0.0;
+    for (int64_t s = 0; s < n_slabs; ++s) a += (double)part[s * p + j];
+    double corr = 0.0;
+    int nm = nmiss[j];
+    if (nm) {
+        if (impute) {
+            for (int64_t e = miss_ptr[j]; e < miss_ptr[j + 1]; ++e) corr += v[miss_idx[e]] - vbar;
+        } else {
+            corr = -vbar * (double)nm;
+        }
+    }
+    out[j] = sinv[j] * (a + mu[j] * corr);
+}
+
+__global__ void k_vec_sum(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
+    // single block, fixed order: mean of a right-hand side (only used by the stand-alone ihtb_xt_v entry point)
+    __shared__ double sh[32];
+    double a = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) a += v[i];
+    a = block_sum(a, sh);
+    if (threadIdx.x == 0) out[0] = a;
+}
+
+struct SweepScratch {
+    DBuf<double> part64;
+    DBuf<float> part32;
+};
+
+// dV: n x m column-major device array; dOut: p x m. vbar_host[t] = mean of column t (host values).
+void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* vbar_host, int64_t m, double* dOut,
+                           int mode, cudaStream_t s, void* scratch_any, float* sweep_ms) {
+    SweepScratch local;
+    SweepScratch* sc = scratch_any ? reinterpret_cast<SweepScratch*>(scratch_any) : &local;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (sweep_ms) {
+        IHTB_CUDA(cudaEventCreate(&e0)); IHTB_CUDA(cudaEventCreate(&e1));
+        IHTB_CUDA(cudaEventRecord(e0, s));
+    }
+    for (int64_t t = 0; t < m; ++t) {
+        const double* v = dV + t * g->n;
+        double* out = dOut + t * g->p;
+        if (mode == IHTB_SWEEP_EXACT) {
+            int64_t words = g->stride >> 2;
+            int64_t n_slabs = ceil_div(words, EX_THREADS);
+            if (sc->part64.n < (size_t)(n_slabs * g->p)) sc->part64.alloc((size_t)(n_slabs * g->p));
+            dim3 grid((unsigned)ceil_div(g->p, EX_COLS_PER_CTA), (unsigned)n_slabs);
+            IHTB_LAUNCH(k_sweep_exact, grid, EX_THREADS, 0, s, geno_view(g), v, vbar_host[t], sc->part64.p);
+            IHTB_LAUNCH((k_sweep_epilogue<double>), (unsigned)ceil_div(g->p, 256), 256, 0, s, sc->part64.p, n_slabs,
+                        g->p, g->mu.p, g->sinv.p, g->nmiss.p, g->miss_ptr.p, g->miss_idx.p, v, vbar_host[t],
+                        g->impute, out);
+        } else {
+            int64_t n_slabs = sweep_fast_num_slabs(g);
+            if (sc->part32.n < (size_t)(n_slabs * g->p)) sc->part32.alloc((size_t)(n_slabs * g->p));
+            sweep_fast_partials(g, v, vbar_host[t], sc->part32.p, &n_slabs, s);
+            IHTB_LAUNCH((k_sweep_epilogue<float>), (unsigned)ceil_div(g->p, 256), 256, 0, s, sc->part32.p, n_slabs,
+                        g->p, g->mu.p, g->sinv.p, g->nmiss.p, g->miss_ptr.p, g->miss_idx.p, v, vbar_host[t],
+                        g->impute, out);
+        }
+    }
+    if (sweep_ms) {
+        IHTB_CUDA(cudaEventRecord(e1, s));
+        IHTB_CUDA(cudaEventSynchronize(e1));
+        IHTB_CUDA(cudaEventElapsedTime(sweep_ms, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+}
+
+void* sweep_scratch_create() { return new SweepScratch(); }
+void sweep_scratch_destroy(void* p) { delete reinterpret_cast<SweepScratch*>(p); }
+
+}  // namespace ihtb
+
+using namespace ihtb;
+
+extern "C" int32_t ihtb_xt_v(const ihtb_geno* g, const double* V, int64_t m, double* out, int32_t sweep_mode) {
+    return guard([&] {
+        IHTB_CHECK(g && V && out && m >= 1, IHTB_EINVAL, "bad argument");
+        IHTB_CHECK(sweep_mode == IHTB_SWEEP_FAST || sweep_mode == IHTB_SWEEP_EXACT, IHTB_EINVAL, "bad sweep_mode");
+        IHTB_CUDA(cudaSetDevice(g->device));
+        DBuf<double> dV((size_t)(g->n * m)), dOut((size_t)(g->p * m)), dsum(1);
+        IHTB_CUDA(cudaMemcpy(dV.p, V, g->n * m * sizeof(double), cudaMemcpyHostToDevice));
+        std::vector<double> vbar((size_t)m);
+        for (int64_t t = 0; t < m; ++t) {
+            IHTB_LAUNCH(k_vec_sum, 1, 1024, 0, 0, dV.p + t * g->n, g->n, dsum.p);
+            double sum = 0.0;
+            IHTB_CUDA(cudaMemcpy(&sum, dsum.p, sizeof(double), cudaMemcpyDeviceToHost));
+            vbar[t] = sum / (double)g->n;
+        }
+        sweep_xt_v_with_means(g, dV.p, vbar.data(), m, dOut.p, sweep_mode, 0, nullptr, nullptr);
+        IHTB_CUDA(cudaMemcpy(out, dOut.p, g->p * m * sizeof(double), cudaMemcpyDeviceToHost));
+    });
+}

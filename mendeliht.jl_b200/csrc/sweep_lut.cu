@@ -1,0 +1,256 @@
+// FAST X'v sweep for sm_100a: byte-indexed lookup tables ("four Russians") in shared memory.
+//
+// Why: at 6.5 TB/s a B200 SM must consume ~100 genotypes per clock; a decode + FMA per genotype is ALU-bound at
+// less than half of that.  Here every packed byte (4 genotypes) costs one PRMT (address),
+// one conflict-free LDS.32 (table lookup) and one FADD.
+//
+// Work decomposition: the matrix is cut into slabs of 512 samples (= one 128-byte chunk per column).  A CTA owns a
+// contiguous range of (slab, 128-column block) units.  For its current slab it builds, from u = v - mean(v) (FP32),
+//     T[t][value][w] = sum_{s<4} dosage((value >> 2s) & 3) * u[512*slab + 16*w + 4*t + s]
+// for the 32 words w of a chunk and the 4 bytes t of a word: 4*256*32 floats = 128 KB.  Lane w of a consumer warp
+// owns word w of a column chunk, so the 32 lookups of one LDS hit 32 distinct banks whatever the data bytes are.
+// The 256 rows (value) of a table are 256 bytes apart and each pair of tables fills one 64 KB-aligned window of
+// shared memory, so the lookup address is a single PRMT: byte 1 of a per-lane base register is replaced by the
+// data byte.
+//
+// Data movement: a producer warp streams column chunks into a ring of 16 KB shared-memory stages with
+// cp.async.bulk (TMA bulk copy, SASS UBLKCP) completing on mbarriers; 8 consumer warps each reduce 16 columns per
+// stage with a butterfly so that lanes 0..15 end up holding one column sum each.  Slab partial sums are written as
+// FP32 [slab][column]; the epilogue (sweep.cu) adds them in FP64 in slab order.  Everything is deterministic.
+#include "common.cuh"
+
+namespace ihtb {
+
+constexpr int LUT_CONSUMER_WARPS = 8;
+constexpr int LUT_THREADS = (LUT_CONSUMER_WARPS + 1) * 32;
+constexpr int LUT_STAGE_COLS = 128;
+constexpr int LUT_STAGE_BYTES = LUT_STAGE_COLS * 128;
+constexpr int LUT_COLS_PER_WARP = LUT_STAGE_COLS / LUT_CONSUMER_WARPS;   // 16
+constexpr int LUT_MAX_STAGES = 6;
+constexpr int LUT_TABLE_BYTES = 131072;
+constexpr int LUT_SMEM_BYTES = 232448;   // 227 KB: everything the SM has
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W_%=;\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void consumer_bar() {   // named barrier 1 over the 256 consumer threads
+    asm volatile("bar.sync 1, %0;" ::"n"(LUT_CONSUMER_WARPS * 32) : "memory");
+}
+
+// shared-memory plan (computed identically by every thread)
+struct LutPlan {
+    uint32_t bar_full, bar_empty;      // arrays of 8-byte mbarriers
+    uint32_t tab;                      // 64 KB-aligned, 128 KB
+    uint32_t lo0, hi0;                 // first stage below / above the tables
+    int n_lo, n_stages;
+    __device__ __forceinline__ uint32_t stage(int s) const {
+        return (s < n_lo) ? lo0 + (uint32_t)s * LUT_STAGE_BYTES : hi0 + (uint32_t)(s - n_lo) * LUT_STAGE_BYTES;
+    }
+};
+__device__ __forceinline__ LutPlan lut_plan(uint32_t base, uint32_t bytes) {
+    LutPlan pl;
+    uint32_t end = base + bytes;
+    pl.tab = (base + 65535u) & ~65535u;
+    pl.bar_full = 0; pl.bar_empty = 0; pl.n_stages = 0;
+    uint32_t lo = (base + 127u) & ~127u, lo_end = pl.tab;
+    uint32_t hi = pl.tab + LUT_TABLE_BYTES, hi_end = end;
+    // barriers: 128 bytes at the first free spot
+    if (lo + 128u <= lo_end) { pl.bar_full = lo; lo += 128u; }
+    else { pl.bar_full = hi; hi += 128u; }
+    pl.bar_empty = pl.bar_full + 64u;
+    pl.lo0 = lo; pl.hi0 = hi;
+    pl.n_lo = (lo_end > lo) ? (int)((lo_end - lo) / LUT_STAGE_BYTES) : 0;
+    if (pl.n_lo > LUT_MAX_STAGES) pl.n_lo = LUT_MAX_STAGES;
+    int n_hi = (hi_end > hi) ? (int)((hi_end - hi) / LUT_STAGE_BYTES) : 0;
+    pl.n_stages = pl.n_lo + n_hi;
+    if (pl.n_stages > LUT_MAX_STAGES) pl.n_stages = LUT_MAX_STAGES;
+    return pl;
+}
+
+// build T for one slab; executed by the 256 consumer threads
+__device__ __forceinline__ void lut_build(uint32_t tab, const double* __restrict__ v, double vbar, int64_t n,
+                                          int64_t slab, int tid) {
+    // thread -> (half, group): group = t*32 + w (128 groups), half selects values [0,128) or [128,256)
+    const int group = tid & 127, half = tid >> 7;
+    const int t = group >> 5, w = group & 31;
+    float f[4][4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        int64_t i = slab * 512 + 16 * w + 4 * t + s;
+        float u = (i < n) ? __double2float_rn(__dsub_rn(v[i], vbar)) : 0.0f;
+        f[s][0] = 0.0f; f[s][1] = 0.0f; f[s][2] = u; f[s][3] = u + u;   // codes 00, 01 (missing -> 0), 10, 11
+    }
+    // address of row `value`: window(t>>1) + value*256 + (t&1)*128 + 4*w
+    const uint32_t rowbase = tab + (uint32_t)(t >> 1) * 65536u + (uint32_t)(t & 1) * 128u + 4u * (uint32_t)w;
+#pragma unroll
+    for (int c3 = 0; c3 < 2; ++c3) {
+        const int v3 = 2 * half + c3;
+        const float a3 = half ? f[3][2 + c3] : 0.0f;   // values 0,1 of the top sample add nothing
+#pragma unroll
+        for (int v2 = 0; v2 < 4; ++v2) {
+            const float a2 = a3 + f[2][v2];
+#pragma unroll
+            for (int v1 = 0; v1 < 4; ++v1) {
+                const float a1 = a2 + f[1][v1];
+#pragma unroll
+                for (int v0 = 0; v0 < 4; ++v0) {
+                    const uint32_t value = (uint32_t)(v3 << 6 | v2 << 4 | v1 << 2 | v0);
+                    sts_f32(rowbase + value * 256u, a1 + f[0][v0]);
+                }
+            }
+        }
+    }
+}
+
+// Units: u = slab * n_cblocks + cblock, CTA b handles [u_begin(b), u_begin(b+1)).
+__global__ void __launch_bounds__(LUT_THREADS, 1)
+k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t p, int64_t n, int64_t n_slabs,
+            const double* __restrict__ v, double vbar, float* __restrict__ part, uint32_t dyn_bytes) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const LutPlan pl = lut_plan(smem_u32(smem_raw), dyn_bytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = pl.n_stages;
+
+    const int64_t n_cblocks = (p + LUT_STAGE_COLS - 1) / LUT_STAGE_COLS;
+    const int64_t units = n_slabs * n_cblocks;
+    const int64_t u_beg = units * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t u_end = units * (int64_t)(blockIdx.x + 1) / gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(pl.bar_full + 8u * s, 1);
+            mbar_init(pl.bar_empty + 8u * s, LUT_CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == LUT_CONSUMER_WARPS) {
+        // ===== producer warp: stream column chunks with bulk async copies =====
+        int st = 0; uint32_t ph = 0;
+        for (int64_t u = u_beg; u < u_end; ++u) {
+            const int64_t slab = u / n_cblocks, cb = u % n_cblocks;
+            const int64_t j0 = cb * LUT_STAGE_COLS;
+            const int ncols = (int)((p - j0 < LUT_STAGE_COLS) ? (p - j0) : LUT_STAGE_COLS);
+            mbar_wait(pl.bar_empty + 8u * st, ph ^ 1u);
+            const uint8_t* src = bed + j0 * cs_j + slab * cs_s;
+            if (cs_j == 128) {               // slab-major tiled layout: one contiguous copy
+                if (lane == 0) {
+                    mbar_expect_tx(pl.bar_full + 8u * st, (uint32_t)ncols * 128u);
+                    bulk_g2s(pl.stage(st), src, (uint32_t)ncols * 128u, pl.bar_full + 8u * st);
+                }
+            } else {                          // column-major layout: one 128-byte copy per column
+                if (lane == 0) mbar_expect_tx(pl.bar_full + 8u * st, (uint32_t)ncols * 128u);
+                __syncwarp();
+                for (int c = lane; c < ncols; c += 32)
+                    bulk_g2s(pl.stage(st) + 128u * c, src + (int64_t)c * cs_j, 128u, pl.bar_full + 8u * st);
+            }
+            if (++st == S) { st = 0; ph ^= 1u; }
+        }
+    } else {
+        // ===== consumer warps =====
+        const int tid = threadIdx.x;      // 0..255
+        // per-lane base registers for the 4 bytes of a word: byte 1 gets replaced by the data byte
+        uint32_t lb[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            lb[t] = pl.tab + (uint32_t)(t >> 1) * 65536u + (uint32_t)(t & 1) * 128u + 4u * (uint32_t)lane;
+        int st = 0; uint32_t ph = 0;
+        int64_t cur_slab = -1;
+        for (int64_t u = u_beg; u < u_end; ++u) {
+            const int64_t slab = u / n_cblocks, cb = u % n_cblocks;
+            if (slab != cur_slab) {
+                consumer_bar();               // everyone finished looking up the previous slab's tables
+                lut_build(pl.tab, v, vbar, n, slab, tid);
+                consumer_bar();
+                cur_slab = slab;
+            }
+            mbar_wait(pl.bar_full + 8u * st, ph);
+            const uint32_t colbase = pl.stage(st) + (uint32_t)(warp * LUT_COLS_PER_WARP) * 128u + 4u * (uint32_t)lane;
+            float acc[LUT_COLS_PER_WARP];
+#pragma unroll
+            for (int c = 0; c < LUT_COLS_PER_WARP; ++c) {
+                const uint32_t w = lds_u32(colbase + 128u * c);
+                const float t0 = lds_f32(__byte_perm(w, lb[0], 0x7604));
+                const float t1 = lds_f32(__byte_perm(w, lb[1], 0x7614));
+                const float t2 = lds_f32(__byte_perm(w, lb[2], 0x7624));
+                const float t3 = lds_f32(__byte_perm(w, lb[3], 0x7634));
+                acc[c] = (t0 + t1) + (t2 + t3);
+            }
+            // the stage's bytes are now in registers: hand the slot back to the producer
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pl.bar_empty + 8u * st);
+            // butterfly: 16 column sums per lane -> one per lane (lanes l and l^16 hold the same column)
+#pragma unroll
+            for (int h = 8, o = 16; h >= 1; h >>= 1, o >>= 1) {
+                const bool upper = (lane & o) != 0;
+#pragma unroll
+                for (int c = 0; c < h; ++c) {
+                    const float send = upper ? acc[c] : acc[c + h];
+                    const float keep = upper ? acc[c + h] : acc[c];
+                    acc[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+            // after the 4 halving steps lane bits (16,8,4,2) select the column: col = bit16*8 + bit8*4 + bit4*2 + bit2
+            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            const int64_t j = cb * LUT_STAGE_COLS + warp * LUT_COLS_PER_WARP + col;
+            if ((lane & 1) == 0 && j < p) part[slab * p + j] = acc[0];
+            if (++st == S) { st = 0; ph ^= 1u; }
+        }
+    }
+}
+
+int64_t sweep_fast_num_slabs(const ihtb_geno* g) { return g->stride / 128; }
+
+void sweep_fast_partials(const ihtb_geno* g, const double* d_v, double vbar, float* d_part, int64_t* n_slabs_out,
+                         cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        IHTB_CUDA(cudaFuncSetAttribute(k_sweep_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES));
+        configured = true;
+    }
+    const int64_t n_slabs = sweep_fast_num_slabs(g);
+    *n_slabs_out = n_slabs;
+    const int64_t n_cblocks = ceil_div(g->p, LUT_STAGE_COLS);
+    int64_t units = n_slabs * n_cblocks;
+    int grid = g->sm_count;
+    if (units < grid) grid = (int)units;
+    IHTB_LAUNCH(k_sweep_lut, grid, LUT_THREADS, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n, n_slabs, d_v,
+                vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
+}
+
+}  // namespace ihtb

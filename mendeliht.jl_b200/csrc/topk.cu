@@ -1,0 +1,156 @@
+// Top-k projection support: candidate selection for project_k! (reference src/utilities.jl:553-559) over
+// v_j = b0_j + eta * df_j, j = 1..p, with an error bound on df.
+//
+// The sweep's df_j may carry an absolute error of at most e_j = eta * sinv_j * bound (FAST mode: FP32 partial sums).
+// With L_j = |v_j| - e_j and U_j = |v_j| + e_j, let tau be the k-th largest L.  The true k-th largest |v| is >= tau,
+// so every member of the true top-k has U_j >= tau.  This file finds tau with a 3-pass radix select on the
+// order-preserving uint32 image of L (rounded down to FP32), then compacts {j : U_j >= tau} (U rounded up).  The fit
+// re-scores those few columns exactly in FP64 and takes the top-k of the exact values, ties broken by lowest index,
+// so the selected support does not depend on the sweep arithmetic.  Only integer atomics: deterministic.
+#include "topk.cuh"
+
+namespace ihtb {
+
+constexpr int TK_THREADS = 256;
+constexpr int TK_BINS = 2048;
+
+static inline int tk_grid(int64_t p) {
+    int64_t b = ceil_div(p, TK_THREADS * 4);
+    return (int)(b < 1 ? 1 : (b > 592 ? 592 : b));
+}
+
+__device__ __forceinline__ void hist_flush(const int* sh, int* g, int nb) {
+    for (int b = threadIdx.x; b < nb; b += blockDim.x)
+        if (sh[b]) atomicAdd(&g[b], sh[b]);
+}
+
+// pass 0: keys + histogram of the top 11 bits of keyL
+__global__ void __launch_bounds__(TK_THREADS)
+k_keys_hist0(int64_t p, const double* __restrict__ dfa, const double* __restrict__ b0d,
+             const double* __restrict__ sinv, double eta, double bound, uint32_t* __restrict__ keyL,
+             uint32_t* __restrict__ keyU, int* __restrict__ hist) {
+    __shared__ int sh[TK_BINS];
+    for (int b = threadIdx.x; b < TK_BINS; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p; j += (int64_t)gridDim.x * blockDim.x) {
+        double v = b0d[j] + eta * dfa[j];
+        double a = fabs(v);
+        double e = fabs(eta) * sinv[j] * bound + a * 4e-16;
+        double lo = a - e, up = a + e;
+        if (!(lo > 0.0)) lo = 0.0;          // also maps NaN to 0
+        if (!(up >= 0.0)) up = INFINITY;    // NaN: always a candidate
+        uint32_t kl = __float_as_uint(__double2float_rd(lo));
+        uint32_t ku = __float_as_uint(__double2float_ru(up));
+        keyL[j] = kl; keyU[j] = ku;
+        atomicAdd(&sh[kl >> 21], 1);
+    }
+    __syncthreads();
+    hist_flush(sh, hist, TK_BINS);
+}
+
+// later passes: histogram of `bits` bits at `shift` among keys whose higher bits equal st->prefix
+__global__ void __launch_bounds__(TK_THREADS)
+k_hist(int64_t p, const uint32_t* __restrict__ keyL, const TopkState* __restrict__ st, int shift, int bits,
+       int* __restrict__ hist) {
+    __shared__ int sh[TK_BINS];
+    const int nb = 1 << bits;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    const uint32_t prefix = st->prefix;
+    const uint32_t himask = ~((1u << (shift + bits)) - 1u);   // bits above this digit
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p; j += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t k = keyL[j];
+        if ((k & himask) == (prefix & himask)) atomicAdd(&sh[(k >> shift) & (nb - 1)], 1);
+    }
+    __syncthreads();
+    hist_flush(sh, hist, nb);
+}
+
+// one block of 1024 threads: find the digit whose suffix count crosses k_rem, then clear the histogram
+__global__ void __launch_bounds__(1024)
+k_pick(int* __restrict__ hist, TopkState* __restrict__ st, int shift, int bits) {
+    __shared__ int warp_tot[32];
+    const int nb = 1 << bits;
+    const int t = threadIdx.x;
+    // reversed order: position r <-> bin nb-1-r, two positions per thread
+    const int r0 = 2 * t, r1 = 2 * t + 1;
+    const int c0 = (r0 < nb) ? hist[nb - 1 - r0] : 0;
+    const int c1 = (r1 < nb) ? hist[nb - 1 - r1] : 0;
+    int s = c0 + c1;
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((t & 31) >= o) incl += v;
+    }
+    if ((t & 31) == 31) warp_tot[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+        int v = warp_tot[t];
+        int sc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, sc, o);
+            if (t >= o) sc += u;
+        }
+        warp_tot[t] = sc - v;   // exclusive prefix of warp totals
+    }
+    __syncthreads();
+    incl += warp_tot[t >> 5];
+    const int excl = incl - s;
+    const int k = st->k_rem;
+    __syncthreads();
+    if (excl < k && k <= incl) {
+        int bin, krem;
+        if (excl + c0 >= k) { bin = nb - 1 - r0; krem = k - excl; }
+        else { bin = nb - 1 - r1; krem = k - excl - c0; }
+        st->prefix |= (uint32_t)bin << shift;
+        st->k_rem = krem;
+    }
+    for (int b = t; b < TK_BINS; b += blockDim.x) hist[b] = 0;
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+k_compact(int64_t p, const uint32_t* __restrict__ keyU, TopkState* __restrict__ st, int64_t* __restrict__ cand,
+          int cap) {
+    const uint32_t tau = st->prefix;
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p; j += (int64_t)gridDim.x * blockDim.x) {
+        if (keyU[j] >= tau) {
+            int pos = atomicAdd(&st->count, 1);
+            if (pos < cap) cand[pos] = j;
+        }
+    }
+}
+
+__global__ void k_topk_reset(TopkState* st, int k) {
+    st->prefix = 0; st->k_rem = k; st->count = 0; st->pad = 0;
+}
+
+// dense b0 maintenance: zero old support entries, write new ones
+__global__ void k_scatter(double* __restrict__ dst, const int64_t* __restrict__ idx, const double* __restrict__ val,
+                          int64_t k, int zero_only) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < k) dst[idx[t]] = zero_only ? 0.0 : val[t];
+}
+
+void topk_candidates(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, double eta,
+                     double bound, int64_t k, cudaStream_t s) {
+    int grid = tk_grid(c.p);
+    int kk = (int)(k < c.p ? k : c.p);
+    IHTB_LAUNCH(k_topk_reset, 1, 1, 0, s, c.st, kk);
+    IHTB_LAUNCH(k_keys_hist0, grid, TK_THREADS, 0, s, c.p, d_dfa, d_b0d, d_sinv, eta, bound, c.keyL, c.keyU, c.hist);
+    IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 21, 11);
+    IHTB_LAUNCH(k_hist, grid, TK_THREADS, 0, s, c.p, c.keyL, c.st, 10, 11, c.hist);
+    IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 10, 11);
+    IHTB_LAUNCH(k_hist, grid, TK_THREADS, 0, s, c.p, c.keyL, c.st, 0, 10, c.hist);
+    IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 0, 10);
+    IHTB_LAUNCH(k_compact, grid, TK_THREADS, 0, s, c.p, c.keyU, c.st, c.cand, c.cap);
+}
+
+void scatter_dense(double* d_dst, const int64_t* d_idx, const double* d_val, int64_t k, int zero_only,
+                   cudaStream_t s) {
+    if (k == 0) return;
+    IHTB_LAUNCH(k_scatter, (unsigned)ceil_div(k, 128), 128, 0, s, d_dst, d_idx, d_val, k, zero_only);
+}
+
+}  // namespace ihtb

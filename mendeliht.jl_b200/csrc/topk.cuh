@@ -1,0 +1,27 @@
+#pragma once
+#include "common.cuh"
+
+namespace ihtb {
+
+struct TopkState {
+    uint32_t prefix;   // after the 3 passes: tau = k-th largest lower-bound key
+    int32_t k_rem;
+    int32_t count;     // candidates found (may exceed cap)
+    int32_t pad;
+};
+
+struct TopkCtx {
+    int64_t p;
+    uint32_t* keyL;
+    uint32_t* keyU;
+    int* hist;         // 2048 ints, zero on entry
+    TopkState* st;
+    int64_t* cand;
+    int cap;
+};
+
+void topk_candidates(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, double eta,
+                     double bound, int64_t k, cudaStream_t s);
+void scatter_dense(double* d_dst, const int64_t* d_idx, const double* d_val, int64_t k, int zero_only, cudaStream_t s);
+
+}  // namespace ihtb

@@ -1,0 +1,151 @@
+"""GPU parity of the IHT loop against the CPU oracle and the reference's published trace, through the C ABI.
+
+Bar (BASELINE.json north_star): support indices and iteration counts identical; beta, loglikelihood and CV MSEs
+within 1e-6 relative (the fit re-scores every top-k candidate in FP64, so this holds for both sweep modes)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import mendeliht_jl_b200 as m
+from mendeliht_jl_b200 import synth
+from oracle import cv as ocv
+from oracle import glm, iht, snp
+from conftest import GOLDEN
+
+RTOL = 1e-6
+MODES = [m.SWEEP_FAST, m.SWEEP_EXACT]
+
+
+def _compare(res, ref, rtol=RTOL):
+    assert res.iter == ref.iter
+    assert np.array_equal(np.flatnonzero(res.beta), np.flatnonzero(ref.beta))      # support: exact
+    np.testing.assert_allclose(res.beta, ref.beta, rtol=rtol, atol=1e-12)
+    np.testing.assert_allclose(res.c, ref.c, rtol=rtol, atol=1e-12)
+    assert abs(res.logl - ref.logl) <= rtol * abs(ref.logl)
+    assert abs(res.sigma_g - ref.sigma_g) <= rtol * abs(ref.sigma_g) + 1e-12
+    assert [t[1] for t in res.trace] == ref.trace.backtracks
+    np.testing.assert_allclose([t[0] for t in res.trace], ref.trace.logl, rtol=rtol)
+    np.testing.assert_allclose([t[2] for t in res.trace], ref.trace.tol, rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_docs_trace_normal_k7(normal_data, mode):
+    """docs/src/man/examples.md:230-268 straight against the CUDA path."""
+    gold = json.load(open(os.path.join(GOLDEN, "docs_trace_normal_k7.json")))
+    g = m.B200SnpLinAlg.from_bed_columns(normal_data["bed"], normal_data["n"])
+    res = m.fit_iht(normal_data["y"], g, normal_data["z"], k=7, d="Normal", l="IdentityLink", sweep_mode=mode)
+    assert res.iter == gold["iter"]
+    np.testing.assert_allclose([t[0] for t in res.trace], gold["logl"], rtol=1e-9)
+    np.testing.assert_allclose([t[2] for t in res.trace], gold["tol"], rtol=1e-6)
+    assert [t[1] for t in res.trace] == gold["backtracks"]
+    assert list(np.flatnonzero(res.beta) + 1) == gold["support_1based"]
+    np.testing.assert_allclose(res.beta[np.flatnonzero(res.beta)], gold["beta_6sig"], rtol=2e-6)
+    np.testing.assert_allclose(res.c, gold["c_6sig"], rtol=2e-6)
+    assert abs(res.sigma_g - gold["pve"]) < 1e-9
+    assert abs(res.logl - gold["final_logl"]) < 1e-7
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_config1_readme_call(normal_data, normal_oracle, mode):
+    """BASELINE config 1: iht(datadir/normal, 9, Normal) (README.md:104) vs the oracle."""
+    g = m.B200SnpLinAlg.from_bed_columns(normal_data["bed"], normal_data["n"])
+    res = m.fit_iht(normal_data["y"], g, None, k=9, sweep_mode=mode)
+    ref = iht.fit_iht(normal_data["y"], normal_oracle, None, k=9)
+    _compare(res, ref)
+    assert res.iter == 10 and list(np.flatnonzero(res.beta) + 1) == [1266, 3137, 4246, 4717, 6290, 7629, 7755, 8375, 9415]
+
+
+CASES = [
+    ("Normal", "IdentityLink", 1200, 3000, 8, 2, 0.0),
+    ("Bernoulli", "LogitLink", 1500, 3000, 6, 0, 0.0),
+    ("Poisson", "LogLink", 1500, 2500, 6, 1, 0.0),
+    ("NegativeBinomial", "LogLink", 1500, 2500, 6, 0, 0.0),
+    ("Normal", "IdentityLink", 1003, 2001, 5, 1, 0.01),      # ragged n, missing genotypes
+    ("Bernoulli", "LogitLink", 1111, 1500, 4, 2, 0.005),
+]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("d,l,n,p,k,ncov,miss", CASES)
+def test_fit_matches_oracle(d, l, n, p, k, ncov, miss, mode):
+    seed = 100 + n + p
+    y, z, _, _, _ = synth.simulate_response(seed, n, p, k, d, n_cov=ncov, missing_rate=miss)
+    bed = synth.packed_columns(seed, n, np.arange(p), miss)
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    o = snp.SnpLinAlgOracle(bed, n)
+    res = m.fit_iht(y, g, z, k=k + 2, d=d, l=l, nb_r=10.0, sweep_mode=mode)
+    ref = iht.fit_iht(y, o, z, k=k + 2, d=d, l=l, nb_r=10.0)
+    _compare(res, ref)
+
+
+def test_zkeep_lets_covariates_compete():
+    n, p, k = 1200, 2000, 5
+    y, z, _, _, _ = synth.simulate_response(7, n, p, k, "Normal", n_cov=3)
+    bed = synth.packed_columns(7, n, np.arange(p))
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    o = snp.SnpLinAlgOracle(bed, n)
+    zkeep = np.array([True, False, True, False])
+    res = m.fit_iht(y, g, z, k=6, zkeep=zkeep)
+    ref = iht.fit_iht(y, o, z, k=6, zkeep=zkeep)
+    _compare(res, ref)
+    assert np.count_nonzero(res.beta) + np.count_nonzero(res.c[~zkeep]) <= 6
+
+
+def test_max_iter_exit_and_min_iter():
+    n, p = 1000, 1500
+    y, z, _, _, _ = synth.simulate_response(3, n, p, 5, "Normal")
+    bed = synth.packed_columns(3, n, np.arange(p))
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    o = snp.SnpLinAlgOracle(bed, n)
+    for kw in ({"max_iter": 3}, {"max_iter": 1}, {"min_iter": 8}, {"tol": 1e-2}, {"max_step": 0}):
+        res = m.fit_iht(y, g, z, k=5, **kw)
+        ref = iht.fit_iht(y, o, z, k=5, **kw)
+        _compare(res, ref)
+
+
+def test_cv_matches_oracle():
+    n, p = 1000, 2000
+    y, z, _, _, _ = synth.simulate_response(21, n, p, 4, "Poisson", n_cov=1)
+    bed = synth.packed_columns(21, n, np.arange(p))
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    o = snp.SnpLinAlgOracle(bed, n)
+    folds = synth.folds_for(21, n, 3)
+    path = [1, 3, 5, 8]
+    mses, iters = m.cv_iht(y, g, z, d="Poisson", l="LogLink", path=path, q=3, folds=folds, return_grid=True)
+    rmse, rgrid, riters = ocv.cv_iht(y, o, z, d=glm.POISSON, l=glm.LOG, path=path, q=3, folds=folds, return_grid=True)
+    assert np.array_equal(iters, riters)
+    np.testing.assert_allclose(mses, rgrid, rtol=RTOL)
+    np.testing.assert_allclose(m.meanloss(mses, 3, folds), rmse, rtol=RTOL)
+    assert np.all(mses > 0)
+
+
+def test_properties_at_scale():
+    """Size-independent checks at a size the oracle cannot hold: exactly k non-zeros, intercept estimated,
+    FAST and EXACT sweeps give the same support / iterations and the same beta to 1e-9."""
+    n, p, k = 20000, 60000, 10
+    g = m.B200SnpLinAlg.synthetic(n, p, 77)
+    y, z, idx, beta, c = synth.simulate_response(78, n, p, k, "Bernoulli", geno_seed=77)
+    a = m.fit_iht(y, g, z, k=k, d="Bernoulli", l="LogitLink", sweep_mode=m.SWEEP_FAST)
+    b = m.fit_iht(y, g, z, k=k, d="Bernoulli", l="LogitLink", sweep_mode=m.SWEEP_EXACT)
+    assert np.count_nonzero(a.beta) == k and a.c[0] != 0
+    assert a.iter == b.iter and np.array_equal(np.flatnonzero(a.beta), np.flatnonzero(b.beta))
+    np.testing.assert_allclose(a.beta, b.beta, rtol=1e-9, atol=1e-12)
+    assert abs(a.logl - b.logl) < 1e-9 * abs(b.logl)
+    strong = idx[np.abs(beta) > 0.25]
+    assert set(strong) <= set(np.flatnonzero(a.beta))
+
+
+def test_dimension_errors():
+    g = m.B200SnpLinAlg.synthetic(100, 50, 1)
+    with pytest.raises(m.DimensionMismatch):
+        m.fit_iht(np.zeros(99), g, None, k=3)
+    with pytest.raises(m.DimensionMismatch):
+        m.fit_iht(np.zeros(100), g, np.ones((100, 2)), k=3, zkeep=np.array([True]))
+    with pytest.raises(AssertionError):
+        m.fit_iht(np.zeros(100), g, None, k=-1)
+    with pytest.raises(ValueError):
+        m.cv_iht(np.zeros(100), g, None, path=[60], folds=np.ones(100, int))

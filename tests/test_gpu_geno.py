@@ -1,0 +1,108 @@
+"""GPU parity of the genotype operator (SnpLinAlg replacement) against the CPU oracle, through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import mendeliht_jl_b200 as m
+from mendeliht_jl_b200 import synth
+from oracle import snp
+
+LAYOUTS = ["tiled", "colmajor"]
+
+
+def _make(bed, n, layout):
+    os.environ["IHTB_LAYOUT"] = layout
+    try:
+        return m.B200SnpLinAlg.from_bed_columns(bed, n)
+    finally:
+        os.environ.pop("IHTB_LAYOUT", None)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("n,p,miss", [(1000, 257, 0.0), (1003, 300, 0.02), (515, 64, 0.3), (7, 5, 0.0), (2049, 130, 0.001)])
+def test_stats_decode_packed_bit_exact(layout, n, p, miss):
+    bed = synth.packed_columns(11, n, np.arange(p), miss)
+    g = _make(bed, n, layout)
+    o = snp.SnpLinAlgOracle(bed, n)
+    mu, sinv, nm = g.stats()
+    assert np.array_equal(nm, o.nmiss)
+    assert np.array_equal(mu, o.mu)                 # integer counts, one IEEE division: bit-exact
+    assert np.array_equal(sinv, o.sigma_inv)
+    assert np.array_equal(g.decode(), o.dense())    # decoded genotypes bit-exact
+    assert np.array_equal(g.decode(3, min(n, 40), 1, min(p, 9)), o.dense()[3:min(n, 40), 1:min(p, 9)])
+    assert np.array_equal(g.packed(), bed)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_device_generator_matches_numpy_twin(layout):
+    os.environ["IHTB_LAYOUT"] = layout
+    try:
+        for n, p, miss, j0 in [(1003, 200, 0.0, 0), (2500, 150, 0.01, 1000)]:
+            g = m.B200SnpLinAlg.synthetic(n, p, 2024, miss, j0)
+            assert np.array_equal(g.packed(), synth.packed_columns(2024, n, np.arange(j0, j0 + p), miss))
+    finally:
+        os.environ.pop("IHTB_LAYOUT", None)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("n,p,miss", [(1000, 300, 0.0), (1003, 513, 0.01), (4099, 260, 0.0), (600, 129, 0.2)])
+def test_xt_v_exact_and_fast(layout, n, p, miss):
+    bed = synth.packed_columns(5, n, np.arange(p), miss)
+    g = _make(bed, n, layout)
+    o = snp.SnpLinAlgOracle(bed, n)
+    rng = np.random.default_rng(0)
+    v = rng.normal(size=n) + 0.3
+    ref = o.xt_v(v)
+    scale = np.abs(ref).max()
+    ex = g.xt_v(v, m.SWEEP_EXACT)
+    np.testing.assert_allclose(ex, ref, rtol=0, atol=1e-11 * scale)      # FP64: stated tolerance 1e-6 rel, we see ~1e-14
+    fa = g.xt_v(v, m.SWEEP_FAST)
+    # FP32-accumulate class (north_star tolerance 1e-4 relative); the proven bound is 2^-18 * ||v - mean||_1 * sinv
+    bound = (2.0 ** -18) * np.abs(v - v.mean()).sum() * o.sigma_inv
+    assert np.all(np.abs(fa - ref) <= bound + 1e-12 * scale)
+    assert np.max(np.abs(fa - ref)) < 1e-4 * scale
+    # multi right-hand sides (MvNormal skinny X'R)
+    V = rng.normal(size=(n, 3))
+    np.testing.assert_allclose(g.xt_v(V, m.SWEEP_EXACT), o.xt_v(V), rtol=0, atol=1e-11 * np.abs(o.xt_v(V)).max())
+    # linearity (size-independent property)
+    a = g.xt_v(v, m.SWEEP_EXACT); b = g.xt_v(2 * v + 1.0, m.SWEEP_EXACT)
+    np.testing.assert_allclose(b, 2 * a, rtol=0, atol=1e-10 * scale)    # centring kills the constant
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_x_support_bit_exact(layout):
+    n, p = 1003, 400
+    bed = synth.packed_columns(9, n, np.arange(p), 0.01)
+    g = _make(bed, n, layout)
+    o = snp.SnpLinAlgOracle(bed, n)
+    rng = np.random.default_rng(1)
+    idx = np.sort(rng.permutation(p)[:37])
+    coef = rng.normal(size=37)
+    # same formula, same order of additions as the reference's getindex loop: bit-exact
+    assert np.array_equal(g.x_support(idx, coef), o.support_xb(idx, coef))
+    C = rng.normal(size=(37, 5))
+    got = g.x_support(idx, C)
+    for t in range(5):
+        assert np.array_equal(got[:, t], o.support_xb(idx, C[:, t]))
+    assert np.array_equal(g.x_support(np.zeros(0, np.int64), np.zeros(0)), np.zeros(n))
+
+
+def test_bundled_fixture_sweep(normal_data, normal_oracle):
+    g = m.B200SnpLinAlg.from_bed_columns(normal_data["bed"], normal_data["n"])
+    r = normal_data["y"] - normal_data["y"].mean()
+    ref = normal_oracle.xt_v(r)
+    np.testing.assert_allclose(g.xt_v(r, m.SWEEP_EXACT), ref, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(g.xt_v(r, m.SWEEP_FAST), ref, rtol=0, atol=1e-4 * np.abs(ref).max())
+
+
+def test_errors():
+    with pytest.raises(m.DimensionMismatch):
+        m.B200SnpLinAlg.from_bed_columns(np.zeros((4, 2), dtype=np.uint8), 100)   # stride < ceil(n/4)
+    g = m.B200SnpLinAlg.synthetic(100, 10, 1)
+    with pytest.raises(m.DimensionMismatch):
+        g.decode(0, 101, 0, 1)
+    with pytest.raises(m.DimensionMismatch):
+        g.x_support(np.array([10]), np.array([1.0]))

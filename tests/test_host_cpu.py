@@ -1,0 +1,94 @@
+"""CPU-only checks of the host layer: the C-ABI library loads and exports every symbol include/ihtb200.h declares,
+the numpy twin of the device generator is deterministic, and the product never imports the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "ihtb200.h")).read()
+    return sorted(set(re.findall(r"^\s*int32_t\s+(ihtb_\w+)\s*\(", hdr, flags=re.M)))
+
+
+def test_library_exports_every_declared_symbol():
+    import mendeliht_jl_b200 as m
+    lib = m.load()
+    syms = _declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ihtb200.h but not exported"
+    # and the ctypes table covers exactly the header
+    assert sorted(m._lib.SIGNATURES) == syms
+    assert lib.ihtb_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    import mendeliht_jl_b200 as m
+    assert ctypes.sizeof(m._lib.Cfg) == 48
+    assert ctypes.sizeof(m._lib.Result) == 72
+    assert ctypes.sizeof(m._lib.IterTrace) == 32
+
+
+def test_no_cpu_fallback_without_device():
+    import mendeliht_jl_b200 as m
+    if m.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(m.CudaError):
+        m.B200SnpLinAlg.synthetic(64, 8, 1)
+    with pytest.raises(m.CudaError):
+        m.B200SnpLinAlg.from_bed_columns(np.zeros((8, 16), dtype=np.uint8), 64)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mendeliht.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_synth_numpy_twin_is_deterministic_and_sane():
+    from mendeliht_jl_b200 import synth
+    a = synth.codes(2024, 2000, np.arange(50))
+    b = synth.codes(2024, 2000, np.arange(50))
+    assert np.array_equal(a, b)
+    assert set(np.unique(a)) <= {0, 2, 3}
+    # columns are a pure function of (seed, j): any subset reproduces
+    assert np.array_equal(synth.codes(2024, 2000, [7, 31]), a[:, [7, 31]])
+    # allele frequency follows maf_j
+    _, maf = synth.maf_threshold(synth.col_key(2024, np.arange(50)))
+    dos = np.array([0, 0, 1, 2])[a]
+    assert np.all(np.abs(dos.mean(axis=0) / 2 - maf) < 0.05)
+    m = synth.codes(2024, 4000, np.arange(20), missing_rate=0.05)
+    assert 0.03 < (m == 1).mean() < 0.07
+    pk = synth.packed_columns(2024, 1003, [0, 1, 2])
+    from oracle import snp
+    assert np.array_equal(snp.unpack_codes(pk, 1003), synth.codes(2024, 1003, [0, 1, 2]))
+
+
+def test_cv_grid_and_meanloss_match_oracle():
+    import mendeliht_jl_b200 as m
+    from oracle import cv as ocv
+    assert m.allocate_fold_and_k(5, range(1, 21)) == ocv.allocate_fold_and_k(5, range(1, 21))
+    rng = np.random.default_rng(0)
+    folds = rng.integers(1, 6, size=1000)
+    loss = rng.random(100)
+    np.testing.assert_array_equal(m.meanloss(loss, 5, folds), ocv.meanloss(loss, 5, folds))
+
+
+def test_argument_checks_mirror_reference_asserts():
+    import mendeliht_jl_b200 as m
+    from mendeliht_jl_b200 import api
+    with pytest.raises(AssertionError):
+        api._check_args(k=-1, max_iter=10, max_step=3, tol=1e-4)
+    with pytest.raises(AssertionError):
+        api._check_args(k=1, max_iter=-1, max_step=3, tol=1e-4)
+    with pytest.raises(AssertionError):
+        api._check_args(k=1, max_iter=10, max_step=3, tol=1e-17)
+    assert m.canonicallink("NegativeBinomial") == "LogLink" and m.canonicallink("Bernoulli") == "LogitLink"
