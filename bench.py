@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Benchmark of the IHT hot path (BASELINE.json metric: IHT iterations/s, with the X'r sweep against the HBM roofline).
+
+Workload at N=1 = BASELINE.json configs[1]: synthetic PLINK n=50,000 x p=500,000, Bernoulli/LogitLink, k=20 `fit_iht`.
+A "step" is one complete `fit_iht` (init_iht_indices! + the loop to convergence, reference defaults); the metric is
+IHT iterations per second = (iterations summed over the K timed fits) / (device time of those fits).
+  value : inputs (genotypes, y, z) resident in HBM, K x (ihtb_fit_init + ihtb_fit_run), CUDA events on the fit stream
+  e2e   : K x the public `fit_iht(y, x, z)` call with HOST y / z and beta read back (the genotype operator `x` is
+          constructed once from HOST .bed bytes before the timed region, like SnpLinAlg in the reference)
+  roofline : the X'r sweep kernel timed alone with CUDA events (algorithmic bytes = p*ceil(n/4) + 8n + 24p)
+  cpu_baseline : the CPU restatement of the reference (oracle/, C+OpenMP kernels) on a column sample
+`--impl reference` times that CPU restatement as the reference arm (Julia is not installed in this image).
+At N>1 the SNP columns are sharded over the ranks (weak scaling: p = 500,000 columns per GPU).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+N_SAMPLES = 50_000
+P_PER_GPU = 500_000
+K_SPARSITY = 20
+SEED = 2024
+DIST, LINK = "Bernoulli", "LogitLink"
+CPU_SAMPLE_COLS = 40_000
+
+
+def sweep_bytes(n, p):
+    return p * ((n + 3) // 4) + 8 * n + 24 * p
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, nm in enumerate(names):
+                if len(r) > 2 + i and r[2 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_iters_per_sec(n, p_full, k, steps, warmup):
+    """CPU restatement of the reference on a column sample of the same workload; scaled to the full column count
+    (an IHT iteration is dominated by the O(n p) sweep, reference test/fit_profile.ipynb: 77-87 %)."""
+    from oracle import cpu as ocpu
+    from oracle import glm as oglm
+    from oracle import iht as oiht
+    from mendeliht_jl_b200 import synth
+    ps = min(CPU_SAMPLE_COLS, p_full)
+    bed = ocpu.synth_columns(SEED, n, 0, ps)
+    x = ocpu.PackedSnpLinAlgCPU(bed, n)
+    y, z, _, _, _ = synth.simulate_response(SEED + 1, n, ps, k, DIST, geno_seed=SEED)
+    tot_it, tot_t = 0, 0.0
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        res = oiht.fit_iht(y, x, z, k=k, d=oglm.BERNOULLI, l=oglm.LOGIT)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            tot_it += res.iter
+            tot_t += dt
+    v = v_sample = tot_it / tot_t
+    v = v_sample * ps / p_full
+    sample = (f"fit_iht on n={n} x first {ps} of {p_full} columns ({DIST}, k={k}), {steps} fit(s), "
+              f"{tot_it} iterations in {tot_t:.2f}s = {v_sample:.2f} it/s on the sample, scaled by {ps}/{p_full}")
+    return v, x.threads, sample, tot_t / max(steps, 1) * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    v, threads, sample, ms = cpu_port_iters_per_sec(N_SAMPLES, P_PER_GPU * args.gpus, K_SPARSITY, steps,
+                                                    min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "iht_iterations_per_sec", "value": v, "unit": "iterations/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "Julia/SnpArrays.jl cannot run in this image; this is the C+OpenMP/numpy restatement of the reference "
+                "algorithm (oracle/) on all host cores",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": f"BASELINE configs[1]: synthetic PLINK n={N_SAMPLES} p={P_PER_GPU * n_gpus} "
+                        f"{DIST}/{LINK} k={K_SPARSITY} fit_iht" + (f", SNP columns sharded over {n_gpus} GPUs"
+                                                                   if n_gpus > 1 else ""),
+            "n": N_SAMPLES, "p": P_PER_GPU * n_gpus, "k": K_SPARSITY, "dist": DIST, "link": LINK, "seed": SEED,
+            "sweep_mode": "FAST (FP32 LUT partials, FP64 re-scoring of top-k candidates)",
+            "l2_policy": "inputs larger than L2 (6.25 GB packed genotypes per sweep vs 126 MB L2)"}
+
+
+def run_ours(args):
+    import mendeliht_jl_b200 as m
+    from mendeliht_jl_b200 import synth
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from mendeliht_jl_b200 import parallel
+        return parallel.bench_sharded(args, rank, world, local_rank, globals())
+
+    assert m.device_count() > 0, "bench.py needs a CUDA device (no CPU fallback)"
+    lib = m.load()
+    m._lib.check(lib.ihtb_set_device(0))
+    n, p, k = N_SAMPLES, P_PER_GPU, K_SPARSITY
+
+    # ---- inputs: HOST .bed bytes -> device genotype operator (constructed once, like SnpLinAlg) ----
+    t0 = time.perf_counter()
+    bed = np.empty((p, (n + 3) // 4), dtype=np.uint8)
+    m._lib.check(lib.ihtb_synth_host(n, p, 0, SEED, 0.0, bed.ctypes.data_as(C.POINTER(C.c_uint8))))
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    t_upload = time.perf_counter() - t0
+    del bed
+    y, z, true_idx, true_beta, _ = synth.simulate_response(SEED + 1, n, p, k, DIST, geno_seed=SEED)
+
+    launches0 = m.launch_count()
+    clocks = ClockSampler(0)
+
+    # ---- value: device-resident fits ----
+    v = m.IHTVariable(g, z, y, k, DIST, LINK)
+    for _ in range(args.warmup):
+        v.init_iht_indices(None)
+        v.fit(trace_cap=0)
+    clocks.start()
+    ms = C.c_double(0.0)
+    m._lib.check(lib.ihtb_fit_timer(v._h, 0, None))
+    l_before = m.launch_count()
+    iters = sweeps = 0
+    sweep_s = 0.0
+    for _ in range(args.steps):
+        v.init_iht_indices(None)
+        res, _ = v.fit(trace_cap=0)
+        iters += int(res.iter); sweeps += int(res.n_sweeps); sweep_s += res.sweep_seconds
+    m._lib.check(lib.ihtb_fit_timer(v._h, 1, C.byref(ms)))
+    l_timed = m.launch_count() - l_before
+    t_value = ms.value * 1e-3
+    beta, c, _, _ = v.get()
+    v.close()
+
+    # ---- e2e: public API, host buffers in / out every step ----
+    for _ in range(min(args.warmup, 1)):
+        m.fit_iht(y, g, z, k=k, d=DIST, l=LINK)
+    t0 = time.perf_counter()
+    e_iters = 0
+    for _ in range(args.steps):
+        r = m.fit_iht(y, g, z, k=k, d=DIST, l=LINK)
+        e_iters += r.iter
+    t_e2e = time.perf_counter() - t0
+    clk = clocks.stop()
+
+    # ---- roofline: the sweep kernel timed alone ----
+    mk, mt = C.c_double(0.0), C.c_double(0.0)
+    m._lib.check(lib.ihtb_sweep_bench(g._h, m.SWEEP_FAST, 3, 20, C.byref(mk), C.byref(mt)))
+    peak, peak_src = measured_peak()
+    abytes = sweep_bytes(n, p)
+    achieved = abytes / (mk.value * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- CPU baseline (bounded sample) ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            cv, threads, sample, _ = cpu_port_iters_per_sec(n, p, k, 1, 0)
+            cpu = {"value": cv, "unit": "iterations/s", "cores": threads, "kind": "port", "sample": sample}
+        except Exception as e:  # the baseline is a report, not a dependency of the product path
+            cpu = {"value": None, "unit": "iterations/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+
+    nz = np.flatnonzero(beta)
+    line = {
+        "metric": "iht_iterations_per_sec", "value": iters / t_value, "unit": "iterations/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_value / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(1),
+        "iterations_per_fit": iters / args.steps, "sweeps_per_fit": sweeps / args.steps,
+        "sweep_ms_in_fit": sweep_s / max(sweeps - args.steps, 1) * 1e3,
+        "sweep_share_of_step": sweep_s / t_value,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "k_sweep_lut",
+                     "algorithmic_bytes_per_launch": abytes, "kernel_ms": mk.value,
+                     "sweep_with_epilogue_ms": mt.value, "sweep_with_epilogue_gbs": abytes / (mt.value * 1e-3) / 1e9},
+        "e2e": {"value": e_iters / t_e2e, "unit": "iterations/s",
+                "h2d_bytes_per_step": int(y.nbytes + z.nbytes), "d2h_bytes_per_step": int(beta.nbytes + c.nbytes),
+                "ms_per_step": t_e2e / args.steps * 1e3,
+                "note": "fit_iht(y, x, z) with host y/z and beta copied back; x (genotype operator) built once from "
+                        "host .bed bytes before the timed region",
+                "geno_host_generate_s": t_gen, "geno_create_from_host_s": t_upload,
+                "geno_h2d_bytes": int(p * ((n + 3) // 4))},
+        "gpu_launches": int(l_timed),
+        "clocks": clk,
+        "cpu_baseline": cpu,
+        "check": {"support_size": int(nz.size), "true_positives": int(np.intersect1d(nz, true_idx).size),
+                  "iterations": iters // args.steps},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -98,6 +98,8 @@ int32_t ihtb_geno_create(const uint8_t* bed_cols, int64_t n, int64_t p, int64_t 
  * (seed, global column, sample).  Columns [j0, j0+p_local) of a p_global-column matrix (j0=0, p_local=p for one GPU). */
 int32_t ihtb_geno_create_synthetic(int64_t n, int64_t p_local, int64_t j0, uint64_t seed, double missing_rate,
                                    ihtb_geno** out);
+/* host twin of the device generator: fills out[ncols][ceil(n/4)] with the same bytes (multi-threaded, no GPU needed) */
+int32_t ihtb_synth_host(int64_t n, int64_t ncols, int64_t j0, uint64_t seed, double missing_rate, uint8_t* out);
 int32_t ihtb_geno_dims(const ihtb_geno* g, int64_t* n, int64_t* p);
 int32_t ihtb_geno_stats(const ihtb_geno* g, double* mu, double* sigma_inv, int64_t* n_missing);
 /* bit-exact getindex: out[(j-j0)*(i1-i0) + (i-i0)] = x[i, j] for i in [i0,i1), j in [j0,j1)  (src/utilities.jl:102,735) */
@@ -108,6 +110,10 @@ int32_t ihtb_geno_packed(const ihtb_geno* g, int64_t j0, int64_t j1, uint8_t* ou
 int32_t ihtb_xt_v(const ihtb_geno* g, const double* V, int64_t m, double* out, int32_t sweep_mode);
 /* x[:, idx] * coef: idx are 0-based columns, coef is k x m column-major, out is n x m  (src/utilities.jl:95-111,728-743) */
 int32_t ihtb_x_support(const ihtb_geno* g, const int64_t* idx, int64_t k, const double* coef, int64_t m, double* out);
+/* measurement hook: the sweep timed alone on a device-resident vector with CUDA events on its own stream;
+ * ms_kernel = the dominant kernel, ms_total = kernel + epilogue, both averaged over `reps` launches */
+int32_t ihtb_sweep_bench(const ihtb_geno* g, int32_t sweep_mode, int32_t warmup, int32_t reps, double* ms_kernel,
+                         double* ms_total);
 int32_t ihtb_geno_destroy(ihtb_geno* g);
 
 /* ---- univariate fit (fit_iht / fit_iht! / init_iht_indices!, src/fit.jl:60-207, src/utilities.jl:366-438) ---- */
@@ -120,6 +126,8 @@ int32_t ihtb_fit_run(ihtb_fit* f, ihtb_result* result, ihtb_iter_trace* trace, i
 /* any pointer may be NULL; beta[p], c[q], mu[n], xb[n] */
 int32_t ihtb_fit_get(const ihtb_fit* f, double* beta, double* c, double* mu, double* xb);
 int32_t ihtb_fit_predict(ihtb_fit* f, const uint8_t* test_mask, double* deviance);   /* predict! (src/cross_validation.jl:279-286) */
+/* CUDA-event stopwatch on the fit's stream: which=0 start, which=1 stop (elapsed device milliseconds in *ms) */
+int32_t ihtb_fit_timer(ihtb_fit* f, int32_t which, double* ms);
 int32_t ihtb_fit_destroy(ihtb_fit* f);
 
 #ifdef __cplusplus

@@ -73,12 +73,14 @@ SIGNATURES = {
     "ihtb_launch_count": [_i64],
     "ihtb_geno_create": [_u8, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _pp],
     "ihtb_geno_create_synthetic": [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_double, _pp],
+    "ihtb_synth_host": [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_double, _u8],
     "ihtb_geno_dims": [_p, _i64, _i64],
     "ihtb_geno_stats": [_p, _f64, _f64, _i64],
     "ihtb_geno_decode": [_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _f64],
     "ihtb_geno_packed": [_p, C.c_int64, C.c_int64, _u8],
     "ihtb_xt_v": [_p, _f64, C.c_int64, _f64, C.c_int32],
     "ihtb_x_support": [_p, _i64, C.c_int64, _f64, C.c_int64, _f64],
+    "ihtb_sweep_bench": [_p, C.c_int32, C.c_int32, C.c_int32, _f64, _f64],
     "ihtb_geno_destroy": [_p],
     "ihtb_fit_create": [_p, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), _pp],
     "ihtb_fit_set_k": [_p, C.c_int64],
@@ -86,6 +88,7 @@ SIGNATURES = {
     "ihtb_fit_run": [_p, C.POINTER(Result), C.POINTER(IterTrace), C.c_int64],
     "ihtb_fit_get": [_p, _f64, _f64, _f64, _f64],
     "ihtb_fit_predict": [_p, _u8, _f64],
+    "ihtb_fit_timer": [_p, C.c_int32, _f64],
     "ihtb_fit_destroy": [_p],
 }
 

@@ -108,8 +108,8 @@ class B200SnpLinAlg:
         idx = np.ascontiguousarray(idx, dtype=np.int64)
         coef = np.asarray(coef, dtype=np.float64)
         one = coef.ndim == 1
-        cm = np.asfortranarray(coef.reshape(idx.shape[0], -1))
-        m = cm.shape[1]
+        m = 1 if one else coef.shape[1]
+        cm = np.asfortranarray(coef.reshape(idx.shape[0], m))
         out = np.empty((self.n, m), order="F")
         check(load().ihtb_x_support(self._h, ptr(idx, C.c_int64), idx.shape[0],
                                     cm.ctypes.data_as(C.POINTER(C.c_double)), m,

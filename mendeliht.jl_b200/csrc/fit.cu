@@ -56,7 +56,7 @@ struct ihtb_fit {
     HBuf<double> h_scal, h_gout;
     HBuf<int64_t> h_sel;
     void* sweep_scratch = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
     bool sweep_pending = false;
     GlmCtx glm{};
     TopkCtx tk{};
@@ -82,6 +82,8 @@ struct ihtb_fit {
         if (sweep_scratch) sweep_scratch_destroy(sweep_scratch);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (tm0) cudaEventDestroy(tm0);
+        if (tm1) cudaEventDestroy(tm1);
         if (s) cudaStreamDestroy(s);
     }
 
@@ -553,6 +555,26 @@ int32_t ihtb_fit_predict(ihtb_fit* f, const uint8_t* test_mask, double* deviance
         f->update_xb();
         f->glm_update(1);
         *deviance = f->last_dev;
+    });
+}
+
+// CUDA-event stopwatch on the fit's stream (bench.py): which = 0 records the start event, 1 records the stop event
+// and returns the elapsed device time between them in milliseconds.
+int32_t ihtb_fit_timer(ihtb_fit* f, int32_t which, double* ms) {
+    return guard([&] {
+        IHTB_CHECK(f, IHTB_EINVAL, "NULL fit handle");
+        IHTB_CUDA(cudaSetDevice(f->g->device));
+        if (!f->tm0) { IHTB_CUDA(cudaEventCreate(&f->tm0)); IHTB_CUDA(cudaEventCreate(&f->tm1)); }
+        if (which == 0) {
+            IHTB_CUDA(cudaStreamSynchronize(f->s));
+            IHTB_CUDA(cudaEventRecord(f->tm0, f->s));
+        } else {
+            IHTB_CUDA(cudaEventRecord(f->tm1, f->s));
+            IHTB_CUDA(cudaEventSynchronize(f->tm1));
+            float t = 0.f;
+            IHTB_CUDA(cudaEventElapsedTime(&t, f->tm0, f->tm1));
+            if (ms) *ms = t;
+        }
     });
 }
 

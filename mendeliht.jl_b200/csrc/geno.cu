@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "synth.cuh"
 #include <mutex>
+#include <thread>
 #include <stdlib.h>
 #include <string.h>
 
@@ -301,6 +302,37 @@ int32_t ihtb_geno_create_synthetic(int64_t n, int64_t p_local, int64_t j0, uint6
             throw;
         }
         *out = g;
+    });
+}
+
+// host twin of k_synth (multi-threaded); lets callers build host-resident .bed columns identical to the device ones
+int32_t ihtb_synth_host(int64_t n, int64_t ncols, int64_t j0, uint64_t seed, double missing_rate, uint8_t* out) {
+    return guard([&] {
+        IHTB_CHECK(out && n > 0 && ncols >= 0, IHTB_EINVAL, "bad argument");
+        const int64_t nbytes = (n + 3) / 4;
+        const uint32_t miss_thr = synth_missing_threshold(missing_rate);
+        unsigned nt = std::thread::hardware_concurrency();
+        if (nt == 0) nt = 1;
+        if ((int64_t)nt > ncols) nt = (unsigned)(ncols > 0 ? ncols : 1);
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; ++t) {
+            pool.emplace_back([=] {
+                for (int64_t c = ncols * t / nt; c < ncols * (t + 1) / nt; ++c) {
+                    uint64_t key = synth_col_key(seed, (uint64_t)(j0 + c));
+                    uint64_t thr = synth_maf_threshold(key);
+                    uint8_t* col = out + c * nbytes;
+                    for (int64_t b = 0; b < nbytes; ++b) {
+                        uint32_t byte = 0;
+                        for (int s = 0; s < 4; ++s) {
+                            int64_t i = 4 * b + s;
+                            if (i < n) byte |= synth_code(key, thr, miss_thr, (uint64_t)i) << (2 * s);
+                        }
+                        col[b] = (uint8_t)byte;
+                    }
+                }
+            });
+        }
+        for (auto& th : pool) th.join();
     });
 }
 

@@ -175,3 +175,67 @@ extern "C" int32_t ihtb_xt_v(const ihtb_geno* g, const double* V, int64_t m, dou
         IHTB_CUDA(cudaMemcpy(out, dOut.p, g->p * m * sizeof(double), cudaMemcpyDeviceToHost));
     });
 }
+
+// ---- measurement hooks (bench.py): sweep timed alone on a device-resident vector, CUDA events on its stream ------
+namespace ihtb {
+void sweep_fast_kernel_only(const ihtb_geno* g, const double* d_v, double vbar, float* d_part, cudaStream_t s);
+__global__ void k_fill_vec(double* v, int64_t n, uint64_t seed) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t x = seed + (uint64_t)i * 0x9E3779B97F4A7C15ull;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+    v[i] = ((double)(x >> 11) * (1.0 / 9007199254740992.0) - 0.5) * 2.0;
+}
+}  // namespace ihtb
+
+extern "C" int32_t ihtb_sweep_bench(const ihtb_geno* g, int32_t sweep_mode, int32_t warmup, int32_t reps,
+                                    double* ms_kernel, double* ms_total) {
+    return guard([&] {
+        IHTB_CHECK(g && reps >= 1 && warmup >= 0, IHTB_EINVAL, "bad argument");
+        IHTB_CUDA(cudaSetDevice(g->device));
+        cudaStream_t s;
+        IHTB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        DBuf<double> dV((size_t)g->n), dOut((size_t)g->p);
+        IHTB_LAUNCH(k_fill_vec, (unsigned)ceil_div(g->n, 256), 256, 0, s, dV.p, g->n, 12345ull);
+        double vbar = 0.0;
+        SweepScratch sc;
+        cudaEvent_t e0, e1;
+        IHTB_CUDA(cudaEventCreate(&e0)); IHTB_CUDA(cudaEventCreate(&e1));
+        for (int i = 0; i < warmup; ++i)
+            sweep_xt_v_with_means(g, dV.p, &vbar, 1, dOut.p, sweep_mode, s, &sc, nullptr);
+        // (a) whole sweep = partial-sum kernel + epilogue
+        IHTB_CUDA(cudaEventRecord(e0, s));
+        for (int i = 0; i < reps; ++i)
+            sweep_xt_v_with_means(g, dV.p, &vbar, 1, dOut.p, sweep_mode, s, &sc, nullptr);
+        IHTB_CUDA(cudaEventRecord(e1, s));
+        IHTB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        IHTB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms_total) *ms_total = ms / reps;
+        // (b) the dominant kernel alone
+        if (ms_kernel) {
+            *ms_kernel = 0.0;
+            if (sweep_mode == IHTB_SWEEP_FAST) {
+                IHTB_CUDA(cudaEventRecord(e0, s));
+                for (int i = 0; i < reps; ++i) sweep_fast_kernel_only(g, dV.p, vbar, sc.part32.p, s);
+                IHTB_CUDA(cudaEventRecord(e1, s));
+                IHTB_CUDA(cudaEventSynchronize(e1));
+                IHTB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+                *ms_kernel = ms / reps;
+            } else {
+                int64_t words = g->stride >> 2;
+                int64_t n_slabs = ceil_div(words, EX_THREADS);
+                dim3 grid((unsigned)ceil_div(g->p, EX_COLS_PER_CTA), (unsigned)n_slabs);
+                IHTB_CUDA(cudaEventRecord(e0, s));
+                for (int i = 0; i < reps; ++i)
+                    IHTB_LAUNCH(k_sweep_exact, grid, EX_THREADS, 0, s, geno_view(g), dV.p, vbar, sc.part64.p);
+                IHTB_CUDA(cudaEventRecord(e1, s));
+                IHTB_CUDA(cudaEventSynchronize(e1));
+                IHTB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+                *ms_kernel = ms / reps;
+            }
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        cudaStreamDestroy(s);
+    });
+}

@@ -234,7 +234,15 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
     }
 }
 
+void sweep_fast_partials(const ihtb_geno* g, const double* d_v, double vbar, float* d_part, int64_t* n_slabs_out,
+                         cudaStream_t s);
+
 int64_t sweep_fast_num_slabs(const ihtb_geno* g) { return g->stride / 128; }
+
+void sweep_fast_kernel_only(const ihtb_geno* g, const double* d_v, double vbar, float* d_part, cudaStream_t s) {
+    int64_t ns = 0;
+    sweep_fast_partials(g, d_v, vbar, d_part, &ns, s);
+}
 
 void sweep_fast_partials(const ihtb_geno* g, const double* d_v, double vbar, float* d_part, int64_t* n_slabs_out,
                          cudaStream_t s) {
