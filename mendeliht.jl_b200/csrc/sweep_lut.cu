@@ -18,14 +18,12 @@
 // stage with a butterfly so that lanes 0..15 end up holding one column sum each.  Slab partial sums are written as
 // FP32 [slab][column]; the epilogue (sweep.cu) adds them in FP64 in slab order.  Everything is deterministic.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ihtb {
 
-constexpr int LUT_CONSUMER_WARPS = 8;
-constexpr int LUT_THREADS = (LUT_CONSUMER_WARPS + 1) * 32;
 constexpr int LUT_STAGE_COLS = 128;
 constexpr int LUT_STAGE_BYTES = LUT_STAGE_COLS * 128;
-constexpr int LUT_COLS_PER_WARP = LUT_STAGE_COLS / LUT_CONSUMER_WARPS;   // 16
 constexpr int LUT_MAX_STAGES = 6;
 constexpr int LUT_TABLE_BYTES = 131072;
 constexpr int LUT_SMEM_BYTES = 232448;   // 227 KB: everything the SM has
@@ -66,8 +64,9 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-__device__ __forceinline__ void consumer_bar() {   // named barrier 1 over the 256 consumer threads
-    asm volatile("bar.sync 1, %0;" ::"n"(LUT_CONSUMER_WARPS * 32) : "memory");
+template <int NT>
+__device__ __forceinline__ void consumer_bar() {   // named barrier 1 over the NT consumer threads
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
 }
 
 // shared-memory plan (computed identically by every thread)
@@ -100,45 +99,51 @@ __device__ __forceinline__ LutPlan lut_plan(uint32_t base, uint32_t bytes) {
     return pl;
 }
 
-// build T for one slab; executed by the 256 consumer threads
+// build T for one slab; executed by the NT (256 or 512) consumer threads
+template <int NT>
 __device__ __forceinline__ void lut_build(uint32_t tab, const double* __restrict__ v, double vbar, int64_t n,
                                           int64_t slab, int tid) {
-    // thread -> (half, group): group = t*32 + w (128 groups), half selects values [0,128) or [128,256)
-    const int group = tid & 127, half = tid >> 7;
+    // thread -> (part, group): group = t*32 + w (128 groups); part selects a range of the top sample's code v3
+    constexpr int PARTS = NT / 128;          // 2 or 4
+    constexpr int V3_PER = 4 / PARTS;        // 2 or 1
+    const int group = tid & 127, part = tid >> 7;
     const int t = group >> 5, w = group & 31;
-    float f[4][4];
+    float u[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         int64_t i = slab * 512 + 16 * w + 4 * t + s;
-        float u = (i < n) ? __double2float_rn(__dsub_rn(v[i], vbar)) : 0.0f;
-        f[s][0] = 0.0f; f[s][1] = 0.0f; f[s][2] = u; f[s][3] = u + u;   // codes 00, 01 (missing -> 0), 10, 11
+        u[s] = (i < n) ? __double2float_rn(__dsub_rn(v[i], vbar)) : 0.0f;
     }
+    // dosage table of one sample: codes 00, 01 (missing -> 0), 10, 11
+    auto f = [&](int s, int code) -> float { return code == 2 ? u[s] : (code == 3 ? u[s] + u[s] : 0.0f); };
     // address of row `value`: window(t>>1) + value*256 + (t&1)*128 + 4*w
     const uint32_t rowbase = tab + (uint32_t)(t >> 1) * 65536u + (uint32_t)(t & 1) * 128u + 4u * (uint32_t)w;
 #pragma unroll
-    for (int c3 = 0; c3 < 2; ++c3) {
-        const int v3 = 2 * half + c3;
-        const float a3 = half ? f[3][2 + c3] : 0.0f;   // values 0,1 of the top sample add nothing
+    for (int c3 = 0; c3 < V3_PER; ++c3) {
+        const int v3 = part * V3_PER + c3;                 // runtime, but only used arithmetically
+        const float a3 = (v3 == 2) ? u[3] : ((v3 == 3) ? u[3] + u[3] : 0.0f);
+        const uint32_t base3 = rowbase + (uint32_t)v3 * (64u * 256u);
 #pragma unroll
         for (int v2 = 0; v2 < 4; ++v2) {
-            const float a2 = a3 + f[2][v2];
+            const float a2 = a3 + f(2, v2);
 #pragma unroll
             for (int v1 = 0; v1 < 4; ++v1) {
-                const float a1 = a2 + f[1][v1];
+                const float a1 = a2 + f(1, v1);
 #pragma unroll
-                for (int v0 = 0; v0 < 4; ++v0) {
-                    const uint32_t value = (uint32_t)(v3 << 6 | v2 << 4 | v1 << 2 | v0);
-                    sts_f32(rowbase + value * 256u, a1 + f[0][v0]);
-                }
+                for (int v0 = 0; v0 < 4; ++v0)
+                    sts_f32(base3 + (uint32_t)(v2 << 4 | v1 << 2 | v0) * 256u, a1 + f(0, v0));
             }
         }
     }
 }
 
 // Units: u = slab * n_cblocks + cblock, CTA b handles [u_begin(b), u_begin(b+1)).
-__global__ void __launch_bounds__(LUT_THREADS, 1)
+// CW consumer warps (8 or 16) + 1 producer warp; each consumer warp reduces CPW = 128/CW columns per stage.
+template <int CW>
+__global__ void __launch_bounds__((CW + 1) * 32, 1)
 k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t p, int64_t n, int64_t n_slabs,
             const double* __restrict__ v, double vbar, float* __restrict__ part, uint32_t dyn_bytes) {
+    constexpr int CPW = LUT_STAGE_COLS / CW;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const LutPlan pl = lut_plan(smem_u32(smem_raw), dyn_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -152,13 +157,13 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(pl.bar_full + 8u * s, 1);
-            mbar_init(pl.bar_empty + 8u * s, LUT_CONSUMER_WARPS);
+            mbar_init(pl.bar_empty + 8u * s, CW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == LUT_CONSUMER_WARPS) {
+    if (warp == CW) {
         // ===== producer warp: stream column chunks with bulk async copies =====
         int st = 0; uint32_t ph = 0;
         for (int64_t u = u_beg; u < u_end; ++u) {
@@ -182,7 +187,7 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
         }
     } else {
         // ===== consumer warps =====
-        const int tid = threadIdx.x;      // 0..255
+        const int tid = threadIdx.x;      // 0 .. CW*32-1
         // per-lane base registers for the 4 bytes of a word: byte 1 gets replaced by the data byte
         uint32_t lb[4];
 #pragma unroll
@@ -193,16 +198,16 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
         for (int64_t u = u_beg; u < u_end; ++u) {
             const int64_t slab = u / n_cblocks, cb = u % n_cblocks;
             if (slab != cur_slab) {
-                consumer_bar();               // everyone finished looking up the previous slab's tables
-                lut_build(pl.tab, v, vbar, n, slab, tid);
-                consumer_bar();
+                consumer_bar<CW * 32>();      // everyone finished looking up the previous slab's tables
+                lut_build<CW * 32>(pl.tab, v, vbar, n, slab, tid);
+                consumer_bar<CW * 32>();
                 cur_slab = slab;
             }
             mbar_wait(pl.bar_full + 8u * st, ph);
-            const uint32_t colbase = pl.stage(st) + (uint32_t)(warp * LUT_COLS_PER_WARP) * 128u + 4u * (uint32_t)lane;
-            float acc[LUT_COLS_PER_WARP];
+            const uint32_t colbase = pl.stage(st) + (uint32_t)(warp * CPW) * 128u + 4u * (uint32_t)lane;
+            float acc[CPW];
 #pragma unroll
-            for (int c = 0; c < LUT_COLS_PER_WARP; ++c) {
+            for (int c = 0; c < CPW; ++c) {
                 const uint32_t w = lds_u32(colbase + 128u * c);
                 const float t0 = lds_f32(__byte_perm(w, lb[0], 0x7604));
                 const float t1 = lds_f32(__byte_perm(w, lb[1], 0x7614));
@@ -213,9 +218,10 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
             // the stage's bytes are now in registers: hand the slot back to the producer
             __syncwarp();
             if (lane == 0) mbar_arrive(pl.bar_empty + 8u * st);
-            // butterfly: 16 column sums per lane -> one per lane (lanes l and l^16 hold the same column)
+            // butterfly: CPW column sums per lane -> one per lane; lane bits 4,3,.. select the column
+            int o = 16;
 #pragma unroll
-            for (int h = 8, o = 16; h >= 1; h >>= 1, o >>= 1) {
+            for (int h = CPW / 2; h >= 1; h >>= 1, o >>= 1) {
                 const bool upper = (lane & o) != 0;
 #pragma unroll
                 for (int c = 0; c < h; ++c) {
@@ -224,11 +230,12 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
                     acc[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
                 }
             }
-            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
-            // after the 4 halving steps lane bits (16,8,4,2) select the column: col = bit16*8 + bit8*4 + bit4*2 + bit2
-            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            const int64_t j = cb * LUT_STAGE_COLS + warp * LUT_COLS_PER_WARP + col;
-            if ((lane & 1) == 0 && j < p) part[slab * p + j] = acc[0];
+#pragma unroll
+            for (int oo = 16 / CPW; oo >= 1; oo >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], oo);
+            constexpr int LPC = 32 / CPW;          // lanes per column after the butterfly
+            const int col = lane / LPC;
+            const int64_t j = cb * LUT_STAGE_COLS + warp * CPW + col;
+            if ((lane & (LPC - 1)) == 0 && j < p) part[slab * p + j] = acc[0];
             if (++st == S) { st = 0; ph ^= 1u; }
         }
     }
@@ -246,10 +253,12 @@ void sweep_fast_kernel_only(const ihtb_geno* g, const double* d_v, double vbar, 
 
 void sweep_fast_partials(const ihtb_geno* g, const double* d_v, double vbar, float* d_part, int64_t* n_slabs_out,
                          cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        IHTB_CUDA(cudaFuncSetAttribute(k_sweep_lut, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES));
-        configured = true;
+    static int cw = 0;
+    if (!cw) {
+        IHTB_CUDA(cudaFuncSetAttribute(k_sweep_lut<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES));
+        IHTB_CUDA(cudaFuncSetAttribute(k_sweep_lut<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES));
+        const char* e = getenv("IHTB_LUT_WARPS");
+        cw = (e && atoi(e) == 8) ? 8 : 16;
     }
     const int64_t n_slabs = sweep_fast_num_slabs(g);
     *n_slabs_out = n_slabs;
@@ -257,8 +266,13 @@ void sweep_fast_partials(const ihtb_geno* g, const double* d_v, double vbar, flo
     int64_t units = n_slabs * n_cblocks;
     int grid = g->sm_count;
     if (units < grid) grid = (int)units;
-    IHTB_LAUNCH(k_sweep_lut, grid, LUT_THREADS, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n, n_slabs, d_v,
-                vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
+    if (cw == 8) {
+        IHTB_LAUNCH(k_sweep_lut<8>, grid, 9 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n, n_slabs,
+                    d_v, vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
+    } else {
+        IHTB_LAUNCH(k_sweep_lut<16>, grid, 17 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n, n_slabs,
+                    d_v, vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
+    }
 }
 
 }  // namespace ihtb

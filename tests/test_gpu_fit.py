@@ -65,7 +65,8 @@ def test_config1_readme_call(normal_data, normal_oracle, mode):
 CASES = [
     # d, link, n, p, true k, fitted k, covariates, missing rate
     ("Normal", "IdentityLink", 1200, 3000, 8, 10, 2, 0.0),
-    ("Bernoulli", "LogitLink", 1500, 3000, 6, 6, 0, 0.0),
+    ("Bernoulli", "LogitLink", 2000, 3000, 5, 7, 1, 0.0),
+    ("Bernoulli", "LogitLink", 3000, 2000, 4, 4, 0, 0.0),
     ("Poisson", "LogLink", 1500, 2500, 6, 8, 1, 0.0),
     ("NegativeBinomial", "LogLink", 1500, 2500, 6, 8, 0, 0.0),
     ("Normal", "IdentityLink", 1003, 2001, 5, 7, 1, 0.01),      # ragged n, missing genotypes
