@@ -137,13 +137,16 @@ __device__ __forceinline__ void lut_build(uint32_t tab, const double* __restrict
     }
 }
 
-// Units: u = slab * n_cblocks + cblock, CTA b handles [u_begin(b), u_begin(b+1)).
-// CW consumer warps (8 or 16) + 1 producer warp; each consumer warp reduces CPW = 128/CW columns per stage.
-template <int CW>
+// Units: u = slab * n_cblocks + cblock, CTA b handles [u_begin(b), u_begin(b+1)), slab by slab.
+// CW consumer warps in G groups (+ 1 producer warp).  Group g consumes the CTA's units with (local index % G) == g, and
+// each of its CW/G warps reduces CPW = 128*G/CW columns of that unit, so per-unit bookkeeping is amortised over 16
+// columns per warp while 16 warps keep the shared-memory pipe busy.
+template <int CW, int G>
 __global__ void __launch_bounds__((CW + 1) * 32, 1)
 k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t p, int64_t n, int64_t n_slabs,
             const double* __restrict__ v, double vbar, float* __restrict__ part, uint32_t dyn_bytes) {
-    constexpr int CPW = LUT_STAGE_COLS / CW;
+    constexpr int WPG = CW / G;                      // warps per group
+    constexpr int CPW = LUT_STAGE_COLS / WPG;        // columns per warp per unit
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const LutPlan pl = lut_plan(smem_u32(smem_raw), dyn_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -153,11 +156,14 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
     const int64_t units = n_slabs * n_cblocks;
     const int64_t u_beg = units * (int64_t)blockIdx.x / gridDim.x;
     const int64_t u_end = units * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    if (u_beg >= u_end) return;
+    const int64_t slab_beg = u_beg / n_cblocks, slab_end = (u_end - 1) / n_cblocks;   // inclusive
+    const int ncb = (int)n_cblocks;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(pl.bar_full + 8u * s, 1);
-            mbar_init(pl.bar_empty + 8u * s, CW);
+            mbar_init(pl.bar_empty + 8u * s, WPG);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -166,77 +172,90 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
     if (warp == CW) {
         // ===== producer warp: stream column chunks with bulk async copies =====
         int st = 0; uint32_t ph = 0;
-        for (int64_t u = u_beg; u < u_end; ++u) {
-            const int64_t slab = u / n_cblocks, cb = u % n_cblocks;
-            const int64_t j0 = cb * LUT_STAGE_COLS;
-            const int ncols = (int)((p - j0 < LUT_STAGE_COLS) ? (p - j0) : LUT_STAGE_COLS);
-            mbar_wait(pl.bar_empty + 8u * st, ph ^ 1u);
-            const uint8_t* src = bed + j0 * cs_j + slab * cs_s;
-            if (cs_j == 128) {               // slab-major tiled layout: one contiguous copy
-                if (lane == 0) {
-                    mbar_expect_tx(pl.bar_full + 8u * st, (uint32_t)ncols * 128u);
-                    bulk_g2s(pl.stage(st), src, (uint32_t)ncols * 128u, pl.bar_full + 8u * st);
+        for (int64_t slab = slab_beg; slab <= slab_end; ++slab) {
+            const int cb0 = (slab == slab_beg) ? (int)(u_beg - slab * n_cblocks) : 0;
+            const int cb1 = (slab == slab_end) ? (int)(u_end - slab * n_cblocks) : ncb;    // exclusive
+            for (int cb = cb0; cb < cb1; ++cb) {
+                const int64_t j0 = (int64_t)cb * LUT_STAGE_COLS;
+                const int ncols = (int)((p - j0 < LUT_STAGE_COLS) ? (p - j0) : LUT_STAGE_COLS);
+                mbar_wait(pl.bar_empty + 8u * st, ph ^ 1u);
+                const uint8_t* src = bed + j0 * cs_j + slab * cs_s;
+                if (cs_j == 128) {               // slab-major tiled layout: one contiguous copy
+                    if (lane == 0) {
+                        mbar_expect_tx(pl.bar_full + 8u * st, (uint32_t)ncols * 128u);
+                        bulk_g2s(pl.stage(st), src, (uint32_t)ncols * 128u, pl.bar_full + 8u * st);
+                    }
+                } else {                          // column-major layout: one 128-byte copy per column
+                    if (lane == 0) mbar_expect_tx(pl.bar_full + 8u * st, (uint32_t)ncols * 128u);
+                    __syncwarp();
+                    for (int c = lane; c < ncols; c += 32)
+                        bulk_g2s(pl.stage(st) + 128u * c, src + (int64_t)c * cs_j, 128u, pl.bar_full + 8u * st);
                 }
-            } else {                          // column-major layout: one 128-byte copy per column
-                if (lane == 0) mbar_expect_tx(pl.bar_full + 8u * st, (uint32_t)ncols * 128u);
-                __syncwarp();
-                for (int c = lane; c < ncols; c += 32)
-                    bulk_g2s(pl.stage(st) + 128u * c, src + (int64_t)c * cs_j, 128u, pl.bar_full + 8u * st);
+                if (++st == S) { st = 0; ph ^= 1u; }
             }
-            if (++st == S) { st = 0; ph ^= 1u; }
         }
     } else {
         // ===== consumer warps =====
         const int tid = threadIdx.x;      // 0 .. CW*32-1
+        const int grp = warp / WPG, wg = warp % WPG;
         // per-lane base registers for the 4 bytes of a word: byte 1 gets replaced by the data byte
         uint32_t lb[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t)
             lb[t] = pl.tab + (uint32_t)(t >> 1) * 65536u + (uint32_t)(t & 1) * 128u + 4u * (uint32_t)lane;
-        int st = 0; uint32_t ph = 0;
-        int64_t cur_slab = -1;
-        for (int64_t u = u_beg; u < u_end; ++u) {
-            const int64_t slab = u / n_cblocks, cb = u % n_cblocks;
-            if (slab != cur_slab) {
-                consumer_bar<CW * 32>();      // everyone finished looking up the previous slab's tables
-                lut_build<CW * 32>(pl.tab, v, vbar, n, slab, tid);
-                consumer_bar<CW * 32>();
-                cur_slab = slab;
-            }
-            mbar_wait(pl.bar_full + 8u * st, ph);
-            const uint32_t colbase = pl.stage(st) + (uint32_t)(warp * CPW) * 128u + 4u * (uint32_t)lane;
-            float acc[CPW];
+        constexpr int LPC = 32 / CPW;                 // lanes holding the same column after the butterfly
+        const int col = wg * CPW + lane / LPC;        // column (within a unit) this lane stores
+        const bool writer = (lane & (LPC - 1)) == 0;
+        const uint32_t lane_off = (uint32_t)(wg * CPW) * 128u + 4u * (uint32_t)lane;
+        // this group's position in the stage ring: local unit index i = grp, grp+G, ...
+        int st = grp % S; uint32_t ph = (uint32_t)((grp / S) & 1);
+        int i_next = grp;                             // local index of this group's next unit
+        int i_base = 0;                               // local index of the first unit of the current slab
+        for (int64_t slab = slab_beg; slab <= slab_end; ++slab) {
+            const int cb0 = (slab == slab_beg) ? (int)(u_beg - slab * n_cblocks) : 0;
+            const int cb1 = (slab == slab_end) ? (int)(u_end - slab * n_cblocks) : ncb;
+            consumer_bar<CW * 32>();      // everyone finished looking up the previous slab's tables
+            lut_build<CW * 32>(pl.tab, v, vbar, n, slab, tid);
+            consumer_bar<CW * 32>();
+            float* __restrict__ outp = part + slab * p + col;
+            const int i_end = i_base + (cb1 - cb0);
+            for (; i_next < i_end; i_next += G) {
+                const int cb = cb0 + (i_next - i_base);
+                mbar_wait(pl.bar_full + 8u * st, ph);
+                const uint32_t colbase = pl.stage(st) + lane_off;
+                float acc[CPW];
 #pragma unroll
-            for (int c = 0; c < CPW; ++c) {
-                const uint32_t w = lds_u32(colbase + 128u * c);
-                const float t0 = lds_f32(__byte_perm(w, lb[0], 0x7604));
-                const float t1 = lds_f32(__byte_perm(w, lb[1], 0x7614));
-                const float t2 = lds_f32(__byte_perm(w, lb[2], 0x7624));
-                const float t3 = lds_f32(__byte_perm(w, lb[3], 0x7634));
-                acc[c] = (t0 + t1) + (t2 + t3);
-            }
-            // the stage's bytes are now in registers: hand the slot back to the producer
-            __syncwarp();
-            if (lane == 0) mbar_arrive(pl.bar_empty + 8u * st);
-            // butterfly: CPW column sums per lane -> one per lane; lane bits 4,3,.. select the column
-            int o = 16;
-#pragma unroll
-            for (int h = CPW / 2; h >= 1; h >>= 1, o >>= 1) {
-                const bool upper = (lane & o) != 0;
-#pragma unroll
-                for (int c = 0; c < h; ++c) {
-                    const float send = upper ? acc[c] : acc[c + h];
-                    const float keep = upper ? acc[c + h] : acc[c];
-                    acc[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                for (int c = 0; c < CPW; ++c) {
+                    const uint32_t w = lds_u32(colbase + 128u * c);
+                    const float t0 = lds_f32(__byte_perm(w, lb[0], 0x7604));
+                    const float t1 = lds_f32(__byte_perm(w, lb[1], 0x7614));
+                    const float t2 = lds_f32(__byte_perm(w, lb[2], 0x7624));
+                    const float t3 = lds_f32(__byte_perm(w, lb[3], 0x7634));
+                    acc[c] = (t0 + t1) + (t2 + t3);
                 }
-            }
+                // the stage's bytes are now in registers: hand the slot back to the producer
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pl.bar_empty + 8u * st);
+                // butterfly: CPW column sums per lane -> one per lane; the high lane bits select the column
+                int o = 16;
 #pragma unroll
-            for (int oo = 16 / CPW; oo >= 1; oo >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], oo);
-            constexpr int LPC = 32 / CPW;          // lanes per column after the butterfly
-            const int col = lane / LPC;
-            const int64_t j = cb * LUT_STAGE_COLS + warp * CPW + col;
-            if ((lane & (LPC - 1)) == 0 && j < p) part[slab * p + j] = acc[0];
-            if (++st == S) { st = 0; ph ^= 1u; }
+                for (int h = CPW / 2; h >= 1; h >>= 1, o >>= 1) {
+                    const bool upper = (lane & o) != 0;
+#pragma unroll
+                    for (int c = 0; c < h; ++c) {
+                        const float send = upper ? acc[c] : acc[c + h];
+                        const float keep = upper ? acc[c + h] : acc[c];
+                        acc[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                    }
+                }
+#pragma unroll
+                for (int oo = 16 / CPW; oo >= 1; oo >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], oo);
+                const int jj = cb * LUT_STAGE_COLS + col;
+                if (writer && jj < (int)p) outp[cb * LUT_STAGE_COLS] = acc[0];
+                st += G;
+                if (st >= S) { st -= S; ph ^= 1u; }
+            }
+            i_base = i_end;
         }
     }
 }
@@ -255,10 +274,12 @@ void sweep_fast_partials(const ihtb_geno* g, const double* d_v, double vbar, flo
                          cudaStream_t s) {
     static int cw = 0;
     if (!cw) {
-        IHTB_CUDA(cudaFuncSetAttribute(k_sweep_lut<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES));
-        IHTB_CUDA(cudaFuncSetAttribute(k_sweep_lut<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES));
-        const char* e = getenv("IHTB_LUT_WARPS");
-        cw = (e && atoi(e) == 8) ? 8 : 16;
+        IHTB_CUDA(cudaFuncSetAttribute(k_sweep_lut<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES));
+        IHTB_CUDA(cudaFuncSetAttribute(k_sweep_lut<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES));
+        IHTB_CUDA(cudaFuncSetAttribute(k_sweep_lut<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES));
+        const char* e = getenv("IHTB_LUT_WARPS");       // tuning knob: 8 = <8,1>, 16 = <16,1>, default <16,2>
+        cw = e ? atoi(e) : 162;
+        if (cw != 8 && cw != 16) cw = 162;
     }
     const int64_t n_slabs = sweep_fast_num_slabs(g);
     *n_slabs_out = n_slabs;
@@ -266,12 +287,16 @@ void sweep_fast_partials(const ihtb_geno* g, const double* d_v, double vbar, flo
     int64_t units = n_slabs * n_cblocks;
     int grid = g->sm_count;
     if (units < grid) grid = (int)units;
+    IHTB_CHECK(g->p < (int64_t(1) << 31) - 256, IHTB_EDIM, "more than 2^31 SNP columns on one GPU");
     if (cw == 8) {
-        IHTB_LAUNCH(k_sweep_lut<8>, grid, 9 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n, n_slabs,
-                    d_v, vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
+        IHTB_LAUNCH((k_sweep_lut<8, 1>), grid, 9 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n,
+                    n_slabs, d_v, vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
+    } else if (cw == 16) {
+        IHTB_LAUNCH((k_sweep_lut<16, 1>), grid, 17 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n,
+                    n_slabs, d_v, vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
     } else {
-        IHTB_LAUNCH(k_sweep_lut<16>, grid, 17 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n, n_slabs,
-                    d_v, vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
+        IHTB_LAUNCH((k_sweep_lut<16, 2>), grid, 17 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n,
+                    n_slabs, d_v, vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
     }
 }
 
