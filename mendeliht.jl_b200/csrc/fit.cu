@@ -18,6 +18,7 @@
 #include <chrono>
 #include <cmath>
 #include <memory>
+#include <mutex>
 #include <unordered_map>
 
 namespace ihtb {
@@ -38,6 +39,7 @@ static const double kExactBound = 1e-13;
 
 struct ihtb_fit {
     const ihtb_geno* g = nullptr;
+    int device = 0;
     int64_t n = 0, p = 0, q = 0;
     ihtb_cfg cfg{};
     cudaStream_t s = nullptr;
@@ -92,12 +94,6 @@ struct ihtb_fit {
     void readback_scal(int nv) {
         IHTB_CUDA(cudaMemcpyAsync(h_scal.p, d_scal.p, nv * sizeof(double), cudaMemcpyDeviceToHost, s));
         sync();
-        if (sweep_pending) {
-            float ms = 0.f;
-            IHTB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-            sweep_ms_total += ms;
-            sweep_pending = false;
-        }
     }
     template <typename T>
     void upload(T* dst, const T* src, size_t count) {
@@ -138,8 +134,7 @@ struct ihtb_fit {
         if (need.empty()) return;
         IHTB_CHECK((int64_t)need.size() <= (int64_t)d_cols.n, IHTB_ENUMERIC, "too many columns to re-score");
         upload(d_cols.p, need.data(), need.size());
-        upload(d_vbar.p, &rbar, 1);
-        xt_gather(g, d_cols.p, (int64_t)need.size(), d_r.p, 1, d_vbar.p, d_gout.p, s);
+        xt_gather(g, d_cols.p, (int64_t)need.size(), d_r.p, 1, d_vbar.p, d_gout.p, s);   // d_vbar = mean(r), set by score
         IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_gout.p, need.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
         sync();
         for (size_t t = 0; t < need.size(); ++t) df_exact[need[t]] = h_gout.p[t];
@@ -147,22 +142,31 @@ struct ihtb_fit {
     }
 
     // ---- score! : r, df2 = Z'r, df = X'r (src/utilities.jl:126-135) ------------------------------
+    // One host round trip: the sweep and the exact re-scoring of the current support are enqueued right behind the
+    // residual kernel (the mean of r stays on the device), and all scalars come back with the gather results.
     void score_and_sweep() {
-        glm_score(glm, s);
-        readback_scal(2 + (int)q);
+        glm_score(glm, s);                                   // scal: sum r, sum |r|, df2[q]
+        glm_mean_from_sum(glm, d_vbar.p, s);                 // d_vbar[0] = scal[0] / n
+        IHTB_CUDA(cudaMemcpyAsync(h_scal.p, d_scal.p, (2 + q) * sizeof(double), cudaMemcpyDeviceToHost, s));
+        IHTB_CUDA(cudaEventRecord(ev0, s));
+        sweep_xt_v_with_means(g, d_r.p, d_vbar.p, 1, d_dfa.p, cfg.sweep_mode, s, sweep_scratch, nullptr);
+        IHTB_CUDA(cudaEventRecord(ev1, s));
+        ++n_sweeps;
+        df_exact.clear();
+        df_sparse = false;
+        if (!idx.empty()) {
+            exact_df(idx);                                   // syncs the stream
+        } else {
+            sync();
+        }
+        float ms = 0.f;
+        IHTB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        sweep_ms_total += ms;
         double rsum = h_scal.p[0], rl1 = h_scal.p[1];
         for (int64_t l = 0; l < q; ++l) df2[l] = h_scal.p[2 + l];
         rbar = rsum / (double)n;
         double ul1 = rl1 + (double)n * std::fabs(rbar);    // >= ||r - rbar||_1
         bound = (cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound) * ul1;
-        IHTB_CUDA(cudaEventRecord(ev0, s));
-        sweep_xt_v_with_means(g, d_r.p, &rbar, 1, d_dfa.p, cfg.sweep_mode, s, sweep_scratch, nullptr);
-        IHTB_CUDA(cudaEventRecord(ev1, s));
-        sweep_pending = true;
-        ++n_sweeps;
-        df_exact.clear();
-        df_sparse = false;
-        exact_df(idx);
     }
 
     double df_at(int64_t j) const {
@@ -455,6 +459,58 @@ struct ihtb_fit {
 
 extern "C" {
 
+// Workspaces (device buffers, pinned buffers, stream, events) are expensive to create (~200 ms of cudaMalloc /
+// cudaMallocHost / cudaFree at n=50k, p=500k), so destroyed fits are parked here and re-bound by the next
+// ihtb_fit_create with the same shape on the same device.
+static std::mutex g_cache_mu;
+static std::vector<ihtb_fit*> g_cache;
+static const size_t kCacheMax = 4;
+
+static ihtb_fit* cache_take(int device, int64_t n, int64_t p, int64_t q, int cap) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (size_t i = 0; i < g_cache.size(); ++i) {
+        ihtb_fit* f = g_cache[i];
+        if (f->device == device && f->n == n && f->p == p && f->q == q && f->cap == cap) {
+            g_cache.erase(g_cache.begin() + i);
+            return f;
+        }
+    }
+    return nullptr;
+}
+
+// (C linkage, internal: called by ihtb_geno_destroy)
+void ihtb_internal_fit_cache_clear(int device) {
+    std::vector<ihtb_fit*> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (size_t i = 0; i < g_cache.size();) {
+            if (device < 0 || g_cache[i]->device == device) { drop.push_back(g_cache[i]); g_cache.erase(g_cache.begin() + i); }
+            else ++i;
+        }
+    }
+    for (ihtb_fit* f : drop) { cudaSetDevice(f->device); delete f; }
+}
+
+static ihtb_fit* fit_allocate(const ihtb_geno* g, int64_t q, int cap) {
+    std::unique_ptr<ihtb_fit> f(new ihtb_fit());
+    int64_t n = g->n, p = g->p;
+    f->device = g->device; f->n = n; f->p = p; f->q = q; f->cap = cap;
+    IHTB_CUDA(cudaStreamCreateWithFlags(&f->s, cudaStreamNonBlocking));
+    IHTB_CUDA(cudaEventCreate(&f->ev0));
+    IHTB_CUDA(cudaEventCreate(&f->ev1));
+    f->d_y.alloc(n); f->d_z.alloc(n * q); f->d_w.alloc(n); f->d_xb.alloc(n); f->d_zc.alloc(n); f->d_mu.alloc(n);
+    f->d_r.alloc(n); f->d_xs.alloc(n); f->d_dfa.alloc(p); f->d_b0d.alloc(p); f->d_mask.alloc(n);
+    f->d_part.alloc((size_t)GLM_MAX_BLOCKS * (2 + q)); f->d_scal.alloc(2 + q + 8); f->d_small.alloc(2 * q);
+    size_t cols_cap = 2 * (size_t)cap + 64;
+    f->d_coef.alloc(cols_cap); f->d_gout.alloc(cols_cap); f->d_vbar.alloc(1); f->d_sval.alloc(cols_cap);
+    f->d_idx.alloc(cols_cap); f->d_cols.alloc(cols_cap); f->d_sidx.alloc(cols_cap);
+    f->d_keyL.alloc(p); f->d_keyU.alloc(p); f->d_hist.alloc(2048); f->d_sel.alloc(2 + cap);
+    f->h_scal.alloc(2 + q + 8); f->h_gout.alloc(cols_cap); f->h_sel.alloc(2 + cap);
+    f->sweep_scratch = sweep_scratch_create();
+    f->d_b0d.zero(f->s); f->d_hist.zero(f->s);
+    return f.release();
+}
+
 int32_t ihtb_fit_create(const ihtb_geno* g, const double* y, const double* z, int64_t q, const uint8_t* zkeep,
                         const ihtb_cfg* cfg, ihtb_fit** out) {
     return guard([&] {
@@ -470,29 +526,20 @@ int32_t ihtb_fit_create(const ihtb_geno* g, const double* y, const double* z, in
                    "bad sweep_mode");
         IHTB_CHECK(cfg->k <= g->p, IHTB_EINVAL, "k cannot exceed the number of SNPs");
         IHTB_CUDA(cudaSetDevice(g->device));
-        std::unique_ptr<ihtb_fit> f(new ihtb_fit());
-        f->g = g; f->n = g->n; f->p = g->p; f->q = q; f->cfg = *cfg;
+        int cap = (int)std::max<int64_t>(4096, 4 * cfg->k + 1024);
+        std::unique_ptr<ihtb_fit> f(cache_take(g->device, g->n, g->p, q, cap));
+        if (!f) f.reset(fit_allocate(g, q, cap));
+        int64_t n = g->n, p = g->p;
+        f->g = g; f->cfg = *cfg;
         f->zkeep.assign((size_t)q, 1);
         if (zkeep) for (int64_t l = 0; l < q; ++l) f->zkeep[l] = zkeep[l] ? 1 : 0;
         f->zkeepn = 0;
         for (auto v : f->zkeep) f->zkeepn += v;
-        int64_t n = g->n, p = g->p;
-        f->cap = (int)std::max<int64_t>(4096, 4 * cfg->k + 1024);
-        IHTB_CUDA(cudaStreamCreateWithFlags(&f->s, cudaStreamNonBlocking));
-        IHTB_CUDA(cudaEventCreate(&f->ev0));
-        IHTB_CUDA(cudaEventCreate(&f->ev1));
-        f->d_y.alloc(n); f->d_z.alloc(n * q); f->d_w.alloc(n); f->d_xb.alloc(n); f->d_zc.alloc(n); f->d_mu.alloc(n);
-        f->d_r.alloc(n); f->d_xs.alloc(n); f->d_dfa.alloc(p); f->d_b0d.alloc(p); f->d_mask.alloc(n);
-        f->d_part.alloc((size_t)GLM_MAX_BLOCKS * (2 + q)); f->d_scal.alloc(2 + q + 8); f->d_small.alloc(2 * q);
-        size_t cols_cap = 2 * (size_t)f->cap + 64;
-        f->d_coef.alloc(cols_cap); f->d_gout.alloc(cols_cap); f->d_vbar.alloc(1); f->d_sval.alloc(cols_cap);
-        f->d_idx.alloc(cols_cap); f->d_cols.alloc(cols_cap); f->d_sidx.alloc(cols_cap);
-        f->d_keyL.alloc(p); f->d_keyU.alloc(p); f->d_hist.alloc(2048); f->d_sel.alloc(2 + f->cap);
-        f->h_scal.alloc(2 + q + 8); f->h_gout.alloc(cols_cap); f->h_sel.alloc(2 + f->cap);
-        f->sweep_scratch = sweep_scratch_create();
+        f->inited = false; f->sweep_pending = false;
+        f->n_sweeps = 0; f->n_backtracks = 0; f->sweep_ms_total = 0.0;
         IHTB_CUDA(cudaMemcpyAsync(f->d_y.p, y, n * sizeof(double), cudaMemcpyHostToDevice, f->s));
         IHTB_CUDA(cudaMemcpyAsync(f->d_z.p, z, n * q * sizeof(double), cudaMemcpyHostToDevice, f->s));
-        f->d_b0d.zero(f->s); f->d_hist.zero(f->s); f->d_xb.zero(f->s); f->d_zc.zero(f->s);
+        f->d_xb.zero(f->s); f->d_zc.zero(f->s);
         f->glm = GlmCtx{n, q, f->d_z.p, f->d_y.p, f->d_w.p, f->d_xb.p, f->d_zc.p, f->d_mu.p, f->d_r.p, f->d_part.p,
                         f->d_scal.p, cfg->dist, cfg->link, cfg->nb_r};
         f->tk = TopkCtx{p, f->d_keyL.p, f->d_keyU.p, f->d_hist.p, reinterpret_cast<TopkState*>(f->d_sel.p),
@@ -580,10 +627,15 @@ int32_t ihtb_fit_timer(ihtb_fit* f, int32_t which, double* ms) {
 
 int32_t ihtb_fit_destroy(ihtb_fit* f) {
     return guard([&] {
-        if (f) {
-            cudaSetDevice(f->g->device);
-            delete f;
+        if (!f) return;
+        cudaSetDevice(f->device);
+        cudaStreamSynchronize(f->s);
+        f->g = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_cache_mu);
+            if (g_cache.size() < kCacheMax) { g_cache.push_back(f); return; }
         }
+        delete f;
     });
 }
 

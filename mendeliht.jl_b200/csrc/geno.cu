@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+extern "C" void ihtb_internal_fit_cache_clear(int device);
+
 namespace ihtb {
 
 static thread_local std::string t_last_error;
@@ -151,15 +153,6 @@ __global__ void k_synth(GenoView g, int64_t j0, uint64_t seed, uint32_t miss_thr
     *reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(gv_ptr(g, j, 4 * w))) = out;
 }
 
-__global__ void k_prefix_ptr(const int32_t* __restrict__ nmiss, int64_t p, int64_t* __restrict__ ptr) {
-    // single-thread exclusive scan (p <= a few million; runs once per handle)
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        int64_t acc = 0;
-        for (int64_t j = 0; j < p; ++j) { ptr[j] = acc; acc += nmiss[j]; }
-        ptr[p] = acc;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
@@ -170,9 +163,15 @@ static void finish_handle(ihtb_geno* g) {
     IHTB_LAUNCH(k_col_stats, (unsigned)ceil_div(threads, 256), 256, 0, s, geno_view(g), g->scale, g->mu.p, g->sinv.p,
                 g->nmiss.p);
     g->miss_ptr.alloc(g->p + 1);
-    IHTB_LAUNCH(k_prefix_ptr, 1, 32, 0, s, g->nmiss.p, g->p, g->miss_ptr.p);
     int64_t total = 0;
-    IHTB_CUDA(cudaMemcpy(&total, g->miss_ptr.p + g->p, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    {   // exclusive scan of the per-column missing counts (host: once per handle, p <= a few million)
+        std::vector<int32_t> hn((size_t)g->p);
+        std::vector<int64_t> hp((size_t)g->p + 1);
+        IHTB_CUDA(cudaMemcpy(hn.data(), g->nmiss.p, g->p * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int64_t j = 0; j < g->p; ++j) { hp[j] = total; total += hn[j]; }
+        hp[g->p] = total;
+        IHTB_CUDA(cudaMemcpy(g->miss_ptr.p, hp.data(), (g->p + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
     g->total_missing = total;
     if (total > 0) {
         g->miss_idx.alloc(total);
@@ -395,6 +394,7 @@ int32_t ihtb_geno_destroy(ihtb_geno* g) {
     return guard([&] {
         if (g) {
             cudaSetDevice(g->device);
+            ihtb_internal_fit_cache_clear(g->device);   // parked fit workspaces give their memory back with the matrix
             delete g;
         }
     });

@@ -144,28 +144,37 @@ k_set_weights(int64_t n, const uint8_t* __restrict__ mask, const double* __restr
     if (threadIdx.x == 0) { part[blockIdx.x * 2] = sw; part[blockIdx.x * 2 + 1] = sy; }
 }
 
-// out[v] = sum_b part[b*nv + v], blocks in order (deterministic)
+// out[v] = sum_b part[b*nv + v]: one warp per value, lanes stride over the blocks, fixed shuffle tree (deterministic)
 __global__ void k_finalize(const double* __restrict__ part, int nblocks, int nv, double* __restrict__ out) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
     if (v >= nv) return;
     double a = 0.0;
-    for (int b = 0; b < nblocks; ++b) a += part[b * nv + v];
-    out[v] = a;
+    for (int b = lane; b < nblocks; b += 32) a += part[b * nv + v];
+    a = warp_sum(a);
+    if (lane == 0) out[v] = a;
+}
+
+__global__ void k_mean_from_sum(const double* __restrict__ scal, int64_t n, double* __restrict__ out) {
+    out[0] = scal[0] / (double)n;
 }
 
 // ---- launchers ------------------------------------------------------------------------------------
+void glm_mean_from_sum(GlmCtx& c, double* d_mean, cudaStream_t s) {
+    IHTB_LAUNCH(k_mean_from_sum, 1, 1, 0, s, c.scal, c.n, d_mean);
+}
 void glm_mu(GlmCtx& c, const double* d_c, int add_zc, cudaStream_t s) {
     int grid = glm_grid(c.n);
     IHTB_LAUNCH(k_glm_mu, grid, GLM_THREADS, 0, s, c.n, c.q, c.Z, d_c, c.xb, c.zc, c.mu, c.y, c.w, c.dist, c.link,
                 c.nb_r, add_zc, c.part);
-    IHTB_LAUNCH(k_finalize, 1, 32, 0, s, c.part, grid, 3, c.scal);
+    IHTB_LAUNCH(k_finalize, 1, 96, 0, s, c.part, grid, 3, c.scal);
 }
 void glm_score(GlmCtx& c, cudaStream_t s) {
     int grid = glm_grid(c.n);
     int nv = 2 + (int)c.q;
     IHTB_LAUNCH(k_score, grid, GLM_THREADS, 0, s, c.n, c.q, c.Z, c.xb, c.zc, c.mu, c.y, c.w, c.dist, c.link, c.nb_r,
                 c.r, c.part);
-    IHTB_LAUNCH(k_finalize, (unsigned)ceil_div(nv, 32), 32, 0, s, c.part, grid, nv, c.scal);
+    IHTB_LAUNCH(k_finalize, (unsigned)ceil_div(nv, 4), 128, 0, s, c.part, grid, nv, c.scal);
 }
 void glm_stepsize(GlmCtx& c, const double* d_d2, const double* d_xs, cudaStream_t s) {
     int grid = glm_grid(c.n);
@@ -176,17 +185,17 @@ void glm_stepsize(GlmCtx& c, const double* d_d2, const double* d_xs, cudaStream_
 void glm_sum2(GlmCtx& c, const double* a, const double* b, cudaStream_t s) {
     int grid = glm_grid(c.n);
     IHTB_LAUNCH(k_sum2, grid, GLM_THREADS, 0, s, c.n, a, b, c.part);
-    IHTB_LAUNCH(k_finalize, 1, 32, 0, s, c.part, grid, 2, c.scal);
+    IHTB_LAUNCH(k_finalize, 1, 64, 0, s, c.part, grid, 2, c.scal);
 }
 void glm_ssq2(GlmCtx& c, const double* a, double ma, const double* b, double mb, cudaStream_t s) {
     int grid = glm_grid(c.n);
     IHTB_LAUNCH(k_ssq2, grid, GLM_THREADS, 0, s, c.n, a, ma, b, mb, c.part);
-    IHTB_LAUNCH(k_finalize, 1, 32, 0, s, c.part, grid, 2, c.scal);
+    IHTB_LAUNCH(k_finalize, 1, 64, 0, s, c.part, grid, 2, c.scal);
 }
 void glm_set_weights(GlmCtx& c, const uint8_t* d_mask, cudaStream_t s) {
     int grid = glm_grid(c.n);
     IHTB_LAUNCH(k_set_weights, grid, GLM_THREADS, 0, s, c.n, d_mask, c.y, c.w, c.part);
-    IHTB_LAUNCH(k_finalize, 1, 32, 0, s, c.part, grid, 2, c.scal);
+    IHTB_LAUNCH(k_finalize, 1, 64, 0, s, c.part, grid, 2, c.scal);
 }
 
 }  // namespace ihtb

@@ -108,6 +108,7 @@ struct GlmCtx {
 };
 
 void glm_mu(GlmCtx& c, const double* d_c, int add_zc, cudaStream_t s);        // scal: dev, lp, sum w
+void glm_mean_from_sum(GlmCtx& c, double* d_mean, cudaStream_t s);             // d_mean[0] = scal[0] / n
 void glm_score(GlmCtx& c, cudaStream_t s);                                      // scal: sum r, sum |r|, df2[q]
 void glm_stepsize(GlmCtx& c, const double* d_d2, const double* d_xs, cudaStream_t s);   // scal: denom
 void glm_sum2(GlmCtx& c, const double* a, const double* b, cudaStream_t s);

@@ -85,20 +85,24 @@ void x_support(const ihtb_geno* g, const int64_t* d_idx, int64_t k, const double
 
 // Exact column dots. out[c + t*ncols] = sinv_j * (A + mu_j * (impute ? Mm : -vbar_t * nmiss_j)),
 //   A = sum_{obs i} dos_ij (v_it - vbar_t), Mm = sum_{missing i} (v_it - vbar_t), j = cols[c].
-// One CTA per column, one thread per packed byte per step, fixed-tree reduction (deterministic).
+// grid = (ncols, nsplit): each CTA reduces a contiguous byte range of one column with a fixed tree, a second tiny
+// kernel adds the splits in order (deterministic, no atomics).
+constexpr int XG_MAX_SPLIT = 64;
+
 template <int M>
 __global__ void __launch_bounds__(256)
-k_xt_gather(GenoView gv, const int64_t* __restrict__ cols, int64_t ncols, const double* __restrict__ v,
-            const double* __restrict__ vbar, double* __restrict__ out) {
+k_xt_gather(GenoView gv, const int64_t* __restrict__ cols, int64_t split_bytes, const double* __restrict__ v,
+            const double* __restrict__ vbar, double* __restrict__ part /*[ncols][nsplit][2M]*/) {
     __shared__ double sh[32];
     const int64_t nbytes = gv.nbytes, n = gv.n;
-    const int impute = gv.impute;
-    int64_t c = blockIdx.x;
-    int64_t j = cols[c];
+    const int64_t c = blockIdx.x, sp = blockIdx.y;
+    const int64_t j = cols[c];
+    const int64_t b0 = sp * split_bytes;
+    const int64_t b1 = (b0 + split_bytes < nbytes) ? b0 + split_bytes : nbytes;
     double a[M], mm[M], vb[M];
 #pragma unroll
     for (int t = 0; t < M; ++t) { a[t] = 0.0; mm[t] = 0.0; vb[t] = vbar[t]; }
-    for (int64_t b = threadIdx.x; b < nbytes; b += blockDim.x) {
+    for (int64_t b = b0 + threadIdx.x; b < b1; b += blockDim.x) {
         uint32_t byte = *gv_ptr(gv, j, b);
         if (byte == 0) continue;
 #pragma unroll
@@ -115,23 +119,55 @@ k_xt_gather(GenoView gv, const int64_t* __restrict__ cols, int64_t ncols, const 
             }
         }
     }
-    double m = gv.mu[j], si = gv.sinv[j];
-    double nm = (double)gv.nmiss[j];
+    double* o = part + (c * gridDim.y + sp) * (2 * M);
 #pragma unroll
     for (int t = 0; t < M; ++t) {
         double at = block_sum(a[t], sh);
         double mt = block_sum(mm[t], sh);
-        if (threadIdx.x == 0) {
-            double corr = impute ? mt : __dmul_rn(-vb[t], nm);
-            out[c + (int64_t)t * ncols] = __dmul_rn(si, __dadd_rn(at, __dmul_rn(m, corr)));
-        }
+        if (threadIdx.x == 0) { o[2 * t] = at; o[2 * t + 1] = mt; }
     }
+}
+
+template <int M>
+__global__ void k_xt_gather_fin(GenoView gv, const int64_t* __restrict__ cols, int64_t ncols, int nsplit,
+                                const double* __restrict__ vbar, const double* __restrict__ part,
+                                double* __restrict__ out) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= ncols * M) return;
+    int64_t c = e / M;
+    int t = (int)(e % M);
+    double at = 0.0, mt = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) {
+        const double* o = part + (c * nsplit + sp) * (2 * M);
+        at = __dadd_rn(at, o[2 * t]);
+        mt = __dadd_rn(mt, o[2 * t + 1]);
+    }
+    int64_t j = cols[c];
+    double corr = gv.impute ? mt : __dmul_rn(-vbar[t], (double)gv.nmiss[j]);
+    out[c + (int64_t)t * ncols] = __dmul_rn(gv.sinv[j], __dadd_rn(at, __dmul_rn(gv.mu[j], corr)));
+}
+
+static DBuf<double>& gather_scratch(int device) {
+    static thread_local DBuf<double> buf[16];
+    return buf[device & 15];
 }
 
 template <int M>
 static void launch_xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t ncols, const double* d_v,
                              const double* d_vbar, double* d_out, cudaStream_t s) {
-    IHTB_LAUNCH((k_xt_gather<M>), (unsigned)ncols, 256, 0, s, geno_view(g), d_cols, ncols, d_v, d_vbar, d_out);
+    int64_t split_bytes = ceil_div(ceil_div(g->nbytes, XG_MAX_SPLIT), 256) * 256;
+    if (split_bytes < 1024) split_bytes = 1024;
+    int nsplit = (int)ceil_div(g->nbytes, split_bytes);
+    DBuf<double>& sc = gather_scratch(g->device);
+    size_t need = (size_t)ncols * nsplit * 2 * M;
+    if (sc.n < need) {
+        IHTB_CUDA(cudaStreamSynchronize(s));
+        sc.alloc(need < 65536 ? 65536 : need);
+    }
+    dim3 grid((unsigned)ncols, (unsigned)nsplit);
+    IHTB_LAUNCH((k_xt_gather<M>), grid, 256, 0, s, geno_view(g), d_cols, split_bytes, d_v, d_vbar, sc.p);
+    IHTB_LAUNCH((k_xt_gather_fin<M>), (unsigned)ceil_div(ncols * M, 128), 128, 0, s, geno_view(g), d_cols, ncols,
+                nsplit, d_vbar, sc.p, d_out);
 }
 
 void xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t ncols, const double* d_v, int64_t m,

@@ -14,7 +14,7 @@
 
 namespace ihtb {
 
-void sweep_fast_partials(const ihtb_geno* g, const double* d_v, double vbar, float* d_part, int64_t* n_slabs,
+void sweep_fast_partials(const ihtb_geno* g, const double* d_v, const double* d_vbar, float* d_part, int64_t* n_slabs,
                          cudaStream_t s);
 int64_t sweep_fast_num_slabs(const ihtb_geno* g);
 
@@ -23,7 +23,8 @@ constexpr int EX_CB = 8;                 // columns per register tile
 constexpr int EX_COLS_PER_CTA = 512;
 
 __global__ void __launch_bounds__(EX_THREADS)
-k_sweep_exact(GenoView gv, const double* __restrict__ v, double vbar, double* __restrict__ part /*[n_slabs][p]*/) {
+k_sweep_exact(GenoView gv, const double* __restrict__ v, const double* __restrict__ vbar_p, double* __restrict__ part /*[n_slabs][p]*/) {
+    const double vbar = *vbar_p;
     __shared__ double red[EX_THREADS / 32][EX_CB];
     const int64_t p = gv.p, n = gv.n;
     const int64_t words = gv.stride >> 2;
@@ -79,10 +80,12 @@ template <typename T>
 __global__ void k_sweep_epilogue(const T* __restrict__ part, int64_t n_slabs, int64_t p,
                                  const double* __restrict__ mu, const double* __restrict__ sinv,
                                  const int32_t* __restrict__ nmiss, const int64_t* __restrict__ miss_ptr,
-                                 const int32_t* __restrict__ miss_idx, const double* __restrict__ v, double vbar,
+                                 const int32_t* __restrict__ miss_idx, const double* __restrict__ v,
+                                 const double* __restrict__ vbar_p,
                                  int impute, double* __restrict__ out) {
     int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (j >= p) return;
+    const double vbar = *vbar_p;
     double a = 0.0;
     for (int64_t s = 0; s < n_slabs; ++s) a += (double)part[s * p + j];
     double corr = 0.0;
@@ -97,13 +100,13 @@ __global__ void k_sweep_epilogue(const T* __restrict__ part, int64_t n_slabs, in
     out[j] = sinv[j] * (a + mu[j] * corr);
 }
 
-__global__ void k_vec_sum(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
+__global__ void k_vec_mean(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
     // single block, fixed order: mean of a right-hand side (only used by the stand-alone ihtb_xt_v entry point)
     __shared__ double sh[32];
     double a = 0.0;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) a += v[i];
     a = block_sum(a, sh);
-    if (threadIdx.x == 0) out[0] = a;
+    if (threadIdx.x == 0) out[0] = a / (double)n;
 }
 
 struct SweepScratch {
@@ -111,8 +114,9 @@ struct SweepScratch {
     DBuf<float> part32;
 };
 
-// dV: n x m column-major device array; dOut: p x m. vbar_host[t] = mean of column t (host values).
-void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* vbar_host, int64_t m, double* dOut,
+// dV: n x m column-major device array; dOut: p x m. d_vbar[t] = mean of column t (DEVICE array, so a sweep can be
+// enqueued right behind the kernel that produced the mean without a host round trip).
+void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* d_vbar, int64_t m, double* dOut,
                            int mode, cudaStream_t s, void* scratch_any, float* sweep_ms) {
     SweepScratch local;
     SweepScratch* sc = scratch_any ? reinterpret_cast<SweepScratch*>(scratch_any) : &local;
@@ -129,16 +133,16 @@ void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* v
             int64_t n_slabs = ceil_div(words, EX_THREADS);
             if (sc->part64.n < (size_t)(n_slabs * g->p)) sc->part64.alloc((size_t)(n_slabs * g->p));
             dim3 grid((unsigned)ceil_div(g->p, EX_COLS_PER_CTA), (unsigned)n_slabs);
-            IHTB_LAUNCH(k_sweep_exact, grid, EX_THREADS, 0, s, geno_view(g), v, vbar_host[t], sc->part64.p);
+            IHTB_LAUNCH(k_sweep_exact, grid, EX_THREADS, 0, s, geno_view(g), v, d_vbar + t, sc->part64.p);
             IHTB_LAUNCH((k_sweep_epilogue<double>), (unsigned)ceil_div(g->p, 256), 256, 0, s, sc->part64.p, n_slabs,
-                        g->p, g->mu.p, g->sinv.p, g->nmiss.p, g->miss_ptr.p, g->miss_idx.p, v, vbar_host[t],
+                        g->p, g->mu.p, g->sinv.p, g->nmiss.p, g->miss_ptr.p, g->miss_idx.p, v, d_vbar + t,
                         g->impute, out);
         } else {
             int64_t n_slabs = sweep_fast_num_slabs(g);
             if (sc->part32.n < (size_t)(n_slabs * g->p)) sc->part32.alloc((size_t)(n_slabs * g->p));
-            sweep_fast_partials(g, v, vbar_host[t], sc->part32.p, &n_slabs, s);
+            sweep_fast_partials(g, v, d_vbar + t, sc->part32.p, &n_slabs, s);
             IHTB_LAUNCH((k_sweep_epilogue<float>), (unsigned)ceil_div(g->p, 256), 256, 0, s, sc->part32.p, n_slabs,
-                        g->p, g->mu.p, g->sinv.p, g->nmiss.p, g->miss_ptr.p, g->miss_idx.p, v, vbar_host[t],
+                        g->p, g->mu.p, g->sinv.p, g->nmiss.p, g->miss_ptr.p, g->miss_idx.p, v, d_vbar + t,
                         g->impute, out);
         }
     }
@@ -162,23 +166,18 @@ extern "C" int32_t ihtb_xt_v(const ihtb_geno* g, const double* V, int64_t m, dou
         IHTB_CHECK(g && V && out && m >= 1, IHTB_EINVAL, "bad argument");
         IHTB_CHECK(sweep_mode == IHTB_SWEEP_FAST || sweep_mode == IHTB_SWEEP_EXACT, IHTB_EINVAL, "bad sweep_mode");
         IHTB_CUDA(cudaSetDevice(g->device));
-        DBuf<double> dV((size_t)(g->n * m)), dOut((size_t)(g->p * m)), dsum(1);
+        DBuf<double> dV((size_t)(g->n * m)), dOut((size_t)(g->p * m)), dmean((size_t)m);
         IHTB_CUDA(cudaMemcpy(dV.p, V, g->n * m * sizeof(double), cudaMemcpyHostToDevice));
-        std::vector<double> vbar((size_t)m);
-        for (int64_t t = 0; t < m; ++t) {
-            IHTB_LAUNCH(k_vec_sum, 1, 1024, 0, 0, dV.p + t * g->n, g->n, dsum.p);
-            double sum = 0.0;
-            IHTB_CUDA(cudaMemcpy(&sum, dsum.p, sizeof(double), cudaMemcpyDeviceToHost));
-            vbar[t] = sum / (double)g->n;
-        }
-        sweep_xt_v_with_means(g, dV.p, vbar.data(), m, dOut.p, sweep_mode, 0, nullptr, nullptr);
+        for (int64_t t = 0; t < m; ++t)
+            IHTB_LAUNCH(k_vec_mean, 1, 1024, 0, 0, dV.p + t * g->n, g->n, dmean.p + t);
+        sweep_xt_v_with_means(g, dV.p, dmean.p, m, dOut.p, sweep_mode, 0, nullptr, nullptr);
         IHTB_CUDA(cudaMemcpy(out, dOut.p, g->p * m * sizeof(double), cudaMemcpyDeviceToHost));
     });
 }
 
 // ---- measurement hooks (bench.py): sweep timed alone on a device-resident vector, CUDA events on its stream ------
 namespace ihtb {
-void sweep_fast_kernel_only(const ihtb_geno* g, const double* d_v, double vbar, float* d_part, cudaStream_t s);
+void sweep_fast_kernel_only(const ihtb_geno* g, const double* d_v, const double* d_vbar, float* d_part, cudaStream_t s);
 __global__ void k_fill_vec(double* v, int64_t n, uint64_t seed) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -197,16 +196,17 @@ extern "C" int32_t ihtb_sweep_bench(const ihtb_geno* g, int32_t sweep_mode, int3
         IHTB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         DBuf<double> dV((size_t)g->n), dOut((size_t)g->p);
         IHTB_LAUNCH(k_fill_vec, (unsigned)ceil_div(g->n, 256), 256, 0, s, dV.p, g->n, 12345ull);
-        double vbar = 0.0;
+        DBuf<double> dmean(1);
+        IHTB_LAUNCH(k_vec_mean, 1, 1024, 0, s, dV.p, g->n, dmean.p);
         SweepScratch sc;
         cudaEvent_t e0, e1;
         IHTB_CUDA(cudaEventCreate(&e0)); IHTB_CUDA(cudaEventCreate(&e1));
         for (int i = 0; i < warmup; ++i)
-            sweep_xt_v_with_means(g, dV.p, &vbar, 1, dOut.p, sweep_mode, s, &sc, nullptr);
+            sweep_xt_v_with_means(g, dV.p, dmean.p, 1, dOut.p, sweep_mode, s, &sc, nullptr);
         // (a) whole sweep = partial-sum kernel + epilogue
         IHTB_CUDA(cudaEventRecord(e0, s));
         for (int i = 0; i < reps; ++i)
-            sweep_xt_v_with_means(g, dV.p, &vbar, 1, dOut.p, sweep_mode, s, &sc, nullptr);
+            sweep_xt_v_with_means(g, dV.p, dmean.p, 1, dOut.p, sweep_mode, s, &sc, nullptr);
         IHTB_CUDA(cudaEventRecord(e1, s));
         IHTB_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;
@@ -217,7 +217,7 @@ extern "C" int32_t ihtb_sweep_bench(const ihtb_geno* g, int32_t sweep_mode, int3
             *ms_kernel = 0.0;
             if (sweep_mode == IHTB_SWEEP_FAST) {
                 IHTB_CUDA(cudaEventRecord(e0, s));
-                for (int i = 0; i < reps; ++i) sweep_fast_kernel_only(g, dV.p, vbar, sc.part32.p, s);
+                for (int i = 0; i < reps; ++i) sweep_fast_kernel_only(g, dV.p, dmean.p, sc.part32.p, s);
                 IHTB_CUDA(cudaEventRecord(e1, s));
                 IHTB_CUDA(cudaEventSynchronize(e1));
                 IHTB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
@@ -228,7 +228,7 @@ extern "C" int32_t ihtb_sweep_bench(const ihtb_geno* g, int32_t sweep_mode, int3
                 dim3 grid((unsigned)ceil_div(g->p, EX_COLS_PER_CTA), (unsigned)n_slabs);
                 IHTB_CUDA(cudaEventRecord(e0, s));
                 for (int i = 0; i < reps; ++i)
-                    IHTB_LAUNCH(k_sweep_exact, grid, EX_THREADS, 0, s, geno_view(g), dV.p, vbar, sc.part64.p);
+                    IHTB_LAUNCH(k_sweep_exact, grid, EX_THREADS, 0, s, geno_view(g), dV.p, dmean.p, sc.part64.p);
                 IHTB_CUDA(cudaEventRecord(e1, s));
                 IHTB_CUDA(cudaEventSynchronize(e1));
                 IHTB_CUDA(cudaEventElapsedTime(&ms, e0, e1));

@@ -144,7 +144,9 @@ __device__ __forceinline__ void lut_build(uint32_t tab, const double* __restrict
 template <int CW, int G>
 __global__ void __launch_bounds__((CW + 1) * 32, 1)
 k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t p, int64_t n, int64_t n_slabs,
-            const double* __restrict__ v, double vbar, float* __restrict__ part, uint32_t dyn_bytes) {
+            const double* __restrict__ v, const double* __restrict__ vbar_p, float* __restrict__ part,
+            uint32_t dyn_bytes) {
+    const double vbar = *vbar_p;
     constexpr int WPG = CW / G;                      // warps per group
     constexpr int CPW = LUT_STAGE_COLS / WPG;        // columns per warp per unit
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -260,17 +262,17 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
     }
 }
 
-void sweep_fast_partials(const ihtb_geno* g, const double* d_v, double vbar, float* d_part, int64_t* n_slabs_out,
+void sweep_fast_partials(const ihtb_geno* g, const double* d_v, const double* d_vbar, float* d_part, int64_t* n_slabs_out,
                          cudaStream_t s);
 
 int64_t sweep_fast_num_slabs(const ihtb_geno* g) { return g->stride / 128; }
 
-void sweep_fast_kernel_only(const ihtb_geno* g, const double* d_v, double vbar, float* d_part, cudaStream_t s) {
+void sweep_fast_kernel_only(const ihtb_geno* g, const double* d_v, const double* d_vbar, float* d_part, cudaStream_t s) {
     int64_t ns = 0;
-    sweep_fast_partials(g, d_v, vbar, d_part, &ns, s);
+    sweep_fast_partials(g, d_v, d_vbar, d_part, &ns, s);
 }
 
-void sweep_fast_partials(const ihtb_geno* g, const double* d_v, double vbar, float* d_part, int64_t* n_slabs_out,
+void sweep_fast_partials(const ihtb_geno* g, const double* d_v, const double* d_vbar, float* d_part, int64_t* n_slabs_out,
                          cudaStream_t s) {
     static int cw = 0;
     if (!cw) {
@@ -290,13 +292,13 @@ void sweep_fast_partials(const ihtb_geno* g, const double* d_v, double vbar, flo
     IHTB_CHECK(g->p < (int64_t(1) << 31) - 256, IHTB_EDIM, "more than 2^31 SNP columns on one GPU");
     if (cw == 8) {
         IHTB_LAUNCH((k_sweep_lut<8, 1>), grid, 9 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n,
-                    n_slabs, d_v, vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
+                    n_slabs, d_v, d_vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
     } else if (cw == 16) {
         IHTB_LAUNCH((k_sweep_lut<16, 1>), grid, 17 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n,
-                    n_slabs, d_v, vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
+                    n_slabs, d_v, d_vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
     } else {
         IHTB_LAUNCH((k_sweep_lut<16, 2>), grid, 17 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n,
-                    n_slabs, d_v, vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
+                    n_slabs, d_v, d_vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
     }
 }
 
