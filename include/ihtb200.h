@@ -120,6 +120,12 @@ int32_t ihtb_geno_destroy(ihtb_geno* g);
 /* y[n]; z is n x q column-major with the intercept in column 0; zkeep[q] (0/1) or NULL for all kept. */
 int32_t ihtb_fit_create(const ihtb_geno* g, const double* y, const double* z, int64_t q, const uint8_t* zkeep,
                         const ihtb_cfg* cfg, ihtb_fit** out);
+/* SNP-sharded fit, one process per GPU: this rank's genotype handle holds global columns [j0, j0+p_local) of a
+ * p_global-column matrix (j0 as given to ihtb_geno_create_synthetic / ihtb_geno_set_offset).  y, z and every n-vector
+ * are replicated; partial X*beta is all-reduced (NCCL) and per-shard top-k candidates are all-gathered, so every rank
+ * returns the same global model.  beta in ihtb_fit_get has p_global entries.  comm == NULL: plain single-GPU fit. */
+int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_global, const double* y,
+                                const double* z, int64_t q, const uint8_t* zkeep, const ihtb_cfg* cfg, ihtb_fit** out);
 int32_t ihtb_fit_set_k(ihtb_fit* f, int64_t k);                       /* v.k = sparsity (src/cross_validation.jl:110) */
 int32_t ihtb_fit_init(ihtb_fit* f, const uint8_t* train_mask);         /* init_iht_indices!; NULL = all samples */
 int32_t ihtb_fit_run(ihtb_fit* f, ihtb_result* result, ihtb_iter_trace* trace, int64_t trace_cap);   /* fit_iht! + pve */
@@ -129,6 +135,13 @@ int32_t ihtb_fit_predict(ihtb_fit* f, const uint8_t* test_mask, double* deviance
 /* CUDA-event stopwatch on the fit's stream: which=0 start, which=1 stop (elapsed device milliseconds in *ms) */
 int32_t ihtb_fit_timer(ihtb_fit* f, int32_t which, double* ms);
 int32_t ihtb_fit_destroy(ihtb_fit* f);
+
+/* ---- multi-GPU plumbing (NCCL over NVLink; rendezvous of the 128-byte id is the host's job, e.g. torch.distributed) ---- */
+/* nccl_lib_path may be NULL: $IHTB_NCCL_LIB, then libnccl.so.2 are tried (dlopen at run time, no link-time dependency) */
+int32_t ihtb_comm_unique_id(const char* nccl_lib_path, uint8_t* out128);
+int32_t ihtb_comm_create(const char* nccl_lib_path, const uint8_t* id128, int32_t rank, int32_t nranks, ihtb_comm** out);
+int32_t ihtb_comm_destroy(ihtb_comm* c);
+int32_t ihtb_geno_set_offset(ihtb_geno* g, int64_t j0);   /* global index of local column 0 for host-uploaded shards */
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,7 @@ SIGNATURES = {
     "ihtb_sweep_bench": [_p, C.c_int32, C.c_int32, C.c_int32, _f64, _f64],
     "ihtb_geno_destroy": [_p],
     "ihtb_fit_create": [_p, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), _pp],
+    "ihtb_fit_create_sharded": [_p, _p, C.c_int64, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), _pp],
     "ihtb_fit_set_k": [_p, C.c_int64],
     "ihtb_fit_init": [_p, _u8],
     "ihtb_fit_run": [_p, C.POINTER(Result), C.POINTER(IterTrace), C.c_int64],
@@ -90,6 +91,10 @@ SIGNATURES = {
     "ihtb_fit_predict": [_p, _u8, _f64],
     "ihtb_fit_timer": [_p, C.c_int32, _f64],
     "ihtb_fit_destroy": [_p],
+    "ihtb_comm_unique_id": [C.c_char_p, _u8],
+    "ihtb_comm_create": [C.c_char_p, _u8, C.c_int32, C.c_int32, _pp],
+    "ihtb_comm_destroy": [_p],
+    "ihtb_geno_set_offset": [_p, C.c_int64],
 }
 
 _lib = None

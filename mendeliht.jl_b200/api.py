@@ -152,7 +152,7 @@ class IHTVariable:
     """`IHTVariable` (src/data_structures.jl:4-43): one fit's device workspace."""
 
     def __init__(self, x: B200SnpLinAlg, z, y, k, d=NORMAL, l="IdentityLink", zkeep=None, nb_r=1.0, tol=1e-4,
-                 max_iter=200, min_iter=5, max_step=3, sweep_mode=_lib.SWEEP_FAST):
+                 max_iter=200, min_iter=5, max_step=3, sweep_mode=_lib.SWEEP_FAST, comm=None, p_global=None):
         y = f64(y)
         z = np.asarray(z, dtype=np.float64)
         if z.ndim == 1:
@@ -167,14 +167,17 @@ class IHTVariable:
             zk = np.ascontiguousarray(zkeep, dtype=np.uint8)
             if zk.shape[0] != q:
                 raise _lib.DimensionMismatch(_lib.IHTB_EDIM, f"zkeep must have length {q} but was {zk.shape[0]}")
-        self.x, self.n, self.p, self.q, self.d = x, n, x.p, q, d
+        self.comm = comm
+        self.p_global = int(p_global) if (comm is not None and p_global is not None) else x.p
+        self.x, self.n, self.p, self.q, self.d = x, n, self.p_global, q, d
         self.cfg = Cfg(DIST_ID[d], LINK_ID[l], int(k), float(nb_r), float(tol), int(max_iter), int(min_iter),
                        int(max_step), int(sweep_mode))
         zf = np.asfortranarray(z)
         self._h = C.c_void_p()
-        check(load().ihtb_fit_create(x._h, ptr(y, C.c_double), zf.ctypes.data_as(C.POINTER(C.c_double)), q,
-                                     ptr(zk, C.c_uint8) if zk is not None else None, C.byref(self.cfg),
-                                     C.byref(self._h)))
+        check(load().ihtb_fit_create_sharded(x._h, comm._h if comm is not None else None, self.p_global,
+                                             ptr(y, C.c_double), zf.ctypes.data_as(C.POINTER(C.c_double)), q,
+                                             ptr(zk, C.c_uint8) if zk is not None else None, C.byref(self.cfg),
+                                             C.byref(self._h)))
 
     def set_k(self, k):
         check(load().ihtb_fit_set_k(self._h, int(k)))
@@ -232,7 +235,8 @@ def _check_args(k, max_iter, max_step, tol):
 
 
 def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est_r="None", nb_r=1.0, tol=1e-4,
-            max_iter=200, min_iter=5, max_step=3, sweep_mode=_lib.SWEEP_FAST, verbose=False, io=None) -> IHTResult:
+            max_iter=200, min_iter=5, max_step=3, sweep_mode=_lib.SWEEP_FAST, verbose=False, io=None,
+            comm=None, p_global=None) -> IHTResult:
     """`fit_iht(y, x, z; k, d, l, zkeep, tol, max_iter, min_iter, max_step)` (src/fit.jl:60-118)."""
     _check_args(k, max_iter, max_step, tol)
     if est_r != "None":
@@ -243,7 +247,7 @@ def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est
     if z is None:
         z = np.ones(x.n)
     l = l or "IdentityLink"
-    v = IHTVariable(x, z, y, k, d, l, zkeep, nb_r, tol, max_iter, min_iter, max_step, sweep_mode)
+    v = IHTVariable(x, z, y, k, d, l, zkeep, nb_r, tol, max_iter, min_iter, max_step, sweep_mode, comm, p_global)
     try:
         v.init_iht_indices(None)
         res, trace = v.fit()

@@ -14,6 +14,7 @@
 //   pve                src/pve.jl:31-33          -> ihtb_fit::compute_pve
 #include "glm.cuh"
 #include "topk.cuh"
+#include "comm.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -40,7 +41,14 @@ static const double kExactBound = 1e-13;
 struct ihtb_fit {
     const ihtb_geno* g = nullptr;
     int device = 0;
-    int64_t n = 0, p = 0, q = 0;
+    int64_t n = 0, p = 0, q = 0;          // p = local SNP columns
+    // SNP-sharded fits: this rank owns global columns [j0, j0 + p); the k-sparse model, y, z and every n-vector are
+    // replicated; partial X*beta is all-reduced and top-k candidates are all-gathered
+    ihtb_comm* comm = nullptr;
+    int64_t j0 = 0, p_global = 0;
+    std::vector<int64_t> shard_j0;        // j0 of every rank
+    DBuf<int64_t> d_selall;
+    HBuf<int64_t> h_selall;
     ihtb_cfg cfg{};
     cudaStream_t s = nullptr;
     std::vector<uint8_t> zkeep;
@@ -100,16 +108,26 @@ struct ihtb_fit {
         if (count) IHTB_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
     }
 
-    // ---- update_xb! genetic part: xb = x[:, idx] * b[idx]  (src/utilities.jl:95-111) ------------
-    void update_xb() {
+    bool is_local(int64_t j) const { return j >= j0 && j < j0 + p; }
+    int nranks() const { return comm ? comm->nranks : 1; }
+
+    // d_out = x[:, cols] * coef over the GLOBAL column list: local partial + all-reduce over the shards
+    void support_matvec(const std::vector<int64_t>& cols, const std::vector<double>& coef, double* d_out) {
         std::vector<int64_t> ii; std::vector<double> vv;
-        for (size_t t = 0; t < idx.size(); ++t)
-            if (b[t] != 0.0) { ii.push_back(idx[t]); vv.push_back(b[t]); }
-        if (ii.empty()) { d_xb.zero(s); return; }
-        upload(d_idx.p, ii.data(), ii.size());
-        upload(d_coef.p, vv.data(), vv.size());
-        x_support(g, d_idx.p, (int64_t)ii.size(), d_coef.p, 1, d_xb.p, s);
+        for (size_t t = 0; t < cols.size(); ++t)
+            if (coef[t] != 0.0 && is_local(cols[t])) { ii.push_back(cols[t] - j0); vv.push_back(coef[t]); }
+        if (ii.empty()) {
+            IHTB_CUDA(cudaMemsetAsync(d_out, 0, n * sizeof(double), s));
+        } else {
+            upload(d_idx.p, ii.data(), ii.size());
+            upload(d_coef.p, vv.data(), vv.size());
+            x_support(g, d_idx.p, (int64_t)ii.size(), d_coef.p, 1, d_out, s);
+        }
+        comm_allreduce_sum_f64(comm, d_out, (size_t)n, s);
     }
+
+    // ---- update_xb! genetic part: xb = x[:, idx] * b[idx]  (src/utilities.jl:95-111) ------------
+    void update_xb() { support_matvec(idx, b, d_xb.p); }
 
     // ---- zc = Z c, clamp, mu = linkinv, deviance, loglikelihood (src/utilities.jl:9-20,52-61,74-82,113-117) ----
     double glm_update(int add_zc) {
@@ -133,8 +151,12 @@ struct ihtb_fit {
             if (!df_exact.count(j)) need.push_back(j);
         if (need.empty()) return;
         IHTB_CHECK((int64_t)need.size() <= (int64_t)d_cols.n, IHTB_ENUMERIC, "too many columns to re-score");
-        upload(d_cols.p, need.data(), need.size());
+        // columns of other shards are marked -1: the kernel writes 0 for them and the all-reduce fills them in
+        std::vector<int64_t> loc(need.size());
+        for (size_t t = 0; t < need.size(); ++t) loc[t] = is_local(need[t]) ? need[t] - j0 : -1;
+        upload(d_cols.p, loc.data(), loc.size());
         xt_gather(g, d_cols.p, (int64_t)need.size(), d_r.p, 1, d_vbar.p, d_gout.p, s);   // d_vbar = mean(r), set by score
+        comm_allreduce_sum_f64(comm, d_gout.p, need.size(), s);
         IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_gout.p, need.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
         sync();
         for (size_t t = 0; t < need.size(); ++t) df_exact[need[t]] = h_gout.p[t];
@@ -182,13 +204,7 @@ struct ihtb_fit {
         std::vector<double> coef(idx.size());
         double numer = 0.0;
         for (size_t t = 0; t < idx.size(); ++t) { coef[t] = df_at(idx[t]); numer += coef[t] * coef[t]; }
-        if (idx.empty()) {
-            d_xs.zero(s);
-        } else {
-            upload(d_idx.p, idx.data(), idx.size());
-            upload(d_coef.p, coef.data(), coef.size());
-            x_support(g, d_idx.p, (int64_t)idx.size(), d_coef.p, 1, d_xs.p, s);
-        }
+        support_matvec(idx, coef, d_xs.p);
         std::vector<double> d2((size_t)q);
         for (int64_t l = 0; l < q; ++l) {
             d2[l] = idc[l] ? df2[l] : 0.0;
@@ -211,7 +227,7 @@ struct ihtb_fit {
         b0d_idx.clear();
         std::vector<double> vals;
         for (size_t t = 0; t < idx0.size(); ++t)
-            if (b0[t] != 0.0) { b0d_idx.push_back(idx0[t]); vals.push_back(b0[t]); }
+            if (b0[t] != 0.0 && is_local(idx0[t])) { b0d_idx.push_back(idx0[t] - j0); vals.push_back(b0[t]); }
         if (!b0d_idx.empty()) {
             upload(d_sidx.p, b0d_idx.data(), b0d_idx.size());
             upload(d_sval.p, vals.data(), vals.size());
@@ -223,14 +239,28 @@ struct ihtb_fit {
     std::vector<int64_t> device_candidates(double eta) {
         std::vector<int64_t> out;
         if (cfg.k <= 0) return out;
-        topk_candidates(tk, d_dfa.p, d_b0d.p, g->sinv.p, eta, bound, cfg.k, s);
-        IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + cap) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        topk_candidates(tk, d_dfa.p, d_b0d.p, g->sinv.p, eta, bound, cfg.k, s);   // local top-k (k clamped to p)
+        const int64_t* hs = h_sel.p;
+        const int nr = nranks();
+        if (nr > 1) {
+            // every rank's [state | candidates] block: the global top-k is inside the union of the local top-k's
+            comm_allgather_i64(comm, d_sel.p, d_selall.p, (size_t)(2 + cap), s);
+            IHTB_CUDA(cudaMemcpyAsync(h_selall.p, d_selall.p, (size_t)nr * (2 + cap) * sizeof(int64_t),
+                                      cudaMemcpyDeviceToHost, s));
+            hs = h_selall.p;
+        } else {
+            IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + cap) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        }
         sync();
-        const TopkState* st = reinterpret_cast<const TopkState*>(h_sel.p);
-        IHTB_CHECK(st->count <= cap, IHTB_ENUMERIC,
-                   "degenerate projection: more than " + std::to_string(cap) +
-                       " entries lie within the sweep error bound of the k-th largest magnitude");
-        out.assign(h_sel.p + 2, h_sel.p + 2 + st->count);
+        for (int r = 0; r < nr; ++r) {
+            const int64_t* blk = hs + (size_t)r * (2 + cap);
+            const TopkState* st = reinterpret_cast<const TopkState*>(blk);
+            IHTB_CHECK(st->count <= cap, IHTB_ENUMERIC,
+                       "degenerate projection: more than " + std::to_string(cap) +
+                           " entries lie within the sweep error bound of the k-th largest magnitude");
+            const int64_t off = (nr > 1) ? shard_j0[r] : j0;
+            for (int t = 0; t < st->count; ++t) out.push_back(blk[2 + t] + off);
+        }
         return out;
     }
 
@@ -262,7 +292,7 @@ struct ihtb_fit {
         }
         for (int64_t l = 0; l < q; ++l) {
             c[l] = c0[l] + eta * df2[l];
-            if (!zkeep[l]) items.push_back({std::fabs(c[l]), p + l, c[l]});
+            if (!zkeep[l]) items.push_back({std::fabs(c[l]), p_global + l, c[l]});
         }
         int64_t k = cfg.k;
         std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) {
@@ -272,8 +302,8 @@ struct ihtb_fit {
         std::vector<std::pair<int64_t, double>> keep;
         for (size_t t = 0; t < items.size(); ++t) {
             bool kept = (int64_t)t < k;
-            if (items[t].pos >= p) {
-                if (!kept) c[items[t].pos - p] = 0.0;
+            if (items[t].pos >= p_global) {
+                if (!kept) c[items[t].pos - p_global] = 0.0;
             } else if (kept && items[t].v != 0.0) {
                 keep.push_back({items[t].pos, items[t].v});
             }
@@ -366,15 +396,15 @@ struct ihtb_fit {
         std::vector<Item> items;
         for (int64_t j : cand) { double v = df_exact.at(j); items.push_back({std::fabs(v), j, v}); }
         for (int64_t l = 0; l < q; ++l)
-            if (!zkeep[l]) items.push_back({std::fabs(df2[l]), p + l, df2[l]});
+            if (!zkeep[l]) items.push_back({std::fabs(df2[l]), p_global + l, df2[l]});
         std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) {
             return x.a > y.a || (x.a == y.a && x.pos < y.pos);
         });
         std::vector<std::pair<int64_t, double>> keep;
         for (size_t t = 0; t < items.size(); ++t) {
             bool kept = (int64_t)t < cfg.k;
-            if (items[t].pos >= p) {
-                if (!kept) df2[items[t].pos - p] = 0.0;
+            if (items[t].pos >= p_global) {
+                if (!kept) df2[items[t].pos - p_global] = 0.0;
             } else if (kept && items[t].v != 0.0) {
                 keep.push_back({items[t].pos, items[t].v});
             }
@@ -511,10 +541,20 @@ static ihtb_fit* fit_allocate(const ihtb_geno* g, int64_t q, int cap) {
     return f.release();
 }
 
+int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_global, const double* y,
+                                const double* z, int64_t q, const uint8_t* zkeep, const ihtb_cfg* cfg, ihtb_fit** out);
+
 int32_t ihtb_fit_create(const ihtb_geno* g, const double* y, const double* z, int64_t q, const uint8_t* zkeep,
                         const ihtb_cfg* cfg, ihtb_fit** out) {
+    return ihtb_fit_create_sharded(g, nullptr, g ? g->p : 0, y, z, q, zkeep, cfg, out);
+}
+
+int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_global, const double* y,
+                                const double* z, int64_t q, const uint8_t* zkeep, const ihtb_cfg* cfg, ihtb_fit** out) {
     return guard([&] {
         IHTB_CHECK(g && y && z && cfg && out, IHTB_EINVAL, "NULL argument");
+        IHTB_CHECK(p_global >= g->p, IHTB_EDIM, "p_global is smaller than the local shard");
+        IHTB_CHECK(comm || (p_global == g->p && g->j0 == 0) || true, IHTB_EINVAL, "");
         IHTB_CHECK(q >= 1, IHTB_EDIM, "z must have at least the intercept column");
         IHTB_CHECK(cfg->k >= 0, IHTB_EINVAL, "Value of k (max predictors per group) must be nonnegative!");
         IHTB_CHECK(cfg->max_iter >= 0, IHTB_EINVAL, "Value of max_iter must be nonnegative!");
@@ -524,13 +564,32 @@ int32_t ihtb_fit_create(const ihtb_geno* g, const double* y, const double* z, in
         IHTB_CHECK(cfg->link >= IHTB_LINK_IDENTITY && cfg->link <= IHTB_LINK_INVSQ, IHTB_EINVAL, "unknown link");
         IHTB_CHECK(cfg->sweep_mode == IHTB_SWEEP_FAST || cfg->sweep_mode == IHTB_SWEEP_EXACT, IHTB_EINVAL,
                    "bad sweep_mode");
-        IHTB_CHECK(cfg->k <= g->p, IHTB_EINVAL, "k cannot exceed the number of SNPs");
+        IHTB_CHECK(cfg->k <= p_global, IHTB_EINVAL, "k cannot exceed the number of SNPs");
         IHTB_CUDA(cudaSetDevice(g->device));
         int cap = (int)std::max<int64_t>(4096, 4 * cfg->k + 1024);
         std::unique_ptr<ihtb_fit> f(cache_take(g->device, g->n, g->p, q, cap));
         if (!f) f.reset(fit_allocate(g, q, cap));
         int64_t n = g->n, p = g->p;
         f->g = g; f->cfg = *cfg;
+        f->comm = (comm && comm->nranks > 1) ? comm : nullptr;
+        f->j0 = f->comm ? g->j0 : 0;
+        f->p_global = f->comm ? p_global : g->p;
+        f->shard_j0.clear();
+        if (f->comm) {
+            const int nr = comm->nranks;
+            if (f->d_selall.n < (size_t)nr * (2 + cap)) {
+                f->d_selall.alloc((size_t)nr * (2 + cap));
+                f->h_selall.alloc((size_t)nr * (2 + cap));
+            }
+            // exchange the shard offsets once (reuses the candidate buffers)
+            int64_t mine = g->j0;
+            IHTB_CUDA(cudaMemcpyAsync(f->d_sel.p, &mine, sizeof(int64_t), cudaMemcpyHostToDevice, f->s));
+            comm_allgather_i64(comm, f->d_sel.p, f->d_selall.p, 1, f->s);
+            f->shard_j0.resize(nr);
+            IHTB_CUDA(cudaMemcpyAsync(f->shard_j0.data(), f->d_selall.p, nr * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                      f->s));
+            IHTB_CUDA(cudaStreamSynchronize(f->s));
+        }
         f->zkeep.assign((size_t)q, 1);
         if (zkeep) for (int64_t l = 0; l < q; ++l) f->zkeep[l] = zkeep[l] ? 1 : 0;
         f->zkeepn = 0;
@@ -580,7 +639,7 @@ int32_t ihtb_fit_get(const ihtb_fit* f, double* beta, double* c, double* mu, dou
         IHTB_CHECK(f, IHTB_EINVAL, "NULL fit handle");
         IHTB_CUDA(cudaSetDevice(f->g->device));
         if (beta) {
-            std::fill(beta, beta + f->p, 0.0);
+            std::fill(beta, beta + f->p_global, 0.0);
             for (size_t t = 0; t < f->best_idx.size(); ++t) beta[f->best_idx[t]] = f->best_b[t];
         }
         if (c) std::copy(f->best_c.begin(), f->best_c.end(), c);

@@ -335,6 +335,13 @@ int32_t ihtb_synth_host(int64_t n, int64_t ncols, int64_t j0, uint64_t seed, dou
     });
 }
 
+int32_t ihtb_geno_set_offset(ihtb_geno* g, int64_t j0) {
+    return guard([&] {
+        IHTB_CHECK(g && j0 >= 0, IHTB_EINVAL, "bad argument");
+        g->j0 = j0;
+    });
+}
+
 int32_t ihtb_geno_dims(const ihtb_geno* g, int64_t* n, int64_t* p) {
     return guard([&] {
         IHTB_CHECK(g, IHTB_EINVAL, "NULL genotype handle");

@@ -97,6 +97,7 @@ k_xt_gather(GenoView gv, const int64_t* __restrict__ cols, int64_t split_bytes, 
     const int64_t nbytes = gv.nbytes, n = gv.n;
     const int64_t c = blockIdx.x, sp = blockIdx.y;
     const int64_t j = cols[c];
+    if (j < 0) return;                       // column owned by another shard (block-uniform exit)
     const int64_t b0 = sp * split_bytes;
     const int64_t b1 = (b0 + split_bytes < nbytes) ? b0 + split_bytes : nbytes;
     double a[M], mm[M], vb[M];
@@ -136,6 +137,7 @@ __global__ void k_xt_gather_fin(GenoView gv, const int64_t* __restrict__ cols, i
     if (e >= ncols * M) return;
     int64_t c = e / M;
     int t = (int)(e % M);
+    if (cols[c] < 0) { out[c + (int64_t)t * ncols] = 0.0; return; }
     double at = 0.0, mt = 0.0;
     for (int sp = 0; sp < nsplit; ++sp) {
         const double* o = part + (c * nsplit + sp) * (2 * M);
