@@ -26,8 +26,8 @@ sys.path.insert(0, ROOT)
 
 import numpy as np
 
-N_SAMPLES = 50_000
-P_PER_GPU = 500_000
+N_SAMPLES = int(os.environ.get("IHTB_BENCH_N", 50_000))      # overrides are for debugging only
+P_PER_GPU = int(os.environ.get("IHTB_BENCH_P", 500_000))
 K_SPARSITY = 20
 SEED = 2024
 DIST, LINK = "Bernoulli", "LogitLink"

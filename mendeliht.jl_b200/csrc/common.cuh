@@ -18,6 +18,7 @@ struct Error : std::runtime_error {
 void set_last_error(const std::string& m);
 const std::string& last_error();
 int64_t& launch_counter();
+bool debug_sync();   // IHTB_DEBUG_SYNC=1: synchronise and check after every kernel launch
 
 #define IHTB_CUDA(call)                                                                      \
     do {                                                                                     \
@@ -37,6 +38,11 @@ int64_t& launch_counter();
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);  \
         ::ihtb::launch_counter()++;                                  \
         IHTB_CUDA(cudaGetLastError());                               \
+        if (::ihtb::debug_sync()) {                                  \
+            cudaError_t e2__ = cudaStreamSynchronize(stream);        \
+            if (e2__ != cudaSuccess)                                 \
+                throw ::ihtb::Error(IHTB_ECUDA, std::string("kernel " #kernel " failed: ") + cudaGetErrorString(e2__)); \
+        }                                                            \
     } while (0)
 
 template <typename F>

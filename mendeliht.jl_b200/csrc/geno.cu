@@ -19,6 +19,11 @@ int64_t& launch_counter() {
     static int64_t c = 0;
     return c;
 }
+bool debug_sync() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("IHTB_DEBUG_SYNC"); v = (e && *e == '1') ? 1 : 0; }
+    return v == 1;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Kernels

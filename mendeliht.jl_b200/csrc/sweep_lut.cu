@@ -141,6 +141,9 @@ __device__ __forceinline__ void lut_build(uint32_t tab, const double* __restrict
 // CW consumer warps in G groups (+ 1 producer warp).  Group g consumes the CTA's units with (local index % G) == g, and
 // each of its CW/G warps reduces CPW = 128*G/CW columns of that unit, so per-unit bookkeeping is amortised over 16
 // columns per warp while 16 warps keep the shared-memory pipe busy.
+// Every group has its OWN ring of stages and mbarriers (ring g = stage slots [ring_off(g), ring_off(g) + ring_len(g))):
+// a warp must observe every phase of a barrier it waits on, otherwise a parity wait issued a whole phase early is
+// satisfied by the preceding phase (the mbarrier ABA hazard) and the warp would read a slot before it is refilled.
 template <int CW, int G>
 __global__ void __launch_bounds__((CW + 1) * 32, 1)
 k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t p, int64_t n, int64_t n_slabs,
@@ -153,6 +156,8 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
     const LutPlan pl = lut_plan(smem_u32(smem_raw), dyn_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = pl.n_stages;
+    auto ring_len = [S](int g) { return (S + (G - 1 - g)) / G; };          // S = 5, G = 2 -> 3, 2
+    auto ring_off = [S](int g) { int o = 0; for (int r = 0; r < g; ++r) o += (S + (G - 1 - r)) / G; return o; };
 
     const int64_t n_cblocks = (p + LUT_STAGE_COLS - 1) / LUT_STAGE_COLS;
     const int64_t units = n_slabs * n_cblocks;
@@ -173,13 +178,20 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
 
     if (warp == CW) {
         // ===== producer warp: stream column chunks with bulk async copies =====
-        int st = 0; uint32_t ph = 0;
+        int rst[G]; uint32_t rph[G];                 // per-ring position
+#pragma unroll
+        for (int r = 0; r < G; ++r) { rst[r] = 0; rph[r] = 0; }
+        int ring = 0;                                // ring of the next unit (local unit index % G)
         for (int64_t slab = slab_beg; slab <= slab_end; ++slab) {
             const int cb0 = (slab == slab_beg) ? (int)(u_beg - slab * n_cblocks) : 0;
             const int cb1 = (slab == slab_end) ? (int)(u_end - slab * n_cblocks) : ncb;    // exclusive
             for (int cb = cb0; cb < cb1; ++cb) {
                 const int64_t j0 = (int64_t)cb * LUT_STAGE_COLS;
                 const int ncols = (int)((p - j0 < LUT_STAGE_COLS) ? (p - j0) : LUT_STAGE_COLS);
+                int st = 0; uint32_t ph = 0;
+#pragma unroll
+                for (int r = 0; r < G; ++r)
+                    if (r == ring) { st = ring_off(r) + rst[r]; ph = rph[r]; }
                 mbar_wait(pl.bar_empty + 8u * st, ph ^ 1u);
                 const uint8_t* src = bed + j0 * cs_j + slab * cs_s;
                 if (cs_j == 128) {               // slab-major tiled layout: one contiguous copy
@@ -193,7 +205,10 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
                     for (int c = lane; c < ncols; c += 32)
                         bulk_g2s(pl.stage(st) + 128u * c, src + (int64_t)c * cs_j, 128u, pl.bar_full + 8u * st);
                 }
-                if (++st == S) { st = 0; ph ^= 1u; }
+#pragma unroll
+                for (int r = 0; r < G; ++r)
+                    if (r == ring && ++rst[r] == ring_len(r)) { rst[r] = 0; rph[r] ^= 1u; }
+                if (++ring == G) ring = 0;
             }
         }
     } else {
@@ -209,8 +224,9 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
         const int col = wg * CPW + lane / LPC;        // column (within a unit) this lane stores
         const bool writer = (lane & (LPC - 1)) == 0;
         const uint32_t lane_off = (uint32_t)(wg * CPW) * 128u + 4u * (uint32_t)lane;
-        // this group's position in the stage ring: local unit index i = grp, grp+G, ...
-        int st = grp % S; uint32_t ph = (uint32_t)((grp / S) & 1);
+        // this group's own stage ring; it consumes local unit indices i = grp, grp+G, ...
+        const int my_off = ring_off(grp), my_len = ring_len(grp);
+        int rs = 0; uint32_t ph = 0;                  // slot within the ring, phase parity
         int i_next = grp;                             // local index of this group's next unit
         int i_base = 0;                               // local index of the first unit of the current slab
         for (int64_t slab = slab_beg; slab <= slab_end; ++slab) {
@@ -223,6 +239,7 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
             const int i_end = i_base + (cb1 - cb0);
             for (; i_next < i_end; i_next += G) {
                 const int cb = cb0 + (i_next - i_base);
+                const int st = my_off + rs;
                 mbar_wait(pl.bar_full + 8u * st, ph);
                 const uint32_t colbase = pl.stage(st) + lane_off;
                 float acc[CPW];
@@ -254,8 +271,7 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
                 for (int oo = 16 / CPW; oo >= 1; oo >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], oo);
                 const int jj = cb * LUT_STAGE_COLS + col;
                 if (writer && jj < (int)p) outp[cb * LUT_STAGE_COLS] = acc[0];
-                st += G;
-                if (st >= S) { st -= S; ph ^= 1u; }
+                if (++rs == my_len) { rs = 0; ph ^= 1u; }
             }
             i_base = i_end;
         }

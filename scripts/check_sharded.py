@@ -32,6 +32,17 @@ for d, l, n, p, k, ncov, miss in [("Normal", "IdentityLink", 5000, 20001, 8, 2, 
     ok = ok and same
     print(f"rank {rank} {d}: sharded iter={res.iter} full iter={ref.iter} same={same} "
           f"max|dbeta|={np.abs(res.beta - ref.beta).max():.3e} logl {res.logl:.9f} vs {ref.logl:.9f}", flush=True)
+# full BASELINE size per GPU: FAST and EXACT sweeps must give the same support / iterations / beta (stress for the pipeline)
+n, pg, k = 50000, 500000 * world, 20
+y, z, *_ = synth.simulate_response(2025, n, pg, k, "Bernoulli", geno_seed=2024)
+j0, pl = parallel.shard_range(pg, world, rank)
+g_loc = m.B200SnpLinAlg.synthetic(n, pl, 2024, 0.0, j0)
+ra = m.fit_iht(y, g_loc, z, k=k, d="Bernoulli", l="LogitLink", comm=comm, p_global=pg, sweep_mode=m.SWEEP_FAST)
+rb = m.fit_iht(y, g_loc, z, k=k, d="Bernoulli", l="LogitLink", comm=comm, p_global=pg, sweep_mode=m.SWEEP_EXACT)
+same = (ra.iter == rb.iter and np.array_equal(np.flatnonzero(ra.beta), np.flatnonzero(rb.beta))
+        and np.allclose(ra.beta, rb.beta, rtol=1e-9, atol=1e-12))
+ok = ok and same
+print(f"rank {rank} full-size FAST vs EXACT: iter {ra.iter}/{rb.iter} same={same}", flush=True)
 dist.barrier()
 comm.close()
 dist.destroy_process_group()

@@ -98,6 +98,25 @@ def test_bundled_fixture_sweep(normal_data, normal_oracle):
     np.testing.assert_allclose(g.xt_v(r, m.SWEEP_FAST), ref, rtol=0, atol=1e-4 * np.abs(ref).max())
 
 
+def test_fast_sweep_matches_exact_at_scale():
+    """BASELINE-size property check (the oracle cannot hold this matrix): the FAST sweep stays inside its proven
+    error bound of the EXACT sweep for every column, repeatedly (catches pipeline races that small cases miss)."""
+    n, p = 50000, 200000
+    g = m.B200SnpLinAlg.synthetic(n, p, 2024)
+    _, sinv, _ = g.stats()
+    rng = np.random.default_rng(3)
+    for rep in range(4):
+        v = rng.normal(size=n) * (1 + rep) + 0.1 * rep
+        ex = g.xt_v(v, m.SWEEP_EXACT)
+        fa = g.xt_v(v, m.SWEEP_FAST)
+        bound = (2.0 ** -18) * np.abs(v - v.mean()).sum() * sinv
+        assert np.all(np.abs(fa - ex) <= bound + 1e-9 * np.abs(ex).max())
+    # checksum of checksums against a column subsample computed by the numpy twin of the generator
+    cols = np.sort(rng.permutation(p)[:64])
+    xs = synth.standardized_columns(2024, n, cols)
+    np.testing.assert_allclose(ex[cols], xs.T @ v, rtol=0, atol=1e-8 * np.abs(ex).max())
+
+
 def test_errors():
     with pytest.raises(m.DimensionMismatch):
         m.B200SnpLinAlg.from_bed_columns(np.zeros((4, 2), dtype=np.uint8), 100)   # stride < ceil(n/4)
