@@ -24,7 +24,7 @@ namespace ihtb {
 
 constexpr int LUT_STAGE_COLS = 128;
 constexpr int LUT_STAGE_BYTES = LUT_STAGE_COLS * 128;
-constexpr int LUT_MAX_STAGES = 6;
+constexpr int LUT_MAX_STAGES = 8;
 constexpr int LUT_TABLE_BYTES = 131072;
 constexpr int LUT_SMEM_BYTES = 232448;   // 227 KB: everything the SM has
 
@@ -86,10 +86,10 @@ __device__ __forceinline__ LutPlan lut_plan(uint32_t base, uint32_t bytes) {
     pl.bar_full = 0; pl.bar_empty = 0; pl.n_stages = 0;
     uint32_t lo = (base + 127u) & ~127u, lo_end = pl.tab;
     uint32_t hi = pl.tab + LUT_TABLE_BYTES, hi_end = end;
-    // barriers: 128 bytes at the first free spot
-    if (lo + 128u <= lo_end) { pl.bar_full = lo; lo += 128u; }
-    else { pl.bar_full = hi; hi += 128u; }
-    pl.bar_empty = pl.bar_full + 64u;
+    // barriers: 256 bytes at the first free spot: full[2][LUT_MAX_STAGES] then empty[LUT_MAX_STAGES]
+    if (lo + 256u <= lo_end) { pl.bar_full = lo; lo += 256u; }
+    else { pl.bar_full = hi; hi += 256u; }
+    pl.bar_empty = pl.bar_full + 8u * 2u * LUT_MAX_STAGES;
     pl.lo0 = lo; pl.hi0 = hi;
     pl.n_lo = (lo_end > lo) ? (int)((lo_end - lo) / LUT_STAGE_BYTES) : 0;
     if (pl.n_lo > LUT_MAX_STAGES) pl.n_lo = LUT_MAX_STAGES;
@@ -141,9 +141,11 @@ __device__ __forceinline__ void lut_build(uint32_t tab, const double* __restrict
 // CW consumer warps in G groups (+ 1 producer warp).  Group g consumes the CTA's units with (local index % G) == g, and
 // each of its CW/G warps reduces CPW = 128*G/CW columns of that unit, so per-unit bookkeeping is amortised over 16
 // columns per warp while 16 warps keep the shared-memory pipe busy.
-// Every group has its OWN ring of stages and mbarriers (ring g = stage slots [ring_off(g), ring_off(g) + ring_len(g))):
-// a warp must observe every phase of a barrier it waits on, otherwise a parity wait issued a whole phase early is
-// satisfied by the preceding phase (the mbarrier ABA hazard) and the warp would read a slot before it is refilled.
+// The groups share one ring of S stages (unit i uses stage i % S) and one "empty" mbarrier per stage, but every
+// group has its OWN "full" mbarrier per stage: the producer signals full[i % G][i % S].  A warp must observe every
+// phase of a barrier it waits on -- a parity wait issued a whole phase early is satisfied by the preceding phase
+// (the mbarrier ABA hazard) and the warp would read a slot before it is refilled.  With per-group full barriers a
+// group sees exactly the fills meant for it, in order, while the groups still progress independently.
 template <int CW, int G>
 __global__ void __launch_bounds__((CW + 1) * 32, 1)
 k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t p, int64_t n, int64_t n_slabs,
@@ -156,8 +158,8 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
     const LutPlan pl = lut_plan(smem_u32(smem_raw), dyn_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = pl.n_stages;
-    auto ring_len = [S](int g) { return (S + (G - 1 - g)) / G; };          // S = 5, G = 2 -> 3, 2
-    auto ring_off = [S](int g) { int o = 0; for (int r = 0; r < g; ++r) o += (S + (G - 1 - r)) / G; return o; };
+    // (group, stage) pairs repeat with period lcm(S, G) in the unit index; G is 1 or 2
+    const int period = (S % G == 0) ? S : S * G;
 
     const int64_t n_cblocks = (p + LUT_STAGE_COLS - 1) / LUT_STAGE_COLS;
     const int64_t units = n_slabs * n_cblocks;
@@ -169,7 +171,7 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(pl.bar_full + 8u * s, 1);
+            for (int g = 0; g < G; ++g) mbar_init(pl.bar_full + 8u * (g * LUT_MAX_STAGES + s), 1);
             mbar_init(pl.bar_empty + 8u * s, WPG);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -178,37 +180,30 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
 
     if (warp == CW) {
         // ===== producer warp: stream column chunks with bulk async copies =====
-        int rst[G]; uint32_t rph[G];                 // per-ring position
-#pragma unroll
-        for (int r = 0; r < G; ++r) { rst[r] = 0; rph[r] = 0; }
-        int ring = 0;                                // ring of the next unit (local unit index % G)
+        int st = 0; uint32_t ph = 0;                 // stage of the next unit, parity of its "empty" phase
+        int grp_of = 0;                              // group that owns the next unit (local unit index % G)
         for (int64_t slab = slab_beg; slab <= slab_end; ++slab) {
             const int cb0 = (slab == slab_beg) ? (int)(u_beg - slab * n_cblocks) : 0;
             const int cb1 = (slab == slab_end) ? (int)(u_end - slab * n_cblocks) : ncb;    // exclusive
             for (int cb = cb0; cb < cb1; ++cb) {
                 const int64_t j0 = (int64_t)cb * LUT_STAGE_COLS;
                 const int ncols = (int)((p - j0 < LUT_STAGE_COLS) ? (p - j0) : LUT_STAGE_COLS);
-                int st = 0; uint32_t ph = 0;
-#pragma unroll
-                for (int r = 0; r < G; ++r)
-                    if (r == ring) { st = ring_off(r) + rst[r]; ph = rph[r]; }
+                const uint32_t fullbar = pl.bar_full + 8u * (uint32_t)(grp_of * LUT_MAX_STAGES + st);
                 mbar_wait(pl.bar_empty + 8u * st, ph ^ 1u);
                 const uint8_t* src = bed + j0 * cs_j + slab * cs_s;
                 if (cs_j == 128) {               // slab-major tiled layout: one contiguous copy
                     if (lane == 0) {
-                        mbar_expect_tx(pl.bar_full + 8u * st, (uint32_t)ncols * 128u);
-                        bulk_g2s(pl.stage(st), src, (uint32_t)ncols * 128u, pl.bar_full + 8u * st);
+                        mbar_expect_tx(fullbar, (uint32_t)ncols * 128u);
+                        bulk_g2s(pl.stage(st), src, (uint32_t)ncols * 128u, fullbar);
                     }
                 } else {                          // column-major layout: one 128-byte copy per column
-                    if (lane == 0) mbar_expect_tx(pl.bar_full + 8u * st, (uint32_t)ncols * 128u);
+                    if (lane == 0) mbar_expect_tx(fullbar, (uint32_t)ncols * 128u);
                     __syncwarp();
                     for (int c = lane; c < ncols; c += 32)
-                        bulk_g2s(pl.stage(st) + 128u * c, src + (int64_t)c * cs_j, 128u, pl.bar_full + 8u * st);
+                        bulk_g2s(pl.stage(st) + 128u * c, src + (int64_t)c * cs_j, 128u, fullbar);
                 }
-#pragma unroll
-                for (int r = 0; r < G; ++r)
-                    if (r == ring && ++rst[r] == ring_len(r)) { rst[r] = 0; rph[r] ^= 1u; }
-                if (++ring == G) ring = 0;
+                if (++st == S) { st = 0; ph ^= 1u; }
+                if (++grp_of == G) grp_of = 0;
             }
         }
     } else {
@@ -224,9 +219,9 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
         const int col = wg * CPW + lane / LPC;        // column (within a unit) this lane stores
         const bool writer = (lane & (LPC - 1)) == 0;
         const uint32_t lane_off = (uint32_t)(wg * CPW) * 128u + 4u * (uint32_t)lane;
-        // this group's own stage ring; it consumes local unit indices i = grp, grp+G, ...
-        const int my_off = ring_off(grp), my_len = ring_len(grp);
-        int rs = 0; uint32_t ph = 0;                  // slot within the ring, phase parity
+        // this group consumes local unit indices i = grp, grp+G, ...: stage i % S, full-barrier parity (i / period) & 1
+        int st = grp % S, ip = grp % period; uint32_t ph = (uint32_t)((grp / period) & 1);
+        const uint32_t my_full = pl.bar_full + 8u * (uint32_t)(grp * LUT_MAX_STAGES);
         int i_next = grp;                             // local index of this group's next unit
         int i_base = 0;                               // local index of the first unit of the current slab
         for (int64_t slab = slab_beg; slab <= slab_end; ++slab) {
@@ -239,8 +234,7 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
             const int i_end = i_base + (cb1 - cb0);
             for (; i_next < i_end; i_next += G) {
                 const int cb = cb0 + (i_next - i_base);
-                const int st = my_off + rs;
-                mbar_wait(pl.bar_full + 8u * st, ph);
+                mbar_wait(my_full + 8u * st, ph);
                 const uint32_t colbase = pl.stage(st) + lane_off;
                 float acc[CPW];
 #pragma unroll
@@ -271,7 +265,8 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
                 for (int oo = 16 / CPW; oo >= 1; oo >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], oo);
                 const int jj = cb * LUT_STAGE_COLS + col;
                 if (writer && jj < (int)p) outp[cb * LUT_STAGE_COLS] = acc[0];
-                if (++rs == my_len) { rs = 0; ph ^= 1u; }
+                st += G; if (st >= S) st -= S;
+                ip += G; if (ip >= period) { ip -= period; ph ^= 1u; }
             }
             i_base = i_end;
         }
