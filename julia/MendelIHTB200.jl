@@ -1,0 +1,142 @@
+# MendelIHTB200.jl — Julia shim that routes MendelIHT's IHT hot path to libihtb200.so through ccall.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: Julia is not installed in the build image.  The Python mirror
+# (mendeliht.jl_b200/api.py) binds the very same C entry points and is what the tests run; this file shows the
+# reference-side binding a maintainer adds (see INTEGRATION.md).  Entry points: include/ihtb200.h.
+module MendelIHTB200
+
+using MendelIHT, SnpArrays, Distributions, GLM, LinearAlgebra
+import MendelIHT: fit_iht, cv_iht, IHTResult, pve
+
+const LIB = get(ENV, "IHTB200_LIB", "libihtb200")
+
+# ---- status codes -> the exception types the reference throws -------------------------------------------------
+function last_error()
+    buf = Vector{UInt8}(undef, 1024)
+    ccall((:ihtb_last_error, LIB), Int32, (Ptr{UInt8}, Int64), buf, 1024)
+    unsafe_string(pointer(buf))
+end
+function check(status::Int32)
+    status == 0 && return
+    msg = last_error()
+    status == -1 && throw(ArgumentError(msg))          # @assert / ArgumentError (src/fit.jl:87-90)
+    status == -2 && throw(DimensionMismatch(msg))      # src/data_structures.jl:63-85
+    status == -3 && throw(DomainError(msg))            # src/utilities.jl:554
+    status == -4 && error(msg)                         # "Loglikelihood function is NaN, aborting..." (src/fit.jl:259)
+    error("libihtb200: $msg (status $status)")
+end
+
+# ---- SnpLinAlg replacement -------------------------------------------------------------------------------------
+"Device-resident genotype operator; drop-in for `SnpLinAlg{Float64}(s; center, scale, impute)` (src/wrapper.jl:68)."
+mutable struct B200SnpLinAlg <: AbstractMatrix{Float64}
+    handle::Ptr{Cvoid}
+    n::Int
+    p::Int
+    center::Bool
+    scale::Bool
+    impute::Bool
+    function B200SnpLinAlg(s::SnpArray; model=ADDITIVE_MODEL, center::Bool=true, scale::Bool=true, impute::Bool=true)
+        model == ADDITIVE_MODEL || error("only ADDITIVE_MODEL is supported")
+        n, p = size(s)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        # s.data is the mmapped packed matrix, ceil(n/4) x p bytes, SNP-major: exactly bed_cols
+        check(ccall((:ihtb_geno_create, LIB), Int32,
+                    (Ptr{UInt8}, Int64, Int64, Int64, Int32, Int32, Int32, Ref{Ptr{Cvoid}}),
+                    s.data, n, p, size(s.data, 1), center, scale, impute, h))
+        x = new(h[], n, p, center, scale, impute)
+        finalizer(x -> ccall((:ihtb_geno_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle), x)
+        return x
+    end
+end
+Base.size(x::B200SnpLinAlg) = (x.n, x.p)
+function Base.getindex(x::B200SnpLinAlg, i::Int, j::Int)    # bit-exact with SnpLinAlg getindex (src/utilities.jl:102)
+    out = Ref{Float64}(0.0)
+    check(ccall((:ihtb_geno_decode, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ref{Float64}),
+                x.handle, i - 1, i, j - 1, j, out))
+    out[]
+end
+"mul!(out, Transpose(x), v)  (src/utilities.jl:133, src/multivariate.jl:85)"
+function LinearAlgebra.mul!(out::AbstractVecOrMat{Float64}, xt::Transpose{Float64,B200SnpLinAlg},
+                            v::AbstractVecOrMat{Float64})
+    x = xt.parent
+    check(ccall((:ihtb_xt_v, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int32),
+                x.handle, v, size(v, 2), out, 1))       # 1 = IHTB_SWEEP_EXACT for stand-alone products
+    out
+end
+
+# ---- fit_iht on the device -----------------------------------------------------------------------------------
+struct Cfg
+    dist::Int32; link::Int32; k::Int64; nb_r::Float64; tol::Float64
+    max_iter::Int32; min_iter::Int32; max_step::Int32; sweep_mode::Int32
+end
+mutable struct CResult
+    time::Float64; logl::Float64; iter::Int64; sigma_g::Float64; n_sweeps::Int64; n_backtracks::Int64
+    sweep_seconds::Float64; n_launches::Int64; n_steps::Int64
+    CResult() = new(0, 0, 0, 0, 0, 0, 0, 0, 0)
+end
+distcode(::Normal) = Int32(0); distcode(::Bernoulli) = Int32(1); distcode(::Poisson) = Int32(2)
+distcode(::NegativeBinomial) = Int32(3)
+linkcode(::IdentityLink) = Int32(0); linkcode(::LogitLink) = Int32(1); linkcode(::LogLink) = Int32(2)
+linkcode(::ProbitLink) = Int32(3); linkcode(::CloglogLink) = Int32(4); linkcode(::CauchitLink) = Int32(5)
+linkcode(::SqrtLink) = Int32(6); linkcode(::InverseLink) = Int32(7); linkcode(::InverseSquareLink) = Int32(8)
+
+"Same signature and return type as MendelIHT.fit_iht (src/fit.jl:60-118) for `x::B200SnpLinAlg`."
+function fit_iht(y::AbstractVector{Float64}, x::B200SnpLinAlg, z::AbstractVecOrMat{Float64};
+                 k::Int=10, J::Int=1, d::Distribution=Normal(), l::Link=IdentityLink(),
+                 zkeep::BitVector=trues(size(z, 2)), est_r::Symbol=:None, tol::Float64=1e-4, max_iter::Int=200,
+                 min_iter::Int=5, max_step::Int=3, verbose::Bool=false, io::IO=stdout, kwargs...)
+    est_r == :None || error("est_r is not supported on the device path yet")
+    x.center || error("x is not centered! Please construct SnpLinAlg{Float64}(::SnpArray, center=true, scale=true)")
+    zm = z isa AbstractVector ? reshape(z, :, 1) : Matrix(z)
+    r = d isa NegativeBinomial ? d.r : 1.0
+    cfg = Ref(Cfg(distcode(d), linkcode(l), k, r, tol, max_iter, min_iter, max_step, 0))
+    fh = Ref{Ptr{Cvoid}}(C_NULL)
+    keep = UInt8.(zkeep)
+    check(ccall((:ihtb_fit_create, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{UInt8}, Ref{Cfg}, Ref{Ptr{Cvoid}}),
+                x.handle, y, zm, size(zm, 2), keep, cfg, fh))
+    try
+        check(ccall((:ihtb_fit_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), fh[], C_NULL))
+        res = CResult()
+        check(ccall((:ihtb_fit_run, LIB), Int32, (Ptr{Cvoid}, Ref{CResult}, Ptr{Cvoid}, Int64), fh[], res, C_NULL, 0))
+        beta = zeros(x.p); c = zeros(size(zm, 2))
+        check(ccall((:ihtb_fit_get, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    fh[], beta, c, C_NULL, C_NULL))
+        return IHTResult(res.time, res.logl, res.iter, beta, c, J, k, Int[], d, res.sigma_g)
+    finally
+        ccall((:ihtb_fit_destroy, LIB), Int32, (Ptr{Cvoid},), fh[])
+    end
+end
+
+"cv_iht (src/cross_validation.jl:60-131): one device workspace, the (fold, k) grid run back to back."
+function cv_iht(y::AbstractVector{Float64}, x::B200SnpLinAlg, z::AbstractVecOrMat{Float64};
+                d::Distribution=Normal(), l::Link=IdentityLink(), path::AbstractVector{<:Integer}=1:20, q::Int=5,
+                folds::AbstractVector{Int}=rand(1:q, size(x, 1)), zkeep::BitVector=trues(size(z, 2)),
+                max_iter::Int=100, min_iter::Int=5, kwargs...)
+    maximum(path) > size(x, 2) && error("Sparsity level in `path` cannot be larger than total number of variables")
+    zm = z isa AbstractVector ? reshape(z, :, 1) : Matrix(z)
+    r = d isa NegativeBinomial ? d.r : 1.0
+    cfg = Ref(Cfg(distcode(d), linkcode(l), maximum(path), r, 1e-4, max_iter, min_iter, 3, 0))
+    fh = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ihtb_fit_create, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{UInt8}, Ref{Cfg}, Ref{Ptr{Cvoid}}),
+                x.handle, y, zm, size(zm, 2), UInt8.(zkeep), cfg, fh))
+    combos = MendelIHT.allocate_fold_and_k(q, path)
+    mses = zeros(length(combos))
+    try
+        for (i, (fold, k)) in enumerate(combos)
+            test = UInt8.(folds .== fold); train = UInt8.(folds .!= fold)
+            check(ccall((:ihtb_fit_set_k, LIB), Int32, (Ptr{Cvoid}, Int64), fh[], k))
+            check(ccall((:ihtb_fit_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), fh[], train))
+            check(ccall((:ihtb_fit_run, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64), fh[], C_NULL, C_NULL, 0))
+            dev = Ref{Float64}(0.0)
+            check(ccall((:ihtb_fit_predict, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Ref{Float64}), fh[], test, dev))
+            mses[i] = dev[]
+        end
+    finally
+        ccall((:ihtb_fit_destroy, LIB), Int32, (Ptr{Cvoid},), fh[])
+    end
+    return MendelIHT.meanloss(mses, q, folds)
+end
+
+end # module

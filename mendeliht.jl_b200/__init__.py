@@ -8,8 +8,8 @@ from . import _lib, synth
 from ._lib import (SWEEP_EXACT, SWEEP_FAST, CudaError, DimensionMismatch, IHTBError, NumericError, device_count,
                    launch_count, load)
 from .api import (BERNOULLI, NEGBIN, NORMAL, POISSON, B200SnpLinAlg, IHTResult, IHTVariable, allocate_fold_and_k,
-                  canonicallink, cv_iht, fit_iht, meanloss)
+                  canonicallink, cross_validate, cv_iht, fit_iht, iht, meanloss, parse_covariates)
 
 __all__ = ["B200SnpLinAlg", "IHTResult", "IHTVariable", "fit_iht", "cv_iht", "allocate_fold_and_k", "meanloss",
-           "canonicallink", "NORMAL", "BERNOULLI", "POISSON", "NEGBIN", "SWEEP_FAST", "SWEEP_EXACT", "load",
+           "canonicallink", "iht", "cross_validate", "parse_covariates", "NORMAL", "BERNOULLI", "POISSON", "NEGBIN", "SWEEP_FAST", "SWEEP_EXACT", "load",
            "device_count", "launch_count", "IHTBError", "DimensionMismatch", "NumericError", "CudaError", "synth"]

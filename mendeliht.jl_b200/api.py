@@ -312,3 +312,88 @@ def cv_iht(y, x: B200SnpLinAlg, z=None, d=NORMAL, l=None, path=range(1, 21), q=5
     if return_grid:
         return mses, iters
     return meanloss(mses, q, folds)
+
+
+# ---- file-level wrappers (reference src/wrapper.jl) ----------------------------------------------------------------
+def _read_fam_phenotype(path: str, col: int = 6) -> np.ndarray:
+    """`parse_phenotypes(x::SnpData, col, ::Normal)` (src/wrapper.jl:170-191): column `col` (1-based) of the .fam file,
+    "-9"/"NA" imputed with the mean of the observed phenotypes."""
+    vals, missing = [], []
+    with open(path) as f:
+        for i, line in enumerate(f):
+            tok = line.split()[col - 1]
+            if tok in ("-9", "NA"):
+                vals.append(0.0); missing.append(i)
+            else:
+                vals.append(float(tok))
+    y = np.asarray(vals)
+    if missing:
+        y[missing] = (y.sum()) / (len(vals) - len(missing))
+    return y
+
+
+def parse_covariates(filename: str, exclude_std_idx=(), standardize: bool = True) -> np.ndarray:
+    """`parse_covariates` (src/wrapper.jl:228-247): comma separated, first column all ones, every other column not in
+    `exclude_std_idx` (1-based) standardised to mean 0 / variance 1 with the n-1 standard deviation."""
+    z = np.loadtxt(filename, delimiter=",", dtype=np.float64, ndmin=2)
+    std_idx = np.ones(z.shape[1], dtype=bool)
+    for i in exclude_std_idx:
+        std_idx[i - 1] = False
+    if np.all(z[:, 0] == 1):
+        std_idx[0] = False
+    if standardize:
+        n = z.shape[0]
+        for j in np.flatnonzero(std_idx):
+            mu = z[:, j].sum() / n
+            s = 1.0 / np.sqrt(((z[:, j] - mu) ** 2).sum() / (n - 1))
+            z[:, j] = (z[:, j] - mu) * s
+    return z
+
+
+def _load_plink(filename: str, phenotypes, d: str):
+    fam = filename + ".fam"
+    n = sum(1 for _ in open(fam))
+    x = B200SnpLinAlg.from_bed_file(filename + ".bed", n)
+    if isinstance(phenotypes, int):
+        y = _read_fam_phenotype(fam, phenotypes)
+        if d != NORMAL and np.any(~np.isfinite(y)):
+            raise ValueError("Missing phenotype detected; automatic imputation is only possible for quantitative traits")
+    else:
+        y = np.loadtxt(phenotypes, delimiter=",", dtype=np.float64)
+    return x, y
+
+
+def iht(filename: str, k: int, d: str = NORMAL, phenotypes=6, covariates: str = "", summaryfile: str = None,
+        betafile: str = None, exclude_std_idx=(), **kwargs) -> IHTResult:
+    """`iht(filename, k, d; phenotypes, covariates, ...)` (src/wrapper.jl:52-120) for binary PLINK input: reads
+    `filename`.bed/.fam, builds the device genotype operator with center/scale/impute, standardises covariates and
+    runs `fit_iht` with the canonical link (LogLink for NegativeBinomial).  Optional text outputs like the reference."""
+    x, y = _load_plink(filename, phenotypes, d)
+    z = np.ones(x.n) if covariates == "" else parse_covariates(covariates, exclude_std_idx)
+    result = fit_iht(y, x, z, k=k, d=d, l=canonicallink(d), **kwargs)
+    if summaryfile:
+        with open(summaryfile, "w") as f:
+            nz = np.flatnonzero(result.beta)
+            f.write(f"\nIHT estimated {nz.size} nonzero SNP predictors and {np.count_nonzero(result.c)} "
+                    f"non-genetic predictors.\n\nCompute time (sec):     {result.time}\n"
+                    f"Final loglikelihood:    {result.logl}\nSNP PVE:                {result.sigma_g}\n"
+                    f"Iterations:             {result.iter}\n\nSelected genetic predictors:\n")
+            for j in nz:
+                f.write(f"{j + 1}\t{result.beta[j]}\n")
+    if betafile:
+        np.savetxt(betafile, result.beta)
+    return result
+
+
+def cross_validate(filename: str, d: str = NORMAL, path=range(1, 21), q: int = 5, phenotypes=6, covariates: str = "",
+                   cv_summaryfile: str = None, exclude_std_idx=(), folds=None, **kwargs) -> np.ndarray:
+    """`cross_validate(filename, d; path, q, ...)` (src/wrapper.jl:301-349) for binary PLINK input."""
+    x, y = _load_plink(filename, phenotypes, d)
+    z = np.ones(x.n) if covariates == "" else parse_covariates(covariates, exclude_std_idx)
+    mse = cv_iht(y, x, z, d=d, l=canonicallink(d), path=path, q=q, folds=folds, **kwargs)
+    if cv_summaryfile:
+        with open(cv_summaryfile, "w") as f:
+            f.write("k\tmse\n")
+            for kk, mm in zip(path, mse):
+                f.write(f"{kk}\t{mm}\n")
+    return mse

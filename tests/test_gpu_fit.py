@@ -173,3 +173,23 @@ def test_dimension_errors():
         m.fit_iht(np.zeros(100), g, None, k=-1)
     with pytest.raises(ValueError):
         m.cv_iht(np.zeros(100), g, None, path=[60], folds=np.ones(100, int))
+
+
+def test_file_wrappers_on_bundled_plink(tmp_path, normal_data):
+    """iht("normal", 7, Normal, covariates="covariates.txt") through the file-level wrapper == docs trace."""
+    import shutil
+    gold = json.load(open(os.path.join(GOLDEN, "docs_trace_normal_k7.json")))
+    shutil.copy(os.path.join(GOLDEN, "normal.bed"), tmp_path / "normal.bed")
+    with open(tmp_path / "normal.fam", "w") as f:
+        for i, yi in enumerate(normal_data["y"]):
+            f.write(f"{i + 1}\t1\t0\t0\t1\t{yi!r}\n")
+    shutil.copy(os.path.join(GOLDEN, "covariates.txt"), tmp_path / "covariates.txt")
+    res = m.iht(str(tmp_path / "normal"), 7, "Normal", covariates=str(tmp_path / "covariates.txt"),
+                summaryfile=str(tmp_path / "iht.summary.txt"), betafile=str(tmp_path / "iht.beta.txt"))
+    assert res.iter == gold["iter"] and list(np.flatnonzero(res.beta) + 1) == gold["support_1based"]
+    np.testing.assert_allclose([t[0] for t in res.trace], gold["logl"], rtol=1e-9)
+    assert os.path.exists(tmp_path / "iht.summary.txt") and np.loadtxt(tmp_path / "iht.beta.txt").shape == (10000,)
+    folds = synth.folds_for(1, 1000, 3)
+    mse = m.cross_validate(str(tmp_path / "normal"), "Normal", path=[5, 7, 9], q=3,
+                           covariates=str(tmp_path / "covariates.txt"), folds=folds)
+    assert mse.shape == (3,) and np.all(mse > 0)
