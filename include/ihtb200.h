@@ -136,6 +136,21 @@ int32_t ihtb_fit_predict(ihtb_fit* f, const uint8_t* test_mask, double* deviance
 int32_t ihtb_fit_timer(ihtb_fit* f, int32_t which, double* ms);
 int32_t ihtb_fit_destroy(ihtb_fit* f);
 
+/* ---- multivariate Normal fit (mIHTVariable, src/multivariate.jl; fit_iht(Y, Transpose(xla), Z), src/fit.jl:60-118) ----
+ * Y is n x r column-major (one trait per column; the reference stores r x n), z is n x q column-major with the
+ * intercept first, 2 <= r <= 16, every covariate kept.  cfg->k counts non-zero ENTRIES of the r x p matrix B
+ * (src/data_structures.jl:233); cfg->dist / link are ignored. */
+int32_t ihtb_mvfit_create(const ihtb_geno* g, const double* Y, int64_t r, const double* z, int64_t q,
+                          const ihtb_cfg* cfg, ihtb_mvfit** out);
+int32_t ihtb_mvfit_set_k(ihtb_mvfit* f, int64_t k);
+int32_t ihtb_mvfit_init(ihtb_mvfit* f, const uint8_t* train_mask);
+int32_t ihtb_mvfit_run(ihtb_mvfit* f, ihtb_result* result, ihtb_iter_trace* trace, int64_t trace_cap);
+/* beta: r x p column-major (trait fastest, like Julia's best_B); c: r x q column-major; Sigma: r x r = inv(Gamma);
+ * sigma_g[r]: per-trait PVE (src/pve.jl:35-37).  Any pointer may be NULL. */
+int32_t ihtb_mvfit_get(const ihtb_mvfit* f, double* beta, double* c, double* Sigma, double* sigma_g);
+int32_t ihtb_mvfit_predict(ihtb_mvfit* f, const uint8_t* test_mask, double* mse);   /* src/cross_validation.jl:288-299 */
+int32_t ihtb_mvfit_destroy(ihtb_mvfit* f);
+
 /* ---- multi-GPU plumbing (NCCL over NVLink; rendezvous of the 128-byte id is the host's job, e.g. torch.distributed) ---- */
 /* nccl_lib_path may be NULL: $IHTB_NCCL_LIB, then libnccl.so.2 are tried (dlopen at run time, no link-time dependency) */
 int32_t ihtb_comm_unique_id(const char* nccl_lib_path, uint8_t* out128);

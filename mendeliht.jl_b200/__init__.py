@@ -7,7 +7,8 @@ host-side mirror of the reference's Julia API.  There is no CPU fallback.
 from . import _lib, synth
 from ._lib import (SWEEP_EXACT, SWEEP_FAST, CudaError, DimensionMismatch, IHTBError, NumericError, device_count,
                    launch_count, load)
-from .api import (BERNOULLI, NEGBIN, NORMAL, POISSON, B200SnpLinAlg, IHTResult, IHTVariable, allocate_fold_and_k,
+from .api import (BERNOULLI, NEGBIN, NORMAL, POISSON, B200SnpLinAlg, IHTResult, IHTVariable, mIHTResult, mIHTVariable,
+                  is_multivariate, allocate_fold_and_k,
                   canonicallink, cross_validate, cv_iht, fit_iht, iht, meanloss, parse_covariates)
 
 __all__ = ["B200SnpLinAlg", "IHTResult", "IHTVariable", "fit_iht", "cv_iht", "allocate_fold_and_k", "meanloss",

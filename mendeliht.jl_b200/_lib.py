@@ -91,6 +91,13 @@ SIGNATURES = {
     "ihtb_fit_predict": [_p, _u8, _f64],
     "ihtb_fit_timer": [_p, C.c_int32, _f64],
     "ihtb_fit_destroy": [_p],
+    "ihtb_mvfit_create": [_p, _f64, C.c_int64, _f64, C.c_int64, C.POINTER(Cfg), _pp],
+    "ihtb_mvfit_set_k": [_p, C.c_int64],
+    "ihtb_mvfit_init": [_p, _u8],
+    "ihtb_mvfit_run": [_p, C.POINTER(Result), C.POINTER(IterTrace), C.c_int64],
+    "ihtb_mvfit_get": [_p, _f64, _f64, _f64, _f64],
+    "ihtb_mvfit_predict": [_p, _u8, _f64],
+    "ihtb_mvfit_destroy": [_p],
     "ihtb_comm_unique_id": [C.c_char_p, _u8],
     "ihtb_comm_create": [C.c_char_p, _u8, C.c_int32, C.c_int32, _pp],
     "ihtb_comm_destroy": [_p],

@@ -222,6 +222,115 @@ class IHTVariable:
             pass
 
 
+@dataclass
+class mIHTResult:
+    """`mIHTResult` (src/data_structures.jl:263-275)."""
+    time: float
+    logl: float
+    iter: int
+    beta: np.ndarray      # r x p
+    c: np.ndarray         # r x q
+    k: int
+    traits: int
+    Sigma: np.ndarray
+    sigma_g: np.ndarray
+    trace: list = field(default_factory=list)
+    n_sweeps: int = 0
+    n_backtracks: int = 0
+    sweep_seconds: float = 0.0
+    n_launches: int = 0
+
+
+def is_multivariate(y) -> bool:
+    """`is_multivariate` (src/multivariate.jl:481-483)."""
+    y = np.asarray(y)
+    return y.ndim == 2 and y.shape[0] > 1 and y.shape[1] > 1
+
+
+class mIHTVariable:
+    """`mIHTVariable` (src/data_structures.jl:140-180).  Reference layout on the Python side: Y is r x n, Z is q x n
+    (samples are columns); `x` is the n x p genotype operator whose transpose the reference passes."""
+
+    def __init__(self, x: B200SnpLinAlg, z, y, k, zkeep=None, tol=1e-4, max_iter=200, min_iter=5, max_step=3,
+                 sweep_mode=_lib.SWEEP_FAST):
+        Y = np.asarray(y, dtype=np.float64)
+        Z = np.asarray(z, dtype=np.float64)
+        if Z.ndim == 1:
+            Z = Z.reshape(1, -1)
+        r, n = Y.shape
+        if not (n == x.n == Z.shape[1]):
+            raise _lib.DimensionMismatch(
+                _lib.IHTB_EDIM, f"number of samples in y, x, and z = {n}, {x.n}, {Z.shape[1]} are not equal")
+        q = Z.shape[0]
+        if zkeep is not None:
+            zk = np.asarray(zkeep, dtype=bool)
+            if zk.shape[0] != q:
+                raise _lib.DimensionMismatch(_lib.IHTB_EDIM, f"zkeep must have length {q} but was {zk.shape[0]}")
+            if not zk.all():
+                raise NotImplementedError("multivariate zkeep with false entries is ill-defined in the reference")
+        self.x, self.n, self.p, self.q, self.r = x, n, x.p, q, r
+        self.cfg = Cfg(0, 0, int(k), 1.0, float(tol), int(max_iter), int(min_iter), int(max_step), int(sweep_mode))
+        Yc = np.asfortranarray(Y.T)      # n x r column-major
+        Zc = np.asfortranarray(Z.T)      # n x q column-major
+        self._h = C.c_void_p()
+        check(load().ihtb_mvfit_create(x._h, Yc.ctypes.data_as(C.POINTER(C.c_double)), r,
+                                       Zc.ctypes.data_as(C.POINTER(C.c_double)), q, C.byref(self.cfg),
+                                       C.byref(self._h)))
+
+    def set_k(self, k):
+        check(load().ihtb_mvfit_set_k(self._h, int(k)))
+
+    def init_iht_indices(self, train_mask=None):
+        m = None if train_mask is None else np.ascontiguousarray(train_mask, dtype=np.uint8)
+        check(load().ihtb_mvfit_init(self._h, ptr(m, C.c_uint8) if m is not None else None))
+
+    def fit(self, trace_cap=None):
+        cap = int(self.cfg.max_iter) if trace_cap is None else trace_cap
+        res = Result()
+        tr = (IterTrace * max(cap, 1))()
+        check(load().ihtb_mvfit_run(self._h, C.byref(res), tr, cap))
+        n_it = min(int(res.n_steps), cap)
+        return res, [(tr[i].logl, tr[i].backtracks, tr[i].tol, tr[i].eta, tr[i].n_candidates) for i in range(n_it)]
+
+    def get(self):
+        beta = np.empty((self.r, self.p), order="F"); c = np.empty((self.r, self.q), order="F")
+        S = np.empty((self.r, self.r)); sg = np.empty(self.r)
+        check(load().ihtb_mvfit_get(self._h, beta.ctypes.data_as(C.POINTER(C.c_double)),
+                                    c.ctypes.data_as(C.POINTER(C.c_double)), ptr(S, C.c_double), ptr(sg, C.c_double)))
+        return np.ascontiguousarray(beta), np.ascontiguousarray(c), S, sg
+
+    def predict(self, test_mask=None) -> float:
+        m = None if test_mask is None else np.ascontiguousarray(test_mask, dtype=np.uint8)
+        out = C.c_double(0.0)
+        check(load().ihtb_mvfit_predict(self._h, ptr(m, C.c_uint8) if m is not None else None, C.byref(out)))
+        return float(out.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().ihtb_mvfit_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _fit_mv(y, x, z, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode) -> mIHTResult:
+    if z is None:
+        z = np.ones((1, x.n))
+    v = mIHTVariable(x, z, y, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode)
+    try:
+        v.init_iht_indices(None)
+        res, trace = v.fit()
+        beta, c, S, sg = v.get()
+    finally:
+        v.close()
+    return mIHTResult(res.time, res.logl, int(res.iter), beta, c, k, v.r, S, sg, trace, int(res.n_sweeps),
+                      int(res.n_backtracks), res.sweep_seconds, int(res.n_launches))
+
+
 def _check_args(k, max_iter, max_step, tol):
     # the reference's @assert lines (src/fit.jl:87-90, src/utilities.jl:913)
     if max_iter < 0:
@@ -239,6 +348,8 @@ def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est
             comm=None, p_global=None) -> IHTResult:
     """`fit_iht(y, x, z; k, d, l, zkeep, tol, max_iter, min_iter, max_step)` (src/fit.jl:60-118)."""
     _check_args(k, max_iter, max_step, tol)
+    if is_multivariate(y):      # d = MvNormal: Y is r x n, Z is q x n (src/fit.jl:66,125)
+        return _fit_mv(y, x, z, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode)
     if est_r != "None":
         raise NotImplementedError("est_r = :MM / :Newton is not implemented on the device path yet")
     if not x.center:
@@ -291,13 +402,17 @@ def cv_iht(y, x: B200SnpLinAlg, z=None, d=NORMAL, l=None, path=range(1, 21), q=5
     if folds is None:
         folds = np.random.default_rng().integers(1, q + 1, size=x.n)
     folds = np.asarray(folds)
+    mv = is_multivariate(y)
     if z is None:
-        z = np.ones(x.n)
+        z = np.ones((1, x.n)) if mv else np.ones(x.n)
     l = l or "IdentityLink"
     grid = allocate_fold_and_k(q, path)
     todo = range(len(grid)) if combos is None else combos
     mses = np.zeros(len(grid)); iters = np.zeros(len(grid), dtype=np.int64)
-    v = IHTVariable(x, z, y, max(path), d, l, zkeep, nb_r, 1e-4, max_iter, min_iter, 3, sweep_mode)
+    if mv:
+        v = mIHTVariable(x, z, y, max(path), zkeep, 1e-4, max_iter, min_iter, 3, sweep_mode)
+    else:
+        v = IHTVariable(x, z, y, max(path), d, l, zkeep, nb_r, 1e-4, max_iter, min_iter, 3, sweep_mode)
     try:
         for i in todo:
             fold, k = grid[i]

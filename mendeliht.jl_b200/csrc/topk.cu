@@ -27,15 +27,17 @@ __device__ __forceinline__ void hist_flush(const int* sh, int* g, int nb) {
 // pass 0: keys + histogram of the top 11 bits of keyL
 __global__ void __launch_bounds__(TK_THREADS)
 k_keys_hist0(int64_t p, const double* __restrict__ dfa, const double* __restrict__ b0d,
-             const double* __restrict__ sinv, double eta, double bound, uint32_t* __restrict__ keyL,
-             uint32_t* __restrict__ keyU, int* __restrict__ hist) {
+             const double* __restrict__ sinv, int64_t p_mod, const double* __restrict__ bounds, double eta,
+             double bound, uint32_t* __restrict__ keyL, uint32_t* __restrict__ keyU, int* __restrict__ hist) {
     __shared__ int sh[TK_BINS];
     for (int b = threadIdx.x; b < TK_BINS; b += blockDim.x) sh[b] = 0;
     __syncthreads();
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p; j += (int64_t)gridDim.x * blockDim.x) {
         double v = b0d[j] + eta * dfa[j];
         double a = fabs(v);
-        double e = fabs(eta) * sinv[j] * bound + a * 4e-16;
+        // blocked form (multivariate: entry j = t*p_mod + column): per-block bound, sinv of the column
+        const double bj = bounds ? bounds[j / p_mod] : bound;
+        double e = fabs(eta) * sinv[bounds ? (j % p_mod) : j] * bj + a * 4e-16;
         double lo = a - e, up = a + e;
         if (!(lo > 0.0)) lo = 0.0;          // also maps NaN to 0
         if (!(up >= 0.0)) up = INFINITY;    // NaN: always a candidate
@@ -133,18 +135,30 @@ __global__ void k_scatter(double* __restrict__ dst, const int64_t* __restrict__ 
     if (t < k) dst[idx[t]] = zero_only ? 0.0 : val[t];
 }
 
-void topk_candidates(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, double eta,
-                     double bound, int64_t k, cudaStream_t s) {
+static void topk_run(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, int64_t p_mod,
+                     const double* d_bounds, double eta, double bound, int64_t k, cudaStream_t s) {
     int grid = tk_grid(c.p);
     int kk = (int)(k < c.p ? k : c.p);
     IHTB_LAUNCH(k_topk_reset, 1, 1, 0, s, c.st, kk);
-    IHTB_LAUNCH(k_keys_hist0, grid, TK_THREADS, 0, s, c.p, d_dfa, d_b0d, d_sinv, eta, bound, c.keyL, c.keyU, c.hist);
+    IHTB_LAUNCH(k_keys_hist0, grid, TK_THREADS, 0, s, c.p, d_dfa, d_b0d, d_sinv, p_mod, d_bounds, eta, bound, c.keyL,
+                c.keyU, c.hist);
     IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 21, 11);
     IHTB_LAUNCH(k_hist, grid, TK_THREADS, 0, s, c.p, c.keyL, c.st, 10, 11, c.hist);
     IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 10, 11);
     IHTB_LAUNCH(k_hist, grid, TK_THREADS, 0, s, c.p, c.keyL, c.st, 0, 10, c.hist);
     IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 0, 10);
     IHTB_LAUNCH(k_compact, grid, TK_THREADS, 0, s, c.p, c.keyU, c.st, c.cand, c.cap);
+}
+
+void topk_candidates(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, double eta,
+                     double bound, int64_t k, cudaStream_t s) {
+    topk_run(c, d_dfa, d_b0d, d_sinv, c.p, nullptr, eta, bound, k, s);
+}
+
+// entries e = t*p_mod + j (t-th right-hand side of column j): bound d_bounds[t], scale d_sinv[j]
+void topk_candidates_blocked(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, int64_t p_mod,
+                             const double* d_bounds, double eta, int64_t k, cudaStream_t s) {
+    topk_run(c, d_dfa, d_b0d, d_sinv, p_mod, d_bounds, eta, 0.0, k, s);
 }
 
 void scatter_dense(double* d_dst, const int64_t* d_idx, const double* d_val, int64_t k, int zero_only,

@@ -182,7 +182,7 @@ def test_file_wrappers_on_bundled_plink(tmp_path, normal_data):
     shutil.copy(os.path.join(GOLDEN, "normal.bed"), tmp_path / "normal.bed")
     with open(tmp_path / "normal.fam", "w") as f:
         for i, yi in enumerate(normal_data["y"]):
-            f.write(f"{i + 1}\t1\t0\t0\t1\t{yi!r}\n")
+            f.write(f"{i + 1}\t1\t0\t0\t1\t{float(yi)!r}\n")
     shutil.copy(os.path.join(GOLDEN, "covariates.txt"), tmp_path / "covariates.txt")
     res = m.iht(str(tmp_path / "normal"), 7, "Normal", covariates=str(tmp_path / "covariates.txt"),
                 summaryfile=str(tmp_path / "iht.summary.txt"), betafile=str(tmp_path / "iht.beta.txt"))
@@ -193,3 +193,72 @@ def test_file_wrappers_on_bundled_plink(tmp_path, normal_data):
     mse = m.cross_validate(str(tmp_path / "normal"), "Normal", path=[5, 7, 9], q=3,
                            covariates=str(tmp_path / "covariates.txt"), folds=folds)
     assert mse.shape == (3,) and np.all(mse > 0)
+
+
+# ---- multivariate Normal (BASELINE config 4 family) ---------------------------------------------------------------
+def _mv_data(seed, n, p, r, k):
+    rng = np.random.default_rng(seed)
+    bed = synth.packed_columns(seed, n, np.arange(p))
+    idx = np.sort(rng.permutation(p)[:k])
+    xs = synth.standardized_columns(seed, n, idx)
+    B = np.zeros((r, k))
+    for c in range(k):
+        B[rng.integers(0, r), c] = rng.normal() * 0.8
+    A = rng.normal(size=(r, r)); cov = A @ A.T / r + np.eye(r) * 0.5
+    E = np.linalg.cholesky(cov) @ rng.normal(size=(r, n))
+    Z = np.vstack([np.ones(n), rng.normal(size=n)])
+    Cm = rng.normal(size=(r, 2)) * 0.5
+    Y = B @ xs.T + Cm @ Z + E
+    return bed, Y, Z
+
+
+def _compare_mv(res, ref, rtol=RTOL):
+    assert res.iter == ref.iter
+    assert np.array_equal(res.beta != 0, ref.beta != 0)
+    np.testing.assert_allclose(res.beta, ref.beta, rtol=rtol, atol=1e-12)
+    np.testing.assert_allclose(res.c, ref.c, rtol=rtol, atol=1e-12)
+    assert abs(res.logl - ref.logl) <= rtol * abs(ref.logl)
+    np.testing.assert_allclose(res.Sigma, ref.Sigma, rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(res.sigma_g, ref.sigma_g, rtol=rtol)
+    assert [t[1] for t in res.trace] == ref.trace.backtracks
+    np.testing.assert_allclose([t[0] for t in res.trace], ref.trace.logl, rtol=rtol)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("n,p,r,k", [(1200, 2500, 2, 8), (1500, 2000, 3, 9), (1003, 1500, 5, 10)])
+def test_mv_fit_matches_oracle(n, p, r, k, mode):
+    from oracle import mviht
+    bed, Y, Z = _mv_data(40 + r, n, p, r, k)
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    res = m.fit_iht(Y, g, Z, k=k + 2, sweep_mode=mode)
+    ref = mviht.fit_mv_iht(Y, snp.SnpLinAlgOracle(bed, n), Z, k=k + 2)
+    assert isinstance(res, m.mIHTResult) and res.traits == r
+    _compare_mv(res, ref)
+
+
+def test_mv_bundled_fixture():
+    """Bundled data/multivariate.* (r = 2), k = 10: same support as the survey probe / oracle."""
+    from oracle import mviht
+    Y = np.loadtxt(os.path.join(GOLDEN, "multivariate_y.txt")).T
+    n = Y.shape[1]
+    bed = snp.read_bed(os.path.join(GOLDEN, "multivariate.bed"), n)
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    res = m.fit_iht(Y, g, None, k=10)
+    ref = mviht.fit_mv_iht(Y, snp.SnpLinAlgOracle(bed, n), None, k=10)
+    _compare_mv(res, ref)
+    assert list(np.flatnonzero(res.beta[0]) + 1) == [134, 442, 450, 1891, 2557, 3243, 3931, 9289]
+    assert list(np.flatnonzero(res.beta[1]) + 1) == [1014, 5214]
+
+
+def test_mv_cv_and_errors():
+    from oracle import cv as ocv2
+    bed, Y, Z = _mv_data(77, 900, 1200, 2, 5)
+    g = m.B200SnpLinAlg.from_bed_columns(bed, 900)
+    folds = synth.folds_for(3, 900, 3)
+    mses, iters = m.cv_iht(Y, g, Z, path=[2, 5, 8], q=3, folds=folds, return_grid=True)
+    _, rgrid, riters = ocv2.cv_iht(Y, snp.SnpLinAlgOracle(bed, 900), Z, path=[2, 5, 8], q=3, folds=folds,
+                                   return_grid=True)
+    assert np.array_equal(iters, riters)
+    np.testing.assert_allclose(mses, rgrid, rtol=RTOL)
+    with pytest.raises(m.DimensionMismatch):
+        m.fit_iht(Y[:, :-1], g, Z, k=3)          # test/multivariate_test.jl:109-110
