@@ -20,6 +20,7 @@
 #include <cmath>
 #include <memory>
 #include <mutex>
+#include <string.h>
 #include <unordered_map>
 
 namespace ihtb {
@@ -47,8 +48,9 @@ struct ihtb_fit {
     ihtb_comm* comm = nullptr;
     int64_t j0 = 0, p_global = 0;
     std::vector<int64_t> shard_j0;        // j0 of every rank
-    DBuf<int64_t> d_selall;
-    HBuf<int64_t> h_selall;
+    DBuf<int64_t> d_selall, d_pack, d_packall;
+    HBuf<int64_t> h_selall, h_packall;
+    int capx = 512;                       // per-rank capacity of the (index, value) candidate exchange
     ihtb_cfg cfg{};
     cudaStream_t s = nullptr;
     std::vector<uint8_t> zkeep;
@@ -145,18 +147,20 @@ struct ihtb_fit {
     }
 
     // ---- exact df_j for a list of columns (cached until the next sweep) --------------------------
-    void exact_df(const std::vector<int64_t>& cols) {
+    // exchange = false (sharded fits): only this rank's columns are computed; the others arrive later piggy-backed on
+    // a collective that is needed anyway (stepsize all-reduce / candidate all-gather)
+    void exact_df(const std::vector<int64_t>& cols, bool exchange = true) {
         std::vector<int64_t> need;
         for (int64_t j : cols)
-            if (!df_exact.count(j)) need.push_back(j);
-        if (need.empty()) return;
+            if (!df_exact.count(j) && (exchange || is_local(j))) need.push_back(j);
+        if (need.empty()) { if (!exchange) sync(); return; }
         IHTB_CHECK((int64_t)need.size() <= (int64_t)d_cols.n, IHTB_ENUMERIC, "too many columns to re-score");
         // columns of other shards are marked -1: the kernel writes 0 for them and the all-reduce fills them in
         std::vector<int64_t> loc(need.size());
         for (size_t t = 0; t < need.size(); ++t) loc[t] = is_local(need[t]) ? need[t] - j0 : -1;
         upload(d_cols.p, loc.data(), loc.size());
         xt_gather(g, d_cols.p, (int64_t)need.size(), d_r.p, 1, d_vbar.p, d_gout.p, s);   // d_vbar = mean(r), set by score
-        comm_allreduce_sum_f64(comm, d_gout.p, need.size(), s);
+        if (exchange) comm_allreduce_sum_f64(comm, d_gout.p, need.size(), s);
         IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_gout.p, need.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
         sync();
         for (size_t t = 0; t < need.size(); ++t) df_exact[need[t]] = h_gout.p[t];
@@ -177,7 +181,7 @@ struct ihtb_fit {
         df_exact.clear();
         df_sparse = false;
         if (!idx.empty()) {
-            exact_df(idx);                                   // syncs the stream
+            exact_df(idx, /*exchange=*/comm == nullptr);     // syncs the stream
         } else {
             sync();
         }
@@ -203,8 +207,31 @@ struct ihtb_fit {
     double stepsize() {
         std::vector<double> coef(idx.size());
         double numer = 0.0;
-        for (size_t t = 0; t < idx.size(); ++t) { coef[t] = df_at(idx[t]); numer += coef[t] * coef[t]; }
-        support_matvec(idx, coef, d_xs.p);
+        const bool piggyback = comm && !df_sparse && !idx.empty();
+        if (piggyback) {
+            // sharded: each rank knows the exact df of its own support columns only.  Its partial X*df needs nothing
+            // else, and the k values ride behind the n-vector in the same all-reduce (other ranks contribute zeros).
+            std::vector<int64_t> ii; std::vector<double> vv, tail(idx.size(), 0.0);
+            for (size_t t = 0; t < idx.size(); ++t)
+                if (is_local(idx[t])) {
+                    double v = df_exact.at(idx[t]);
+                    tail[t] = v;
+                    if (v != 0.0) { ii.push_back(idx[t] - j0); vv.push_back(v); }
+                }
+            if (ii.empty()) {
+                IHTB_CUDA(cudaMemsetAsync(d_xs.p, 0, n * sizeof(double), s));
+            } else {
+                upload(d_idx.p, ii.data(), ii.size());
+                upload(d_coef.p, vv.data(), vv.size());
+                x_support(g, d_idx.p, (int64_t)ii.size(), d_coef.p, 1, d_xs.p, s);
+            }
+            upload(d_xs.p + n, tail.data(), tail.size());
+            comm_allreduce_sum_f64(comm, d_xs.p, (size_t)n + idx.size(), s);
+            IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_xs.p + n, idx.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        } else {
+            for (size_t t = 0; t < idx.size(); ++t) { coef[t] = df_at(idx[t]); numer += coef[t] * coef[t]; }
+            support_matvec(idx, coef, d_xs.p);
+        }
         std::vector<double> d2((size_t)q);
         for (int64_t l = 0; l < q; ++l) {
             d2[l] = idc[l] ? df2[l] : 0.0;
@@ -213,6 +240,11 @@ struct ihtb_fit {
         upload(d_small.p + q, d2.data(), (size_t)q);
         glm_stepsize(glm, d_small.p + q, d_xs.p, s);
         readback_scal(1);
+        if (piggyback)
+            for (size_t t = 0; t < idx.size(); ++t) {
+                df_exact[idx[t]] = h_gout.p[t];
+                numer += h_gout.p[t] * h_gout.p[t];
+            }
         double denom = h_scal.p[0];
         double eta = numer / denom;
         if (std::isinf(eta) || std::isnan(eta)) eta = 1e-8;
@@ -264,6 +296,55 @@ struct ihtb_fit {
         return out;
     }
 
+    // Sharded candidate exchange in ONE collective: every rank re-scores its own local top-k candidates (and its part
+    // of the previous support) exactly, then all-gathers (index, exact df) pairs.  Returns the global candidate list;
+    // df_exact holds their values afterwards.
+    std::vector<int64_t> sharded_candidates(double eta) {
+        std::vector<int64_t> L;
+        if (cfg.k > 0) {
+            topk_candidates(tk, d_dfa.p, d_b0d.p, g->sinv.p, eta, bound, cfg.k, s);
+            IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + cap) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            sync();
+            const TopkState* st = reinterpret_cast<const TopkState*>(h_sel.p);
+            IHTB_CHECK(st->count <= cap, IHTB_ENUMERIC, "degenerate projection: too many entries within the error bound");
+            for (int t = 0; t < st->count; ++t) L.push_back(h_sel.p[2 + t] + j0);
+        }
+        for (int64_t j : idx0)
+            if (is_local(j)) L.push_back(j);
+        std::sort(L.begin(), L.end());
+        L.erase(std::unique(L.begin(), L.end()), L.end());
+        IHTB_CHECK((int)L.size() <= capx, IHTB_ENUMERIC,
+                   "too many local top-k candidates for the sharded exchange (" + std::to_string(L.size()) + ")");
+        std::vector<int64_t> loc(L.size());
+        for (size_t t = 0; t < L.size(); ++t) loc[t] = L[t] - j0;
+        const int nr = nranks();
+        const size_t blk = 2 + 2 * (size_t)capx;
+        if (!L.empty()) {
+            upload(d_cols.p, loc.data(), loc.size());
+            upload(d_sidx.p, L.data(), L.size());
+            xt_gather(g, d_cols.p, (int64_t)L.size(), d_r.p, 1, d_vbar.p, d_gout.p, s);
+        }
+        pack_candidates(d_pack.p, (int64_t)L.size(), d_sidx.p, d_gout.p, capx, s);
+        comm_allgather_i64(comm, d_pack.p, d_packall.p, blk, s);
+        IHTB_CUDA(cudaMemcpyAsync(h_packall.p, d_packall.p, nr * blk * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        sync();
+        n_cand_iter += (int64_t)L.size();
+        std::vector<int64_t> cand;
+        for (int r = 0; r < nr; ++r) {
+            const int64_t* b_ = h_packall.p + (size_t)r * blk;
+            const int64_t cnt = b_[0];
+            for (int64_t t = 0; t < cnt; ++t) {
+                double v;
+                memcpy(&v, &b_[2 + capx + t], sizeof(double));
+                df_exact[b_[2 + t]] = v;
+                cand.push_back(b_[2 + t]);
+            }
+        }
+        std::sort(cand.begin(), cand.end());
+        cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+        return cand;
+    }
+
     static double b_lookup(const std::vector<int64_t>& ii, const std::vector<double>& vv, int64_t j) {
         auto it = std::lower_bound(ii.begin(), ii.end(), j);
         return (it != ii.end() && *it == j) ? vv[it - ii.begin()] : 0.0;
@@ -275,13 +356,15 @@ struct ihtb_fit {
         std::vector<int64_t> cand;
         if (df_sparse) {
             cand = dfs_idx;
+        } else if (comm) {
+            cand = sharded_candidates(eta);      // already includes every rank's part of idx0, values in df_exact
         } else {
             cand = device_candidates(eta);
         }
         cand.insert(cand.end(), idx0.begin(), idx0.end());
         std::sort(cand.begin(), cand.end());
         cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
-        if (!df_sparse) exact_df(cand);
+        if (!df_sparse && !comm) exact_df(cand);
 
         struct Item { double a; int64_t pos; double v; };
         std::vector<Item> items;
@@ -389,9 +472,14 @@ struct ihtb_fit {
         glm_update(1);        // zc = Z c, mu (the reference does not clamp here; xb = 0 and |c1| is small)
         score_and_sweep();
         // first k entries chosen from the largest gradient; df itself becomes its projection (:417-425)
-        std::vector<int64_t> cand = device_candidates(1.0);
-        std::sort(cand.begin(), cand.end());
-        exact_df(cand);
+        std::vector<int64_t> cand;
+        if (comm) {
+            cand = sharded_candidates(1.0);
+        } else {
+            cand = device_candidates(1.0);
+            std::sort(cand.begin(), cand.end());
+            exact_df(cand);
+        }
         struct Item { double a; int64_t pos; double v; };
         std::vector<Item> items;
         for (int64_t j : cand) { double v = df_exact.at(j); items.push_back({std::fabs(v), j, v}); }
@@ -529,7 +617,7 @@ static ihtb_fit* fit_allocate(const ihtb_geno* g, int64_t q, int cap) {
     IHTB_CUDA(cudaEventCreate(&f->ev0));
     IHTB_CUDA(cudaEventCreate(&f->ev1));
     f->d_y.alloc(n); f->d_z.alloc(n * q); f->d_w.alloc(n); f->d_xb.alloc(n); f->d_zc.alloc(n); f->d_mu.alloc(n);
-    f->d_r.alloc(n); f->d_xs.alloc(n); f->d_dfa.alloc(p); f->d_b0d.alloc(p); f->d_mask.alloc(n);
+    f->d_r.alloc(n); f->d_xs.alloc(n + 2 * (size_t)cap + 64); f->d_dfa.alloc(p); f->d_b0d.alloc(p); f->d_mask.alloc(n);
     f->d_part.alloc((size_t)GLM_MAX_BLOCKS * (2 + q)); f->d_scal.alloc(2 + q + 8); f->d_small.alloc(2 * q);
     size_t cols_cap = 2 * (size_t)cap + 64;
     f->d_coef.alloc(cols_cap); f->d_gout.alloc(cols_cap); f->d_vbar.alloc(1); f->d_sval.alloc(cols_cap);
@@ -580,6 +668,13 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
             if (f->d_selall.n < (size_t)nr * (2 + cap)) {
                 f->d_selall.alloc((size_t)nr * (2 + cap));
                 f->h_selall.alloc((size_t)nr * (2 + cap));
+            }
+            f->capx = (int)std::min<int64_t>(cap, std::max<int64_t>(512, 2 * cfg->k + 256));
+            const size_t blk = 2 + 2 * (size_t)f->capx;
+            if (f->d_packall.n < (size_t)nr * blk) {
+                f->d_pack.alloc(blk);
+                f->d_packall.alloc((size_t)nr * blk);
+                f->h_packall.alloc((size_t)nr * blk);
             }
             // exchange the shard offsets once (reuses the candidate buffers)
             int64_t mine = g->j0;

@@ -161,6 +161,22 @@ void topk_candidates_blocked(TopkCtx& c, const double* d_dfa, const double* d_b0
     topk_run(c, d_dfa, d_b0d, d_sinv, p_mod, d_bounds, eta, 0.0, k, s);
 }
 
+// block = [count, 0, idx[capx], bits(val)[capx]] for the sharded candidate all-gather
+__global__ void k_pack_candidates(int64_t* __restrict__ block, int64_t count, const int64_t* __restrict__ gidx,
+                                  const double* __restrict__ vals, int capx) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t == 0) { block[0] = count; block[1] = 0; }
+    if (t < count) {
+        block[2 + t] = gidx[t];
+        block[2 + capx + t] = __double_as_longlong(vals[t]);
+    }
+}
+void pack_candidates(int64_t* d_block, int64_t count, const int64_t* d_gidx, const double* d_vals, int capx,
+                     cudaStream_t s) {
+    IHTB_LAUNCH(k_pack_candidates, (unsigned)ceil_div(count > 0 ? count : 1, 128), 128, 0, s, d_block, count, d_gidx,
+                d_vals, capx);
+}
+
 void scatter_dense(double* d_dst, const int64_t* d_idx, const double* d_val, int64_t k, int zero_only,
                    cudaStream_t s) {
     if (k == 0) return;
