@@ -52,12 +52,14 @@ typedef struct ihtb_cfg {
     int32_t dist;        /* IHTB_NORMAL ...                                   `d`        */
     int32_t link;        /* IHTB_LINK_*                                       `l`        */
     int64_t k;           /* sparsity                                          `k`        */
-    double  nb_r;        /* NegativeBinomial r (fixed; est_r = :None)         `d.r`      */
+    double  nb_r;        /* NegativeBinomial r (starting value when est_r != 0)  `d.r`    */
     double  tol;         /* 1e-4                                              `tol`      */
     int32_t max_iter;    /* 200 (100 in cv_iht)                               `max_iter` */
     int32_t min_iter;    /* 5                                                 `min_iter` */
     int32_t max_step;    /* 3                                                 `max_step` */
     int32_t sweep_mode;  /* IHTB_SWEEP_FAST | IHTB_SWEEP_EXACT                           */
+    int32_t est_r;       /* 0 = :None, 1 = :MM, 2 = :Newton (NegativeBinomial only)   `est_r`    */
+    int32_t reserved;
 } ihtb_cfg;
 
 /* IHTResult (src/data_structures.jl:245-258); beta/c are written through ihtb_fit_get */

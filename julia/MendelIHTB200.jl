@@ -67,7 +67,7 @@ end
 # ---- fit_iht on the device -----------------------------------------------------------------------------------
 struct Cfg
     dist::Int32; link::Int32; k::Int64; nb_r::Float64; tol::Float64
-    max_iter::Int32; min_iter::Int32; max_step::Int32; sweep_mode::Int32
+    max_iter::Int32; min_iter::Int32; max_step::Int32; sweep_mode::Int32; est_r::Int32; reserved::Int32
 end
 mutable struct CResult
     time::Float64; logl::Float64; iter::Int64; sigma_g::Float64; n_sweeps::Int64; n_backtracks::Int64
@@ -85,11 +85,12 @@ function fit_iht(y::AbstractVector{Float64}, x::B200SnpLinAlg, z::AbstractVecOrM
                  k::Int=10, J::Int=1, d::Distribution=Normal(), l::Link=IdentityLink(),
                  zkeep::BitVector=trues(size(z, 2)), est_r::Symbol=:None, tol::Float64=1e-4, max_iter::Int=200,
                  min_iter::Int=5, max_step::Int=3, verbose::Bool=false, io::IO=stdout, kwargs...)
-    est_r == :None || error("est_r is not supported on the device path yet")
+    est = est_r == :None ? Int32(0) : est_r == :MM ? Int32(1) : est_r == :Newton ? Int32(2) :
+          throw(ArgumentError("Only support method is Newton or MM, but got $est_r"))
     x.center || error("x is not centered! Please construct SnpLinAlg{Float64}(::SnpArray, center=true, scale=true)")
     zm = z isa AbstractVector ? reshape(z, :, 1) : Matrix(z)
     r = d isa NegativeBinomial ? d.r : 1.0
-    cfg = Ref(Cfg(distcode(d), linkcode(l), k, r, tol, max_iter, min_iter, max_step, 0))
+    cfg = Ref(Cfg(distcode(d), linkcode(l), k, r, tol, max_iter, min_iter, max_step, 0, est, 0))
     fh = Ref{Ptr{Cvoid}}(C_NULL)
     keep = UInt8.(zkeep)
     check(ccall((:ihtb_fit_create, LIB), Int32,
@@ -116,7 +117,7 @@ function cv_iht(y::AbstractVector{Float64}, x::B200SnpLinAlg, z::AbstractVecOrMa
     maximum(path) > size(x, 2) && error("Sparsity level in `path` cannot be larger than total number of variables")
     zm = z isa AbstractVector ? reshape(z, :, 1) : Matrix(z)
     r = d isa NegativeBinomial ? d.r : 1.0
-    cfg = Ref(Cfg(distcode(d), linkcode(l), maximum(path), r, 1e-4, max_iter, min_iter, 3, 0))
+    cfg = Ref(Cfg(distcode(d), linkcode(l), maximum(path), r, 1e-4, max_iter, min_iter, 3, 0, 0, 0))
     fh = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ihtb_fit_create, LIB), Int32,
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{UInt8}, Ref{Cfg}, Ref{Ptr{Cvoid}}),

@@ -44,7 +44,7 @@ _EXC = {IHTB_EINVAL: IHTBError, IHTB_EDIM: DimensionMismatch, IHTB_EDOMAIN: IHTB
 class Cfg(C.Structure):
     _fields_ = [("dist", C.c_int32), ("link", C.c_int32), ("k", C.c_int64), ("nb_r", C.c_double),
                 ("tol", C.c_double), ("max_iter", C.c_int32), ("min_iter", C.c_int32), ("max_step", C.c_int32),
-                ("sweep_mode", C.c_int32)]
+                ("sweep_mode", C.c_int32), ("est_r", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Result(C.Structure):

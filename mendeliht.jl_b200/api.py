@@ -20,6 +20,7 @@ from ._lib import Cfg, IterTrace, Result, check, f64, load, ptr
 
 NORMAL, BERNOULLI, POISSON, NEGBIN = "Normal", "Bernoulli", "Poisson", "NegativeBinomial"
 DIST_ID = {NORMAL: 0, BERNOULLI: 1, POISSON: 2, NEGBIN: 3}
+EST_R_ID = {"None": 0, "MM": 1, "Newton": 2}
 LINK_ID = {"IdentityLink": 0, "LogitLink": 1, "LogLink": 2, "ProbitLink": 3, "CloglogLink": 4, "CauchitLink": 5,
            "SqrtLink": 6, "InverseLink": 7, "InverseSquareLink": 8}
 
@@ -152,7 +153,8 @@ class IHTVariable:
     """`IHTVariable` (src/data_structures.jl:4-43): one fit's device workspace."""
 
     def __init__(self, x: B200SnpLinAlg, z, y, k, d=NORMAL, l="IdentityLink", zkeep=None, nb_r=1.0, tol=1e-4,
-                 max_iter=200, min_iter=5, max_step=3, sweep_mode=_lib.SWEEP_FAST, comm=None, p_global=None):
+                 max_iter=200, min_iter=5, max_step=3, sweep_mode=_lib.SWEEP_FAST, comm=None, p_global=None,
+                 est_r="None"):
         y = f64(y)
         z = np.asarray(z, dtype=np.float64)
         if z.ndim == 1:
@@ -170,8 +172,13 @@ class IHTVariable:
         self.comm = comm
         self.p_global = int(p_global) if (comm is not None and p_global is not None) else x.p
         self.x, self.n, self.p, self.q, self.d = x, n, self.p_global, q, d
+        if est_r not in EST_R_ID:
+            raise ValueError(f"Only support method is Newton or MM, but got {est_r}")
+        if est_r != "None" and d != NEGBIN:
+            raise _lib.IHTBError(_lib.IHTB_EINVAL, "Only negative binomial regression currently supports nuisance "
+                                                   "parameter estimation")
         self.cfg = Cfg(DIST_ID[d], LINK_ID[l], int(k), float(nb_r), float(tol), int(max_iter), int(min_iter),
-                       int(max_step), int(sweep_mode))
+                       int(max_step), int(sweep_mode), EST_R_ID[est_r], 0)
         zf = np.asfortranarray(z)
         self._h = C.c_void_p()
         check(load().ihtb_fit_create_sharded(x._h, comm._h if comm is not None else None, self.p_global,
@@ -269,7 +276,8 @@ class mIHTVariable:
             if not zk.all():
                 raise NotImplementedError("multivariate zkeep with false entries is ill-defined in the reference")
         self.x, self.n, self.p, self.q, self.r = x, n, x.p, q, r
-        self.cfg = Cfg(0, 0, int(k), 1.0, float(tol), int(max_iter), int(min_iter), int(max_step), int(sweep_mode))
+        self.cfg = Cfg(0, 0, int(k), 1.0, float(tol), int(max_iter), int(min_iter), int(max_step), int(sweep_mode),
+                       0, 0)
         Yc = np.asfortranarray(Y.T)      # n x r column-major
         Zc = np.asfortranarray(Z.T)      # n x q column-major
         self._h = C.c_void_p()
@@ -350,15 +358,14 @@ def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est
     _check_args(k, max_iter, max_step, tol)
     if is_multivariate(y):      # d = MvNormal: Y is r x n, Z is q x n (src/fit.jl:66,125)
         return _fit_mv(y, x, z, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode)
-    if est_r != "None":
-        raise NotImplementedError("est_r = :MM / :Newton is not implemented on the device path yet")
     if not x.center:
         raise _lib.IHTBError(_lib.IHTB_EUNSUPPORTED, "x is not centered! Please construct SnpLinAlg{Float64}"
                                                      "(::SnpArray, center=true, scale=true)")
     if z is None:
         z = np.ones(x.n)
     l = l or "IdentityLink"
-    v = IHTVariable(x, z, y, k, d, l, zkeep, nb_r, tol, max_iter, min_iter, max_step, sweep_mode, comm, p_global)
+    v = IHTVariable(x, z, y, k, d, l, zkeep, nb_r, tol, max_iter, min_iter, max_step, sweep_mode, comm, p_global,
+                    est_r)
     try:
         v.init_iht_indices(None)
         res, trace = v.fit()

@@ -76,7 +76,7 @@ struct ihtb_fit {
     // host model state (k-sparse)
     std::vector<int64_t> idx, idx0, best_idx, b0d_idx;
     std::vector<double> b, b0, best_b;
-    std::vector<double> c, c0, best_c, df2;
+    std::vector<double> c, c0, best_c, df2, h_y, h_mu;
     std::vector<uint8_t> idc, idc0;
     std::unordered_map<int64_t, double> df_exact;
     bool df_sparse = false;
@@ -144,6 +144,89 @@ struct ihtb_fit {
             return -0.5 * (dev / phi) - sw * (0.5 * std::log(2.0 * M_PI) + std::log(sigma));
         }
         return lp;
+    }
+
+    // ---- mle_for_r: nuisance parameter of the negative binomial (src/utilities.jl:141-247) ---------------
+    // n-vector loops on the host (mu and y are copied back); the loglikelihood of the Newton line search runs on
+    // the device through glm_update.  Like the reference, the estimate persists in the fit variable (v.d).
+    static double digamma(double x) {
+        double r = 0.0;
+        while (x < 6.0) { r -= 1.0 / x; x += 1.0; }
+        double f = 1.0 / (x * x);
+        return r + std::log(x) - 0.5 / x -
+               f * (1.0 / 12 - f * (1.0 / 120 - f * (1.0 / 252 - f * (1.0 / 240 - f * (1.0 / 132)))));
+    }
+    static double trigamma(double x) {
+        double r = 0.0;
+        while (x < 6.0) { r += 1.0 / (x * x); x += 1.0; }
+        double f = 1.0 / (x * x);
+        return r + 1.0 / x + f / 2 + f / x * (1.0 / 6 - f * (1.0 / 30 - f * (1.0 / 42 - f * (1.0 / 30))));
+    }
+    void fetch_mu() {
+        h_mu.resize((size_t)n);
+        IHTB_CUDA(cudaMemcpyAsync(h_mu.data(), d_mu.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        sync();
+    }
+    double nb_logl(double r) {            // negbin_loglikelihood(r): v.d = NegativeBinomial(r); loglikelihood(v)
+        glm.nb_r = r;
+        return glm_update(1);
+    }
+    void mle_for_r() {
+        fetch_mu();
+        const std::vector<double>& y = h_y;
+        double r = glm.nb_r;
+        if (cfg.est_r == 1) {             // update_r_MM (:158-173)
+            double num = 0.0, den = 0.0;
+            for (int64_t i = 0; i < n; ++i) {
+                for (int64_t j = 0; j <= (int64_t)y[i] - 1; ++j) num += r / (r + (double)j);
+                den += std::log(r / (r + h_mu[i]));
+            }
+            glm.nb_r = -num / den;
+            return;
+        }
+        // update_r_newton (:180-247)
+        auto d1 = [&](double rr) {
+            double a = 0.0;
+            for (int64_t i = 0; i < n; ++i)
+                a += -(y[i] + rr) / (h_mu[i] + rr) - std::log(h_mu[i] + rr) + 1.0 + std::log(rr) + digamma(rr + y[i]) -
+                     digamma(rr);
+            return a;
+        };
+        auto d2 = [&](double rr) {
+            double a = 0.0;
+            for (int64_t i = 0; i < n; ++i)
+                a += (y[i] + rr) / ((h_mu[i] + rr) * (h_mu[i] + rr)) - 2.0 / (h_mu[i] + rr) + 1.0 / rr +
+                     trigamma(rr + y[i]) - trigamma(rr);
+            return a;
+        };
+        double new_r = 1.0, stepsize = 1.0;
+        for (int it = 0; it < 100; ++it) {
+            double dx = d1(r), dx2 = d2(r);
+            double increment = dx2 < 0 ? dx / dx2 : dx;
+            new_r = r - stepsize * increment;
+            double old_logl = nb_logl(r);
+            for (int j = 0; j < 20; ++j) {
+                if (new_r <= 0) {
+                    stepsize /= 2; new_r = r - stepsize * increment;
+                } else {
+                    double new_logl = nb_logl(new_r);
+                    if (old_logl >= new_logl) { stepsize /= 2; new_r = r - stepsize * increment; }
+                    else break;
+                }
+            }
+            if (std::fabs(r - new_r) <= 1e-6) { glm.nb_r = new_r; return; }
+            r = new_r;
+        }
+        glm.nb_r = r;
+    }
+    // update_mu!; [mle_for_r]; loglikelihood  (src/fit.jl:226-240, src/utilities.jl:966-972)
+    double mu_r_logl() {
+        double l = glm_update(1);
+        if (cfg.est_r != 0) {
+            mle_for_r();
+            l = glm_update(1);
+        }
+        return l;
     }
 
     // ---- exact df_j for a list of columns (cached until the next sweep) --------------------------
@@ -511,14 +594,14 @@ struct ihtb_fit {
         eta = stepsize();
         gradstep(eta);
         update_xb();
-        new_logl = glm_update(1);
+        new_logl = mu_r_logl();
         eta_step = 0;
         while (old_logl > new_logl && eta_step < cfg.max_step) {    // _iht_backtrack_ (src/utilities.jl:484-486)
             eta /= 2;
             idx = idx0; b = b0; c = c0;                              // backtrack! (src/utilities.jl:959-973)
             gradstep(eta);
             update_xb();
-            new_logl = glm_update(1);
+            new_logl = mu_r_logl();
             ++eta_step;
             ++n_backtracks;
         }
@@ -691,6 +774,10 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
         for (auto v : f->zkeep) f->zkeepn += v;
         f->inited = false; f->sweep_pending = false;
         f->n_sweeps = 0; f->n_backtracks = 0; f->sweep_ms_total = 0.0;
+        IHTB_CHECK(cfg->est_r == 0 || cfg->dist == IHTB_NEGBIN, IHTB_EINVAL,
+                   "Only negative binomial regression currently supports nuisance parameter estimation");
+        IHTB_CHECK(cfg->est_r >= 0 && cfg->est_r <= 2, IHTB_EINVAL, "Only support method is Newton or MM");
+        if (cfg->est_r != 0) f->h_y.assign(y, y + n); else f->h_y.clear();
         IHTB_CUDA(cudaMemcpyAsync(f->d_y.p, y, n * sizeof(double), cudaMemcpyHostToDevice, f->s));
         IHTB_CUDA(cudaMemcpyAsync(f->d_z.p, z, n * q * sizeof(double), cudaMemcpyHostToDevice, f->s));
         f->d_xb.zero(f->s); f->d_zc.zero(f->s);

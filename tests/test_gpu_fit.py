@@ -262,3 +262,19 @@ def test_mv_cv_and_errors():
     np.testing.assert_allclose(mses, rgrid, rtol=RTOL)
     with pytest.raises(m.DimensionMismatch):
         m.fit_iht(Y[:, :-1], g, Z, k=3)          # test/multivariate_test.jl:109-110
+
+
+@pytest.mark.parametrize("est_r", ["MM", "Newton"])
+def test_negbin_nuisance_estimation(est_r):
+    """test/L0_reg_test.jl:245-297: est_r = :MM / :Newton for NegativeBinomial; compared with the oracle's mle_for_r."""
+    n, p, k = 1500, 2000, 5
+    y, z, _, _, _ = synth.simulate_response(91, n, p, k, "NegativeBinomial", nb_r=5.0)
+    bed = synth.packed_columns(91, n, np.arange(p))
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    res = m.fit_iht(y, g, z, k=k + 1, d="NegativeBinomial", l="LogLink", est_r=est_r, nb_r=1.0)
+    ref = iht.fit_iht(y, snp.SnpLinAlgOracle(bed, n), z, k=k + 1, d=glm.NEGBIN, l=glm.LOG, est_r=est_r, nb_r=1.0)
+    assert res.iter == ref.iter and np.array_equal(np.flatnonzero(res.beta), np.flatnonzero(ref.beta))
+    np.testing.assert_allclose(res.beta, ref.beta, rtol=1e-5, atol=1e-10)
+    assert abs(res.logl - ref.logl) <= 1e-6 * abs(ref.logl)
+    with pytest.raises(m.IHTBError):
+        m.fit_iht(y, g, z, k=3, d="Poisson", l="LogLink", est_r="MM")

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     import mendeliht_jl_b200 as m
-    assert ctypes.sizeof(m._lib.Cfg) == 48
+    assert ctypes.sizeof(m._lib.Cfg) == 56
     assert ctypes.sizeof(m._lib.Result) == 72
     assert ctypes.sizeof(m._lib.IterTrace) == 32
 
