@@ -197,6 +197,10 @@ def run_ours(args):
     m._lib.check(lib.ihtb_fit_timer(v._h, 1, C.byref(ms)))
     l_timed = m.launch_count() - l_before
     t_value = ms.value * 1e-3
+    ph = (C.c_double * 4)()
+    m._lib.check(lib.ihtb_fit_phase_times(v._h, ph))
+    phases = {k: ph[i] / max(iters + args.warmup * (iters // max(args.steps, 1)), 1) * 1e3
+              for i, k in enumerate(["stepsize_ms", "gradstep_ms", "xb_glm_ms", "score_sweep_ms"])}
     beta, c, _, _ = v.get()
     v.close()
 
@@ -242,7 +246,7 @@ def run_ours(args):
         "config": workload_config(1),
         "iterations_per_fit": iters / args.steps, "sweeps_per_fit": sweeps / args.steps,
         "sweep_ms_in_fit": sweep_s / max(sweeps - args.steps, 1) * 1e3,
-        "sweep_share_of_step": sweep_s / t_value,
+        "sweep_share_of_step": sweep_s / t_value, "host_phase_ms_per_iteration": phases,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "k_sweep_lut",
                      "algorithmic_bytes_per_launch": abytes, "kernel_ms": mk.value,

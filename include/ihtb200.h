@@ -136,6 +136,8 @@ int32_t ihtb_fit_get(const ihtb_fit* f, double* beta, double* c, double* mu, dou
 int32_t ihtb_fit_predict(ihtb_fit* f, const uint8_t* test_mask, double* deviance);   /* predict! (src/cross_validation.jl:279-286) */
 /* CUDA-event stopwatch on the fit's stream: which=0 start, which=1 stop (elapsed device milliseconds in *ms) */
 int32_t ihtb_fit_timer(ihtb_fit* f, int32_t which, double* ms);
+/* measurement hook: host wall-clock seconds in [stepsize, gradstep, update_xb+loglikelihood, score+sweep] */
+int32_t ihtb_fit_phase_times(const ihtb_fit* f, double* out4);
 int32_t ihtb_fit_destroy(ihtb_fit* f);
 
 /* ---- multivariate Normal fit (mIHTVariable, src/multivariate.jl; fit_iht(Y, Transpose(xla), Z), src/fit.jl:60-118) ----

@@ -90,6 +90,7 @@ SIGNATURES = {
     "ihtb_fit_get": [_p, _f64, _f64, _f64, _f64],
     "ihtb_fit_predict": [_p, _u8, _f64],
     "ihtb_fit_timer": [_p, C.c_int32, _f64],
+    "ihtb_fit_phase_times": [_p, _f64],
     "ihtb_fit_destroy": [_p],
     "ihtb_mvfit_create": [_p, _f64, C.c_int64, _f64, C.c_int64, C.POINTER(Cfg), _pp],
     "ihtb_mvfit_set_k": [_p, C.c_int64],

@@ -590,22 +590,36 @@ struct ihtb_fit {
     }
 
     // ---- iht_one_step! (src/fit.jl:213-263) --------------------------------------------------------
+    // host wall-clock per phase (seconds): stepsize, gradstep, xb + glm, score + sweep (ihtb_fit_phase_times)
+    double phase[4] = {0, 0, 0, 0};
+    static double now() {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
     void one_step(double old_logl, double& eta, int& eta_step, double& new_logl) {
+        double t0 = now();
         eta = stepsize();
+        double t1 = now(); phase[0] += t1 - t0;
         gradstep(eta);
+        double t2 = now(); phase[1] += t2 - t1;
         update_xb();
         new_logl = mu_r_logl();
+        double t3 = now(); phase[2] += t3 - t2;
         eta_step = 0;
         while (old_logl > new_logl && eta_step < cfg.max_step) {    // _iht_backtrack_ (src/utilities.jl:484-486)
             eta /= 2;
             idx = idx0; b = b0; c = c0;                              // backtrack! (src/utilities.jl:959-973)
+            double u0 = now();
             gradstep(eta);
+            double u1 = now(); phase[1] += u1 - u0;
             update_xb();
             new_logl = mu_r_logl();
+            phase[2] += now() - u1;
             ++eta_step;
             ++n_backtracks;
         }
+        double t4 = now();
         score_and_sweep();
+        phase[3] += now() - t4;
         IHTB_CHECK(!std::isnan(new_logl), IHTB_ENUMERIC, "Loglikelihood function is NaN, aborting...");
         IHTB_CHECK(!std::isinf(new_logl), IHTB_ENUMERIC, "Loglikelihood function is Inf, aborting...");
     }
@@ -774,6 +788,7 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
         for (auto v : f->zkeep) f->zkeepn += v;
         f->inited = false; f->sweep_pending = false;
         f->n_sweeps = 0; f->n_backtracks = 0; f->sweep_ms_total = 0.0;
+        for (int i = 0; i < 4; ++i) f->phase[i] = 0.0;
         IHTB_CHECK(cfg->est_r == 0 || cfg->dist == IHTB_NEGBIN, IHTB_EINVAL,
                    "Only negative binomial regression currently supports nuisance parameter estimation");
         IHTB_CHECK(cfg->est_r >= 0 && cfg->est_r <= 2, IHTB_EINVAL, "Only support method is Newton or MM");
@@ -863,6 +878,14 @@ int32_t ihtb_fit_timer(ihtb_fit* f, int32_t which, double* ms) {
             IHTB_CUDA(cudaEventElapsedTime(&t, f->tm0, f->tm1));
             if (ms) *ms = t;
         }
+    });
+}
+
+// host wall-clock seconds spent in [stepsize, gradstep, update_xb + loglikelihood, score + sweep] since creation
+int32_t ihtb_fit_phase_times(const ihtb_fit* f, double* out4) {
+    return guard([&] {
+        IHTB_CHECK(f && out4, IHTB_EINVAL, "NULL argument");
+        for (int i = 0; i < 4; ++i) out4[i] = f->phase[i];
     });
 }
 

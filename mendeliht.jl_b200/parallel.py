@@ -128,6 +128,10 @@ def bench_sharded(args, rank, world, local_rank, G):
     check(lib.ihtb_fit_timer(v._h, 1, C.byref(ms)))
     dist.barrier(); torch.cuda.synchronize()
     launches = _lib.launch_count() - l0
+    ph = (C.c_double * 4)()
+    check(lib.ihtb_fit_phase_times(v._h, ph))
+    n_it_all = max(iters * (args.steps + args.warmup) // max(args.steps, 1), 1)
+    phases = {k: ph[i] / n_it_all * 1e3 for i, k in enumerate(["stepsize_ms", "gradstep_ms", "xb_glm_ms", "score_sweep_ms"])}
     t = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_value = float(t.item()) * 1e-3
@@ -165,6 +169,7 @@ def bench_sharded(args, rank, world, local_rank, G):
             "config": G["workload_config"](world),
             "iterations_per_fit": iters / args.steps, "sweeps_per_fit": sweeps / args.steps,
             "sweep_ms_in_fit": sweep_s / max(sweeps - args.steps, 1) * 1e3, "sweep_share_of_step": sweep_s / t_value,
+            "host_phase_ms_per_iteration": phases,
             "packed_bytes_swept_per_sec_all_gpus": sweeps * G["sweep_bytes"](n, p) / t_value,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "k_sweep_lut (per GPU, slowest rank)",
