@@ -79,6 +79,7 @@ struct ihtb_fit {
     std::vector<double> c, c0, best_c, df2, h_y, h_mu;
     std::vector<uint8_t> idc, idc0;
     std::unordered_map<int64_t, double> df_exact;
+    std::vector<int64_t> cand_cache;      // candidate columns of the last sweep (global indices, sorted)
     bool df_sparse = false;
     std::vector<int64_t> dfs_idx;
     std::vector<double> dfs_val;
@@ -251,8 +252,12 @@ struct ihtb_fit {
     }
 
     // ---- score! : r, df2 = Z'r, df = X'r (src/utilities.jl:126-135) ------------------------------
-    // One host round trip: the sweep and the exact re-scoring of the current support are enqueued right behind the
-    // residual kernel (the mean of r stays on the device), and all scalars come back with the gather results.
+    // One host round trip for everything that follows a sweep.  Enqueued back to back on the stream:
+    //   k_score -> mean(r) -> sweep -> eta-independent candidate selection (top-(k+|supp|) of |df| with the sweep's
+    //   error bound, computed on the device) -> exact FP64 re-scoring of those candidates and of the current support
+    //   [-> sharded: one all-gather of (index, exact value) pairs].
+    // The top-k of |b0 + eta*df| always lies in supp(b0) plus the k largest |df_j| outside it, for ANY eta, so the
+    // gradient step and all its backtracks are then pure host work on ~2k exact values.
     void score_and_sweep() {
         glm_score(glm, s);                                   // scal: sum r, sum |r|, df2[q]
         glm_mean_from_sum(glm, d_vbar.p, s);                 // d_vbar[0] = scal[0] / n
@@ -261,21 +266,79 @@ struct ihtb_fit {
         sweep_xt_v_with_means(g, d_r.p, d_vbar.p, 1, d_dfa.p, cfg.sweep_mode, s, sweep_scratch, nullptr);
         IHTB_CUDA(cudaEventRecord(ev1, s));
         ++n_sweeps;
-        df_exact.clear();
+        df_exact.clear(); cand_cache.clear();
         df_sparse = false;
-        if (!idx.empty()) {
-            exact_df(idx, /*exchange=*/comm == nullptr);     // syncs the stream
-        } else {
-            sync();
+        const double coef = cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound;
+        // this rank's part of the current support (local indices)
+        std::vector<int64_t> supp_loc;
+        for (int64_t j : idx)
+            if (is_local(j)) supp_loc.push_back(j - j0);
+        const int nsupp = (int)supp_loc.size();
+        int glaunch = 0;
+        if (cfg.k > 0) {
+            const int64_t ksel = cfg.k + (int64_t)idx.size();
+            topk_candidates_absdf(tk, d_dfa.p, g->sinv.p, d_scal.p, coef, ksel, s);
+            glaunch = (int)std::min<int64_t>(comm ? capx / 2 : cap, ksel + 64);
+            xt_gather(g, tk.cand, glaunch, d_r.p, 1, d_vbar.p, d_gout.p, s);      // slots beyond the count hold -1
         }
+        if (nsupp) {
+            upload(d_cols.p, supp_loc.data(), supp_loc.size());
+            xt_gather(g, d_cols.p, nsupp, d_r.p, 1, d_vbar.p, d_gout.p + glaunch, s);
+        }
+        if (!comm) {
+            IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + glaunch) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_gout.p, (glaunch + nsupp) * sizeof(double), cudaMemcpyDeviceToHost, s));
+            sync();
+            const TopkState* st = reinterpret_cast<const TopkState*>(h_sel.p);
+            const int count = cfg.k > 0 ? st->count : 0;
+            IHTB_CHECK(count <= cap, IHTB_ENUMERIC,
+                       "degenerate projection: more than " + std::to_string(cap) +
+                           " entries lie within the sweep error bound of the k-th largest |gradient|");
+            for (int t = 0; t < std::min(count, glaunch); ++t) {
+                df_exact[h_sel.p[2 + t]] = h_gout.p[t];
+                cand_cache.push_back(h_sel.p[2 + t]);
+            }
+            for (int t = 0; t < nsupp; ++t) df_exact[supp_loc[t]] = h_gout.p[glaunch + t];
+            if (count > glaunch) {                       // rare: many near-ties; fetch and re-score the remainder
+                IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + count) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+                sync();
+                std::vector<int64_t> rest(h_sel.p + 2 + glaunch, h_sel.p + 2 + count);
+                exact_df(rest);
+                cand_cache.insert(cand_cache.end(), rest.begin(), rest.end());
+            }
+        } else {
+            const int nr = nranks();
+            const size_t blk = 2 + 2 * (size_t)capx;
+            IHTB_CHECK(nsupp <= capx / 2, IHTB_ENUMERIC, "support too large for the sharded candidate exchange");
+            pack_sweep_candidates(d_pack.p, reinterpret_cast<const TopkState*>(d_sel.p), tk.cand, glaunch, d_gout.p,
+                                  d_cols.p, nsupp, d_gout.p + glaunch, j0, capx, s);
+            comm_allgather_i64(comm, d_pack.p, d_packall.p, blk, s);
+            IHTB_CUDA(cudaMemcpyAsync(h_packall.p, d_packall.p, nr * blk * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            sync();
+            for (int r = 0; r < nr; ++r) {
+                const int64_t* b_ = h_packall.p + (size_t)r * blk;
+                IHTB_CHECK(b_[0] <= glaunch, IHTB_ENUMERIC,
+                           "degenerate projection: too many local candidates within the sweep error bound");
+                for (int t = 0; t < capx; ++t) {
+                    const int64_t j = b_[2 + t];
+                    if (j < 0) continue;
+                    double v;
+                    memcpy(&v, &b_[2 + capx + t], sizeof(double));
+                    df_exact[j] = v;
+                    if (t < capx / 2) cand_cache.push_back(j);
+                }
+            }
+        }
+        std::sort(cand_cache.begin(), cand_cache.end());
+        cand_cache.erase(std::unique(cand_cache.begin(), cand_cache.end()), cand_cache.end());
+        n_cand_iter += (int64_t)cand_cache.size();
         float ms = 0.f;
         IHTB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
         sweep_ms_total += ms;
         double rsum = h_scal.p[0], rl1 = h_scal.p[1];
         for (int64_t l = 0; l < q; ++l) df2[l] = h_scal.p[2 + l];
         rbar = rsum / (double)n;
-        double ul1 = rl1 + (double)n * std::fabs(rbar);    // >= ||r - rbar||_1
-        bound = (cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound) * ul1;
+        bound = coef * (rl1 + std::fabs(rsum));              // same value the selection kernel used
     }
 
     double df_at(int64_t j) const {
@@ -290,31 +353,8 @@ struct ihtb_fit {
     double stepsize() {
         std::vector<double> coef(idx.size());
         double numer = 0.0;
-        const bool piggyback = comm && !df_sparse && !idx.empty();
-        if (piggyback) {
-            // sharded: each rank knows the exact df of its own support columns only.  Its partial X*df needs nothing
-            // else, and the k values ride behind the n-vector in the same all-reduce (other ranks contribute zeros).
-            std::vector<int64_t> ii; std::vector<double> vv, tail(idx.size(), 0.0);
-            for (size_t t = 0; t < idx.size(); ++t)
-                if (is_local(idx[t])) {
-                    double v = df_exact.at(idx[t]);
-                    tail[t] = v;
-                    if (v != 0.0) { ii.push_back(idx[t] - j0); vv.push_back(v); }
-                }
-            if (ii.empty()) {
-                IHTB_CUDA(cudaMemsetAsync(d_xs.p, 0, n * sizeof(double), s));
-            } else {
-                upload(d_idx.p, ii.data(), ii.size());
-                upload(d_coef.p, vv.data(), vv.size());
-                x_support(g, d_idx.p, (int64_t)ii.size(), d_coef.p, 1, d_xs.p, s);
-            }
-            upload(d_xs.p + n, tail.data(), tail.size());
-            comm_allreduce_sum_f64(comm, d_xs.p, (size_t)n + idx.size(), s);
-            IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_xs.p + n, idx.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-        } else {
-            for (size_t t = 0; t < idx.size(); ++t) { coef[t] = df_at(idx[t]); numer += coef[t] * coef[t]; }
-            support_matvec(idx, coef, d_xs.p);
-        }
+        for (size_t t = 0; t < idx.size(); ++t) { coef[t] = df_at(idx[t]); numer += coef[t] * coef[t]; }
+        support_matvec(idx, coef, d_xs.p);
         std::vector<double> d2((size_t)q);
         for (int64_t l = 0; l < q; ++l) {
             d2[l] = idc[l] ? df2[l] : 0.0;
@@ -323,11 +363,6 @@ struct ihtb_fit {
         upload(d_small.p + q, d2.data(), (size_t)q);
         glm_stepsize(glm, d_small.p + q, d_xs.p, s);
         readback_scal(1);
-        if (piggyback)
-            for (size_t t = 0; t < idx.size(); ++t) {
-                df_exact[idx[t]] = h_gout.p[t];
-                numer += h_gout.p[t] * h_gout.p[t];
-            }
         double denom = h_scal.p[0];
         double eta = numer / denom;
         if (std::isinf(eta) || std::isnan(eta)) eta = 1e-8;
@@ -350,84 +385,6 @@ struct ihtb_fit {
         }
     }
 
-    // candidates of the device selection over |b0 + eta*df| (dense df from the last sweep)
-    std::vector<int64_t> device_candidates(double eta) {
-        std::vector<int64_t> out;
-        if (cfg.k <= 0) return out;
-        topk_candidates(tk, d_dfa.p, d_b0d.p, g->sinv.p, eta, bound, cfg.k, s);   // local top-k (k clamped to p)
-        const int64_t* hs = h_sel.p;
-        const int nr = nranks();
-        if (nr > 1) {
-            // every rank's [state | candidates] block: the global top-k is inside the union of the local top-k's
-            comm_allgather_i64(comm, d_sel.p, d_selall.p, (size_t)(2 + cap), s);
-            IHTB_CUDA(cudaMemcpyAsync(h_selall.p, d_selall.p, (size_t)nr * (2 + cap) * sizeof(int64_t),
-                                      cudaMemcpyDeviceToHost, s));
-            hs = h_selall.p;
-        } else {
-            IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + cap) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-        }
-        sync();
-        for (int r = 0; r < nr; ++r) {
-            const int64_t* blk = hs + (size_t)r * (2 + cap);
-            const TopkState* st = reinterpret_cast<const TopkState*>(blk);
-            IHTB_CHECK(st->count <= cap, IHTB_ENUMERIC,
-                       "degenerate projection: more than " + std::to_string(cap) +
-                           " entries lie within the sweep error bound of the k-th largest magnitude");
-            const int64_t off = (nr > 1) ? shard_j0[r] : j0;
-            for (int t = 0; t < st->count; ++t) out.push_back(blk[2 + t] + off);
-        }
-        return out;
-    }
-
-    // Sharded candidate exchange in ONE collective: every rank re-scores its own local top-k candidates (and its part
-    // of the previous support) exactly, then all-gathers (index, exact df) pairs.  Returns the global candidate list;
-    // df_exact holds their values afterwards.
-    std::vector<int64_t> sharded_candidates(double eta) {
-        std::vector<int64_t> L;
-        if (cfg.k > 0) {
-            topk_candidates(tk, d_dfa.p, d_b0d.p, g->sinv.p, eta, bound, cfg.k, s);
-            IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + cap) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-            sync();
-            const TopkState* st = reinterpret_cast<const TopkState*>(h_sel.p);
-            IHTB_CHECK(st->count <= cap, IHTB_ENUMERIC, "degenerate projection: too many entries within the error bound");
-            for (int t = 0; t < st->count; ++t) L.push_back(h_sel.p[2 + t] + j0);
-        }
-        for (int64_t j : idx0)
-            if (is_local(j)) L.push_back(j);
-        std::sort(L.begin(), L.end());
-        L.erase(std::unique(L.begin(), L.end()), L.end());
-        IHTB_CHECK((int)L.size() <= capx, IHTB_ENUMERIC,
-                   "too many local top-k candidates for the sharded exchange (" + std::to_string(L.size()) + ")");
-        std::vector<int64_t> loc(L.size());
-        for (size_t t = 0; t < L.size(); ++t) loc[t] = L[t] - j0;
-        const int nr = nranks();
-        const size_t blk = 2 + 2 * (size_t)capx;
-        if (!L.empty()) {
-            upload(d_cols.p, loc.data(), loc.size());
-            upload(d_sidx.p, L.data(), L.size());
-            xt_gather(g, d_cols.p, (int64_t)L.size(), d_r.p, 1, d_vbar.p, d_gout.p, s);
-        }
-        pack_candidates(d_pack.p, (int64_t)L.size(), d_sidx.p, d_gout.p, capx, s);
-        comm_allgather_i64(comm, d_pack.p, d_packall.p, blk, s);
-        IHTB_CUDA(cudaMemcpyAsync(h_packall.p, d_packall.p, nr * blk * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-        sync();
-        n_cand_iter += (int64_t)L.size();
-        std::vector<int64_t> cand;
-        for (int r = 0; r < nr; ++r) {
-            const int64_t* b_ = h_packall.p + (size_t)r * blk;
-            const int64_t cnt = b_[0];
-            for (int64_t t = 0; t < cnt; ++t) {
-                double v;
-                memcpy(&v, &b_[2 + capx + t], sizeof(double));
-                df_exact[b_[2 + t]] = v;
-                cand.push_back(b_[2 + t]);
-            }
-        }
-        std::sort(cand.begin(), cand.end());
-        cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
-        return cand;
-    }
-
     static double b_lookup(const std::vector<int64_t>& ii, const std::vector<double>& vv, int64_t j) {
         auto it = std::lower_bound(ii.begin(), ii.end(), j);
         return (it != ii.end() && *it == j) ? vv[it - ii.begin()] : 0.0;
@@ -437,17 +394,10 @@ struct ihtb_fit {
     // Ties at the k-th magnitude: lowest position in [b; c] wins (the reference prunes at random, :444-458).
     void gradstep(double eta) {
         std::vector<int64_t> cand;
-        if (df_sparse) {
-            cand = dfs_idx;
-        } else if (comm) {
-            cand = sharded_candidates(eta);      // already includes every rank's part of idx0, values in df_exact
-        } else {
-            cand = device_candidates(eta);
-        }
+        cand = df_sparse ? dfs_idx : cand_cache;     // chosen once per sweep, exact values already in df_exact
         cand.insert(cand.end(), idx0.begin(), idx0.end());
         std::sort(cand.begin(), cand.end());
         cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
-        if (!df_sparse && !comm) exact_df(cand);
 
         struct Item { double a; int64_t pos; double v; };
         std::vector<Item> items;
@@ -555,14 +505,7 @@ struct ihtb_fit {
         glm_update(1);        // zc = Z c, mu (the reference does not clamp here; xb = 0 and |c1| is small)
         score_and_sweep();
         // first k entries chosen from the largest gradient; df itself becomes its projection (:417-425)
-        std::vector<int64_t> cand;
-        if (comm) {
-            cand = sharded_candidates(1.0);
-        } else {
-            cand = device_candidates(1.0);
-            std::sort(cand.begin(), cand.end());
-            exact_df(cand);
-        }
+        std::vector<int64_t> cand = cand_cache;      // top-k of |df| with exact values (score_and_sweep)
         struct Item { double a; int64_t pos; double v; };
         std::vector<Item> items;
         for (int64_t j : cand) { double v = df_exact.at(j); items.push_back({std::fabs(v), j, v}); }
@@ -766,7 +709,7 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
                 f->d_selall.alloc((size_t)nr * (2 + cap));
                 f->h_selall.alloc((size_t)nr * (2 + cap));
             }
-            f->capx = (int)std::min<int64_t>(cap, std::max<int64_t>(512, 2 * cfg->k + 256));
+            f->capx = (int)std::max<int64_t>(1024, 2 * (2 * cfg->k + 64 + 64));   // candidates | support halves
             const size_t blk = 2 + 2 * (size_t)f->capx;
             if (f->d_packall.n < (size_t)nr * blk) {
                 f->d_pack.alloc(blk);

@@ -28,12 +28,16 @@ __device__ __forceinline__ void hist_flush(const int* sh, int* g, int nb) {
 __global__ void __launch_bounds__(TK_THREADS)
 k_keys_hist0(int64_t p, const double* __restrict__ dfa, const double* __restrict__ b0d,
              const double* __restrict__ sinv, int64_t p_mod, const double* __restrict__ bounds, double eta,
-             double bound, uint32_t* __restrict__ keyL, uint32_t* __restrict__ keyU, int* __restrict__ hist) {
+             double bound, const double* __restrict__ scal, double bound_coef, uint32_t* __restrict__ keyL,
+             uint32_t* __restrict__ keyU, int* __restrict__ hist) {
+    // scal != NULL: the bound comes from the score kernel's sums still on the device:
+    // bound = coef * (sum|r| + |sum r|) >= coef * ||r - mean(r)||_1 (no host round trip between sweep and selection)
+    if (scal) bound = bound_coef * (scal[1] + fabs(scal[0]));
     __shared__ int sh[TK_BINS];
     for (int b = threadIdx.x; b < TK_BINS; b += blockDim.x) sh[b] = 0;
     __syncthreads();
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p; j += (int64_t)gridDim.x * blockDim.x) {
-        double v = b0d[j] + eta * dfa[j];
+        double v = (b0d ? b0d[j] : 0.0) + eta * dfa[j];
         double a = fabs(v);
         // blocked form (multivariate: entry j = t*p_mod + column): per-block bound, sinv of the column
         const double bj = bounds ? bounds[j / p_mod] : bound;
@@ -136,12 +140,13 @@ __global__ void k_scatter(double* __restrict__ dst, const int64_t* __restrict__ 
 }
 
 static void topk_run(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, int64_t p_mod,
-                     const double* d_bounds, double eta, double bound, int64_t k, cudaStream_t s) {
+                     const double* d_bounds, double eta, double bound, int64_t k, cudaStream_t s,
+                     const double* d_scal = nullptr, double bound_coef = 0.0) {
     int grid = tk_grid(c.p);
     int kk = (int)(k < c.p ? k : c.p);
     IHTB_LAUNCH(k_topk_reset, 1, 1, 0, s, c.st, kk);
-    IHTB_LAUNCH(k_keys_hist0, grid, TK_THREADS, 0, s, c.p, d_dfa, d_b0d, d_sinv, p_mod, d_bounds, eta, bound, c.keyL,
-                c.keyU, c.hist);
+    IHTB_LAUNCH(k_keys_hist0, grid, TK_THREADS, 0, s, c.p, d_dfa, d_b0d, d_sinv, p_mod, d_bounds, eta, bound, d_scal,
+                bound_coef, c.keyL, c.keyU, c.hist);
     IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 21, 11);
     IHTB_LAUNCH(k_hist, grid, TK_THREADS, 0, s, c.p, c.keyL, c.st, 10, 11, c.hist);
     IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 10, 11);
@@ -153,6 +158,16 @@ static void topk_run(TopkCtx& c, const double* d_dfa, const double* d_b0d, const
 void topk_candidates(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, double eta,
                      double bound, int64_t k, cudaStream_t s) {
     topk_run(c, d_dfa, d_b0d, d_sinv, c.p, nullptr, eta, bound, k, s);
+}
+
+// candidates by |df_j| alone (eta-independent): the top-k of |b0 + eta*df| always lies in supp(b0) plus the k largest
+// |df_j| outside the support, whatever eta is, so ONE selection per sweep serves the gradient step and all of its
+// backtracks.  The error bound is computed on the device from the score sums d_scal = [sum r, sum |r|, ...].
+void topk_candidates_absdf(TopkCtx& c, const double* d_dfa, const double* d_sinv, const double* d_scal,
+                           double bound_coef, int64_t k, cudaStream_t s) {
+    // unused candidate slots stay -1 so that a gather launched over a fixed number of slots can skip them
+    IHTB_CUDA(cudaMemsetAsync(c.cand, 0xFF, (size_t)c.cap * sizeof(int64_t), s));
+    topk_run(c, d_dfa, nullptr, d_sinv, c.p, nullptr, 1.0, 0.0, k, s, d_scal, bound_coef);
 }
 
 // entries e = t*p_mod + j (t-th right-hand side of column j): bound d_bounds[t], scale d_sinv[j]
@@ -171,6 +186,34 @@ __global__ void k_pack_candidates(int64_t* __restrict__ block, int64_t count, co
         block[2 + capx + t] = __double_as_longlong(vals[t]);
     }
 }
+// Sharded fits, once per sweep: block = [n_cand, n_supp, idx[capx], bits(val)[capx]]; slots [0, capx/2) hold this rank's
+// device-selected candidates (local index + j0, exact df from the gather over the first `glaunch` slots), slots
+// [capx/2, capx) its part of the current support.
+__global__ void k_pack_sweep(int64_t* __restrict__ block, const TopkState* __restrict__ st,
+                             const int64_t* __restrict__ cand, int glaunch, const double* __restrict__ cand_vals,
+                             const int64_t* __restrict__ supp, int nsupp, const double* __restrict__ supp_vals,
+                             int64_t j0, int capx) {
+    const int half = capx / 2;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) { block[0] = st->count; block[1] = nsupp; }
+    if (t < half) {
+        const bool ok = t < st->count && t < glaunch;
+        block[2 + t] = ok ? cand[t] + j0 : -1;
+        block[2 + capx + t] = ok ? __double_as_longlong(cand_vals[t]) : 0;
+    } else if (t < capx) {
+        const int u = t - half;
+        const bool ok = u < nsupp;
+        block[2 + t] = ok ? supp[u] + j0 : -1;
+        block[2 + capx + t] = ok ? __double_as_longlong(supp_vals[u]) : 0;
+    }
+}
+void pack_sweep_candidates(int64_t* d_block, const TopkState* d_st, const int64_t* d_cand, int glaunch,
+                           const double* d_cand_vals, const int64_t* d_supp, int nsupp, const double* d_supp_vals,
+                           int64_t j0, int capx, cudaStream_t s) {
+    IHTB_LAUNCH(k_pack_sweep, (unsigned)ceil_div(capx, 128), 128, 0, s, d_block, d_st, d_cand, glaunch, d_cand_vals,
+                d_supp, nsupp, d_supp_vals, j0, capx);
+}
+
 void pack_candidates(int64_t* d_block, int64_t count, const int64_t* d_gidx, const double* d_vals, int capx,
                      cudaStream_t s) {
     IHTB_LAUNCH(k_pack_candidates, (unsigned)ceil_div(count > 0 ? count : 1, 128), 128, 0, s, d_block, count, d_gidx,

@@ -24,6 +24,11 @@ void topk_candidates(TopkCtx& c, const double* d_dfa, const double* d_b0d, const
                      double bound, int64_t k, cudaStream_t s);
 void topk_candidates_blocked(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, int64_t p_mod,
                              const double* d_bounds, double eta, int64_t k, cudaStream_t s);
+void topk_candidates_absdf(TopkCtx& c, const double* d_dfa, const double* d_sinv, const double* d_scal,
+                           double bound_coef, int64_t k, cudaStream_t s);
+void pack_sweep_candidates(int64_t* d_block, const TopkState* d_st, const int64_t* d_cand, int glaunch,
+                           const double* d_cand_vals, const int64_t* d_supp, int nsupp, const double* d_supp_vals,
+                           int64_t j0, int capx, cudaStream_t s);
 void pack_candidates(int64_t* d_block, int64_t count, const int64_t* d_gidx, const double* d_vals, int capx,
                      cudaStream_t s);
 void scatter_dense(double* d_dst, const int64_t* d_idx, const double* d_val, int64_t k, int zero_only, cudaStream_t s);
