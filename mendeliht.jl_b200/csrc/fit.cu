@@ -83,7 +83,8 @@ struct ihtb_fit {
     bool df_sparse = false;
     std::vector<int64_t> dfs_idx;
     std::vector<double> dfs_val;
-    double rbar = 0.0, bound = 0.0, sum_w = 0.0, last_dev = 0.0;
+    double rbar = 0.0, bound = 0.0, sum_w = 0.0, last_dev = 0.0, denom_next = 0.0;
+    bool denom_ready = false;
     bool inited = false;
 
     // statistics
@@ -285,6 +286,19 @@ struct ihtb_fit {
             upload(d_cols.p, supp_loc.data(), supp_loc.size());
             xt_gather(g, d_cols.p, nsupp, d_r.p, 1, d_vbar.p, d_gout.p + glaunch, s);
         }
+        // the next iteration's step-size denominator ||sqrt(W) (X[:,idx] df[idx] + Z[:,idc] df2[idc])||^2 needs nothing
+        // from the host either: the support's exact df values are in d_gout, df2 is in d_scal (src/utilities.jl:728-756)
+        {
+            if (nsupp) x_support(g, d_cols.p, nsupp, d_gout.p + glaunch, 1, d_xs.p, s);
+            else IHTB_CUDA(cudaMemsetAsync(d_xs.p, 0, n * sizeof(double), s));
+            comm_allreduce_sum_f64(comm, d_xs.p, (size_t)n, s);
+            std::vector<double> mask((size_t)q);
+            for (int64_t l = 0; l < q; ++l) mask[l] = idc[l] ? 1.0 : 0.0;
+            upload(d_small.p + q, mask.data(), (size_t)q);
+            glm_stepsize(glm, d_scal.p + 2, d_xs.p, s, d_small.p + q, d_scal.p + 2 + q);
+            IHTB_CUDA(cudaMemcpyAsync(h_scal.p + 2 + q, d_scal.p + 2 + q, sizeof(double), cudaMemcpyDeviceToHost, s));
+            denom_ready = true;
+        }
         if (!comm) {
             IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + glaunch) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
             IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_gout.p, (glaunch + nsupp) * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -337,6 +351,7 @@ struct ihtb_fit {
         sweep_ms_total += ms;
         double rsum = h_scal.p[0], rl1 = h_scal.p[1];
         for (int64_t l = 0; l < q; ++l) df2[l] = h_scal.p[2 + l];
+        denom_next = h_scal.p[2 + q];
         rbar = rsum / (double)n;
         bound = coef * (rl1 + std::fabs(rsum));              // same value the selection kernel used
     }
@@ -354,6 +369,15 @@ struct ihtb_fit {
         std::vector<double> coef(idx.size());
         double numer = 0.0;
         for (size_t t = 0; t < idx.size(); ++t) { coef[t] = df_at(idx[t]); numer += coef[t] * coef[t]; }
+        if (denom_ready && !df_sparse) {       // denominator already computed behind the sweep (score_and_sweep)
+            denom_ready = false;
+            for (int64_t l = 0; l < q; ++l)
+                if (idc[l]) numer += df2[l] * df2[l];
+            double eta = numer / denom_next;
+            if (std::isinf(eta) || std::isnan(eta)) eta = 1e-8;
+            return eta;
+        }
+        denom_ready = false;
         support_matvec(idx, coef, d_xs.p);
         std::vector<double> d2((size_t)q);
         for (int64_t l = 0; l < q; ++l) {
@@ -729,7 +753,7 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
         if (zkeep) for (int64_t l = 0; l < q; ++l) f->zkeep[l] = zkeep[l] ? 1 : 0;
         f->zkeepn = 0;
         for (auto v : f->zkeep) f->zkeepn += v;
-        f->inited = false; f->sweep_pending = false;
+        f->inited = false; f->sweep_pending = false; f->denom_ready = false;
         f->n_sweeps = 0; f->n_backtracks = 0; f->sweep_ms_total = 0.0;
         for (int i = 0; i < 4; ++i) f->phase[i] = 0.0;
         IHTB_CHECK(cfg->est_r == 0 || cfg->dist == IHTB_NEGBIN, IHTB_EINVAL,

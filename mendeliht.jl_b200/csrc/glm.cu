@@ -86,14 +86,15 @@ k_score(int64_t n, int64_t q, const double* __restrict__ Z, const double* __rest
 // xgk_i = (xs_i + sum_l Z[i,l] d2_l) * sqrt(mueta^2 / glmvar) * w_i ; partial [0] = sum xgk_i^2
 __global__ void __launch_bounds__(GLM_THREADS)
 k_stepsize(int64_t n, int64_t q, const double* __restrict__ Z, const double* __restrict__ d2,
-           const double* __restrict__ xs, const double* __restrict__ xb, const double* __restrict__ zc,
+           const double* __restrict__ d2mask, const double* __restrict__ xs, const double* __restrict__ xb,
+           const double* __restrict__ zc,
            const double* __restrict__ mu, const double* __restrict__ w, int dist, int link, double nb_r,
            double* __restrict__ part) {
     __shared__ double sh[32];
     double a = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double zd = 0.0;
-        for (int64_t l = 0; l < q; ++l) zd += Z[i + l * n] * d2[l];
+        for (int64_t l = 0; l < q; ++l) zd += Z[i + l * n] * (d2mask ? d2[l] * d2mask[l] : d2[l]);
         double g = glm_mueta(link, xb[i] + zc[i]);
         double sw = sqrt(g * g / glm_var(dist, mu[i], nb_r)) * w[i];
         double v = (xs[i] + zd) * sw;
@@ -176,11 +177,12 @@ void glm_score(GlmCtx& c, cudaStream_t s) {
                 c.r, c.part);
     IHTB_LAUNCH(k_finalize, (unsigned)ceil_div(nv, 4), 128, 0, s, c.part, grid, nv, c.scal);
 }
-void glm_stepsize(GlmCtx& c, const double* d_d2, const double* d_xs, cudaStream_t s) {
+void glm_stepsize(GlmCtx& c, const double* d_d2, const double* d_xs, cudaStream_t s, const double* d_d2mask,
+                  double* d_out) {
     int grid = glm_grid(c.n);
-    IHTB_LAUNCH(k_stepsize, grid, GLM_THREADS, 0, s, c.n, c.q, c.Z, d_d2, d_xs, c.xb, c.zc, c.mu, c.w, c.dist, c.link,
-                c.nb_r, c.part);
-    IHTB_LAUNCH(k_finalize, 1, 32, 0, s, c.part, grid, 1, c.scal);
+    IHTB_LAUNCH(k_stepsize, grid, GLM_THREADS, 0, s, c.n, c.q, c.Z, d_d2, d_d2mask, d_xs, c.xb, c.zc, c.mu, c.w, c.dist,
+                c.link, c.nb_r, c.part);
+    IHTB_LAUNCH(k_finalize, 1, 32, 0, s, c.part, grid, 1, d_out ? d_out : c.scal);
 }
 void glm_sum2(GlmCtx& c, const double* a, const double* b, cudaStream_t s) {
     int grid = glm_grid(c.n);

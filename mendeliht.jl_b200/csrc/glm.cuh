@@ -110,7 +110,9 @@ struct GlmCtx {
 void glm_mu(GlmCtx& c, const double* d_c, int add_zc, cudaStream_t s);        // scal: dev, lp, sum w
 void glm_mean_from_sum(GlmCtx& c, double* d_mean, cudaStream_t s);             // d_mean[0] = scal[0] / n
 void glm_score(GlmCtx& c, cudaStream_t s);                                      // scal: sum r, sum |r|, df2[q]
-void glm_stepsize(GlmCtx& c, const double* d_d2, const double* d_xs, cudaStream_t s);   // scal: denom
+// scal[0] (or *d_out) = sum of squares of sqrt(W) (xs + Z (d2 .* d2mask)); d2mask may be NULL
+void glm_stepsize(GlmCtx& c, const double* d_d2, const double* d_xs, cudaStream_t s, const double* d_d2mask = nullptr,
+                  double* d_out = nullptr);
 void glm_sum2(GlmCtx& c, const double* a, const double* b, cudaStream_t s);
 void glm_ssq2(GlmCtx& c, const double* a, double ma, const double* b, double mb, cudaStream_t s);
 void glm_set_weights(GlmCtx& c, const uint8_t* d_mask, cudaStream_t s);        // scal: sum w, sum y*w
