@@ -20,7 +20,7 @@ RTOL = 1e-6
 MODES = [m.SWEEP_FAST, m.SWEEP_EXACT]
 
 
-def _compare(res, ref, rtol=RTOL):
+def _compare(res, ref, rtol=RTOL, check_backtracks=True):
     assert res.iter == ref.iter
     assert np.array_equal(np.flatnonzero(res.beta), np.flatnonzero(ref.beta))      # support: exact
     np.testing.assert_allclose(res.beta, ref.beta, rtol=rtol, atol=1e-12)
@@ -30,9 +30,10 @@ def _compare(res, ref, rtol=RTOL):
     else:
         assert res.logl == ref.logl
     assert abs(res.sigma_g - ref.sigma_g) <= rtol * abs(ref.sigma_g) + 1e-12
-    assert [t[1] for t in res.trace] == ref.trace.backtracks
+    if check_backtracks:
+        assert [t[1] for t in res.trace] == ref.trace.backtracks
+        np.testing.assert_allclose([t[2] for t in res.trace], ref.trace.tol, rtol=max(1e-5, 10 * rtol), atol=1e-12)
     np.testing.assert_allclose([t[0] for t in res.trace], ref.trace.logl, rtol=rtol)
-    np.testing.assert_allclose([t[2] for t in res.trace], ref.trace.tol, rtol=max(1e-5, 10 * rtol), atol=1e-12)
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -278,3 +279,44 @@ def test_negbin_nuisance_estimation(est_r):
     assert abs(res.logl - ref.logl) <= 1e-6 * abs(ref.logl)
     with pytest.raises(m.IHTBError):
         m.fit_iht(y, g, z, k=3, d="Poisson", l="LogLink", est_r="MM")
+
+
+@pytest.mark.parametrize("d,l", [("Bernoulli", "ProbitLink"), ("Bernoulli", "CloglogLink"), ("Normal", "LogLink")])
+def test_non_canonical_links(d, l):
+    """docs/src/index.md "Available link functions": the device GLM kernels carry all nine GLM.jl links."""
+    n, p, k = 2000 if d == "Bernoulli" else 1500, 2000, 4
+    seed = 500 + n
+    y, z, *_ = synth.simulate_response(seed, n, p, k, d, n_cov=1)
+    if d == "Normal":
+        y = np.abs(y) + 0.5
+    bed = synth.packed_columns(seed, n, np.arange(p))
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    kfit = 4 if d == "Bernoulli" else 5
+    res = m.fit_iht(y, g, z, k=kfit, d=d, l=l)
+    ref = iht.fit_iht(y, snp.SnpLinAlgOracle(bed, n), z, k=kfit, d=d, l=l)
+    assert ref.iter < 200
+    _compare(res, ref, rtol=1e-5)
+
+
+def test_edge_cases():
+    """k = p, k = 1, a monomorphic column (sigma_inv = 1), a column that is entirely missing is not supported by the
+    reference either (mu = NaN) so it is not exercised; p < 128 (one partial column block), n < 512 (one partial slab)."""
+    rng = np.random.default_rng(0)
+    n, p = 301, 37
+    g_ = rng.integers(0, 3, size=(n, p)); g_[:, 5] = 0                      # monomorphic SNP
+    bed = snp.pack_codes(snp.dosage_to_codes(g_))
+    o = snp.SnpLinAlgOracle(bed, n)
+    x = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    mu, sinv, _ = x.stats()
+    assert sinv[5] == 1.0 and mu[5] == 0.0
+    y = o.dense()[:, [3, 20]] @ np.array([1.0, -0.7]) + rng.normal(size=n) * 0.5 + 2.0
+    for k in (1, 2, 10, p):
+        res = m.fit_iht(y, x, None, k=k)
+        ref = iht.fit_iht(y, o, None, k=k)
+        # with k = 1 the iterate sits on a fixed point after two steps: old and new loglikelihood are equal to the
+        # last ulp, so `prev_logl > logl` (src/utilities.jl:485) is decided by rounding noise -> backtrack counts
+        # are not comparable there (model, loglikelihood and iteration count still are)
+        _compare(res, ref, check_backtracks=(k != 1))
+    v = rng.normal(size=n)
+    np.testing.assert_allclose(x.xt_v(v, m.SWEEP_FAST), o.xt_v(v), atol=1e-4 * np.abs(o.xt_v(v)).max())
+    np.testing.assert_allclose(x.xt_v(v, m.SWEEP_EXACT), o.xt_v(v), atol=1e-11 * np.abs(o.xt_v(v)).max())
