@@ -130,6 +130,9 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
                                 const double* z, int64_t q, const uint8_t* zkeep, const ihtb_cfg* cfg, ihtb_fit** out);
 int32_t ihtb_fit_set_k(ihtb_fit* f, int64_t k);                       /* v.k = sparsity (src/cross_validation.jl:110) */
 int32_t ihtb_fit_init(ihtb_fit* f, const uint8_t* train_mask);         /* init_iht_indices!; NULL = all samples */
+/* init_iht_indices!(v, init_beta = true, ...): beta starts from per-SNP univariate regressions (initialize_beta!,
+ * src/utilities.jl:776-842; Normal traits only, like the reference) */
+int32_t ihtb_fit_init_beta(ihtb_fit* f, const uint8_t* train_mask);
 int32_t ihtb_fit_run(ihtb_fit* f, ihtb_result* result, ihtb_iter_trace* trace, int64_t trace_cap);   /* fit_iht! + pve */
 /* any pointer may be NULL; beta[p], c[q], mu[n], xb[n] */
 int32_t ihtb_fit_get(const ihtb_fit* f, double* beta, double* c, double* mu, double* xb);

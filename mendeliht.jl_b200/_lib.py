@@ -86,6 +86,7 @@ SIGNATURES = {
     "ihtb_fit_create_sharded": [_p, _p, C.c_int64, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), _pp],
     "ihtb_fit_set_k": [_p, C.c_int64],
     "ihtb_fit_init": [_p, _u8],
+    "ihtb_fit_init_beta": [_p, _u8],
     "ihtb_fit_run": [_p, C.POINTER(Result), C.POINTER(IterTrace), C.c_int64],
     "ihtb_fit_get": [_p, _f64, _f64, _f64, _f64],
     "ihtb_fit_predict": [_p, _u8, _f64],

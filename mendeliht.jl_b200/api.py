@@ -190,9 +190,10 @@ class IHTVariable:
         check(load().ihtb_fit_set_k(self._h, int(k)))
         self.cfg.k = int(k)
 
-    def init_iht_indices(self, train_mask=None):
+    def init_iht_indices(self, train_mask=None, init_beta=False):
         m = None if train_mask is None else np.ascontiguousarray(train_mask, dtype=np.uint8)
-        check(load().ihtb_fit_init(self._h, ptr(m, C.c_uint8) if m is not None else None))
+        fn = load().ihtb_fit_init_beta if init_beta else load().ihtb_fit_init
+        check(fn(self._h, ptr(m, C.c_uint8) if m is not None else None))
 
     def fit(self, trace_cap=None):
         cap = int(self.cfg.max_iter) if trace_cap is None else trace_cap
@@ -353,7 +354,7 @@ def _check_args(k, max_iter, max_step, tol):
 
 def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est_r="None", nb_r=1.0, tol=1e-4,
             max_iter=200, min_iter=5, max_step=3, sweep_mode=_lib.SWEEP_FAST, verbose=False, io=None,
-            comm=None, p_global=None) -> IHTResult:
+            comm=None, p_global=None, init_beta=False) -> IHTResult:
     """`fit_iht(y, x, z; k, d, l, zkeep, tol, max_iter, min_iter, max_step)` (src/fit.jl:60-118)."""
     _check_args(k, max_iter, max_step, tol)
     if is_multivariate(y):      # d = MvNormal: Y is r x n, Z is q x n (src/fit.jl:66,125)
@@ -367,7 +368,7 @@ def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est
     v = IHTVariable(x, z, y, k, d, l, zkeep, nb_r, tol, max_iter, min_iter, max_step, sweep_mode, comm, p_global,
                     est_r)
     try:
-        v.init_iht_indices(None)
+        v.init_iht_indices(None, init_beta)
         res, trace = v.fit()
         beta, c, _, _ = v.get()
     finally:
@@ -400,7 +401,8 @@ def meanloss(fitloss, q: int, folds):
 
 
 def cv_iht(y, x: B200SnpLinAlg, z=None, d=NORMAL, l=None, path=range(1, 21), q=5, folds=None, zkeep=None,
-           nb_r=1.0, max_iter=100, min_iter=5, sweep_mode=_lib.SWEEP_FAST, combos=None, return_grid=False):
+           nb_r=1.0, max_iter=100, min_iter=5, sweep_mode=_lib.SWEEP_FAST, combos=None, return_grid=False,
+           init_beta=False):
     """`cv_iht` (src/cross_validation.jl:60-131).  `folds` in 1..q (drawn with numpy's default_rng if omitted).
     `combos`: optional subset of grid positions to run (used by the multi-GPU farm, parallel.py)."""
     path = [int(k) for k in path]
@@ -425,7 +427,10 @@ def cv_iht(y, x: B200SnpLinAlg, z=None, d=NORMAL, l=None, path=range(1, 21), q=5
             fold, k = grid[i]
             test = folds == fold
             v.set_k(k)
-            v.init_iht_indices(~test)
+            if mv:
+                v.init_iht_indices(~test)
+            else:
+                v.init_iht_indices(~test, init_beta)
             res, _ = v.fit(trace_cap=0)
             iters[i] = res.iter
             mses[i] = v.predict(test)

@@ -28,6 +28,8 @@ void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* v
                            int mode, cudaStream_t s, void* scratch_any, float* sweep_ms);
 void* sweep_scratch_create();
 void sweep_scratch_destroy(void* p);
+void sweep_class_sums(const ihtb_geno* g, const double* d_v, double* d_w1, double* d_w2, double* d_wm, cudaStream_t s,
+                      void* scratch_any);
 }  // namespace ihtb
 
 using namespace ihtb;
@@ -83,7 +85,7 @@ struct ihtb_fit {
     bool df_sparse = false;
     std::vector<int64_t> dfs_idx;
     std::vector<double> dfs_val;
-    double rbar = 0.0, bound = 0.0, sum_w = 0.0, last_dev = 0.0, denom_next = 0.0;
+    double rbar = 0.0, bound = 0.0, sum_w = 0.0, sum_wy = 0.0, last_dev = 0.0, denom_next = 0.0;
     bool denom_ready = false;
     bool inited = false;
 
@@ -267,6 +269,13 @@ struct ihtb_fit {
         sweep_xt_v_with_means(g, d_r.p, d_vbar.p, 1, d_dfa.p, cfg.sweep_mode, s, sweep_scratch, nullptr);
         IHTB_CUDA(cudaEventRecord(ev1, s));
         ++n_sweeps;
+        select_rescore(/*rerun=*/false);
+    }
+
+    // Candidate selection + exact re-scoring for the CURRENT idx against the last sweep's df (see score_and_sweep).
+    // rerun = true: called a second time for the same sweep (init_beta changes the support after the sweep); the
+    // score sums are no longer on the device, so the host copy of the error bound is used and no scalars are read.
+    void select_rescore(bool rerun) {
         df_exact.clear(); cand_cache.clear();
         df_sparse = false;
         const double coef = cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound;
@@ -278,7 +287,7 @@ struct ihtb_fit {
         int glaunch = 0;
         if (cfg.k > 0) {
             const int64_t ksel = cfg.k + (int64_t)idx.size();
-            topk_candidates_absdf(tk, d_dfa.p, g->sinv.p, d_scal.p, coef, ksel, s);
+            topk_candidates_absdf(tk, d_dfa.p, g->sinv.p, rerun ? nullptr : d_scal.p, coef, ksel, s, bound);
             glaunch = (int)std::min<int64_t>(comm ? capx / 2 : cap, ksel + 64);
             xt_gather(g, tk.cand, glaunch, d_r.p, 1, d_vbar.p, d_gout.p, s);      // slots beyond the count hold -1
         }
@@ -288,7 +297,8 @@ struct ihtb_fit {
         }
         // the next iteration's step-size denominator ||sqrt(W) (X[:,idx] df[idx] + Z[:,idc] df2[idc])||^2 needs nothing
         // from the host either: the support's exact df values are in d_gout, df2 is in d_scal (src/utilities.jl:728-756)
-        {
+        denom_ready = false;
+        if (!rerun) {
             if (nsupp) x_support(g, d_cols.p, nsupp, d_gout.p + glaunch, 1, d_xs.p, s);
             else IHTB_CUDA(cudaMemsetAsync(d_xs.p, 0, n * sizeof(double), s));
             comm_allreduce_sum_f64(comm, d_xs.p, (size_t)n, s);
@@ -346,6 +356,7 @@ struct ihtb_fit {
         std::sort(cand_cache.begin(), cand_cache.end());
         cand_cache.erase(std::unique(cand_cache.begin(), cand_cache.end()), cand_cache.end());
         n_cand_iter += (int64_t)cand_cache.size();
+        if (rerun) return;
         float ms = 0.f;
         IHTB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
         sweep_ms_total += ms;
@@ -501,7 +512,82 @@ struct ihtb_fit {
     }
 
     // ---- init_iht_indices! (src/utilities.jl:366-438) ----------------------------------------------
-    void init(const uint8_t* train_mask) {
+    // ---- initialize_beta! + project_k! (src/utilities.jl:776-842, 412-414, 561-573): univariate regression of y on
+    // [1, x_j] over the training samples for every SNP (two exact class-sum passes over the packed matrix) and covariate.
+    void do_init_beta() {
+        IHTB_CHECK(cfg.dist == IHTB_NORMAL, IHTB_EINVAL, "Intializing beta values only work for Gaussian phenotypes! Sorry!");
+        IHTB_CHECK(!comm, IHTB_EUNSUPPORTED, "init_beta is not available for SNP-sharded fits yet");
+        DBuf<double> cls((size_t)(7 * p));           // W1 W2 Wm Y1 Y2 Ym beta
+        double *W1 = cls.p, *W2 = W1 + p, *Wm = W2 + p, *Y1 = Wm + p, *Y2 = Y1 + p, *Ym = Y2 + p, *bd = Ym + p;
+        init_beta_products(glm, d_xs.p, s);                                   // d_xs = w .* y
+        sweep_class_sums(g, d_w.p, W1, W2, Wm, s, sweep_scratch);
+        sweep_class_sums(g, d_xs.p, Y1, Y2, Ym, s, sweep_scratch);
+        n_sweeps += 2;
+        init_beta_solve(glm, p, W1, W2, Wm, Y1, Y2, Ym, sum_w, sum_wy, g->mu.p, g->sinv.p, g->impute, bd, s);   // scal[0] = sum of intercepts
+        readback_scal(1);
+        double c0sum = h_scal.p[0];
+        // covariates 2..q (host 2x2 solves on device-reduced sums: N, sum z, sum z^2, sum z y)
+        std::fill(c.begin(), c.end(), 0.0);
+        if (q > 1) {
+            init_beta_cov_sums(glm, s);                                         // scal[3*(l-1) + {0,1,2}]
+            readback_scal(3 * ((int)q - 1));
+            for (int64_t l = 1; l < q; ++l) {
+                double sx = h_scal.p[3 * (l - 1)], sxx = h_scal.p[3 * (l - 1) + 1], sxy = h_scal.p[3 * (l - 1) + 2];
+                double icpt = sum_wy, slope = sxy;
+                double u11 = std::sqrt(sum_w), u12 = sx / u11, dd = sxx - u12 * u12;
+                if (sum_w > 0 && dd > 0) {
+                    double u22 = std::sqrt(dd), t1 = sum_wy / u11, t2 = (sxy - u12 * t1) / u22;
+                    slope = t2 / u22; icpt = (t1 - u12 * slope) / u11;
+                }
+                c0sum += icpt;
+                c[l] = std::min(std::max(slope, -2.0), 2.0);
+            }
+        }
+        c[0] = std::min(std::max(c0sum / (double)(p + q - 1), -2.0), 2.0);
+        // project_k!(v): top (k + zkeepn) of [b; c with Inf at kept covariates]
+        std::vector<int64_t> cand;
+        if (cfg.k > 0) {
+            topk_candidates(tk, bd, nullptr, g->sinv.p, 1.0, 0.0, cfg.k, s);
+            IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + cap) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            sync();
+            const TopkState* st = reinterpret_cast<const TopkState*>(h_sel.p);
+            IHTB_CHECK(st->count <= cap, IHTB_ENUMERIC, "degenerate projection of the initial beta (too many ties)");
+            cand.assign(h_sel.p + 2, h_sel.p + 2 + st->count);
+            std::sort(cand.begin(), cand.end());
+        }
+        std::vector<double> vals(cand.size());
+        if (!cand.empty()) {
+            upload(d_cols.p, cand.data(), cand.size());
+            take_values(bd, d_cols.p, (int64_t)cand.size(), d_gout.p, s);
+            IHTB_CUDA(cudaMemcpyAsync(vals.data(), d_gout.p, cand.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+            sync();
+        }
+        struct Item { double a; int64_t pos; double v; };
+        std::vector<Item> items;
+        for (size_t t = 0; t < cand.size(); ++t) items.push_back({std::fabs(vals[t]), cand[t], vals[t]});
+        for (int64_t l = 0; l < q; ++l)
+            if (!zkeep[l]) items.push_back({std::fabs(c[l]), p_global + l, c[l]});
+        std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) {
+            return x.a > y.a || (x.a == y.a && x.pos < y.pos);
+        });
+        std::vector<std::pair<int64_t, double>> keep;
+        for (size_t t = 0; t < items.size(); ++t) {
+            bool kept = (int64_t)t < cfg.k;
+            if (items[t].pos >= p_global) {
+                if (!kept) c[items[t].pos - p_global] = 0.0;
+            } else if (kept && items[t].v != 0.0) {
+                keep.push_back({items[t].pos, items[t].v});
+            }
+        }
+        std::sort(keep.begin(), keep.end());
+        idx.clear(); b.clear();
+        for (auto& kv : keep) { idx.push_back(kv.first); b.push_back(kv.second); }
+        for (int64_t l = 0; l < q; ++l) idc[l] = c[l] != 0.0;
+        // df keeps the full gradient of the intercept-only model; xb / zc / mu are NOT refreshed (:412-414)
+        select_rescore(/*rerun=*/true);
+    }
+
+    void init(const uint8_t* train_mask, bool init_beta = false) {
         idx.clear(); b.clear(); idx0.clear(); b0.clear(); best_idx.clear(); best_b.clear();
         c.assign((size_t)q, 0.0); c0 = c; best_c = c; df2.assign((size_t)q, 0.0);
         idc.assign(zkeep.begin(), zkeep.end()); idc0 = idc;
@@ -516,6 +602,7 @@ struct ihtb_fit {
         glm_set_weights(glm, dm, s);
         readback_scal(2);
         sum_w = h_scal.p[0];
+        sum_wy = h_scal.p[1];
         double ybar = h_scal.p[1] / sum_w;
         // intercept by Newton's method with the step clamped to +-1 (:394-405)
         for (int it = 0; it < 20; ++it) {
@@ -528,6 +615,11 @@ struct ihtb_fit {
         }
         glm_update(1);        // zc = Z c, mu (the reference does not clamp here; xb = 0 and |c1| is small)
         score_and_sweep();
+        if (init_beta) {
+            do_init_beta();
+            inited = true;
+            return;
+        }
         // first k entries chosen from the largest gradient; df itself becomes its projection (:417-425)
         std::vector<int64_t> cand = cand_cache;      // top-k of |df| with exact values (score_and_sweep)
         struct Item { double a; int64_t pos; double v; };
@@ -787,6 +879,14 @@ int32_t ihtb_fit_init(ihtb_fit* f, const uint8_t* train_mask) {
         IHTB_CHECK(f, IHTB_EINVAL, "NULL fit handle");
         IHTB_CUDA(cudaSetDevice(f->g->device));
         f->init(train_mask);
+    });
+}
+
+int32_t ihtb_fit_init_beta(ihtb_fit* f, const uint8_t* train_mask) {
+    return guard([&] {
+        IHTB_CHECK(f, IHTB_EINVAL, "NULL fit handle");
+        IHTB_CUDA(cudaSetDevice(f->g->device));
+        f->init(train_mask, /*init_beta=*/true);
     });
 }
 

@@ -160,7 +160,79 @@ __global__ void k_mean_from_sum(const double* __restrict__ scal, int64_t n, doub
     out[0] = scal[0] / (double)n;
 }
 
+// ---- init_beta helpers (reference initialize_beta! / linreg!, src/utilities.jl:776-842) ------------------------------
+__global__ void k_wy(int64_t n, const double* __restrict__ w, const double* __restrict__ y, double* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = w[i] * y[i];
+}
+// per SNP: regression of y on [1, x_j] over the weighted samples from the class sums; slope clamped to [-2, 2];
+// a failed 2x2 Cholesky leaves (sum y, sum x y) like the reference's try/catch.  part[block] = sum of intercepts.
+__global__ void __launch_bounds__(GLM_THREADS)
+k_init_beta(int64_t p, const double* __restrict__ W1, const double* __restrict__ W2, const double* __restrict__ Wm,
+            const double* __restrict__ Y1, const double* __restrict__ Y2, const double* __restrict__ Ym, double N,
+            double SY, const double* __restrict__ mu, const double* __restrict__ sinv, int impute,
+            double* __restrict__ beta, double* __restrict__ part) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p; j += (int64_t)gridDim.x * blockDim.x) {
+        const double m = mu[j], si = sinv[j];
+        const double a0 = (0.0 - m) * si, a1 = (1.0 - m) * si, a2 = (2.0 - m) * si, am = impute ? 0.0 : a0;
+        const double w1 = W1[j], w2 = W2[j], wm = Wm[j], w0 = N - w1 - w2 - wm;
+        const double y1 = Y1[j], y2 = Y2[j], ym = Ym[j], y0 = SY - y1 - y2 - ym;
+        const double sx = a0 * w0 + a1 * w1 + a2 * w2 + am * wm;
+        const double sxx = a0 * a0 * w0 + a1 * a1 * w1 + a2 * a2 * w2 + am * am * wm;
+        const double sxy = a0 * y0 + a1 * y1 + a2 * y2 + am * ym;
+        double icpt = SY, slope = sxy;
+        const double u11 = sqrt(N), u12 = sx / u11, dd = sxx - u12 * u12;
+        if (N > 0.0 && dd > 0.0) {
+            const double u22 = sqrt(dd), t1 = SY / u11, t2 = (sxy - u12 * t1) / u22;
+            slope = t2 / u22;
+            icpt = (t1 - u12 * slope) / u11;
+        }
+        beta[j] = fmin(fmax(slope, -2.0), 2.0);
+        acc += icpt;
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+// covariates l = 1..q-1: partial sums [3(l-1)+0] sum w z, [+1] sum w z^2, [+2] sum w z y
+__global__ void __launch_bounds__(GLM_THREADS)
+k_cov_sums(int64_t n, int64_t q, const double* __restrict__ Z, const double* __restrict__ y,
+           const double* __restrict__ w, double* __restrict__ part) {
+    __shared__ double sh[32];
+    const int nv = 3 * ((int)q - 1);
+    for (int64_t l = 1; l < q; ++l) {
+        double a = 0.0, b = 0.0, c = 0.0;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+            double z = Z[i + l * n], wi = w[i];
+            a += wi * z; b += wi * z * z; c += wi * z * y[i];
+        }
+        a = block_sum(a, sh); b = block_sum(b, sh); c = block_sum(c, sh);
+        if (threadIdx.x == 0) {
+            part[blockIdx.x * nv + 3 * (l - 1)] = a;
+            part[blockIdx.x * nv + 3 * (l - 1) + 1] = b;
+            part[blockIdx.x * nv + 3 * (l - 1) + 2] = c;
+        }
+    }
+}
+
 // ---- launchers ------------------------------------------------------------------------------------
+void init_beta_products(GlmCtx& c, double* d_wy, cudaStream_t s) {
+    IHTB_LAUNCH(k_wy, (unsigned)ceil_div(c.n, 256), 256, 0, s, c.n, c.w, c.y, d_wy);
+}
+void init_beta_solve(GlmCtx& c, int64_t p, const double* W1, const double* W2, const double* Wm, const double* Y1,
+                     const double* Y2, const double* Ym, double N, double SY, const double* mu, const double* sinv,
+                     int impute, double* d_beta, cudaStream_t s) {
+    int grid = glm_grid(p);
+    IHTB_LAUNCH(k_init_beta, grid, GLM_THREADS, 0, s, p, W1, W2, Wm, Y1, Y2, Ym, N, SY, mu, sinv, impute, d_beta, c.part);
+    IHTB_LAUNCH(k_finalize, 1, 32, 0, s, c.part, grid, 1, c.scal);
+}
+void init_beta_cov_sums(GlmCtx& c, cudaStream_t s) {
+    int grid = glm_grid(c.n);
+    int nv = 3 * ((int)c.q - 1);
+    IHTB_LAUNCH(k_cov_sums, grid, GLM_THREADS, 0, s, c.n, c.q, c.Z, c.y, c.w, c.part);
+    IHTB_LAUNCH(k_finalize, (unsigned)ceil_div(nv, 4), 128, 0, s, c.part, grid, nv, c.scal);
+}
 void glm_mean_from_sum(GlmCtx& c, double* d_mean, cudaStream_t s) {
     IHTB_LAUNCH(k_mean_from_sum, 1, 1, 0, s, c.scal, c.n, d_mean);
 }

@@ -115,6 +115,11 @@ void glm_stepsize(GlmCtx& c, const double* d_d2, const double* d_xs, cudaStream_
                   double* d_out = nullptr);
 void glm_sum2(GlmCtx& c, const double* a, const double* b, cudaStream_t s);
 void glm_ssq2(GlmCtx& c, const double* a, double ma, const double* b, double mb, cudaStream_t s);
+void init_beta_products(GlmCtx& c, double* d_wy, cudaStream_t s);             // d_wy = w .* y
+void init_beta_solve(GlmCtx& c, int64_t p, const double* W1, const double* W2, const double* Wm, const double* Y1,
+                     const double* Y2, const double* Ym, double N, double SY, const double* mu, const double* sinv,
+                     int impute, double* d_beta, cudaStream_t s);                   // scal[0] = sum of intercepts
+void init_beta_cov_sums(GlmCtx& c, cudaStream_t s);                               // scal[3(l-1)+{0,1,2}]
 void glm_set_weights(GlmCtx& c, const uint8_t* d_mask, cudaStream_t s);        // scal: sum w, sum y*w
 
 }  // namespace ihtb

@@ -239,3 +239,88 @@ extern "C" int32_t ihtb_sweep_bench(const ihtb_geno* g, int32_t sweep_mode, int3
         cudaStreamDestroy(s);
     });
 }
+
+// ---- class sums for init_beta (reference initialize_beta!, src/utilities.jl:776-812) -------------------------------
+// W1_j = sum_i v_i [g_ij = 1], W2_j = sum_i v_i [g_ij = 2], Wm_j = sum_i v_i [g_ij missing]  (v NOT centred).
+// With the four possible standardised values of a column, sum x, sum x^2 and sum x*y over the training samples follow
+// from these sums for v = w and v = w.*y, so the univariate regressions need two exact passes over the matrix.
+namespace ihtb {
+
+__global__ void __launch_bounds__(EX_THREADS)
+k_sweep_class_exact(GenoView gv, const double* __restrict__ v, double* __restrict__ part1, double* __restrict__ part2) {
+    __shared__ double red[EX_THREADS / 32][2 * EX_CB];
+    const int64_t p = gv.p, n = gv.n;
+    const int64_t words = gv.stride >> 2;
+    const int64_t slab = blockIdx.y;
+    const int64_t w = slab * EX_THREADS + threadIdx.x;
+    const bool live = w < words;
+    double u[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        int64_t i = 16 * w + s;
+        u[s] = (live && i < n) ? v[i] : 0.0;
+    }
+    const int64_t jbeg = blockIdx.x * (int64_t)EX_COLS_PER_CTA;
+    const int64_t jend = (jbeg + EX_COLS_PER_CTA < p) ? jbeg + EX_COLS_PER_CTA : p;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t j0 = jbeg; j0 < jend; j0 += EX_CB) {
+        double a1[EX_CB], a2[EX_CB];
+#pragma unroll
+        for (int c = 0; c < EX_CB; ++c) {
+            int64_t j = j0 + c;
+            uint32_t x = (live && j < jend) ? *reinterpret_cast<const uint32_t*>(gv_ptr(gv, j, 4 * w)) : 0u;
+            double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int s = 0; s < 16; ++s) {
+                uint32_t code = (x >> (2 * s)) & 3u;
+                s1 += (code == 2) ? u[s] : 0.0;
+                s2 += (code == 3) ? u[s] : 0.0;
+            }
+            a1[c] = warp_sum(s1);
+            a2[c] = warp_sum(s2);
+        }
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < EX_CB; ++c) { red[warp][c] = a1[c]; red[warp][EX_CB + c] = a2[c]; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * EX_CB) {
+            int c = threadIdx.x % EX_CB;
+            if (j0 + c < jend) {
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < EX_THREADS / 32; ++q) t += red[q][threadIdx.x];
+                (threadIdx.x < EX_CB ? part1 : part2)[slab * p + j0 + c] = t;
+            }
+        }
+    }
+}
+
+__global__ void k_class_epilogue(const double* __restrict__ part1, const double* __restrict__ part2, int64_t n_slabs,
+                                 int64_t p, const int64_t* __restrict__ miss_ptr, const int32_t* __restrict__ miss_idx,
+                                 const double* __restrict__ v, double* __restrict__ out1, double* __restrict__ out2,
+                                 double* __restrict__ outm) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= p) return;
+    double a = 0.0, b = 0.0, m = 0.0;
+    for (int64_t s = 0; s < n_slabs; ++s) { a += part1[s * p + j]; b += part2[s * p + j]; }
+    for (int64_t e = miss_ptr[j]; e < miss_ptr[j + 1]; ++e) m += v[miss_idx[e]];
+    out1[j] = a; out2[j] = b; outm[j] = m;
+}
+
+void sweep_class_sums(const ihtb_geno* g, const double* d_v, double* d_w1, double* d_w2, double* d_wm, cudaStream_t s,
+                      void* scratch_any) {
+    SweepScratch* sc = reinterpret_cast<SweepScratch*>(scratch_any);
+    int64_t words = g->stride >> 2;
+    int64_t n_slabs = ceil_div(words, EX_THREADS);
+    if (sc->part64.n < (size_t)(2 * n_slabs * g->p)) sc->part64.alloc((size_t)(2 * n_slabs * g->p));
+    double* p1 = sc->part64.p;
+    double* p2 = sc->part64.p + n_slabs * g->p;
+    dim3 grid((unsigned)ceil_div(g->p, EX_COLS_PER_CTA), (unsigned)n_slabs);
+    IHTB_LAUNCH(k_sweep_class_exact, grid, EX_THREADS, 0, s, geno_view(g), d_v, p1, p2);
+    IHTB_LAUNCH(k_class_epilogue, (unsigned)ceil_div(g->p, 256), 256, 0, s, p1, p2, n_slabs, g->p, g->miss_ptr.p,
+                g->miss_idx.p, d_v, d_w1, d_w2, d_wm);
+}
+
+}  // namespace ihtb

@@ -164,10 +164,19 @@ void topk_candidates(TopkCtx& c, const double* d_dfa, const double* d_b0d, const
 // |df_j| outside the support, whatever eta is, so ONE selection per sweep serves the gradient step and all of its
 // backtracks.  The error bound is computed on the device from the score sums d_scal = [sum r, sum |r|, ...].
 void topk_candidates_absdf(TopkCtx& c, const double* d_dfa, const double* d_sinv, const double* d_scal,
-                           double bound_coef, int64_t k, cudaStream_t s) {
+                           double bound_coef, int64_t k, cudaStream_t s, double host_bound) {
     // unused candidate slots stay -1 so that a gather launched over a fixed number of slots can skip them
     IHTB_CUDA(cudaMemsetAsync(c.cand, 0xFF, (size_t)c.cap * sizeof(int64_t), s));
-    topk_run(c, d_dfa, nullptr, d_sinv, c.p, nullptr, 1.0, 0.0, k, s, d_scal, bound_coef);
+    topk_run(c, d_dfa, nullptr, d_sinv, c.p, nullptr, 1.0, d_scal ? 0.0 : host_bound, k, s, d_scal, bound_coef);
+}
+
+__global__ void k_take(const double* __restrict__ src, const int64_t* __restrict__ idx, int64_t k,
+                       double* __restrict__ dst) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < k) dst[t] = src[idx[t]];
+}
+void take_values(const double* d_src, const int64_t* d_idx, int64_t k, double* d_dst, cudaStream_t s) {
+    if (k) IHTB_LAUNCH(k_take, (unsigned)ceil_div(k, 128), 128, 0, s, d_src, d_idx, k, d_dst);
 }
 
 // entries e = t*p_mod + j (t-th right-hand side of column j): bound d_bounds[t], scale d_sinv[j]

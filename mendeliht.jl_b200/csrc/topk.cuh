@@ -24,8 +24,10 @@ void topk_candidates(TopkCtx& c, const double* d_dfa, const double* d_b0d, const
                      double bound, int64_t k, cudaStream_t s);
 void topk_candidates_blocked(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, int64_t p_mod,
                              const double* d_bounds, double eta, int64_t k, cudaStream_t s);
+// d_scal != NULL: bound = bound_coef * (d_scal[1] + |d_scal[0]|) on the device; else host_bound is used
 void topk_candidates_absdf(TopkCtx& c, const double* d_dfa, const double* d_sinv, const double* d_scal,
-                           double bound_coef, int64_t k, cudaStream_t s);
+                           double bound_coef, int64_t k, cudaStream_t s, double host_bound = 0.0);
+void take_values(const double* d_src, const int64_t* d_idx, int64_t k, double* d_dst, cudaStream_t s);
 void pack_sweep_candidates(int64_t* d_block, const TopkState* d_st, const int64_t* d_cand, int glaunch,
                            const double* d_cand_vals, const int64_t* d_supp, int nsupp, const double* d_supp_vals,
                            int64_t j0, int capx, cudaStream_t s);

@@ -149,7 +149,47 @@ class IHTVariable:
             prune_ties(self.b, self.idx, nonzero - sparsity)
 
     # -- src/utilities.jl:366-438
-    def init_iht_indices(self, cv_idx: np.ndarray):
+    # -- src/utilities.jl:776-842 (`initialize_beta!` + `linreg!`)
+    def initialize_beta(self, cv_idx):
+        """Univariate regression of y on [1, x_i] over the training samples for every SNP and covariate.
+        A failed 2x2 Cholesky (monomorphic column in the training set) leaves xty unsolved: beta_i = sum(x y),
+        intercept contribution = sum(y) (the reference's try/catch, :836-841)."""
+        cv = np.asarray(cv_idx, dtype=bool)
+        ys = self.y[cv]
+        N = float(cv.sum())
+        sy = float(ys.sum())
+
+        def linreg(xs):                       # xs: [N, m] -> intercepts [m], slopes [m]
+            sx = xs.sum(axis=0); sxx = (xs * xs).sum(axis=0); sxy = xs.T @ ys
+            icpt = np.full(xs.shape[1], sy); slope = sxy.copy()
+            with np.errstate(divide="ignore", invalid="ignore"):
+                u11 = np.sqrt(N); u12 = sx / u11
+                d = sxx - u12 * u12
+                ok = d > 0
+                u22 = np.sqrt(np.where(ok, d, 1.0))
+                t1 = sy / u11
+                t2 = (sxy - u12 * t1) / u22
+                b2 = t2 / u22
+                b1 = (t1 - u12 * b2) / u11
+            icpt[ok] = b1[ok]; slope[ok] = b2[ok]
+            return icpt, slope
+
+        c0 = 0.0
+        for j0 in range(0, self.p, 2048):     # column blocks bound the memory of the dense slice
+            xs = self.x.dense()[:, j0:j0 + 2048][cv]
+            icpt, slope = linreg(xs)
+            c0 += float(icpt.sum())
+            self.b[j0:j0 + 2048] = slope
+        if self.q > 1:
+            icpt, slope = linreg(self.z[cv][:, 1:])
+            c0 += float(icpt.sum())
+            self.c[1:] = slope
+        self.c[0] = c0 / (self.p + self.q - 1)
+        np.clip(self.b, -2, 2, out=self.b)
+        np.clip(self.c, -2, 2, out=self.c)
+        self.b0 = self.b.copy(); self.c0 = self.c.copy()
+
+    def init_iht_indices(self, cv_idx: np.ndarray, init_beta: bool = False):
         for a in (self.b, self.b0, self.best_b, self.xb, self.xgk, self.r, self.df, self.df2, self.c,
                   self.best_c, self.c0, self.zc, self.mu, self.cv_wts):
             a[...] = 0
@@ -167,6 +207,14 @@ class IHTVariable:
         self.zc = self.z @ self.c
         self.update_mu()
         self.score()
+        if init_beta:                          # :412-414 (df keeps the full gradient, xb / zc / mu are not refreshed)
+            if self.d != glm.NORMAL:
+                raise ValueError("Intializing beta values only work for Gaussian phenotypes! Sorry!")
+            self.initialize_beta(cv_idx)
+            self._project_full(self.b, self.c)            # project_k!(v) :561-573
+            self.idx = self.b != 0
+            self.idc = self.c != 0
+            return
         # first k non-zero entries chosen from largest gradient; df itself is projected (:417-425)
         self._project_full(self.df, self.df2)
         self.idx = self.df != 0
@@ -342,7 +390,7 @@ def pve(y, mu):
 
 
 def fit_iht(y, x, z=None, k=10, d=glm.NORMAL, l=None, zkeep=None, est_r="None", nb_r=1.0,
-            tol=1e-4, max_iter=200, min_iter=5, max_step=3, cv_train_idx=None) -> IHTResult:
+            tol=1e-4, max_iter=200, min_iter=5, max_step=3, cv_train_idx=None, init_beta=False) -> IHTResult:
     """`fit_iht` (src/fit.jl:60-118) on an oracle SnpLinAlg `x` (see oracle/snp.py)."""
     if z is None:
         z = np.ones(x.shape[0])
@@ -353,7 +401,7 @@ def fit_iht(y, x, z=None, k=10, d=glm.NORMAL, l=None, zkeep=None, est_r="None", 
     if not tol > np.finfo(np.float64).eps:
         raise AssertionError("Value of global tol must exceed machine precision!")
     v = IHTVariable(x, z, y, k, d, l, zkeep=zkeep, est_r=est_r, nb_r=nb_r)
-    v.init_iht_indices(np.ones(v.n, bool) if cv_train_idx is None else cv_train_idx)
+    v.init_iht_indices(np.ones(v.n, bool) if cv_train_idx is None else cv_train_idx, init_beta)
     trace = IHTTrace()
     best_logl, mm_iter = fit_iht_loop(v, tol=tol, max_iter=max_iter, min_iter=min_iter,
                                       max_step=max_step, trace=trace)

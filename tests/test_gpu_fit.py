@@ -320,3 +320,26 @@ def test_edge_cases():
     v = rng.normal(size=n)
     np.testing.assert_allclose(x.xt_v(v, m.SWEEP_FAST), o.xt_v(v), atol=1e-4 * np.abs(o.xt_v(v)).max())
     np.testing.assert_allclose(x.xt_v(v, m.SWEEP_EXACT), o.xt_v(v), atol=1e-11 * np.abs(o.xt_v(v)).max())
+
+
+def test_init_beta_matches_oracle():
+    """test/L0_reg_test.jl:299-321 (init_beta = true): beta starts from univariate regressions (initialize_beta!)."""
+    n, p, k = 1200, 2500, 6
+    y, z, _, _, _ = synth.simulate_response(61, n, p, k, "Normal", n_cov=2, missing_rate=0.01)
+    bed = synth.packed_columns(61, n, np.arange(p), 0.01)
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    o = snp.SnpLinAlgOracle(bed, n)
+    for mode in MODES:
+        res = m.fit_iht(y, g, z, k=k + 1, init_beta=True, sweep_mode=mode)
+        ref = iht.fit_iht(y, o, z, k=k + 1, init_beta=True)
+        _compare(res, ref)
+    plain = m.fit_iht(y, g, z, k=k + 1)
+    assert res.iter != plain.iter or not np.array_equal(res.beta, plain.beta)      # it really is a different start
+    # under a CV mask, and through cv_iht
+    folds = synth.folds_for(9, n, 3)
+    mses, iters = m.cv_iht(y, g, z, path=[3, 7], q=3, folds=folds, init_beta=True, return_grid=True)
+    _, rgrid, riters = ocv.cv_iht(y, o, z, path=[3, 7], q=3, folds=folds, init_beta=True, return_grid=True)
+    assert np.array_equal(iters, riters)
+    np.testing.assert_allclose(mses, rgrid, rtol=RTOL)
+    with pytest.raises(m.IHTBError):
+        m.fit_iht((y > 0).astype(float), g, z, k=3, d="Bernoulli", l="LogitLink", init_beta=True)

@@ -178,3 +178,21 @@ def test_cv_small_all_positive(normal_data, normal_oracle):
     mse = ocv.cv_iht(normal_data["y"], normal_oracle, normal_data["z"], path=[1, 5, 7], q=3, folds=folds)
     assert mse.shape == (3,) and np.all(mse > 0)
     assert np.argmin(mse) == 2
+
+
+def test_initialize_beta_is_univariate_least_squares(normal_data, normal_oracle):
+    """`initialize_beta!` / `linreg!` (src/utilities.jl:776-842): slope of y ~ 1 + x_j, clamped to [-2, 2]; intercept
+    averaged over all p + q - 1 regressions."""
+    y, z, n = normal_data["y"], normal_data["z"], normal_data["n"]
+    v = iht.IHTVariable(normal_oracle, z, y, 7, glm.NORMAL, glm.IDENTITY)
+    v.init_iht_indices(np.ones(n, bool))
+    v.b[:] = 0
+    v.initialize_beta(np.ones(n, bool))
+    icpts = []
+    for j in (0, 17, 4716, 9414):
+        X = np.c_[np.ones(n), normal_oracle.dense()[:, j]]
+        sol = np.linalg.lstsq(X, y, rcond=None)[0]
+        assert abs(np.clip(sol[1], -2, 2) - v.b[j]) < 1e-12
+    res = iht.fit_iht(y, normal_oracle, z, k=7, init_beta=True)
+    assert list(np.flatnonzero(res.beta) + 1) == [3137, 4246, 4717, 6290, 7755, 8375, 9415]     # same optimum
+    assert abs(res.logl - (-1397.88074)) < 1e-4
