@@ -343,14 +343,17 @@ struct ihtb_fit {
                 const int64_t* b_ = h_packall.p + (size_t)r * blk;
                 IHTB_CHECK(b_[0] <= glaunch, IHTB_ENUMERIC,
                            "degenerate projection: too many local candidates within the sweep error bound");
-                for (int t = 0; t < capx; ++t) {
+                const int half = capx / 2;
+                auto take = [&](int t, bool is_cand) {
                     const int64_t j = b_[2 + t];
-                    if (j < 0) continue;
+                    if (j < 0) return;
                     double v;
                     memcpy(&v, &b_[2 + capx + t], sizeof(double));
                     df_exact[j] = v;
-                    if (t < capx / 2) cand_cache.push_back(j);
-                }
+                    if (is_cand) cand_cache.push_back(j);
+                };
+                for (int t = 0; t < (int)b_[0]; ++t) take(t, true);                 // rank r's candidates
+                for (int t = 0; t < (int)b_[1]; ++t) take(half + t, false);         // rank r's part of the support
             }
         }
         std::sort(cand_cache.begin(), cand_cache.end());
