@@ -163,6 +163,9 @@ int32_t ihtb_mvfit_destroy(ihtb_mvfit* f);
 int32_t ihtb_comm_unique_id(const char* nccl_lib_path, uint8_t* out128);
 int32_t ihtb_comm_create(const char* nccl_lib_path, const uint8_t* id128, int32_t rank, int32_t nranks, ihtb_comm** out);
 int32_t ihtb_comm_destroy(ihtb_comm* c);
+/* collective: average device time (us) of `reps` back-to-back all-reduces of n doubles, use_p2p = 0: ncclAllReduce,
+ * 1: the peer-memory push + local reduce that sharded fits use (IHTB_EUNSUPPORTED when IPC mapping is unavailable) */
+int32_t ihtb_comm_allreduce_bench(ihtb_comm* c, int64_t n, int32_t reps, int32_t use_p2p, double* us_per_op);
 int32_t ihtb_geno_set_offset(ihtb_geno* g, int64_t j0);   /* global index of local column 0 for host-uploaded shards */
 
 #ifdef __cplusplus

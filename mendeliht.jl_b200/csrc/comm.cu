@@ -106,6 +106,7 @@ int32_t ihtb_comm_create(const char* nccl_lib_path, const uint8_t* id128, int32_
 int32_t ihtb_comm_destroy(ihtb_comm* c) {
     return guard([&] {
         if (!c) return;
+        p2p_teardown(c);
         if (c->comm) g_nccl.CommDestroy(c->comm);
         delete c;
     });

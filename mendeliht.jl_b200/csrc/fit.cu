@@ -122,13 +122,24 @@ struct ihtb_fit {
         std::vector<int64_t> ii; std::vector<double> vv;
         for (size_t t = 0; t < cols.size(); ++t)
             if (coef[t] != 0.0 && is_local(cols[t])) { ii.push_back(cols[t] - j0); vv.push_back(coef[t]); }
-        if (ii.empty()) {
-            IHTB_CUDA(cudaMemsetAsync(d_out, 0, n * sizeof(double), s));
-        } else {
+        if (!ii.empty()) {
             upload(d_idx.p, ii.data(), ii.size());
             upload(d_coef.p, vv.data(), vv.size());
-            x_support(g, d_idx.p, (int64_t)ii.size(), d_coef.p, 1, d_out, s);
         }
+        support_matvec_dev(ii.empty() ? nullptr : d_idx.p, (int64_t)ii.size(), d_coef.p, d_out);
+    }
+
+    // same with the local index / coefficient lists already on the device.  Sharded fits with the peer-memory path:
+    // the partial vector is produced straight into every rank's slot and reduced locally (p2p.cu); otherwise NCCL.
+    void support_matvec_dev(const int64_t* d_idx_loc, int64_t k_loc, const double* d_coef_loc, double* d_out) {
+        if (p2p_ready(comm, (size_t)n)) {
+            if (k_loc > 0) x_support_push(g, d_idx_loc, k_loc, d_coef_loc, comm, s);
+            else p2p_push(comm, nullptr, (size_t)n, s);
+            p2p_reduce(comm, d_out, (size_t)n, s);
+            return;
+        }
+        if (k_loc > 0) x_support(g, d_idx_loc, k_loc, d_coef_loc, 1, d_out, s);
+        else IHTB_CUDA(cudaMemsetAsync(d_out, 0, n * sizeof(double), s));
         comm_allreduce_sum_f64(comm, d_out, (size_t)n, s);
     }
 
@@ -299,9 +310,7 @@ struct ihtb_fit {
         // from the host either: the support's exact df values are in d_gout, df2 is in d_scal (src/utilities.jl:728-756)
         denom_ready = false;
         if (!rerun) {
-            if (nsupp) x_support(g, d_cols.p, nsupp, d_gout.p + glaunch, 1, d_xs.p, s);
-            else IHTB_CUDA(cudaMemsetAsync(d_xs.p, 0, n * sizeof(double), s));
-            comm_allreduce_sum_f64(comm, d_xs.p, (size_t)n, s);
+            support_matvec_dev(d_cols.p, nsupp, d_gout.p + glaunch, d_xs.p);
             std::vector<double> mask((size_t)q);
             for (int64_t l = 0; l < q; ++l) mask[l] = idc[l] ? 1.0 : 0.0;
             upload(d_small.p + q, mask.data(), (size_t)q);
@@ -359,6 +368,27 @@ struct ihtb_fit {
         std::sort(cand_cache.begin(), cand_cache.end());
         cand_cache.erase(std::unique(cand_cache.begin(), cand_cache.end()), cand_cache.end());
         n_cand_iter += (int64_t)cand_cache.size();
+        // Only the k largest exact |df| OUTSIDE the support can enter P_k(b0 + eta*df) for any eta (the support itself
+        // is always a candidate); with R ranks the merged list holds R x (k + |supp|) entries, so trim it once here
+        // instead of sorting it in every gradstep/backtrack.  Entries within a relative 1e-12 of the k-th value stay:
+        // eta*df may round two nearly equal magnitudes to a tie, which is then broken by index.
+        if ((int64_t)cand_cache.size() > cfg.k) {
+            std::vector<std::pair<double, int64_t>> outside;
+            outside.reserve(cand_cache.size());
+            for (int64_t j : cand_cache)
+                if (!std::binary_search(idx.begin(), idx.end(), j)) outside.push_back({std::fabs(df_exact.at(j)), j});
+            if ((int64_t)outside.size() > cfg.k) {
+                std::nth_element(outside.begin(), outside.begin() + (cfg.k - 1), outside.end(),
+                                 [](const std::pair<double, int64_t>& x, const std::pair<double, int64_t>& y) {
+                                     return x.first > y.first;
+                                 });
+                const double thr = outside[(size_t)cfg.k - 1].first * (1.0 - 1e-12);
+                cand_cache.clear();
+                for (const auto& e : outside)
+                    if (e.first >= thr) cand_cache.push_back(e.second);
+                std::sort(cand_cache.begin(), cand_cache.end());
+            }
+        }
         if (rerun) return;
         float ms = 0.f;
         IHTB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -719,6 +749,7 @@ struct ihtb_fit {
             }
         }
         compute_pve();
+        IHTB_CHECK(!p2p_failed(comm), IHTB_ECUDA, "peer-memory all-reduce timed out waiting for another rank");
         inited = false;   // like the reference, a fitted variable must be re-initialised before another fit
         if (res) {
             res->time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -843,6 +874,7 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
             IHTB_CUDA(cudaMemcpyAsync(f->shard_j0.data(), f->d_selall.p, nr * sizeof(int64_t), cudaMemcpyDeviceToHost,
                                       f->s));
             IHTB_CUDA(cudaStreamSynchronize(f->s));
+            p2p_setup(comm, (size_t)n, f->s);      // collective; silently stays on NCCL if IPC mapping is unavailable
         }
         f->zkeep.assign((size_t)q, 1);
         if (zkeep) for (int64_t l = 0; l < q; ++l) f->zkeep[l] = zkeep[l] ? 1 : 0;

@@ -3,6 +3,7 @@
 // (src/utilities.jl:728-743) and their multivariate forms (src/multivariate.jl:24,234); the column dots
 // re-score top-k candidates exactly (same value mul!(df, Transpose(x), r) gives for those columns).
 #include "common.cuh"
+#include "comm.cuh"
 
 namespace ihtb {
 
@@ -10,10 +11,13 @@ constexpr int XS_CHUNK = 32;  // columns staged per shared-memory table refill
 
 // out[i, t] = sum_c x[i, idx_c] * coef[c, t], ascending c (the order the reference's single-thread loop uses).
 // One thread per packed byte (4 samples). tab[c][code][t] = ((dos(code) - mu) * sinv) * coef[c, t].
-template <int M>
+// PUSH (M == 1, SNP-sharded fits): instead of `out`, the partial vector is stored into slot[parity][my_rank] of EVERY
+// rank through the IPC-mapped peer pointers in `pv`, and the last CTA publishes the flags (comm.cuh) -- the all-reduce
+// that follows is then a local sum of nranks slots (k_p2p_reduce).
+template <int M, bool PUSH>
 __global__ void __launch_bounds__(256)
 k_x_support(GenoView gv, const int64_t* __restrict__ idx, int64_t k, const double* __restrict__ coef,
-            double* __restrict__ out) {
+            double* __restrict__ out, P2PView pv, unsigned long long seq) {
     const int64_t nbytes = gv.nbytes, n = gv.n;
     const double* __restrict__ mu = gv.mu;
     const double* __restrict__ sinv = gv.sinv;
@@ -52,6 +56,27 @@ k_x_support(GenoView gv, const int64_t* __restrict__ idx, int64_t k, const doubl
             }
         }
     }
+    if (PUSH) {
+        // stage the CTA's 1024 contiguous samples so that every peer store is a full 16-byte lane of a 128-byte line
+        // (NVLink write packets with all bytes enabled)
+        __shared__ double stage[PUSH ? 1024 : 1];
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < 4; ++s) stage[4 * threadIdx.x + s] = acc[s][0];
+        __syncthreads();
+        const int64_t base = 1024 * (int64_t)blockIdx.x;
+        for (int e = 2 * threadIdx.x; e < 1024; e += 512) {
+            const int64_t i = base + e;
+            if (i + 1 < n) {
+                const double2 x = make_double2(stage[e], stage[e + 1]);
+                for (int r = 0; r < pv.nranks; ++r) *reinterpret_cast<double2*>(pv.push_slot[r] + i) = x;
+            } else if (i < n) {
+                for (int r = 0; r < pv.nranks; ++r) pv.push_slot[r][i] = stage[e];
+            }
+        }
+        p2p_publish(pv, seq);
+        return;
+    }
     if (b < nbytes) {
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
@@ -66,7 +91,14 @@ k_x_support(GenoView gv, const int64_t* __restrict__ idx, int64_t k, const doubl
 template <int M>
 static void launch_x_support(const ihtb_geno* g, const int64_t* d_idx, int64_t k, const double* d_coef, double* d_out,
                              cudaStream_t s) {
-    IHTB_LAUNCH((k_x_support<M>), (unsigned)ceil_div(g->nbytes, 256), 256, 0, s, geno_view(g), d_idx, k, d_coef, d_out);
+    IHTB_LAUNCH((k_x_support<M, false>), (unsigned)ceil_div(g->nbytes, 256), 256, 0, s, geno_view(g), d_idx, k, d_coef,
+                d_out, P2PView{}, 0ull);
+}
+
+void x_support_push(const ihtb_geno* g, const int64_t* d_idx, int64_t k, const double* d_coef, ihtb_comm* c,
+                    cudaStream_t s) {
+    IHTB_LAUNCH((k_x_support<1, true>), (unsigned)ceil_div(g->nbytes, 256), 256, 0, s, geno_view(g), d_idx, k, d_coef,
+                (double*)nullptr, p2p_view(c), (unsigned long long)(c->p2p_seq + 1));
 }
 
 void x_support(const ihtb_geno* g, const int64_t* d_idx, int64_t k, const double* d_coef, int64_t m, double* d_out,

@@ -67,6 +67,12 @@ class Comm:
         check(lib.ihtb_comm_create(cpath, uid.ctypes.data_as(C.POINTER(C.c_uint8)), self.rank, self.world,
                                    C.byref(self._h)))
 
+    def allreduce_latency_us(self, n: int, reps: int = 200, p2p: bool = True) -> float:
+        """Collective micro-benchmark (device time per all-reduce of n doubles); every rank must call it."""
+        out = C.c_double(0.0)
+        check(load().ihtb_comm_allreduce_bench(self._h, n, reps, 1 if p2p else 0, C.byref(out)))
+        return out.value
+
     def close(self):
         if getattr(self, "_h", None):
             load().ihtb_comm_destroy(self._h)
