@@ -59,7 +59,7 @@ typedef struct ihtb_cfg {
     int32_t max_step;    /* 3                                                 `max_step` */
     int32_t sweep_mode;  /* IHTB_SWEEP_FAST | IHTB_SWEEP_EXACT                           */
     int32_t est_r;       /* 0 = :None, 1 = :MM, 2 = :Newton (NegativeBinomial only)   `est_r`    */
-    int32_t reserved;
+    int32_t debias;      /* 1: refit the support by IRLS when it did not change, iterations >= 5 (src/fit.jl:187-188) */
 } ihtb_cfg;
 
 /* IHTResult (src/data_structures.jl:245-258); beta/c are written through ihtb_fit_get */
@@ -95,6 +95,14 @@ int32_t ihtb_launch_count(int64_t* count);   /* kernels launched by this library
 /* bed_cols: SNP-major packed columns WITHOUT the 3 magic bytes; column j starts at bed_cols + j*col_stride_bytes. */
 int32_t ihtb_geno_create(const uint8_t* bed_cols, int64_t n, int64_t p, int64_t col_stride_bytes,
                          int32_t center, int32_t scale, int32_t impute, ihtb_geno** out);
+/* Piecewise ingest: per-chromosome .bed files or sources that are not one mappable array.  create_empty
+ * allocates the HBM matrix, load_columns streams PLINK columns [j_first, j_first+ncols) through pinned double buffers
+ * (any order, each column exactly once), finalize computes mu/sigma_inv and the missing-sample index.  Every other
+ * call returns IHTB_EINVAL on a handle that is not finalized.  ihtb_geno_create = the three in one call. */
+int32_t ihtb_geno_create_empty(int64_t n, int64_t p, int32_t center, int32_t scale, int32_t impute, ihtb_geno** out);
+int32_t ihtb_geno_load_columns(ihtb_geno* g, const uint8_t* bed_cols, int64_t col_stride_bytes, int64_t j_first,
+                               int64_t ncols);
+int32_t ihtb_geno_finalize(ihtb_geno* g);
 /* Synthetic PLINK matrix generated on the device (mirrors simulate_random_snparray, src/simulate_utilities.jl:23-51):
  * maf_j = clip(0.5*U, 0.01, 0.5), genotype = Bern(maf)+Bern(maf), optional missing rate; counter-based hash keyed by
  * (seed, global column, sample).  Columns [j0, j0+p_local) of a p_global-column matrix (j0=0, p_local=p for one GPU). */
@@ -104,6 +112,10 @@ int32_t ihtb_geno_create_synthetic(int64_t n, int64_t p_local, int64_t j0, uint6
 int32_t ihtb_synth_host(int64_t n, int64_t ncols, int64_t j0, uint64_t seed, double missing_rate, uint8_t* out);
 int32_t ihtb_geno_dims(const ihtb_geno* g, int64_t* n, int64_t* p);
 int32_t ihtb_geno_stats(const ihtb_geno* g, double* mu, double* sigma_inv, int64_t* n_missing);
+/* SnpArrays `counts(s, dims=1)`: counts[4*j + c] = samples of column j with code c (0: 00, 1: 01 = missing, 2: 10, 3: 11) */
+int32_t ihtb_geno_counts(const ihtb_geno* g, int64_t* counts_4_by_p);
+/* SnpArrays `maf(s)` (used by maf_weights, src/utilities.jl:692-697): (n1 + 2 n2) / (2 n_obs), folded to <= 0.5 */
+int32_t ihtb_geno_maf(const ihtb_geno* g, double* maf);
 /* bit-exact getindex: out[(j-j0)*(i1-i0) + (i-i0)] = x[i, j] for i in [i0,i1), j in [j0,j1)  (src/utilities.jl:102,735) */
 int32_t ihtb_geno_decode(const ihtb_geno* g, int64_t i0, int64_t i1, int64_t j0, int64_t j1, double* out_colmajor);
 /* packed bytes of columns [j0,j1), ceil(n/4) bytes each (for generator parity and .bed export) */
@@ -128,6 +140,10 @@ int32_t ihtb_fit_create(const ihtb_geno* g, const double* y, const double* z, in
  * returns the same global model.  beta in ihtb_fit_get has p_global entries.  comm == NULL: plain single-GPU fit. */
 int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_global, const double* y,
                                 const double* z, int64_t q, const uint8_t* zkeep, const ihtb_cfg* cfg, ihtb_fit** out);
+/* prior weights on the SNPs (keyword `weight`, src/fit.jl:69; scale b before project_k!, src/utilities.jl:291-354):
+ * weight[p_global] > 0 (the whole vector on every rank of a sharded fit), NULL clears.  Call before ihtb_fit_init.
+ * Covariates keep weight 1 (the reference indexes weight[p+1..p+q] out of bounds there). */
+int32_t ihtb_fit_set_weights(ihtb_fit* f, const double* weight);
 int32_t ihtb_fit_set_k(ihtb_fit* f, int64_t k);                       /* v.k = sparsity (src/cross_validation.jl:110) */
 int32_t ihtb_fit_init(ihtb_fit* f, const uint8_t* train_mask);         /* init_iht_indices!; NULL = all samples */
 /* init_iht_indices!(v, init_beta = true, ...): beta starts from per-SNP univariate regressions (initialize_beta!,

@@ -67,7 +67,7 @@ end
 # ---- fit_iht on the device -----------------------------------------------------------------------------------
 struct Cfg
     dist::Int32; link::Int32; k::Int64; nb_r::Float64; tol::Float64
-    max_iter::Int32; min_iter::Int32; max_step::Int32; sweep_mode::Int32; est_r::Int32; reserved::Int32
+    max_iter::Int32; min_iter::Int32; max_step::Int32; sweep_mode::Int32; est_r::Int32; debias::Int32
 end
 mutable struct CResult
     time::Float64; logl::Float64; iter::Int64; sigma_g::Float64; n_sweeps::Int64; n_backtracks::Int64

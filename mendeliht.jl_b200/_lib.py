@@ -44,7 +44,7 @@ _EXC = {IHTB_EINVAL: IHTBError, IHTB_EDIM: DimensionMismatch, IHTB_EDOMAIN: IHTB
 class Cfg(C.Structure):
     _fields_ = [("dist", C.c_int32), ("link", C.c_int32), ("k", C.c_int64), ("nb_r", C.c_double),
                 ("tol", C.c_double), ("max_iter", C.c_int32), ("min_iter", C.c_int32), ("max_step", C.c_int32),
-                ("sweep_mode", C.c_int32), ("est_r", C.c_int32), ("reserved", C.c_int32)]
+                ("sweep_mode", C.c_int32), ("est_r", C.c_int32), ("debias", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -72,6 +72,11 @@ SIGNATURES = {
     "ihtb_set_device": [C.c_int32],
     "ihtb_launch_count": [_i64],
     "ihtb_geno_create": [_u8, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _pp],
+    "ihtb_geno_create_empty": [C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _pp],
+    "ihtb_geno_load_columns": [_p, _u8, C.c_int64, C.c_int64, C.c_int64],
+    "ihtb_geno_finalize": [_p],
+    "ihtb_geno_counts": [_p, _i64],
+    "ihtb_geno_maf": [_p, _f64],
     "ihtb_geno_create_synthetic": [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_double, _pp],
     "ihtb_synth_host": [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_double, _u8],
     "ihtb_geno_dims": [_p, _i64, _i64],
@@ -84,6 +89,7 @@ SIGNATURES = {
     "ihtb_geno_destroy": [_p],
     "ihtb_fit_create": [_p, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), _pp],
     "ihtb_fit_create_sharded": [_p, _p, C.c_int64, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), _pp],
+    "ihtb_fit_set_weights": [_p, _f64],
     "ihtb_fit_set_k": [_p, C.c_int64],
     "ihtb_fit_init": [_p, _u8],
     "ihtb_fit_init_beta": [_p, _u8],

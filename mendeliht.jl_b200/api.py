@@ -53,11 +53,37 @@ class B200SnpLinAlg:
 
     @classmethod
     def from_bed_file(cls, path: str, n: int, **kw):
-        raw = np.fromfile(path, dtype=np.uint8)
-        if raw[:3].tobytes() != bytes([0x6C, 0x1B, 0x01]):
-            raise ValueError("not a SNP-major PLINK .bed file")
+        """One SNP-major PLINK .bed file.  The file is memory-mapped and streamed to the device in 64 MiB chunks, so
+        host memory stays bounded for files larger than RAM."""
+        return cls.from_bed_files([path], n, **kw)
+
+    @classmethod
+    def from_bed_files(cls, paths, n: int, center=True, scale=True, impute=True):
+        """Several .bed files over the same n samples (e.g. one per chromosome), concatenated SNP-wise in the order
+        given (ihtb_geno_create_empty / ihtb_geno_load_columns / ihtb_geno_finalize)."""
         stride = (n + 3) // 4
-        return cls.from_bed_columns(raw[3:].reshape(-1, stride), n, **kw)
+        maps = []
+        for path in paths:
+            mm = np.memmap(path, dtype=np.uint8, mode="r")
+            if mm.shape[0] < 3 or bytes(mm[:3]) != bytes([0x6C, 0x1B, 0x01]):
+                raise ValueError(f"{path}: not a SNP-major PLINK .bed file")
+            if (mm.shape[0] - 3) % stride:
+                raise _lib.DimensionMismatch(_lib.IHTB_EDIM, f"{path}: size is not 3 + p*ceil(n/4) bytes for n={n}")
+            maps.append(mm)
+        p = sum((mm.shape[0] - 3) // stride for mm in maps)
+        lib = load()
+        h = C.c_void_p()
+        check(lib.ihtb_geno_create_empty(n, p, int(center), int(scale), int(impute), C.byref(h)))
+        obj = cls(h, n, p)
+        obj.center, obj.scale, obj.impute = bool(center), bool(scale), bool(impute)
+        j = 0
+        for mm in maps:
+            cols = (mm.shape[0] - 3) // stride
+            base = mm.ctypes.data + 3
+            check(lib.ihtb_geno_load_columns(h, C.cast(C.c_void_p(base), C.POINTER(C.c_uint8)), stride, j, cols))
+            j += cols
+        check(lib.ihtb_geno_finalize(h))
+        return obj
 
     @classmethod
     def synthetic(cls, n: int, p: int, seed: int, missing_rate: float = 0.0, j0: int = 0):
@@ -76,6 +102,18 @@ class B200SnpLinAlg:
         mu = np.empty(self.p); sinv = np.empty(self.p); nm = np.empty(self.p, dtype=np.int64)
         check(load().ihtb_geno_stats(self._h, ptr(mu, C.c_double), ptr(sinv, C.c_double), ptr(nm, C.c_int64)))
         return mu, sinv, nm
+
+    def counts(self) -> np.ndarray:
+        """SnpArrays `counts(s, dims=1)`: int64 [4, p], rows = codes 00, 01 (missing), 10, 11."""
+        out = np.empty((self.p, 4), dtype=np.int64)
+        check(load().ihtb_geno_counts(self._h, ptr(out, C.c_int64)))
+        return out.T
+
+    def maf(self) -> np.ndarray:
+        """SnpArrays `maf(s)`: minor allele frequency of every SNP."""
+        out = np.empty(self.p)
+        check(load().ihtb_geno_maf(self._h, ptr(out, C.c_double)))
+        return out
 
     def decode(self, i0=0, i1=None, j0=0, j1=None) -> np.ndarray:
         """x[i0:i1, j0:j1] through the getindex formula, float64 [i1-i0, j1-j0]."""
@@ -154,7 +192,7 @@ class IHTVariable:
 
     def __init__(self, x: B200SnpLinAlg, z, y, k, d=NORMAL, l="IdentityLink", zkeep=None, nb_r=1.0, tol=1e-4,
                  max_iter=200, min_iter=5, max_step=3, sweep_mode=_lib.SWEEP_FAST, comm=None, p_global=None,
-                 est_r="None"):
+                 est_r="None", weight=None, debias=False):
         y = f64(y)
         z = np.asarray(z, dtype=np.float64)
         if z.ndim == 1:
@@ -178,13 +216,24 @@ class IHTVariable:
             raise _lib.IHTBError(_lib.IHTB_EINVAL, "Only negative binomial regression currently supports nuisance "
                                                    "parameter estimation")
         self.cfg = Cfg(DIST_ID[d], LINK_ID[l], int(k), float(nb_r), float(tol), int(max_iter), int(min_iter),
-                       int(max_step), int(sweep_mode), EST_R_ID[est_r], 0)
+                       int(max_step), int(sweep_mode), EST_R_ID[est_r], 1 if debias else 0)
         zf = np.asfortranarray(z)
         self._h = C.c_void_p()
         check(load().ihtb_fit_create_sharded(x._h, comm._h if comm is not None else None, self.p_global,
                                              ptr(y, C.c_double), zf.ctypes.data_as(C.POINTER(C.c_double)), q,
                                              ptr(zk, C.c_uint8) if zk is not None else None, C.byref(self.cfg),
                                              C.byref(self._h)))
+        if weight is not None and len(weight) > 0:
+            w = f64(weight)
+            if w.shape[0] != self.p_global:       # src/data_structures.jl:71-73
+                self.close()
+                raise _lib.DimensionMismatch(_lib.IHTB_EDIM,
+                                             f"weight must have length {self.p_global} but was {w.shape[0]}")
+            try:
+                check(load().ihtb_fit_set_weights(self._h, ptr(w, C.c_double)))
+            except Exception:
+                self.close()
+                raise
 
     def set_k(self, k):
         check(load().ihtb_fit_set_k(self._h, int(k)))
@@ -354,10 +403,15 @@ def _check_args(k, max_iter, max_step, tol):
 
 def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est_r="None", nb_r=1.0, tol=1e-4,
             max_iter=200, min_iter=5, max_step=3, sweep_mode=_lib.SWEEP_FAST, verbose=False, io=None,
-            comm=None, p_global=None, init_beta=False) -> IHTResult:
-    """`fit_iht(y, x, z; k, d, l, zkeep, tol, max_iter, min_iter, max_step)` (src/fit.jl:60-118)."""
+            comm=None, p_global=None, init_beta=False, weight=None, debias=False, use_maf=False) -> IHTResult:
+    """`fit_iht(y, x, z; k, d, l, weight, zkeep, est_r, debias, tol, max_iter, min_iter, max_step, init_beta)`
+    (src/fit.jl:60-118).  `use_maf` is accepted and, like in the reference, only reported (src/fit.jl:72,108):
+    pass `weight=maf_weights(x)` to weight the projection by allele frequency."""
     _check_args(k, max_iter, max_step, tol)
     if is_multivariate(y):      # d = MvNormal: Y is r x n, Z is q x n (src/fit.jl:66,125)
+        if debias:
+            raise _lib.IHTBError(_lib.IHTB_EUNSUPPORTED,
+                                 "Currently the debiasing routine for multivariate IHT is broken, sorry!")
         return _fit_mv(y, x, z, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode)
     if not x.center:
         raise _lib.IHTBError(_lib.IHTB_EUNSUPPORTED, "x is not centered! Please construct SnpLinAlg{Float64}"
@@ -366,7 +420,7 @@ def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est
         z = np.ones(x.n)
     l = l or "IdentityLink"
     v = IHTVariable(x, z, y, k, d, l, zkeep, nb_r, tol, max_iter, min_iter, max_step, sweep_mode, comm, p_global,
-                    est_r)
+                    est_r, weight, debias)
     try:
         v.init_iht_indices(None, init_beta)
         res, trace = v.fit()
@@ -380,6 +434,15 @@ def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est
             print(f"Iteration {i + 1}: loglikelihood = {t[0]}, backtracks = {t[1]}, tol = {t[2]}", file=out)
     return IHTResult(res.time, res.logl, int(res.iter), beta, c, 1, k, [], d, res.sigma_g, trace, int(res.n_sweeps),
                      int(res.n_backtracks), res.sweep_seconds, int(res.n_launches))
+
+
+def maf_weights(x: B200SnpLinAlg, max_weight: float = np.inf) -> np.ndarray:
+    """`maf_weights(x; max_weight)` (src/utilities.jl:692-697): w_j = 1 / (2 sqrt(p_j (1 - p_j))) clamped to
+    [1, max_weight], p_j the minor allele frequency."""
+    p = x.maf()
+    with np.errstate(divide="ignore"):
+        w = 1.0 / (2.0 * np.sqrt(p * (1.0 - p)))
+    return np.clip(w, 1.0, max_weight)
 
 
 def allocate_fold_and_k(q: int, path):
@@ -402,7 +465,7 @@ def meanloss(fitloss, q: int, folds):
 
 def cv_iht(y, x: B200SnpLinAlg, z=None, d=NORMAL, l=None, path=range(1, 21), q=5, folds=None, zkeep=None,
            nb_r=1.0, max_iter=100, min_iter=5, sweep_mode=_lib.SWEEP_FAST, combos=None, return_grid=False,
-           init_beta=False):
+           init_beta=False, weight=None, debias=False):
     """`cv_iht` (src/cross_validation.jl:60-131).  `folds` in 1..q (drawn with numpy's default_rng if omitted).
     `combos`: optional subset of grid positions to run (used by the multi-GPU farm, parallel.py)."""
     path = [int(k) for k in path]
@@ -421,7 +484,8 @@ def cv_iht(y, x: B200SnpLinAlg, z=None, d=NORMAL, l=None, path=range(1, 21), q=5
     if mv:
         v = mIHTVariable(x, z, y, max(path), zkeep, 1e-4, max_iter, min_iter, 3, sweep_mode)
     else:
-        v = IHTVariable(x, z, y, max(path), d, l, zkeep, nb_r, 1e-4, max_iter, min_iter, 3, sweep_mode)
+        v = IHTVariable(x, z, y, max(path), d, l, zkeep, nb_r, 1e-4, max_iter, min_iter, 3, sweep_mode,
+                        weight=weight, debias=debias)
     try:
         for i in todo:
             fold, k = grid[i]

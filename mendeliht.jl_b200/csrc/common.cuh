@@ -131,7 +131,12 @@ struct ihtb_geno {
     ihtb::DBuf<int64_t> miss_ptr;   // [p+1]
     ihtb::DBuf<int32_t> miss_idx;   // sample indices
     int64_t total_missing = 0;
+    bool ready = false;             // columns loaded and statistics computed (false between create_empty and finalize)
 };
+
+static inline void geno_require_ready(const ihtb_geno* g) {
+    IHTB_CHECK(g && g->ready, IHTB_EINVAL, "genotype handle is not finalized (ihtb_geno_finalize)");
+}
 
 // what kernels see of a genotype handle
 struct GenoView {

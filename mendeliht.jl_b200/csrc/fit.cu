@@ -15,6 +15,7 @@
 #include "glm.cuh"
 #include "topk.cuh"
 #include "comm.cuh"
+#include "debias.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -81,6 +82,20 @@ struct ihtb_fit {
     std::vector<double> c, c0, best_c, df2, h_y, h_mu;
     std::vector<uint8_t> idc, idc0;
     std::unordered_map<int64_t, double> df_exact;
+    // prior weights (src/data_structures.jl:36): host copy over all p_global SNPs, device copy of this rank's columns
+    std::vector<double> wt;
+    DBuf<double> d_wt;
+    double w_at(int64_t j) const { return wt.empty() ? 1.0 : wt[(size_t)j]; }
+    void set_weights(const double* w) {
+        if (!w) { wt.clear(); tk.wt = nullptr; return; }
+        for (int64_t j = 0; j < p_global; ++j)
+            IHTB_CHECK(w[j] > 0.0 && std::isfinite(w[j]), IHTB_EDOMAIN, "weights must be positive and finite");
+        wt.assign(w, w + p_global);
+        if (d_wt.n < (size_t)p) d_wt.alloc((size_t)p);
+        IHTB_CUDA(cudaMemcpyAsync(d_wt.p, wt.data() + j0, (size_t)p * sizeof(double), cudaMemcpyHostToDevice, s));
+        sync();
+        tk.wt = d_wt.p;
+    }
     std::vector<int64_t> cand_cache;      // candidate columns of the last sweep (global indices, sorted)
     bool df_sparse = false;
     std::vector<int64_t> dfs_idx;
@@ -376,7 +391,8 @@ struct ihtb_fit {
             std::vector<std::pair<double, int64_t>> outside;
             outside.reserve(cand_cache.size());
             for (int64_t j : cand_cache)
-                if (!std::binary_search(idx.begin(), idx.end(), j)) outside.push_back({std::fabs(df_exact.at(j)), j});
+                if (!std::binary_search(idx.begin(), idx.end(), j))
+                    outside.push_back({std::fabs(df_exact.at(j)) * w_at(j), j});
             if ((int64_t)outside.size() > cfg.k) {
                 std::nth_element(outside.begin(), outside.begin() + (cfg.k - 1), outside.end(),
                                  [](const std::pair<double, int64_t>& x, const std::pair<double, int64_t>& y) {
@@ -472,7 +488,12 @@ struct ihtb_fit {
         items.reserve(cand.size() + (size_t)q);
         for (int64_t j : cand) {
             double v = b_lookup(idx0, b0, j) + eta * df_at(j);
-            items.push_back({std::fabs(v), j, v});
+            if (!wt.empty()) {          // vectorize!: a = b*w ... unvectorize!: b = a/w (src/utilities.jl:302-304,340-342)
+                const double w = wt[(size_t)j], a = v * w;
+                items.push_back({std::fabs(a), j, a / w});
+            } else {
+                items.push_back({std::fabs(v), j, v});
+            }
         }
         for (int64_t l = 0; l < q; ++l) {
             c[l] = c0[l] + eta * df2[l];
@@ -496,6 +517,17 @@ struct ihtb_fit {
         for (auto& kv : keep) { idx.push_back(kv.first); b.push_back(kv.second); }
         for (int64_t l = 0; l < q; ++l) idc[l] = c[l] != 0.0;
     }
+
+    // ---- debias! (src/utilities.jl:1014-1020): b[idx] = GLM refit of y on x[:, idx]; xb / mu / df stay as they are ----
+    DebiasWs debias_ws;
+    void debias() {
+        if (idx.empty()) return;
+        IHTB_CHECK(!comm, IHTB_EUNSUPPORTED, "debias is not available for SNP-sharded fits yet");
+        upload(d_cols.p, idx.data(), idx.size());
+        debias_irls(g, d_y.p, cfg.dist, cfg.link, glm.nb_r, d_cols.p, (int)idx.size(), b.data(), debias_ws, s);
+        ++n_debias;
+    }
+    int64_t n_debias = 0;
 
     // ---- save_prev! (src/utilities.jl:702-712) ----------------------------------------------------
     double save_prev(double cur, double best) {
@@ -597,7 +629,10 @@ struct ihtb_fit {
         }
         struct Item { double a; int64_t pos; double v; };
         std::vector<Item> items;
-        for (size_t t = 0; t < cand.size(); ++t) items.push_back({std::fabs(vals[t]), cand[t], vals[t]});
+        for (size_t t = 0; t < cand.size(); ++t) {
+            const double w = w_at(cand[t]), a = vals[t] * w;
+            items.push_back({std::fabs(a), cand[t], wt.empty() ? vals[t] : a / w});
+        }
         for (int64_t l = 0; l < q; ++l)
             if (!zkeep[l]) items.push_back({std::fabs(c[l]), p_global + l, c[l]});
         std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) {
@@ -657,7 +692,11 @@ struct ihtb_fit {
         std::vector<int64_t> cand = cand_cache;      // top-k of |df| with exact values (score_and_sweep)
         struct Item { double a; int64_t pos; double v; };
         std::vector<Item> items;
-        for (int64_t j : cand) { double v = df_exact.at(j); items.push_back({std::fabs(v), j, v}); }
+        for (int64_t j : cand) {
+            double v = df_exact.at(j);
+            const double w = w_at(j), a = v * w;
+            items.push_back({std::fabs(a), j, wt.empty() ? v : a / w});
+        }
         for (int64_t l = 0; l < q; ++l)
             if (!zkeep[l]) items.push_back({std::fabs(df2[l]), p_global + l, df2[l]});
         std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) {
@@ -738,6 +777,7 @@ struct ihtb_fit {
             n_cand_iter = 0;
             one_step(next_logl, eta, eta_step, next_logl);
             ++n_steps;
+            if (cfg.debias && iter >= 5 && idx == idx0) debias();        // src/fit.jl:187-188
             double scaled_norm = check_convergence();
             if (trace && iter - 1 < trace_cap)
                 trace[iter - 1] = ihtb_iter_trace{next_logl, scaled_norm, eta, eta_step, (int32_t)n_cand_iter};
@@ -832,6 +872,7 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
     return guard([&] {
         IHTB_CHECK(g && y && z && cfg && out, IHTB_EINVAL, "NULL argument");
         IHTB_CHECK(p_global >= g->p, IHTB_EDIM, "p_global is smaller than the local shard");
+        geno_require_ready(g);
         IHTB_CHECK(comm || (p_global == g->p && g->j0 == 0) || true, IHTB_EINVAL, "");
         IHTB_CHECK(q >= 1, IHTB_EDIM, "z must have at least the intercept column");
         IHTB_CHECK(cfg->k >= 0, IHTB_EINVAL, "Value of k (max predictors per group) must be nonnegative!");
@@ -894,8 +935,17 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
                         f->d_scal.p, cfg->dist, cfg->link, cfg->nb_r};
         f->tk = TopkCtx{p, f->d_keyL.p, f->d_keyU.p, f->d_hist.p, reinterpret_cast<TopkState*>(f->d_sel.p),
                         f->d_sel.p + 2, f->cap};
+        f->wt.clear();
         f->sync();
         *out = f.release();
+    });
+}
+
+int32_t ihtb_fit_set_weights(ihtb_fit* f, const double* weight) {
+    return guard([&] {
+        IHTB_CHECK(f, IHTB_EINVAL, "NULL fit handle");
+        IHTB_CUDA(cudaSetDevice(f->g->device));
+        f->set_weights(weight);
     });
 }
 

@@ -94,6 +94,33 @@ __global__ void k_col_stats(GenoView g, int scale, double* __restrict__ mu, doub
     }
 }
 
+// one warp per column: how many samples carry each 2-bit code (SnpArrays `counts(s, dims=1)`: rows 00, 01 = missing, 10, 11)
+__global__ void k_col_counts(GenoView g, int64_t* __restrict__ out /*[4][p] column-major 4 x p*/) {
+    int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (j >= g.p) return;
+    int64_t nvec = g.stride >> 4;
+    int c1 = 0, c2 = 0, cm = 0;
+    for (int64_t v = lane; v < nvec; v += 32) {
+        uint4 q = *reinterpret_cast<const uint4*>(gv_ptr(g, j, 16 * v));
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            uint32_t lo = w[t] & 0x55555555u, hi = (w[t] >> 1) & 0x55555555u;
+            cm += __popc(lo & ~hi);
+            c1 += __popc(hi & ~lo);
+            c2 += __popc(hi & lo);
+        }
+    }
+    c1 = warp_sum(c1); c2 = warp_sum(c2); cm = warp_sum(cm);
+    if (lane == 0) {
+        out[4 * j + 0] = g.n - c1 - c2 - cm;      // padding beyond n is zero-filled = code 00, hence n - others
+        out[4 * j + 1] = cm;
+        out[4 * j + 2] = c1;
+        out[4 * j + 3] = c2;
+    }
+}
+
 // CSR fill of missing sample indices: one warp per column, ordered by sample index
 __global__ void k_fill_missing(GenoView g, const int64_t* __restrict__ ptr, int32_t* __restrict__ idx) {
     int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -254,6 +281,69 @@ int32_t ihtb_launch_count(int64_t* count) {
     });
 }
 
+// Host -> HBM ingest of `ncols` PLINK columns starting at local column j_dst.  Two pinned buffers: while chunk i is
+// copied to the device and repacked into the tiled layout on `st`, a pool of host threads gathers chunk i+1 from the
+// caller's (typically mmapped, page-faulting) memory into the other buffer, so file I/O, PCIe and the repack overlap
+// and the resident host footprint is bounded (2 x 64 MiB) whatever the file size.
+static void upload_columns(ihtb_geno* g, const uint8_t* bed_cols, int64_t col_stride_bytes, int64_t j_dst, int64_t ncols) {
+    const int64_t pitch = ceil_div(g->nbytes, 16) * 16;
+    int64_t cols_per = (int64_t(64) << 20) / pitch;
+    if (cols_per < 1) cols_per = 1;
+    if (cols_per > ncols) cols_per = ncols;
+    const int NB = 2;
+    HBuf<uint8_t> hbuf[NB];
+    DBuf<uint8_t> dbuf[NB];
+    cudaEvent_t done[NB];
+    cudaStream_t st;
+    IHTB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (int b = 0; b < NB; ++b) {
+        hbuf[b].alloc((size_t)(cols_per * pitch));
+        dbuf[b].alloc((size_t)(cols_per * pitch));
+        IHTB_CUDA(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+    }
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    if (nt > 16) nt = 16;
+    const GenoView gv = geno_view(g);
+    const int64_t vec_per_col = (g->nbytes + 15) >> 4;
+    const int64_t nbytes = g->nbytes;
+    int b = 0;
+    try {
+        for (int64_t j = 0; j < ncols; j += cols_per, b ^= 1) {
+            const int64_t h = (ncols - j < cols_per) ? ncols - j : cols_per;
+            IHTB_CUDA(cudaEventSynchronize(done[b]));                 // buffer b is free again
+            uint8_t* dst = hbuf[b].p;
+            const uint8_t* src = bed_cols + j * col_stride_bytes;
+            const unsigned use = (unsigned)std::min<int64_t>(nt, h);
+            std::vector<std::thread> pool;
+            for (unsigned t = 1; t < use; ++t)
+                pool.emplace_back([=] {
+                    for (int64_t c = h * t / use; c < h * (t + 1) / use; ++c)
+                        memcpy(dst + c * pitch, src + c * col_stride_bytes, (size_t)nbytes);
+                });
+            for (int64_t c = 0; c < h / use; ++c) memcpy(dst + c * pitch, src + c * col_stride_bytes, (size_t)nbytes);
+            for (auto& th : pool) th.join();
+            IHTB_CUDA(cudaMemcpyAsync(dbuf[b].p, hbuf[b].p, (size_t)(h * pitch), cudaMemcpyHostToDevice, st));
+            IHTB_LAUNCH(k_repack, (unsigned)ceil_div(h * vec_per_col, 256), 256, 0, st, dbuf[b].p, pitch, j_dst + j, h, gv);
+            IHTB_CUDA(cudaEventRecord(done[b], st));
+        }
+        IHTB_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        for (int i = 0; i < NB; ++i) cudaEventDestroy(done[i]);
+        cudaStreamDestroy(st);
+        throw;
+    }
+    for (int i = 0; i < NB; ++i) cudaEventDestroy(done[i]);
+    cudaStreamDestroy(st);
+}
+
+static void seal_handle(ihtb_geno* g) {
+    if (g->n % 4) IHTB_LAUNCH(k_mask_tail, (unsigned)ceil_div(g->p, 256), 256, 0, 0, geno_view(g), (int)(g->n % 4));
+    finish_handle(g);
+    g->ready = true;
+}
+
 int32_t ihtb_geno_create(const uint8_t* bed_cols, int64_t n, int64_t p, int64_t col_stride_bytes, int32_t center,
                          int32_t scale, int32_t impute, ihtb_geno** out) {
     return guard([&] {
@@ -262,29 +352,50 @@ int32_t ihtb_geno_create(const uint8_t* bed_cols, int64_t n, int64_t p, int64_t 
         ihtb_geno* g = new_handle(n, p, center, scale, impute);
         try {
             IHTB_CUDA(cudaMemset(g->bed.p, 0, (size_t)(g->p * g->stride)));
-            // H2D in column blocks of <= 256 MiB through a staging buffer, then repack into the device layout
-            int64_t pitch = ceil_div(g->nbytes, 16) * 16;
-            int64_t cols_per = (int64_t(256) << 20) / pitch;
-            if (cols_per < 1) cols_per = 1;
-            if (cols_per > p) cols_per = p;
-            DBuf<uint8_t> staging((size_t)(cols_per * pitch));
-            GenoView gv = geno_view(g);
-            int64_t vec_per_col = (g->nbytes + 15) >> 4;
-            for (int64_t j = 0; j < p; j += cols_per) {
-                int64_t h = (p - j < cols_per) ? p - j : cols_per;
-                IHTB_CUDA(cudaMemcpy2D(staging.p, (size_t)pitch, bed_cols + j * col_stride_bytes,
-                                       (size_t)col_stride_bytes, (size_t)g->nbytes, (size_t)h,
-                                       cudaMemcpyHostToDevice));
-                IHTB_LAUNCH(k_repack, (unsigned)ceil_div(h * vec_per_col, 256), 256, 0, 0, staging.p, pitch, j, h, gv);
-                IHTB_CUDA(cudaDeviceSynchronize());
-            }
-            if (n % 4) IHTB_LAUNCH(k_mask_tail, (unsigned)ceil_div(p, 256), 256, 0, 0, gv, (int)(n % 4));
-            finish_handle(g);
+            upload_columns(g, bed_cols, col_stride_bytes, 0, p);
+            seal_handle(g);
         } catch (...) {
             delete g;
             throw;
         }
         *out = g;
+    });
+}
+
+// ---- piecewise ingest: per-chromosome files, or sources that cannot be mapped as one array -----------------------
+int32_t ihtb_geno_create_empty(int64_t n, int64_t p, int32_t center, int32_t scale, int32_t impute, ihtb_geno** out) {
+    return guard([&] {
+        IHTB_CHECK(out, IHTB_EINVAL, "NULL argument");
+        ihtb_geno* g = new_handle(n, p, center, scale, impute);
+        try {
+            IHTB_CUDA(cudaMemset(g->bed.p, 0, (size_t)(g->p * g->stride)));
+        } catch (...) {
+            delete g;
+            throw;
+        }
+        g->ready = false;
+        *out = g;
+    });
+}
+
+int32_t ihtb_geno_load_columns(ihtb_geno* g, const uint8_t* bed_cols, int64_t col_stride_bytes, int64_t j_first,
+                               int64_t ncols) {
+    return guard([&] {
+        IHTB_CHECK(g && bed_cols, IHTB_EINVAL, "NULL argument");
+        IHTB_CHECK(!g->ready, IHTB_EINVAL, "genotype handle is already finalized");
+        IHTB_CHECK(col_stride_bytes >= g->nbytes, IHTB_EDIM, "col_stride_bytes is smaller than ceil(n/4)");
+        IHTB_CHECK(j_first >= 0 && ncols >= 0 && j_first + ncols <= g->p, IHTB_EDIM, "column range outside the matrix");
+        IHTB_CUDA(cudaSetDevice(g->device));
+        if (ncols > 0) upload_columns(g, bed_cols, col_stride_bytes, j_first, ncols);
+    });
+}
+
+int32_t ihtb_geno_finalize(ihtb_geno* g) {
+    return guard([&] {
+        IHTB_CHECK(g, IHTB_EINVAL, "NULL argument");
+        IHTB_CHECK(!g->ready, IHTB_EINVAL, "genotype handle is already finalized");
+        IHTB_CUDA(cudaSetDevice(g->device));
+        seal_handle(g);
     });
 }
 
@@ -301,6 +412,7 @@ int32_t ihtb_geno_create_synthetic(int64_t n, int64_t p_local, int64_t j0, uint6
             int64_t total = g->p * words;
             IHTB_LAUNCH(k_synth, (unsigned)ceil_div(total, 256), 256, 0, 0, geno_view(g), j0, seed, miss_thr);
             finish_handle(g);
+            g->ready = true;
         } catch (...) {
             delete g;
             throw;
@@ -358,6 +470,7 @@ int32_t ihtb_geno_dims(const ihtb_geno* g, int64_t* n, int64_t* p) {
 int32_t ihtb_geno_stats(const ihtb_geno* g, double* mu, double* sigma_inv, int64_t* n_missing) {
     return guard([&] {
         IHTB_CHECK(g, IHTB_EINVAL, "NULL genotype handle");
+        geno_require_ready(g);
         IHTB_CUDA(cudaSetDevice(g->device));
         if (mu) IHTB_CUDA(cudaMemcpy(mu, g->mu.p, g->p * sizeof(double), cudaMemcpyDeviceToHost));
         if (sigma_inv) IHTB_CUDA(cudaMemcpy(sigma_inv, g->sinv.p, g->p * sizeof(double), cudaMemcpyDeviceToHost));
@@ -369,11 +482,36 @@ int32_t ihtb_geno_stats(const ihtb_geno* g, double* mu, double* sigma_inv, int64
     });
 }
 
+int32_t ihtb_geno_counts(const ihtb_geno* g, int64_t* counts) {
+    return guard([&] {
+        IHTB_CHECK(g && counts, IHTB_EINVAL, "NULL argument");
+        geno_require_ready(g);
+        IHTB_CUDA(cudaSetDevice(g->device));
+        DBuf<int64_t> d((size_t)(4 * g->p));
+        IHTB_LAUNCH(k_col_counts, (unsigned)ceil_div(g->p * 32, 256), 256, 0, 0, geno_view(g), d.p);
+        IHTB_CUDA(cudaMemcpy(counts, d.p, (size_t)(4 * g->p) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    });
+}
+
+int32_t ihtb_geno_maf(const ihtb_geno* g, double* maf) {
+    return guard([&] {
+        IHTB_CHECK(g && maf, IHTB_EINVAL, "NULL argument");
+        geno_require_ready(g);
+        IHTB_CUDA(cudaSetDevice(g->device));
+        IHTB_CUDA(cudaMemcpy(maf, g->mu.p, g->p * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int64_t j = 0; j < g->p; ++j) {          // (n1 + 2 n2) / (2 n_obs), folded to the minor allele
+            double f = maf[j] / 2.0;
+            maf[j] = f > 0.5 ? 1.0 - f : f;
+        }
+    });
+}
+
 int32_t ihtb_geno_decode(const ihtb_geno* g, int64_t i0, int64_t i1, int64_t j0, int64_t j1, double* out) {
     return guard([&] {
         IHTB_CHECK(g && out, IHTB_EINVAL, "NULL argument");
         IHTB_CHECK(0 <= i0 && i0 <= i1 && i1 <= g->n && 0 <= j0 && j0 <= j1 && j1 <= g->p, IHTB_EDIM,
                    "decode block out of bounds");
+        geno_require_ready(g);
         IHTB_CUDA(cudaSetDevice(g->device));
         int64_t total = (i1 - i0) * (j1 - j0);
         if (total == 0) return;
@@ -387,6 +525,7 @@ int32_t ihtb_geno_packed(const ihtb_geno* g, int64_t j0, int64_t j1, uint8_t* ou
     return guard([&] {
         IHTB_CHECK(g && out, IHTB_EINVAL, "NULL argument");
         IHTB_CHECK(0 <= j0 && j0 <= j1 && j1 <= g->p, IHTB_EDIM, "column range out of bounds");
+        geno_require_ready(g);
         IHTB_CUDA(cudaSetDevice(g->device));
         if (j1 == j0) return;
         int64_t cols_per = (int64_t(256) << 20) / g->nbytes;

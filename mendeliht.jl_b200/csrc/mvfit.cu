@@ -620,7 +620,10 @@ int32_t ihtb_mvfit_create(const ihtb_geno* g, const double* Y, int64_t r, const 
                           const ihtb_cfg* cfg, ihtb_mvfit** out) {
     return guard([&] {
         IHTB_CHECK(g && Y && z && cfg && out, IHTB_EINVAL, "NULL argument");
+        geno_require_ready(g);
         IHTB_CHECK(r >= 2 && r <= MV_MAXR, IHTB_EUNSUPPORTED, "multivariate IHT supports 2..16 traits");
+        IHTB_CHECK(!cfg->debias, IHTB_EUNSUPPORTED,
+                   "Currently the debiasing routine for multivariate IHT is broken, sorry!");   // src/multivariate.jl:570
         IHTB_CHECK(q >= 1, IHTB_EDIM, "z must have at least the intercept row");
         IHTB_CHECK(cfg->k >= 1 && cfg->k <= g->p * r, IHTB_EINVAL, "Multivariate IHT requires 1 <= k <= r*p");
         IHTB_CHECK(cfg->max_iter >= 0 && cfg->max_step >= 0 && cfg->tol > 2.220446049250313e-16, IHTB_EINVAL,

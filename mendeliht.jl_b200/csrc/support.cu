@@ -227,6 +227,7 @@ extern "C" int32_t ihtb_x_support(const ihtb_geno* g, const int64_t* idx, int64_
                                   double* out) {
     return guard([&] {
         IHTB_CHECK(g && out && m >= 1 && k >= 0, IHTB_EINVAL, "bad argument");
+        geno_require_ready(g);
         IHTB_CHECK(k == 0 || (idx && coef), IHTB_EINVAL, "NULL idx/coef");
         IHTB_CUDA(cudaSetDevice(g->device));
         for (int64_t c = 0; c < k; ++c)

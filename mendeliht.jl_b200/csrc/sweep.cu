@@ -164,6 +164,7 @@ using namespace ihtb;
 extern "C" int32_t ihtb_xt_v(const ihtb_geno* g, const double* V, int64_t m, double* out, int32_t sweep_mode) {
     return guard([&] {
         IHTB_CHECK(g && V && out && m >= 1, IHTB_EINVAL, "bad argument");
+        geno_require_ready(g);
         IHTB_CHECK(sweep_mode == IHTB_SWEEP_FAST || sweep_mode == IHTB_SWEEP_EXACT, IHTB_EINVAL, "bad sweep_mode");
         IHTB_CUDA(cudaSetDevice(g->device));
         DBuf<double> dV((size_t)(g->n * m)), dOut((size_t)(g->p * m)), dmean((size_t)m);
@@ -191,6 +192,7 @@ extern "C" int32_t ihtb_sweep_bench(const ihtb_geno* g, int32_t sweep_mode, int3
                                     double* ms_kernel, double* ms_total) {
     return guard([&] {
         IHTB_CHECK(g && reps >= 1 && warmup >= 0, IHTB_EINVAL, "bad argument");
+        geno_require_ready(g);
         IHTB_CUDA(cudaSetDevice(g->device));
         cudaStream_t s;
         IHTB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));

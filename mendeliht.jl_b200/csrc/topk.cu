@@ -28,8 +28,8 @@ __device__ __forceinline__ void hist_flush(const int* sh, int* g, int nb) {
 __global__ void __launch_bounds__(TK_THREADS)
 k_keys_hist0(int64_t p, const double* __restrict__ dfa, const double* __restrict__ b0d,
              const double* __restrict__ sinv, int64_t p_mod, const double* __restrict__ bounds, double eta,
-             double bound, const double* __restrict__ scal, double bound_coef, uint32_t* __restrict__ keyL,
-             uint32_t* __restrict__ keyU, int* __restrict__ hist) {
+             double bound, const double* __restrict__ scal, double bound_coef, const double* __restrict__ wt,
+             uint32_t* __restrict__ keyL, uint32_t* __restrict__ keyU, int* __restrict__ hist) {
     // scal != NULL: the bound comes from the score kernel's sums still on the device:
     // bound = coef * (sum|r| + |sum r|) >= coef * ||r - mean(r)||_1 (no host round trip between sweep and selection)
     if (scal) bound = bound_coef * (scal[1] + fabs(scal[0]));
@@ -38,10 +38,12 @@ k_keys_hist0(int64_t p, const double* __restrict__ dfa, const double* __restrict
     __syncthreads();
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p; j += (int64_t)gridDim.x * blockDim.x) {
         double v = (b0d ? b0d[j] : 0.0) + eta * dfa[j];
-        double a = fabs(v);
+        // prior weights (src/utilities.jl:291-315): the projection ranks |v_j| * w_j, so magnitude and error scale by w_j
+        const double w = wt ? wt[j] : 1.0;
+        double a = fabs(v) * w;
         // blocked form (multivariate: entry j = t*p_mod + column): per-block bound, sinv of the column
         const double bj = bounds ? bounds[j / p_mod] : bound;
-        double e = fabs(eta) * sinv[bounds ? (j % p_mod) : j] * bj + a * 4e-16;
+        double e = fabs(eta) * sinv[bounds ? (j % p_mod) : j] * bj * w + a * 4e-16;
         double lo = a - e, up = a + e;
         if (!(lo > 0.0)) lo = 0.0;          // also maps NaN to 0
         if (!(up >= 0.0)) up = INFINITY;    // NaN: always a candidate
@@ -146,7 +148,7 @@ static void topk_run(TopkCtx& c, const double* d_dfa, const double* d_b0d, const
     int kk = (int)(k < c.p ? k : c.p);
     IHTB_LAUNCH(k_topk_reset, 1, 1, 0, s, c.st, kk);
     IHTB_LAUNCH(k_keys_hist0, grid, TK_THREADS, 0, s, c.p, d_dfa, d_b0d, d_sinv, p_mod, d_bounds, eta, bound, d_scal,
-                bound_coef, c.keyL, c.keyU, c.hist);
+                bound_coef, c.wt, c.keyL, c.keyU, c.hist);
     IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 21, 11);
     IHTB_LAUNCH(k_hist, grid, TK_THREADS, 0, s, c.p, c.keyL, c.st, 10, 11, c.hist);
     IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 10, 11);

@@ -18,6 +18,7 @@ struct TopkCtx {
     TopkState* st;
     int64_t* cand;
     int cap;
+    const double* wt = nullptr;   // optional prior weights [p]: keys rank |v_j| * wt_j
 };
 
 void topk_candidates(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, double eta,

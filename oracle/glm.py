@@ -7,7 +7,7 @@ call sites `src/utilities.jl:32-43,56,80,130,402,749`).  Neither package is vend
 from __future__ import annotations
 
 import numpy as np
-from scipy.special import gammaln, erf, xlogy, betaln
+from scipy.special import gammaln, erf, xlogy, betaln, ndtri
 
 NORMAL, BERNOULLI, POISSON, NEGBIN = "Normal", "Bernoulli", "Poisson", "NegativeBinomial"
 IDENTITY, LOGIT, LOG, PROBIT, CLOGLOG, CAUCHIT, SQRT, INVERSE, INVSQ = (
@@ -129,3 +129,89 @@ def loglikelihood(d: str, y, mu, wts, r: float = 1.0) -> float:
     CV masks."""
     phi = deviance(d, y, mu, wts, r) / y.shape[0]
     return float(np.sum(wts * logpdf(d, y, mu, phi, r)))
+
+
+# ---- GLM.jl `fit(GeneralizedLinearModel, X, y, d, l)` (used by `debias!`, reference src/utilities.jl:1014-1020) --------
+def linkfun(l: str, mu):
+    """GLM.jl `linkfun` (the inverse of `linkinv`)."""
+    mu = np.asarray(mu, dtype=np.float64)
+    if l == IDENTITY:
+        return mu.copy()
+    if l == LOGIT:
+        return np.log(mu / (1.0 - mu))
+    if l == LOG:
+        return np.log(mu)
+    if l == PROBIT:
+        return ndtri(mu)
+    if l == CLOGLOG:
+        return np.log(-np.log1p(-mu))
+    if l == CAUCHIT:
+        return np.tan(np.pi * (mu - 0.5))
+    if l == SQRT:
+        return np.sqrt(mu)
+    if l == INVERSE:
+        return 1.0 / mu
+    if l == INVSQ:
+        return 1.0 / (mu * mu)
+    raise ValueError(l)
+
+
+def mustart(d: str, y):
+    """GLM.jl `mustart(d, y, wt=1)`: the starting mean of IRLS."""
+    y = np.asarray(y, dtype=np.float64)
+    if d == NORMAL:
+        return y.copy()
+    if d == BERNOULLI:
+        return (y + 0.5) / 2.0
+    if d == POISSON:
+        return y + 0.1
+    if d == NEGBIN:
+        return np.where(y == 0, y + 1.0 / 6.0, y)
+    raise ValueError(d)
+
+
+class ConvergenceException(RuntimeError):
+    pass
+
+
+def glm_fit(X, y, d: str, l: str, r: float = 1.0, maxiter=30, minstepfac=0.001, atol=1e-6, rtol=1e-6):
+    """IRLS exactly as GLM.jl 1.x `_fit!` runs it with default arguments (no weights, no offset, no intercept added):
+    start from eta = linkfun(mustart(y)), one weighted least-squares solve on the working response, then Newton steps
+    with step-halving while the deviance increases, stop when devold - dev < max(rtol*devold, atol).
+    Working weights are mueta^2/var (GLM.jl uses the algebraically equal mueta for canonical links)."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+
+    def update(eta):
+        mu = linkinv(l, eta)
+        dmu = mueta(l, eta)
+        wrkres = (y - mu) / dmu
+        wrkwt = dmu * dmu / glmvar(d, mu, r)
+        return wrkres, wrkwt, float(np.sum(devresid(d, y, mu, r)))
+
+    def delbeta(resp, wt):
+        xw = X * wt[:, None]
+        return np.linalg.solve(xw.T @ X, xw.T @ resp)
+
+    eta = linkfun(l, mustart(d, y))
+    wrkres, wrkwt, _ = update(eta)
+    beta0 = delbeta(wrkres + eta, wrkwt)
+    wrkres, wrkwt, devold = update(X @ beta0)
+    for _ in range(maxiter):
+        f = 1.0
+        delta = delbeta(wrkres, wrkwt)
+        wrkres, wrkwt, dev = update(X @ (beta0 + delta))
+        if np.isnan(dev):
+            dev = np.inf
+        while dev > devold + rtol * dev:
+            f /= 2.0
+            if not f > minstepfac:
+                raise RuntimeError(f"step-halving failed at beta0 = {beta0}")
+            wrkres, wrkwt, dev = update(X @ (beta0 + f * delta))
+            if np.isnan(dev):
+                dev = np.inf
+        beta0 = beta0 + f * delta
+        if devold - dev < max(rtol * devold, atol):
+            return beta0
+        devold = dev
+    raise ConvergenceException(f"failure to converge after {maxiter} iterations.")

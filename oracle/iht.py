@@ -82,7 +82,7 @@ class IHTResult:
 class IHTVariable:
     """`IHTVariable` (src/data_structures.jl:4-43), memory_efficient=true branch."""
 
-    def __init__(self, x, z, y, k, d, l, zkeep=None, est_r="None", nb_r=1.0):
+    def __init__(self, x, z, y, k, d, l, zkeep=None, est_r="None", nb_r=1.0, weight=None):
         self.x, self.y = x, np.asarray(y, dtype=np.float64)
         z = np.asarray(z, dtype=np.float64)
         self.z = z.reshape(-1, 1) if z.ndim == 1 else z
@@ -96,6 +96,13 @@ class IHTVariable:
         if self.zkeep.shape[0] != q:
             raise ValueError(f"zkeep must have length {q} but was {self.zkeep.shape[0]}")
         self.zkeepn = int(self.zkeep.sum())
+        # prior weights scale b before the projection (src/data_structures.jl:36,71-73: length p).  The reference's
+        # vectorize!/unvectorize! index weight[p+1:p+q] for the covariates, which is out of bounds under @inbounds
+        # (src/utilities.jl:305-308,346-351); kept covariates overwrite that slot with Inf, so only projected covariates
+        # (zkeep false) would see it.  Oracle and product define the covariate weights as 1.
+        self.weight = None if weight is None or len(weight) == 0 else np.asarray(weight, dtype=np.float64)
+        if self.weight is not None and self.weight.shape[0] != p:
+            raise ValueError(f"weight must have length {p} but was {self.weight.shape[0]}")
         self.b = np.zeros(p); self.b0 = np.zeros(p); self.best_b = np.zeros(p)
         self.xb = np.zeros(n); self.xgk = np.zeros(n)
         self.idx = np.zeros(p, bool); self.idx0 = np.zeros(p, bool)
@@ -133,12 +140,13 @@ class IHTVariable:
         self.df = self.x.xt_v(self.r)
         self.df2 = self.z.T @ self.r
 
-    # -- src/utilities.jl:291-354 + 553-559 + 444-458 (no weights / groups)
+    # -- src/utilities.jl:291-354 + 553-559 + 444-458 (no groups)
     def _project_full(self, b, c):
         """vectorize! -> project_k!(k + zkeepn) -> unvectorize!; returns nothing (in place)."""
-        full = np.concatenate([b, np.where(self.zkeep, np.inf, c)])
+        bw = b if self.weight is None else b * self.weight
+        full = np.concatenate([bw, np.where(self.zkeep, np.inf, c)])
         project_k(full, self.k + self.zkeepn)
-        b[:] = full[: self.p]
+        b[:] = full[: self.p] if self.weight is None else full[: self.p] / self.weight
         cpart = full[self.p:]
         c[~self.zkeep] = cpart[~self.zkeep]
 
@@ -280,6 +288,14 @@ class IHTVariable:
         self.update_xb()
         self.mu = glm.linkinv(self.l, self.xb)   # genotype predictors only
 
+    # -- src/utilities.jl:1014-1020 (memory_efficient=false branch: xk = x[:, idx], ALL n samples, no covariates)
+    def debias(self):
+        idx = np.flatnonzero(self.idx)
+        if idx.size == 0:
+            return
+        xk = self.x.dense()[:, idx]
+        self.b[idx] = glm.glm_fit(xk, self.y, self.d, self.l, self.nb_r)
+
     # -- src/utilities.jl:141-247
     def mle_for_r(self):
         if self.est_r == "MM":
@@ -358,7 +374,8 @@ def iht_one_step(v: IHTVariable, old_logl: float, nstep: int):
     return eta, eta_step, new_logl
 
 
-def fit_iht_loop(v: IHTVariable, tol=1e-4, max_iter=200, min_iter=5, max_step=3, trace: IHTTrace = None):
+def fit_iht_loop(v: IHTVariable, tol=1e-4, max_iter=200, min_iter=5, max_step=3, trace: IHTTrace = None,
+                 debias: bool = False):
     """`fit_iht!` (src/fit.jl:145-207).  Returns (best_logl, mm_iter)."""
     mm_iter = 0
     next_logl = -np.inf
@@ -371,6 +388,8 @@ def fit_iht_loop(v: IHTVariable, tol=1e-4, max_iter=200, min_iter=5, max_step=3,
             break
         best_logl = v.save_prev(next_logl, best_logl)
         eta, eta_step, next_logl = iht_one_step(v, next_logl, max_step)
+        if debias and it >= 5 and np.array_equal(v.idx, v.idx0):      # src/fit.jl:187-188
+            v.debias()
         scaled_norm = v.check_convergence()
         if trace is not None:
             trace.logl.append(next_logl); trace.backtracks.append(eta_step)
@@ -390,7 +409,8 @@ def pve(y, mu):
 
 
 def fit_iht(y, x, z=None, k=10, d=glm.NORMAL, l=None, zkeep=None, est_r="None", nb_r=1.0,
-            tol=1e-4, max_iter=200, min_iter=5, max_step=3, cv_train_idx=None, init_beta=False) -> IHTResult:
+            tol=1e-4, max_iter=200, min_iter=5, max_step=3, cv_train_idx=None, init_beta=False,
+            weight=None, debias=False) -> IHTResult:
     """`fit_iht` (src/fit.jl:60-118) on an oracle SnpLinAlg `x` (see oracle/snp.py)."""
     if z is None:
         z = np.ones(x.shape[0])
@@ -400,11 +420,11 @@ def fit_iht(y, x, z=None, k=10, d=glm.NORMAL, l=None, zkeep=None, est_r="None", 
         raise AssertionError("max_iter, max_step and k must be nonnegative")
     if not tol > np.finfo(np.float64).eps:
         raise AssertionError("Value of global tol must exceed machine precision!")
-    v = IHTVariable(x, z, y, k, d, l, zkeep=zkeep, est_r=est_r, nb_r=nb_r)
+    v = IHTVariable(x, z, y, k, d, l, zkeep=zkeep, est_r=est_r, nb_r=nb_r, weight=weight)
     v.init_iht_indices(np.ones(v.n, bool) if cv_train_idx is None else cv_train_idx, init_beta)
     trace = IHTTrace()
     best_logl, mm_iter = fit_iht_loop(v, tol=tol, max_iter=max_iter, min_iter=min_iter,
-                                      max_step=max_step, trace=trace)
+                                      max_step=max_step, trace=trace, debias=debias)
     res = IHTResult(0.0, best_logl, mm_iter, v.best_b.copy(), v.best_c.copy(), 1, k, [], d,
                     pve(v.y, v.mu), trace, v.nb_r)
     res.v = v

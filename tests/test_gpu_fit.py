@@ -343,3 +343,101 @@ def test_init_beta_matches_oracle():
     np.testing.assert_allclose(mses, rgrid, rtol=RTOL)
     with pytest.raises(m.IHTBError):
         m.fit_iht((y > 0).astype(float), g, z, k=3, d="Bernoulli", l="LogitLink", init_beta=True)
+
+
+WEIGHT_CASES = [
+    ("Normal", "IdentityLink", 1200, 3000, 8, 10, 2, 0.0),
+    ("Bernoulli", "LogitLink", 2000, 3000, 5, 7, 1, 0.0),
+    ("Poisson", "LogLink", 1500, 2500, 6, 8, 1, 0.005),
+]
+
+
+@pytest.mark.parametrize("d,l,n,p,k,kfit,ncov,miss", WEIGHT_CASES)
+def test_prior_weights_match_oracle(d, l, n, p, k, kfit, ncov, miss):
+    """`weight` keyword (src/fit.jl:69, docs 'maf_weights'): the projection ranks |b_j| * w_j (src/utilities.jl:291-354)."""
+    seed = 100 + n + p
+    y, z, _, _, _ = synth.simulate_response(seed, n, p, k, d, n_cov=ncov, missing_rate=miss)
+    bed = synth.packed_columns(seed, n, np.arange(p), miss)
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    o = snp.SnpLinAlgOracle(bed, n)
+    w = m.maf_weights(g, max_weight=5.0)
+    maf = np.minimum(o.mu / 2, 1 - o.mu / 2)
+    np.testing.assert_array_equal(g.maf(), maf)                       # SnpArrays maf(), bit for bit
+    np.testing.assert_array_equal(w, np.clip(1 / (2 * np.sqrt(maf * (1 - maf))), 1.0, 5.0))
+    plain = m.fit_iht(y, g, z, k=kfit, d=d, l=l)
+    for mode in MODES:
+        res = m.fit_iht(y, g, z, k=kfit, d=d, l=l, weight=w, sweep_mode=mode)
+        ref = iht.fit_iht(y, o, z, k=kfit, d=d, l=l, weight=w)
+        assert ref.iter < 200
+        _compare(res, ref)
+    assert not np.array_equal(np.flatnonzero(res.beta), np.flatnonzero(plain.beta))    # the weights do matter here
+    # a fit without weights after a weighted one on the same cached workspace is unweighted again
+    again = m.fit_iht(y, g, z, k=kfit, d=d, l=l)
+    np.testing.assert_array_equal(again.beta, plain.beta)
+    with pytest.raises(m.DimensionMismatch):
+        m.fit_iht(y, g, z, k=kfit, d=d, l=l, weight=w[:-1])
+    with pytest.raises(m.IHTBError):
+        m.fit_iht(y, g, z, k=kfit, d=d, l=l, weight=-w)
+
+
+def test_prior_weights_cv_and_init_beta():
+    n, p, k = 1200, 2000, 5
+    y, z, _, _, _ = synth.simulate_response(77, n, p, k, "Normal", n_cov=1)
+    bed = synth.packed_columns(77, n, np.arange(p))
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    o = snp.SnpLinAlgOracle(bed, n)
+    w = m.maf_weights(g, max_weight=4.0)
+    folds = synth.folds_for(5, n, 3)
+    mses, iters = m.cv_iht(y, g, z, path=[2, 5, 8], q=3, folds=folds, weight=w, return_grid=True)
+    _, rgrid, riters = ocv.cv_iht(y, o, z, path=[2, 5, 8], q=3, folds=folds, weight=w, return_grid=True)
+    assert np.array_equal(iters, riters)
+    np.testing.assert_allclose(mses, rgrid, rtol=RTOL)
+    res = m.fit_iht(y, g, z, k=6, weight=w, init_beta=True)
+    ref = iht.fit_iht(y, o, z, k=6, weight=w, init_beta=True)
+    _compare(res, ref)
+
+
+DEBIAS_CASES = [
+    ("Normal", "IdentityLink", 1200, 3000, 8, 10, 2, 0.0, {}),
+    ("Bernoulli", "LogitLink", 2000, 3000, 5, 7, 1, 0.0, {}),
+    ("Bernoulli", "ProbitLink", 2000, 2500, 5, 6, 1, 0.005, {"max_iter": 25}),
+    ("Poisson", "LogLink", 1500, 2500, 6, 8, 1, 0.0, {"max_iter": 25}),
+    ("NegativeBinomial", "LogLink", 1500, 2500, 6, 8, 0, 0.0, {"max_iter": 12}),
+]
+
+
+@pytest.mark.parametrize("d,l,n,p,k,kfit,ncov,miss,kw", DEBIAS_CASES)
+def test_debias_matches_oracle(d, l, n, p, k, kfit, ncov, miss, kw):
+    """`debias=true` (src/fit.jl:187-188, src/utilities.jl:1014-1020): when the support did not change (iteration >= 5)
+    beta[idx] is replaced by GLM.jl's IRLS fit of y on x[:, idx].  GLM.jl is not in the reference tree: the oracle
+    restates its `_fit!` loop (oracle/glm.py::glm_fit), so this parity is oracle-pinned only."""
+    seed = 100 + n + p
+    y, z, _, _, _ = synth.simulate_response(seed, n, p, k, d, n_cov=ncov, missing_rate=miss)
+    bed = synth.packed_columns(seed, n, np.arange(p), miss)
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    o = snp.SnpLinAlgOracle(bed, n)
+    plain = m.fit_iht(y, g, z, k=kfit, d=d, l=l, nb_r=10.0, **kw)
+    for mode in MODES:
+        res = m.fit_iht(y, g, z, k=kfit, d=d, l=l, nb_r=10.0, debias=True, sweep_mode=mode, **kw)
+        ref = iht.fit_iht(y, o, z, k=kfit, d=d, l=l, nb_r=10.0, debias=True, **kw)
+        _compare(res, ref)
+    assert not np.array_equal(res.beta, plain.beta)
+
+
+def test_debias_cv_and_mv_error():
+    n, p, k = 1500, 2000, 5
+    y, z, _, _, _ = synth.simulate_response(31, n, p, k, "Bernoulli", n_cov=0)
+    bed = synth.packed_columns(31, n, np.arange(p))
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    o = snp.SnpLinAlgOracle(bed, n)
+    folds = synth.folds_for(3, n, 3)
+    # test/cv_iht_test.jl:26-29: cv_iht(..., debias=true, max_iter=10)
+    mses, iters = m.cv_iht(y, g, z, d="Bernoulli", l="LogitLink", path=[3, 6], q=3, folds=folds, debias=True,
+                           max_iter=10, return_grid=True)
+    _, rgrid, riters = ocv.cv_iht(y, o, z, d="Bernoulli", l="LogitLink", path=[3, 6], q=3, folds=folds, debias=True,
+                                  max_iter=10, return_grid=True)
+    assert np.array_equal(iters, riters) and np.all(mses > 0)
+    np.testing.assert_allclose(mses, rgrid, rtol=RTOL)
+    Y = np.vstack([y, 1 - y])
+    with pytest.raises(m.IHTBError, match="debiasing routine for multivariate"):
+        m.fit_iht(Y, g, np.ones((1, n)), k=4, debias=True)

@@ -125,3 +125,49 @@ def test_errors():
         g.decode(0, 101, 0, 1)
     with pytest.raises(m.DimensionMismatch):
         g.x_support(np.array([10]), np.array([1.0]))
+
+
+def test_counts_maf_and_piecewise_ingest(tmp_path):
+    """SnpArrays counts/maf and ingest from several .bed files == ingest of the concatenation."""
+    n, p, miss = 1003, 777, 0.02
+    bed = synth.packed_columns(5, n, np.arange(p), miss)
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    codes = np.stack([(bed >> (2 * s)) & 3 for s in range(4)], axis=2).reshape(p, -1)[:, :n]
+    cnt = np.stack([(codes == c).sum(axis=1) for c in range(4)])
+    np.testing.assert_array_equal(g.counts(), cnt)
+    nobs = n - cnt[1]
+    f = (cnt[2] + 2 * cnt[3]) / (2 * nobs)
+    np.testing.assert_array_equal(g.maf(), np.where(f > 0.5, 1 - f, f))
+    # three "chromosomes" of unequal size, written as real .bed files
+    cuts = [0, 300, 301, p]
+    paths = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        path = tmp_path / f"chr{a}.bed"
+        with open(path, "wb") as fh:
+            fh.write(bytes([0x6C, 0x1B, 0x01])); fh.write(bed[a:b].tobytes())
+        paths.append(str(path))
+    g2 = m.B200SnpLinAlg.from_bed_files(paths, n)
+    assert g2.shape == (n, p)
+    np.testing.assert_array_equal(g2.packed(), g.packed())
+    for a, b in zip(g2.stats(), g.stats()):
+        np.testing.assert_array_equal(a, b)
+    v = np.random.default_rng(0).normal(size=n)
+    np.testing.assert_array_equal(g2.xt_v(v, m.SWEEP_EXACT), g.xt_v(v, m.SWEEP_EXACT))
+    # a handle that is not finalized refuses to compute
+    lib = m.load()
+    import ctypes as C
+    h = C.c_void_p()
+    m._lib.check(lib.ihtb_geno_create_empty(n, p, 1, 1, 1, C.byref(h)))
+    mu = np.empty(p)
+    assert lib.ihtb_geno_stats(h, mu.ctypes.data_as(C.POINTER(C.c_double)), None, None) == m._lib.IHTB_EINVAL
+    bedc = np.ascontiguousarray(bed)
+    m._lib.check(lib.ihtb_geno_load_columns(h, bedc.ctypes.data_as(C.POINTER(C.c_uint8)), bedc.shape[1], 0, p))
+    m._lib.check(lib.ihtb_geno_finalize(h))
+    assert lib.ihtb_geno_finalize(h) == m._lib.IHTB_EINVAL
+    m._lib.check(lib.ihtb_geno_stats(h, mu.ctypes.data_as(C.POINTER(C.c_double)), None, None))
+    np.testing.assert_array_equal(mu, g.stats()[0])
+    lib.ihtb_geno_destroy(h)
+    with pytest.raises(ValueError):
+        bad = tmp_path / "bad.bed"
+        bad.write_bytes(b"\x00\x00\x00" + bed[:2].tobytes())
+        m.B200SnpLinAlg.from_bed_files([str(bad)], n)

@@ -196,3 +196,39 @@ def test_initialize_beta_is_univariate_least_squares(normal_data, normal_oracle)
     res = iht.fit_iht(y, normal_oracle, z, k=7, init_beta=True)
     assert list(np.flatnonzero(res.beta) + 1) == [3137, 4246, 4717, 6290, 7755, 8375, 9415]     # same optimum
     assert abs(res.logl - (-1397.88074)) < 1e-4
+
+
+def test_glm_fit_restates_irls():
+    """oracle/glm.py::glm_fit (GLM.jl `_fit!`, used by debias!): exact OLS for Normal/identity in one Newton step, a
+    stationary point of the likelihood for the other families, `linkfun` inverts `linkinv`."""
+    rng = np.random.default_rng(1)
+    n, k = 800, 4
+    X = rng.standard_normal((n, k)); bt = 0.4 * rng.standard_normal(k)
+    y = X @ bt + rng.standard_normal(n)
+    np.testing.assert_allclose(glm.glm_fit(X, y, glm.NORMAL, glm.IDENTITY), np.linalg.lstsq(X, y, rcond=None)[0], rtol=1e-10)
+    for d, l in [(glm.BERNOULLI, glm.LOGIT), (glm.POISSON, glm.LOG), (glm.BERNOULLI, glm.PROBIT)]:
+        mu = glm.linkinv(l, X @ bt)
+        yy = (rng.random(n) < mu).astype(float) if d == glm.BERNOULLI else rng.poisson(mu).astype(float)
+        b = glm.glm_fit(X, yy, d, l)
+        eta = X @ b
+        score = X.T @ ((yy - glm.linkinv(l, eta)) * glm.mueta(l, eta) / glm.glmvar(d, glm.linkinv(l, eta)))
+        assert np.abs(score).max() < 0.05 * np.sqrt(n)              # stops on the deviance criterion, not the score
+    for l in (glm.IDENTITY, glm.LOGIT, glm.LOG, glm.PROBIT, glm.CLOGLOG, glm.CAUCHIT, glm.SQRT, glm.INVERSE, glm.INVSQ):
+        mu = np.array([0.2, 0.5, 0.9])
+        np.testing.assert_allclose(glm.linkinv(l, glm.linkfun(l, mu)), mu, rtol=1e-12)
+
+
+def test_debias_and_weights_on_bundled_data(normal_data, normal_oracle):
+    """Debiasing (src/fit.jl:187-188) refits the support without shrinkage; weights rescale the projection only."""
+    y = normal_data["y"]
+    plain = iht.fit_iht(y, normal_oracle, None, k=9)
+    deb = iht.fit_iht(y, normal_oracle, None, k=9, debias=True)
+    assert np.array_equal(np.flatnonzero(deb.beta), np.flatnonzero(plain.beta))
+    assert deb.iter <= plain.iter
+    ones = iht.fit_iht(y, normal_oracle, None, k=9, weight=np.ones(normal_oracle.shape[1]))
+    np.testing.assert_array_equal(ones.beta, plain.beta)
+    w = np.ones(normal_oracle.shape[1]); w[:5000] = 100.0           # favour the first half of the genome
+    heavy = iht.fit_iht(y, normal_oracle, None, k=9, weight=w)
+    assert (np.flatnonzero(heavy.beta) < 5000).sum() > (np.flatnonzero(plain.beta) < 5000).sum()
+    with pytest.raises(ValueError):
+        iht.fit_iht(y, normal_oracle, None, k=9, weight=np.ones(3))
