@@ -144,6 +144,12 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
  * weight[p_global] > 0 (the whole vector on every rank of a sharded fit), NULL clears.  Call before ihtb_fit_init.
  * Covariates keep weight 1 (the reference indexes weight[p+1..p+q] out of bounds there). */
 int32_t ihtb_fit_set_weights(ihtb_fit* f, const double* weight);
+/* doubly sparse projection (keywords J, k, group: src/fit.jl:64-68; project_group_sparse!, src/utilities.jl:613-679):
+ * group[p] holds 1-based group ids, at most J groups stay active with at most k predictors each; ks = NULL uses
+ * cfg.k for every group, otherwise ks[n_groups] is the per-group maximum (the reference's vector-valued k; cfg.k is
+ * then ignored, check_group src/utilities.jl:902-915 applies).  group = NULL clears.  Call before ihtb_fit_init.
+ * Group fits always use the exact FP64 sweep.  Not available for sharded fits (IHTB_EUNSUPPORTED). */
+int32_t ihtb_fit_set_groups(ihtb_fit* f, const int32_t* group, int32_t J, const int64_t* ks, int64_t n_groups);
 int32_t ihtb_fit_set_k(ihtb_fit* f, int64_t k);                       /* v.k = sparsity (src/cross_validation.jl:110) */
 int32_t ihtb_fit_init(ihtb_fit* f, const uint8_t* train_mask);         /* init_iht_indices!; NULL = all samples */
 /* init_iht_indices!(v, init_beta = true, ...): beta starts from per-SNP univariate regressions (initialize_beta!,

@@ -90,6 +90,7 @@ SIGNATURES = {
     "ihtb_fit_create": [_p, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), _pp],
     "ihtb_fit_create_sharded": [_p, _p, C.c_int64, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), _pp],
     "ihtb_fit_set_weights": [_p, _f64],
+    "ihtb_fit_set_groups": [_p, C.POINTER(C.c_int32), C.c_int32, _i64, C.c_int64],
     "ihtb_fit_set_k": [_p, C.c_int64],
     "ihtb_fit_init": [_p, _u8],
     "ihtb_fit_init_beta": [_p, _u8],

@@ -192,7 +192,7 @@ class IHTVariable:
 
     def __init__(self, x: B200SnpLinAlg, z, y, k, d=NORMAL, l="IdentityLink", zkeep=None, nb_r=1.0, tol=1e-4,
                  max_iter=200, min_iter=5, max_step=3, sweep_mode=_lib.SWEEP_FAST, comm=None, p_global=None,
-                 est_r="None", weight=None, debias=False):
+                 est_r="None", weight=None, debias=False, J=1, group=None):
         y = f64(y)
         z = np.asarray(z, dtype=np.float64)
         if z.ndim == 1:
@@ -215,6 +215,11 @@ class IHTVariable:
         if est_r != "None" and d != NEGBIN:
             raise _lib.IHTBError(_lib.IHTB_EINVAL, "Only negative binomial regression currently supports nuisance "
                                                    "parameter estimation")
+        # a vector k = per-group sparsity `ks`, and then v.k = 0 (src/data_structures.jl:75-81)
+        ks = None
+        if not np.isscalar(k):
+            ks = np.ascontiguousarray(k, dtype=np.int64)
+            k = 0
         self.cfg = Cfg(DIST_ID[d], LINK_ID[l], int(k), float(nb_r), float(tol), int(max_iter), int(min_iter),
                        int(max_step), int(sweep_mode), EST_R_ID[est_r], 1 if debias else 0)
         zf = np.asfortranarray(z)
@@ -223,6 +228,22 @@ class IHTVariable:
                                              ptr(y, C.c_double), zf.ctypes.data_as(C.POINTER(C.c_double)), q,
                                              ptr(zk, C.c_uint8) if zk is not None else None, C.byref(self.cfg),
                                              C.byref(self._h)))
+        if group is not None and len(group) > 0:
+            grp = np.ascontiguousarray(group, dtype=np.int32)
+            try:
+                if grp.shape[0] != self.p_global:      # src/data_structures.jl:67-69
+                    raise _lib.DimensionMismatch(_lib.IHTB_EDIM,
+                                                 f"group must have length {self.p_global} but was {grp.shape[0]}")
+                check(load().ihtb_fit_set_groups(self._h, grp.ctypes.data_as(C.POINTER(C.c_int32)), int(J),
+                                                 ptr(ks, C.c_int64) if ks is not None else None,
+                                                 0 if ks is None else ks.shape[0]))
+            except Exception:
+                self.close()
+                raise
+        elif ks is not None:
+            self.close()
+            raise AssertionError("Doubly sparse projection specified (since k is a vector) but there are no group "
+                                 "information.")
         if weight is not None and len(weight) > 0:
             w = f64(weight)
             if w.shape[0] != self.p_global:       # src/data_structures.jl:71-73
@@ -397,17 +418,20 @@ def _check_args(k, max_iter, max_step, tol):
         raise AssertionError("Value of max_step must be nonnegative!\n")
     if not tol > np.finfo(np.float64).eps:
         raise AssertionError("Value of global tol must exceed machine precision!\n")
-    if k < 0:
+    if np.isscalar(k) and k < 0:
         raise AssertionError("Value of k (max predictors per group) must be nonnegative!\n")
 
 
 def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est_r="None", nb_r=1.0, tol=1e-4,
             max_iter=200, min_iter=5, max_step=3, sweep_mode=_lib.SWEEP_FAST, verbose=False, io=None,
-            comm=None, p_global=None, init_beta=False, weight=None, debias=False, use_maf=False) -> IHTResult:
+            comm=None, p_global=None, init_beta=False, weight=None, debias=False, use_maf=False, J=1,
+            group=None) -> IHTResult:
     """`fit_iht(y, x, z; k, d, l, weight, zkeep, est_r, debias, tol, max_iter, min_iter, max_step, init_beta)`
     (src/fit.jl:60-118).  `use_maf` is accepted and, like in the reference, only reported (src/fit.jl:72,108):
     pass `weight=maf_weights(x)` to weight the projection by allele frequency."""
     _check_args(k, max_iter, max_step, tol)
+    if J < 0:
+        raise AssertionError("Value of J (max number of groups) must be nonnegative!\n")
     if is_multivariate(y):      # d = MvNormal: Y is r x n, Z is q x n (src/fit.jl:66,125)
         if debias:
             raise _lib.IHTBError(_lib.IHTB_EUNSUPPORTED,
@@ -420,7 +444,7 @@ def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est
         z = np.ones(x.n)
     l = l or "IdentityLink"
     v = IHTVariable(x, z, y, k, d, l, zkeep, nb_r, tol, max_iter, min_iter, max_step, sweep_mode, comm, p_global,
-                    est_r, weight, debias)
+                    est_r, weight, debias, J, group)
     try:
         v.init_iht_indices(None, init_beta)
         res, trace = v.fit()
@@ -432,7 +456,8 @@ def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est
         out = io or sys.stdout
         for i, t in enumerate(trace):
             print(f"Iteration {i + 1}: loglikelihood = {t[0]}, backtracks = {t[1]}, tol = {t[2]}", file=out)
-    return IHTResult(res.time, res.logl, int(res.iter), beta, c, 1, k, [], d, res.sigma_g, trace, int(res.n_sweeps),
+    return IHTResult(res.time, res.logl, int(res.iter), beta, c, J, k, [] if group is None else list(group), d,
+                     res.sigma_g, trace, int(res.n_sweeps),
                      int(res.n_backtracks), res.sweep_seconds, int(res.n_launches))
 
 
@@ -465,7 +490,7 @@ def meanloss(fitloss, q: int, folds):
 
 def cv_iht(y, x: B200SnpLinAlg, z=None, d=NORMAL, l=None, path=range(1, 21), q=5, folds=None, zkeep=None,
            nb_r=1.0, max_iter=100, min_iter=5, sweep_mode=_lib.SWEEP_FAST, combos=None, return_grid=False,
-           init_beta=False, weight=None, debias=False):
+           init_beta=False, weight=None, debias=False, J=1, group=None):
     """`cv_iht` (src/cross_validation.jl:60-131).  `folds` in 1..q (drawn with numpy's default_rng if omitted).
     `combos`: optional subset of grid positions to run (used by the multi-GPU farm, parallel.py)."""
     path = [int(k) for k in path]
@@ -485,7 +510,7 @@ def cv_iht(y, x: B200SnpLinAlg, z=None, d=NORMAL, l=None, path=range(1, 21), q=5
         v = mIHTVariable(x, z, y, max(path), zkeep, 1e-4, max_iter, min_iter, 3, sweep_mode)
     else:
         v = IHTVariable(x, z, y, max(path), d, l, zkeep, nb_r, 1e-4, max_iter, min_iter, 3, sweep_mode,
-                        weight=weight, debias=debias)
+                        weight=weight, debias=debias, J=J, group=group)
     try:
         for i in todo:
             fold, k = grid[i]

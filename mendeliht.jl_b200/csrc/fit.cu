@@ -16,6 +16,7 @@
 #include "topk.cuh"
 #include "comm.cuh"
 #include "debias.cuh"
+#include "groups.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -302,6 +303,11 @@ struct ihtb_fit {
     // rerun = true: called a second time for the same sweep (init_beta changes the support after the sweep); the
     // score sums are no longer on the device, so the host copy of the error bound is used and no scalars are read.
     void select_rescore(bool rerun) {
+        if (grouped() && !init_plain) {
+            select_groups();
+            if (!rerun) finish_sweep_scalars(kExactBound);
+            return;
+        }
         df_exact.clear(); cand_cache.clear();
         df_sparse = false;
         const double coef = cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound;
@@ -406,6 +412,11 @@ struct ihtb_fit {
             }
         }
         if (rerun) return;
+        finish_sweep_scalars(coef);
+    }
+
+    // host copies of the score sums that travelled back with the candidates
+    void finish_sweep_scalars(double coef) {
         float ms = 0.f;
         IHTB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
         sweep_ms_total += ms;
@@ -477,6 +488,7 @@ struct ihtb_fit {
     // ---- _iht_gradstep! : b = P_k(b0 + eta*df), c = c0 + eta*df2 (src/utilities.jl:252-280) --------
     // Ties at the k-th magnitude: lowest position in [b; c] wins (the reference prunes at random, :444-458).
     void gradstep(double eta) {
+        if (grouped()) { gradstep_group(eta); return; }
         std::vector<int64_t> cand;
         cand = df_sparse ? dfs_idx : cand_cache;     // chosen once per sweep, exact values already in df_exact
         cand.insert(cand.end(), idx0.begin(), idx0.end());
@@ -516,6 +528,135 @@ struct ihtb_fit {
         std::sort(keep.begin(), keep.end());
         for (auto& kv : keep) { idx.push_back(kv.first); b.push_back(kv.second); }
         for (int64_t l = 0; l < q; ++l) idc[l] = c[l] != 0.0;
+    }
+
+    // ---- doubly sparse projection (keywords J / k / group; project_group_sparse!, src/utilities.jl:613-679) --------
+    std::unique_ptr<GroupCtx> grpctx;          // null: plain top-k projection
+    bool init_plain = false;                    // init_iht_indices! with a scalar k projects WITHOUT groups (:417-425)
+    bool grouped() const { return (bool)grpctx; }
+    void set_groups(const int32_t* group1, int J, const int64_t* ks, int64_t n_groups) {
+        if (!group1) { grpctx.reset(); return; }
+        IHTB_CHECK(!comm, IHTB_EUNSUPPORTED, "group projection is not available for SNP-sharded fits yet");
+        IHTB_CHECK(J >= 0, IHTB_EINVAL, "Value of J (max number of groups) must be nonnegative!");
+        std::unique_ptr<GroupCtx> gc(new GroupCtx());
+        gc->build(p, group1, J, ks, n_groups, cfg.k);
+        grpctx = std::move(gc);
+        cfg.sweep_mode = IHTB_SWEEP_EXACT;      // group candidates are ranked on the exact gradient (groups.cu)
+    }
+
+    // once per sweep: exact df of the support, per-group candidate lists, and the groups that can matter
+    void select_groups() {
+        GroupCtx& gc = *grpctx;
+        df_exact.clear(); cand_cache.clear();
+        df_sparse = false; denom_ready = false;
+        group_topk(gc, d_dfa.p, cfg.k, s);
+        const size_t nsupp = idx.size();
+        if (nsupp) {
+            upload(d_cols.p, idx.data(), nsupp);
+            take_values(d_dfa.p, d_cols.p, (int64_t)nsupp, d_gout.p, s);
+            IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_gout.p, nsupp * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
+        IHTB_CUDA(cudaMemcpyAsync(gc.h_gT.p, gc.d_gT.p, (size_t)gc.G * sizeof(double), cudaMemcpyDeviceToHost, s));
+        sync();
+        for (size_t t = 0; t < nsupp; ++t) df_exact[idx[t]] = h_gout.p[t];
+        std::vector<char> has((size_t)gc.G, 0);
+        for (int64_t j : idx) has[(size_t)gc.grp[(size_t)j]] = 1;
+        std::vector<int32_t> chosen;
+        std::vector<std::pair<double, int>> others;
+        for (int g = 0; g < gc.G; ++g) {
+            if (has[(size_t)g]) chosen.push_back(g);
+            else others.push_back({gc.h_gT.p[g], g});
+        }
+        if (gc.J > 0 && !others.empty()) {
+            const size_t need = std::min<size_t>((size_t)gc.J, others.size());
+            std::nth_element(others.begin(), others.begin() + (need - 1), others.end(),
+                             [](const std::pair<double, int>& x, const std::pair<double, int>& y) { return x.first > y.first; });
+            const double thr = others[need - 1].first;
+            for (const auto& o : others)
+                if (o.first >= thr) chosen.push_back(o.second);
+        }
+        IHTB_CHECK(chosen.size() <= 65536, IHTB_ENUMERIC, "degenerate group projection: too many groups tie at the J-th norm");
+        std::sort(chosen.begin(), chosen.end());
+        const int nc = (int)chosen.size();
+        if (nc) {
+            gc.ensure_chosen(nc);
+            IHTB_CUDA(cudaMemcpyAsync(gc.d_chosen.p, chosen.data(), (size_t)nc * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+            group_take(gc, nc, s);
+            IHTB_CUDA(cudaMemcpyAsync(gc.h_oidx.p, gc.d_oidx.p, (size_t)nc * gc.lcap * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            IHTB_CUDA(cudaMemcpyAsync(gc.h_oval.p, gc.d_oval.p, (size_t)nc * gc.lcap * sizeof(double), cudaMemcpyDeviceToHost, s));
+            sync();
+            for (int64_t t = 0; t < (int64_t)nc * gc.lcap; ++t) {
+                const int64_t j = gc.h_oidx.p[t];
+                if (j < 0) continue;
+                df_exact[j] = gc.h_oval.p[t];
+                cand_cache.push_back(j);
+            }
+        }
+        std::sort(cand_cache.begin(), cand_cache.end());
+        cand_cache.erase(std::unique(cand_cache.begin(), cand_cache.end()), cand_cache.end());
+        n_cand_iter += (int64_t)cand_cache.size();
+    }
+
+    // project_group_sparse! restricted to the candidate entries (position j, value v); returns the survivors
+    struct GItem { double a; int64_t j; double v; int g; };
+    std::vector<std::pair<int64_t, double>> project_groups(std::vector<GItem>& items) const {
+        const GroupCtx& gc = *grpctx;
+        std::sort(items.begin(), items.end(), [](const GItem& x, const GItem& y) { return x.a > y.a || (x.a == y.a && x.j < y.j); });
+        std::unordered_map<int, std::pair<int64_t, double>> acc;       // group -> (count, norm of its k_g largest)
+        for (const GItem& it : items) {
+            auto& e = acc[it.g];
+            if (e.first < gc.k_of(it.g, cfg.k)) { e.second += it.v * it.v; ++e.first; }
+        }
+        std::vector<std::pair<double, int>> order;
+        for (const auto& kv : acc) order.push_back({kv.second.second, kv.first});
+        std::sort(order.begin(), order.end(), [](const std::pair<double, int>& x, const std::pair<double, int>& y) {
+            return x.first > y.first || (x.first == y.first && x.second < y.second);
+        });
+        std::unordered_map<int, int> rank;
+        for (size_t i = 0; i < order.size(); ++i) rank[order[i].second] = (int)i + 1;
+        std::unordered_map<int, int64_t> cnt;
+        std::vector<std::pair<int64_t, double>> keep;
+        for (const GItem& it : items) {
+            int64_t& c_ = cnt[it.g];
+            if (rank[it.g] > gc.J || c_ >= gc.k_of(it.g, cfg.k)) continue;
+            ++c_;
+            if (it.v != 0.0) keep.push_back({it.j, it.v});
+        }
+        std::sort(keep.begin(), keep.end());
+        return keep;
+    }
+
+    void gradstep_group(double eta) {
+        const GroupCtx& gc = *grpctx;
+        std::vector<int64_t> cand = df_sparse ? dfs_idx : cand_cache;
+        cand.insert(cand.end(), idx0.begin(), idx0.end());
+        std::sort(cand.begin(), cand.end());
+        cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+        std::vector<GItem> items;
+        items.reserve(cand.size());
+        for (int64_t j : cand) {
+            const double v = b_lookup(idx0, b0, j) + eta * df_at(j);
+            items.push_back({std::fabs(v), j, v, gc.grp[(size_t)j]});
+        }
+        for (int64_t l = 0; l < q; ++l) c[l] = c0[l] + eta * df2[l];      // covariates are not projected (:267-269)
+        auto keep = project_groups(items);
+        for (int64_t l = 0; l < q; ++l) idc[l] = c[l] != 0.0;
+        if (!gc.ks_vector) {                    // _choose! (src/utilities.jl:444-458) with J groups
+            int64_t nonzero = (int64_t)keep.size() - zkeepn;
+            for (int64_t l = 0; l < q; ++l) nonzero += idc[l] ? 1 : 0;
+            const int64_t limit = (int64_t)(gc.J == 0 ? 1 : gc.J) * (cfg.k + zkeepn);
+            if (nonzero > limit) {              // drop the smallest magnitudes, highest index first
+                std::vector<std::pair<int64_t, double>> byabs = keep;
+                std::sort(byabs.begin(), byabs.end(), [](const std::pair<int64_t, double>& x, const std::pair<int64_t, double>& y) {
+                    return std::fabs(x.second) < std::fabs(y.second) || (std::fabs(x.second) == std::fabs(y.second) && x.first > y.first);
+                });
+                const size_t excess = std::min<size_t>((size_t)(nonzero - limit), byabs.size());
+                for (size_t t = 0; t < excess; ++t)
+                    keep.erase(std::find(keep.begin(), keep.end(), byabs[t]));
+            }
+        }
+        idx.clear(); b.clear();
+        for (auto& kv : keep) { idx.push_back(kv.first); b.push_back(kv.second); }
     }
 
     // ---- debias! (src/utilities.jl:1014-1020): b[idx] = GLM refit of y on x[:, idx]; xb / mu / df stay as they are ----
@@ -682,7 +823,22 @@ struct ihtb_fit {
             if (std::fabs(g1 - ybar) < 1e-10) break;
         }
         glm_update(1);        // zc = Z c, mu (the reference does not clamp here; xb = 0 and |c1| is small)
+        init_plain = grouped() && !grpctx->ks_vector && !init_beta;
         score_and_sweep();
+        init_plain = false;
+        if (grouped() && grpctx->ks_vector && !init_beta) {
+            // :426-430: df is projected by groups, the support is read off v.b (all zero): the fit starts from an
+            // EMPTY support with the group-projected gradient, every covariate active
+            std::vector<GItem> items;
+            for (int64_t j : cand_cache) { double v = df_exact.at(j); items.push_back({std::fabs(v), j, v, grpctx->grp[(size_t)j]}); }
+            auto keep = project_groups(items);
+            for (auto& kv : keep) { dfs_idx.push_back(kv.first); dfs_val.push_back(kv.second); }
+            df_sparse = true;
+            idx.clear(); b.clear();
+            for (int64_t l = 0; l < q; ++l) idc[l] = 1;
+            inited = true;
+            return;
+        }
         if (init_beta) {
             do_init_beta();
             inited = true;
@@ -936,6 +1092,8 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
         f->tk = TopkCtx{p, f->d_keyL.p, f->d_keyU.p, f->d_hist.p, reinterpret_cast<TopkState*>(f->d_sel.p),
                         f->d_sel.p + 2, f->cap};
         f->wt.clear();
+        f->grpctx.reset();
+        f->init_plain = false;
         f->sync();
         *out = f.release();
     });
@@ -949,12 +1107,22 @@ int32_t ihtb_fit_set_weights(ihtb_fit* f, const double* weight) {
     });
 }
 
+int32_t ihtb_fit_set_groups(ihtb_fit* f, const int32_t* group, int32_t J, const int64_t* ks, int64_t n_groups) {
+    return guard([&] {
+        IHTB_CHECK(f, IHTB_EINVAL, "NULL fit handle");
+        IHTB_CUDA(cudaSetDevice(f->g->device));
+        f->set_groups(group, J, ks, n_groups);
+    });
+}
+
 int32_t ihtb_fit_set_k(ihtb_fit* f, int64_t k) {
     return guard([&] {
         IHTB_CHECK(f, IHTB_EINVAL, "NULL fit handle");
         IHTB_CHECK(k >= 0 && k <= f->p, IHTB_EINVAL, "Sparsity level cannot be larger than total number of variables");
         IHTB_CHECK(4 * k + 1024 <= f->cap, IHTB_EINVAL,
                    "k exceeds the candidate capacity this fit handle was created with (create it with the largest k)");
+        IHTB_CHECK(!f->grouped() || f->grpctx->ks_vector || k <= f->grpctx->kcap, IHTB_EINVAL,
+                   "k exceeds the group candidate capacity (create the fit with the largest k of the path)");
         f->cfg.k = k;
     });
 }

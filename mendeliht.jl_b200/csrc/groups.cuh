@@ -1,0 +1,36 @@
+#pragma once
+#include "common.cuh"
+
+namespace ihtb {
+
+// Group structure of a doubly sparse fit (keywords J / k / group, reference src/fit.jl:64-68,
+// project_group_sparse! src/utilities.jl:613-679).
+struct GroupCtx {
+    int64_t p = 0;
+    int G = 0;                      // number of groups (ids 0..G-1 on the host, 1-based at the ABI)
+    int J = 1;
+    bool ks_vector = false;         // k given per group (the reference's `ks`)
+    int64_t kcap = 0;               // scalar k the list capacities were sized for
+    std::vector<int32_t> grp;       // [p] group of every SNP
+    std::vector<int64_t> ks;        // [G] (ks_vector only)
+    std::vector<int64_t> gsize, goff;   // members per group; offset of each group's candidate list (goff[G] = total)
+    int64_t lcap = 0;               // longest candidate list
+    DBuf<int64_t> d_order, d_gptr, d_goff, d_ks, d_gidx, d_oidx;
+    DBuf<double> d_gval, d_gT, d_oval;
+    DBuf<int32_t> d_chosen;
+    HBuf<double> h_gT, h_oval;
+    HBuf<int64_t> h_oidx;
+    int chosen_cap = 0;
+
+    int64_t k_of(int g, int64_t kscalar) const { return ks_vector ? ks[(size_t)g] : kscalar; }
+    void build(int64_t p_, const int32_t* group1, int J_, const int64_t* ks_, int64_t n_groups, int64_t kscalar);
+    void ensure_chosen(int n);
+};
+
+// per group: the min(2 k_g, |g|) largest |df| in (|df| desc, index asc) order -> d_gidx / d_gval (-1 padded), and
+// T_g = sum of the k_g largest df^2 -> d_gT
+void group_topk(GroupCtx& c, const double* d_dfa, int64_t kscalar, cudaStream_t s);
+// copy the candidate lists of `n` chosen groups (ids in c.d_chosen) into c.d_oidx / c.d_oval, lcap slots per group
+void group_take(GroupCtx& c, int n, cudaStream_t s);
+
+}  // namespace ihtb

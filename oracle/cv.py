@@ -33,7 +33,7 @@ def meanloss(fitloss, q: int, folds):
 
 def cv_iht(y, x, z=None, d=glm.NORMAL, l=glm.IDENTITY, path=range(1, 21), q=5, folds=None,
            zkeep=None, max_iter=100, min_iter=5, nb_r=1.0, return_grid=False, init_beta=False, weight=None,
-           debias=False):
+           debias=False, J=1, group=None):
     """`cv_iht` (:60-131), univariate or multivariate by the shape of y."""
     y = np.asarray(y, dtype=np.float64)
     multivariate = y.ndim == 2 and y.shape[0] > 1 and y.shape[1] > 1
@@ -60,7 +60,7 @@ def cv_iht(y, x, z=None, d=glm.NORMAL, l=glm.IDENTITY, path=range(1, 21), q=5, f
             v.update_xb(); v.update_mu()
             mses[i] = float(np.sum((v.Y - v.mu) ** 2 * v.cv_wts[None, :]))
         else:
-            v = IHTVariable(x, z, y, k, d, l, zkeep=zkeep, nb_r=nb_r, weight=weight)
+            v = IHTVariable(x, z, y, k, d, l, zkeep=zkeep, nb_r=nb_r, weight=weight, J=J, group=group)
             v.init_iht_indices(train, init_beta)
             _, iters[i] = fit_iht_loop(v, max_iter=max_iter, min_iter=min_iter, debias=debias)
             v.cv_wts[train] = 0.0; v.cv_wts[test] = 1.0

@@ -43,6 +43,47 @@ def project_k(x: np.ndarray, k: int) -> None:
     x[ax < a] = 0.0
 
 
+def project_group_sparse(y: np.ndarray, group: np.ndarray, J: int, k) -> None:
+    """`project_group_sparse!(y, group, J, k)` (src/utilities.jl:613-679), k an int or one int per group (1-based
+    group ids).  Both sorts are stable, so equal magnitudes keep index order and equal group norms keep group order."""
+    group = np.asarray(group, dtype=np.int64)
+    groups = int(group.max())
+    kk = np.full(groups, int(k), dtype=np.int64) if np.isscalar(k) else np.asarray(k, dtype=np.int64)
+    perm = np.argsort(-np.abs(y), kind="stable")
+    group_count = np.zeros(groups, dtype=np.int64)
+    group_norm = np.zeros(groups)
+    for j in perm:
+        g = group[j] - 1
+        if group_count[g] < kk[g]:
+            group_norm[g] += y[j] ** 2
+            group_count[g] += 1
+    order = np.argsort(-group_norm, kind="stable")
+    group_rank = np.empty(groups, dtype=np.int64)
+    group_rank[order] = np.arange(1, groups + 1)
+    group_count[:] = 1
+    for j in perm:
+        g = group[j] - 1
+        if group_rank[g] > J or group_count[g] > kk[g]:
+            y[j] = 0.0
+        else:
+            group_count[g] += 1
+
+
+def check_group(k, group) -> None:
+    """`check_group` (src/utilities.jl:902-915)."""
+    if not np.isscalar(k):
+        if group is None or len(group) <= 1:
+            raise AssertionError("Doubly sparse projection specified (since k is a vector) but there are no group information.")
+        group = np.asarray(group)
+        for i, ki in enumerate(k, start=1):
+            members = int((group == i).sum())
+            if not members > ki:
+                raise ValueError(f"Maximum predictors for group {i} was {ki} but there are only {members} predictors is "
+                                 "this group. Please choose a smaller number.")
+    elif k < 0:
+        raise AssertionError("Value of k (max predictors per group) must be nonnegative!")
+
+
 def prune_ties(vals: np.ndarray, nz_mask: np.ndarray, excess: int) -> None:
     """Deterministic replacement for `_choose!`: drop `excess` smallest-magnitude support entries,
     highest index first (only ties at the threshold can be in excess)."""
@@ -82,7 +123,7 @@ class IHTResult:
 class IHTVariable:
     """`IHTVariable` (src/data_structures.jl:4-43), memory_efficient=true branch."""
 
-    def __init__(self, x, z, y, k, d, l, zkeep=None, est_r="None", nb_r=1.0, weight=None):
+    def __init__(self, x, z, y, k, d, l, zkeep=None, est_r="None", nb_r=1.0, weight=None, J=1, group=None):
         self.x, self.y = x, np.asarray(y, dtype=np.float64)
         z = np.asarray(z, dtype=np.float64)
         self.z = z.reshape(-1, 1) if z.ndim == 1 else z
@@ -91,7 +132,16 @@ class IHTVariable:
         if not (self.y.shape[0] == n == self.z.shape[0]):
             raise ValueError(f"row dimension of y, x, and z ({self.y.shape[0]}, {n}, {self.z.shape[0]}) are not equal")
         self.n, self.p, self.q = n, p, q
-        self.k, self.d, self.l, self.est_r, self.nb_r = int(k), d, l, est_r, float(nb_r)
+        # src/data_structures.jl:75-81: a vector k means per-group sparsity (`ks`), and then v.k = 0
+        if np.isscalar(k):
+            self.k, self.ks = int(k), None
+        else:
+            self.k, self.ks = 0, np.asarray(k, dtype=np.int64)
+        self.J = int(J)
+        self.group = None if group is None or len(group) == 0 else np.asarray(group, dtype=np.int64)
+        if self.group is not None and self.group.shape[0] != p:
+            raise ValueError(f"group must have length {p} but was {self.group.shape[0]}")
+        self.d, self.l, self.est_r, self.nb_r = d, l, est_r, float(nb_r)
         self.zkeep = np.ones(q, dtype=bool) if zkeep is None else np.asarray(zkeep, dtype=bool)
         if self.zkeep.shape[0] != q:
             raise ValueError(f"zkeep must have length {q} but was {self.zkeep.shape[0]}")
@@ -152,9 +202,10 @@ class IHTVariable:
 
     def _choose(self):
         sparsity = self.k + self.zkeepn
+        groups = 1 if self.J == 0 else self.J
         nonzero = int(self.idx.sum()) + int(self.idc.sum()) - self.zkeepn
-        if nonzero > sparsity:
-            prune_ties(self.b, self.idx, nonzero - sparsity)
+        if nonzero > groups * sparsity:
+            prune_ties(self.b, self.idx, nonzero - groups * sparsity)
 
     # -- src/utilities.jl:366-438
     # -- src/utilities.jl:776-842 (`initialize_beta!` + `linreg!`)
@@ -223,11 +274,18 @@ class IHTVariable:
             self.idx = self.b != 0
             self.idc = self.c != 0
             return
+        if self.ks is not None:
+            # :426-430: per-group sparsity projects df by groups, then reads the support off v.b -- which is all zero
+            # at this point, so the fit starts from an EMPTY support with the group-projected gradient.
+            project_group_sparse(self.df, self.group, self.J, self.ks)
+            self.idx = self.b != 0
+            self.idc = np.ones(self.q, dtype=bool)
+            return
         # first k non-zero entries chosen from largest gradient; df itself is projected (:417-425)
         self._project_full(self.df, self.df2)
         self.idx = self.df != 0
         self.idc = self.zkeep.copy()
-        sparsity = self.k + self.zkeepn
+        sparsity = (self.k + self.zkeepn) * (1 if self.J == 0 else self.J)
         nonzero = int(self.idx.sum()) + int(self.idc.sum()) - self.zkeepn
         if nonzero > sparsity:
             # `_choose!` zeroes v.b (already 0) and clears idx; df keeps its value (:450-456)
@@ -254,10 +312,14 @@ class IHTVariable:
     def iht_gradstep(self, eta):
         self.b += eta * self.df
         self.c += eta * self.df2
-        self._project_full(self.b, self.c)
+        if self.group is None:
+            self._project_full(self.b, self.c)
+        else:      # :267-269: groups project b only; no covariate selection, no weights
+            project_group_sparse(self.b, self.group, self.J, self.k if self.ks is None else self.ks)
         self.idx = self.b != 0
         self.idc = self.c != 0
-        self._choose()
+        if self.ks is None:
+            self._choose()
 
     # -- src/utilities.jl:702-712
     def save_prev(self, cur_logl, best_logl):
@@ -410,22 +472,23 @@ def pve(y, mu):
 
 def fit_iht(y, x, z=None, k=10, d=glm.NORMAL, l=None, zkeep=None, est_r="None", nb_r=1.0,
             tol=1e-4, max_iter=200, min_iter=5, max_step=3, cv_train_idx=None, init_beta=False,
-            weight=None, debias=False) -> IHTResult:
+            weight=None, debias=False, J=1, group=None) -> IHTResult:
     """`fit_iht` (src/fit.jl:60-118) on an oracle SnpLinAlg `x` (see oracle/snp.py)."""
     if z is None:
         z = np.ones(x.shape[0])
     if l is None:
         l = glm.IDENTITY
-    if max_iter < 0 or max_step < 0 or k < 0:
-        raise AssertionError("max_iter, max_step and k must be nonnegative")
+    if max_iter < 0 or max_step < 0 or J < 0:
+        raise AssertionError("J, max_iter and max_step must be nonnegative")
+    check_group(k, group)
     if not tol > np.finfo(np.float64).eps:
         raise AssertionError("Value of global tol must exceed machine precision!")
-    v = IHTVariable(x, z, y, k, d, l, zkeep=zkeep, est_r=est_r, nb_r=nb_r, weight=weight)
+    v = IHTVariable(x, z, y, k, d, l, zkeep=zkeep, est_r=est_r, nb_r=nb_r, weight=weight, J=J, group=group)
     v.init_iht_indices(np.ones(v.n, bool) if cv_train_idx is None else cv_train_idx, init_beta)
     trace = IHTTrace()
     best_logl, mm_iter = fit_iht_loop(v, tol=tol, max_iter=max_iter, min_iter=min_iter,
                                       max_step=max_step, trace=trace, debias=debias)
-    res = IHTResult(0.0, best_logl, mm_iter, v.best_b.copy(), v.best_c.copy(), 1, k, [], d,
+    res = IHTResult(0.0, best_logl, mm_iter, v.best_b.copy(), v.best_c.copy(), J, k, [] if group is None else list(group), d,
                     pve(v.y, v.mu), trace, v.nb_r)
     res.v = v
     return res

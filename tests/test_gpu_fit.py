@@ -441,3 +441,59 @@ def test_debias_cv_and_mv_error():
     Y = np.vstack([y, 1 - y])
     with pytest.raises(m.IHTBError, match="debiasing routine for multivariate"):
         m.fit_iht(Y, g, np.ones((1, n)), k=4, debias=True)
+
+
+GROUP_CASES = [("Normal", "IdentityLink"), ("Bernoulli", "LogitLink"), ("Poisson", "LogLink")]
+
+
+@pytest.mark.parametrize("d,l", GROUP_CASES)
+def test_group_projection_matches_oracle(d, l):
+    """Doubly sparse projection (J groups x k predictors, src/utilities.jl:613-679; test/L0_reg_test.jl:185-243):
+    contiguous blocks, per-group k vector (empty initial support, :426-430) and scattered membership."""
+    n, p, k = 1500, 3000, 6
+    y, z, _, _, _ = synth.simulate_response(41, n, p, k, d, n_cov=1)
+    bed = synth.packed_columns(41, n, np.arange(p))
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    o = snp.SnpLinAlgOracle(bed, n)
+    blocks = np.arange(p) // 100 + 1
+    ks = [2] * 30; ks[3] = 1
+    scattered = np.random.default_rng(0).integers(1, 8, p)
+    for kw in ({"k": 2, "J": 4, "group": blocks}, {"k": ks, "J": 3, "group": blocks}, {"k": 2, "J": 3, "group": scattered},
+               {"k": 3, "J": 1, "group": np.ones(p, dtype=int)}):
+        res = m.fit_iht(y, g, z, d=d, l=l, **kw)
+        ref = iht.fit_iht(y, o, z, d=d, l=l, **kw)
+        assert ref.iter < 200
+        _compare(res, ref)
+        nz = np.flatnonzero(res.beta)
+        grp = np.asarray(kw["group"])
+        assert len(set(grp[nz])) <= kw["J"]
+        kmax = kw["k"] if np.isscalar(kw["k"]) else None
+        for gid in set(grp[nz]):
+            assert (grp[nz] == gid).sum() <= (kmax if kmax is not None else kw["k"][gid - 1])
+    # one group that holds everything == plain top-k projection after the first iteration's start
+    assert np.count_nonzero(res.beta) <= 3
+
+
+def test_group_projection_cv_weights_errors():
+    n, p, k = 1200, 2000, 5
+    y, z, _, _, _ = synth.simulate_response(43, n, p, k, "Normal", n_cov=1)
+    bed = synth.packed_columns(43, n, np.arange(p))
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    o = snp.SnpLinAlgOracle(bed, n)
+    blocks = np.arange(p) // 50 + 1
+    folds = synth.folds_for(4, n, 3)
+    mses, iters = m.cv_iht(y, g, z, path=[1, 2, 3], q=3, folds=folds, J=3, group=blocks, return_grid=True)
+    _, rgrid, riters = ocv.cv_iht(y, o, z, path=[1, 2, 3], q=3, folds=folds, J=3, group=blocks, return_grid=True)
+    assert np.array_equal(iters, riters)
+    np.testing.assert_allclose(mses, rgrid, rtol=RTOL)
+    w = m.maf_weights(g, max_weight=3.0)           # weights only shape the initial (ungrouped) support in group mode
+    _compare(m.fit_iht(y, g, z, k=2, J=3, group=blocks, weight=w, debias=True),
+             iht.fit_iht(y, o, z, k=2, J=3, group=blocks, weight=w, debias=True))
+    with pytest.raises(m.DimensionMismatch):
+        m.fit_iht(y, g, z, k=2, J=3, group=blocks[:-1])
+    with pytest.raises(AssertionError):
+        m.fit_iht(y, g, z, k=[1, 2])
+    with pytest.raises(m.IHTBError):                # check_group: a group with no more members than its k
+        m.fit_iht(y, g, z, k=[50] * 40, J=2, group=blocks)
+    with pytest.raises(AssertionError):
+        m.fit_iht(y, g, z, k=2, J=-1, group=blocks)

@@ -232,3 +232,32 @@ def test_debias_and_weights_on_bundled_data(normal_data, normal_oracle):
     assert (np.flatnonzero(heavy.beta) < 5000).sum() > (np.flatnonzero(plain.beta) < 5000).sum()
     with pytest.raises(ValueError):
         iht.fit_iht(y, normal_oracle, None, k=9, weight=np.ones(3))
+
+
+def test_project_group_sparse_properties():
+    """The reference's own property tests (test/utilities_test.jl:180-213)."""
+    rng = np.random.default_rng(3)
+    y = rng.standard_normal(10); group = rng.integers(1, 6, 10); x = y.copy()
+    iht.project_group_sparse(x, group, 2, 3)
+    nz = np.flatnonzero(x)
+    assert np.all(x[nz] == y[nz]) and nz.size <= 6
+    y = 5 * rng.random(15); yc = y.copy()
+    group = np.array([1, 2, 2, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5])
+    iht.project_group_sparse(y, group, 2, [1, 1, 2, 2, 3])
+    nz = np.flatnonzero(y)
+    assert np.all(y[nz] == yc[nz]) and nz.size <= 2 + 3
+    y = rng.standard_normal(100000); x = y.copy()
+    iht.project_k(x, 10)
+    iht.project_group_sparse(y, np.ones(100000, dtype=int), 1, 10)
+    assert np.all(x == y)
+
+
+def test_grouped_fit_selects_J_times_k(normal_data, normal_oracle):
+    """test/L0_reg_test.jl:236-242: J groups with k predictors each give J*k non-zero coefficients."""
+    p = normal_oracle.shape[1]
+    group = np.arange(p) // 500 + 1
+    res = iht.fit_iht(normal_data["y"], normal_oracle, None, k=3, J=3, group=group)
+    nz = np.flatnonzero(res.beta)
+    assert nz.size == 9 and len(set(group[nz])) == 3
+    with pytest.raises(ValueError):
+        iht.fit_iht(normal_data["y"], normal_oracle, None, k=[600] * 20, J=2, group=group)
