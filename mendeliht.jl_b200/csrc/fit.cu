@@ -304,8 +304,8 @@ struct ihtb_fit {
     // score sums are no longer on the device, so the host copy of the error bound is used and no scalars are read.
     void select_rescore(bool rerun) {
         if (grouped() && !init_plain) {
-            select_groups();
-            if (!rerun) finish_sweep_scalars(kExactBound);
+            select_groups(rerun);
+            if (!rerun) finish_sweep_scalars(cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound);
             return;
         }
         df_exact.clear(); cand_cache.clear();
@@ -539,53 +539,64 @@ struct ihtb_fit {
         IHTB_CHECK(!comm, IHTB_EUNSUPPORTED, "group projection is not available for SNP-sharded fits yet");
         IHTB_CHECK(J >= 0, IHTB_EINVAL, "Value of J (max number of groups) must be nonnegative!");
         std::unique_ptr<GroupCtx> gc(new GroupCtx());
-        gc->build(p, group1, J, ks, n_groups, cfg.k);
+        std::vector<double> h_sinv((size_t)p);
+        IHTB_CUDA(cudaMemcpy(h_sinv.data(), g->sinv.p, (size_t)p * sizeof(double), cudaMemcpyDeviceToHost));
+        gc->build(p, group1, J, ks, n_groups, cfg.k, h_sinv.data());
         grpctx = std::move(gc);
-        cfg.sweep_mode = IHTB_SWEEP_EXACT;      // group candidates are ranked on the exact gradient (groups.cu)
     }
 
-    // once per sweep: exact df of the support, per-group candidate lists, and the groups that can matter
-    void select_groups() {
+    // once per sweep: per-group candidate lists (with the sweep's error bound), the groups that can matter, and the
+    // exact FP64 df of their candidates and of the current support (groups.cu)
+    void select_groups(bool rerun) {
         GroupCtx& gc = *grpctx;
         df_exact.clear(); cand_cache.clear();
         df_sparse = false; denom_ready = false;
-        group_topk(gc, d_dfa.p, cfg.k, s);
+        const double coef = cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound;
+        group_topk(gc, d_dfa.p, g->sinv.p, rerun ? nullptr : d_scal.p, coef, bound, cfg.k, s);
         const size_t nsupp = idx.size();
         if (nsupp) {
             upload(d_cols.p, idx.data(), nsupp);
-            take_values(d_dfa.p, d_cols.p, (int64_t)nsupp, d_gout.p, s);
+            xt_gather(g, d_cols.p, (int64_t)nsupp, d_r.p, 1, d_vbar.p, d_gout.p, s);
             IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_gout.p, nsupp * sizeof(double), cudaMemcpyDeviceToHost, s));
         }
-        IHTB_CUDA(cudaMemcpyAsync(gc.h_gT.p, gc.d_gT.p, (size_t)gc.G * sizeof(double), cudaMemcpyDeviceToHost, s));
+        const size_t G = (size_t)gc.G;
+        IHTB_CUDA(cudaMemcpyAsync(gc.h_gT.p, gc.d_gT.p, (2 * G + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
         sync();
+        IHTB_CHECK(gc.h_gT.p[2 * G] == 0.0, IHTB_ENUMERIC,
+                   "degenerate group projection: too many entries of one group lie within the sweep error bound of its "
+                   "2k-th largest |gradient|");
         for (size_t t = 0; t < nsupp; ++t) df_exact[idx[t]] = h_gout.p[t];
-        std::vector<char> has((size_t)gc.G, 0);
+        const double *TL = gc.h_gT.p, *TU = gc.h_gT.p + G;
+        std::vector<char> has(G, 0);
         for (int64_t j : idx) has[(size_t)gc.grp[(size_t)j]] = 1;
         std::vector<int32_t> chosen;
-        std::vector<std::pair<double, int>> others;
-        for (int g = 0; g < gc.G; ++g) {
-            if (has[(size_t)g]) chosen.push_back(g);
-            else others.push_back({gc.h_gT.p[g], g});
+        std::vector<double> lows;
+        for (size_t gi = 0; gi < G; ++gi) {
+            if (has[gi]) chosen.push_back((int32_t)gi);
+            else lows.push_back(TL[gi]);
         }
-        if (gc.J > 0 && !others.empty()) {
-            const size_t need = std::min<size_t>((size_t)gc.J, others.size());
-            std::nth_element(others.begin(), others.begin() + (need - 1), others.end(),
-                             [](const std::pair<double, int>& x, const std::pair<double, int>& y) { return x.first > y.first; });
-            const double thr = others[need - 1].first;
-            for (const auto& o : others)
-                if (o.first >= thr) chosen.push_back(o.second);
+        if (gc.J > 0 && !lows.empty()) {
+            // a group without support entries can reach the J best norms only if its upper bound reaches the J-th
+            // largest lower bound among such groups
+            const size_t need = std::min<size_t>((size_t)gc.J, lows.size());
+            std::nth_element(lows.begin(), lows.begin() + (need - 1), lows.end(), std::greater<double>());
+            const double thr = lows[need - 1];
+            for (size_t gi = 0; gi < G; ++gi)
+                if (!has[gi] && TU[gi] >= thr) chosen.push_back((int32_t)gi);
         }
         IHTB_CHECK(chosen.size() <= 65536, IHTB_ENUMERIC, "degenerate group projection: too many groups tie at the J-th norm");
         std::sort(chosen.begin(), chosen.end());
         const int nc = (int)chosen.size();
         if (nc) {
             gc.ensure_chosen(nc);
+            const int64_t slots = (int64_t)nc * gc.lcap;
             IHTB_CUDA(cudaMemcpyAsync(gc.d_chosen.p, chosen.data(), (size_t)nc * sizeof(int32_t), cudaMemcpyHostToDevice, s));
             group_take(gc, nc, s);
-            IHTB_CUDA(cudaMemcpyAsync(gc.h_oidx.p, gc.d_oidx.p, (size_t)nc * gc.lcap * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-            IHTB_CUDA(cudaMemcpyAsync(gc.h_oval.p, gc.d_oval.p, (size_t)nc * gc.lcap * sizeof(double), cudaMemcpyDeviceToHost, s));
+            xt_gather(g, gc.d_oidx.p, slots, d_r.p, 1, d_vbar.p, gc.d_oval.p, s);      // slots holding -1 are skipped
+            IHTB_CUDA(cudaMemcpyAsync(gc.h_oidx.p, gc.d_oidx.p, (size_t)slots * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            IHTB_CUDA(cudaMemcpyAsync(gc.h_oval.p, gc.d_oval.p, (size_t)slots * sizeof(double), cudaMemcpyDeviceToHost, s));
             sync();
-            for (int64_t t = 0; t < (int64_t)nc * gc.lcap; ++t) {
+            for (int64_t t = 0; t < slots; ++t) {
                 const int64_t j = gc.h_oidx.p[t];
                 if (j < 0) continue;
                 df_exact[j] = gc.h_oval.p[t];
