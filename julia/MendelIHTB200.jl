@@ -80,30 +80,61 @@ linkcode(::IdentityLink) = Int32(0); linkcode(::LogitLink) = Int32(1); linkcode(
 linkcode(::ProbitLink) = Int32(3); linkcode(::CloglogLink) = Int32(4); linkcode(::CauchitLink) = Int32(5)
 linkcode(::SqrtLink) = Int32(6); linkcode(::InverseLink) = Int32(7); linkcode(::InverseSquareLink) = Int32(8)
 
+"SnpArrays.maf / MendelIHT.maf_weights (src/utilities.jl:692-697) from the device-side allele counts."
+function maf(x::B200SnpLinAlg)
+    out = Vector{Float64}(undef, x.p)
+    check(ccall((:ihtb_geno_maf, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), x.handle, out))
+    out
+end
+function MendelIHT.maf_weights(x::B200SnpLinAlg; max_weight::Float64=Inf)
+    p = maf(x)
+    clamp!(p .= 1 ./ (2 .* sqrt.(p .* (1 .- p))), 1.0, max_weight)
+end
+
+# weight / group / per-group k are attached to the fit handle before ihtb_fit_init
+function attach_options(fh, p::Int, k::Union{Int,Vector{Int}}, J::Int, group::AbstractVector{Int},
+                        weight::AbstractVector{Float64})
+    if length(group) > 0
+        length(group) == p || throw(DimensionMismatch("group must have length $p but was $(length(group))"))
+        ks = k isa Vector ? Int64.(k) : Int64[]
+        check(ccall((:ihtb_fit_set_groups, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int32, Ptr{Int64}, Int64),
+                    fh, Int32.(group), J, k isa Vector ? ks : C_NULL, length(ks)))
+    end
+    if length(weight) > 0
+        length(weight) == p || throw(DimensionMismatch("weight must have length $p but was $(length(weight))"))
+        check(ccall((:ihtb_fit_set_weights, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), fh, weight))
+    end
+end
+
 "Same signature and return type as MendelIHT.fit_iht (src/fit.jl:60-118) for `x::B200SnpLinAlg`."
 function fit_iht(y::AbstractVector{Float64}, x::B200SnpLinAlg, z::AbstractVecOrMat{Float64};
-                 k::Int=10, J::Int=1, d::Distribution=Normal(), l::Link=IdentityLink(),
-                 zkeep::BitVector=trues(size(z, 2)), est_r::Symbol=:None, tol::Float64=1e-4, max_iter::Int=200,
+                 k::Union{Int,Vector{Int}}=10, J::Int=1, d::Distribution=Normal(), l::Link=IdentityLink(),
+                 group::AbstractVector{Int}=Int[], weight::AbstractVector{Float64}=Float64[],
+                 zkeep::BitVector=trues(size(z, 2)), est_r::Symbol=:None, debias::Bool=false, init_beta::Bool=false,
+                 tol::Float64=1e-4, max_iter::Int=200,
                  min_iter::Int=5, max_step::Int=3, verbose::Bool=false, io::IO=stdout, kwargs...)
     est = est_r == :None ? Int32(0) : est_r == :MM ? Int32(1) : est_r == :Newton ? Int32(2) :
           throw(ArgumentError("Only support method is Newton or MM, but got $est_r"))
     x.center || error("x is not centered! Please construct SnpLinAlg{Float64}(::SnpArray, center=true, scale=true)")
     zm = z isa AbstractVector ? reshape(z, :, 1) : Matrix(z)
     r = d isa NegativeBinomial ? d.r : 1.0
-    cfg = Ref(Cfg(distcode(d), linkcode(l), k, r, tol, max_iter, min_iter, max_step, 0, est, 0))
+    MendelIHT.check_group(k, group)                                       # src/utilities.jl:902-915
+    kscalar = k isa Vector ? 0 : k                                         # src/data_structures.jl:75-81
+    cfg = Ref(Cfg(distcode(d), linkcode(l), kscalar, r, tol, max_iter, min_iter, max_step, 0, est, debias))
     fh = Ref{Ptr{Cvoid}}(C_NULL)
     keep = UInt8.(zkeep)
     check(ccall((:ihtb_fit_create, LIB), Int32,
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{UInt8}, Ref{Cfg}, Ref{Ptr{Cvoid}}),
                 x.handle, y, zm, size(zm, 2), keep, cfg, fh))
     try
-        check(ccall((:ihtb_fit_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), fh[], C_NULL))
+        attach_options(fh[], x.p, k, J, group, weight)
+        check(ccall((init_beta ? :ihtb_fit_init_beta : :ihtb_fit_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), fh[], C_NULL))
         res = CResult()
         check(ccall((:ihtb_fit_run, LIB), Int32, (Ptr{Cvoid}, Ref{CResult}, Ptr{Cvoid}, Int64), fh[], res, C_NULL, 0))
         beta = zeros(x.p); c = zeros(size(zm, 2))
         check(ccall((:ihtb_fit_get, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                     fh[], beta, c, C_NULL, C_NULL))
-        return IHTResult(res.time, res.logl, res.iter, beta, c, J, k, Int[], d, res.sigma_g)
+        return IHTResult(res.time, res.logl, res.iter, beta, c, J, k, collect(group), d, res.sigma_g)
     finally
         ccall((:ihtb_fit_destroy, LIB), Int32, (Ptr{Cvoid},), fh[])
     end
@@ -113,15 +144,17 @@ end
 function cv_iht(y::AbstractVector{Float64}, x::B200SnpLinAlg, z::AbstractVecOrMat{Float64};
                 d::Distribution=Normal(), l::Link=IdentityLink(), path::AbstractVector{<:Integer}=1:20, q::Int=5,
                 folds::AbstractVector{Int}=rand(1:q, size(x, 1)), zkeep::BitVector=trues(size(z, 2)),
-                max_iter::Int=100, min_iter::Int=5, kwargs...)
+                J::Int=1, group::AbstractVector{Int}=Int[], weight::AbstractVector{Float64}=Float64[],
+                debias::Bool=false, max_iter::Int=100, min_iter::Int=5, kwargs...)
     maximum(path) > size(x, 2) && error("Sparsity level in `path` cannot be larger than total number of variables")
     zm = z isa AbstractVector ? reshape(z, :, 1) : Matrix(z)
     r = d isa NegativeBinomial ? d.r : 1.0
-    cfg = Ref(Cfg(distcode(d), linkcode(l), maximum(path), r, 1e-4, max_iter, min_iter, 3, 0, 0, 0))
+    cfg = Ref(Cfg(distcode(d), linkcode(l), maximum(path), r, 1e-4, max_iter, min_iter, 3, 0, 0, debias))
     fh = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ihtb_fit_create, LIB), Int32,
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{UInt8}, Ref{Cfg}, Ref{Ptr{Cvoid}}),
                 x.handle, y, zm, size(zm, 2), UInt8.(zkeep), cfg, fh))
+    attach_options(fh[], x.p, maximum(path), J, group, weight)
     combos = MendelIHT.allocate_fold_and_k(q, path)
     mses = zeros(length(combos))
     try
