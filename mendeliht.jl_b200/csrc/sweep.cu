@@ -11,12 +11,20 @@
 //  EXACT: FP64 FMA per genotype, slab partials in FP64 (this file, k_sweep_exact).
 //  FAST : FP32 byte-indexed lookup tables in shared memory (sweep_lut.cu).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ihtb {
 
 void sweep_fast_partials(const ihtb_geno* g, const double* d_v, const double* d_vbar, float* d_part, int64_t* n_slabs,
                          cudaStream_t s);
 int64_t sweep_fast_num_slabs(const ihtb_geno* g);
+void sweep_exact_lut_partials(const ihtb_geno* g, const double* d_v, const double* d_vbar, double* d_part, cudaStream_t s);
+
+// tiled layout: table-driven FP64 kernel (sweep_lut64.cu); column-major debug layout or IHTB_EXACT_LEGACY=1: k_sweep_exact
+static bool exact_uses_lut(const ihtb_geno* g) {
+    static const bool legacy = [] { const char* e = getenv("IHTB_EXACT_LEGACY"); return e && *e == '1'; }();
+    return g->cs_j == 128 && !legacy;
+}
 
 constexpr int EX_THREADS = 128;          // one 32-bit word (16 samples) per thread -> 2048 samples per slab
 constexpr int EX_CB = 8;                 // columns per register tile
@@ -128,7 +136,14 @@ void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* d
     for (int64_t t = 0; t < m; ++t) {
         const double* v = dV + t * g->n;
         double* out = dOut + t * g->p;
-        if (mode == IHTB_SWEEP_EXACT) {
+        if (mode == IHTB_SWEEP_EXACT && exact_uses_lut(g)) {
+            const int64_t n_slabs = g->stride / 128;
+            if (sc->part64.n < (size_t)(n_slabs * g->p)) sc->part64.alloc((size_t)(n_slabs * g->p));
+            sweep_exact_lut_partials(g, v, d_vbar + t, sc->part64.p, s);
+            IHTB_LAUNCH((k_sweep_epilogue<double>), (unsigned)ceil_div(g->p, 256), 256, 0, s, sc->part64.p, n_slabs,
+                        g->p, g->mu.p, g->sinv.p, g->nmiss.p, g->miss_ptr.p, g->miss_idx.p, v, d_vbar + t,
+                        g->impute, out);
+        } else if (mode == IHTB_SWEEP_EXACT) {
             int64_t words = g->stride >> 2;
             int64_t n_slabs = ceil_div(words, EX_THREADS);
             if (sc->part64.n < (size_t)(n_slabs * g->p)) sc->part64.alloc((size_t)(n_slabs * g->p));
@@ -220,6 +235,13 @@ extern "C" int32_t ihtb_sweep_bench(const ihtb_geno* g, int32_t sweep_mode, int3
             if (sweep_mode == IHTB_SWEEP_FAST) {
                 IHTB_CUDA(cudaEventRecord(e0, s));
                 for (int i = 0; i < reps; ++i) sweep_fast_kernel_only(g, dV.p, dmean.p, sc.part32.p, s);
+                IHTB_CUDA(cudaEventRecord(e1, s));
+                IHTB_CUDA(cudaEventSynchronize(e1));
+                IHTB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+                *ms_kernel = ms / reps;
+            } else if (exact_uses_lut(g)) {
+                IHTB_CUDA(cudaEventRecord(e0, s));
+                for (int i = 0; i < reps; ++i) sweep_exact_lut_partials(g, dV.p, dmean.p, sc.part64.p, s);
                 IHTB_CUDA(cudaEventRecord(e1, s));
                 IHTB_CUDA(cudaEventSynchronize(e1));
                 IHTB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
