@@ -180,6 +180,14 @@ int32_t ihtb_mvfit_get(const ihtb_mvfit* f, double* beta, double* c, double* Sig
 int32_t ihtb_mvfit_predict(ihtb_mvfit* f, const uint8_t* test_mask, double* mse);   /* src/cross_validation.jl:288-299 */
 int32_t ihtb_mvfit_destroy(ihtb_mvfit* f);
 
+/* cv_iht in one call (src/cross_validation.jl:60-131): folds[n] in 1..nfolds, path[npath] sparsity levels; every
+ * (fold, k) fit masks the fold out, then mses[(fold-1)*npath + t] = out-of-fold deviance (predict!, :279-286) and
+ * iters (optional) the iteration counts.  cfg.k is ignored, cfg.max_iter is the reference's max_iter = 100 default's
+ * slot.  weight may be NULL.  The caller applies meanloss (:304-320). */
+int32_t ihtb_cv_run(const ihtb_geno* g, const double* y, const double* z, int64_t q, const uint8_t* zkeep,
+                    const ihtb_cfg* cfg, const int32_t* folds, int32_t nfolds, const int64_t* path, int64_t npath,
+                    const double* weight, double* mses, int64_t* iters);
+
 /* ---- multi-GPU plumbing (NCCL over NVLink; rendezvous of the 128-byte id is the host's job, e.g. torch.distributed) ---- */
 /* nccl_lib_path may be NULL: $IHTB_NCCL_LIB, then libnccl.so.2 are tried (dlopen at run time, no link-time dependency) */
 int32_t ihtb_comm_unique_id(const char* nccl_lib_path, uint8_t* out128);

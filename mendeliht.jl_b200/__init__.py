@@ -9,8 +9,8 @@ from ._lib import (SWEEP_EXACT, SWEEP_FAST, CudaError, DimensionMismatch, IHTBEr
                    launch_count, load)
 from .api import (BERNOULLI, NEGBIN, NORMAL, POISSON, B200SnpLinAlg, IHTResult, IHTVariable, mIHTResult, mIHTVariable,
                   is_multivariate, allocate_fold_and_k,
-                  canonicallink, cross_validate, cv_iht, fit_iht, iht, maf_weights, meanloss, parse_covariates)
+                  canonicallink, cross_validate, cv_iht, cv_run, fit_iht, iht, maf_weights, meanloss, parse_covariates)
 
-__all__ = ["B200SnpLinAlg", "IHTResult", "IHTVariable", "fit_iht", "cv_iht", "allocate_fold_and_k", "meanloss",
+__all__ = ["B200SnpLinAlg", "IHTResult", "IHTVariable", "fit_iht", "cv_iht", "cv_run", "allocate_fold_and_k", "meanloss",
            "canonicallink", "maf_weights", "iht", "cross_validate", "parse_covariates", "NORMAL", "BERNOULLI", "POISSON", "NEGBIN", "SWEEP_FAST", "SWEEP_EXACT", "load",
            "device_count", "launch_count", "IHTBError", "DimensionMismatch", "NumericError", "CudaError", "synth"]

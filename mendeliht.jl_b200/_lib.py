@@ -100,6 +100,8 @@ SIGNATURES = {
     "ihtb_fit_timer": [_p, C.c_int32, _f64],
     "ihtb_fit_phase_times": [_p, _f64],
     "ihtb_fit_destroy": [_p],
+    "ihtb_cv_run": [_p, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), C.POINTER(C.c_int32), C.c_int32, _i64, C.c_int64,
+                    _f64, _f64, _i64],
     "ihtb_mvfit_create": [_p, _f64, C.c_int64, _f64, C.c_int64, C.POINTER(Cfg), _pp],
     "ihtb_mvfit_set_k": [_p, C.c_int64],
     "ihtb_mvfit_init": [_p, _u8],

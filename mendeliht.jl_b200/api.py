@@ -488,6 +488,27 @@ def meanloss(fitloss, q: int, folds):
     return loss
 
 
+def cv_run(y, x: B200SnpLinAlg, z, folds, q: int, path, d=NORMAL, l="IdentityLink", zkeep=None, nb_r=1.0, max_iter=100,
+           min_iter=5, sweep_mode=_lib.SWEEP_FAST, weight=None, debias=False):
+    """The whole univariate (fold, k) grid in ONE library call (`ihtb_cv_run`); returns (mses, iters), fold-major."""
+    y = f64(y)
+    z = np.asarray(z, dtype=np.float64)
+    zf = np.asfortranarray(z.reshape(x.n, -1))
+    nq = zf.shape[1]
+    zk = None if zkeep is None else np.ascontiguousarray(zkeep, dtype=np.uint8)
+    fl = np.ascontiguousarray(folds, dtype=np.int32)
+    pa = np.ascontiguousarray(list(path), dtype=np.int64)
+    cfg = Cfg(DIST_ID[d], LINK_ID[l], int(pa.max()), float(nb_r), 1e-4, int(max_iter), int(min_iter), 3,
+              int(sweep_mode), 0, 1 if debias else 0)
+    mses = np.zeros(q * pa.shape[0]); iters = np.zeros(q * pa.shape[0], dtype=np.int64)
+    w = None if weight is None else f64(weight)
+    check(load().ihtb_cv_run(x._h, ptr(y, C.c_double), zf.ctypes.data_as(C.POINTER(C.c_double)), nq,
+                             ptr(zk, C.c_uint8) if zk is not None else None, C.byref(cfg),
+                             fl.ctypes.data_as(C.POINTER(C.c_int32)), q, ptr(pa, C.c_int64), pa.shape[0],
+                             ptr(w, C.c_double) if w is not None else None, ptr(mses, C.c_double), ptr(iters, C.c_int64)))
+    return mses, iters
+
+
 def cv_iht(y, x: B200SnpLinAlg, z=None, d=NORMAL, l=None, path=range(1, 21), q=5, folds=None, zkeep=None,
            nb_r=1.0, max_iter=100, min_iter=5, sweep_mode=_lib.SWEEP_FAST, combos=None, return_grid=False,
            init_beta=False, weight=None, debias=False, J=1, group=None):

@@ -893,7 +893,97 @@ struct ihtb_fit {
     static double now() {
         return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     }
+    // The gradient step and ALL its possible backtracks in one device round trip: the candidate models
+    // P_k(b0 + eta/2^s * df), s = 0..max_step, only need host work on the exact candidate values, so they are built
+    // up front, evaluated together (one k_x_support over the union of their supports with an n x M output, one
+    // batched k_glm_mu), and the host then walks the reference's loop `while prev_logl > logl && step < max_step`
+    // over the M log-likelihoods.  Per model the arithmetic is identical to the one-at-a-time path (zero
+    // coefficients add exact zeros; same blocks and reduction order), so results do not change -- only the number of
+    // host<->device synchronisations per iteration (1 instead of 1 + #backtracks).
+    static constexpr int kMaxBatch = 4;
+    DBuf<double> d_xbM, d_zcM, d_muM, d_partM, d_scalM, d_cM, d_coefM;
+    HBuf<double> h_scalM;
+    bool batch_ok() const {
+        static const bool off = [] { const char* e = getenv("IHTB_NO_BATCH"); return e && *e == '1'; }();
+        return !off && !comm && cfg.est_r == 0 && cfg.max_step >= 1 && cfg.max_step + 1 <= kMaxBatch;
+    }
+    void one_step_batched(double old_logl, double& eta, int& eta_step, double& new_logl) {
+        if (d_xbM.n < (size_t)(kMaxBatch * n)) {
+            d_xbM.alloc((size_t)(kMaxBatch * n)); d_zcM.alloc((size_t)(kMaxBatch * n)); d_muM.alloc((size_t)(kMaxBatch * n));
+            d_partM.alloc((size_t)kMaxBatch * GLM_MAX_BLOCKS * 3); d_scalM.alloc(kMaxBatch * 3); h_scalM.alloc(kMaxBatch * 3);
+            d_cM.alloc((size_t)(kMaxBatch * q)); d_coefM.alloc((size_t)kMaxBatch * (size_t)cap);
+        }
+        double t0 = now();
+        const double eta0 = stepsize();
+        double t1 = now(); phase[0] += t1 - t0;
+        const int M = cfg.max_step + 1;
+        struct Model { double eta; std::vector<int64_t> idx; std::vector<double> b, c; std::vector<uint8_t> idc; };
+        std::vector<Model> mods((size_t)M);
+        double e = eta0;
+        for (int m = 0; m < M; ++m) {
+            if (m) { e /= 2; idx = idx0; b = b0; c = c0; }               // backtrack! (src/utilities.jl:959-973)
+            gradstep(e);
+            mods[(size_t)m] = Model{e, idx, b, c, idc};
+        }
+        std::vector<int64_t> uni;
+        for (const Model& md : mods) uni.insert(uni.end(), md.idx.begin(), md.idx.end());
+        std::sort(uni.begin(), uni.end());
+        uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
+        const size_t U = uni.size();
+        IHTB_CHECK(U * (size_t)M <= d_coefM.n && U <= d_idx.n, IHTB_ENUMERIC, "support union too large for the batched step");
+        std::vector<double> coefM(U * (size_t)M, 0.0), cM((size_t)(M * q));
+        for (int m = 0; m < M; ++m) {
+            const Model& md = mods[(size_t)m];
+            for (size_t t = 0; t < md.idx.size(); ++t) {
+                const size_t pos = (size_t)(std::lower_bound(uni.begin(), uni.end(), md.idx[t]) - uni.begin());
+                coefM[pos + (size_t)m * U] = md.b[t];
+            }
+            for (int64_t l = 0; l < q; ++l) cM[(size_t)(m * q + l)] = md.c[(size_t)l];
+        }
+        double t2 = now(); phase[1] += t2 - t1;
+        if (U) {
+            upload(d_idx.p, uni.data(), U);
+            upload(d_coefM.p, coefM.data(), coefM.size());
+            x_support(g, d_idx.p, (int64_t)U, d_coefM.p, M, d_xbM.p, s);
+        } else {
+            IHTB_CUDA(cudaMemsetAsync(d_xbM.p, 0, (size_t)(M * n) * sizeof(double), s));
+        }
+        upload(d_cM.p, cM.data(), cM.size());
+        glm_mu_batched(glm, d_cM.p, M, d_xbM.p, d_zcM.p, d_muM.p, d_partM.p, d_scalM.p, s);
+        IHTB_CUDA(cudaMemcpyAsync(h_scalM.p, d_scalM.p, (size_t)(3 * M) * sizeof(double), cudaMemcpyDeviceToHost, s));
+        sync();
+        auto logl_of = [&](int m) {
+            const double dev = h_scalM.p[3 * m], lp = h_scalM.p[3 * m + 1], sw = h_scalM.p[3 * m + 2];
+            if (cfg.dist == IHTB_NORMAL) {
+                const double phi = dev / (double)n, sigma = std::sqrt(phi);
+                return -0.5 * (dev / phi) - sw * (0.5 * std::log(2.0 * M_PI) + std::log(sigma));
+            }
+            return lp;
+        };
+        int sidx = 0;
+        new_logl = logl_of(0);
+        while (old_logl > new_logl && sidx < cfg.max_step) {                // _iht_backtrack_ (src/utilities.jl:484-486)
+            ++sidx;
+            new_logl = logl_of(sidx);
+            ++n_backtracks;
+        }
+        const Model& win = mods[(size_t)sidx];
+        idx = win.idx; b = win.b; c = win.c; idc = win.idc;
+        eta = win.eta; eta_step = sidx;
+        last_dev = h_scalM.p[3 * sidx];
+        const size_t nb = (size_t)n * sizeof(double);
+        IHTB_CUDA(cudaMemcpyAsync(d_xb.p, d_xbM.p + (size_t)sidx * n, nb, cudaMemcpyDeviceToDevice, s));
+        IHTB_CUDA(cudaMemcpyAsync(d_zc.p, d_zcM.p + (size_t)sidx * n, nb, cudaMemcpyDeviceToDevice, s));
+        IHTB_CUDA(cudaMemcpyAsync(d_mu.p, d_muM.p + (size_t)sidx * n, nb, cudaMemcpyDeviceToDevice, s));
+        double t3 = now(); phase[2] += t3 - t2;
+        score_and_sweep();
+        phase[3] += now() - t3;
+        IHTB_CHECK(!std::isnan(new_logl), IHTB_ENUMERIC, "Loglikelihood function is NaN, aborting...");
+        IHTB_CHECK(!std::isinf(new_logl), IHTB_ENUMERIC, "Loglikelihood function is Inf, aborting...");
+    }
+
     void one_step(double old_logl, double& eta, int& eta_step, double& new_logl) {
+        if (batch_ok()) { one_step_batched(old_logl, eta, eta_step, new_logl); return; }
         double t0 = now();
         eta = stepsize();
         double t1 = now(); phase[0] += t1 - t0;
@@ -1218,6 +1308,55 @@ int32_t ihtb_fit_phase_times(const ihtb_fit* f, double* out4) {
         IHTB_CHECK(f && out4, IHTB_EINVAL, "NULL argument");
         for (int i = 0; i < 4; ++i) out4[i] = f->phase[i];
     });
+}
+
+// cv_iht in one call (src/cross_validation.jl:60-131): the (fold, k) grid of allocate_fold_and_k (:217-223) run back
+// to back on one workspace -- every fit sweeps all n rows with the fold masked out, mu_j / sigma_j stay full-sample --
+// and the out-of-fold deviance of each fit (predict!, :279-286).  mses is fold-major, nfolds x npath; the caller
+// applies meanloss (:304-320).  The reference fans this grid out over threads; one GPU runs it sequentially, several
+// GPUs deal the grid round-robin (parallel.py).
+int32_t ihtb_cv_run(const ihtb_geno* g, const double* y, const double* z, int64_t q, const uint8_t* zkeep,
+                    const ihtb_cfg* cfg, const int32_t* folds, int32_t nfolds, const int64_t* path, int64_t npath,
+                    const double* weight, double* mses, int64_t* iters) {
+    int32_t rc = guard([&] {
+        IHTB_CHECK(g && cfg && folds && path && mses, IHTB_EINVAL, "NULL argument");
+        IHTB_CHECK(nfolds >= 1 && npath >= 1, IHTB_EINVAL, "empty cross-validation grid");
+        for (int64_t t = 0; t < npath; ++t)
+            IHTB_CHECK(path[t] >= 0 && path[t] <= g->p, IHTB_EINVAL,
+                       "Sparsity level in `path` cannot be larger than total number of variables");
+    });
+    if (rc != IHTB_OK) return rc;
+    ihtb_cfg c = *cfg;
+    c.k = *std::max_element(path, path + npath);
+    ihtb_fit* f = nullptr;
+    rc = ihtb_fit_create(g, y, z, q, zkeep, &c, &f);
+    if (rc != IHTB_OK) return rc;
+    if (weight) rc = ihtb_fit_set_weights(f, weight);
+    const int64_t n = g->n;
+    std::vector<uint8_t> train((size_t)n), test((size_t)n);
+    for (int32_t fold = 1; fold <= nfolds && rc == IHTB_OK; ++fold) {
+        for (int64_t i = 0; i < n; ++i) { test[(size_t)i] = folds[i] == fold; train[(size_t)i] = !test[(size_t)i]; }
+        for (int64_t t = 0; t < npath && rc == IHTB_OK; ++t) {
+            ihtb_result res;
+            double dev = 0.0;
+            rc = ihtb_fit_set_k(f, path[t]);
+            if (rc == IHTB_OK) rc = ihtb_fit_init(f, train.data());
+            if (rc == IHTB_OK) rc = ihtb_fit_run(f, &res, nullptr, 0);
+            if (rc == IHTB_OK) rc = ihtb_fit_predict(f, test.data(), &dev);
+            if (rc == IHTB_OK) {
+                mses[(int64_t)(fold - 1) * npath + t] = dev;
+                if (iters) iters[(int64_t)(fold - 1) * npath + t] = res.iter;
+            }
+        }
+    }
+    if (rc != IHTB_OK) {                       // keep the first error message across the cleanup call
+        char msg[1024];
+        ihtb_last_error(msg, sizeof(msg));
+        ihtb_fit_destroy(f);
+        set_last_error(msg);
+        return rc;
+    }
+    return ihtb_fit_destroy(f);
 }
 
 int32_t ihtb_fit_destroy(ihtb_fit* f) {

@@ -21,6 +21,10 @@ k_glm_mu(int64_t n, int64_t q, const double* __restrict__ Z, const double* __res
          double* __restrict__ zc, double* __restrict__ mu, const double* __restrict__ y, const double* __restrict__ w,
          int dist, int link, double nb_r, int add_zc, double* __restrict__ part) {
     __shared__ double sh[32];
+    // blockIdx.y = model of a batched evaluation (glm_mu_batched): every model has its own c, xb, zc, mu and partial
+    // sums, laid out back to back, and is reduced exactly like a single model (same blocks, same order)
+    c += blockIdx.y * q; xb += blockIdx.y * n; zc += blockIdx.y * n; mu += blockIdx.y * n;
+    part += (int64_t)blockIdx.y * gridDim.x * 3;
     double a_dev = 0.0, a_lp = 0.0, a_w = 0.0;
     const bool clampit = dist != IHTB_NORMAL;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -147,6 +151,7 @@ k_set_weights(int64_t n, const uint8_t* __restrict__ mask, const double* __restr
 
 // out[v] = sum_b part[b*nv + v]: one warp per value, lanes stride over the blocks, fixed shuffle tree (deterministic)
 __global__ void k_finalize(const double* __restrict__ part, int nblocks, int nv, double* __restrict__ out) {
+    part += (int64_t)blockIdx.y * nblocks * nv; out += blockIdx.y * nv;       // batched: one row of sums per model
     int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (v >= nv) return;
@@ -241,6 +246,15 @@ void glm_mu(GlmCtx& c, const double* d_c, int add_zc, cudaStream_t s) {
     IHTB_LAUNCH(k_glm_mu, grid, GLM_THREADS, 0, s, c.n, c.q, c.Z, d_c, c.xb, c.zc, c.mu, c.y, c.w, c.dist, c.link,
                 c.nb_r, add_zc, c.part);
     IHTB_LAUNCH(k_finalize, 1, 96, 0, s, c.part, grid, 3, c.scal);
+}
+// M models at once (the gradient step and its backtracks): xbM / zcM / muM are n x M, d_cM is q x M, d_scalM gets
+// [dev, lp, sum w] per model.  Per model the arithmetic is that of glm_mu.
+void glm_mu_batched(GlmCtx& c, const double* d_cM, int M, double* xbM, double* zcM, double* muM, double* d_partM,
+                    double* d_scalM, cudaStream_t s) {
+    int grid = glm_grid(c.n);
+    IHTB_LAUNCH(k_glm_mu, dim3(grid, M), GLM_THREADS, 0, s, c.n, c.q, c.Z, d_cM, xbM, zcM, muM, c.y, c.w, c.dist, c.link,
+                c.nb_r, 1, d_partM);
+    IHTB_LAUNCH(k_finalize, dim3(1, M), 96, 0, s, d_partM, grid, 3, d_scalM);
 }
 void glm_score(GlmCtx& c, cudaStream_t s) {
     int grid = glm_grid(c.n);

@@ -108,6 +108,8 @@ struct GlmCtx {
 };
 
 void glm_mu(GlmCtx& c, const double* d_c, int add_zc, cudaStream_t s);        // scal: dev, lp, sum w
+void glm_mu_batched(GlmCtx& c, const double* d_cM, int M, double* xbM, double* zcM, double* muM, double* d_partM,
+                    double* d_scalM, cudaStream_t s);                           // d_scalM[3m..]: dev, lp, sum w of model m
 void glm_mean_from_sum(GlmCtx& c, double* d_mean, cudaStream_t s);             // d_mean[0] = scal[0] / n
 void glm_score(GlmCtx& c, cudaStream_t s);                                      // scal: sum r, sum |r|, df2[q]
 // scal[0] (or *d_out) = sum of squares of sqrt(W) (xs + Z (d2 .* d2mask)); d2mask may be NULL
