@@ -151,10 +151,10 @@ def test_cv_matches_oracle():
 def test_cv_run_single_call_matches_loop():
     """`ihtb_cv_run` (the whole grid in one library call) == the host loop over fit handles == the oracle."""
     n, p, k = 1500, 2500, 5
-    y, z, _, _, _ = synth.simulate_response(19, n, p, k, "Poisson", n_cov=1, missing_rate=0.002)
-    bed = synth.packed_columns(19, n, np.arange(p), 0.002)
+    y, z, _, _, _ = synth.simulate_response(23, n, p, k, "Poisson", n_cov=1, missing_rate=0.002)
+    bed = synth.packed_columns(23, n, np.arange(p), 0.002)
     g = m.B200SnpLinAlg.from_bed_columns(bed, n)
-    folds = synth.folds_for(19, n, 3)
+    folds = synth.folds_for(23, n, 3)
     path = [2, 4, 7]
     mses, iters = m.cv_run(y, g, z, folds, 3, path, d="Poisson", l="LogLink")
     lm, li = m.cv_iht(y, g, z, d="Poisson", l="LogLink", path=path, q=3, folds=folds, return_grid=True)
@@ -162,7 +162,7 @@ def test_cv_run_single_call_matches_loop():
     np.testing.assert_array_equal(iters, li)
     _, rgrid, riters = ocv.cv_iht(y, snp.SnpLinAlgOracle(bed, n), z, d="Poisson", l="LogLink", path=path, q=3,
                                   folds=folds, return_grid=True)
-    assert np.array_equal(iters, riters)
+    assert np.array_equal(iters, riters) and riters.max() < 100      # converging fits (cf. test_oscillating_fit)
     np.testing.assert_allclose(mses, rgrid, rtol=RTOL)
     with pytest.raises(m.IHTBError):
         m.cv_run(y, g, z, folds, 3, [p + 1], d="Poisson", l="LogLink")
