@@ -62,13 +62,13 @@ struct ihtb_fit {
     int cap = 4096;
 
     // device state
-    DBuf<double> d_y, d_z, d_w, d_xb, d_zc, d_mu, d_r, d_xs, d_dfa, d_b0d, d_part, d_scal, d_small, d_coef, d_gout,
-        d_vbar, d_sval;
+    DBuf<double> d_y, d_z, d_w, d_xb, d_zc, d_mu, d_r, d_xs, d_dfa, d_part, d_scal, d_small, d_coef, d_gout,
+        d_vbar;
     DBuf<uint8_t> d_mask;
     DBuf<uint32_t> d_keyL, d_keyU;
     DBuf<int> d_hist;
     DBuf<int64_t> d_sel;   // [TopkState (2 x int64) | cand[cap]]
-    DBuf<int64_t> d_idx, d_cols, d_sidx;
+    DBuf<int64_t> d_idx, d_cols;
     HBuf<double> h_scal, h_gout;
     HBuf<int64_t> h_sel;
     void* sweep_scratch = nullptr;
@@ -78,7 +78,7 @@ struct ihtb_fit {
     TopkCtx tk{};
 
     // host model state (k-sparse)
-    std::vector<int64_t> idx, idx0, best_idx, b0d_idx;
+    std::vector<int64_t> idx, idx0, best_idx;
     std::vector<double> b, b0, best_b;
     std::vector<double> c, c0, best_c, df2, h_y, h_mu;
     std::vector<uint8_t> idc, idc0;
@@ -464,22 +464,6 @@ struct ihtb_fit {
         return eta;
     }
 
-    void sync_b0d() {   // device dense copy of b0 used by the candidate selection
-        if (!b0d_idx.empty()) {
-            upload(d_sidx.p, b0d_idx.data(), b0d_idx.size());
-            scatter_dense(d_b0d.p, d_sidx.p, nullptr, (int64_t)b0d_idx.size(), 1, s);
-        }
-        b0d_idx.clear();
-        std::vector<double> vals;
-        for (size_t t = 0; t < idx0.size(); ++t)
-            if (b0[t] != 0.0 && is_local(idx0[t])) { b0d_idx.push_back(idx0[t] - j0); vals.push_back(b0[t]); }
-        if (!b0d_idx.empty()) {
-            upload(d_sidx.p, b0d_idx.data(), b0d_idx.size());
-            upload(d_sval.p, vals.data(), vals.size());
-            scatter_dense(d_b0d.p, d_sidx.p, d_sval.p, (int64_t)b0d_idx.size(), 0, s);
-        }
-    }
-
     static double b_lookup(const std::vector<int64_t>& ii, const std::vector<double>& vv, int64_t j) {
         auto it = std::lower_bound(ii.begin(), ii.end(), j);
         return (it != ii.end() && *it == j) ? vv[it - ii.begin()] : 0.0;
@@ -685,7 +669,6 @@ struct ihtb_fit {
     double save_prev(double cur, double best) {
         idx0 = idx; b0 = b; c0 = c; idc0 = idc;
         if (cur > best) { best_idx = idx; best_b = b; best_c = c; }
-        sync_b0d();
         return std::max(cur, best);
     }
 
@@ -813,7 +796,6 @@ struct ihtb_fit {
         idc.assign(zkeep.begin(), zkeep.end()); idc0 = idc;
         df_exact.clear(); dfs_idx.clear(); dfs_val.clear(); df_sparse = false;
         d_xb.zero(s);
-        sync_b0d();     // idx0 empty -> clears the dense copy
         const uint8_t* dm = nullptr;
         if (train_mask) {
             upload(d_mask.p, train_mask, (size_t)n);
@@ -1104,15 +1086,15 @@ static ihtb_fit* fit_allocate(const ihtb_geno* g, int64_t q, int cap) {
     IHTB_CUDA(cudaEventCreate(&f->ev0));
     IHTB_CUDA(cudaEventCreate(&f->ev1));
     f->d_y.alloc(n); f->d_z.alloc(n * q); f->d_w.alloc(n); f->d_xb.alloc(n); f->d_zc.alloc(n); f->d_mu.alloc(n);
-    f->d_r.alloc(n); f->d_xs.alloc(n + 2 * (size_t)cap + 64); f->d_dfa.alloc(p); f->d_b0d.alloc(p); f->d_mask.alloc(n);
+    f->d_r.alloc(n); f->d_xs.alloc(n + 2 * (size_t)cap + 64); f->d_dfa.alloc(p); f->d_mask.alloc(n);
     f->d_part.alloc((size_t)GLM_MAX_BLOCKS * (2 + q)); f->d_scal.alloc(2 + q + 8); f->d_small.alloc(2 * q);
     size_t cols_cap = 2 * (size_t)cap + 64;
-    f->d_coef.alloc(cols_cap); f->d_gout.alloc(cols_cap); f->d_vbar.alloc(1); f->d_sval.alloc(cols_cap);
-    f->d_idx.alloc(cols_cap); f->d_cols.alloc(cols_cap); f->d_sidx.alloc(cols_cap);
+    f->d_coef.alloc(cols_cap); f->d_gout.alloc(cols_cap); f->d_vbar.alloc(1);
+    f->d_idx.alloc(cols_cap); f->d_cols.alloc(cols_cap);
     f->d_keyL.alloc(p); f->d_keyU.alloc(p); f->d_hist.alloc(2048); f->d_sel.alloc(2 + cap);
     f->h_scal.alloc(2 + q + 8); f->h_gout.alloc(cols_cap); f->h_sel.alloc(2 + cap);
     f->sweep_scratch = sweep_scratch_create();
-    f->d_b0d.zero(f->s); f->d_hist.zero(f->s);
+    f->d_hist.zero(f->s);
     return f.release();
 }
 
