@@ -173,6 +173,8 @@ int32_t ihtb_mvfit_create(const ihtb_geno* g, const double* Y, int64_t r, const 
                           const ihtb_cfg* cfg, ihtb_mvfit** out);
 int32_t ihtb_mvfit_set_k(ihtb_mvfit* f, int64_t k);
 int32_t ihtb_mvfit_init(ihtb_mvfit* f, const uint8_t* train_mask);
+/* init_beta = true (src/multivariate.jl:425-429, initialize_beta! :519-558): B starts from per-trait univariate regressions */
+int32_t ihtb_mvfit_init_beta(ihtb_mvfit* f, const uint8_t* train_mask);
 int32_t ihtb_mvfit_run(ihtb_mvfit* f, ihtb_result* result, ihtb_iter_trace* trace, int64_t trace_cap);
 /* beta: r x p column-major (trait fastest, like Julia's best_B); c: r x q column-major; Sigma: r x r = inv(Gamma);
  * sigma_g[r]: per-trait PVE (src/pve.jl:35-37).  Any pointer may be NULL. */

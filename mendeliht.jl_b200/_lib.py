@@ -105,6 +105,7 @@ SIGNATURES = {
     "ihtb_mvfit_create": [_p, _f64, C.c_int64, _f64, C.c_int64, C.POINTER(Cfg), _pp],
     "ihtb_mvfit_set_k": [_p, C.c_int64],
     "ihtb_mvfit_init": [_p, _u8],
+    "ihtb_mvfit_init_beta": [_p, _u8],
     "ihtb_mvfit_run": [_p, C.POINTER(Result), C.POINTER(IterTrace), C.c_int64],
     "ihtb_mvfit_get": [_p, _f64, _f64, _f64, _f64],
     "ihtb_mvfit_predict": [_p, _u8, _f64],

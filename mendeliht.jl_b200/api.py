@@ -359,9 +359,10 @@ class mIHTVariable:
     def set_k(self, k):
         check(load().ihtb_mvfit_set_k(self._h, int(k)))
 
-    def init_iht_indices(self, train_mask=None):
+    def init_iht_indices(self, train_mask=None, init_beta=False):
         m = None if train_mask is None else np.ascontiguousarray(train_mask, dtype=np.uint8)
-        check(load().ihtb_mvfit_init(self._h, ptr(m, C.c_uint8) if m is not None else None))
+        fn = load().ihtb_mvfit_init_beta if init_beta else load().ihtb_mvfit_init
+        check(fn(self._h, ptr(m, C.c_uint8) if m is not None else None))
 
     def fit(self, trace_cap=None):
         cap = int(self.cfg.max_iter) if trace_cap is None else trace_cap
@@ -396,12 +397,12 @@ class mIHTVariable:
             pass
 
 
-def _fit_mv(y, x, z, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode) -> mIHTResult:
+def _fit_mv(y, x, z, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode, init_beta=False) -> mIHTResult:
     if z is None:
         z = np.ones((1, x.n))
     v = mIHTVariable(x, z, y, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode)
     try:
-        v.init_iht_indices(None)
+        v.init_iht_indices(None, init_beta)
         res, trace = v.fit()
         beta, c, S, sg = v.get()
     finally:
@@ -436,7 +437,7 @@ def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est
         if debias:
             raise _lib.IHTBError(_lib.IHTB_EUNSUPPORTED,
                                  "Currently the debiasing routine for multivariate IHT is broken, sorry!")
-        return _fit_mv(y, x, z, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode)
+        return _fit_mv(y, x, z, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode, init_beta)
     if not x.center:
         raise _lib.IHTBError(_lib.IHTB_EUNSUPPORTED, "x is not centered! Please construct SnpLinAlg{Float64}"
                                                      "(::SnpArray, center=true, scale=true)")
@@ -537,10 +538,7 @@ def cv_iht(y, x: B200SnpLinAlg, z=None, d=NORMAL, l=None, path=range(1, 21), q=5
             fold, k = grid[i]
             test = folds == fold
             v.set_k(k)
-            if mv:
-                v.init_iht_indices(~test)
-            else:
-                v.init_iht_indices(~test, init_beta)
+            v.init_iht_indices(~test, init_beta)
             res, _ = v.fit(trace_cap=0)
             iters[i] = res.iter
             mses[i] = v.predict(test)

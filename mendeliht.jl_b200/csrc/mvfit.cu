@@ -25,6 +25,8 @@ void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* d
                            int mode, cudaStream_t s, void* scratch_any, float* sweep_ms);
 void* sweep_scratch_create();
 void sweep_scratch_destroy(void* p);
+void sweep_class_sums(const ihtb_geno* g, const double* d_v, double* d_w1, double* d_w2, double* d_wm, cudaStream_t s,
+                      void* scratch_any);
 
 constexpr int MV_MAXR = 16;
 constexpr int MV_THREADS = 256;
@@ -518,7 +520,86 @@ struct ihtb_mvfit {
         IHTB_LAUNCH(k_mv_weights, (unsigned)ceil_div(n, 256), 256, 0, s, n, dm, d_w.p);
     }
     // init_iht_indices! :376-452
-    void init(const uint8_t* train_mask) {
+    // initialize_beta! (src/multivariate.jl:519-558) + project_k!(v) + update_xb! (:425-429): every B[t, j] starts at
+    // the slope of the univariate regression of trait t on [1, x_j] over the training samples (clamped to +-2), the
+    // intercept of trait t at the mean of all those regressions' intercepts; then the k largest entries are kept.
+    // The per-SNP sums come from the exact class-sum sweep (one pass for the weights, one per trait), like the
+    // univariate ihtb_fit_init_beta.  The reference accumulates the intercepts from several threads without
+    // synchronisation; this is the single-thread result.
+    void do_init_beta(const uint8_t* train_mask, const std::vector<double>& sy) {
+        DBuf<double> cls((size_t)(6 * p)), bd((size_t)(p * r)), wy((size_t)n);
+        double *W1 = cls.p, *W2 = W1 + p, *Wm = W2 + p, *Y1 = Wm + p, *Y2 = Y1 + p, *Ym = Y2 + p;
+        sweep_class_sums(g, d_w.p, W1, W2, Wm, s, sweep_scratch);
+        ++n_sweeps;
+        std::vector<double> c0sum((size_t)r, 0.0);
+        for (int t = 0; t < r; ++t) {
+            GlmCtx tmp{n, q, d_Z.p, d_Y.p + (size_t)t * n, d_w.p, nullptr, nullptr, nullptr, nullptr, d_part.p, d_scal.p,
+                       IHTB_NORMAL, IHTB_LINK_IDENTITY, 1.0};
+            init_beta_products(tmp, wy.p, s);
+            sweep_class_sums(g, wy.p, Y1, Y2, Ym, s, sweep_scratch);
+            ++n_sweeps;
+            init_beta_solve(tmp, p, W1, W2, Wm, Y1, Y2, Ym, n_train, sy[(size_t)t], g->mu.p, g->sinv.p, g->impute,
+                            bd.p + (size_t)t * p, s);
+            readback(1);
+            c0sum[(size_t)t] = h_scal.p[0];
+        }
+        // covariates 2..q: the same 2x2 regression on the host (r*q*n work)
+        std::fill(C.begin(), C.end(), 0.0);
+        if (q > 1) {
+            std::vector<double> hY((size_t)(n * r)), hZ((size_t)(n * q));
+            IHTB_CUDA(cudaMemcpyAsync(hY.data(), d_Y.p, hY.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+            IHTB_CUDA(cudaMemcpyAsync(hZ.data(), d_Z.p, hZ.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+            sync();
+            for (int t = 0; t < r; ++t)
+                for (int64_t l = 1; l < q; ++l) {
+                    double sx = 0.0, sxx = 0.0, sxy = 0.0;
+                    for (int64_t i = 0; i < n; ++i) {
+                        if (train_mask && !train_mask[i]) continue;
+                        const double z = hZ[(size_t)(i + l * n)];
+                        sx += z; sxx += z * z; sxy += z * hY[(size_t)(i + (int64_t)t * n)];
+                    }
+                    double icpt = sy[(size_t)t], slope = sxy;
+                    const double u11 = std::sqrt(n_train), u12 = sx / u11, dd = sxx - u12 * u12;
+                    if (n_train > 0 && dd > 0) {
+                        const double u22 = std::sqrt(dd), t1 = sy[(size_t)t] / u11, t2 = (sxy - u12 * t1) / u22;
+                        slope = t2 / u22; icpt = (t1 - u12 * slope) / u11;
+                    }
+                    c0sum[(size_t)t] += icpt;
+                    C[(size_t)(t * q + l)] = std::min(std::max(slope, -2.0), 2.0);
+                }
+        }
+        for (int t = 0; t < r; ++t)
+            C[(size_t)(t * q)] = std::min(std::max(c0sum[(size_t)t] / (double)(p + q - 1), -2.0), 2.0);
+        // project_k!(v): the k largest |B| entries (ties: lowest position in vec(B)); covariates are all kept
+        std::vector<double> zeros((size_t)r, 0.0);
+        upload(d_bounds.p, zeros.data(), zeros.size());
+        topk_candidates_blocked(tk, bd.p, nullptr, g->sinv.p, p, d_bounds.p, 1.0, cfg.k, s);
+        IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + cap) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        sync();
+        const TopkState* st = reinterpret_cast<const TopkState*>(h_sel.p);
+        IHTB_CHECK(st->count <= cap && (size_t)st->count <= d_gout.n, IHTB_ENUMERIC,
+                   "degenerate projection of the initial beta (too many ties)");
+        const int cnt = st->count;
+        take_values(bd.p, d_sel.p + 2, cnt, d_gout.p, s);
+        IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_gout.p, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+        sync();
+        struct Item { double a; int64_t pos; double v; };
+        std::vector<Item> items;
+        for (int e = 0; e < cnt; ++e) {
+            const int64_t pos_dev = h_sel.p[2 + e], t = pos_dev / p, j = pos_dev % p;
+            items.push_back({std::fabs(h_gout.p[e]), j * r + t, h_gout.p[e]});
+        }
+        std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) {
+            return x.a > y.a || (x.a == y.a && x.pos < y.pos);
+        });
+        B.clear();
+        for (size_t e = 0; e < items.size() && (int64_t)e < cfg.k; ++e)
+            if (items[e].v != 0.0) B[items[e].pos] = items[e].v;
+        B0 = B; C0 = C;
+        update_xb();
+    }
+
+    void init(const uint8_t* train_mask, bool init_beta = false) {
         IHTB_CHECK(cfg.k >= 1, IHTB_EINVAL, "Multivariate IHT requires k >= 1!");
         B.clear(); B0.clear(); bestB.clear(); dfs.clear(); df_exact.clear(); df_sparse = false;
         C.assign((size_t)r * q, 0.0); C0 = C; bestC = C; df2.assign((size_t)r * q, 0.0);
@@ -537,9 +618,15 @@ struct ihtb_mvfit {
         IHTB_LAUNCH(k_mv_score, grid, MV_THREADS, 0, s, n, r, q, d_resid.p, small(Gamma), d_Z.p, d_R1.p, d_part.p);
         finalize(grid, nv);
         readback(nv);
-        for (int t = 0; t < r; ++t) C[t * q + 0] = h_scal.p[t] / n_train;   // ybar_t (:415-422)
+        std::vector<double> sy((size_t)r);
+        for (int t = 0; t < r; ++t) { sy[(size_t)t] = h_scal.p[t]; C[t * q + 0] = h_scal.p[t] / n_train; }   // ybar_t (:415-422)
         resid_gram();                                                // CZ, mu, resid
+        if (init_beta) {
+            do_init_beta(train_mask, sy);
+            resid_gram();                                            // mu, resid of the initialised model
+        }
         score_and_sweep();                                           // Gamma = I
+        if (init_beta) { inited = true; return; }                    // df keeps the full gradient (:436 `if !init_beta`)
         // first k entries of the gradient by magnitude; df becomes its projection (:436-445)
         std::vector<int64_t> cols = device_candidate_cols(1.0);
         std::sort(cols.begin(), cols.end());
@@ -662,6 +749,14 @@ int32_t ihtb_mvfit_init(ihtb_mvfit* f, const uint8_t* train_mask) {
         IHTB_CHECK(f, IHTB_EINVAL, "NULL fit handle");
         IHTB_CUDA(cudaSetDevice(f->device));
         f->init(train_mask);
+    });
+}
+
+int32_t ihtb_mvfit_init_beta(ihtb_mvfit* f, const uint8_t* train_mask) {
+    return guard([&] {
+        IHTB_CHECK(f, IHTB_EINVAL, "NULL fit handle");
+        IHTB_CUDA(cudaSetDevice(f->device));
+        f->init(train_mask, /*init_beta=*/true);
     });
 }
 

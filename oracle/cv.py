@@ -54,7 +54,7 @@ def cv_iht(y, x, z=None, d=glm.NORMAL, l=glm.IDENTITY, path=range(1, 21), q=5, f
         train = ~test
         if multivariate:
             v = MvIHTVariable(x, z, y, k, zkeep)
-            v.init_iht_indices(train)
+            v.init_iht_indices(train, init_beta)
             _, iters[i] = mv_fit_loop(v, max_iter=max_iter, min_iter=min_iter)
             v.cv_wts[train] = 0.0; v.cv_wts[test] = 1.0
             v.update_xb(); v.update_mu()

@@ -84,6 +84,27 @@ def check_group(k, group) -> None:
         raise AssertionError("Value of k (max predictors per group) must be nonnegative!")
 
 
+def linreg_columns(xs: np.ndarray, ys: np.ndarray):
+    """`linreg!` (src/utilities.jl:824-842) for every column of xs [N, m] at once: regression of ys on [1, x] through
+    the 2x2 Cholesky factor.  A failed factorisation (constant column) leaves xty unsolved: slope = sum(x y),
+    intercept = sum(y) (the reference's try/catch, :836-841).  Returns (intercepts [m], slopes [m])."""
+    N = float(xs.shape[0])
+    sy = float(ys.sum())
+    sx = xs.sum(axis=0); sxx = (xs * xs).sum(axis=0); sxy = xs.T @ ys
+    icpt = np.full(xs.shape[1], sy); slope = sxy.copy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        u11 = np.sqrt(N); u12 = sx / u11
+        d = sxx - u12 * u12
+        ok = d > 0
+        u22 = np.sqrt(np.where(ok, d, 1.0))
+        t1 = sy / u11
+        t2 = (sxy - u12 * t1) / u22
+        b2 = t2 / u22
+        b1 = (t1 - u12 * b2) / u11
+    icpt[ok] = b1[ok]; slope[ok] = b2[ok]
+    return icpt, slope
+
+
 def prune_ties(vals: np.ndarray, nz_mask: np.ndarray, excess: int) -> None:
     """Deterministic replacement for `_choose!`: drop `excess` smallest-magnitude support entries,
     highest index first (only ties at the threshold can be in excess)."""
@@ -215,23 +236,9 @@ class IHTVariable:
         intercept contribution = sum(y) (the reference's try/catch, :836-841)."""
         cv = np.asarray(cv_idx, dtype=bool)
         ys = self.y[cv]
-        N = float(cv.sum())
-        sy = float(ys.sum())
 
-        def linreg(xs):                       # xs: [N, m] -> intercepts [m], slopes [m]
-            sx = xs.sum(axis=0); sxx = (xs * xs).sum(axis=0); sxy = xs.T @ ys
-            icpt = np.full(xs.shape[1], sy); slope = sxy.copy()
-            with np.errstate(divide="ignore", invalid="ignore"):
-                u11 = np.sqrt(N); u12 = sx / u11
-                d = sxx - u12 * u12
-                ok = d > 0
-                u22 = np.sqrt(np.where(ok, d, 1.0))
-                t1 = sy / u11
-                t2 = (sxy - u12 * t1) / u22
-                b2 = t2 / u22
-                b1 = (t1 - u12 * b2) / u11
-            icpt[ok] = b1[ok]; slope[ok] = b2[ok]
-            return icpt, slope
+        def linreg(xs):
+            return linreg_columns(xs, ys)
 
         c0 = 0.0
         for j0 in range(0, self.p, 2048):     # column blocks bound the memory of the dense slice

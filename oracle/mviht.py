@@ -93,7 +93,29 @@ class MvIHTVariable:
         return int(np.count_nonzero(self.cv_wts))
 
     # :376-452
-    def init_iht_indices(self, cv_idx):
+    # :519-558 (`initialize_beta!`, executed in trait order; the reference adds the intercepts to a shared `C0` from
+    # several threads without synchronisation, the restatement is the single-thread result)
+    def initialize_beta(self, cv_idx):
+        from .iht import linreg_columns
+        cv = np.asarray(cv_idx, dtype=bool)
+        for j in range(self.r):
+            ys = self.Y[j, cv]
+            c0 = 0.0
+            for j0 in range(0, self.p, 2048):
+                xs = self.x.dense()[:, j0:j0 + 2048][cv]
+                icpt, slope = linreg_columns(xs, ys)
+                c0 += float(icpt.sum())
+                self.B[j, j0:j0 + 2048] = slope
+            if self.q > 1:
+                icpt, slope = linreg_columns(self.Z[1:, cv].T, ys)
+                c0 += float(icpt.sum())
+                self.C[j, 1:] = slope
+            self.C[j, 0] = c0 / (self.p + self.q - 1)
+        np.clip(self.C, -2, 2, out=self.C)
+        np.clip(self.B, -2, 2, out=self.B)
+        self.B0 = self.B.copy(); self.C0 = self.C.copy()
+
+    def init_iht_indices(self, cv_idx, init_beta=False):
         if self.k < 1:
             raise ValueError("Multivariate IHT requires k >= 1!")
         r, p, q, n = self.r, self.p, self.q, self.n
@@ -107,7 +129,13 @@ class MvIHTVariable:
         nz = self.nsamples()
         self.C[:, 0] = (self.Y * self.cv_wts[None, :]).sum(axis=1) / nz
         self.CZ = self.C @ self.Z
+        if init_beta:                              # :425-429
+            self.initialize_beta(cv_idx)
+            self._project()
+            self.update_xb()
         self.update_mu(); self.update_resid(); self.score()
+        if init_beta:
+            return
         full = self._vectorize(self.df, self.df2)
         project_k(full, self.k + self.zkeepn)
         self._unvectorize(full, self.df, self.df2)
@@ -159,6 +187,10 @@ class MvIHTVariable:
     def iht_gradstep(self, eta):
         self.B += eta * self.df
         self.C += eta * self.df2
+        self._project()
+
+    # project_k!(v::mIHTVariable) :106-127
+    def _project(self):
         full = self._vectorize(self.B, self.C)
         project_k(full, self.k + self.zkeepn)
         self._unvectorize(full, self.B, self.C)
@@ -251,13 +283,13 @@ def mv_fit_loop(v, tol=1e-4, max_iter=200, min_iter=5, max_step=3, trace=None):
 
 
 def fit_mv_iht(Y, x, Z=None, k=10, zkeep=None, tol=1e-4, max_iter=200, min_iter=5, max_step=3,
-               cv_train_idx=None) -> MvIHTResult:
+               cv_train_idx=None, init_beta=False) -> MvIHTResult:
     """`fit_iht(Y, Transpose(xla), Z; k)` for MvNormal (src/fit.jl:60-118)."""
     Y = np.asarray(Y, dtype=np.float64)
     if Z is None:
         Z = np.ones((1, Y.shape[1]))
     v = MvIHTVariable(x, Z, Y, k, zkeep)
-    v.init_iht_indices(np.ones(v.n, bool) if cv_train_idx is None else cv_train_idx)
+    v.init_iht_indices(np.ones(v.n, bool) if cv_train_idx is None else cv_train_idx, init_beta)
     trace = MvTrace()
     best_logl, mm_iter = mv_fit_loop(v, tol, max_iter, min_iter, max_step, trace)
     sg = np.array([np.var(v.mu[i], ddof=1) / np.var(v.Y[i], ddof=1) for i in range(v.r)])

@@ -257,6 +257,26 @@ def test_mv_fit_matches_oracle(n, p, r, k, mode):
     _compare_mv(res, ref)
 
 
+def test_mv_init_beta_matches_oracle():
+    """init_beta = true for MvNormal (src/multivariate.jl:425-429, 519-558), also under a CV mask."""
+    from oracle import mviht
+    n, p, r, k = 1200, 2000, 3, 9
+    bed, Y, Z = _mv_data(77, n, p, r, k)
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    o = snp.SnpLinAlgOracle(bed, n)
+    for mode in MODES:
+        res = m.fit_iht(Y, g, Z, k=k + 1, init_beta=True, sweep_mode=mode)
+        ref = mviht.fit_mv_iht(Y, o, Z, k=k + 1, init_beta=True)
+        _compare_mv(res, ref)
+    plain = m.fit_iht(Y, g, Z, k=k + 1)
+    assert res.iter != plain.iter or not np.array_equal(res.beta, plain.beta)
+    folds = synth.folds_for(3, n, 2)
+    mses, iters = m.cv_iht(Y, g, Z, path=[4, 9], q=2, folds=folds, init_beta=True, return_grid=True)
+    _, rgrid, riters = ocv.cv_iht(Y, o, Z, path=[4, 9], q=2, folds=folds, init_beta=True, return_grid=True)
+    assert np.array_equal(iters, riters)
+    np.testing.assert_allclose(mses, rgrid, rtol=RTOL)
+
+
 def test_mv_bundled_fixture():
     """Bundled data/multivariate.* (r = 2), k = 10: same support as the survey probe / oracle."""
     from oracle import mviht
