@@ -32,6 +32,19 @@ for d, l, n, p, k, ncov, miss in [("Normal", "IdentityLink", 5000, 20001, 8, 2, 
     ok = ok and same
     print(f"rank {rank} {d}: sharded iter={res.iter} full iter={ref.iter} same={same} "
           f"max|dbeta|={np.abs(res.beta - ref.beta).max():.3e} logl {res.logl:.9f} vs {ref.logl:.9f}", flush=True)
+# prior weights on a sharded fit: every rank holds the whole weight vector, the device keys use the local slice
+n, p, k = 4000, 16000, 6
+y, z, *_ = synth.simulate_response(55, n, p, k, "Normal", n_cov=1)
+j0, pl = parallel.shard_range(p, world, rank)
+g_loc = m.B200SnpLinAlg.synthetic(n, pl, 55, 0.0, j0)
+g_full = m.B200SnpLinAlg.synthetic(n, p, 55, 0.0, 0)
+w = m.maf_weights(g_full, max_weight=4.0)
+res = m.fit_iht(y, g_loc, z, k=k + 2, weight=w, comm=comm, p_global=p)
+ref = m.fit_iht(y, g_full, z, k=k + 2, weight=w)
+same = (res.iter == ref.iter and np.array_equal(np.flatnonzero(res.beta), np.flatnonzero(ref.beta))
+        and np.allclose(res.beta, ref.beta, rtol=1e-9, atol=1e-12))
+ok = ok and same
+print(f"rank {rank} weighted: sharded iter={res.iter} full iter={ref.iter} same={same}", flush=True)
 # full BASELINE size per GPU: FAST and EXACT sweeps must give the same support / iterations / beta (stress for the pipeline)
 n, pg, k = 50000, 500000 * world, 20
 y, z, *_ = synth.simulate_response(2025, n, pg, k, "Bernoulli", geno_seed=2024)

@@ -537,3 +537,22 @@ def test_group_projection_cv_weights_errors():
         m.fit_iht(y, g, z, k=[50] * 40, J=2, group=blocks)
     with pytest.raises(AssertionError):
         m.fit_iht(y, g, z, k=2, J=-1, group=blocks)
+
+
+def test_next_tier_options_against_frozen_fixtures(normal_data):
+    """CUDA path vs tests/golden/oracle_regression.json (weights, debias, groups, per-group k, init_beta on the bundled
+    1000 x 10000 PLINK file): support and iteration counts identical, values within 1e-6."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(GOLDEN, "make_oracle_regression.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    frozen = json.load(open(os.path.join(GOLDEN, "oracle_regression.json")))
+    g = m.B200SnpLinAlg.from_bed_file(os.path.join(GOLDEN, "normal.bed"), 1000)
+    for name, kw in mk.cases(g.p).items():
+        res = m.fit_iht(normal_data["y"], g, None, **kw)
+        want = frozen[name]
+        nz = np.flatnonzero(res.beta)
+        assert res.iter == want["iter"] and list(nz) == want["support_0based"], name
+        np.testing.assert_allclose(res.beta[nz], want["beta"], rtol=RTOL, err_msg=name)
+        np.testing.assert_allclose(res.c, want["c"], rtol=RTOL, err_msg=name)
+        assert abs(res.logl - want["logl"]) <= RTOL * abs(want["logl"]), name
+        assert abs(res.sigma_g - want["sigma_g"]) <= RTOL * abs(want["sigma_g"]), name

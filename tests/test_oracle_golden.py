@@ -261,3 +261,19 @@ def test_grouped_fit_selects_J_times_k(normal_data, normal_oracle):
     assert nz.size == 9 and len(set(group[nz])) == 3
     with pytest.raises(ValueError):
         iht.fit_iht(normal_data["y"], normal_oracle, None, k=[600] * 20, J=2, group=group)
+
+
+def test_oracle_regression_next_tier_options(normal_data, normal_oracle):
+    """The oracle's frozen answers for weights / debias / groups / init_beta on the bundled data
+    (tests/golden/make_oracle_regression.py; oracle-derived, not reference-published)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(GOLDEN, "make_oracle_regression.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    frozen = json.load(open(os.path.join(GOLDEN, "oracle_regression.json")))
+    for name, kw in mk.cases(normal_oracle.shape[1]).items():
+        got = mk.run(normal_data["y"], normal_oracle, kw)
+        want = frozen[name]
+        assert got["iter"] == want["iter"] and got["support_0based"] == want["support_0based"], name
+        np.testing.assert_allclose(got["beta"], want["beta"], rtol=1e-9, err_msg=name)
+        np.testing.assert_allclose(got["c"], want["c"], rtol=1e-9, err_msg=name)
+        assert abs(got["logl"] - want["logl"]) <= 1e-9 * abs(want["logl"]), name
