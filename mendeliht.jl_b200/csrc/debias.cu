@@ -8,6 +8,7 @@
 // and one tiled weighted Gram kernel [X u]' W [X u]; the k x k Cholesky solve runs on the host.  All reductions have a
 // fixed order (deterministic).
 #include "debias.cuh"
+#include "comm.cuh"
 #include "glm.cuh"
 
 namespace ihtb {
@@ -48,6 +49,7 @@ __global__ void k_decode_cols(GenoView gv, int center, const int64_t* __restrict
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n * k) return;
     const int64_t c = t / n, i = t % n, j = cols[c];
+    if (j < 0) { out[t] = 0.0; return; }          // column of another shard: filled in by the all-reduce
     uint32_t code = (*gv_ptr(gv, j, i >> 2) >> (2 * (i & 3))) & 3u;
     double m = gv.mu[j];
     double g = (code == 2) ? 1.0 : (code == 3) ? 2.0 : (code == 1) ? (gv.impute ? m : 0.0) : 0.0;
@@ -184,13 +186,16 @@ void DebiasWs::ensure(int64_t n, int k) {
 }
 
 void debias_irls(const ihtb_geno* g, const double* d_y, int dist, int link, double nb_r, const int64_t* d_cols, int k,
-                 double* beta_out, DebiasWs& ws, cudaStream_t s) {
+                 double* beta_out, DebiasWs& ws, cudaStream_t s, ihtb_comm* comm) {
     IHTB_CHECK(k >= 1 && k <= DB_MAX_K, IHTB_EUNSUPPORTED,
                "debiasing supports at most " + std::to_string(DB_MAX_K) + " predictors in the support");
     const int64_t n = g->n;
     const int kk = k + 1;
     ws.ensure(n, k);
     IHTB_LAUNCH(k_decode_cols, (unsigned)ceil_div(n * k, 256), 256, 0, s, geno_view(g), g->center, d_cols, (int64_t)k, ws.xk.p);
+    // SNP-sharded fits: every rank decodes its own support columns (zeros elsewhere); one all-reduce of the n x k block
+    // gives all ranks the same dense matrix, and the refit then runs replicated
+    if (comm) comm_allreduce_sum_f64(comm, ws.xk.p, (size_t)(n * k), s);
     const int eval_grid = (int)std::min<int64_t>(1024, ceil_div(n, 256));
     const int ntiles = (kk + DB_TILE - 1) / DB_TILE;
     const int npairs = ntiles * (ntiles + 1) / 2;

@@ -658,9 +658,10 @@ struct ihtb_fit {
     DebiasWs debias_ws;
     void debias() {
         if (idx.empty()) return;
-        IHTB_CHECK(!comm, IHTB_EUNSUPPORTED, "debias is not available for SNP-sharded fits yet");
-        upload(d_cols.p, idx.data(), idx.size());
-        debias_irls(g, d_y.p, cfg.dist, cfg.link, glm.nb_r, d_cols.p, (int)idx.size(), b.data(), debias_ws, s);
+        std::vector<int64_t> loc(idx.size());
+        for (size_t t = 0; t < idx.size(); ++t) loc[t] = is_local(idx[t]) ? idx[t] - j0 : -1;
+        upload(d_cols.p, loc.data(), loc.size());
+        debias_irls(g, d_y.p, cfg.dist, cfg.link, glm.nb_r, d_cols.p, (int)idx.size(), b.data(), debias_ws, s, comm);
         ++n_debias;
     }
     int64_t n_debias = 0;
@@ -716,7 +717,8 @@ struct ihtb_fit {
     // [1, x_j] over the training samples for every SNP (two exact class-sum passes over the packed matrix) and covariate.
     void do_init_beta() {
         IHTB_CHECK(cfg.dist == IHTB_NORMAL, IHTB_EINVAL, "Intializing beta values only work for Gaussian phenotypes! Sorry!");
-        IHTB_CHECK(!comm, IHTB_EUNSUPPORTED, "init_beta is not available for SNP-sharded fits yet");
+        // SNP-sharded fits: the class sums and regressions are per column (no communication); the sum of the intercepts
+        // is all-reduced, and every rank's local top-k of the initial beta is all-gathered for the global projection
         DBuf<double> cls((size_t)(7 * p));           // W1 W2 Wm Y1 Y2 Ym beta
         double *W1 = cls.p, *W2 = W1 + p, *Wm = W2 + p, *Y1 = Wm + p, *Y2 = Y1 + p, *Ym = Y2 + p, *bd = Ym + p;
         init_beta_products(glm, d_xs.p, s);                                   // d_xs = w .* y
@@ -724,6 +726,7 @@ struct ihtb_fit {
         sweep_class_sums(g, d_xs.p, Y1, Y2, Ym, s, sweep_scratch);
         n_sweeps += 2;
         init_beta_solve(glm, p, W1, W2, Wm, Y1, Y2, Ym, sum_w, sum_wy, g->mu.p, g->sinv.p, g->impute, bd, s);   // scal[0] = sum of intercepts
+        if (comm) comm_allreduce_sum_f64(comm, d_scal.p, 1, s);
         readback_scal(1);
         double c0sum = h_scal.p[0];
         // covariates 2..q (host 2x2 solves on device-reduced sums: N, sum z, sum z^2, sum z y)
@@ -743,7 +746,7 @@ struct ihtb_fit {
                 c[l] = std::min(std::max(slope, -2.0), 2.0);
             }
         }
-        c[0] = std::min(std::max(c0sum / (double)(p + q - 1), -2.0), 2.0);
+        c[0] = std::min(std::max(c0sum / (double)(p_global + q - 1), -2.0), 2.0);
         // project_k!(v): top (k + zkeepn) of [b; c with Inf at kept covariates]
         std::vector<int64_t> cand;
         if (cfg.k > 0) {
@@ -761,6 +764,31 @@ struct ihtb_fit {
             take_values(bd, d_cols.p, (int64_t)cand.size(), d_gout.p, s);
             IHTB_CUDA(cudaMemcpyAsync(vals.data(), d_gout.p, cand.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
             sync();
+        }
+        if (comm) {        // exchange (global index, value) of the local candidates: block = [count, 0, idx[capx], bits[capx]]
+            const size_t blk = 2 + 2 * (size_t)capx;
+            IHTB_CHECK((int64_t)cand.size() <= capx, IHTB_ENUMERIC, "degenerate projection of the initial beta (too many ties)");
+            std::vector<int64_t> mine(blk, 0);
+            mine[0] = (int64_t)cand.size();
+            for (size_t t = 0; t < cand.size(); ++t) {
+                mine[2 + t] = cand[t] + j0;
+                memcpy(&mine[2 + capx + t], &vals[t], sizeof(double));
+            }
+            upload(d_pack.p, mine.data(), blk);
+            comm_allgather_i64(comm, d_pack.p, d_packall.p, blk, s);
+            const int nr = nranks();
+            IHTB_CUDA(cudaMemcpyAsync(h_packall.p, d_packall.p, nr * blk * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            sync();
+            cand.clear(); vals.clear();
+            for (int rk = 0; rk < nr; ++rk) {
+                const int64_t* b_ = h_packall.p + (size_t)rk * blk;
+                for (int64_t t = 0; t < b_[0]; ++t) {
+                    double v;
+                    memcpy(&v, &b_[2 + capx + t], sizeof(double));
+                    cand.push_back(b_[2 + t]);
+                    vals.push_back(v);
+                }
+            }
         }
         struct Item { double a; int64_t pos; double v; };
         std::vector<Item> items;

@@ -45,6 +45,20 @@ same = (res.iter == ref.iter and np.array_equal(np.flatnonzero(res.beta), np.fla
         and np.allclose(res.beta, ref.beta, rtol=1e-9, atol=1e-12))
 ok = ok and same
 print(f"rank {rank} weighted: sharded iter={res.iter} full iter={ref.iter} same={same}", flush=True)
+res = m.fit_iht(y, g_loc, z, k=k + 2, init_beta=True, comm=comm, p_global=p)
+ref = m.fit_iht(y, g_full, z, k=k + 2, init_beta=True)
+same = (res.iter == ref.iter and np.array_equal(np.flatnonzero(res.beta), np.flatnonzero(ref.beta))
+        and np.allclose(res.beta, ref.beta, rtol=1e-9, atol=1e-12) and np.allclose(res.c, ref.c, rtol=1e-9))
+ok = ok and same
+print(f"rank {rank} init_beta: sharded iter={res.iter} full iter={ref.iter} same={same}", flush=True)
+yb, zb, *_ = synth.simulate_response(56, n, p, k, "Bernoulli", geno_seed=55)
+res = m.fit_iht(yb, g_loc, zb, k=k + 1, d="Bernoulli", l="LogitLink", debias=True, comm=comm, p_global=p)
+ref = m.fit_iht(yb, g_full, zb, k=k + 1, d="Bernoulli", l="LogitLink", debias=True)
+same = (res.iter == ref.iter and np.array_equal(np.flatnonzero(res.beta), np.flatnonzero(ref.beta))
+        and np.allclose(res.beta, ref.beta, rtol=1e-8, atol=1e-12))
+ok = ok and same
+print(f"rank {rank} debias: sharded iter={res.iter} full iter={ref.iter} same={same} "
+      f"max|dbeta|={np.abs(res.beta - ref.beta).max():.3e}", flush=True)
 # full BASELINE size per GPU: FAST and EXACT sweeps must give the same support / iterations / beta (stress for the pipeline)
 n, pg, k = 50000, 500000 * world, 20
 y, z, *_ = synth.simulate_response(2025, n, pg, k, "Bernoulli", geno_seed=2024)
