@@ -148,7 +148,8 @@ int32_t ihtb_fit_set_weights(ihtb_fit* f, const double* weight);
  * group[p] holds 1-based group ids, at most J groups stay active with at most k predictors each; ks = NULL uses
  * cfg.k for every group, otherwise ks[n_groups] is the per-group maximum (the reference's vector-valued k; cfg.k is
  * then ignored, check_group src/utilities.jl:902-915 applies).  group = NULL clears.  Call before ihtb_fit_init.
- * Group fits always use the exact FP64 sweep.  Not available for sharded fits (IHTB_EUNSUPPORTED). */
+ * Works with either sweep mode (per-group candidate lists carry the sweep's error bound and are re-scored in FP64).
+ * Not available for sharded fits (IHTB_EUNSUPPORTED). */
 int32_t ihtb_fit_set_groups(ihtb_fit* f, const int32_t* group, int32_t J, const int64_t* ks, int64_t n_groups);
 int32_t ihtb_fit_set_k(ihtb_fit* f, int64_t k);                       /* v.k = sparsity (src/cross_validation.jl:110) */
 int32_t ihtb_fit_init(ihtb_fit* f, const uint8_t* train_mask);         /* init_iht_indices!; NULL = all samples */
