@@ -149,7 +149,7 @@ int32_t ihtb_fit_set_weights(ihtb_fit* f, const double* weight);
  * cfg.k for every group, otherwise ks[n_groups] is the per-group maximum (the reference's vector-valued k; cfg.k is
  * then ignored, check_group src/utilities.jl:902-915 applies).  group = NULL clears.  Call before ihtb_fit_init.
  * Works with either sweep mode (per-group candidate lists carry the sweep's error bound and are re-scored in FP64).
- * Not available for sharded fits (IHTB_EUNSUPPORTED). */
+ * On a sharded fit `group` still has p_global entries (the whole matrix) on every rank. */
 int32_t ihtb_fit_set_groups(ihtb_fit* f, const int32_t* group, int32_t J, const int64_t* ks, int64_t n_groups);
 int32_t ihtb_fit_set_k(ihtb_fit* f, int64_t k);                       /* v.k = sparsity (src/cross_validation.jl:110) */
 int32_t ihtb_fit_init(ihtb_fit* f, const uint8_t* train_mask);         /* init_iht_indices!; NULL = all samples */

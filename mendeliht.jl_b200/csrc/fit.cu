@@ -520,12 +520,11 @@ struct ihtb_fit {
     bool grouped() const { return (bool)grpctx; }
     void set_groups(const int32_t* group1, int J, const int64_t* ks, int64_t n_groups) {
         if (!group1) { grpctx.reset(); return; }
-        IHTB_CHECK(!comm, IHTB_EUNSUPPORTED, "group projection is not available for SNP-sharded fits yet");
         IHTB_CHECK(J >= 0, IHTB_EINVAL, "Value of J (max number of groups) must be nonnegative!");
         std::unique_ptr<GroupCtx> gc(new GroupCtx());
         std::vector<double> h_sinv((size_t)p);
         IHTB_CUDA(cudaMemcpy(h_sinv.data(), g->sinv.p, (size_t)p * sizeof(double), cudaMemcpyDeviceToHost));
-        gc->build(p, group1, J, ks, n_groups, cfg.k, h_sinv.data());
+        gc->build(p, j0, p_global, group1, J, ks, n_groups, cfg.k, h_sinv.data());
         grpctx = std::move(gc);
     }
 
@@ -537,20 +536,32 @@ struct ihtb_fit {
         df_sparse = false; denom_ready = false;
         const double coef = cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound;
         group_topk(gc, d_dfa.p, g->sinv.p, rerun ? nullptr : d_scal.p, coef, bound, cfg.k, s);
-        const size_t nsupp = idx.size();
-        if (nsupp) {
-            upload(d_cols.p, idx.data(), nsupp);
-            xt_gather(g, d_cols.p, (int64_t)nsupp, d_r.p, 1, d_vbar.p, d_gout.p, s);
-            IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_gout.p, nsupp * sizeof(double), cudaMemcpyDeviceToHost, s));
+        const size_t G = (size_t)gc.G, nT = 2 * G + 1;
+        const int nr = nranks();
+        std::vector<double> TL(G), TU(G);
+        bool overflow = false;
+        if (comm) {
+            // SNP-sharded: a group's members are spread over the ranks.  T_g <= sum of the local upper bounds and
+            // T_g >= every local lower bound, so the bounds of all ranks are gathered and combined
+            if (gc.d_Tall.n < nT * (size_t)nr) { gc.d_Tall.alloc(nT * (size_t)nr); gc.h_Tall.alloc(nT * (size_t)nr); }
+            comm_allgather_i64(comm, reinterpret_cast<const int64_t*>(gc.d_gT.p), gc.d_Tall.p, nT, s);
+            IHTB_CUDA(cudaMemcpyAsync(gc.h_Tall.p, gc.d_Tall.p, nT * (size_t)nr * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            sync();
+            std::fill(TL.begin(), TL.end(), 0.0); std::fill(TU.begin(), TU.end(), 0.0);
+            for (int rk = 0; rk < nr; ++rk) {
+                const double* T = reinterpret_cast<const double*>(gc.h_Tall.p) + (size_t)rk * nT;
+                for (size_t gi = 0; gi < G; ++gi) { TL[gi] = std::max(TL[gi], T[gi]); TU[gi] += T[G + gi]; }
+                overflow = overflow || T[2 * G] != 0.0;
+            }
+        } else {
+            IHTB_CUDA(cudaMemcpyAsync(gc.h_gT.p, gc.d_gT.p, nT * sizeof(double), cudaMemcpyDeviceToHost, s));
+            sync();
+            for (size_t gi = 0; gi < G; ++gi) { TL[gi] = gc.h_gT.p[gi]; TU[gi] = gc.h_gT.p[G + gi]; }
+            overflow = gc.h_gT.p[2 * G] != 0.0;
         }
-        const size_t G = (size_t)gc.G;
-        IHTB_CUDA(cudaMemcpyAsync(gc.h_gT.p, gc.d_gT.p, (2 * G + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
-        sync();
-        IHTB_CHECK(gc.h_gT.p[2 * G] == 0.0, IHTB_ENUMERIC,
+        IHTB_CHECK(!overflow, IHTB_ENUMERIC,
                    "degenerate group projection: too many entries of one group lie within the sweep error bound of its "
                    "2k-th largest |gradient|");
-        for (size_t t = 0; t < nsupp; ++t) df_exact[idx[t]] = h_gout.p[t];
-        const double *TL = gc.h_gT.p, *TU = gc.h_gT.p + G;
         std::vector<char> has(G, 0);
         for (int64_t j : idx) has[(size_t)gc.grp[(size_t)j]] = 1;
         std::vector<int32_t> chosen;
@@ -570,22 +581,50 @@ struct ihtb_fit {
         }
         IHTB_CHECK(chosen.size() <= 65536, IHTB_ENUMERIC, "degenerate group projection: too many groups tie at the J-th norm");
         std::sort(chosen.begin(), chosen.end());
+        // columns to re-score exactly: the chosen groups' lists (lcap slots each, -1 padded) + this rank's support columns
         const int nc = (int)chosen.size();
+        const int64_t nsupp = (int64_t)idx.size();
+        const int64_t list_slots = (int64_t)nc * gc.lcap, slots = list_slots + nsupp;
+        if (slots == 0) return;
+        gc.ensure_chosen(std::max(nc, 1));
+        if (gc.d_oidx.n < (size_t)slots) {
+            gc.d_oidx.alloc((size_t)slots); gc.d_oval.alloc((size_t)slots);
+            gc.h_oidx.alloc((size_t)slots); gc.h_oval.alloc((size_t)slots);
+        }
         if (nc) {
-            gc.ensure_chosen(nc);
-            const int64_t slots = (int64_t)nc * gc.lcap;
             IHTB_CUDA(cudaMemcpyAsync(gc.d_chosen.p, chosen.data(), (size_t)nc * sizeof(int32_t), cudaMemcpyHostToDevice, s));
             group_take(gc, nc, s);
-            xt_gather(g, gc.d_oidx.p, slots, d_r.p, 1, d_vbar.p, gc.d_oval.p, s);      // slots holding -1 are skipped
+        }
+        std::vector<int64_t> supp_loc((size_t)nsupp);
+        for (int64_t t = 0; t < nsupp; ++t) supp_loc[(size_t)t] = is_local(idx[(size_t)t]) ? idx[(size_t)t] - j0 : -1;
+        upload(gc.d_oidx.p + list_slots, supp_loc.data(), (size_t)nsupp);
+        xt_gather(g, gc.d_oidx.p, slots, d_r.p, 1, d_vbar.p, gc.d_oval.p, s);          // slots holding -1 are skipped
+        auto take = [&](int64_t t, int64_t j, double v) {
+            if (j < 0) return;
+            df_exact[j] = v;
+            if (t < list_slots) cand_cache.push_back(j);
+        };
+        if (comm) {
+            const size_t blk = 2 * (size_t)slots;
+            if (gc.d_blk.n < blk) gc.d_blk.alloc(blk);
+            if (gc.d_blkall.n < blk * (size_t)nr) { gc.d_blkall.alloc(blk * (size_t)nr); gc.h_blkall.alloc(blk * (size_t)nr); }
+            group_pack(gc.d_oidx.p, gc.d_oval.p, slots, j0, gc.d_blk.p, s);
+            comm_allgather_i64(comm, gc.d_blk.p, gc.d_blkall.p, blk, s);
+            IHTB_CUDA(cudaMemcpyAsync(gc.h_blkall.p, gc.d_blkall.p, blk * (size_t)nr * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+            sync();
+            for (int rk = 0; rk < nr; ++rk) {
+                const int64_t* b_ = gc.h_blkall.p + (size_t)rk * blk;
+                for (int64_t t = 0; t < slots; ++t) {
+                    double v;
+                    memcpy(&v, &b_[slots + t], sizeof(double));
+                    take(t, b_[t], v);
+                }
+            }
+        } else {
             IHTB_CUDA(cudaMemcpyAsync(gc.h_oidx.p, gc.d_oidx.p, (size_t)slots * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
             IHTB_CUDA(cudaMemcpyAsync(gc.h_oval.p, gc.d_oval.p, (size_t)slots * sizeof(double), cudaMemcpyDeviceToHost, s));
             sync();
-            for (int64_t t = 0; t < slots; ++t) {
-                const int64_t j = gc.h_oidx.p[t];
-                if (j < 0) continue;
-                df_exact[j] = gc.h_oval.p[t];
-                cand_cache.push_back(j);
-            }
+            for (int64_t t = 0; t < slots; ++t) take(t, gc.h_oidx.p[t], gc.h_oval.p[t]);
         }
         std::sort(cand_cache.begin(), cand_cache.end());
         cand_cache.erase(std::unique(cand_cache.begin(), cand_cache.end()), cand_cache.end());

@@ -117,11 +117,13 @@ __global__ void k_group_take(const int32_t* __restrict__ chosen, int n, int64_t 
     oidx[t] = (u < len) ? gidx[goff[g] + u] : -1;
 }
 
-void GroupCtx::build(int64_t p_, const int32_t* group1, int J_, const int64_t* ks_, int64_t n_groups, int64_t kscalar,
-                     const double* h_sinv) {
+// group1: 1-based group of every SNP of the WHOLE matrix (p_global entries); this handle owns columns [j0, j0+p).
+// Group ids, check_group and the list capacity lcap are global; the member lists are those of the local columns.
+void GroupCtx::build(int64_t p_, int64_t j0, int64_t p_global, const int32_t* group1, int J_, const int64_t* ks_,
+                     int64_t n_groups, int64_t kscalar, const double* h_sinv) {
     p = p_; J = J_;
     int gmax = 0;
-    for (int64_t j = 0; j < p; ++j) {
+    for (int64_t j = 0; j < p_global; ++j) {
         IHTB_CHECK(group1[j] >= 1, IHTB_EDOMAIN, "group ids must be >= 1");
         gmax = std::max(gmax, (int)group1[j]);
     }
@@ -129,7 +131,7 @@ void GroupCtx::build(int64_t p_, const int32_t* group1, int J_, const int64_t* k
     ks_vector = ks_ != nullptr;
     if (ks_vector) {
         // check_group (src/utilities.jl:902-915)
-        IHTB_CHECK(p > 1, IHTB_EINVAL, "Doubly sparse projection specified (since k is a vector) but there are no group information.");
+        IHTB_CHECK(p_global > 1, IHTB_EINVAL, "Doubly sparse projection specified (since k is a vector) but there are no group information.");
         IHTB_CHECK(n_groups >= G, IHTB_EDIM, "k must have one entry per group");
         ks.assign(ks_, ks_ + n_groups);
         if ((int64_t)G < n_groups) G = (int)n_groups;
@@ -137,33 +139,41 @@ void GroupCtx::build(int64_t p_, const int32_t* group1, int J_, const int64_t* k
         ks.clear();
     }
     kcap = kscalar;
-    grp.resize((size_t)p);
+    grp.resize((size_t)p_global);
+    std::vector<int64_t> gsize_all((size_t)G, 0);
     gsize.assign((size_t)G, 0);
-    for (int64_t j = 0; j < p; ++j) { grp[(size_t)j] = group1[j] - 1; ++gsize[(size_t)grp[(size_t)j]]; }
+    for (int64_t j = 0; j < p_global; ++j) {
+        grp[(size_t)j] = group1[j] - 1;
+        ++gsize_all[(size_t)grp[(size_t)j]];
+        if (j >= j0 && j < j0 + p) ++gsize[(size_t)grp[(size_t)j]];
+    }
     if (ks_vector)
         for (int g = 0; g < G; ++g)
-            IHTB_CHECK(gsize[(size_t)g] > ks[(size_t)g], IHTB_EDOMAIN,
+            IHTB_CHECK(gsize_all[(size_t)g] > ks[(size_t)g], IHTB_EDOMAIN,
                        "Maximum predictors for group " + std::to_string(g + 1) + " was " + std::to_string(ks[(size_t)g]) +
-                           " but there are only " + std::to_string(gsize[(size_t)g]) +
+                           " but there are only " + std::to_string(gsize_all[(size_t)g]) +
                            " predictors is this group. Please choose a smaller number.");
     std::vector<int64_t> gptr((size_t)G + 1, 0), order((size_t)p);
     for (int g = 0; g < G; ++g) gptr[(size_t)g + 1] = gptr[(size_t)g] + gsize[(size_t)g];
     {
         std::vector<int64_t> fill(gptr.begin(), gptr.end() - 1);
-        for (int64_t j = 0; j < p; ++j) order[(size_t)fill[(size_t)grp[(size_t)j]]++] = j;
+        for (int64_t j = 0; j < p; ++j) order[(size_t)fill[(size_t)grp[(size_t)(j0 + j)]]++] = j;      // LOCAL column indices
     }
     goff.assign((size_t)G + 1, 0);
     lcap = 1;
     for (int g = 0; g < G; ++g) {
-        const int64_t len = std::min<int64_t>(2 * k_of(g, kscalar) + GT_EXTRA, gsize[(size_t)g]);
-        goff[(size_t)g + 1] = goff[(size_t)g] + len;
-        lcap = std::max(lcap, len);
+        const int64_t want = 2 * k_of(g, kscalar) + GT_EXTRA;
+        goff[(size_t)g + 1] = goff[(size_t)g] + std::min<int64_t>(want, gsize[(size_t)g]);
+        lcap = std::max(lcap, std::min<int64_t>(want, gsize_all[(size_t)g]));      // the same on every rank
     }
     const int64_t L = std::max<int64_t>(goff[(size_t)G], 1);
-    d_order.alloc((size_t)p); d_gptr.alloc((size_t)G + 1); d_goff.alloc((size_t)G + 1);
+    d_order.alloc((size_t)std::max<int64_t>(p, 1)); d_gptr.alloc((size_t)G + 1); d_goff.alloc((size_t)G + 1);
     d_gidx.alloc((size_t)L); d_gT.alloc(2 * (size_t)G + 1); h_gT.alloc(2 * (size_t)G + 1);
     std::vector<double> smax((size_t)G, 0.0);
-    for (int64_t j = 0; j < p; ++j) smax[(size_t)grp[(size_t)j]] = std::max(smax[(size_t)grp[(size_t)j]], h_sinv[j]);
+    for (int64_t j = 0; j < p; ++j) {
+        double& m = smax[(size_t)grp[(size_t)(j0 + j)]];
+        m = std::max(m, h_sinv[j]);
+    }
     d_smax.alloc((size_t)G);
     IHTB_CUDA(cudaMemcpy(d_smax.p, smax.data(), (size_t)G * sizeof(double), cudaMemcpyHostToDevice));
     IHTB_CUDA(cudaMemcpy(d_order.p, order.data(), (size_t)p * sizeof(int64_t), cudaMemcpyHostToDevice));
@@ -191,6 +201,19 @@ void group_topk(GroupCtx& c, const double* d_dfa, const double* d_sinv, const do
     IHTB_LAUNCH(k_group_topk, c.G, GT_THREADS, 0, s, d_dfa, d_sinv, d_scal, bound_coef, host_bound, c.d_order.p,
                 c.d_gptr.p, c.d_goff.p, c.ks_vector ? c.d_ks.p : (const int64_t*)nullptr, kscalar, c.d_smax.p, c.G,
                 c.d_gidx.p, c.d_gT.p);
+}
+
+// sharded exchange block: [global index or -1 | bits of the exact value] for `slots` gathered columns
+__global__ void k_group_pack(const int64_t* __restrict__ oidx, const double* __restrict__ oval, int64_t slots,
+                             int64_t j0, int64_t* __restrict__ block) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= slots) return;
+    const int64_t j = oidx[t];
+    block[t] = j >= 0 ? j + j0 : -1;
+    block[slots + t] = j >= 0 ? __double_as_longlong(oval[t]) : 0;
+}
+void group_pack(const int64_t* d_oidx, const double* d_oval, int64_t slots, int64_t j0, int64_t* d_block, cudaStream_t s) {
+    if (slots) IHTB_LAUNCH(k_group_pack, (unsigned)ceil_div(slots, 128), 128, 0, s, d_oidx, d_oval, slots, j0, d_block);
 }
 
 void group_take(GroupCtx& c, int n, cudaStream_t s) {

@@ -51,6 +51,15 @@ same = (res.iter == ref.iter and np.array_equal(np.flatnonzero(res.beta), np.fla
         and np.allclose(res.beta, ref.beta, rtol=1e-9, atol=1e-12) and np.allclose(res.c, ref.c, rtol=1e-9))
 ok = ok and same
 print(f"rank {rank} init_beta: sharded iter={res.iter} full iter={ref.iter} same={same}", flush=True)
+blocks = np.arange(p) // 333 + 1            # groups that straddle the shard boundary
+for kw in ({"k": 2, "J": 4}, {"k": [2] * int(blocks.max()), "J": 3}):
+    res = m.fit_iht(y, g_loc, z, group=blocks, comm=comm, p_global=p, **kw)
+    ref = m.fit_iht(y, g_full, z, group=blocks, **kw)
+    same = (res.iter == ref.iter and np.array_equal(np.flatnonzero(res.beta), np.flatnonzero(ref.beta))
+            and np.allclose(res.beta, ref.beta, rtol=1e-9, atol=1e-12))
+    ok = ok and same
+    print(f"rank {rank} groups {'ks' if not np.isscalar(kw['k']) else 'k'}: sharded iter={res.iter} full iter={ref.iter} "
+          f"same={same} nnz={np.count_nonzero(res.beta)}", flush=True)
 yb, zb, *_ = synth.simulate_response(56, n, p, k, "Bernoulli", geno_seed=55)
 res = m.fit_iht(yb, g_loc, zb, k=k + 1, d="Bernoulli", l="LogitLink", debias=True, comm=comm, p_global=p)
 ref = m.fit_iht(yb, g_full, zb, k=k + 1, d="Bernoulli", l="LogitLink", debias=True)
