@@ -92,3 +92,27 @@ def test_argument_checks_mirror_reference_asserts():
     with pytest.raises(AssertionError):
         api._check_args(k=1, max_iter=10, max_step=3, tol=1e-17)
     assert m.canonicallink("NegativeBinomial") == "LogLink" and m.canonicallink("Bernoulli") == "LogitLink"
+
+
+def test_wrapper_parsers_without_gpu(tmp_path):
+    """`parse_covariates` (src/wrapper.jl:228-247) and the .fam phenotype reader (:170-191) are pure host code."""
+    import mendeliht_jl_b200 as m
+    from mendeliht_jl_b200 import api
+    from conftest import GOLDEN
+    z = m.parse_covariates(os.path.join(GOLDEN, "covariates.txt"))
+    raw = np.loadtxt(os.path.join(GOLDEN, "covariates.txt"), delimiter=",")
+    assert np.all(z[:, 0] == 1)                                   # the intercept column is never standardised
+    np.testing.assert_allclose(z[:, 1].mean(), 0.0, atol=1e-12)
+    np.testing.assert_allclose(z[:, 1].std(ddof=1), 1.0, rtol=1e-12)
+    np.testing.assert_allclose(z[:, 1], (raw[:, 1] - raw[:, 1].mean()) / raw[:, 1].std(ddof=1), rtol=1e-12)
+    z_excl = m.parse_covariates(os.path.join(GOLDEN, "covariates.txt"), exclude_std_idx=[2])
+    np.testing.assert_array_equal(z_excl[:, 1], raw[:, 1])
+    fam = tmp_path / "t.fam"
+    fam.write_text("f1 i1 0 0 1 1.5\nf2 i2 0 0 2 -9\nf3 i3 0 0 1 NA\nf4 i4 0 0 2 2.5\n")
+    y = api._read_fam_phenotype(str(fam))
+    np.testing.assert_allclose(y, [1.5, 2.0, 2.0, 2.5])          # missing -> mean of the observed
+    w = np.array([0.5, 0.1, 0.01])
+    assert m.canonicallink("NegativeBinomial") == "LogLink" and m.canonicallink("Bernoulli") == "LogitLink"
+    assert m.allocate_fold_and_k(2, [3, 5]) == [(1, 3), (1, 5), (2, 3), (2, 5)]
+    with pytest.raises(AssertionError):
+        api._check_args(5, 10, 3, 0.0)
