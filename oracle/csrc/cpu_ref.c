@@ -62,6 +62,122 @@ void cpu_col_stats(const uint8_t* bed, int64_t n, int64_t p, int64_t stride, dou
     }
 }
 
+/* ---- SIMD column dot for the CPU baseline ---------------------------------------------------------------------
+ * sum_i dosage_ij v_i over the first nb packed bytes of a column (code 01 counts 0) and, separately, the sum of v over
+ * the missing samples (the mean-imputation term mu_j * sum_{missing} v_i is added by the caller).  Same decode + FMA
+ * per genotype as SnpArrays' SnpLinAlg kernels (LoopVectorization-tiled in the reference), written with explicit
+ * AVX2 / AVX-512 intrinsics and dispatched at run time, because gcc does not vectorise the table-lookup loop below.
+ * FP64 accumulation throughout; only the order of the additions differs from the scalar loop. */
+#include <immintrin.h>
+
+static inline double miss16(uint32_t w, const double* vv) {      /* w: 16 bits = 8 samples; sum of v over codes 01 */
+    uint32_t m = w & ~(w >> 1) & 0x5555u;
+    double s = 0.0;
+    while (m) {
+        int bit = __builtin_ctz(m);
+        s += vv[bit >> 1];
+        m &= m - 1;
+    }
+    return s;
+}
+
+__attribute__((target("avx2,fma")))
+static double col_dot_avx2(const uint8_t* col, const double* v, int64_t nb, double* miss_sum) {
+    const __m256i sh = _mm256_setr_epi32(0, 2, 4, 6, 8, 10, 12, 14);
+    const __m256i three = _mm256_set1_epi32(3);
+    const __m256 tab = _mm256_setr_ps(0.f, 0.f, 1.f, 2.f, 0.f, 0.f, 1.f, 2.f);
+    __m256d a0 = _mm256_setzero_pd(), a1 = _mm256_setzero_pd(), a2 = _mm256_setzero_pd(), a3 = _mm256_setzero_pd();
+    double ms = 0.0;
+    int64_t b = 0;
+    for (; b + 4 <= nb; b += 4) {
+        uint32_t w0 = (uint32_t)col[b] | ((uint32_t)col[b + 1] << 8);
+        uint32_t w1 = (uint32_t)col[b + 2] | ((uint32_t)col[b + 3] << 8);
+        const double* vv = v + 4 * b;
+        if ((w0 & ~(w0 >> 1) & 0x5555u) | (w1 & ~(w1 >> 1) & 0x5555u)) ms += miss16(w0, vv) + miss16(w1, vv + 8);
+        __m256i c0 = _mm256_and_si256(_mm256_srlv_epi32(_mm256_set1_epi32((int)w0), sh), three);
+        __m256i c1 = _mm256_and_si256(_mm256_srlv_epi32(_mm256_set1_epi32((int)w1), sh), three);
+        __m256 d0 = _mm256_permutevar_ps(tab, c0), d1 = _mm256_permutevar_ps(tab, c1);
+        a0 = _mm256_fmadd_pd(_mm256_cvtps_pd(_mm256_castps256_ps128(d0)), _mm256_loadu_pd(vv), a0);
+        a1 = _mm256_fmadd_pd(_mm256_cvtps_pd(_mm256_extractf128_ps(d0, 1)), _mm256_loadu_pd(vv + 4), a1);
+        a2 = _mm256_fmadd_pd(_mm256_cvtps_pd(_mm256_castps256_ps128(d1)), _mm256_loadu_pd(vv + 8), a2);
+        a3 = _mm256_fmadd_pd(_mm256_cvtps_pd(_mm256_extractf128_ps(d1, 1)), _mm256_loadu_pd(vv + 12), a3);
+    }
+    __m256d t = _mm256_add_pd(_mm256_add_pd(a0, a1), _mm256_add_pd(a2, a3));
+    double lanes[4];
+    _mm256_storeu_pd(lanes, t);
+    double acc = (lanes[0] + lanes[1]) + (lanes[2] + lanes[3]);
+    for (; b < nb; ++b) {
+        uint32_t byte = col[b];
+        for (int s = 0; s < 4; ++s) {
+            uint32_t code = (byte >> (2 * s)) & 3u;
+            double x = v[4 * b + s];
+            if (code == 1u) ms += x; else if (code == 2u) acc += x; else if (code == 3u) acc += 2.0 * x;
+        }
+    }
+    *miss_sum = ms;
+    return acc;
+}
+
+__attribute__((target("avx512f,avx512bw,avx512dq,avx2,fma")))
+static double col_dot_avx512(const uint8_t* col, const double* v, int64_t nb, double* miss_sum) {
+    const __m512i sh = _mm512_setr_epi32(0, 2, 4, 6, 8, 10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30);
+    const __m512i three = _mm512_set1_epi32(3);
+    const __m512 tab = _mm512_setr_ps(0.f, 0.f, 1.f, 2.f, 0.f, 0.f, 1.f, 2.f, 0.f, 0.f, 1.f, 2.f, 0.f, 0.f, 1.f, 2.f);
+    __m512d a0 = _mm512_setzero_pd(), a1 = _mm512_setzero_pd(), a2 = _mm512_setzero_pd(), a3 = _mm512_setzero_pd();
+    double ms = 0.0;
+    int64_t b = 0;
+    for (; b + 8 <= nb; b += 8) {
+        uint32_t w0, w1;
+        memcpy(&w0, col + b, 4); memcpy(&w1, col + b + 4, 4);
+        const double* vv = v + 4 * b;
+        if ((w0 & ~(w0 >> 1) & 0x55555555u) | (w1 & ~(w1 >> 1) & 0x55555555u))
+            ms += miss16(w0 & 0xFFFFu, vv) + miss16(w0 >> 16, vv + 8) + miss16(w1 & 0xFFFFu, vv + 16) + miss16(w1 >> 16, vv + 24);
+        __m512i c0 = _mm512_and_si512(_mm512_srlv_epi32(_mm512_set1_epi32((int)w0), sh), three);
+        __m512i c1 = _mm512_and_si512(_mm512_srlv_epi32(_mm512_set1_epi32((int)w1), sh), three);
+        __m512 d0 = _mm512_permutexvar_ps(c0, tab), d1 = _mm512_permutexvar_ps(c1, tab);
+        a0 = _mm512_fmadd_pd(_mm512_cvtps_pd(_mm512_castps512_ps256(d0)), _mm512_loadu_pd(vv), a0);
+        a1 = _mm512_fmadd_pd(_mm512_cvtps_pd(_mm512_extractf32x8_ps(d0, 1)), _mm512_loadu_pd(vv + 8), a1);
+        a2 = _mm512_fmadd_pd(_mm512_cvtps_pd(_mm512_castps512_ps256(d1)), _mm512_loadu_pd(vv + 16), a2);
+        a3 = _mm512_fmadd_pd(_mm512_cvtps_pd(_mm512_extractf32x8_ps(d1, 1)), _mm512_loadu_pd(vv + 24), a3);
+    }
+    double acc = _mm512_reduce_add_pd(_mm512_add_pd(_mm512_add_pd(a0, a1), _mm512_add_pd(a2, a3)));
+    for (; b < nb; ++b) {
+        uint32_t byte = col[b];
+        for (int s = 0; s < 4; ++s) {
+            uint32_t code = (byte >> (2 * s)) & 3u;
+            double x = v[4 * b + s];
+            if (code == 1u) ms += x; else if (code == 2u) acc += x; else if (code == 3u) acc += 2.0 * x;
+        }
+    }
+    *miss_sum = ms;
+    return acc;
+}
+
+/* 0: scalar table loop, 1: AVX2, 2: AVX-512 (env IHTCPU_SIMD=0/1/2 overrides the detection) */
+static int g_simd_level = -1;
+static int simd_level(void) {
+    int level = g_simd_level;
+    if (level < 0) {
+        int l = 0;
+        __builtin_cpu_init();
+        if (__builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma")) l = 1;
+        if (l == 1 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+            __builtin_cpu_supports("avx512dq")) l = 2;
+        const char* e = getenv("IHTCPU_SIMD");
+        if (e && *e >= '0' && *e <= '2' && (*e - '0') <= l) l = *e - '0';
+        level = g_simd_level = l;
+    }
+    return level;
+}
+int cpu_simd_level(void) { return simd_level(); }
+/* tests: force a lower level (never above what the CPU supports); returns the level in effect */
+int cpu_set_simd_level(int l) {
+    g_simd_level = -1;
+    int max = simd_level();
+    if (l >= 0 && l < max) g_simd_level = l;
+    return g_simd_level;
+}
+
 /* out_j = sinv_j * (sum_i gimp_ij v_i - mu_j * sum_i v_i) for m right-hand sides (V is n x m column-major) */
 void cpu_xt_v(const uint8_t* bed, int64_t n, int64_t p, int64_t stride, const double* mu, const double* sinv,
               const double* V, int64_t m, double* out) {
@@ -70,10 +186,21 @@ void cpu_xt_v(const uint8_t* bed, int64_t n, int64_t p, int64_t stride, const do
         double vsum = 0.0;
         for (int64_t i = 0; i < n; ++i) vsum += v[i];
         const int64_t nfull = n >> 2;
+        const int simd = simd_level();
 #pragma omp parallel for schedule(static)
         for (int64_t j = 0; j < p; ++j) {
             const uint8_t* col = bed + j * stride;
             const double mj = mu[j];
+            if (simd > 0) {
+                double ms = 0.0;
+                double acc = simd == 2 ? col_dot_avx512(col, v, nfull, &ms) : col_dot_avx2(col, v, nfull, &ms);
+                for (int64_t i = 4 * nfull; i < n; ++i) {
+                    uint32_t code = (col[i >> 2] >> (2 * (i & 3))) & 3u;
+                    if (code == 1u) ms += v[i]; else if (code == 2u) acc += v[i]; else if (code == 3u) acc += 2.0 * v[i];
+                }
+                out[j + t * p] = sinv[j] * ((acc + mj * ms) - mj * vsum);
+                continue;
+            }
             /* per-column 4-entry dosage table; code 01 (missing) is imputed with the column mean */
             const double tab[4] = {0.0, mj, 1.0, 2.0};
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -95,16 +222,26 @@ void cpu_xt_v(const uint8_t* bed, int64_t n, int64_t p, int64_t stride, const do
 /* out_i = sum_c x[i, idx_c] * coef_c with x_ij = ((missing ? mu : g) - mu) * sinv, ascending c */
 void cpu_x_support(const uint8_t* bed, int64_t n, int64_t stride, const double* mu, const double* sinv,
                    const int64_t* idx, int64_t k, const double* coef, double* out) {
-#pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < n; ++i) out[i] = 0.0;
+    /* one parallel region over sample blocks; inside a block the columns are added in ascending order, so every
+     * out[i] sees the same sequence of additions as a column-by-column loop */
+    double* tabs = (double*)malloc((size_t)(k > 0 ? k : 1) * 4 * sizeof(double));
     for (int64_t c = 0; c < k; ++c) {
         const int64_t j = idx[c];
-        const uint8_t* col = bed + j * stride;
         const double mj = mu[j], sj = sinv[j], cj = coef[c];
-        double tab[4];
         const double g[4] = {0.0, mj, 1.0, 2.0};
-        for (int q = 0; q < 4; ++q) tab[q] = ((g[q] - mj) * sj) * cj;
-#pragma omp parallel for schedule(static)
-        for (int64_t i = 0; i < n; ++i) out[i] += tab[(col[i >> 2] >> (2 * (i & 3))) & 3u];
+        for (int q = 0; q < 4; ++q) tabs[4 * c + q] = ((g[q] - mj) * sj) * cj;
     }
+    const int64_t blk = 4096;                       /* multiple of 4: a block starts on a byte boundary */
+    const int64_t nblk = (n + blk - 1) / blk;
+#pragma omp parallel for schedule(static)
+    for (int64_t bi = 0; bi < nblk; ++bi) {
+        const int64_t i0 = bi * blk, i1 = (i0 + blk < n) ? i0 + blk : n;
+        for (int64_t i = i0; i < i1; ++i) out[i] = 0.0;
+        for (int64_t c = 0; c < k; ++c) {
+            const uint8_t* col = bed + idx[c] * stride;
+            const double* tab = tabs + 4 * c;
+            for (int64_t i = i0; i < i1; ++i) out[i] += tab[(col[i >> 2] >> (2 * (i & 3))) & 3u];
+        }
+    }
+    free(tabs);
 }

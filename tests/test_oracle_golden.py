@@ -277,3 +277,25 @@ def test_oracle_regression_next_tier_options(normal_data, normal_oracle):
         np.testing.assert_allclose(got["beta"], want["beta"], rtol=1e-9, err_msg=name)
         np.testing.assert_allclose(got["c"], want["c"], rtol=1e-9, err_msg=name)
         assert abs(got["logl"] - want["logl"]) <= 1e-9 * abs(want["logl"]), name
+
+
+def test_cpu_baseline_simd_kernels_agree_with_scalar():
+    """oracle/csrc/cpu_ref.c: the AVX2 / AVX-512 column dots of the CPU baseline equal the scalar table loop (FP64
+    accumulation, different addition order) and the numpy oracle, including missing genotypes and ragged n."""
+    from oracle import cpu as ocpu
+    from mendeliht_jl_b200 import synth
+    lib = ocpu.load()
+    rng = np.random.default_rng(4)
+    for n, p, miss in ((1003, 300, 0.02), (4099, 64, 0.0), (37, 9, 0.2)):
+        bed = synth.packed_columns(11, n, np.arange(p), miss)
+        x = ocpu.PackedSnpLinAlgCPU(bed, n)
+        v = rng.normal(size=n)
+        want = snp.SnpLinAlgOracle(bed, n).xt_v(v)
+        top = lib.cpu_set_simd_level(-1)
+        outs = []
+        for level in range(top + 1):
+            assert lib.cpu_set_simd_level(level) == level
+            outs.append(x.xt_v(v))
+        lib.cpu_set_simd_level(-1)
+        for o in outs:
+            np.testing.assert_allclose(o, want, rtol=0, atol=1e-11 * np.abs(want).max())
