@@ -31,7 +31,7 @@ P_PER_GPU = int(os.environ.get("IHTB_BENCH_P", 500_000))
 K_SPARSITY = 20
 SEED = 2024
 DIST, LINK = "Bernoulli", "LogitLink"
-CPU_SAMPLE_COLS = 40_000
+CPU_SAMPLE_COLS = 100_000
 # One unit of work = one IHT iteration over one 50k x 500k shard.  At N=1 that is an IHT iteration of configs[1]; at N>1
 # (weak scaling, one shard per GPU) the job performs N shard-iterations per global iteration.
 UNIT = "iterations/s (x 500k-SNP shards)"
