@@ -140,6 +140,39 @@ function fit_iht(y::AbstractVector{Float64}, x::B200SnpLinAlg, z::AbstractVecOrM
     end
 end
 
+"""
+Multivariate (MvNormal) fit: same call as the reference, `fit_iht(Y, Transpose(xla), Z; k)` with Y r x n and Z q x n
+(src/fit.jl:60-118, src/multivariate.jl); returns `mIHTResult`.  The library wants samples as rows (n x r, n x q).
+"""
+function fit_iht(Y::AbstractMatrix{Float64}, xt::Transpose{Float64,B200SnpLinAlg}, Z::AbstractVecOrMat{Float64};
+                 k::Int=10, zkeep::BitVector=trues(size(Z, 1)), init_beta::Bool=false, debias::Bool=false,
+                 tol::Float64=1e-4, max_iter::Int=200, min_iter::Int=5, max_step::Int=3, kwargs...)
+    debias && error("Currently the debiasing routine for multivariate IHT is broken, sorry!")   # src/multivariate.jl:570
+    x = xt.parent
+    r, n = size(Y)
+    Zm = Z isa AbstractVector ? reshape(Z, 1, :) : Matrix(Z)
+    q = size(Zm, 1)
+    (n == x.n == size(Zm, 2)) || throw(DimensionMismatch("number of samples in y, x, and z = $n, $(x.n), $(size(Zm, 2)) are not equal"))
+    all(zkeep) || error("multivariate zkeep with false entries is not supported")
+    Yc = Matrix(transpose(Y)); Zc = Matrix(transpose(Zm))                  # n x r, n x q column-major
+    cfg = Ref(Cfg(0, 0, k, 1.0, tol, max_iter, min_iter, max_step, 0, 0, 0))
+    fh = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ihtb_mvfit_create, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ref{Cfg}, Ref{Ptr{Cvoid}}),
+                x.handle, Yc, r, Zc, q, cfg, fh))
+    try
+        check(ccall((init_beta ? :ihtb_mvfit_init_beta : :ihtb_mvfit_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), fh[], C_NULL))
+        res = CResult()
+        check(ccall((:ihtb_mvfit_run, LIB), Int32, (Ptr{Cvoid}, Ref{CResult}, Ptr{Cvoid}, Int64), fh[], res, C_NULL, 0))
+        B = zeros(r, x.p); C = zeros(r, q); Σ = zeros(r, r); σg = zeros(r)
+        check(ccall((:ihtb_mvfit_get, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    fh[], B, C, Σ, σg))
+        return MendelIHT.mIHTResult(res.time, res.logl, res.iter, B, C, k, r, Σ, σg)   # field order: src/data_structures.jl:263-273
+    finally
+        ccall((:ihtb_mvfit_destroy, LIB), Int32, (Ptr{Cvoid},), fh[])
+    end
+end
+
 "cv_iht (src/cross_validation.jl:60-131): one device workspace, the (fold, k) grid run back to back."
 function cv_iht(y::AbstractVector{Float64}, x::B200SnpLinAlg, z::AbstractVecOrMat{Float64};
                 d::Distribution=Normal(), l::Link=IdentityLink(), path::AbstractVector{<:Integer}=1:20, q::Int=5,
