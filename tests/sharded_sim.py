@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 
 from oracle import glm
-from oracle.iht import IHTTrace, fit_iht_loop
+from oracle.iht import IHTTrace, fit_iht_loop, project_group_sparse
 
 
 def _allreduce(a):
@@ -19,8 +19,9 @@ def _allreduce(a):
 class ShardedIHT:
     """Same state machine as oracle.iht.IHTVariable (memory-efficient branch), sharded by columns."""
 
-    def __init__(self, x_local, j0, p_global, z, y, k, d, l):
+    def __init__(self, x_local, j0, p_global, z, y, k, d, l, J=1, group=None):
         self.x, self.j0, self.p, self.pl = x_local, j0, p_global, x_local.shape[1]
+        self.J, self.group = J, (None if group is None else np.asarray(group, dtype=np.int64))   # 1-based ids, p_global
         self.y = np.asarray(y, float); self.z = z.reshape(-1, 1) if z.ndim == 1 else z
         self.n, self.q, self.k, self.d, self.l = self.y.shape[0], self.z.shape[1], k, d, l
         self.est_r, self.nb_r = "None", 1.0
@@ -49,6 +50,37 @@ class ShardedIHT:
         allb = [torch.zeros(self.k, dtype=torch.int64) for _ in range(self.world)]
         dist.all_gather(allb, torch.from_numpy(buf))
         cand = np.concatenate([b.numpy() for b in allb] + [np.asarray(extra_idx, dtype=np.int64)])
+        return np.unique(cand[cand >= 0])
+
+    def group_candidates(self):
+        """Doubly sparse fits (fit.cu select_groups): every rank lists, per group, its 2k largest local |df| and the
+        sum T of its k largest df^2; the bounds are gathered and combined (lower = max over ranks, upper = sum over
+        ranks), the groups that can reach the J best norms are chosen identically on every rank, and their local lists
+        are all-gathered."""
+        G = int(self.group.max())
+        gl = self.group[self.j0:self.j0 + self.pl]
+        lists, T = [], np.zeros(G)
+        for g in range(1, G + 1):
+            mem = np.flatnonzero(gl == g)
+            order = mem[np.lexsort((mem, -np.abs(self.df_local[mem])))]
+            lists.append(order[:2 * self.k] + self.j0)
+            T[g - 1] = float(np.sum(self.df_local[order[:self.k]] ** 2))
+        allT = [torch.zeros(G, dtype=torch.float64) for _ in range(self.world)]
+        dist.all_gather(allT, torch.from_numpy(T))
+        TL = np.max([t.numpy() for t in allT], axis=0); TU = np.sum([t.numpy() for t in allT], axis=0)
+        has = np.zeros(G, bool); has[self.group[np.flatnonzero(self.b0)] - 1] = True
+        chosen = list(np.flatnonzero(has))
+        lows = TL[~has]
+        if lows.size and self.J > 0:
+            thr = np.sort(lows)[-min(self.J, lows.size)]
+            chosen += [g for g in np.flatnonzero(~has) if TU[g] >= thr]
+        width = 2 * self.k * max(len(chosen), 1)
+        buf = np.full(width, -1, dtype=np.int64)
+        mine = np.concatenate([lists[g] for g in chosen]) if chosen else np.zeros(0, dtype=np.int64)
+        buf[:mine.size] = mine
+        allb = [torch.zeros(width, dtype=torch.int64) for _ in range(self.world)]
+        dist.all_gather(allb, torch.from_numpy(buf))
+        cand = np.concatenate([b.numpy() for b in allb])
         return np.unique(cand[cand >= 0])
 
     # ---- the oracle's interface ---------------------------------------------------------------
@@ -112,6 +144,17 @@ class ShardedIHT:
 
     def iht_gradstep(self, eta):
         supp0 = np.flatnonzero(self.b0)
+        if self.group is not None:
+            if self.use_sparse_df:
+                cand = np.unique(np.concatenate([supp0, np.fromiter(self.df_sparse, dtype=np.int64)]))
+            else:
+                cand = np.unique(np.concatenate([supp0, self.group_candidates()])).astype(np.int64)
+            self.b = np.zeros(self.p)
+            self.b[cand] = self.b0[cand] + eta * self.df_at(cand)
+            project_group_sparse(self.b, self.group, self.J, self.k)       # entries outside `cand` cannot survive
+            self.c = self.c0 + eta * self.df2
+            self.idx = self.b != 0; self.idc = self.c != 0
+            return
         if self.use_sparse_df:
             cand = np.unique(np.concatenate([supp0, np.fromiter(self.df_sparse, dtype=np.int64)]))
         else:
@@ -147,8 +190,8 @@ class ShardedIHT:
         self.mu = glm.linkinv(self.l, self.xb)
 
 
-def fit_sharded(y, x_local, j0, p_global, z, k, d, l, max_iter=200):
-    v = ShardedIHT(x_local, j0, p_global, z, y, k, d, l)
+def fit_sharded(y, x_local, j0, p_global, z, k, d, l, max_iter=200, J=1, group=None):
+    v = ShardedIHT(x_local, j0, p_global, z, y, k, d, l, J, group)
     v.init_iht_indices(np.ones(v.n, bool))
     tr = IHTTrace()
     best, it = fit_iht_loop(v, max_iter=max_iter, trace=tr)

@@ -61,6 +61,20 @@ def w_sharded_fit(rank):
     return out
 
 
+def w_sharded_group_fit(rank):
+    from mendeliht_jl_b200 import parallel
+    from oracle import glm, iht, snp
+    import sharded_sim
+    y, z, bed, n, p, k = _data(glm.NORMAL, seed=17, n=500, p=800, k=4)
+    group = np.arange(p) // 90 + 1                   # 9 groups; one of them straddles the shard boundary at 400
+    j0, pl = parallel.shard_range(p, WORLD, rank)
+    x_loc = snp.SnpLinAlgOracle(bed[j0:j0 + pl], n)
+    v, best, it, tr = sharded_sim.fit_sharded(y, x_loc, j0, p, z, 2, glm.NORMAL, glm.IDENTITY, J=3, group=group)
+    ref = iht.fit_iht(y, snp.SnpLinAlgOracle(bed, n), z, k=2, J=3, group=group)
+    return (it == ref.iter, bool(np.array_equal(np.flatnonzero(v.best_b), np.flatnonzero(ref.beta))),
+            float(np.max(np.abs(v.best_b - ref.beta))), int(np.count_nonzero(ref.beta)))
+
+
 def w_cv_farm(rank):
     from mendeliht_jl_b200 import parallel, api
     from oracle import cv as ocv, glm, snp
@@ -115,3 +129,12 @@ def test_cv_farm_world2():
     assert res[0][3] == [0, 2, 4, 6, 8] and res[1][3] == [1, 3, 5, 7]
     for rank in range(WORLD):
         assert res[rank][0] and res[rank][1] and res[rank][2]
+
+
+def test_sharded_group_protocol_matches_oracle_world2():
+    """Doubly sparse projection over two shards (groups straddling the boundary): gathered per-group bounds and
+    candidate lists reproduce the single-process oracle."""
+    res = _run("w_sharded_group_fit")
+    for rank in range(WORLD):
+        same_it, same_supp, dbeta, nnz = res[rank]
+        assert same_it and same_supp and dbeta < 1e-10 and 0 < nnz <= 6, (rank, res[rank])
