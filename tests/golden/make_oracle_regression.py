@@ -35,6 +35,14 @@ def run(y, o, kw):
             "beta": [float(v) for v in res.beta[nz]], "c": [float(v) for v in res.c], "sigma_g": float(res.sigma_g)}
 
 
+def cv_case(y, o):
+    """3-fold cross-validation over k = 3, 6, 9 with deterministic folds (oracle/cv.py)."""
+    from oracle import cv as ocv
+    folds = 1 + (np.arange(o.shape[0]) % 3)
+    mse, grid, iters = ocv.cv_iht(y, o, None, path=[3, 6, 9], q=3, folds=folds, return_grid=True)
+    return {"mse": [float(v) for v in mse], "grid": [float(v) for v in grid], "iters": [int(v) for v in iters]}
+
+
 def main():
     n = 1000
     raw = np.fromfile(os.path.join(HERE, "normal.bed"), dtype=np.uint8)[3:]
@@ -42,6 +50,7 @@ def main():
     y = np.loadtxt(os.path.join(HERE, "normal_y.txt"))
     o = snp.SnpLinAlgOracle(bed, n)
     out = {name: run(y, o, kw) for name, kw in cases(bed.shape[0]).items()}
+    out["cv_q3_path_3_6_9"] = cv_case(y, o)
     with open(os.path.join(HERE, "oracle_regression.json"), "w") as f:
         json.dump(out, f, indent=1)
 

@@ -277,6 +277,10 @@ def test_oracle_regression_next_tier_options(normal_data, normal_oracle):
         np.testing.assert_allclose(got["beta"], want["beta"], rtol=1e-9, err_msg=name)
         np.testing.assert_allclose(got["c"], want["c"], rtol=1e-9, err_msg=name)
         assert abs(got["logl"] - want["logl"]) <= 1e-9 * abs(want["logl"]), name
+    cv = mk.cv_case(normal_data["y"], normal_oracle)
+    assert cv["iters"] == frozen["cv_q3_path_3_6_9"]["iters"]
+    np.testing.assert_allclose(cv["grid"], frozen["cv_q3_path_3_6_9"]["grid"], rtol=1e-9)
+    np.testing.assert_allclose(cv["mse"], frozen["cv_q3_path_3_6_9"]["mse"], rtol=1e-9)
 
 
 def test_cpu_baseline_simd_kernels_agree_with_scalar():
