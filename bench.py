@@ -8,9 +8,12 @@ IHT iterations per second = (iterations summed over the K timed fits) / (device 
   e2e   : K x the public `fit_iht(y, x, z)` call with HOST y / z and beta read back (the genotype operator `x` is
           constructed once from HOST .bed bytes before the timed region, like SnpLinAlg in the reference)
   roofline : the X'r sweep kernel timed alone with CUDA events (algorithmic bytes = p*ceil(n/4) + 8n + 24p)
-  cpu_baseline : the CPU restatement of the reference (oracle/, C+OpenMP kernels) on a column sample
+  cpu_baseline : the CPU restatement of the reference (oracle/, C+OpenMP kernels) on the WHOLE workload, one fit; the
+          same run is the parity check: `check.oracle_parity` = identical support / iterations / backtracks per
+          iteration, beta and loglikelihood within 1e-6 relative of the oracle's (outside every timed region)
 `--impl reference` times that CPU restatement as the reference arm (Julia is not installed in this image).
-At N>1 the SNP columns are sharded over the ranks (weak scaling: p = 500,000 columns per GPU).
+At N>1 the SNP columns are sharded over the ranks (weak scaling: p = 500,000 columns per GPU); at N=8 the line also
+carries `north_star`: BASELINE configs[4] (n=500k x p=1M, Normal, k=100, 10 covariates) strong-sharded over the 8 GPUs.
 """
 import argparse
 import json
@@ -31,7 +34,9 @@ P_PER_GPU = int(os.environ.get("IHTB_BENCH_P", 500_000))
 K_SPARSITY = 20
 SEED = 2024
 DIST, LINK = "Bernoulli", "LogitLink"
-CPU_SAMPLE_COLS = 100_000
+CPU_SAMPLE_COLS = 500_000     # the reference arm at N>1 samples the first 500k columns of the N x 500k problem
+DTYPE = "f64 (sweep: f32 LUT partials per 512-sample slab, f64 across slabs; top-k candidates re-scored in f64)"
+PARITY_RTOL = 1e-6
 # One unit of work = one IHT iteration over one 50k x 500k shard.  At N=1 that is an IHT iteration of configs[1]; at N>1
 # (weak scaling, one shard per GPU) the job performs N shard-iterations per global iteration.
 UNIT = "iterations/s (x 500k-SNP shards)"
@@ -92,18 +97,21 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_port_iters_per_sec(n, p_full, k, steps, warmup):
-    """CPU restatement of the reference on a column sample of the same workload; scaled to the full column count
-    (an IHT iteration is dominated by the O(n p) sweep, reference test/fit_profile.ipynb: 77-87 %)."""
+def cpu_port_fit(n, p_full, k, bed=None, steps=1, warmup=0):
+    """CPU restatement of the reference (oracle/) on this workload.  p_full <= CPU_SAMPLE_COLS: the whole problem;
+    otherwise the first CPU_SAMPLE_COLS columns with their own simulated response, scaled by sample/p_full (an IHT
+    iteration is dominated by the O(n p) sweep, reference test/fit_profile.ipynb: 77-87 %).
+    Returns (iterations/s, threads, sample text, ms per fit, last oracle result)."""
     from oracle import cpu as ocpu
     from oracle import glm as oglm
     from oracle import iht as oiht
     from mendeliht_jl_b200 import synth
     ps = min(CPU_SAMPLE_COLS, p_full)
-    bed = ocpu.synth_columns(SEED, n, 0, ps)
+    if bed is None or bed.shape[0] != ps:
+        bed = ocpu.synth_columns(SEED, n, 0, ps)
     x = ocpu.PackedSnpLinAlgCPU(bed, n)
     y, z, _, _, _ = synth.simulate_response(SEED + 1, n, ps, k, DIST, geno_seed=SEED)
-    tot_it, tot_t = 0, 0.0
+    tot_it, tot_t, res = 0, 0.0, None
     for s in range(warmup + steps):
         t0 = time.perf_counter()
         res = oiht.fit_iht(y, x, z, k=k, d=oglm.BERNOULLI, l=oglm.LOGIT)
@@ -111,30 +119,54 @@ def cpu_port_iters_per_sec(n, p_full, k, steps, warmup):
         if s >= warmup:
             tot_it += res.iter
             tot_t += dt
-    v = v_sample = tot_it / tot_t
+    v_sample = tot_it / tot_t
     v = v_sample * ps / p_full
-    sample = (f"fit_iht on n={n} x first {ps} of {p_full} columns ({DIST}, k={k}), {steps} fit(s), "
-              f"{tot_it} iterations in {tot_t:.2f}s = {v_sample:.2f} it/s on the sample, scaled by {ps}/{p_full}")
-    return v, x.threads, sample, tot_t / max(steps, 1) * 1e3
+    what = "the whole workload" if ps == p_full else f"the first {ps} of {p_full} columns (scaled by {ps}/{p_full})"
+    sample = (f"fit_iht on n={n} x {what} ({DIST}, k={k}), {steps} fit(s), {tot_it} iterations in {tot_t:.2f}s "
+              f"= {v_sample:.2f} it/s on {x.threads} threads")
+    return v, x.threads, sample, tot_t / max(steps, 1) * 1e3, res
+
+
+def parity_report(res, ref):
+    """Our fit against the oracle's on the same inputs (SURVEY.md 8c bar: support / iterations exact, values 1e-6)."""
+    nz, rz = np.flatnonzero(res.beta), np.flatnonzero(ref.beta)
+    same_supp = bool(np.array_equal(nz, rz))
+    bt, rbt = [t[1] for t in res.trace], list(ref.trace.backtracks)
+    lg, rlg = np.array([t[0] for t in res.trace]), np.asarray(ref.trace.logl, dtype=np.float64)
+    beta_err = None
+    if same_supp and nz.size:
+        beta_err = float(np.max(np.abs(res.beta[nz] - ref.beta[nz]) / np.abs(ref.beta[nz])))
+    c_err = float(np.max(np.abs(res.c - ref.c) / np.maximum(np.abs(ref.c), 1e-12)))
+    logl_err = float(abs(res.logl - ref.logl) / abs(ref.logl))
+    trace_err = float(np.max(np.abs(lg - rlg) / np.abs(rlg))) if lg.shape == rlg.shape and lg.size else None
+    ok = (same_supp and int(res.iter) == int(ref.iter) and bt == rbt and beta_err is not None
+          and beta_err <= PARITY_RTOL and c_err <= PARITY_RTOL and logl_err <= PARITY_RTOL
+          and trace_err is not None and trace_err <= PARITY_RTOL)
+    return {"oracle_parity": bool(ok), "support_identical": same_supp, "iterations": int(res.iter),
+            "oracle_iterations": int(ref.iter), "backtracks_identical": bt == rbt, "backtracks": int(sum(bt)),
+            "max_rel_err_beta": beta_err, "max_rel_err_c": c_err, "rel_err_logl": logl_err,
+            "max_rel_err_logl_trace": trace_err, "rtol": PARITY_RTOL,
+            "oracle": "oracle.iht.fit_iht over oracle.cpu.PackedSnpLinAlgCPU (C+OpenMP) on the same host .bed bytes"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    v, threads, sample, ms = cpu_port_iters_per_sec(N_SAMPLES, P_PER_GPU * args.gpus, K_SPARSITY, steps,
-                                                    min(args.warmup, 1))
+    # one whole-workload fit at N=1 (about 40 s on 16 cores); at N>1 a 500k-column sample of the N x 500k problem
+    v, threads, sample, ms, _ = cpu_port_fit(N_SAMPLES, P_PER_GPU * args.gpus, K_SPARSITY, steps=1, warmup=0)
+    assert threads > 1 or (os.cpu_count() or 1) == 1, "the CPU reference arm must use all host cores"
     line = {
         "impl": "reference", "metric": "iht_iterations_per_sec", "value": v * args.gpus, "unit": UNIT,
         "global_iterations_per_sec": v,
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+        "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": v * args.gpus, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v * args.gpus, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "Julia/SnpArrays.jl cannot run in this image; this is the C+OpenMP/numpy restatement of the reference "
-                "algorithm (oracle/) on all host cores",
+                "algorithm (oracle/) on all host cores; one step = one whole fit_iht (requested steps/warmup are "
+                "clamped to 1/0 so the run stays within minutes)",
     }
     print(json.dumps(line))
 
@@ -173,7 +205,8 @@ def run_ours(args):
     t0 = time.perf_counter()
     g = m.B200SnpLinAlg.from_bed_columns(bed, n)
     t_upload = time.perf_counter() - t0
-    del bed
+    if args.no_cpu_baseline:
+        del bed
     y, z, true_idx, true_beta, _ = synth.simulate_response(SEED + 1, n, p, k, DIST, geno_seed=SEED)
 
     launches0 = m.launch_count()
@@ -201,7 +234,6 @@ def run_ours(args):
     m._lib.check(lib.ihtb_fit_phase_times(v._h, ph))
     phases = {k: ph[i] / max(iters + args.warmup * (iters // max(args.steps, 1)), 1) * 1e3
               for i, k in enumerate(["stepsize_ms", "gradstep_ms", "xb_glm_ms", "score_sweep_ms"])}
-    beta, c, _, _ = v.get()
     v.close()
 
     # ---- e2e: public API, host buffers in / out every step ----
@@ -213,6 +245,7 @@ def run_ours(args):
         r = m.fit_iht(y, g, z, k=k, d=DIST, l=LINK)
         e_iters += r.iter
     t_e2e = time.perf_counter() - t0
+    beta, c = r.beta, r.c
     clk = clocks.stop()
 
     # ---- roofline: the sweep kernel timed alone ----
@@ -221,34 +254,37 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     abytes = sweep_bytes(n, p)
     achieved = abytes / (mk.value * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = "static: " + tj.get("source", "profiles/sweep_traffic.json") + " (ncu cannot run inside a timed bench)"
         except Exception:
             traffic = None
 
-    # ---- CPU baseline (bounded sample) ----
+    # ---- CPU baseline = the oracle on the whole workload, which is also the parity check (outside every timed region) ----
     cpu = None
-    if not args.no_cpu_baseline:
-        try:
-            cv, threads, sample, _ = cpu_port_iters_per_sec(n, p, k, 1, 0)
-            cpu = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
-        except Exception as e:  # the baseline is a report, not a dependency of the product path
-            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
-
     nz = np.flatnonzero(beta)
+    check = {"support_size": int(nz.size), "true_positives": int(np.intersect1d(nz, true_idx).size),
+             "iterations": iters // args.steps, "oracle_parity": None}
+    if not args.no_cpu_baseline:
+        cv, threads, sample, _, ref = cpu_port_fit(n, p, k, bed=bed, steps=1, warmup=0)
+        del bed
+        cpu = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        check.update(parity_report(r, ref))
+
     line = {
         "metric": "iht_iterations_per_sec", "value": iters / t_value, "unit": UNIT, "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_value / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
         "config": workload_config(1),
         "iterations_per_fit": iters / args.steps, "sweeps_per_fit": sweeps / args.steps,
         "sweep_ms_in_fit": sweep_s / max(sweeps - args.steps, 1) * 1e3,
         "sweep_share_of_step": sweep_s / t_value, "host_phase_ms_per_iteration": phases,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "k_sweep_lut",
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "k_sweep_lut",
                      "algorithmic_bytes_per_launch": abytes, "kernel_ms": mk.value,
                      "sweep_with_epilogue_ms": mt.value, "sweep_with_epilogue_gbs": abytes / (mt.value * 1e-3) / 1e9},
         "e2e": {"value": e_iters / t_e2e, "unit": UNIT,
@@ -261,10 +297,12 @@ def run_ours(args):
         "gpu_launches": int(l_timed),
         "clocks": clk,
         "cpu_baseline": cpu,
-        "check": {"support_size": int(nz.size), "true_positives": int(np.intersect1d(nz, true_idx).size),
-                  "iterations": iters // args.steps},
+        "check": check,
     }
     print(json.dumps(line))
+    if check["oracle_parity"] is False:
+        print("bench.py: the CUDA fit does not match the CPU oracle: " + json.dumps(check), file=sys.stderr)
+        sys.exit(3)
 
 
 def main():

@@ -21,8 +21,24 @@ def load():
             raise ImportError(f"{LIB} missing: run `make -C oracle`")
         lib = C.CDLL(LIB)
         lib.cpu_num_threads.restype = C.c_int
+        lib.cpu_set_num_threads.restype = C.c_int
         _lib = lib
+        # torchrun exports OMP_NUM_THREADS=1 to its workers: the baseline uses every core this process may run on
+        # unless IHTCPU_THREADS says otherwise (round-1 SCALE reference arm ran on one core because of this)
+        set_threads(int(os.environ.get("IHTCPU_THREADS", "0")) or available_cores())
     return _lib
+
+
+def available_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def set_threads(t: int) -> int:
+    """OpenMP threads used by every kernel of the C restatement; returns the count in effect."""
+    return int(load().cpu_set_num_threads(C.c_int(int(t)))) if _lib is not None else int(t)
 
 
 def _p(a, t):
@@ -49,6 +65,20 @@ class PackedSnpLinAlgCPU:
     @property
     def shape(self):
         return (self.n, self.p)
+
+    def columns(self, cols) -> np.ndarray:
+        """x[:, cols] through the getindex formula ((g or mu_j when missing) - mu_j) * sigma_inv_j, n x len(cols);
+        same arithmetic as oracle.snp.SnpLinAlgOracle.dense() on the selected columns."""
+        cols = np.asarray(cols, dtype=np.int64).reshape(-1)
+        out = np.empty((self.n, cols.shape[0]))
+        for t, j in enumerate(cols):
+            b = self.bed[j]
+            codes = np.empty(self.stride * 4, dtype=np.uint8)
+            for s in range(4):
+                codes[s::4] = (b >> (2 * s)) & 3
+            g = np.array([0.0, self.mu[j], 1.0, 2.0])[codes[: self.n]]
+            out[:, t] = (g - self.mu[j]) * self.sigma_inv[j]
+        return out
 
     def xt_v(self, v: np.ndarray) -> np.ndarray:
         v = np.asarray(v, dtype=np.float64)

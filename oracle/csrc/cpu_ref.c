@@ -25,6 +25,17 @@ int cpu_num_threads(void) {
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the CPU baseline must say how many threads it really uses */
+int cpu_set_num_threads(int t) {
+#ifdef _OPENMP
+    if (t >= 1) omp_set_num_threads(t);
+    return omp_get_max_threads();
+#else
+    (void)t;
+    return 1;
+#endif
+}
+
 void cpu_synth(uint64_t seed, int64_t n, int64_t j0, int64_t ncols, double missing_rate, uint8_t* out) {
     const int64_t nbytes = (n + 3) / 4;
     const uint32_t miss_thr = synth_missing_threshold(missing_rate);

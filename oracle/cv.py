@@ -33,8 +33,9 @@ def meanloss(fitloss, q: int, folds):
 
 def cv_iht(y, x, z=None, d=glm.NORMAL, l=glm.IDENTITY, path=range(1, 21), q=5, folds=None,
            zkeep=None, max_iter=100, min_iter=5, nb_r=1.0, return_grid=False, init_beta=False, weight=None,
-           debias=False, J=1, group=None):
-    """`cv_iht` (:60-131), univariate or multivariate by the shape of y."""
+           debias=False, J=1, group=None, combos_todo=None):
+    """`cv_iht` (:60-131), univariate or multivariate by the shape of y.  `combos_todo`: optional subset of grid
+    positions to run (slices of grids too large to run whole on the CPU); the others stay 0."""
     y = np.asarray(y, dtype=np.float64)
     multivariate = y.ndim == 2 and y.shape[0] > 1 and y.shape[1] > 1
     n = x.shape[0]
@@ -50,6 +51,8 @@ def cv_iht(y, x, z=None, d=glm.NORMAL, l=glm.IDENTITY, path=range(1, 21), q=5, f
     mses = np.zeros(len(combos))
     iters = np.zeros(len(combos), dtype=np.int64)
     for i, (fold, k) in enumerate(combos):
+        if combos_todo is not None and i not in combos_todo:
+            continue
         test = folds == fold
         train = ~test
         if multivariate:

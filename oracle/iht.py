@@ -242,7 +242,7 @@ class IHTVariable:
 
         c0 = 0.0
         for j0 in range(0, self.p, 2048):     # column blocks bound the memory of the dense slice
-            xs = self.x.dense()[:, j0:j0 + 2048][cv]
+            xs = self.x.columns(np.arange(j0, min(j0 + 2048, self.p)))[cv]
             icpt, slope = linreg(xs)
             c0 += float(icpt.sum())
             self.b[j0:j0 + 2048] = slope
@@ -362,7 +362,7 @@ class IHTVariable:
         idx = np.flatnonzero(self.idx)
         if idx.size == 0:
             return
-        xk = self.x.dense()[:, idx]
+        xk = self.x.columns(idx)
         self.b[idx] = glm.glm_fit(xk, self.y, self.d, self.l, self.nb_r)
 
     # -- src/utilities.jl:141-247

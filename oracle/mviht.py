@@ -102,7 +102,7 @@ class MvIHTVariable:
             ys = self.Y[j, cv]
             c0 = 0.0
             for j0 in range(0, self.p, 2048):
-                xs = self.x.dense()[:, j0:j0 + 2048][cv]
+                xs = self.x.columns(np.arange(j0, min(j0 + 2048, self.p)))[cv]
                 icpt, slope = linreg_columns(xs, ys)
                 c0 += float(icpt.sum())
                 self.B[j, j0:j0 + 2048] = slope
@@ -152,7 +152,7 @@ class MvIHTVariable:
     # :21-31 (memory-efficient branch: getindex path on the support rows)
     def update_xb(self):
         idx = np.flatnonzero(self.idx)
-        xs = self.x.dense()[:, idx]               # n x |idx|
+        xs = self.x.columns(idx)               # n x |idx|
         self.BX = self.B[:, idx] @ xs.T
         self.CZ = self.C @ self.Z
 
@@ -173,7 +173,7 @@ class MvIHTVariable:
         idx = np.flatnonzero(self.idx)
         dfidx = self.df[:, idx]
         numer = float(np.sum(dfidx ** 2))
-        v = (dfidx @ self.x.dense()[:, idx].T) * self.cv_wts[None, :]
+        v = (dfidx @ self.x.columns(idx).T) * self.cv_wts[None, :]
         self.Gamma = pivoted_cholesky_upper(self.Gamma)
         uv = self.Gamma @ v
         denom = float(np.sum(uv ** 2))

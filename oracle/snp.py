@@ -128,6 +128,10 @@ class SnpLinAlgOracle:
     def getindex(self, i, j):
         return self.dense()[i, j]
 
+    def columns(self, cols) -> np.ndarray:
+        """x[:, cols] through the getindex formula (n x len(cols))."""
+        return self.dense()[:, np.asarray(cols, dtype=np.int64)]
+
     def xt_v(self, v: np.ndarray) -> np.ndarray:
         """mul!(out, Transpose(x), v); v is [n] or [n, m] -> [p] or [p, m]."""
         out = self.gimp.T @ v

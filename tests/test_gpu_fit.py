@@ -15,25 +15,9 @@ from mendeliht_jl_b200 import synth
 from oracle import cv as ocv
 from oracle import glm, iht, snp
 from conftest import GOLDEN
+from parity_helpers import RTOL, compare_fit as _compare, compare_mv_fit as _compare_mv
 
-RTOL = 1e-6
 MODES = [m.SWEEP_FAST, m.SWEEP_EXACT]
-
-
-def _compare(res, ref, rtol=RTOL, check_backtracks=True):
-    assert res.iter == ref.iter
-    assert np.array_equal(np.flatnonzero(res.beta), np.flatnonzero(ref.beta))      # support: exact
-    np.testing.assert_allclose(res.beta, ref.beta, rtol=rtol, atol=1e-12)
-    np.testing.assert_allclose(res.c, ref.c, rtol=rtol, atol=1e-12)
-    if np.isfinite(ref.logl):
-        assert abs(res.logl - ref.logl) <= rtol * abs(ref.logl)
-    else:
-        assert res.logl == ref.logl
-    assert abs(res.sigma_g - ref.sigma_g) <= rtol * abs(ref.sigma_g) + 1e-12
-    if check_backtracks:
-        assert [t[1] for t in res.trace] == ref.trace.backtracks
-        np.testing.assert_allclose([t[2] for t in res.trace], ref.trace.tol, rtol=max(1e-5, 10 * rtol), atol=1e-12)
-    np.testing.assert_allclose([t[0] for t in res.trace], ref.trace.logl, rtol=rtol)
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -231,18 +215,6 @@ def _mv_data(seed, n, p, r, k):
     Cm = rng.normal(size=(r, 2)) * 0.5
     Y = B @ xs.T + Cm @ Z + E
     return bed, Y, Z
-
-
-def _compare_mv(res, ref, rtol=RTOL):
-    assert res.iter == ref.iter
-    assert np.array_equal(res.beta != 0, ref.beta != 0)
-    np.testing.assert_allclose(res.beta, ref.beta, rtol=rtol, atol=1e-12)
-    np.testing.assert_allclose(res.c, ref.c, rtol=rtol, atol=1e-12)
-    assert abs(res.logl - ref.logl) <= rtol * abs(ref.logl)
-    np.testing.assert_allclose(res.Sigma, ref.Sigma, rtol=1e-5, atol=1e-10)
-    np.testing.assert_allclose(res.sigma_g, ref.sigma_g, rtol=rtol)
-    assert [t[1] for t in res.trace] == ref.trace.backtracks
-    np.testing.assert_allclose([t[0] for t in res.trace], ref.trace.logl, rtol=rtol)
 
 
 @pytest.mark.parametrize("mode", MODES)
