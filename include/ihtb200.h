@@ -39,8 +39,12 @@ enum { IHTB_LINK_IDENTITY = 0, IHTB_LINK_LOGIT = 1, IHTB_LINK_LOG = 2, IHTB_LINK
        IHTB_LINK_INVSQ = 8 };
 /* X'v sweep arithmetic.  FAST = FP32 byte-LUT partial sums + FP64 cross-slab sums; the fit then
  * re-scores every top-k candidate exactly in FP64, so support / iteration counts do not depend on it.
- * EXACT = FP64 accumulation throughout (slower kernel; what ihtb_xt_v uses for parity checks). */
-enum { IHTB_SWEEP_FAST = 0, IHTB_SWEEP_EXACT = 1 };
+ * EXACT = FP64 accumulation throughout (slower kernel; what ihtb_xt_v uses for parity checks).
+ * PAIR  = two right-hand sides per pass over the matrix (half2 lookup tables, FP32 sums per slab, FP64 across slabs):
+ *         the skinny multi-trait X'R of MvNormal fits (src/multivariate.jl:85) and two lock-stepped cross-validation
+ *         fits read the matrix once for two vectors.  Error bound 2^-8 ||v - mean||_1 sigma_inv_j per entry; fits still
+ *         re-score their candidates in FP64.  A single (or odd last) right-hand side takes the FAST path. */
+enum { IHTB_SWEEP_FAST = 0, IHTB_SWEEP_EXACT = 1, IHTB_SWEEP_PAIR = 2 };
 
 typedef struct ihtb_geno ihtb_geno;     /* replaces SnpLinAlg{Float64}(s; center, scale, impute) */
 typedef struct ihtb_fit ihtb_fit;       /* replaces IHTVariable{Float64, SnpLinAlg} (src/data_structures.jl:4-43) */

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libihtb200.so")
 
 IHTB_OK, IHTB_EINVAL, IHTB_EDIM, IHTB_EDOMAIN, IHTB_ENUMERIC, IHTB_ECUDA, IHTB_ENOMEM, IHTB_EUNSUPPORTED = (
     0, -1, -2, -3, -4, -5, -6, -7)
-SWEEP_FAST, SWEEP_EXACT = 0, 1
+SWEEP_FAST, SWEEP_EXACT, SWEEP_PAIR = 0, 1, 2
 
 
 class IHTBError(RuntimeError):

@@ -17,7 +17,12 @@ struct Error : std::runtime_error {
 };
 void set_last_error(const std::string& m);
 const std::string& last_error();
-int64_t& launch_counter();
+struct LaunchCounter {        // relaxed atomic: fits on several host threads (multi-device handles) share it
+    int64_t v = 0;
+    LaunchCounter& operator++(int) { __atomic_fetch_add(&v, 1, __ATOMIC_RELAXED); return *this; }
+    operator int64_t() const { return __atomic_load_n(&v, __ATOMIC_RELAXED); }
+};
+LaunchCounter& launch_counter();
 bool debug_sync();   // IHTB_DEBUG_SYNC=1: synchronise and check after every kernel launch
 
 #define IHTB_CUDA(call)                                                                      \
@@ -109,6 +114,17 @@ struct HBuf {
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: set it once per (kernel, device),
+// safely from several host threads (multi-device handles run one host thread per device).  geno.cu keeps the registry.
+bool smem_attr_needed(const void* kernel, int device);
+template <typename K>
+static inline void ensure_dynamic_smem(K kernel, int bytes) {
+    int dev = 0;
+    IHTB_CUDA(cudaGetDevice(&dev));
+    if (!smem_attr_needed(reinterpret_cast<const void*>(kernel), dev)) return;
+    IHTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+}
+
 // ---- genotype handle -----------------------------------------------------------------------
 }  // namespace ihtb
 
@@ -121,7 +137,14 @@ struct ihtb_geno {
     int64_t stride = 0;       // padded bytes per column: multiple of 128 (= 512-sample slabs), zero padded
     // Byte b of column j lives at bed + j*cs_j + (b>>7)*cs_s + (b&127):
     //   column-major: cs_j = stride, cs_s = 128        slab-major tiles: cs_j = 128, cs_s = p*128
+    // quad = 1 (default, "quad-interleaved" slab-major tiles): inside a slab, columns are grouped by four and the 32-bit
+    // words of the four 128-byte chunks are interleaved, so that 16 consecutive bytes hold word w of columns 4q..4q+3:
+    //   bed + (b>>7)*cs_s + (j>>2)*512 + ((b&127)>>2)*16 + (j&3)*4 + (b&3),  cs_s = p4*128, p4 = p rounded up to 4.
+    // One 128-bit load per lane then feeds four columns with lane = word position, which is what the table lookups of
+    // the sweep need (sweep_ldg.cu) -- no shared-memory staging of the genotype stream.
     int64_t cs_j = 0, cs_s = 0;
+    int quad = 0;
+    int64_t p4 = 0;           // columns allocated per slab (p rounded up to a multiple of 4; padding columns are zero)
     int center = 1, scale = 1, impute = 1;
     int sm_count = 148;
     ihtb::DBuf<uint8_t> bed;  // p * stride bytes
@@ -142,16 +165,20 @@ static inline void geno_require_ready(const ihtb_geno* g) {
 struct GenoView {
     const uint8_t* bed;
     int64_t cs_j, cs_s, nbytes, stride, n, p;
+    int quad;
     const double* mu;
     const double* sinv;
     const int32_t* nmiss;
     int impute;
 };
 static inline GenoView geno_view(const ihtb_geno* g) {
-    return GenoView{g->bed.p, g->cs_j, g->cs_s, g->nbytes, g->stride, g->n, g->p, g->mu.p, g->sinv.p, g->nmiss.p,
-                    g->impute};
+    return GenoView{g->bed.p, g->cs_j, g->cs_s, g->nbytes, g->stride, g->n, g->p, g->quad, g->mu.p, g->sinv.p,
+                    g->nmiss.p, g->impute};
 }
+// address of byte b of column j; 32-bit words (4-byte aligned b) are contiguous in every layout
 __device__ __forceinline__ const uint8_t* gv_ptr(const GenoView& g, int64_t j, int64_t b) {
+    if (g.quad)
+        return g.bed + (b >> 7) * g.cs_s + (j >> 2) * 512 + ((b & 127) >> 2) * 16 + (j & 3) * 4 + (b & 3);
     return g.bed + j * g.cs_j + (b >> 7) * g.cs_s + (b & 127);
 }
 

@@ -15,9 +15,18 @@ namespace ihtb {
 static thread_local std::string t_last_error;
 void set_last_error(const std::string& m) { t_last_error = m; }
 const std::string& last_error() { return t_last_error; }
-int64_t& launch_counter() {
-    static int64_t c = 0;
+LaunchCounter& launch_counter() {
+    static LaunchCounter c;
     return c;
+}
+bool smem_attr_needed(const void* kernel, int device) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, int>> done;
+    std::lock_guard<std::mutex> lk(mu);
+    for (const auto& e : done)
+        if (e.first == kernel && e.second == device) return false;
+    done.push_back({kernel, device});
+    return true;
 }
 bool debug_sync() {
     static int v = -1;
@@ -48,9 +57,11 @@ __global__ void k_repack(const uint8_t* __restrict__ staging, int64_t pitch, int
     uint8_t tmp[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) tmp[k] = (16 * v + k < g.nbytes) ? src[k] : (uint8_t)0;
-    uint4 q;
-    memcpy(&q, tmp, 16);
-    *reinterpret_cast<uint4*>(const_cast<uint8_t*>(gv_ptr(g, j0 + c, 16 * v))) = q;
+    uint32_t q[4];
+    memcpy(q, tmp, 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)      // words are the contiguous unit of every layout (gv_ptr)
+        *reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(gv_ptr(g, j0 + c, 16 * v + 4 * k))) = q[k];
 }
 
 // inverse of k_repack for export: out[c][b] = byte b of column j0 + c
@@ -73,8 +84,9 @@ __global__ void k_col_stats(GenoView g, int scale, double* __restrict__ mu, doub
     int64_t nvec = g.stride >> 4;
     int c1 = 0, c2 = 0, cm = 0;
     for (int64_t v = lane; v < nvec; v += 32) {
-        uint4 q = *reinterpret_cast<const uint4*>(gv_ptr(g, j, 16 * v));
-        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t w[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) w[t] = *reinterpret_cast<const uint32_t*>(gv_ptr(g, j, 16 * v + 4 * t));
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             uint32_t lo = w[t] & 0x55555555u, hi = (w[t] >> 1) & 0x55555555u;
@@ -102,8 +114,9 @@ __global__ void k_col_counts(GenoView g, int64_t* __restrict__ out /*[4][p] colu
     int64_t nvec = g.stride >> 4;
     int c1 = 0, c2 = 0, cm = 0;
     for (int64_t v = lane; v < nvec; v += 32) {
-        uint4 q = *reinterpret_cast<const uint4*>(gv_ptr(g, j, 16 * v));
-        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t w[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) w[t] = *reinterpret_cast<const uint32_t*>(gv_ptr(g, j, 16 * v + 4 * t));
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             uint32_t lo = w[t] & 0x55555555u, hi = (w[t] >> 1) & 0x55555555u;
@@ -228,14 +241,17 @@ static ihtb_geno* new_handle(int64_t n, int64_t p, int center, int scale, int im
     g->n = n; g->p = p;
     g->nbytes = (n + 3) / 4;
     g->stride = ceil_div(g->nbytes, 128) * 128;
-    // HBM layout: slab-major 128-byte tiles by default (the sweep then streams contiguous memory);
-    // IHTB_LAYOUT=colmajor keeps PLINK's column-major order (padded stride)
+    // HBM layout (common.cuh): quad-interleaved slab-major tiles by default; IHTB_LAYOUT=tiled keeps plain 128-byte
+    // tiles (the round-1 TMA sweep), IHTB_LAYOUT=colmajor PLINK's column-major order (padded stride, debug only)
     const char* lay = getenv("IHTB_LAYOUT");
-    if (lay && std::string(lay) == "colmajor") { g->cs_j = g->stride; g->cs_s = 128; }
-    else { g->cs_j = 128; g->cs_s = g->p * 128; }
+    g->p4 = (p + 3) / 4 * 4;
+    if (lay && std::string(lay) == "colmajor") { g->cs_j = g->stride; g->cs_s = 128; g->p4 = p; }
+    else if (lay && std::string(lay) == "tiled") { g->cs_j = 128; g->cs_s = g->p * 128; g->p4 = p; }
+    else { g->quad = 1; g->cs_j = 128; g->cs_s = g->p4 * 128; }
     g->center = center; g->scale = scale; g->impute = impute;
     try {
-        g->bed.alloc((size_t)(g->p * g->stride));
+        g->bed.alloc((size_t)(g->p4 * g->stride));
+        if (g->p4 != g->p) IHTB_CUDA(cudaMemset(g->bed.p, 0, (size_t)(g->p4 * g->stride)));   // padding columns
     } catch (...) {
         delete g;
         throw;
@@ -351,7 +367,7 @@ int32_t ihtb_geno_create(const uint8_t* bed_cols, int64_t n, int64_t p, int64_t 
         IHTB_CHECK(col_stride_bytes >= (n + 3) / 4, IHTB_EDIM, "col_stride_bytes is smaller than ceil(n/4)");
         ihtb_geno* g = new_handle(n, p, center, scale, impute);
         try {
-            IHTB_CUDA(cudaMemset(g->bed.p, 0, (size_t)(g->p * g->stride)));
+            IHTB_CUDA(cudaMemset(g->bed.p, 0, (size_t)(g->p4 * g->stride)));
             upload_columns(g, bed_cols, col_stride_bytes, 0, p);
             seal_handle(g);
         } catch (...) {
@@ -368,7 +384,7 @@ int32_t ihtb_geno_create_empty(int64_t n, int64_t p, int32_t center, int32_t sca
         IHTB_CHECK(out, IHTB_EINVAL, "NULL argument");
         ihtb_geno* g = new_handle(n, p, center, scale, impute);
         try {
-            IHTB_CUDA(cudaMemset(g->bed.p, 0, (size_t)(g->p * g->stride)));
+            IHTB_CUDA(cudaMemset(g->bed.p, 0, (size_t)(g->p4 * g->stride)));
         } catch (...) {
             delete g;
             throw;

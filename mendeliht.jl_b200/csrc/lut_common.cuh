@@ -1,0 +1,97 @@
+// Shared pieces of the table-driven FAST sweeps (sweep_lut.cu: TMA stage ring; sweep_ldg.cu: register-prefetched
+// global loads): PTX wrappers and the per-slab table build.
+#pragma once
+#include "common.cuh"
+
+namespace ihtb {
+
+constexpr int LUT_TABLE_BYTES = 131072;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W_%=;\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+template <int NT>
+__device__ __forceinline__ void consumer_bar() {   // named barrier 1 over the NT consumer threads
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
+
+// build T for one slab; executed by the NT (256 or 512) consumer threads
+template <int NT>
+__device__ __forceinline__ void lut_build(uint32_t tab, const double* __restrict__ v, double vbar, int64_t n,
+                                          int64_t slab, int tid) {
+    // thread -> (part, group): group = t*32 + w (128 groups); part selects a range of the top sample's code v3
+    constexpr int PARTS = NT / 128;          // 2 or 4
+    constexpr int V3_PER = 4 / PARTS;        // 2 or 1
+    const int group = tid & 127, part = tid >> 7;
+    const int t = group >> 5, w = group & 31;
+    float u[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        int64_t i = slab * 512 + 16 * w + 4 * t + s;
+        u[s] = (i < n) ? __double2float_rn(__dsub_rn(v[i], vbar)) : 0.0f;
+    }
+    // dosage table of one sample: codes 00, 01 (missing -> 0), 10, 11
+    auto f = [&](int s, int code) -> float { return code == 2 ? u[s] : (code == 3 ? u[s] + u[s] : 0.0f); };
+    // address of row `value`: window(t>>1) + value*256 + (t&1)*128 + 4*w
+    const uint32_t rowbase = tab + (uint32_t)(t >> 1) * 65536u + (uint32_t)(t & 1) * 128u + 4u * (uint32_t)w;
+#pragma unroll
+    for (int c3 = 0; c3 < V3_PER; ++c3) {
+        const int v3 = part * V3_PER + c3;                 // runtime, but only used arithmetically
+        const float a3 = (v3 == 2) ? u[3] : ((v3 == 3) ? u[3] + u[3] : 0.0f);
+        const uint32_t base3 = rowbase + (uint32_t)v3 * (64u * 256u);
+#pragma unroll
+        for (int v2 = 0; v2 < 4; ++v2) {
+            const float a2 = a3 + f(2, v2);
+#pragma unroll
+            for (int v1 = 0; v1 < 4; ++v1) {
+                const float a1 = a2 + f(1, v1);
+#pragma unroll
+                for (int v0 = 0; v0 < 4; ++v0)
+                    sts_f32(base3 + (uint32_t)(v2 << 4 | v1 << 2 | v0) * 256u, a1 + f(0, v0));
+            }
+        }
+    }
+}
+
+}  // namespace ihtb

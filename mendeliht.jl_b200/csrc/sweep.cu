@@ -19,6 +19,8 @@ void sweep_fast_partials(const ihtb_geno* g, const double* d_v, const double* d_
                          cudaStream_t s);
 int64_t sweep_fast_num_slabs(const ihtb_geno* g);
 void sweep_exact_lut_partials(const ihtb_geno* g, const double* d_v, const double* d_vbar, double* d_part, cudaStream_t s);
+void sweep_pair_partials(const ihtb_geno* g, const double* d_v0, const double* d_v1, const double* d_vbar,
+                         const float* d_scale, float* d_part, cudaStream_t s);
 
 // tiled layout: table-driven FP64 kernel (sweep_lut64.cu); column-major debug layout or IHTB_EXACT_LEGACY=1: k_sweep_exact
 static bool exact_uses_lut(const ihtb_geno* g) {
@@ -90,12 +92,13 @@ __global__ void k_sweep_epilogue(const T* __restrict__ part, int64_t n_slabs, in
                                  const int32_t* __restrict__ nmiss, const int64_t* __restrict__ miss_ptr,
                                  const int32_t* __restrict__ miss_idx, const double* __restrict__ v,
                                  const double* __restrict__ vbar_p,
-                                 int impute, double* __restrict__ out) {
+                                 int impute, double* __restrict__ out, const float* __restrict__ scale_p = nullptr) {
     int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (j >= p) return;
     const double vbar = *vbar_p;
     double a = 0.0;
     for (int64_t s = 0; s < n_slabs; ++s) a += (double)part[s * p + j];
+    if (scale_p) a /= (double)*scale_p;            // pair sweep: sums of 2^e-scaled values (exact division)
     double corr = 0.0;
     int nm = nmiss[j];
     if (nm) {
@@ -117,9 +120,34 @@ __global__ void k_vec_mean(const double* __restrict__ v, int64_t n, double* __re
     if (threadIdx.x == 0) out[0] = a / (double)n;
 }
 
+// pair sweep prelude: power-of-two scales that bring max |v - mean| of each right-hand side below 2^9 (the half2 tables
+// of k_sweep_ldg<.., true> then cannot overflow: entries <= 8 * 2^9, sums of four <= 2^14)
+__global__ void k_pair_scale(const double* __restrict__ v0, const double* __restrict__ v1, int64_t n,
+                             const double* __restrict__ vbar, float* __restrict__ scale) {
+    __shared__ double sh[32];
+    for (int t = 0; t < 2; ++t) {
+        const double* v = t ? v1 : v0;
+        const double vb = vbar[t];
+        double m = 0.0;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, fabs(v[i] - vb));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sh[w]);
+            int e = 0;
+            if (m > 0.0 && isfinite(m)) frexp(m, &e);        // m = f * 2^e, f in [0.5, 1)  ->  m < 2^e
+            scale[t] = ldexpf(1.0f, 9 - e);
+        }
+    }
+}
+
 struct SweepScratch {
     DBuf<double> part64;
     DBuf<float> part32;
+    DBuf<float> scale;
 };
 
 // dV: n x m column-major device array; dOut: p x m. d_vbar[t] = mean of column t (DEVICE array, so a sweep can be
@@ -136,6 +164,21 @@ void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* d
     for (int64_t t = 0; t < m; ++t) {
         const double* v = dV + t * g->n;
         double* out = dOut + t * g->p;
+        if (mode == IHTB_SWEEP_PAIR && g->cs_j == 128 && t + 1 < m) {
+            // two right-hand sides per pass over the matrix (half2 tables); an odd last one takes the FAST path below
+            const int64_t n_slabs = g->stride / 128;
+            if (sc->part32.n < (size_t)(2 * n_slabs * g->p)) sc->part32.alloc((size_t)(2 * n_slabs * g->p));
+            if (sc->scale.n < 2) sc->scale.alloc(2);
+            IHTB_LAUNCH(k_pair_scale, 1, 1024, 0, s, v, v + g->n, g->n, d_vbar + t, sc->scale.p);
+            sweep_pair_partials(g, v, v + g->n, d_vbar + t, sc->scale.p, sc->part32.p, s);
+            for (int h = 0; h < 2; ++h)
+                IHTB_LAUNCH((k_sweep_epilogue<float>), (unsigned)ceil_div(g->p, 256), 256, 0, s,
+                            sc->part32.p + (size_t)h * n_slabs * g->p, n_slabs, g->p, g->mu.p, g->sinv.p, g->nmiss.p,
+                            g->miss_ptr.p, g->miss_idx.p, v + h * g->n, d_vbar + t + h, g->impute, out + h * g->p,
+                            sc->scale.p + h);
+            ++t;
+            continue;
+        }
         if (mode == IHTB_SWEEP_EXACT && exact_uses_lut(g)) {
             const int64_t n_slabs = g->stride / 128;
             if (sc->part64.n < (size_t)(n_slabs * g->p)) sc->part64.alloc((size_t)(n_slabs * g->p));
@@ -180,7 +223,8 @@ extern "C" int32_t ihtb_xt_v(const ihtb_geno* g, const double* V, int64_t m, dou
     return guard([&] {
         IHTB_CHECK(g && V && out && m >= 1, IHTB_EINVAL, "bad argument");
         geno_require_ready(g);
-        IHTB_CHECK(sweep_mode == IHTB_SWEEP_FAST || sweep_mode == IHTB_SWEEP_EXACT, IHTB_EINVAL, "bad sweep_mode");
+        IHTB_CHECK(sweep_mode == IHTB_SWEEP_FAST || sweep_mode == IHTB_SWEEP_EXACT || sweep_mode == IHTB_SWEEP_PAIR,
+                   IHTB_EINVAL, "bad sweep_mode");
         IHTB_CUDA(cudaSetDevice(g->device));
         DBuf<double> dV((size_t)(g->n * m)), dOut((size_t)(g->p * m)), dmean((size_t)m);
         IHTB_CUDA(cudaMemcpy(dV.p, V, g->n * m * sizeof(double), cudaMemcpyHostToDevice));
@@ -211,19 +255,20 @@ extern "C" int32_t ihtb_sweep_bench(const ihtb_geno* g, int32_t sweep_mode, int3
         IHTB_CUDA(cudaSetDevice(g->device));
         cudaStream_t s;
         IHTB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-        DBuf<double> dV((size_t)g->n), dOut((size_t)g->p);
-        IHTB_LAUNCH(k_fill_vec, (unsigned)ceil_div(g->n, 256), 256, 0, s, dV.p, g->n, 12345ull);
-        DBuf<double> dmean(1);
-        IHTB_LAUNCH(k_vec_mean, 1, 1024, 0, s, dV.p, g->n, dmean.p);
+        const int64_t mrhs = sweep_mode == IHTB_SWEEP_PAIR ? 2 : 1;       // PAIR: two right-hand sides per launch
+        DBuf<double> dV((size_t)(g->n * mrhs)), dOut((size_t)(g->p * mrhs));
+        IHTB_LAUNCH(k_fill_vec, (unsigned)ceil_div(g->n * mrhs, 256), 256, 0, s, dV.p, g->n * mrhs, 12345ull);
+        DBuf<double> dmean((size_t)mrhs);
+        for (int64_t t = 0; t < mrhs; ++t) IHTB_LAUNCH(k_vec_mean, 1, 1024, 0, s, dV.p + t * g->n, g->n, dmean.p + t);
         SweepScratch sc;
         cudaEvent_t e0, e1;
         IHTB_CUDA(cudaEventCreate(&e0)); IHTB_CUDA(cudaEventCreate(&e1));
         for (int i = 0; i < warmup; ++i)
-            sweep_xt_v_with_means(g, dV.p, dmean.p, 1, dOut.p, sweep_mode, s, &sc, nullptr);
+            sweep_xt_v_with_means(g, dV.p, dmean.p, mrhs, dOut.p, sweep_mode, s, &sc, nullptr);
         // (a) whole sweep = partial-sum kernel + epilogue
         IHTB_CUDA(cudaEventRecord(e0, s));
         for (int i = 0; i < reps; ++i)
-            sweep_xt_v_with_means(g, dV.p, dmean.p, 1, dOut.p, sweep_mode, s, &sc, nullptr);
+            sweep_xt_v_with_means(g, dV.p, dmean.p, mrhs, dOut.p, sweep_mode, s, &sc, nullptr);
         IHTB_CUDA(cudaEventRecord(e1, s));
         IHTB_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;
@@ -232,7 +277,16 @@ extern "C" int32_t ihtb_sweep_bench(const ihtb_geno* g, int32_t sweep_mode, int3
         // (b) the dominant kernel alone
         if (ms_kernel) {
             *ms_kernel = 0.0;
-            if (sweep_mode == IHTB_SWEEP_FAST) {
+            if (sweep_mode == IHTB_SWEEP_PAIR) {
+                IHTB_CHECK(g->cs_j == 128, IHTB_EUNSUPPORTED, "the pair sweep needs a tiled layout");
+                IHTB_CUDA(cudaEventRecord(e0, s));
+                for (int i = 0; i < reps; ++i)
+                    sweep_pair_partials(g, dV.p, dV.p + g->n, dmean.p, sc.scale.p, sc.part32.p, s);
+                IHTB_CUDA(cudaEventRecord(e1, s));
+                IHTB_CUDA(cudaEventSynchronize(e1));
+                IHTB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+                *ms_kernel = ms / reps;
+            } else if (sweep_mode == IHTB_SWEEP_FAST) {
                 IHTB_CUDA(cudaEventRecord(e0, s));
                 for (int i = 0; i < reps; ++i) sweep_fast_kernel_only(g, dV.p, dmean.p, sc.part32.p, s);
                 IHTB_CUDA(cudaEventRecord(e1, s));

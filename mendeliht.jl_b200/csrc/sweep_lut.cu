@@ -17,7 +17,8 @@
 // cp.async.bulk (TMA bulk copy, SASS UBLKCP) completing on mbarriers; 8 consumer warps each reduce 16 columns per
 // stage with a butterfly so that lanes 0..15 end up holding one column sum each.  Slab partial sums are written as
 // FP32 [slab][column]; the epilogue (sweep.cu) adds them in FP64 in slab order.  Everything is deterministic.
-#include "common.cuh"
+#include "lut_common.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace ihtb {
@@ -25,49 +26,7 @@ namespace ihtb {
 constexpr int LUT_STAGE_COLS = 128;
 constexpr int LUT_STAGE_BYTES = LUT_STAGE_COLS * 128;
 constexpr int LUT_MAX_STAGES = 8;
-constexpr int LUT_TABLE_BYTES = 131072;
 constexpr int LUT_SMEM_BYTES = 232448;   // 227 KB: everything the SM has
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n"
-        "W_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra W_%=;\n\t}"
-        ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-template <int NT>
-__device__ __forceinline__ void consumer_bar() {   // named barrier 1 over the NT consumer threads
-    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-}
 
 // shared-memory plan (computed identically by every thread)
 struct LutPlan {
@@ -99,39 +58,36 @@ __device__ __forceinline__ LutPlan lut_plan(uint32_t base, uint32_t bytes) {
     return pl;
 }
 
-// build T for one slab; executed by the NT (256 or 512) consumer threads
-template <int NT>
-__device__ __forceinline__ void lut_build(uint32_t tab, const double* __restrict__ v, double vbar, int64_t n,
-                                          int64_t slab, int tid) {
-    // thread -> (part, group): group = t*32 + w (128 groups); part selects a range of the top sample's code v3
-    constexpr int PARTS = NT / 128;          // 2 or 4
-    constexpr int V3_PER = 4 / PARTS;        // 2 or 1
-    const int group = tid & 127, part = tid >> 7;
+// half2 table of one slab for TWO right-hand sides (the pair sweep): entry = (v0 part | v1 part), each the FP32 sum of
+// up to four scaled values rounded once to FP16; same addressing as lut_build.  512 consumer threads.
+__device__ __forceinline__ void lut_build_h2(uint32_t tab, const double* __restrict__ v0, const double* __restrict__ v1,
+                                             double vbar0, double vbar1, float sc0, float sc1, int64_t n, int64_t slab,
+                                             int tid) {
+    const int group = tid & 127, part = tid >> 7;            // 4 parts: one value of the top sample's code each
     const int t = group >> 5, w = group & 31;
-    float u[4];
+    float a[4], b[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         int64_t i = slab * 512 + 16 * w + 4 * t + s;
-        u[s] = (i < n) ? __double2float_rn(__dsub_rn(v[i], vbar)) : 0.0f;
+        a[s] = (i < n) ? __double2float_rn(__dsub_rn(v0[i], vbar0)) * sc0 : 0.0f;     // power-of-two scale: exact
+        b[s] = (i < n) ? __double2float_rn(__dsub_rn(v1[i], vbar1)) * sc1 : 0.0f;
     }
-    // dosage table of one sample: codes 00, 01 (missing -> 0), 10, 11
-    auto f = [&](int s, int code) -> float { return code == 2 ? u[s] : (code == 3 ? u[s] + u[s] : 0.0f); };
-    // address of row `value`: window(t>>1) + value*256 + (t&1)*128 + 4*w
+    auto fa = [&](int s, int code) -> float { return code == 2 ? a[s] : (code == 3 ? a[s] + a[s] : 0.0f); };
+    auto fb = [&](int s, int code) -> float { return code == 2 ? b[s] : (code == 3 ? b[s] + b[s] : 0.0f); };
     const uint32_t rowbase = tab + (uint32_t)(t >> 1) * 65536u + (uint32_t)(t & 1) * 128u + 4u * (uint32_t)w;
+    const int v3 = part;
+    const float a3 = fa(3, v3), b3 = fb(3, v3);
+    const uint32_t base3 = rowbase + (uint32_t)v3 * (64u * 256u);
 #pragma unroll
-    for (int c3 = 0; c3 < V3_PER; ++c3) {
-        const int v3 = part * V3_PER + c3;                 // runtime, but only used arithmetically
-        const float a3 = (v3 == 2) ? u[3] : ((v3 == 3) ? u[3] + u[3] : 0.0f);
-        const uint32_t base3 = rowbase + (uint32_t)v3 * (64u * 256u);
+    for (int v2 = 0; v2 < 4; ++v2) {
+        const float a2 = a3 + fa(2, v2), b2 = b3 + fb(2, v2);
 #pragma unroll
-        for (int v2 = 0; v2 < 4; ++v2) {
-            const float a2 = a3 + f(2, v2);
+        for (int v1c = 0; v1c < 4; ++v1c) {
+            const float a1 = a2 + fa(1, v1c), b1 = b2 + fb(1, v1c);
 #pragma unroll
-            for (int v1 = 0; v1 < 4; ++v1) {
-                const float a1 = a2 + f(1, v1);
-#pragma unroll
-                for (int v0 = 0; v0 < 4; ++v0)
-                    sts_f32(base3 + (uint32_t)(v2 << 4 | v1 << 2 | v0) * 256u, a1 + f(0, v0));
+            for (int v0c = 0; v0c < 4; ++v0c) {
+                const __half2 h = __floats2half2_rn(a1 + fa(0, v0c), b1 + fb(0, v0c));
+                sts_u32(base3 + (uint32_t)(v2 << 4 | v1c << 2 | v0c) * 256u, *reinterpret_cast<const uint32_t*>(&h));
             }
         }
     }
@@ -146,14 +102,29 @@ __device__ __forceinline__ void lut_build(uint32_t tab, const double* __restrict
 // phase of a barrier it waits on -- a parity wait issued a whole phase early is satisfied by the preceding phase
 // (the mbarrier ABA hazard) and the warp would read a slot before it is refilled.  With per-group full barriers a
 // group sees exactly the fills meant for it, in order, while the groups still progress independently.
-template <int CW, int G>
+//
+// QUAD: quad-interleaved tiles (common.cuh): a stage is 32 quads of 512 bytes, one LDS.128 per lane fetches word
+//       `lane` of four columns (same wavefronts as four LDS.32, a quarter of the instructions).  `p` is then the padded
+//       column count stored per slab and p_out the number of result columns.
+// H2:   the PAIR sweep -- two right-hand sides per pass.  The table entries are half2 (v0 | v1), so ONE lookup serves
+//       both: per word four half2 lookups added with HADD2, converted to FP32 and reduced across lanes in FP32.
+//       Entries are scaled by a power of two per right-hand side (max |u| <= 2^9: entries <= 2^12, sums of four
+//       <= 2^14, no overflow); part is [2][n_slabs][p_out] floats of the SCALED sums.  Error bound, per column sum:
+//       one FP16 rounding per table entry + two levels of HADD2 on partial sums bounded by twice the absolute sum of
+//       the 16 samples of a word: 3 * 2^-11 * 2 ||u||_1 < 2^-8 ||u||_1 (FP32 and subnormal terms are below 1e-5 of that).
+template <int CW, int G, bool QUAD, bool H2>
 __global__ void __launch_bounds__((CW + 1) * 32, 1)
-k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t p, int64_t n, int64_t n_slabs,
-            const double* __restrict__ v, const double* __restrict__ vbar_p, float* __restrict__ part,
+k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t p, int64_t p_out, int64_t n,
+            int64_t n_slabs, const double* __restrict__ v, const double* __restrict__ v1,
+            const double* __restrict__ vbar_p, const float* __restrict__ scale_p, float* __restrict__ part,
             uint32_t dyn_bytes) {
-    const double vbar = *vbar_p;
+    const double vbar = vbar_p[0];
+    const double vbar1 = H2 ? vbar_p[1] : 0.0;
+    const float sc0 = H2 ? scale_p[0] : 1.0f, sc1 = H2 ? scale_p[1] : 1.0f;
     constexpr int WPG = CW / G;                      // warps per group
     constexpr int CPW = LUT_STAGE_COLS / WPG;        // columns per warp per unit
+    static_assert(!QUAD || CPW % 4 == 0, "quad layout: a warp owns whole quads");
+    static_assert(!H2 || (CW == 16 && CPW == 16), "pair sweep: 512 table builders, 16 columns per warp");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const LutPlan pl = lut_plan(smem_u32(smem_raw), dyn_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -191,7 +162,7 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
                 const uint32_t fullbar = pl.bar_full + 8u * (uint32_t)(grp_of * LUT_MAX_STAGES + st);
                 mbar_wait(pl.bar_empty + 8u * st, ph ^ 1u);
                 const uint8_t* src = bed + j0 * cs_j + slab * cs_s;
-                if (cs_j == 128) {               // slab-major tiled layout: one contiguous copy
+                if (cs_j == 128) {               // slab-major tiles (plain or quad-interleaved): one contiguous copy
                     if (lane == 0) {
                         mbar_expect_tx(fullbar, (uint32_t)ncols * 128u);
                         bulk_g2s(pl.stage(st), src, (uint32_t)ncols * 128u, fullbar);
@@ -215,10 +186,13 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
 #pragma unroll
         for (int t = 0; t < 4; ++t)
             lb[t] = pl.tab + (uint32_t)(t >> 1) * 65536u + (uint32_t)(t & 1) * 128u + 4u * (uint32_t)lane;
-        constexpr int LPC = 32 / CPW;                 // lanes holding the same column after the butterfly
-        const int col = wg * CPW + lane / LPC;        // column (within a unit) this lane stores
+        constexpr int NACC = H2 ? 2 * CPW : CPW;      // values reduced per warp and unit
+        constexpr int LPC = 32 / NACC > 0 ? 32 / NACC : 1;   // lanes holding the same value after the butterfly
+        // after the butterfly lane l holds value index l / LPC: (rhs, column) = (idx / CPW, idx % CPW)
+        const int vidx = lane / LPC;
+        const int col = wg * CPW + vidx % CPW;        // column (within a unit) this lane stores
         const bool writer = (lane & (LPC - 1)) == 0;
-        const uint32_t lane_off = (uint32_t)(wg * CPW) * 128u + 4u * (uint32_t)lane;
+        const uint32_t lane_off = (uint32_t)(wg * CPW) * 128u + (QUAD ? 16u : 4u) * (uint32_t)lane;
         // this group consumes local unit indices i = grp, grp+G, ...: stage i % S, full-barrier parity (i / period) & 1
         int st = grp % S, ip = grp % period; uint32_t ph = (uint32_t)((grp / period) & 1);
         const uint32_t my_full = pl.bar_full + 8u * (uint32_t)(grp * LUT_MAX_STAGES);
@@ -228,31 +202,51 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
             const int cb0 = (slab == slab_beg) ? (int)(u_beg - slab * n_cblocks) : 0;
             const int cb1 = (slab == slab_end) ? (int)(u_end - slab * n_cblocks) : ncb;
             consumer_bar<CW * 32>();      // everyone finished looking up the previous slab's tables
-            lut_build<CW * 32>(pl.tab, v, vbar, n, slab, tid);
+            if (H2) lut_build_h2(pl.tab, v, v1, vbar, vbar1, sc0, sc1, n, slab, tid);
+            else lut_build<CW * 32>(pl.tab, v, vbar, n, slab, tid);
             consumer_bar<CW * 32>();
-            float* __restrict__ outp = part + slab * p + col;
+            float* __restrict__ outp = part + ((int64_t)(H2 ? vidx / CPW : 0) * n_slabs + slab) * p_out + col;
             const int i_end = i_base + (cb1 - cb0);
             for (; i_next < i_end; i_next += G) {
                 const int cb = cb0 + (i_next - i_base);
                 mbar_wait(my_full + 8u * st, ph);
                 const uint32_t colbase = pl.stage(st) + lane_off;
-                float acc[CPW];
+                float acc[NACC];
+                uint4 q4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int c = 0; c < CPW; ++c) {
-                    const uint32_t w = lds_u32(colbase + 128u * c);
-                    const float t0 = lds_f32(__byte_perm(w, lb[0], 0x7604));
-                    const float t1 = lds_f32(__byte_perm(w, lb[1], 0x7614));
-                    const float t2 = lds_f32(__byte_perm(w, lb[2], 0x7624));
-                    const float t3 = lds_f32(__byte_perm(w, lb[3], 0x7634));
-                    acc[c] = (t0 + t1) + (t2 + t3);
+                    uint32_t w;
+                    if (QUAD) {
+                        if ((c & 3) == 0) q4 = lds_u128(colbase + 512u * (c >> 2));
+                        w = (c & 3) == 0 ? q4.x : (c & 3) == 1 ? q4.y : (c & 3) == 2 ? q4.z : q4.w;
+                    } else {
+                        w = lds_u32(colbase + 128u * c);
+                    }
+                    if (!H2) {
+                        const float t0 = lds_f32(__byte_perm(w, lb[0], 0x7604));
+                        const float t1 = lds_f32(__byte_perm(w, lb[1], 0x7614));
+                        const float t2 = lds_f32(__byte_perm(w, lb[2], 0x7624));
+                        const float t3 = lds_f32(__byte_perm(w, lb[3], 0x7634));
+                        acc[c] = (t0 + t1) + (t2 + t3);
+                    } else {
+                        const uint32_t r0 = lds_u32(__byte_perm(w, lb[0], 0x7604));
+                        const uint32_t r1 = lds_u32(__byte_perm(w, lb[1], 0x7614));
+                        const uint32_t r2 = lds_u32(__byte_perm(w, lb[2], 0x7624));
+                        const uint32_t r3 = lds_u32(__byte_perm(w, lb[3], 0x7634));
+                        const __half2 h = __hadd2(__hadd2(*reinterpret_cast<const __half2*>(&r0), *reinterpret_cast<const __half2*>(&r1)),
+                                                  __hadd2(*reinterpret_cast<const __half2*>(&r2), *reinterpret_cast<const __half2*>(&r3)));
+                        const float2 f = __half22float2(h);
+                        acc[c] = f.x;
+                        acc[(H2 ? CPW : 0) + c] = f.y;
+                    }
                 }
                 // the stage's bytes are now in registers: hand the slot back to the producer
                 __syncwarp();
                 if (lane == 0) mbar_arrive(pl.bar_empty + 8u * st);
-                // butterfly: CPW column sums per lane -> one per lane; the high lane bits select the column
+                // butterfly: NACC sums per lane -> one per lane; the high lane bits select the value
                 int o = 16;
 #pragma unroll
-                for (int h = CPW / 2; h >= 1; h >>= 1, o >>= 1) {
+                for (int h = NACC / 2; h >= 1; h >>= 1, o >>= 1) {
                     const bool upper = (lane & o) != 0;
 #pragma unroll
                     for (int c = 0; c < h; ++c) {
@@ -262,9 +256,9 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
                     }
                 }
 #pragma unroll
-                for (int oo = 16 / CPW; oo >= 1; oo >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], oo);
+                for (int oo = 16 / NACC; oo >= 1; oo >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], oo);
                 const int jj = cb * LUT_STAGE_COLS + col;
-                if (writer && jj < (int)p) outp[cb * LUT_STAGE_COLS] = acc[0];
+                if (writer && jj < (int)p_out) outp[cb * LUT_STAGE_COLS] = acc[0];
                 st += G; if (st >= S) st -= S;
                 ip += G; if (ip >= period) { ip -= period; ph ^= 1u; }
             }
@@ -273,44 +267,41 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
     }
 }
 
-void sweep_fast_partials(const ihtb_geno* g, const double* d_v, const double* d_vbar, float* d_part, int64_t* n_slabs_out,
-                         cudaStream_t s);
-
 int64_t sweep_fast_num_slabs(const ihtb_geno* g) { return g->stride / 128; }
 
-void sweep_fast_kernel_only(const ihtb_geno* g, const double* d_v, const double* d_vbar, float* d_part, cudaStream_t s) {
-    int64_t ns = 0;
-    sweep_fast_partials(g, d_v, d_vbar, d_part, &ns, s);
-}
-
-void sweep_fast_partials(const ihtb_geno* g, const double* d_v, const double* d_vbar, float* d_part, int64_t* n_slabs_out,
-                         cudaStream_t s) {
-    static int cw = 0;
-    if (!cw) {
-        IHTB_CUDA(cudaFuncSetAttribute(k_sweep_lut<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES));
-        IHTB_CUDA(cudaFuncSetAttribute(k_sweep_lut<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES));
-        IHTB_CUDA(cudaFuncSetAttribute(k_sweep_lut<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES));
-        const char* e = getenv("IHTB_LUT_WARPS");       // tuning knob: 8 = <8,1>, 16 = <16,1>, default <16,2>
-        cw = e ? atoi(e) : 162;
-        if (cw != 8 && cw != 16) cw = 162;
-    }
+template <bool QUAD, bool H2>
+static void launch_lut(const ihtb_geno* g, const double* d_v, const double* d_v1, const double* d_vbar,
+                       const float* d_scale, float* d_part, cudaStream_t s) {
+    ensure_dynamic_smem(k_sweep_lut<16, 2, QUAD, H2>, LUT_SMEM_BYTES);
     const int64_t n_slabs = sweep_fast_num_slabs(g);
-    *n_slabs_out = n_slabs;
-    const int64_t n_cblocks = ceil_div(g->p, LUT_STAGE_COLS);
+    const int64_t n_cblocks = ceil_div(g->p4, LUT_STAGE_COLS);
     int64_t units = n_slabs * n_cblocks;
     int grid = g->sm_count;
     if (units < grid) grid = (int)units;
     IHTB_CHECK(g->p < (int64_t(1) << 31) - 256, IHTB_EDIM, "more than 2^31 SNP columns on one GPU");
-    if (cw == 8) {
-        IHTB_LAUNCH((k_sweep_lut<8, 1>), grid, 9 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n,
-                    n_slabs, d_v, d_vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
-    } else if (cw == 16) {
-        IHTB_LAUNCH((k_sweep_lut<16, 1>), grid, 17 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n,
-                    n_slabs, d_v, d_vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
-    } else {
-        IHTB_LAUNCH((k_sweep_lut<16, 2>), grid, 17 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p, g->n,
-                    n_slabs, d_v, d_vbar, d_part, (uint32_t)LUT_SMEM_BYTES);
-    }
+    IHTB_LAUNCH((k_sweep_lut<16, 2, QUAD, H2>), grid, 17 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p4, g->p,
+                g->n, n_slabs, d_v, d_v1, d_vbar, d_scale, d_part, (uint32_t)LUT_SMEM_BYTES);
+}
+
+// FAST sweep, one right-hand side: d_part is [n_slabs][p] floats
+void sweep_fast_partials(const ihtb_geno* g, const double* d_v, const double* d_vbar, float* d_part, int64_t* n_slabs_out,
+                         cudaStream_t s) {
+    if (n_slabs_out) *n_slabs_out = sweep_fast_num_slabs(g);
+    if (g->quad) launch_lut<true, false>(g, d_v, nullptr, d_vbar, nullptr, d_part, s);
+    else launch_lut<false, false>(g, d_v, nullptr, d_vbar, nullptr, d_part, s);
+}
+
+void sweep_fast_kernel_only(const ihtb_geno* g, const double* d_v, const double* d_vbar, float* d_part, cudaStream_t s) {
+    sweep_fast_partials(g, d_v, d_vbar, d_part, nullptr, s);
+}
+
+// PAIR sweep, two right-hand sides per pass: d_vbar[2] means, d_scale[2] power-of-two scales (device);
+// d_part is [2][n_slabs][p] floats of the scaled sums
+void sweep_pair_partials(const ihtb_geno* g, const double* d_v0, const double* d_v1, const double* d_vbar,
+                         const float* d_scale, float* d_part, cudaStream_t s) {
+    IHTB_CHECK(g->cs_j == 128, IHTB_EUNSUPPORTED, "the pair sweep needs a tiled layout");
+    if (g->quad) launch_lut<true, true>(g, d_v0, d_v1, d_vbar, d_scale, d_part, s);
+    else launch_lut<false, true>(g, d_v0, d_v1, d_vbar, d_scale, d_part, s);
 }
 
 }  // namespace ihtb

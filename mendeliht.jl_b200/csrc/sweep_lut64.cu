@@ -82,8 +82,18 @@ __device__ __forceinline__ void build64(uint32_t tab, const double* __restrict__
     }
 }
 
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+// QUAD: quad-interleaved tiles (common.cuh) -- a stage holds 32 quads of 512 bytes, 16 bytes per (quad, word): one
+// LDS.128 per lane fetches word `lane` of four columns (same wavefront count as four LDS.32 on plain tiles).
+// p is the number of columns stored per slab (p4 for QUAD); p_out the number of result columns.
+template <bool QUAD>
 __global__ void __launch_bounds__((X_CW + 1) * 32, 1)
-k_sweep_lut64(const uint8_t* __restrict__ bed, int64_t cs_s, int64_t p, int64_t n, int64_t n_slabs,
+k_sweep_lut64(const uint8_t* __restrict__ bed, int64_t cs_s, int64_t p, int64_t p_out, int64_t n, int64_t n_slabs,
               const double* __restrict__ v, const double* __restrict__ vbar_p, double* __restrict__ part) {
     const double vbar = *vbar_p;
     constexpr int WPG = X_CW / X_G;                 // warps per group
@@ -145,7 +155,8 @@ k_sweep_lut64(const uint8_t* __restrict__ bed, int64_t cs_s, int64_t p, int64_t 
         constexpr int LPC = 32 / CPW;
         const int col = wg * CPW + lane / LPC;
         const bool writer = (lane & (LPC - 1)) == 0;
-        const uint32_t lane_off = (uint32_t)(wg * CPW) * 128u + 4u * (uint32_t)lane;
+        const uint32_t lane_off = QUAD ? (uint32_t)(wg * CPW) * 128u + 16u * (uint32_t)lane
+                                       : (uint32_t)(wg * CPW) * 128u + 4u * (uint32_t)lane;
         int st = grp % S, ip = grp % period; uint32_t ph = (uint32_t)((grp / period) & 1);
         const uint32_t my_full = bar_full + 8u * (uint32_t)(grp * S);
         int i_next = grp;
@@ -156,16 +167,23 @@ k_sweep_lut64(const uint8_t* __restrict__ bed, int64_t cs_s, int64_t p, int64_t 
             consumer_bar();
             build64(tab, v, vbar, n, slab, tid);
             consumer_bar();
-            double* __restrict__ outp = part + slab * p + col;
+            double* __restrict__ outp = part + slab * p_out + col;
             const int i_end = i_base + (cb1 - cb0);
             for (; i_next < i_end; i_next += X_G) {
                 const int cb = cb0 + (i_next - i_base);
                 mbar_wait(my_full + 8u * st, ph);
                 const uint32_t colbase = stage0 + (uint32_t)st * X_STAGE_BYTES + lane_off;
                 double acc[CPW];
+                uint4 q4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int c = 0; c < CPW; ++c) {
-                    const uint32_t w = lds_u32(colbase + 128u * c);
+                    uint32_t w;
+                    if (QUAD) {
+                        if ((c & 3) == 0) q4 = lds_u128(colbase + 512u * (c >> 2));
+                        w = (c & 3) == 0 ? q4.x : (c & 3) == 1 ? q4.y : (c & 3) == 2 ? q4.z : q4.w;
+                    } else {
+                        w = lds_u32(colbase + 128u * c);
+                    }
                     const double d0 = lds_f64(lb[0] | ((w << 8) & 0xF00u));
                     const double d1 = lds_f64(lb[1] | ((w << 4) & 0xF00u));
                     const double d2 = lds_f64(lb[2] | (w & 0xF00u));
@@ -193,7 +211,7 @@ k_sweep_lut64(const uint8_t* __restrict__ bed, int64_t cs_s, int64_t p, int64_t 
 #pragma unroll
                 for (int oo = 16 / CPW; oo >= 1; oo >>= 1) acc[0] = __dadd_rn(acc[0], __shfl_xor_sync(0xffffffffu, acc[0], oo));
                 const int jj = cb * X_STAGE_COLS + col;
-                if (writer && jj < (int)p) outp[cb * X_STAGE_COLS] = acc[0];
+                if (writer && jj < (int)p_out) outp[cb * X_STAGE_COLS] = acc[0];
                 st += X_G; if (st >= S) st -= S;
                 ip += X_G; if (ip >= period) { ip -= period; ph ^= 1u; }
             }
@@ -204,21 +222,23 @@ k_sweep_lut64(const uint8_t* __restrict__ bed, int64_t cs_s, int64_t p, int64_t 
 
 }  // namespace
 
-// tiled layout only (cs_j == 128); d_part is [stride/128][p] doubles
+// tiled layouts only (cs_j == 128, plain or quad-interleaved); d_part is [stride/128][p] doubles
 void sweep_exact_lut_partials(const ihtb_geno* g, const double* d_v, const double* d_vbar, double* d_part, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
-        IHTB_CUDA(cudaFuncSetAttribute(k_sweep_lut64, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM_BYTES));
-        attr = true;
-    }
-    IHTB_CHECK(g->cs_j == 128, IHTB_EINVAL, "the table-driven exact sweep needs the tiled layout");
+    IHTB_CHECK(g->cs_j == 128, IHTB_EINVAL, "the table-driven exact sweep needs a tiled layout");
     IHTB_CHECK(g->p < (int64_t(1) << 31) - 256, IHTB_EDIM, "more than 2^31 SNP columns on one GPU");
     const int64_t n_slabs = g->stride / 128;
-    const int64_t units = n_slabs * ceil_div(g->p, X_STAGE_COLS);
+    const int64_t units = n_slabs * ceil_div(g->p4, X_STAGE_COLS);
     int grid = g->sm_count;
     if (units < grid) grid = (int)units;
-    IHTB_LAUNCH(k_sweep_lut64, grid, (X_CW + 1) * 32, X_SMEM_BYTES, s, g->bed.p, g->cs_s, g->p, g->n, n_slabs, d_v, d_vbar,
-                d_part);
+    if (g->quad) {
+        ensure_dynamic_smem(k_sweep_lut64<true>, X_SMEM_BYTES);
+        IHTB_LAUNCH(k_sweep_lut64<true>, grid, (X_CW + 1) * 32, X_SMEM_BYTES, s, g->bed.p, g->cs_s, g->p4, g->p, g->n,
+                    n_slabs, d_v, d_vbar, d_part);
+    } else {
+        ensure_dynamic_smem(k_sweep_lut64<false>, X_SMEM_BYTES);
+        IHTB_LAUNCH(k_sweep_lut64<false>, grid, (X_CW + 1) * 32, X_SMEM_BYTES, s, g->bed.p, g->cs_s, g->p, g->p, g->n,
+                    n_slabs, d_v, d_vbar, d_part);
+    }
 }
 
 }  // namespace ihtb

@@ -1,5 +1,8 @@
-"""Runs the X'r sweep alone on a device-generated matrix (for ncu captures and quick kernel timing)."""
+"""Runs the X'r sweep alone on a device-generated matrix (for ncu captures and quick kernel timing).
+usage: sweep_only.py [n p reps mode]   mode 0 = FAST, 1 = EXACT, 2 = PAIR (two right-hand sides per pass)
+env:   IHTB_LAYOUT=quad|tiled|colmajor, IHTB_LDG_DEPTH=2|3|4"""
 import ctypes as C
+import json
 import os
 import sys
 
@@ -14,5 +17,9 @@ g = m.B200SnpLinAlg.synthetic(n, p, 2024)
 mk, mt = C.c_double(0), C.c_double(0)
 m._lib.check(m.load().ihtb_sweep_bench(g._h, mode, 2, reps, C.byref(mk), C.byref(mt)))
 b = p * ((n + 3) // 4) + 8 * n + 24 * p
-print(f"n={n} p={p} mode={mode} kernel_ms={mk.value:.4f} total_ms={mt.value:.4f} kernel_GBs={b / mk.value / 1e6:.1f} "
-      f"total_GBs={b / mt.value / 1e6:.1f}")
+rhs = 2 if mode == 2 else 1
+print(json.dumps({"n": n, "p": p, "mode": ["FAST", "EXACT", "PAIR"][mode], "layout": os.environ.get("IHTB_LAYOUT", "quad"),
+                  "ldg_depth": os.environ.get("IHTB_LDG_DEPTH", "3"), "rhs_per_pass": rhs,
+                  "kernel_ms": round(mk.value, 4), "total_ms": round(mt.value, 4),
+                  "kernel_GBs_matrix": round(b / mk.value / 1e6, 1), "total_GBs_matrix": round(b / mt.value / 1e6, 1),
+                  "kernel_ms_per_rhs": round(mk.value / rhs, 4), "frac_of_6552": round(b / mk.value / 1e6 / 6552, 4)}))

@@ -10,7 +10,7 @@ import mendeliht_jl_b200 as m
 from mendeliht_jl_b200 import synth
 from oracle import snp
 
-LAYOUTS = ["tiled", "colmajor"]
+LAYOUTS = ["quad", "tiled", "colmajor"]     # quad = the default quad-interleaved tiles (common.cuh)
 
 
 def _make(bed, n, layout):
@@ -70,6 +70,17 @@ def test_xt_v_exact_and_fast(layout, n, p, miss):
     # linearity (size-independent property)
     a = g.xt_v(v, m.SWEEP_EXACT); b = g.xt_v(2 * v + 1.0, m.SWEEP_EXACT)
     np.testing.assert_allclose(b, 2 * a, rtol=0, atol=1e-10 * scale)    # centring kills the constant
+    # pair sweep (two right-hand sides per pass, half2 tables): proven bound 2^-8 * ||v - mean||_1 * sinv per entry;
+    # right-hand sides of very different magnitude exercise the per-vector power-of-two scaling
+    if layout != "colmajor":
+        V5 = rng.normal(size=(n, 5)) * np.array([1.0, 1e-6, 3e4, 0.02, 7.0]) + np.array([0.0, 1.0, -5.0, 0.0, 2.0])
+        got, want = g.xt_v(V5, m.SWEEP_PAIR), o.xt_v(V5)
+        for t in range(5):
+            bnd = (2.0 ** -8) * np.abs(V5[:, t] - V5[:, t].mean()).sum() * o.sigma_inv
+            assert np.all(np.abs(got[:, t] - want[:, t]) <= bnd + 1e-12 * np.abs(want[:, t]).max()), t
+        assert np.array_equal(g.xt_v(V5[:, :1], m.SWEEP_PAIR), g.xt_v(V5[:, :1], m.SWEEP_FAST))   # odd one out: FAST
+        zero = np.zeros((n, 2)); zero[:, 1] = 3.0                      # constant vectors: u = 0, scale falls back to 1
+        assert np.all(g.xt_v(zero, m.SWEEP_PAIR) == 0.0)
 
 
 @pytest.mark.parametrize("layout", LAYOUTS)
@@ -111,6 +122,10 @@ def test_fast_sweep_matches_exact_at_scale():
         fa = g.xt_v(v, m.SWEEP_FAST)
         bound = (2.0 ** -18) * np.abs(v - v.mean()).sum() * sinv
         assert np.all(np.abs(fa - ex) <= bound + 1e-9 * np.abs(ex).max())
+        v2 = rng.normal(size=n) * 0.01
+        pr = g.xt_v(np.stack([v, v2], axis=1), m.SWEEP_PAIR)
+        assert np.all(np.abs(pr[:, 0] - ex) <= (2.0 ** -8) * np.abs(v - v.mean()).sum() * sinv)
+        assert np.all(np.abs(pr[:, 1] - g.xt_v(v2, m.SWEEP_EXACT)) <= (2.0 ** -8) * np.abs(v2 - v2.mean()).sum() * sinv)
     # checksum of checksums against a column subsample computed by the numpy twin of the generator
     cols = np.sort(rng.permutation(p)[:64])
     xs = synth.standardized_columns(2024, n, cols)
