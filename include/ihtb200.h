@@ -195,13 +195,53 @@ int32_t ihtb_cv_run(const ihtb_geno* g, const double* y, const double* z, int64_
                     const ihtb_cfg* cfg, const int32_t* folds, int32_t nfolds, const int64_t* path, int64_t npath,
                     const double* weight, double* mses, int64_t* iters);
 
-/* ---- multi-GPU plumbing (NCCL over NVLink; rendezvous of the 128-byte id is the host's job, e.g. torch.distributed) ---- */
+/* ---- several GPUs driven by ONE process (SURVEY.md 8b `ngpu`: what a Julia caller of fit_iht / cv_iht binds) ----------
+ * A multi-device genotype operator over `ngpu` devices (devices = NULL: ordinals 0..ngpu-1; at most 8):
+ *   IHTB_MULTI_SHARD     SNP columns block-partitioned over the devices; ihtb_mfit_* then run ONE fit over all of them
+ *                        (BASELINE configs[4]): one host thread per device inside each call, X*beta partials all-reduced
+ *                        and top-k candidates all-gathered by peer-memory kernels over NVLink (no NCCL, no torchrun);
+ *   IHTB_MULTI_REPLICATE the whole matrix on every device; ihtb_mcv_run farms the (fold, k) grid of cv_iht over them
+ *                        (BASELINE configs[2]; the reference's Threads.@threads loop, src/cross_validation.jl:98-121).
+ * The devices must be able to map each other's memory (NVLink / PCIe peer access); otherwise IHTB_ECUDA. */
+enum { IHTB_MULTI_SHARD = 0, IHTB_MULTI_REPLICATE = 1 };
+typedef struct ihtb_mgeno ihtb_mgeno;   /* SnpLinAlg over several GPUs */
+typedef struct ihtb_mfit ihtb_mfit;     /* IHTVariable over a SHARD handle */
+int32_t ihtb_mgeno_create(const uint8_t* bed_cols, int64_t n, int64_t p, int64_t col_stride_bytes, int32_t center,
+                          int32_t scale, int32_t impute, int32_t ngpu, const int32_t* devices, int32_t mode,
+                          ihtb_mgeno** out);
+int32_t ihtb_mgeno_create_synthetic(int64_t n, int64_t p, uint64_t seed, double missing_rate, int32_t ngpu,
+                                    const int32_t* devices, int32_t mode, ihtb_mgeno** out);
+int32_t ihtb_mgeno_info(const ihtb_mgeno* g, int32_t* ngpu, int32_t* mode, int64_t* n, int64_t* p);
+/* borrowed single-device handle of part i (its device ordinal and, for SHARD, the global index of its first column) */
+int32_t ihtb_mgeno_part(const ihtb_mgeno* g, int32_t i, ihtb_geno** part, int32_t* device, int64_t* j0);
+int32_t ihtb_mgeno_destroy(ihtb_mgeno* g);
+/* the ihtb_fit_* calls over a SHARD handle; arguments as in the single-device calls (weight / group have p entries).
+ * result and trace come from device 0 -- every device computes the same global model. */
+int32_t ihtb_mfit_create(const ihtb_mgeno* g, const double* y, const double* z, int64_t q, const uint8_t* zkeep,
+                         const ihtb_cfg* cfg, ihtb_mfit** out);
+int32_t ihtb_mfit_set_weights(ihtb_mfit* f, const double* weight);
+int32_t ihtb_mfit_set_groups(ihtb_mfit* f, const int32_t* group, int32_t J, const int64_t* ks, int64_t n_groups);
+int32_t ihtb_mfit_set_k(ihtb_mfit* f, int64_t k);
+int32_t ihtb_mfit_init(ihtb_mfit* f, const uint8_t* train_mask, int32_t init_beta);
+int32_t ihtb_mfit_run(ihtb_mfit* f, ihtb_result* result, ihtb_iter_trace* trace, int64_t trace_cap);
+int32_t ihtb_mfit_get(const ihtb_mfit* f, double* beta, double* c, double* mu, double* xb);
+int32_t ihtb_mfit_predict(ihtb_mfit* f, const uint8_t* test_mask, double* deviance);
+int32_t ihtb_mfit_timer(ihtb_mfit* f, int32_t which, double* ms);     /* slowest device's CUDA-event time */
+int32_t ihtb_mfit_destroy(ihtb_mfit* f);
+/* ihtb_cv_run over a REPLICATE handle: fits are taken from a shared queue, largest k first (more iterations);
+ * busy_seconds[ngpu] (optional) = wall time each device spent on its share */
+int32_t ihtb_mcv_run(const ihtb_mgeno* g, const double* y, const double* z, int64_t q, const uint8_t* zkeep,
+                     const ihtb_cfg* cfg, const int32_t* folds, int32_t nfolds, const int64_t* path, int64_t npath,
+                     const double* weight, double* mses, int64_t* iters, double* busy_seconds);
+
+/* ---- multi-GPU plumbing, one process per GPU (NCCL over NVLink; rendezvous of the 128-byte id is the host's job, e.g. torch.distributed) ---- */
 /* nccl_lib_path may be NULL: $IHTB_NCCL_LIB, then libnccl.so.2 are tried (dlopen at run time, no link-time dependency) */
 int32_t ihtb_comm_unique_id(const char* nccl_lib_path, uint8_t* out128);
 int32_t ihtb_comm_create(const char* nccl_lib_path, const uint8_t* id128, int32_t rank, int32_t nranks, ihtb_comm** out);
 int32_t ihtb_comm_destroy(ihtb_comm* c);
-/* collective: average device time (us) of `reps` back-to-back all-reduces of n doubles, use_p2p = 0: ncclAllReduce,
- * 1: the peer-memory push + local reduce that sharded fits use (IHTB_EUNSUPPORTED when IPC mapping is unavailable) */
+/* collective: average device time (us) of `reps` back-to-back all-reduces of n doubles.  use_p2p = 0: ncclAllReduce,
+ * 1: the peer-memory path sharded fits take for this n (push-all up to 262144 elements, two-phase reduce-scatter +
+ * all-gather above), 2: force push-all, 3: force two-phase (IHTB_EUNSUPPORTED when peer mapping is unavailable) */
 int32_t ihtb_comm_allreduce_bench(ihtb_comm* c, int64_t n, int32_t reps, int32_t use_p2p, double* us_per_op);
 int32_t ihtb_geno_set_offset(ihtb_geno* g, int64_t j0);   /* global index of local column 0 for host-uploaded shards */
 

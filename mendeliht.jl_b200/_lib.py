@@ -115,6 +115,25 @@ SIGNATURES = {
     "ihtb_comm_destroy": [_p],
     "ihtb_comm_allreduce_bench": [_p, C.c_int64, C.c_int32, C.c_int32, _f64],
     "ihtb_geno_set_offset": [_p, C.c_int64],
+    "ihtb_mgeno_create": [_u8, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                          C.POINTER(C.c_int32), C.c_int32, _pp],
+    "ihtb_mgeno_create_synthetic": [C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_int32, C.POINTER(C.c_int32),
+                                    C.c_int32, _pp],
+    "ihtb_mgeno_info": [_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i64, _i64],
+    "ihtb_mgeno_part": [_p, C.c_int32, _pp, C.POINTER(C.c_int32), _i64],
+    "ihtb_mgeno_destroy": [_p],
+    "ihtb_mfit_create": [_p, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), _pp],
+    "ihtb_mfit_set_weights": [_p, _f64],
+    "ihtb_mfit_set_groups": [_p, C.POINTER(C.c_int32), C.c_int32, _i64, C.c_int64],
+    "ihtb_mfit_set_k": [_p, C.c_int64],
+    "ihtb_mfit_init": [_p, _u8, C.c_int32],
+    "ihtb_mfit_run": [_p, C.POINTER(Result), C.POINTER(IterTrace), C.c_int64],
+    "ihtb_mfit_get": [_p, _f64, _f64, _f64, _f64],
+    "ihtb_mfit_predict": [_p, _u8, _f64],
+    "ihtb_mfit_timer": [_p, C.c_int32, _f64],
+    "ihtb_mfit_destroy": [_p],
+    "ihtb_mcv_run": [_p, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), C.POINTER(C.c_int32), C.c_int32, _i64, C.c_int64,
+                     _f64, _f64, _i64, _f64],
 }
 
 _lib = None

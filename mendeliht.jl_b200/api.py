@@ -167,6 +167,68 @@ class B200SnpLinAlg:
             pass
 
 
+class B200MultiSnpLinAlg:
+    """The genotype operator over several GPUs driven by THIS process (`ihtb_mgeno`, SURVEY.md 8b `ngpu`).
+    mode SHARD: SNP columns block-partitioned over the devices, `fit_iht` runs one fit over all of them;
+    mode REPLICATE: the whole matrix on every device, `cv_iht` farms its (fold, k) grid over them."""
+    SHARD, REPLICATE = 0, 1
+
+    def __init__(self, handle, n, p, ngpu, mode):
+        self._h = handle
+        self.n, self.p, self.ngpu, self.mode = int(n), int(p), int(ngpu), int(mode)
+        self.center = self.scale = self.impute = True
+
+    @staticmethod
+    def _devs(devices):
+        if devices is None:
+            return None
+        return (C.c_int32 * len(devices))(*[int(d) for d in devices])
+
+    @classmethod
+    def from_bed_columns(cls, bed_cols: np.ndarray, n: int, ngpu: int, mode: int = 0, devices=None, center=True,
+                         scale=True, impute=True):
+        bed_cols = np.ascontiguousarray(bed_cols, dtype=np.uint8)
+        if bed_cols.ndim != 2:
+            raise _lib.DimensionMismatch(_lib.IHTB_EDIM, "bed_cols must be [p, ceil(n/4)]")
+        h = C.c_void_p()
+        check(load().ihtb_mgeno_create(ptr(bed_cols, C.c_uint8), n, bed_cols.shape[0], bed_cols.shape[1], int(center),
+                                       int(scale), int(impute), int(ngpu), cls._devs(devices), int(mode), C.byref(h)))
+        return cls(h, n, bed_cols.shape[0], ngpu, mode)
+
+    @classmethod
+    def synthetic(cls, n: int, p: int, seed: int, missing_rate: float = 0.0, ngpu: int = 2, mode: int = 0, devices=None):
+        h = C.c_void_p()
+        check(load().ihtb_mgeno_create_synthetic(n, p, seed, missing_rate, int(ngpu), cls._devs(devices), int(mode),
+                                                 C.byref(h)))
+        return cls(h, n, p, ngpu, mode)
+
+    @property
+    def shape(self):
+        return (self.n, self.p)
+
+    def part(self, i: int) -> "B200SnpLinAlg":
+        """Borrowed single-device operator of part i (do not close it)."""
+        h = C.c_void_p(); dev = C.c_int32(0); j0 = C.c_int64(0)
+        check(load().ihtb_mgeno_part(self._h, int(i), C.byref(h), C.byref(dev), C.byref(j0)))
+        n, p = C.c_int64(0), C.c_int64(0)
+        check(load().ihtb_geno_dims(h, C.byref(n), C.byref(p)))
+        part = B200SnpLinAlg(h, n.value, p.value, j0.value)
+        part.close = lambda: None          # owned by the multi-device handle
+        part.device = int(dev.value)
+        return part
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().ihtb_mgeno_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 @dataclass
 class IHTResult:
     """`IHTResult` (src/data_structures.jl:245-258) + device-side counters."""
@@ -224,17 +286,27 @@ class IHTVariable:
                        int(max_step), int(sweep_mode), EST_R_ID[est_r], 1 if debias else 0)
         zf = np.asfortranarray(z)
         self._h = C.c_void_p()
-        check(load().ihtb_fit_create_sharded(x._h, comm._h if comm is not None else None, self.p_global,
-                                             ptr(y, C.c_double), zf.ctypes.data_as(C.POINTER(C.c_double)), q,
-                                             ptr(zk, C.c_uint8) if zk is not None else None, C.byref(self.cfg),
-                                             C.byref(self._h)))
+        # a SHARD multi-device operator runs the same calls through ihtb_mfit_* (one host thread per device inside)
+        self._multi = isinstance(x, B200MultiSnpLinAlg)
+        self._pre = "ihtb_mfit_" if self._multi else "ihtb_fit_"
+        if self._multi:
+            if x.mode != B200MultiSnpLinAlg.SHARD:
+                raise _lib.IHTBError(_lib.IHTB_EINVAL, "fit_iht over several GPUs needs a SHARD multi-device operator")
+            check(load().ihtb_mfit_create(x._h, ptr(y, C.c_double), zf.ctypes.data_as(C.POINTER(C.c_double)), q,
+                                          ptr(zk, C.c_uint8) if zk is not None else None, C.byref(self.cfg),
+                                          C.byref(self._h)))
+        else:
+            check(load().ihtb_fit_create_sharded(x._h, comm._h if comm is not None else None, self.p_global,
+                                                 ptr(y, C.c_double), zf.ctypes.data_as(C.POINTER(C.c_double)), q,
+                                                 ptr(zk, C.c_uint8) if zk is not None else None, C.byref(self.cfg),
+                                                 C.byref(self._h)))
         if group is not None and len(group) > 0:
             grp = np.ascontiguousarray(group, dtype=np.int32)
             try:
                 if grp.shape[0] != self.p_global:      # src/data_structures.jl:67-69
                     raise _lib.DimensionMismatch(_lib.IHTB_EDIM,
                                                  f"group must have length {self.p_global} but was {grp.shape[0]}")
-                check(load().ihtb_fit_set_groups(self._h, grp.ctypes.data_as(C.POINTER(C.c_int32)), int(J),
+                check(self._fn("set_groups")(self._h, grp.ctypes.data_as(C.POINTER(C.c_int32)), int(J),
                                                  ptr(ks, C.c_int64) if ks is not None else None,
                                                  0 if ks is None else ks.shape[0]))
             except Exception:
@@ -251,25 +323,37 @@ class IHTVariable:
                 raise _lib.DimensionMismatch(_lib.IHTB_EDIM,
                                              f"weight must have length {self.p_global} but was {w.shape[0]}")
             try:
-                check(load().ihtb_fit_set_weights(self._h, ptr(w, C.c_double)))
+                check(self._fn("set_weights")(self._h, ptr(w, C.c_double)))
             except Exception:
                 self.close()
                 raise
 
+    def _fn(self, name):
+        return getattr(load(), self._pre + name)
+
     def set_k(self, k):
-        check(load().ihtb_fit_set_k(self._h, int(k)))
+        check(self._fn("set_k")(self._h, int(k)))
         self.cfg.k = int(k)
 
     def init_iht_indices(self, train_mask=None, init_beta=False):
         m = None if train_mask is None else np.ascontiguousarray(train_mask, dtype=np.uint8)
-        fn = load().ihtb_fit_init_beta if init_beta else load().ihtb_fit_init
-        check(fn(self._h, ptr(m, C.c_uint8) if m is not None else None))
+        mp = ptr(m, C.c_uint8) if m is not None else None
+        if self._multi:
+            check(load().ihtb_mfit_init(self._h, mp, 1 if init_beta else 0))
+        else:
+            check((load().ihtb_fit_init_beta if init_beta else load().ihtb_fit_init)(self._h, mp))
+
+    def timer(self, which: int) -> float:
+        """CUDA-event stopwatch on the fit stream(s): which=0 start, 1 stop -> elapsed device ms (slowest device)."""
+        ms = C.c_double(0.0)
+        check(self._fn("timer")(self._h, int(which), C.byref(ms)))
+        return ms.value
 
     def fit(self, trace_cap=None):
         cap = int(self.cfg.max_iter) if trace_cap is None else trace_cap
         res = Result()
         tr = (IterTrace * max(cap, 1))()
-        check(load().ihtb_fit_run(self._h, C.byref(res), tr, cap))
+        check(self._fn("run")(self._h, C.byref(res), tr, cap))
         n_it = min(int(res.n_steps), cap)
         trace = [(tr[i].logl, tr[i].backtracks, tr[i].tol, tr[i].eta, tr[i].n_candidates) for i in range(n_it)]
         return res, trace
@@ -278,19 +362,19 @@ class IHTVariable:
         beta = np.empty(self.p); c = np.empty(self.q)
         m = np.empty(self.n) if mu else None
         x = np.empty(self.n) if xb else None
-        check(load().ihtb_fit_get(self._h, ptr(beta, C.c_double), ptr(c, C.c_double),
-                                  ptr(m, C.c_double) if mu else None, ptr(x, C.c_double) if xb else None))
+        check(self._fn("get")(self._h, ptr(beta, C.c_double), ptr(c, C.c_double),
+                              ptr(m, C.c_double) if mu else None, ptr(x, C.c_double) if xb else None))
         return beta, c, m, x
 
     def predict(self, test_mask=None) -> float:
         m = None if test_mask is None else np.ascontiguousarray(test_mask, dtype=np.uint8)
         dev = C.c_double(0.0)
-        check(load().ihtb_fit_predict(self._h, ptr(m, C.c_uint8) if m is not None else None, C.byref(dev)))
+        check(self._fn("predict")(self._h, ptr(m, C.c_uint8) if m is not None else None, C.byref(dev)))
         return float(dev.value)
 
     def close(self):
         if getattr(self, "_h", None):
-            load().ihtb_fit_destroy(self._h)
+            self._fn("destroy")(self._h)
             self._h = None
 
     def __del__(self):
@@ -503,6 +587,15 @@ def cv_run(y, x: B200SnpLinAlg, z, folds, q: int, path, d=NORMAL, l="IdentityLin
               int(sweep_mode), 0, 1 if debias else 0)
     mses = np.zeros(q * pa.shape[0]); iters = np.zeros(q * pa.shape[0], dtype=np.int64)
     w = None if weight is None else f64(weight)
+    if isinstance(x, B200MultiSnpLinAlg):      # REPLICATE handle: the grid is farmed over the devices from a work queue
+        busy = np.zeros(x.ngpu)
+        check(load().ihtb_mcv_run(x._h, ptr(y, C.c_double), zf.ctypes.data_as(C.POINTER(C.c_double)), nq,
+                                  ptr(zk, C.c_uint8) if zk is not None else None, C.byref(cfg),
+                                  fl.ctypes.data_as(C.POINTER(C.c_int32)), q, ptr(pa, C.c_int64), pa.shape[0],
+                                  ptr(w, C.c_double) if w is not None else None, ptr(mses, C.c_double),
+                                  ptr(iters, C.c_int64), ptr(busy, C.c_double)))
+        cv_run.last_busy_seconds = busy
+        return mses, iters
     check(load().ihtb_cv_run(x._h, ptr(y, C.c_double), zf.ctypes.data_as(C.POINTER(C.c_double)), nq,
                              ptr(zk, C.c_uint8) if zk is not None else None, C.byref(cfg),
                              fl.ctypes.data_as(C.POINTER(C.c_int32)), q, ptr(pa, C.c_int64), pa.shape[0],

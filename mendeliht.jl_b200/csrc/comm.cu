@@ -1,4 +1,6 @@
-// NCCL plumbing for SNP-sharded fits (one process per GPU; no reference equivalent).
+// NCCL plumbing for SNP-sharded fits (one process per GPU; no reference equivalent).  NCCL carries the
+// rendezvous (IPC handles of the peer-memory region) and is the fallback when peer mapping is unavailable; the
+// collectives of the IHT loop themselves run over peer memory (p2p.cu).
 // libnccl is loaded at run time (dlopen) so that libihtb200.so itself has no link-time NCCL dependency and loads on
 // machines without it; the torch-bundled libnccl.so.2 is reused when the host process already imported torch.
 #include "comm.cuh"
@@ -53,19 +55,21 @@ void nccl_check(int rc, const char* what) {
 
 constexpr int kNcclSum = 0, kNcclInt64 = 4, kNcclFloat64 = 8;
 
-void comm_allreduce_sum_f64(ihtb_comm* c, double* d_buf, size_t count, cudaStream_t s) {
+void nccl_allreduce_sum_f64(ihtb_comm* c, double* d_buf, size_t count, cudaStream_t s) {
     if (!c || c->nranks == 1 || count == 0) return;
+    IHTB_CHECK(c->comm, IHTB_ECUDA, "this communicator has no NCCL backend and its peer memory is not mapped");
     nccl_check(g_nccl.AllReduce(d_buf, d_buf, count, kNcclFloat64, kNcclSum, c->comm, s), "ncclAllReduce");
     ++c->n_collectives;
 }
 
-void comm_allgather_i64(ihtb_comm* c, const int64_t* d_send, int64_t* d_recv, size_t count_per_rank,
+void nccl_allgather_i64(ihtb_comm* c, const int64_t* d_send, int64_t* d_recv, size_t count_per_rank,
                         cudaStream_t s) {
     if (!c || c->nranks == 1) {
         if (d_send != d_recv)
             IHTB_CUDA(cudaMemcpyAsync(d_recv, d_send, count_per_rank * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
         return;
     }
+    IHTB_CHECK(c->comm, IHTB_ECUDA, "this communicator has no NCCL backend and its peer memory is not mapped");
     nccl_check(g_nccl.AllGather(d_send, d_recv, count_per_rank, kNcclInt64, c->comm, s), "ncclAllGather");
     ++c->n_collectives;
 }

@@ -148,15 +148,33 @@ struct ihtb_fit {
     // same with the local index / coefficient lists already on the device.  Sharded fits with the peer-memory path:
     // the partial vector is produced straight into every rank's slot and reduced locally (p2p.cu); otherwise NCCL.
     void support_matvec_dev(const int64_t* d_idx_loc, int64_t k_loc, const double* d_coef_loc, double* d_out) {
-        if (p2p_ready(comm, (size_t)n)) {
-            if (k_loc > 0) x_support_push(g, d_idx_loc, k_loc, d_coef_loc, comm, s);
-            else p2p_push(comm, nullptr, (size_t)n, s);
-            p2p_reduce(comm, d_out, (size_t)n, s);
+        support_matvec_dev_m(d_idx_loc, k_loc, d_coef_loc, 1, d_out);
+    }
+    // m models at once (coef is k_loc x m column-major, d_out is n x m): short vectors take the fused push-all path
+    // (m == 1), long ones are produced straight into this rank's partial area and reduced in two phases (p2p.cu)
+    void support_matvec_dev_m(const int64_t* d_idx_loc, int64_t k_loc, const double* d_coef_loc, int m, double* d_out) {
+        const size_t cnt = (size_t)n * (size_t)m;
+        if (!comm) {
+            if (k_loc > 0) x_support(g, d_idx_loc, k_loc, d_coef_loc, m, d_out, s);
+            else IHTB_CUDA(cudaMemsetAsync(d_out, 0, cnt * sizeof(double), s));
             return;
         }
-        if (k_loc > 0) x_support(g, d_idx_loc, k_loc, d_coef_loc, 1, d_out, s);
-        else IHTB_CUDA(cudaMemsetAsync(d_out, 0, n * sizeof(double), s));
-        comm_allreduce_sum_f64(comm, d_out, (size_t)n, s);
+        if (m == 1 && p2p_pushall_ok(comm, cnt)) {
+            if (k_loc > 0) x_support_push(g, d_idx_loc, k_loc, d_coef_loc, comm, s);
+            else p2p_push(comm, nullptr, cnt, s);
+            p2p_reduce(comm, d_out, cnt, s);
+            return;
+        }
+        if (p2p_mapped(comm) && cnt <= comm->red_cap) {
+            double* part = p2p_partial_ptr(comm);
+            if (k_loc > 0) x_support(g, d_idx_loc, k_loc, d_coef_loc, m, part, s);
+            else IHTB_CUDA(cudaMemsetAsync(part, 0, cnt * sizeof(double), s));
+            p2p_allreduce_2phase(comm, cnt, d_out, s);
+            return;
+        }
+        if (k_loc > 0) x_support(g, d_idx_loc, k_loc, d_coef_loc, m, d_out, s);
+        else IHTB_CUDA(cudaMemsetAsync(d_out, 0, cnt * sizeof(double), s));
+        comm_allreduce_sum_f64(comm, d_out, cnt, s);
     }
 
     // ---- update_xb! genetic part: xb = x[:, idx] * b[idx]  (src/utilities.jl:95-111) ------------
@@ -954,7 +972,7 @@ struct ihtb_fit {
     HBuf<double> h_scalM;
     bool batch_ok() const {
         static const bool off = [] { const char* e = getenv("IHTB_NO_BATCH"); return e && *e == '1'; }();
-        return !off && !comm && cfg.est_r == 0 && cfg.max_step >= 1 && cfg.max_step + 1 <= kMaxBatch;
+        return !off && cfg.est_r == 0 && cfg.max_step >= 1 && cfg.max_step + 1 <= kMaxBatch;
     }
     void one_step_batched(double old_logl, double& eta, int& eta_step, double& new_logl) {
         if (d_xbM.n < (size_t)(kMaxBatch * n)) {
@@ -990,12 +1008,22 @@ struct ihtb_fit {
             for (int64_t l = 0; l < q; ++l) cM[(size_t)(m * q + l)] = md.c[(size_t)l];
         }
         double t2 = now(); phase[1] += t2 - t1;
-        if (U) {
-            upload(d_idx.p, uni.data(), U);
-            upload(d_coefM.p, coefM.data(), coefM.size());
-            x_support(g, d_idx.p, (int64_t)U, d_coefM.p, M, d_xbM.p, s);
-        } else {
-            IHTB_CUDA(cudaMemsetAsync(d_xbM.p, 0, (size_t)(M * n) * sizeof(double), s));
+        {
+            // this rank's columns of the union (all of them on a single GPU), local indices, same order
+            std::vector<int64_t> loc; std::vector<double> coefL;
+            loc.reserve(U);
+            std::vector<size_t> keep_pos;
+            for (size_t t = 0; t < U; ++t)
+                if (is_local(uni[t])) { loc.push_back(uni[t] - j0); keep_pos.push_back(t); }
+            const size_t UL = loc.size();
+            coefL.resize(UL * (size_t)M);
+            for (int m = 0; m < M; ++m)
+                for (size_t t = 0; t < UL; ++t) coefL[t + (size_t)m * UL] = coefM[keep_pos[t] + (size_t)m * U];
+            if (UL) {
+                upload(d_idx.p, loc.data(), UL);
+                upload(d_coefM.p, coefL.data(), coefL.size());
+            }
+            support_matvec_dev_m(UL ? d_idx.p : nullptr, (int64_t)UL, d_coefM.p, M, d_xbM.p);
         }
         upload(d_cM.p, cM.data(), cM.size());
         glm_mu_batched(glm, d_cM.p, M, d_xbM.p, d_zcM.p, d_muM.p, d_partM.p, d_scalM.p, s);
@@ -1118,7 +1146,7 @@ extern "C" {
 // ihtb_fit_create with the same shape on the same device.
 static std::mutex g_cache_mu;
 static std::vector<ihtb_fit*> g_cache;
-static const size_t kCacheMax = 4;
+static const size_t kCacheMax = 16;     // up to 8 devices x 2 shapes
 
 static ihtb_fit* cache_take(int device, int64_t n, int64_t p, int64_t q, int cap) {
     std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -1202,6 +1230,10 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
         f->shard_j0.clear();
         if (f->comm) {
             const int nr = comm->nranks;
+            // peer-memory region (collective; multi-process fits silently stay on NCCL if IPC mapping is unavailable):
+            // all-reduce areas for the batched step (kMaxBatch n-vectors), gather blocks for the candidate exchange
+            p2p_setup(comm, (size_t)ihtb_fit::kMaxBatch * (size_t)n,
+                      (size_t)(2 + 2 * std::max<int64_t>(1024, 2 * (2 * cfg->k + 64 + 64))), f->s);
             if (f->d_selall.n < (size_t)nr * (2 + cap)) {
                 f->d_selall.alloc((size_t)nr * (2 + cap));
                 f->h_selall.alloc((size_t)nr * (2 + cap));
@@ -1221,7 +1253,7 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
             IHTB_CUDA(cudaMemcpyAsync(f->shard_j0.data(), f->d_selall.p, nr * sizeof(int64_t), cudaMemcpyDeviceToHost,
                                       f->s));
             IHTB_CUDA(cudaStreamSynchronize(f->s));
-            p2p_setup(comm, (size_t)n, f->s);      // collective; silently stays on NCCL if IPC mapping is unavailable
+
         }
         f->zkeep.assign((size_t)q, 1);
         if (zkeep) for (int64_t l = 0; l < q; ++l) f->zkeep[l] = zkeep[l] ? 1 : 0;

@@ -98,7 +98,7 @@ static void launch_x_support(const ihtb_geno* g, const int64_t* d_idx, int64_t k
 void x_support_push(const ihtb_geno* g, const int64_t* d_idx, int64_t k, const double* d_coef, ihtb_comm* c,
                     cudaStream_t s) {
     IHTB_LAUNCH((k_x_support<1, true>), (unsigned)ceil_div(g->nbytes, 256), 256, 0, s, geno_view(g), d_idx, k, d_coef,
-                (double*)nullptr, p2p_view(c), (unsigned long long)(c->p2p_seq + 1));
+                (double*)nullptr, p2p_view(c), (unsigned long long)(c->seq[0] + 1));
 }
 
 void x_support(const ihtb_geno* g, const int64_t* d_idx, int64_t k, const double* d_coef, int64_t m, double* d_out,
