@@ -61,7 +61,7 @@ typedef struct ihtb_cfg {
     int32_t max_iter;    /* 200 (100 in cv_iht)                               `max_iter` */
     int32_t min_iter;    /* 5                                                 `min_iter` */
     int32_t max_step;    /* 3                                                 `max_step` */
-    int32_t sweep_mode;  /* IHTB_SWEEP_FAST | IHTB_SWEEP_EXACT                           */
+    int32_t sweep_mode;  /* IHTB_SWEEP_FAST | IHTB_SWEEP_EXACT (| IHTB_SWEEP_PAIR: multivariate fits) */
     int32_t est_r;       /* 0 = :None, 1 = :MM, 2 = :Newton (NegativeBinomial only)   `est_r`    */
     int32_t debias;      /* 1: refit the support by IRLS when it did not change, iterations >= 5 (src/fit.jl:187-188) */
 } ihtb_cfg;
@@ -172,8 +172,9 @@ int32_t ihtb_fit_destroy(ihtb_fit* f);
 
 /* ---- multivariate Normal fit (mIHTVariable, src/multivariate.jl; fit_iht(Y, Transpose(xla), Z), src/fit.jl:60-118) ----
  * Y is n x r column-major (one trait per column; the reference stores r x n), z is n x q column-major with the
- * intercept first, 2 <= r <= 16, every covariate kept.  cfg->k counts non-zero ENTRIES of the r x p matrix B
- * (src/data_structures.jl:233); cfg->dist / link are ignored. */
+ * intercept first, 2 <= r <= 20, every covariate kept.  cfg->k counts non-zero ENTRIES of the r x p matrix B
+ * (src/data_structures.jl:233); cfg->dist / link are ignored.  cfg->sweep_mode = IHTB_SWEEP_PAIR reads the matrix once
+ * per two traits (the skinny X'R of src/multivariate.jl:85). */
 int32_t ihtb_mvfit_create(const ihtb_geno* g, const double* Y, int64_t r, const double* z, int64_t q,
                           const ihtb_cfg* cfg, ihtb_mvfit** out);
 int32_t ihtb_mvfit_set_k(ihtb_mvfit* f, int64_t k);

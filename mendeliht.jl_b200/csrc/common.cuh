@@ -149,6 +149,10 @@ struct ihtb_geno {
     int sm_count = 148;
     ihtb::DBuf<uint8_t> bed;  // p * stride bytes
     ihtb::DBuf<double> mu, sinv;
+    // sgn_j = sinv_j * max(sqrt(sum_i g_ij^2), 1): per-column scale of the L2 error bounds of the table sweeps --
+    // the absolute dot product sum_i g_ij |u_i| that every rounding error is relative to is at most
+    // sqrt(sum_i g_ij^2) * ||u||_2 (Cauchy-Schwarz), which is far tighter than 2 ||u||_1 for the PAIR sweep
+    ihtb::DBuf<double> sgn;
     ihtb::DBuf<int32_t> nmiss;
     // CSR of missing samples per column (sparse imputation correction of the sweep)
     ihtb::DBuf<int64_t> miss_ptr;   // [p+1]

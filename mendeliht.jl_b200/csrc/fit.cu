@@ -17,6 +17,7 @@
 #include "comm.cuh"
 #include "debias.cuh"
 #include "groups.cuh"
+#include "pairer.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -27,7 +28,7 @@
 
 namespace ihtb {
 void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* vbar_host, int64_t m, double* dOut,
-                           int mode, cudaStream_t s, void* scratch_any, float* sweep_ms);
+                           int mode, cudaStream_t s, void* scratch_any, float* sweep_ms, double* d_l2 = nullptr);
 void* sweep_scratch_create();
 void sweep_scratch_destroy(void* p);
 void sweep_class_sums(const ihtb_geno* g, const double* d_v, double* d_w1, double* d_w2, double* d_wm, cudaStream_t s,
@@ -42,6 +43,11 @@ using namespace ihtb;
 // we use 2^-18 = 3.8e-6 (2.7x margin).  The FP64 cross-slab sums add < 1e-13.
 static const double kFastBound = 1.0 / 262144.0;
 static const double kExactBound = 1e-13;
+// PAIR sweep (half2 tables, sweep_lut.cu): one FP16 rounding per table entry + two levels of HADD2 per packed word, each
+// at most 2^-11 of a partial sum bounded by A_j = sum_i g_ij |u_i| <= sqrt(sum_i g_ij^2) ||u||_2 (Cauchy-Schwarz); FP32
+// conversions and sums, the FP32 rounding of u and FP16 subnormals add less than 2^-16 of that.  The bound is
+// kPairBound * ||u||_2 * sgn_j with the per-column scale sgn_j = sinv_j * max(sqrt(sum_i g_ij^2), 1) of the handle.
+static const double kPairBound = 3.1 / 2048.0;
 
 struct ihtb_fit {
     const ihtb_geno* g = nullptr;
@@ -74,6 +80,10 @@ struct ihtb_fit {
     void* sweep_scratch = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
     bool sweep_pending = false;
+    // cross-validation farm: two fits of one device share their sweeps (pairer.cuh); null = every sweep alone
+    SweepPairer* pairer = nullptr;
+    int pair_slot = 0;
+    double sweep_coef = kFastBound;       // error-bound coefficient of the LAST sweep (what the selection must assume)
     GlmCtx glm{};
     TopkCtx tk{};
 
@@ -106,7 +116,7 @@ struct ihtb_fit {
     bool inited = false;
 
     // statistics
-    int64_t n_sweeps = 0, n_backtracks = 0, n_cand_iter = 0;
+    int64_t n_sweeps = 0, n_backtracks = 0, n_cand_iter = 0, n_pair_overflow = 0;
     double sweep_ms_total = 0.0;
     double pve = 0.0;
 
@@ -311,7 +321,17 @@ struct ihtb_fit {
         glm_mean_from_sum(glm, d_vbar.p, s);                 // d_vbar[0] = scal[0] / n
         IHTB_CUDA(cudaMemcpyAsync(h_scal.p, d_scal.p, (2 + q) * sizeof(double), cudaMemcpyDeviceToHost, s));
         IHTB_CUDA(cudaEventRecord(ev0, s));
-        sweep_xt_v_with_means(g, d_r.p, d_vbar.p, 1, d_dfa.p, cfg.sweep_mode, s, sweep_scratch, nullptr);
+        sweep_coef = cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound;
+        if (pairer && cfg.sweep_mode == IHTB_SWEEP_FAST) {
+            IHTB_CHECK(!grouped() && !comm, IHTB_EUNSUPPORTED, "paired sweeps serve plain single-device fits only");
+            if (pairer->sweep(pair_slot, g, d_r.p, d_vbar.p, d_dfa.p, s, sweep_scratch)) {
+                sweep_coef = kPairBound;
+                // ||r - mean||_2 of this fit travels back with the other score sums
+                IHTB_CUDA(cudaMemcpyAsync(h_scal.p + 3 + q, pairer->d_l2 + pair_slot, sizeof(double), cudaMemcpyDeviceToHost, s));
+            }
+        } else {
+            sweep_xt_v_with_means(g, d_r.p, d_vbar.p, 1, d_dfa.p, cfg.sweep_mode, s, sweep_scratch, nullptr);
+        }
         IHTB_CUDA(cudaEventRecord(ev1, s));
         ++n_sweeps;
         select_rescore(/*rerun=*/false);
@@ -323,12 +343,12 @@ struct ihtb_fit {
     void select_rescore(bool rerun) {
         if (grouped() && !init_plain) {
             select_groups(rerun);
-            if (!rerun) finish_sweep_scalars(cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound);
+            if (!rerun) finish_sweep_scalars(sweep_coef);
             return;
         }
         df_exact.clear(); cand_cache.clear();
         df_sparse = false;
-        const double coef = cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound;
+        const double coef = sweep_coef;
         // this rank's part of the current support (local indices)
         std::vector<int64_t> supp_loc;
         for (int64_t j : idx)
@@ -337,8 +357,11 @@ struct ihtb_fit {
         int glaunch = 0;
         if (cfg.k > 0) {
             const int64_t ksel = cfg.k + (int64_t)idx.size();
-            topk_candidates_absdf(tk, d_dfa.p, g->sinv.p, rerun ? nullptr : d_scal.p, coef, ksel, s, bound);
-            glaunch = (int)std::min<int64_t>(comm ? capx / 2 : cap, ksel + 64);
+            const bool paired = coef == kPairBound;        // L2 bound over the handle's sgn scale (see kPairBound)
+            topk_candidates_absdf(tk, d_dfa.p, paired ? g->sgn.p : g->sinv.p, rerun ? nullptr : d_scal.p, coef, ksel, s, bound,
+                                  (paired && !rerun) ? pairer->d_l2 + pair_slot : nullptr);
+            // slots re-scored without a second round trip; the looser bound of a PAIR sweep admits more near-threshold columns
+            glaunch = (int)std::min<int64_t>(comm ? capx / 2 : cap, ksel + (sweep_coef == kPairBound ? 1024 : 64));
             xt_gather(g, tk.cand, glaunch, d_r.p, 1, d_vbar.p, d_gout.p, s);      // slots beyond the count hold -1
         }
         if (nsupp) {
@@ -363,6 +386,16 @@ struct ihtb_fit {
             sync();
             const TopkState* st = reinterpret_cast<const TopkState*>(h_sel.p);
             const int count = cfg.k > 0 ? st->count : 0;
+            if (count > cap && coef == kPairBound && !rerun) {
+                // the looser bound of the PAIR sweep admits more columns than can be re-scored: sweep this residual
+                // alone with the FP32 tables and select again (results never depend on which sweep served them)
+                ++n_pair_overflow;
+                sweep_coef = kFastBound;
+                sweep_xt_v_with_means(g, d_r.p, d_vbar.p, 1, d_dfa.p, IHTB_SWEEP_FAST, s, sweep_scratch, nullptr);
+                IHTB_CUDA(cudaEventRecord(ev1, s));
+                select_rescore(false);
+                return;
+            }
             IHTB_CHECK(count <= cap, IHTB_ENUMERIC,
                        "degenerate projection: more than " + std::to_string(cap) +
                            " entries lie within the sweep error bound of the k-th largest |gradient|");
@@ -442,7 +475,8 @@ struct ihtb_fit {
         for (int64_t l = 0; l < q; ++l) df2[l] = h_scal.p[2 + l];
         denom_next = h_scal.p[2 + q];
         rbar = rsum / (double)n;
-        bound = coef * (rl1 + std::fabs(rsum));              // same value the selection kernel used
+        bound = coef == kPairBound ? coef * h_scal.p[3 + q]  // same value the selection kernel used
+                                   : coef * (rl1 + std::fabs(rsum));
     }
 
     double df_at(int64_t j) const {
@@ -552,7 +586,7 @@ struct ihtb_fit {
         GroupCtx& gc = *grpctx;
         df_exact.clear(); cand_cache.clear();
         df_sparse = false; denom_ready = false;
-        const double coef = cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound;
+        const double coef = sweep_coef;
         group_topk(gc, d_dfa.p, g->sinv.p, rerun ? nullptr : d_scal.p, coef, bound, cfg.k, s);
         const size_t G = (size_t)gc.G, nT = 2 * G + 1;
         const int nr = nranks();
@@ -1391,53 +1425,10 @@ int32_t ihtb_fit_phase_times(const ihtb_fit* f, double* out4) {
     });
 }
 
-// cv_iht in one call (src/cross_validation.jl:60-131): the (fold, k) grid of allocate_fold_and_k (:217-223) run back
-// to back on one workspace -- every fit sweeps all n rows with the fold masked out, mu_j / sigma_j stay full-sample --
-// and the out-of-fold deviance of each fit (predict!, :279-286).  mses is fold-major, nfolds x npath; the caller
-// applies meanloss (:304-320).  The reference fans this grid out over threads; one GPU runs it sequentially, several
-// GPUs deal the grid round-robin (parallel.py).
-int32_t ihtb_cv_run(const ihtb_geno* g, const double* y, const double* z, int64_t q, const uint8_t* zkeep,
-                    const ihtb_cfg* cfg, const int32_t* folds, int32_t nfolds, const int64_t* path, int64_t npath,
-                    const double* weight, double* mses, int64_t* iters) {
-    int32_t rc = guard([&] {
-        IHTB_CHECK(g && cfg && folds && path && mses, IHTB_EINVAL, "NULL argument");
-        IHTB_CHECK(nfolds >= 1 && npath >= 1, IHTB_EINVAL, "empty cross-validation grid");
-        for (int64_t t = 0; t < npath; ++t)
-            IHTB_CHECK(path[t] >= 0 && path[t] <= g->p, IHTB_EINVAL,
-                       "Sparsity level in `path` cannot be larger than total number of variables");
-    });
-    if (rc != IHTB_OK) return rc;
-    ihtb_cfg c = *cfg;
-    c.k = *std::max_element(path, path + npath);
-    ihtb_fit* f = nullptr;
-    rc = ihtb_fit_create(g, y, z, q, zkeep, &c, &f);
-    if (rc != IHTB_OK) return rc;
-    if (weight) rc = ihtb_fit_set_weights(f, weight);
-    const int64_t n = g->n;
-    std::vector<uint8_t> train((size_t)n), test((size_t)n);
-    for (int32_t fold = 1; fold <= nfolds && rc == IHTB_OK; ++fold) {
-        for (int64_t i = 0; i < n; ++i) { test[(size_t)i] = folds[i] == fold; train[(size_t)i] = !test[(size_t)i]; }
-        for (int64_t t = 0; t < npath && rc == IHTB_OK; ++t) {
-            ihtb_result res;
-            double dev = 0.0;
-            rc = ihtb_fit_set_k(f, path[t]);
-            if (rc == IHTB_OK) rc = ihtb_fit_init(f, train.data());
-            if (rc == IHTB_OK) rc = ihtb_fit_run(f, &res, nullptr, 0);
-            if (rc == IHTB_OK) rc = ihtb_fit_predict(f, test.data(), &dev);
-            if (rc == IHTB_OK) {
-                mses[(int64_t)(fold - 1) * npath + t] = dev;
-                if (iters) iters[(int64_t)(fold - 1) * npath + t] = res.iter;
-            }
-        }
-    }
-    if (rc != IHTB_OK) {                       // keep the first error message across the cleanup call
-        char msg[1024];
-        ihtb_last_error(msg, sizeof(msg));
-        ihtb_fit_destroy(f);
-        set_last_error(msg);
-        return rc;
-    }
-    return ihtb_fit_destroy(f);
+// (C linkage, internal: multi.cu) two fits of one device share their sweeps; pairer == NULL detaches
+void ihtb_internal_fit_set_pairer(ihtb_fit* f, void* pairer, int slot) {
+    f->pairer = reinterpret_cast<ihtb::SweepPairer*>(pairer);
+    f->pair_slot = slot;
 }
 
 int32_t ihtb_fit_destroy(ihtb_fit* f) {
@@ -1446,6 +1437,7 @@ int32_t ihtb_fit_destroy(ihtb_fit* f) {
         cudaSetDevice(f->device);
         cudaStreamSynchronize(f->s);
         f->g = nullptr;
+        f->pairer = nullptr;
         {
             std::lock_guard<std::mutex> lk(g_cache_mu);
             if (g_cache.size() < kCacheMax) { g_cache.push_back(f); return; }

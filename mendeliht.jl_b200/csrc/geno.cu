@@ -76,7 +76,7 @@ __global__ void k_export(GenoView g, int64_t j0, int64_t ncols, uint8_t* __restr
 // mu_j = (n1 + 2 n2) / n_obs ; sigma_inv_j = 1/sqrt(mu_j (1 - mu_j/2)) or 1 (same statistic as the
 // reference's standardize_genotypes!, src/wrapper.jl:409-416)
 __global__ void k_col_stats(GenoView g, int scale, double* __restrict__ mu, double* __restrict__ sinv,
-                            int32_t* __restrict__ nmiss) {
+                            int32_t* __restrict__ nmiss, double* __restrict__ sgn) {
     int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (j >= g.p) return;
@@ -101,8 +101,11 @@ __global__ void k_col_stats(GenoView g, int scale, double* __restrict__ mu, doub
         double m = (double)((int64_t)c1 + 2 * (int64_t)c2) / nobs;
         double s = sqrt(__dmul_rn(m, __dsub_rn(1.0, m / 2.0)));
         mu[j] = m;
-        sinv[j] = (scale && s > 0.0) ? 1.0 / s : 1.0;
+        const double si = (scale && s > 0.0) ? 1.0 / s : 1.0;
+        sinv[j] = si;
         nmiss[j] = cm;
+        const double g2 = sqrt((double)((int64_t)c1 + 4 * (int64_t)c2));      // sqrt(sum of squared dosages)
+        sgn[j] = si * (g2 > 1.0 ? g2 : 1.0);
     }
 }
 
@@ -203,10 +206,10 @@ __global__ void k_synth(GenoView g, int64_t j0, uint64_t seed, uint32_t miss_thr
 // ---------------------------------------------------------------------------------------------
 static void finish_handle(ihtb_geno* g) {
     cudaStream_t s = 0;
-    g->mu.alloc(g->p); g->sinv.alloc(g->p); g->nmiss.alloc(g->p);
+    g->mu.alloc(g->p); g->sinv.alloc(g->p); g->nmiss.alloc(g->p); g->sgn.alloc(g->p);
     int64_t threads = g->p * 32;
     IHTB_LAUNCH(k_col_stats, (unsigned)ceil_div(threads, 256), 256, 0, s, geno_view(g), g->scale, g->mu.p, g->sinv.p,
-                g->nmiss.p);
+                g->nmiss.p, g->sgn.p);
     g->miss_ptr.alloc(g->p + 1);
     int64_t total = 0;
     {   // exclusive scan of the per-column missing counts (host: once per handle, p <= a few million)

@@ -7,6 +7,7 @@
 //               (reference src/cross_validation.jl:98-121, a `Threads.@threads` loop) over the devices from a shared
 //               work queue, longest fits (largest k) first.
 #include "comm.cuh"
+#include "pairer.cuh"
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -283,23 +284,29 @@ int32_t ihtb_mfit_destroy(ihtb_mfit* f) {
     });
 }
 
-// ---- cv_iht over a REPLICATE handle: the (fold, k) grid from a shared work queue ------------------------------------
-// mses / iters are fold-major like ihtb_cv_run; busy_seconds[ngpu] (optional) = wall time every device spent fitting.
-// Fits are dealt longest first (larger k -> more iterations), so the devices finish together.
-int32_t ihtb_mcv_run(const ihtb_mgeno* g, const double* y, const double* z, int64_t q, const uint8_t* zkeep,
-                     const ihtb_cfg* cfg, const int32_t* folds, int32_t nfolds, const int64_t* path, int64_t npath,
-                     const double* weight, double* mses, int64_t* iters, double* busy_seconds) {
+// ---- cv_iht: the (fold, k) grid from a shared work queue -----------------------------------------------------------------
+// cv_iht (reference src/cross_validation.jl:60-131) runs q * |path| independent fits on training masks of the SAME matrix
+// (allocate_fold_and_k :217-223; mu_j / sigma_j stay full-sample) and scores each on its held-out fold (predict!,
+// :279-286).  The reference fans the grid out over Julia threads; here every device runs TWO fits at a time, each on its
+// own host thread and stream, and their X'r sweeps are served pairwise by one pass over the matrix (pairer.cuh) -- the
+// grid is bound by the sweep, so this nearly halves the matrix traffic.  Fits come from a shared atomic queue, largest
+// k first (more iterations), so the devices finish together.  mses / iters are fold-major, nfolds x npath; the caller
+// applies meanloss (:304-320).  IHTB_CV_PAIR=0 runs one fit at a time per device.
+extern "C" void ihtb_internal_fit_set_pairer(ihtb_fit* f, void* pairer, int slot);
+
+static int32_t cv_farm(const std::vector<ihtb_geno*>& parts, const std::vector<int>& devices, int64_t n, int64_t p,
+                       const double* y, const double* z, int64_t q, const uint8_t* zkeep, const ihtb_cfg* cfg,
+                       const int32_t* folds, int32_t nfolds, const int64_t* path, int64_t npath, const double* weight,
+                       double* mses, int64_t* iters, double* busy_seconds) {
     int32_t rc = guard([&] {
-        IHTB_CHECK(g && y && z && cfg && folds && path && mses, IHTB_EINVAL, "NULL argument");
-        IHTB_CHECK(g->mode == IHTB_MULTI_REPLICATE, IHTB_EINVAL, "ihtb_mcv_run needs a REPLICATE multi-device handle");
+        IHTB_CHECK(y && z && cfg && folds && path && mses, IHTB_EINVAL, "NULL argument");
         IHTB_CHECK(nfolds >= 1 && npath >= 1, IHTB_EINVAL, "empty cross-validation grid");
         for (int64_t t = 0; t < npath; ++t)
-            IHTB_CHECK(path[t] >= 0 && path[t] <= g->p, IHTB_EINVAL,
+            IHTB_CHECK(path[t] >= 0 && path[t] <= p, IHTB_EINVAL,
                        "Sparsity level in `path` cannot be larger than total number of variables");
     });
     if (rc != IHTB_OK) return rc;
-    const int64_t n = g->n, ngrid = (int64_t)nfolds * npath;
-    // queue order: descending k, then fold
+    const int64_t ngrid = (int64_t)nfolds * npath;
     std::vector<int64_t> order((size_t)ngrid);
     for (int64_t i = 0; i < ngrid; ++i) order[(size_t)i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return path[a % npath] > path[b % npath]; });
@@ -307,18 +314,37 @@ int32_t ihtb_mcv_run(const ihtb_mgeno* g, const double* y, const double* z, int6
     std::atomic<bool> stop(false);
     ihtb_cfg c = *cfg;
     c.k = *std::max_element(path, path + npath);
-    const int nd = (int)g->devices.size();
-    rc = on_all_ranks(nd, g->devices, nullptr, [&](int r) -> int32_t {
+    const int nd = (int)devices.size();
+    // Pairing pays while the PAIR sweep's looser error bound (3.1 * 2^-11 ||u||_2 sgn_j, about 0.0023 sqrt(n) null
+    // standard deviations of a gradient entry) keeps the list of columns to re-score short: on by default up to
+    // n = 20000 samples; IHTB_CV_PAIR=1 forces it (a fit whose list overflows re-sweeps alone), IHTB_CV_PAIR=0 disables it.
+    static const int pair_env = [] { const char* e = getenv("IHTB_CV_PAIR"); return e ? atoi(e) : -1; }();
+    const bool want_pair = pair_env == 1 || (pair_env != 0 && n <= 20000);
+    // the pair sweep needs a tiled layout, FAST arithmetic and at least two fits to pair
+    const int per_dev = (want_pair && c.sweep_mode == IHTB_SWEEP_FAST && ngrid >= 2 && parts[0]->cs_j == 128) ? 2 : 1;
+    std::vector<std::unique_ptr<SweepPairer>> pairers((size_t)nd);
+    if (per_dev == 2) {
+        rc = guard([&] { for (int d = 0; d < nd; ++d) pairers[(size_t)d].reset(new SweepPairer(devices[(size_t)d])); });
+        if (rc != IHTB_OK) return rc;
+    }
+    const int nworkers = nd * per_dev;
+    std::vector<int> wdev((size_t)nworkers);
+    for (int w = 0; w < nworkers; ++w) wdev[(size_t)w] = devices[(size_t)(w / per_dev)];
+    std::vector<double> wbusy((size_t)nworkers, 0.0);
+    rc = on_all_ranks(nworkers, wdev, nullptr, [&](int w) -> int32_t {
+        const int d = w / per_dev, slot = w % per_dev;
+        SweepPairer* pr = per_dev == 2 ? pairers[(size_t)d].get() : nullptr;
         ihtb_fit* f = nullptr;
-        int32_t e = ihtb_fit_create(g->parts[(size_t)r], y, z, q, zkeep, &c, &f);
+        int32_t e = ihtb_fit_create(parts[(size_t)d], y, z, q, zkeep, &c, &f);
         if (e == IHTB_OK && weight) e = ihtb_fit_set_weights(f, weight);
+        if (e == IHTB_OK && pr) ihtb_internal_fit_set_pairer(f, pr, slot);
         std::vector<uint8_t> train((size_t)n), test((size_t)n);
         int last_fold = -1;
         const auto t0 = std::chrono::steady_clock::now();
         while (e == IHTB_OK && !stop.load()) {
-            const int64_t slot = next.fetch_add(1);
-            if (slot >= ngrid) break;
-            const int64_t i = order[(size_t)slot];
+            const int64_t pos = next.fetch_add(1);
+            if (pos >= ngrid) break;
+            const int64_t i = order[(size_t)pos];
             const int fold = (int)(i / npath) + 1;
             const int64_t t = i % npath;
             if (fold != last_fold) {
@@ -336,18 +362,48 @@ int32_t ihtb_mcv_run(const ihtb_mgeno* g, const double* y, const double* z, int6
                 if (iters) iters[i] = res.iter;
             }
         }
-        if (busy_seconds)
-            busy_seconds[r] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        wbusy[(size_t)w] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (pr) pr->leave();                          // the partner sweeps alone from now on (also on an error)
         if (e != IHTB_OK) {
             stop.store(true);
             std::string m = last_error();
-            if (f) ihtb_fit_destroy(f);
+            if (f) { ihtb_internal_fit_set_pairer(f, nullptr, 0); ihtb_fit_destroy(f); }
             set_last_error(m);
             return e;
         }
+        ihtb_internal_fit_set_pairer(f, nullptr, 0);
         return ihtb_fit_destroy(f);
     });
+    if (busy_seconds)
+        for (int d = 0; d < nd; ++d) {
+            double b = 0.0;
+            for (int sl = 0; sl < per_dev; ++sl) b = std::max(b, wbusy[(size_t)(d * per_dev + sl)]);
+            busy_seconds[d] = b;
+        }
     return rc;
+}
+
+// cv_iht in one call on ONE device
+int32_t ihtb_cv_run(const ihtb_geno* g, const double* y, const double* z, int64_t q, const uint8_t* zkeep,
+                    const ihtb_cfg* cfg, const int32_t* folds, int32_t nfolds, const int64_t* path, int64_t npath,
+                    const double* weight, double* mses, int64_t* iters) {
+    if (!g) { set_last_error("NULL argument"); return IHTB_EINVAL; }
+    std::vector<ihtb_geno*> parts{const_cast<ihtb_geno*>(g)};
+    std::vector<int> devices{g->device};
+    return cv_farm(parts, devices, g->n, g->p, y, z, q, zkeep, cfg, folds, nfolds, path, npath, weight, mses, iters, nullptr);
+}
+
+// ... and over the replicas of a REPLICATE handle; busy_seconds[ngpu] (optional) = wall time every device spent fitting
+int32_t ihtb_mcv_run(const ihtb_mgeno* g, const double* y, const double* z, int64_t q, const uint8_t* zkeep,
+                     const ihtb_cfg* cfg, const int32_t* folds, int32_t nfolds, const int64_t* path, int64_t npath,
+                     const double* weight, double* mses, int64_t* iters, double* busy_seconds) {
+    if (!g) { set_last_error("NULL argument"); return IHTB_EINVAL; }
+    if (g->mode != IHTB_MULTI_REPLICATE) {
+        set_last_error("ihtb_mcv_run needs a REPLICATE multi-device handle");
+        return IHTB_EINVAL;
+    }
+    return cv_farm(g->parts, g->devices, g->n, g->p, y, z, q, zkeep, cfg, folds, nfolds, path, npath, weight, mses, iters,
+                   busy_seconds);
 }
 
 }  // extern "C"

@@ -3,8 +3,9 @@
 // Reference function (src/multivariate.jl) -> here
 //   init_iht_indices! :376-452 -> ihtb_mvfit::init          loglikelihood :9-13, solve_Sigma! :276-282 -> resid_gram + host r x r
 //   update_xb! :21-31, update_mu! :39-43, update_resid! :50-58 -> k_x_support<M> + k_mv_resid_gram
-//   score!/update_df! :66-92 (skinny X'R) -> k_mv_score + r single-RHS sweeps (the byte-LUT sweep is shared-memory-pipe
-//       bound, so r passes cost the same LDS work as one multi-RHS pass would)
+//   score!/update_df! :66-92 (skinny X'R, SnpArrays.mul! with an n x r matrix at :85) -> k_mv_score + the sweep:
+//       sweep_mode PAIR reads the matrix once per TWO traits (half2 lookup tables, sweep_lut.cu), an odd last trait and
+//       sweep_mode FAST / EXACT take one single-vector pass per trait; every candidate entry is re-scored in FP64
 //   iht_stepsize! :220-254 (pivoted Cholesky, permutation dropped) -> k_x_support<M> + k_mv_stepsize + host dpstrf
 //   _iht_gradstep!/project_k! :99-127 -> topk_candidates over the r*p entries + exact re-scoring + host top-k
 //   save_prev! :356-367, check_convergence :454-458, backtrack! :460-473, save_best_model! :485-496, pve src/pve.jl:35
@@ -21,14 +22,14 @@
 #include <memory>
 
 namespace ihtb {
-void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* d_vbar, int64_t m, double* dOut,
-                           int mode, cudaStream_t s, void* scratch_any, float* sweep_ms);
+void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* vbar_host, int64_t m, double* dOut,
+                           int mode, cudaStream_t s, void* scratch_any, float* sweep_ms, double* d_l2 = nullptr);
 void* sweep_scratch_create();
 void sweep_scratch_destroy(void* p);
 void sweep_class_sums(const ihtb_geno* g, const double* d_v, double* d_w1, double* d_w2, double* d_wm, cudaStream_t s,
                       void* scratch_any);
 
-constexpr int MV_MAXR = 16;
+constexpr int MV_MAXR = 20;       // the reference paper goes up to 18 traits
 constexpr int MV_THREADS = 256;
 static inline int mv_grid(int64_t n) {
     int64_t b = ceil_div(n, MV_THREADS);
@@ -226,6 +227,10 @@ using namespace ihtb;
 
 static const double kFastBoundMv = 1.0 / 262144.0;
 static const double kExactBoundMv = 1e-13;
+// sweep_mode PAIR: every bound is an L2 bound over the handle's sgn scale (fit.cu kPairBound): paired traits
+// 3.1 * 2^-11 ||u||_2 sgn_j (half2 tables), an odd last trait 2^-20 ||u||_2 sgn_j (FP32 tables: 12 roundings of 2^-24)
+static const double kPairBoundMv = 3.1 / 2048.0;
+static const double kFastL2BoundMv = 1.0 / 1048576.0;
 
 struct ihtb_mvfit {
     const ihtb_geno* g = nullptr;
@@ -241,7 +246,8 @@ struct ihtb_mvfit {
     DBuf<uint32_t> d_keyL, d_keyU;
     DBuf<int> d_hist;
     DBuf<int64_t> d_sel, d_idx, d_cols, d_sidx;
-    HBuf<double> h_scal, h_gout;
+    HBuf<double> h_scal, h_gout, h_l2;
+    DBuf<double> d_l2;                               // ||R1_t - mean||_2 per trait (PAIR sweeps: L2 error bounds)
     HBuf<int64_t> h_sel;
     void* sweep_scratch = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -366,8 +372,12 @@ struct ihtb_mvfit {
         IHTB_LAUNCH(k_mv_means, 1, 32, 0, s, d_scal.p, r, n, d_vbar.p);
         IHTB_CUDA(cudaMemcpyAsync(h_scal.p, d_scal.p, nv * sizeof(double), cudaMemcpyDeviceToHost, s));
         IHTB_CUDA(cudaEventRecord(ev0, s));
-        sweep_xt_v_with_means(g, d_R1.p, d_vbar.p, r, d_dfa.p, cfg.sweep_mode, s, sweep_scratch, nullptr);
+        const bool l2mode = cfg.sweep_mode == IHTB_SWEEP_PAIR && g->cs_j == 128;
+        if (l2mode && d_l2.n < (size_t)r) { d_l2.alloc((size_t)r); h_l2.alloc((size_t)r); }
+        sweep_xt_v_with_means(g, d_R1.p, d_vbar.p, r, d_dfa.p, cfg.sweep_mode, s, sweep_scratch, nullptr,
+                              l2mode ? d_l2.p : nullptr);
         IHTB_CUDA(cudaEventRecord(ev1, s));
+        if (l2mode) IHTB_CUDA(cudaMemcpyAsync(h_l2.p, d_l2.p, (size_t)r * sizeof(double), cudaMemcpyDeviceToHost, s));
         n_sweeps += r;
         df_exact.clear();
         df_sparse = false;
@@ -379,7 +389,8 @@ struct ihtb_mvfit {
         for (int t = 0; t < r; ++t) {
             double mean = h_scal.p[t] / (double)n;
             double ul1 = h_scal.p[r + t] + (double)n * std::fabs(mean);
-            bounds[t] = (cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBoundMv : kExactBoundMv) * ul1;
+            if (l2mode) bounds[t] = (t < 2 * (r / 2) ? kPairBoundMv : kFastL2BoundMv) * h_l2.p[t];
+            else bounds[t] = (cfg.sweep_mode == IHTB_SWEEP_EXACT ? kExactBoundMv : kFastBoundMv) * ul1;
         }
         for (int e = 0; e < r * (int)q; ++e) df2[e] = h_scal.p[2 * r + e];
     }
@@ -436,7 +447,9 @@ struct ihtb_mvfit {
     // candidate columns of the top-k over the r*p entries |B0 + eta*df|
     std::vector<int64_t> device_candidate_cols(double eta) {
         upload(d_bounds.p, bounds.data(), (size_t)r);
-        topk_candidates_blocked(tk, d_dfa.p, d_b0d.p, g->sinv.p, p, d_bounds.p, eta, cfg.k, s);
+        topk_candidates_blocked(tk, d_dfa.p, d_b0d.p,
+                                (cfg.sweep_mode == IHTB_SWEEP_PAIR && g->cs_j == 128) ? g->sgn.p : g->sinv.p, p,
+                                d_bounds.p, eta, cfg.k, s);
         IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + cap) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         sync();
         const TopkState* st = reinterpret_cast<const TopkState*>(h_sel.p);
@@ -708,7 +721,9 @@ int32_t ihtb_mvfit_create(const ihtb_geno* g, const double* Y, int64_t r, const 
     return guard([&] {
         IHTB_CHECK(g && Y && z && cfg && out, IHTB_EINVAL, "NULL argument");
         geno_require_ready(g);
-        IHTB_CHECK(r >= 2 && r <= MV_MAXR, IHTB_EUNSUPPORTED, "multivariate IHT supports 2..16 traits");
+        IHTB_CHECK(r >= 2 && r <= MV_MAXR, IHTB_EUNSUPPORTED, "multivariate IHT supports 2..20 traits");
+        IHTB_CHECK(cfg->sweep_mode == IHTB_SWEEP_FAST || cfg->sweep_mode == IHTB_SWEEP_EXACT ||
+                       cfg->sweep_mode == IHTB_SWEEP_PAIR, IHTB_EINVAL, "bad sweep_mode");
         IHTB_CHECK(!cfg->debias, IHTB_EUNSUPPORTED,
                    "Currently the debiasing routine for multivariate IHT is broken, sorry!");   // src/multivariate.jl:570
         IHTB_CHECK(q >= 1, IHTB_EDIM, "z must have at least the intercept row");

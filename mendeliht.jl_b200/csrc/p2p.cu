@@ -14,8 +14,9 @@
 //  * two-phase all-reduce (long vectors; n = 500k moves 32 MB per rank with push-all and loses to NCCL, round 1):
 //    the producer writes its partial into its OWN partial area.  k_p2p_reduce_scatter announces it, waits for the
 //    peers' announcements, then reduces slice `rank` of the vector -- loads of the R partials over NVLink, summed in
-//    rank order -- and stores the reduced slice into the result area of every rank; k_p2p_gather_wait waits for the R
-//    slices and copies the result out.  Every rank moves 2 (R-1)/R x n x 8 bytes instead of R x n x 8.
+//    rank order -- stores the reduced slice into the result area of every rank, publishes it, waits for the R slices
+//    and copies the result out: one kernel (k_p2p_allreduce2; its grid is co-resident).  Every rank moves
+//    2 (R-1)/R x n x 8 bytes instead of R x n x 8.
 //  * all-gather (top-k candidate blocks): k_p2p_gpush stores this rank's block into gather[parity][my_rank] of every
 //    rank, k_p2p_gwait waits for the R blocks.
 // All sums are taken in rank order by exactly one rank per element, so every rank sees bit-identical results.
@@ -129,9 +130,13 @@ k_p2p_reduce(double* __restrict__ out, int64_t n, P2PView v, unsigned long long 
     }
 }
 
-// two-phase, first kernel: announce my partial, wait for everyone's, reduce slice `rank`, store it to every rank
-__global__ void __launch_bounds__(256)
-k_p2p_reduce_scatter(SymView v, size_t off_partial, size_t off_result, int64_t count, int par, unsigned long long seq) {
+// two-phase all-reduce in ONE kernel (the grid is co-resident, so CTAs may wait on flags that other CTAs of the same
+// grid help to publish): announce my partial, wait for everyone's, reduce slice `rank` (R independent peer loads in
+// flight per lane), store it into every rank's result area, publish; then wait for the R slices and copy the result out.
+constexpr int P2P_AR_THREADS = 512;
+__global__ void __launch_bounds__(P2P_AR_THREADS)
+k_p2p_allreduce2(SymView v, size_t off_partial, size_t off_result, int64_t count, double* __restrict__ out, int par,
+                 unsigned long long seq) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         // the producer kernel ran earlier on this stream: its stores are complete; make them visible system-wide
         __threadfence_system();
@@ -139,29 +144,45 @@ k_p2p_reduce_scatter(SymView v, size_t off_partial, size_t off_result, int64_t c
             asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(sym_flag(v.base[r], 0, par, v.rank)), "l"(seq) : "memory");
     }
     sym_wait_all(v, 0, par, seq);
-    // slices are multiples of 2 elements so that every access is a 16-byte lane
+    // slices are multiples of 2 elements so that every access is a 16-byte lane (the areas hold an even element count)
     const int64_t pairs = (count + 1) / 2;
     const int64_t lo = 2 * (pairs * v.rank / v.nranks), hi = min((int64_t)(2 * (pairs * (v.rank + 1) / v.nranks)), count);
-    for (int64_t i = lo + 2 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x); i < hi; i += 2 * (int64_t)gridDim.x * blockDim.x) {
-        double2 a = make_double2(0.0, 0.0);
-        for (int r = 0; r < v.nranks; ++r) {
-            const double* src = reinterpret_cast<const double*>(v.base[r] + off_partial) + i;
-            // the partial areas are sized to an even element count, so the second lane is always readable
-            const double2 x = __ldcv(reinterpret_cast<const double2*>(src));
-            a.x += x.x; a.y += x.y;
-        }
-        for (int r = 0; r < v.nranks; ++r)
-            *reinterpret_cast<double2*>(reinterpret_cast<double*>(v.base[r] + off_result) + i) = a;
+    const int64_t stride = 2 * (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = lo + 2 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x); i < hi; i += 2 * stride) {
+        // two elements per lane and trip: 2 R loads in flight before the first add
+        const int64_t i2 = i + stride;
+        const bool two = i2 < hi;
+        double2 x[P2P_MAX_RANKS], y[P2P_MAX_RANKS];
+#pragma unroll
+        for (int r = 0; r < P2P_MAX_RANKS; ++r)
+            if (r < v.nranks) {
+                const double* src = reinterpret_cast<const double*>(v.base[r] + off_partial);
+                x[r] = __ldcv(reinterpret_cast<const double2*>(src + i));
+                if (two) y[r] = __ldcv(reinterpret_cast<const double2*>(src + i2));
+            }
+        double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int r = 0; r < P2P_MAX_RANKS; ++r)
+            if (r < v.nranks) { a.x += x[r].x; a.y += x[r].y; if (two) { b.x += y[r].x; b.y += y[r].y; } }
+#pragma unroll
+        for (int r = 0; r < P2P_MAX_RANKS; ++r)
+            if (r < v.nranks) {
+                double* dst = reinterpret_cast<double*>(v.base[r] + off_result);
+                *reinterpret_cast<double2*>(dst + i) = a;
+                if (two) *reinterpret_cast<double2*>(dst + i2) = b;
+            }
     }
     sym_publish(v, 1, par, seq);
-}
-
-__global__ void __launch_bounds__(256)
-k_p2p_gather_wait(SymView v, size_t off_result, int64_t count, double* __restrict__ out, int par, unsigned long long seq) {
     sym_wait_all(v, 1, par, seq);
     const double* res = reinterpret_cast<const double*>(v.base[v.rank] + off_result);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = __ldcv(res + i);
+    for (int64_t i = 2 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x); i < count; i += stride) {
+        if (i + 1 < count) {
+            const double2 x = __ldcv(reinterpret_cast<const double2*>(res + i));
+            out[i] = x.x; out[i + 1] = x.y;
+        } else {
+            out[i] = __ldcv(res + i);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -382,13 +403,16 @@ void p2p_allreduce_2phase(ihtb_comm* c, size_t count, double* d_out, cudaStream_
     const unsigned long long seq = c->seq[0] + 1;
     const int par = (int)(seq % P2P_PAR);
     SymView v = sym_view(c);
-    const size_t slice = (count + c->nranks - 1) / c->nranks;
-    int grid = (int)std::min<size_t>(64, std::max<size_t>(1, (slice / 2 + 255) / 256));
-    IHTB_LAUNCH(k_p2p_reduce_scatter, grid, 256, 0, s, v, c->off_partial + (size_t)par * c->red_cap * sizeof(double),
-                c->off_result + (size_t)par * c->red_cap * sizeof(double), (int64_t)count, par, seq);
-    grid = (int)std::min<size_t>(148, std::max<size_t>(1, (count + 255) / 256));
-    IHTB_LAUNCH(k_p2p_gather_wait, grid, 256, 0, s, v, c->off_result + (size_t)par * c->red_cap * sizeof(double),
-                (int64_t)count, d_out, par, seq);
+    // every CTA waits on flags inside the kernel, so the grid must be co-resident: at most one CTA per SM here
+    static int sm_count[64] = {};
+    if (!sm_count[c->device & 63])
+        IHTB_CUDA(cudaDeviceGetAttribute(&sm_count[c->device & 63], cudaDevAttrMultiProcessorCount, c->device));
+    const size_t slice_pairs = ((count + 1) / 2 + c->nranks - 1) / c->nranks;
+    int grid = (int)std::min<size_t>((size_t)sm_count[c->device & 63],
+                                     std::max<size_t>(1, (slice_pairs + 2 * P2P_AR_THREADS - 1) / (2 * P2P_AR_THREADS)));
+    IHTB_LAUNCH(k_p2p_allreduce2, grid, P2P_AR_THREADS, 0, s, v,
+                c->off_partial + (size_t)par * c->red_cap * sizeof(double),
+                c->off_result + (size_t)par * c->red_cap * sizeof(double), (int64_t)count, d_out, par, seq);
     ++c->seq[0];
     c->seq[1] = c->seq[0];
     ++c->n_collectives;

@@ -4,6 +4,8 @@
 // re-score top-k candidates exactly (same value mul!(df, Transpose(x), r) gives for those columns).
 #include "common.cuh"
 #include "comm.cuh"
+#include <mutex>
+#include <unordered_map>
 
 namespace ihtb {
 
@@ -181,9 +183,16 @@ __global__ void k_xt_gather_fin(GenoView gv, const int64_t* __restrict__ cols, i
     out[c + (int64_t)t * ncols] = __dmul_rn(gv.sinv[j], __dadd_rn(at, __dmul_rn(gv.mu[j], corr)));
 }
 
-static DBuf<double>& gather_scratch(int device) {
-    static thread_local DBuf<double> buf[16];
-    return buf[device & 15];
+// split partial sums of the gather, one buffer per stream (a fit owns its stream; fits of several host threads and
+// devices run concurrently, and the threads of a multi-device call are short-lived, so neither a global nor a
+// thread-local buffer will do).  Buffers live until the process ends.
+static DBuf<double>& gather_scratch(cudaStream_t s) {
+    static std::mutex mu;
+    static std::unordered_map<cudaStream_t, std::unique_ptr<DBuf<double>>> pool;
+    std::lock_guard<std::mutex> lk(mu);
+    auto& slot = pool[s];
+    if (!slot) slot.reset(new DBuf<double>());
+    return *slot;
 }
 
 template <int M>
@@ -192,7 +201,7 @@ static void launch_xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t 
     int64_t split_bytes = ceil_div(ceil_div(g->nbytes, XG_MAX_SPLIT), 256) * 256;
     if (split_bytes < 1024) split_bytes = 1024;
     int nsplit = (int)ceil_div(g->nbytes, split_bytes);
-    DBuf<double>& sc = gather_scratch(g->device);
+    DBuf<double>& sc = gather_scratch(s);
     size_t need = (size_t)ncols * nsplit * 2 * M;
     if (sc.n < need) {
         IHTB_CUDA(cudaStreamSynchronize(s));

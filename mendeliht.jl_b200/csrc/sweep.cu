@@ -11,6 +11,7 @@
 //  EXACT: FP64 FMA per genotype, slab partials in FP64 (this file, k_sweep_exact).
 //  FAST : FP32 byte-indexed lookup tables in shared memory (sweep_lut.cu).
 #include "common.cuh"
+#include "pairer.cuh"
 #include <stdlib.h>
 
 namespace ihtb {
@@ -144,6 +145,16 @@ __global__ void k_pair_scale(const double* __restrict__ v0, const double* __rest
     }
 }
 
+// ||v - mean||_2 in FP64, one block, fixed order (the L2 error bounds of the PAIR sweep)
+__global__ void k_l2norm(const double* __restrict__ v, int64_t n, const double* __restrict__ vbar, double* __restrict__ out) {
+    __shared__ double sh[32];
+    const double vb = vbar[0];
+    double a = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const double u = v[i] - vb; a += u * u; }
+    a = block_sum(a, sh);
+    if (threadIdx.x == 0) out[0] = sqrt(a);
+}
+
 struct SweepScratch {
     DBuf<double> part64;
     DBuf<float> part32;
@@ -152,8 +163,9 @@ struct SweepScratch {
 
 // dV: n x m column-major device array; dOut: p x m. d_vbar[t] = mean of column t (DEVICE array, so a sweep can be
 // enqueued right behind the kernel that produced the mean without a host round trip).
+// d_l2 (optional, m doubles, PAIR mode): ||v_t - mean||_2 of every right-hand side, for the L2 error bounds.
 void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* d_vbar, int64_t m, double* dOut,
-                           int mode, cudaStream_t s, void* scratch_any, float* sweep_ms) {
+                           int mode, cudaStream_t s, void* scratch_any, float* sweep_ms, double* d_l2) {
     SweepScratch local;
     SweepScratch* sc = scratch_any ? reinterpret_cast<SweepScratch*>(scratch_any) : &local;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -161,6 +173,8 @@ void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* d
         IHTB_CUDA(cudaEventCreate(&e0)); IHTB_CUDA(cudaEventCreate(&e1));
         IHTB_CUDA(cudaEventRecord(e0, s));
     }
+    if (d_l2)
+        for (int64_t t = 0; t < m; ++t) IHTB_LAUNCH(k_l2norm, 1, 1024, 0, s, dV + t * g->n, g->n, d_vbar + t, d_l2 + t);
     for (int64_t t = 0; t < m; ++t) {
         const double* v = dV + t * g->n;
         double* out = dOut + t * g->p;
@@ -212,6 +226,83 @@ void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* d
     }
 }
 
+// ---- lock-step pairing of two fits' sweeps (pairer.cuh) -------------------------------------------------------------
+__global__ void k_copy2(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+    out[0] = a[0]; out[1] = b[0];
+}
+
+SweepPairer::SweepPairer(int dev) : device(dev) {
+    IHTB_CUDA(cudaSetDevice(dev));
+    for (int i = 0; i < 2; ++i) IHTB_CUDA(cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming));
+    IHTB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    IHTB_CUDA(cudaMalloc((void**)&d_vbar2, 2 * sizeof(double)));
+    IHTB_CUDA(cudaMalloc((void**)&d_l2, 2 * sizeof(double)));
+    scratch = new SweepScratch();
+}
+SweepPairer::~SweepPairer() {
+    cudaSetDevice(device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) if (ready[i]) cudaEventDestroy(ready[i]);
+    if (done) cudaEventDestroy(done);
+    if (d_vbar2) cudaFree(d_vbar2);
+    if (d_l2) cudaFree(d_l2);
+    delete reinterpret_cast<SweepScratch*>(scratch);
+}
+
+void SweepPairer::leave() {
+    std::lock_guard<std::mutex> lk(mu);
+    --active;
+    cv.notify_all();
+}
+
+bool SweepPairer::sweep(int slot, const ihtb_geno* g, const double* d_v, const double* d_vbar, double* d_out,
+                        cudaStream_t s, void* solo_scratch) {
+    const int other = slot ^ 1;
+    IHTB_CUDA(cudaEventRecord(ready[slot], s));        // v / vbar of this fit are complete at this point of its stream
+    std::unique_lock<std::mutex> lk(mu);
+    if (active >= 2 && g->cs_j == 128) {
+        req[slot] = Req{d_v, d_vbar, d_out, s};
+        has[slot] = true;
+        if (has[other]) {
+            // second to arrive: launch one pass for both on this stream, behind the partner's producer kernels
+            const Req a = req[0], b = req[1];
+            SweepScratch* sc = reinterpret_cast<SweepScratch*>(scratch);
+            const int64_t n_slabs = g->stride / 128;
+            if (sc->part32.n < (size_t)(2 * n_slabs * g->p)) sc->part32.alloc((size_t)(2 * n_slabs * g->p));
+            if (sc->scale.n < 2) sc->scale.alloc(2);
+            IHTB_CUDA(cudaStreamWaitEvent(s, ready[other], 0));
+            IHTB_LAUNCH(k_copy2, 1, 1, 0, s, a.vbar, b.vbar, d_vbar2);
+            IHTB_LAUNCH(k_pair_scale, 1, 1024, 0, s, a.v, b.v, g->n, d_vbar2, sc->scale.p);
+            IHTB_LAUNCH(k_l2norm, 1, 1024, 0, s, a.v, g->n, d_vbar2, d_l2);
+            IHTB_LAUNCH(k_l2norm, 1, 1024, 0, s, b.v, g->n, d_vbar2 + 1, d_l2 + 1);
+            sweep_pair_partials(g, a.v, b.v, d_vbar2, sc->scale.p, sc->part32.p, s);
+            const Req* rq[2] = {&a, &b};
+            for (int h = 0; h < 2; ++h)
+                IHTB_LAUNCH((k_sweep_epilogue<float>), (unsigned)ceil_div(g->p, 256), 256, 0, s,
+                            sc->part32.p + (size_t)h * n_slabs * g->p, n_slabs, g->p, g->mu.p, g->sinv.p, g->nmiss.p,
+                            g->miss_ptr.p, g->miss_idx.p, rq[h]->v, d_vbar2 + h, g->impute, rq[h]->out, sc->scale.p + h);
+            IHTB_CUDA(cudaEventRecord(done, s));
+            has[0] = has[1] = false;
+            ++round;
+            ++n_pair;
+            cv.notify_all();
+            return true;
+        }
+        // first to arrive: wait for the partner's sweep (or for its departure)
+        const unsigned long long r0 = round;
+        cv.wait(lk, [&] { return round != r0 || active < 2; });
+        if (round != r0) {
+            IHTB_CUDA(cudaStreamWaitEvent(s, done, 0));    // the leader's stream wrote this fit's df
+            return true;
+        }
+        has[slot] = false;                                 // partner left: sweep alone
+    }
+    ++n_solo;
+    lk.unlock();
+    sweep_xt_v_with_means(g, d_v, d_vbar, 1, d_out, IHTB_SWEEP_FAST, s, solo_scratch, nullptr, nullptr);
+    return false;
+}
+
 void* sweep_scratch_create() { return new SweepScratch(); }
 void sweep_scratch_destroy(void* p) { delete reinterpret_cast<SweepScratch*>(p); }
 
@@ -230,7 +321,7 @@ extern "C" int32_t ihtb_xt_v(const ihtb_geno* g, const double* V, int64_t m, dou
         IHTB_CUDA(cudaMemcpy(dV.p, V, g->n * m * sizeof(double), cudaMemcpyHostToDevice));
         for (int64_t t = 0; t < m; ++t)
             IHTB_LAUNCH(k_vec_mean, 1, 1024, 0, 0, dV.p + t * g->n, g->n, dmean.p + t);
-        sweep_xt_v_with_means(g, dV.p, dmean.p, m, dOut.p, sweep_mode, 0, nullptr, nullptr);
+        sweep_xt_v_with_means(g, dV.p, dmean.p, m, dOut.p, sweep_mode, 0, nullptr, nullptr, nullptr);
         IHTB_CUDA(cudaMemcpy(out, dOut.p, g->p * m * sizeof(double), cudaMemcpyDeviceToHost));
     });
 }
@@ -264,11 +355,11 @@ extern "C" int32_t ihtb_sweep_bench(const ihtb_geno* g, int32_t sweep_mode, int3
         cudaEvent_t e0, e1;
         IHTB_CUDA(cudaEventCreate(&e0)); IHTB_CUDA(cudaEventCreate(&e1));
         for (int i = 0; i < warmup; ++i)
-            sweep_xt_v_with_means(g, dV.p, dmean.p, mrhs, dOut.p, sweep_mode, s, &sc, nullptr);
+            sweep_xt_v_with_means(g, dV.p, dmean.p, mrhs, dOut.p, sweep_mode, s, &sc, nullptr, nullptr);
         // (a) whole sweep = partial-sum kernel + epilogue
         IHTB_CUDA(cudaEventRecord(e0, s));
         for (int i = 0; i < reps; ++i)
-            sweep_xt_v_with_means(g, dV.p, dmean.p, mrhs, dOut.p, sweep_mode, s, &sc, nullptr);
+            sweep_xt_v_with_means(g, dV.p, dmean.p, mrhs, dOut.p, sweep_mode, s, &sc, nullptr, nullptr);
         IHTB_CUDA(cudaEventRecord(e1, s));
         IHTB_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;

@@ -29,10 +29,13 @@ __global__ void __launch_bounds__(TK_THREADS)
 k_keys_hist0(int64_t p, const double* __restrict__ dfa, const double* __restrict__ b0d,
              const double* __restrict__ sinv, int64_t p_mod, const double* __restrict__ bounds, double eta,
              double bound, const double* __restrict__ scal, double bound_coef, const double* __restrict__ wt,
-             uint32_t* __restrict__ keyL, uint32_t* __restrict__ keyU, int* __restrict__ hist) {
+             uint32_t* __restrict__ keyL, uint32_t* __restrict__ keyU, int* __restrict__ hist,
+             const double* __restrict__ l2) {
     // scal != NULL: the bound comes from the score kernel's sums still on the device:
     // bound = coef * (sum|r| + |sum r|) >= coef * ||r - mean(r)||_1 (no host round trip between sweep and selection)
-    if (scal) bound = bound_coef * (scal[1] + fabs(scal[0]));
+    // l2 != NULL (PAIR sweeps): bound = coef * ||r - mean(r)||_2, and `sinv` is the handle's sgn array
+    if (l2) bound = bound_coef * l2[0];
+    else if (scal) bound = bound_coef * (scal[1] + fabs(scal[0]));
     __shared__ int sh[TK_BINS];
     for (int b = threadIdx.x; b < TK_BINS; b += blockDim.x) sh[b] = 0;
     __syncthreads();
@@ -143,12 +146,12 @@ __global__ void k_scatter(double* __restrict__ dst, const int64_t* __restrict__ 
 
 static void topk_run(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, int64_t p_mod,
                      const double* d_bounds, double eta, double bound, int64_t k, cudaStream_t s,
-                     const double* d_scal = nullptr, double bound_coef = 0.0) {
+                     const double* d_scal = nullptr, double bound_coef = 0.0, const double* d_l2 = nullptr) {
     int grid = tk_grid(c.p);
     int kk = (int)(k < c.p ? k : c.p);
     IHTB_LAUNCH(k_topk_reset, 1, 1, 0, s, c.st, kk);
     IHTB_LAUNCH(k_keys_hist0, grid, TK_THREADS, 0, s, c.p, d_dfa, d_b0d, d_sinv, p_mod, d_bounds, eta, bound, d_scal,
-                bound_coef, c.wt, c.keyL, c.keyU, c.hist);
+                bound_coef, c.wt, c.keyL, c.keyU, c.hist, d_l2);
     IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 21, 11);
     IHTB_LAUNCH(k_hist, grid, TK_THREADS, 0, s, c.p, c.keyL, c.st, 10, 11, c.hist);
     IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 10, 11);
@@ -166,10 +169,11 @@ void topk_candidates(TopkCtx& c, const double* d_dfa, const double* d_b0d, const
 // |df_j| outside the support, whatever eta is, so ONE selection per sweep serves the gradient step and all of its
 // backtracks.  The error bound is computed on the device from the score sums d_scal = [sum r, sum |r|, ...].
 void topk_candidates_absdf(TopkCtx& c, const double* d_dfa, const double* d_sinv, const double* d_scal,
-                           double bound_coef, int64_t k, cudaStream_t s, double host_bound) {
+                           double bound_coef, int64_t k, cudaStream_t s, double host_bound, const double* d_l2) {
     // unused candidate slots stay -1 so that a gather launched over a fixed number of slots can skip them
     IHTB_CUDA(cudaMemsetAsync(c.cand, 0xFF, (size_t)c.cap * sizeof(int64_t), s));
-    topk_run(c, d_dfa, nullptr, d_sinv, c.p, nullptr, 1.0, d_scal ? 0.0 : host_bound, k, s, d_scal, bound_coef);
+    topk_run(c, d_dfa, nullptr, d_sinv, c.p, nullptr, 1.0, (d_scal || d_l2) ? 0.0 : host_bound, k, s, d_scal, bound_coef,
+             d_l2);
 }
 
 __global__ void k_take(const double* __restrict__ src, const int64_t* __restrict__ idx, int64_t k,

@@ -27,7 +27,8 @@ void topk_candidates_blocked(TopkCtx& c, const double* d_dfa, const double* d_b0
                              const double* d_bounds, double eta, int64_t k, cudaStream_t s);
 // d_scal != NULL: bound = bound_coef * (d_scal[1] + |d_scal[0]|) on the device; else host_bound is used
 void topk_candidates_absdf(TopkCtx& c, const double* d_dfa, const double* d_sinv, const double* d_scal,
-                           double bound_coef, int64_t k, cudaStream_t s, double host_bound = 0.0);
+                           double bound_coef, int64_t k, cudaStream_t s, double host_bound = 0.0,
+                           const double* d_l2 = nullptr);
 void take_values(const double* d_src, const int64_t* d_idx, int64_t k, double* d_dst, cudaStream_t s);
 void pack_sweep_candidates(int64_t* d_block, const TopkState* d_st, const int64_t* d_cand, int glaunch,
                            const double* d_cand_vals, const int64_t* d_supp, int nsupp, const double* d_supp_vals,

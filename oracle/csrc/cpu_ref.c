@@ -36,14 +36,53 @@ int cpu_set_num_threads(int t) {
 #endif
 }
 
+static int simd_level(void);
+
+/* AVX-512 form of the generator for the common case (no missing data): 8 samples per step, same integer arithmetic as
+ * synth_code (splitmix64 finalizer, two 32-bit threshold compares), so the bytes are identical to the scalar loop. */
+#include <immintrin.h>
+__attribute__((target("avx512f,avx512dq,avx512bw")))
+static void synth_col_avx512(uint64_t key, uint64_t thr, int64_t n, uint8_t* col) {
+    const __m512i gold = _mm512_set1_epi64((long long)0x9E3779B97F4A7C15ull);
+    const __m512i m1 = _mm512_set1_epi64((long long)0xBF58476D1CE4E5B9ull), m2 = _mm512_set1_epi64((long long)0x94D049BB133111EBull);
+    const __m512i vkey = _mm512_set1_epi64((long long)key), vthr = _mm512_set1_epi64((long long)thr);
+    const __m512i lo32 = _mm512_set1_epi64(0xFFFFFFFFll);
+    const __m512i shl = _mm512_setr_epi64(0, 2, 4, 6, 8, 10, 12, 14);
+    const __m512i one = _mm512_set1_epi64(1);
+    __m512i idx = _mm512_setr_epi64(0, 1, 2, 3, 4, 5, 6, 7);
+    const __m512i eight = _mm512_set1_epi64(8);
+    const int64_t nfull = n / 8;
+    uint16_t* out16 = (uint16_t*)col;
+    for (int64_t b = 0; b < nfull; ++b) {
+        __m512i x = _mm512_xor_si512(vkey, _mm512_mullo_epi64(idx, gold));
+        x = _mm512_mullo_epi64(_mm512_xor_si512(x, _mm512_srli_epi64(x, 30)), m1);
+        x = _mm512_mullo_epi64(_mm512_xor_si512(x, _mm512_srli_epi64(x, 27)), m2);
+        x = _mm512_xor_si512(x, _mm512_srli_epi64(x, 31));
+        const __mmask8 a1 = _mm512_cmplt_epu64_mask(_mm512_and_si512(x, lo32), vthr);
+        const __mmask8 a2 = _mm512_cmplt_epu64_mask(_mm512_srli_epi64(x, 32), vthr);
+        /* g = a1 + a2 in {0,1,2}; code = g ? g + 1 : 0  ->  bit1 = a1|a2, bit0 = a1&a2 */
+        __m512i code = _mm512_maskz_mov_epi64((__mmask8)(a1 | a2), _mm512_set1_epi64(2));
+        code = _mm512_mask_or_epi64(code, (__mmask8)(a1 & a2), code, one);
+        out16[b] = (uint16_t)_mm512_reduce_or_epi64(_mm512_sllv_epi64(code, shl));
+        idx = _mm512_add_epi64(idx, eight);
+    }
+    for (int64_t i = 8 * nfull; i < n; ++i) {          /* tail: fewer than 8 samples */
+        uint32_t c = synth_code(key, thr, 0u, (uint64_t)i);
+        if ((i & 3) == 0) col[i >> 2] = 0;
+        col[i >> 2] |= (uint8_t)(c << (2 * (i & 3)));
+    }
+}
+
 void cpu_synth(uint64_t seed, int64_t n, int64_t j0, int64_t ncols, double missing_rate, uint8_t* out) {
     const int64_t nbytes = (n + 3) / 4;
     const uint32_t miss_thr = synth_missing_threshold(missing_rate);
+    const int fast = simd_level() == 2 && miss_thr == 0;
 #pragma omp parallel for schedule(static)
     for (int64_t c = 0; c < ncols; ++c) {
         uint64_t key = synth_col_key(seed, (uint64_t)(j0 + c));
         uint64_t thr = synth_maf_threshold(key);
         uint8_t* col = out + c * nbytes;
+        if (fast) { synth_col_avx512(key, thr, n, col); continue; }
         for (int64_t b = 0; b < nbytes; ++b) {
             uint32_t byte = 0;
             for (int s = 0; s < 4; ++s) {
@@ -79,8 +118,6 @@ void cpu_col_stats(const uint8_t* bed, int64_t n, int64_t p, int64_t stride, dou
  * per genotype as SnpArrays' SnpLinAlg kernels (LoopVectorization-tiled in the reference), written with explicit
  * AVX2 / AVX-512 intrinsics and dispatched at run time, because gcc does not vectorise the table-lookup loop below.
  * FP64 accumulation throughout; only the order of the additions differs from the scalar loop. */
-#include <immintrin.h>
-
 static inline double miss16(uint32_t w, const double* vv) {      /* w: 16 bits = 8 samples; sum of v over codes 01 */
     uint32_t m = w & ~(w >> 1) & 0x5555u;
     double s = 0.0;

@@ -30,11 +30,14 @@ if "mv" in which:      # configs[3]: MvNormal r=5 traits n=100k p=500k k=50
     Y = np.linalg.cholesky(cov) @ rng.normal(size=(r, n)) + 1.0
     for s in range(0, k, 10):
         Y += B[:, s:s + 10] @ synth.standardized_columns(2026, n, idx[s:s + 10]).T
+    mode = {"fast": m.SWEEP_FAST, "pair": m.SWEEP_PAIR, "exact": m.SWEEP_EXACT}[os.environ.get("MV_SWEEP", "pair")]
+    m.fit_iht(Y, g, None, k=k, sweep_mode=mode)                                   # warm-up
     t0 = time.perf_counter()
-    res = m.fit_iht(Y, g, None, k=k)
+    res = m.fit_iht(Y, g, None, k=k, sweep_mode=mode)
     dt = time.perf_counter() - t0
     nz = np.flatnonzero((res.beta != 0).any(axis=0))
-    print(json.dumps({"config": "configs[3] MvNormal r=5 n=100k p=500k k=50", "iterations": res.iter, "seconds": dt,
+    print(json.dumps({"config": "configs[3] MvNormal r=5 n=100k p=500k k=50", "sweep_mode": os.environ.get("MV_SWEEP", "pair"),
+                      "iterations": res.iter, "seconds": dt,
                       "fit_seconds": res.time, "iters_per_sec": res.iter / res.time, "sweeps": res.n_sweeps,
                       "sweep_seconds": res.sweep_seconds,
                       "sweep_gbs_per_rhs": res.n_sweeps * sweep_bytes(n, p) / res.sweep_seconds / 1e9 if res.sweep_seconds else None,
@@ -48,12 +51,17 @@ if "cv" in which:      # configs[2]: Poisson CV q=5 path 1:20 n=100k p=500k (100
     y, z, idx, beta, _ = synth.simulate_response(2025, n, p, 10, "Poisson", geno_seed=2025)
     folds = synth.folds_for(2025, n, q)
     t0 = time.perf_counter()
-    mses, iters = m.cv_iht(y, g, z, d="Poisson", l="LogLink", path=range(1, 21), q=q, folds=folds, return_grid=True)
+    # the whole grid in ONE library call (ihtb_cv_run): two fits at a time share their sweeps (IHTB_CV_PAIR=0: one at a time)
+    m.cv_run(y, g, z, folds, q, [1, 2], d="Poisson", l="LogLink")                  # warm-up (workspaces)
+    t0 = time.perf_counter()
+    mses, iters = m.cv_run(y, g, z, folds, q, list(range(1, 21)), d="Poisson", l="LogLink")
     dt = time.perf_counter() - t0
     mse = m.meanloss(mses, q, folds)
     print(json.dumps({"config": "configs[2] Poisson CV q=5 path=1:20 n=100k p=500k", "fits": 100, "seconds": dt,
+                      "pair_sweeps": os.environ.get("IHTB_CV_PAIR", "1") != "0",
                       "total_iterations": int(iters.sum()), "iters_per_sec": float(iters.sum()) / dt,
-                      "best_k": int(np.argmin(mse)) + 1, "mse": [float(v) for v in mse]}))
+                      "best_k": int(np.argmin(mse)) + 1, "mse": [float(v) for v in mse],
+                      "grid_checksum": float(np.sum(mses * np.arange(1, mses.size + 1)))}))
     g.close()
 
 if "ukb" in which:     # configs[4]: n=500k p=1M Normal k=100 with 10 covariates, whole matrix on ONE GPU (125 GB)

@@ -217,8 +217,8 @@ def _mv_data(seed, n, p, r, k):
     return bed, Y, Z
 
 
-@pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("n,p,r,k", [(1200, 2500, 2, 8), (1500, 2000, 3, 9), (1003, 1500, 5, 10)])
+@pytest.mark.parametrize("mode", MODES + [m.SWEEP_PAIR])
+@pytest.mark.parametrize("n,p,r,k", [(1200, 2500, 2, 8), (1500, 2000, 3, 9), (1003, 1500, 5, 10), (900, 1200, 18, 12)])
 def test_mv_fit_matches_oracle(n, p, r, k, mode):
     from oracle import mviht
     bed, Y, Z = _mv_data(40 + r, n, p, r, k)

@@ -75,9 +75,14 @@ def test_xt_v_exact_and_fast(layout, n, p, miss):
     if layout != "colmajor":
         V5 = rng.normal(size=(n, 5)) * np.array([1.0, 1e-6, 3e4, 0.02, 7.0]) + np.array([0.0, 1.0, -5.0, 0.0, 2.0])
         got, want = g.xt_v(V5, m.SWEEP_PAIR), o.xt_v(V5)
+        # the bound the fits use: 3.1 * 2^-11 * ||u||_2 * sinv_j * max(sqrt(sum_i g_ij^2), 1)  (Cauchy-Schwarz on the
+        # absolute dot product every FP16 rounding is relative to); the last, odd vector takes the FP32 tables
+        gn = np.maximum(np.sqrt((np.where(np.isnan(snp.dosages(bed, n)), 0.0, snp.dosages(bed, n)) ** 2).sum(axis=0)), 1.0)
         for t in range(5):
-            bnd = (2.0 ** -8) * np.abs(V5[:, t] - V5[:, t].mean()).sum() * o.sigma_inv
+            u = V5[:, t] - V5[:, t].mean()
+            bnd = (3.1 * 2.0 ** -11 if t < 4 else 2.0 ** -20) * np.sqrt((u ** 2).sum()) * o.sigma_inv * gn
             assert np.all(np.abs(got[:, t] - want[:, t]) <= bnd + 1e-12 * np.abs(want[:, t]).max()), t
+            assert np.all(np.abs(got[:, t] - want[:, t]) <= (2.0 ** -8) * np.abs(u).sum() * o.sigma_inv + 1e-12 * np.abs(want[:, t]).max())
         assert np.array_equal(g.xt_v(V5[:, :1], m.SWEEP_PAIR), g.xt_v(V5[:, :1], m.SWEEP_FAST))   # odd one out: FAST
         zero = np.zeros((n, 2)); zero[:, 1] = 3.0                      # constant vectors: u = 0, scale falls back to 1
         assert np.all(g.xt_v(zero, m.SWEEP_PAIR) == 0.0)
@@ -124,8 +129,10 @@ def test_fast_sweep_matches_exact_at_scale():
         assert np.all(np.abs(fa - ex) <= bound + 1e-9 * np.abs(ex).max())
         v2 = rng.normal(size=n) * 0.01
         pr = g.xt_v(np.stack([v, v2], axis=1), m.SWEEP_PAIR)
-        assert np.all(np.abs(pr[:, 0] - ex) <= (2.0 ** -8) * np.abs(v - v.mean()).sum() * sinv)
-        assert np.all(np.abs(pr[:, 1] - g.xt_v(v2, m.SWEEP_EXACT)) <= (2.0 ** -8) * np.abs(v2 - v2.mean()).sum() * sinv)
+        cnt = g.counts()
+        sgn = sinv * np.maximum(np.sqrt(cnt[2] + 4.0 * cnt[3]), 1.0)
+        assert np.all(np.abs(pr[:, 0] - ex) <= 3.1 * 2.0 ** -11 * np.linalg.norm(v - v.mean()) * sgn)
+        assert np.all(np.abs(pr[:, 1] - g.xt_v(v2, m.SWEEP_EXACT)) <= 3.1 * 2.0 ** -11 * np.linalg.norm(v2 - v2.mean()) * sgn)
     # checksum of checksums against a column subsample computed by the numpy twin of the generator
     cols = np.sort(rng.permutation(p)[:64])
     xs = synth.standardized_columns(2024, n, cols)

@@ -77,7 +77,9 @@ def test_config3_mvnormal_r5_100k_x_500k_matches_oracle():
     A = rng.normal(size=(r, r)); cov = A @ A.T / r + 0.5 * np.eye(r)
     Y = np.linalg.cholesky(cov) @ rng.normal(size=(r, n)) + 1.0
     Y += B @ o.columns(idx).T
-    res = m.fit_iht(Y, g, None, k=k)
     ref = mviht.fit_mv_iht(Y, o, None, k=k)
-    compare_mv_fit(res, ref)
+    # FAST: one single-vector pass per trait; PAIR: the skinny X'R, one pass over the matrix per two traits
+    for mode in (m.SWEEP_FAST, m.SWEEP_PAIR):
+        res = m.fit_iht(Y, g, None, k=k, sweep_mode=mode)
+        compare_mv_fit(res, ref)
     g.close()
