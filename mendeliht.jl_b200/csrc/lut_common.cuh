@@ -2,6 +2,7 @@
 // global loads): PTX wrappers and the per-slab table build.
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace ihtb {
 
@@ -89,6 +90,41 @@ __device__ __forceinline__ void lut_build(uint32_t tab, const double* __restrict
 #pragma unroll
                 for (int v0 = 0; v0 < 4; ++v0)
                     sts_f32(base3 + (uint32_t)(v2 << 4 | v1 << 2 | v0) * 256u, a1 + f(0, v0));
+            }
+        }
+    }
+}
+
+// half2 table of one slab for TWO right-hand sides (the pair sweep): entry = (v0 part | v1 part), each the FP32 sum of
+// up to four scaled values rounded once to FP16; same addressing as lut_build.  512 consumer threads.
+__device__ __forceinline__ void lut_build_h2(uint32_t tab, const double* __restrict__ v0, const double* __restrict__ v1,
+                                             double vbar0, double vbar1, float sc0, float sc1, int64_t n, int64_t slab,
+                                             int tid) {
+    const int group = tid & 127, part = tid >> 7;            // 4 parts: one value of the top sample's code each
+    const int t = group >> 5, w = group & 31;
+    float a[4], b[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        int64_t i = slab * 512 + 16 * w + 4 * t + s;
+        a[s] = (i < n) ? __double2float_rn(__dsub_rn(v0[i], vbar0)) * sc0 : 0.0f;     // power-of-two scale: exact
+        b[s] = (i < n) ? __double2float_rn(__dsub_rn(v1[i], vbar1)) * sc1 : 0.0f;
+    }
+    auto fa = [&](int s, int code) -> float { return code == 2 ? a[s] : (code == 3 ? a[s] + a[s] : 0.0f); };
+    auto fb = [&](int s, int code) -> float { return code == 2 ? b[s] : (code == 3 ? b[s] + b[s] : 0.0f); };
+    const uint32_t rowbase = tab + (uint32_t)(t >> 1) * 65536u + (uint32_t)(t & 1) * 128u + 4u * (uint32_t)w;
+    const int v3 = part;
+    const float a3 = fa(3, v3), b3 = fb(3, v3);
+    const uint32_t base3 = rowbase + (uint32_t)v3 * (64u * 256u);
+#pragma unroll
+    for (int v2 = 0; v2 < 4; ++v2) {
+        const float a2 = a3 + fa(2, v2), b2 = b3 + fb(2, v2);
+#pragma unroll
+        for (int v1c = 0; v1c < 4; ++v1c) {
+            const float a1 = a2 + fa(1, v1c), b1 = b2 + fb(1, v1c);
+#pragma unroll
+            for (int v0c = 0; v0c < 4; ++v0c) {
+                const __half2 h = __floats2half2_rn(a1 + fa(0, v0c), b1 + fb(0, v0c));
+                sts_u32(base3 + (uint32_t)(v2 << 4 | v1c << 2 | v0c) * 256u, *reinterpret_cast<const uint32_t*>(&h));
             }
         }
     }

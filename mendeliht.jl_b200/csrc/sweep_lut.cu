@@ -18,7 +18,6 @@
 // stage with a butterfly so that lanes 0..15 end up holding one column sum each.  Slab partial sums are written as
 // FP32 [slab][column]; the epilogue (sweep.cu) adds them in FP64 in slab order.  Everything is deterministic.
 #include "lut_common.cuh"
-#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace ihtb {
@@ -56,41 +55,6 @@ __device__ __forceinline__ LutPlan lut_plan(uint32_t base, uint32_t bytes) {
     pl.n_stages = pl.n_lo + n_hi;
     if (pl.n_stages > LUT_MAX_STAGES) pl.n_stages = LUT_MAX_STAGES;
     return pl;
-}
-
-// half2 table of one slab for TWO right-hand sides (the pair sweep): entry = (v0 part | v1 part), each the FP32 sum of
-// up to four scaled values rounded once to FP16; same addressing as lut_build.  512 consumer threads.
-__device__ __forceinline__ void lut_build_h2(uint32_t tab, const double* __restrict__ v0, const double* __restrict__ v1,
-                                             double vbar0, double vbar1, float sc0, float sc1, int64_t n, int64_t slab,
-                                             int tid) {
-    const int group = tid & 127, part = tid >> 7;            // 4 parts: one value of the top sample's code each
-    const int t = group >> 5, w = group & 31;
-    float a[4], b[4];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        int64_t i = slab * 512 + 16 * w + 4 * t + s;
-        a[s] = (i < n) ? __double2float_rn(__dsub_rn(v0[i], vbar0)) * sc0 : 0.0f;     // power-of-two scale: exact
-        b[s] = (i < n) ? __double2float_rn(__dsub_rn(v1[i], vbar1)) * sc1 : 0.0f;
-    }
-    auto fa = [&](int s, int code) -> float { return code == 2 ? a[s] : (code == 3 ? a[s] + a[s] : 0.0f); };
-    auto fb = [&](int s, int code) -> float { return code == 2 ? b[s] : (code == 3 ? b[s] + b[s] : 0.0f); };
-    const uint32_t rowbase = tab + (uint32_t)(t >> 1) * 65536u + (uint32_t)(t & 1) * 128u + 4u * (uint32_t)w;
-    const int v3 = part;
-    const float a3 = fa(3, v3), b3 = fb(3, v3);
-    const uint32_t base3 = rowbase + (uint32_t)v3 * (64u * 256u);
-#pragma unroll
-    for (int v2 = 0; v2 < 4; ++v2) {
-        const float a2 = a3 + fa(2, v2), b2 = b3 + fb(2, v2);
-#pragma unroll
-        for (int v1c = 0; v1c < 4; ++v1c) {
-            const float a1 = a2 + fa(1, v1c), b1 = b2 + fb(1, v1c);
-#pragma unroll
-            for (int v0c = 0; v0c < 4; ++v0c) {
-                const __half2 h = __floats2half2_rn(a1 + fa(0, v0c), b1 + fb(0, v0c));
-                sts_u32(base3 + (uint32_t)(v2 << 4 | v1c << 2 | v0c) * 256u, *reinterpret_cast<const uint32_t*>(&h));
-            }
-        }
-    }
 }
 
 // Units: u = slab * n_cblocks + cblock, CTA b handles [u_begin(b), u_begin(b+1)), slab by slab.
@@ -269,6 +233,12 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
 
 int64_t sweep_fast_num_slabs(const ihtb_geno* g) { return g->stride / 128; }
 
+// sweep_tmem.cu: the same sweeps with the genotype stream staged through tensor memory (quad layout only)
+bool sweep_tmem_enabled(const ihtb_geno* g);
+void sweep_tmem_partials(const ihtb_geno* g, const double* d_v, const double* d_vbar, float* d_part, cudaStream_t s);
+void sweep_tmem_pair_partials(const ihtb_geno* g, const double* d_v0, const double* d_v1, const double* d_vbar,
+                              const float* d_scale, float* d_part, cudaStream_t s);
+
 template <bool QUAD, bool H2>
 static void launch_lut(const ihtb_geno* g, const double* d_v, const double* d_v1, const double* d_vbar,
                        const float* d_scale, float* d_part, cudaStream_t s) {
@@ -287,6 +257,7 @@ static void launch_lut(const ihtb_geno* g, const double* d_v, const double* d_v1
 void sweep_fast_partials(const ihtb_geno* g, const double* d_v, const double* d_vbar, float* d_part, int64_t* n_slabs_out,
                          cudaStream_t s) {
     if (n_slabs_out) *n_slabs_out = sweep_fast_num_slabs(g);
+    if (sweep_tmem_enabled(g)) { sweep_tmem_partials(g, d_v, d_vbar, d_part, s); return; }
     if (g->quad) launch_lut<true, false>(g, d_v, nullptr, d_vbar, nullptr, d_part, s);
     else launch_lut<false, false>(g, d_v, nullptr, d_vbar, nullptr, d_part, s);
 }
@@ -300,6 +271,7 @@ void sweep_fast_kernel_only(const ihtb_geno* g, const double* d_v, const double*
 void sweep_pair_partials(const ihtb_geno* g, const double* d_v0, const double* d_v1, const double* d_vbar,
                          const float* d_scale, float* d_part, cudaStream_t s) {
     IHTB_CHECK(g->cs_j == 128, IHTB_EUNSUPPORTED, "the pair sweep needs a tiled layout");
+    if (sweep_tmem_enabled(g)) { sweep_tmem_pair_partials(g, d_v0, d_v1, d_vbar, d_scale, d_part, s); return; }
     if (g->quad) launch_lut<true, true>(g, d_v0, d_v1, d_vbar, d_scale, d_part, s);
     else launch_lut<false, true>(g, d_v0, d_v1, d_vbar, d_scale, d_part, s);
 }

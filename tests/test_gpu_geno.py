@@ -88,6 +88,23 @@ def test_xt_v_exact_and_fast(layout, n, p, miss):
         assert np.all(g.xt_v(zero, m.SWEEP_PAIR) == 0.0)
 
 
+def test_tensor_memory_sweep_matches_stage_ring():
+    """IHTB_SWEEP_TMEM=1: the genotype stream staged through tensor memory (tcgen05.cp / tcgen05.ld, sweep_tmem.cu).
+    Same tables, same butterfly, same partial sums per slab: results identical to the default kernel, FAST and PAIR,
+    including ragged n and a column count that is not a multiple of the 256-column unit."""
+    for n, p, miss in [(1003, 513, 0.01), (5000, 3001, 0.0), (600, 7, 0.2)]:
+        bed = synth.packed_columns(5, n, np.arange(p), miss)
+        g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+        V = np.random.default_rng(2).normal(size=(n, 2)) * np.array([1.0, 30.0]) + 0.3
+        want_f, want_p = g.xt_v(V[:, 0], m.SWEEP_FAST), g.xt_v(V, m.SWEEP_PAIR)
+        os.environ["IHTB_SWEEP_TMEM"] = "1"
+        try:
+            got_f, got_p = g.xt_v(V[:, 0], m.SWEEP_FAST), g.xt_v(V, m.SWEEP_PAIR)
+        finally:
+            os.environ.pop("IHTB_SWEEP_TMEM", None)
+        assert np.array_equal(got_f, want_f) and np.array_equal(got_p, want_p)
+
+
 @pytest.mark.parametrize("layout", LAYOUTS)
 def test_x_support_bit_exact(layout):
     n, p = 1003, 400
