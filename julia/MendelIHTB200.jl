@@ -64,6 +64,42 @@ function LinearAlgebra.mul!(out::AbstractVecOrMat{Float64}, xt::Transpose{Float6
     out
 end
 
+# ---- several GPUs driven by this Julia process (include/ihtb200.h, ihtb_mgeno) -----------------------------------
+"""
+    B200MultiSnpLinAlg(s::SnpArray; ngpu, mode = :shard, devices = nothing)
+
+The genotype operator over `ngpu` GPUs of the box.  `mode = :shard` splits the SNP columns over the devices and
+`fit_iht` runs ONE fit over all of them (X*beta partials all-reduced and top-k candidates all-gathered by peer-memory
+kernels over NVLink inside the library); `mode = :replicate` puts the whole matrix on every device and `cv_iht` farms
+its (fold, k) grid over them -- the GPU counterpart of the reference's `Threads.@threads` loop
+(src/cross_validation.jl:98-121).  No torchrun, no second process: one `ccall` per API call.
+"""
+mutable struct B200MultiSnpLinAlg <: AbstractMatrix{Float64}
+    handle::Ptr{Cvoid}
+    n::Int
+    p::Int
+    ngpu::Int
+    mode::Symbol
+    function B200MultiSnpLinAlg(s::SnpArray; ngpu::Int, mode::Symbol=:shard, devices::Union{Nothing,Vector{Int}}=nothing,
+                                center::Bool=true, scale::Bool=true, impute::Bool=true)
+        mode in (:shard, :replicate) || throw(ArgumentError("mode must be :shard or :replicate"))
+        n, p = size(s)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        devs = devices === nothing ? C_NULL : Int32.(devices)
+        check(ccall((:ihtb_mgeno_create, LIB), Int32,
+                    (Ptr{UInt8}, Int64, Int64, Int64, Int32, Int32, Int32, Int32, Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}),
+                    s.data, n, p, size(s.data, 1), center, scale, impute, ngpu, devs, mode == :shard ? 0 : 1, h))
+        x = new(h[], n, p, ngpu, mode)
+        finalizer(x -> ccall((:ihtb_mgeno_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle), x)
+        return x
+    end
+end
+Base.size(x::B200MultiSnpLinAlg) = (x.n, x.p)
+const AnyB200 = Union{B200SnpLinAlg,B200MultiSnpLinAlg}
+# the single-device and the multi-device calls have the same argument lists (ihtb_fit_* / ihtb_mfit_*)
+fitsym(::B200SnpLinAlg, name::Symbol) = Symbol(:ihtb_fit_, name)
+fitsym(::B200MultiSnpLinAlg, name::Symbol) = Symbol(:ihtb_mfit_, name)
+
 # ---- fit_iht on the device -----------------------------------------------------------------------------------
 struct Cfg
     dist::Int32; link::Int32; k::Int64; nb_r::Float64; tol::Float64
@@ -74,6 +110,11 @@ mutable struct CResult
     sweep_seconds::Float64; n_launches::Int64; n_steps::Int64
     CResult() = new(0, 0, 0, 0, 0, 0, 0, 0, 0)
 end
+struct CIterTrace        # one line of the verbose trace (include/ihtb200.h ihtb_iter_trace)
+    logl::Float64; tol::Float64; eta::Float64; backtracks::Int32; n_candidates::Int32
+end
+# keywords of the reference that this path does not implement must fail loudly, not be swallowed by kwargs...
+reject_unknown(kw) = isempty(kw) || throw(ArgumentError("unsupported keyword(s) for the B200 path: $(collect(keys(kw)))"))
 distcode(::Normal) = Int32(0); distcode(::Bernoulli) = Int32(1); distcode(::Poisson) = Int32(2)
 distcode(::NegativeBinomial) = Int32(3)
 linkcode(::IdentityLink) = Int32(0); linkcode(::LogitLink) = Int32(1); linkcode(::LogLink) = Int32(2)
@@ -92,30 +133,43 @@ function MendelIHT.maf_weights(x::B200SnpLinAlg; max_weight::Float64=Inf)
 end
 
 # weight / group / per-group k are attached to the fit handle before ihtb_fit_init
-function attach_options(fh, p::Int, k::Union{Int,Vector{Int}}, J::Int, group::AbstractVector{Int},
+function attach_options(x::AnyB200, fh, p::Int, k::Union{Int,Vector{Int}}, J::Int, group::AbstractVector{Int},
                         weight::AbstractVector{Float64})
     if length(group) > 0
         length(group) == p || throw(DimensionMismatch("group must have length $p but was $(length(group))"))
         ks = k isa Vector ? Int64.(k) : Int64[]
-        check(ccall((:ihtb_fit_set_groups, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int32, Ptr{Int64}, Int64),
+        check(ccall((fitsym(x, :set_groups), LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int32, Ptr{Int64}, Int64),
                     fh, Int32.(group), J, k isa Vector ? ks : C_NULL, length(ks)))
     end
     if length(weight) > 0
         length(weight) == p || throw(DimensionMismatch("weight must have length $p but was $(length(weight))"))
-        check(ccall((:ihtb_fit_set_weights, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), fh, weight))
+        check(ccall((fitsym(x, :set_weights), LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), fh, weight))
     end
 end
+function fit_init(x::B200SnpLinAlg, fh, mask, init_beta::Bool)
+    check(ccall((init_beta ? :ihtb_fit_init_beta : :ihtb_fit_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), fh, mask))
+end
+function fit_init(x::B200MultiSnpLinAlg, fh, mask, init_beta::Bool)
+    check(ccall((:ihtb_mfit_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32), fh, mask, init_beta))
+end
 
-"Same signature and return type as MendelIHT.fit_iht (src/fit.jl:60-118) for `x::B200SnpLinAlg`."
-function fit_iht(y::AbstractVector{Float64}, x::B200SnpLinAlg, z::AbstractVecOrMat{Float64};
+"""
+Same signature and return type as MendelIHT.fit_iht (src/fit.jl:60-118) for `x::B200SnpLinAlg`, or for a
+`B200MultiSnpLinAlg` in `:shard` mode (one fit over several GPUs).  `verbose` / `io` print the reference's
+per-iteration line (src/fit.jl:194-196) from the trace the library records.
+"""
+function fit_iht(y::AbstractVector{Float64}, x::AnyB200, z::AbstractVecOrMat{Float64};
                  k::Union{Int,Vector{Int}}=10, J::Int=1, d::Distribution=Normal(), l::Link=IdentityLink(),
                  group::AbstractVector{Int}=Int[], weight::AbstractVector{Float64}=Float64[],
                  zkeep::BitVector=trues(size(z, 2)), est_r::Symbol=:None, debias::Bool=false, init_beta::Bool=false,
-                 tol::Float64=1e-4, max_iter::Int=200,
+                 use_maf::Bool=false, tol::Float64=1e-4, max_iter::Int=200,
                  min_iter::Int=5, max_step::Int=3, verbose::Bool=false, io::IO=stdout, kwargs...)
+    reject_unknown(kwargs)
     est = est_r == :None ? Int32(0) : est_r == :MM ? Int32(1) : est_r == :Newton ? Int32(2) :
           throw(ArgumentError("Only support method is Newton or MM, but got $est_r"))
-    x.center || error("x is not centered! Please construct SnpLinAlg{Float64}(::SnpArray, center=true, scale=true)")
+    x isa B200SnpLinAlg && !x.center &&
+        error("x is not centered! Please construct SnpLinAlg{Float64}(::SnpArray, center=true, scale=true)")
+    x isa B200MultiSnpLinAlg && x.mode != :shard && throw(ArgumentError("fit_iht over several GPUs needs mode = :shard"))
     zm = z isa AbstractVector ? reshape(z, :, 1) : Matrix(z)
     r = d isa NegativeBinomial ? d.r : 1.0
     MendelIHT.check_group(k, group)                                       # src/utilities.jl:902-915
@@ -123,20 +177,28 @@ function fit_iht(y::AbstractVector{Float64}, x::B200SnpLinAlg, z::AbstractVecOrM
     cfg = Ref(Cfg(distcode(d), linkcode(l), kscalar, r, tol, max_iter, min_iter, max_step, 0, est, debias))
     fh = Ref{Ptr{Cvoid}}(C_NULL)
     keep = UInt8.(zkeep)
-    check(ccall((:ihtb_fit_create, LIB), Int32,
+    check(ccall((fitsym(x, :create), LIB), Int32,
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{UInt8}, Ref{Cfg}, Ref{Ptr{Cvoid}}),
                 x.handle, y, zm, size(zm, 2), keep, cfg, fh))
     try
-        attach_options(fh[], x.p, k, J, group, weight)
-        check(ccall((init_beta ? :ihtb_fit_init_beta : :ihtb_fit_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), fh[], C_NULL))
+        attach_options(x, fh[], x.p, k, J, group, weight)
+        fit_init(x, fh[], C_NULL, init_beta)
         res = CResult()
-        check(ccall((:ihtb_fit_run, LIB), Int32, (Ptr{Cvoid}, Ref{CResult}, Ptr{Cvoid}, Int64), fh[], res, C_NULL, 0))
+        trace = Vector{CIterTrace}(undef, verbose ? max_iter : 0)
+        check(ccall((fitsym(x, :run), LIB), Int32, (Ptr{Cvoid}, Ref{CResult}, Ptr{CIterTrace}, Int64),
+                    fh[], res, verbose ? trace : C_NULL, length(trace)))
+        if verbose                                                         # src/fit.jl:194-196
+            for i in 1:min(res.n_steps, length(trace))
+                t = trace[i]
+                println(io, "Iteration $i: loglikelihood = $(t.logl), backtracks = $(t.backtracks), tol = $(t.tol)")
+            end
+        end
         beta = zeros(x.p); c = zeros(size(zm, 2))
-        check(ccall((:ihtb_fit_get, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        check(ccall((fitsym(x, :get), LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                     fh[], beta, c, C_NULL, C_NULL))
         return IHTResult(res.time, res.logl, res.iter, beta, c, J, k, collect(group), d, res.sigma_g)
     finally
-        ccall((:ihtb_fit_destroy, LIB), Int32, (Ptr{Cvoid},), fh[])
+        ccall((fitsym(x, :destroy), LIB), Int32, (Ptr{Cvoid},), fh[])
     end
 end
 
@@ -146,7 +208,9 @@ Multivariate (MvNormal) fit: same call as the reference, `fit_iht(Y, Transpose(x
 """
 function fit_iht(Y::AbstractMatrix{Float64}, xt::Transpose{Float64,B200SnpLinAlg}, Z::AbstractVecOrMat{Float64};
                  k::Int=10, zkeep::BitVector=trues(size(Z, 1)), init_beta::Bool=false, debias::Bool=false,
-                 tol::Float64=1e-4, max_iter::Int=200, min_iter::Int=5, max_step::Int=3, kwargs...)
+                 tol::Float64=1e-4, max_iter::Int=200, min_iter::Int=5, max_step::Int=3, verbose::Bool=false,
+                 io::IO=stdout, kwargs...)
+    reject_unknown(kwargs)            # J / group / weight do not exist for MvNormal in the reference either
     debias && error("Currently the debiasing routine for multivariate IHT is broken, sorry!")   # src/multivariate.jl:570
     x = xt.parent
     r, n = size(Y)
@@ -155,7 +219,8 @@ function fit_iht(Y::AbstractMatrix{Float64}, xt::Transpose{Float64,B200SnpLinAlg
     (n == x.n == size(Zm, 2)) || throw(DimensionMismatch("number of samples in y, x, and z = $n, $(x.n), $(size(Zm, 2)) are not equal"))
     all(zkeep) || error("multivariate zkeep with false entries is not supported")
     Yc = Matrix(transpose(Y)); Zc = Matrix(transpose(Zm))                  # n x r, n x q column-major
-    cfg = Ref(Cfg(0, 0, k, 1.0, tol, max_iter, min_iter, max_step, 0, 0, 0))
+    # sweep_mode 2 = IHTB_SWEEP_PAIR: the skinny X'R reads the matrix once per two traits (src/multivariate.jl:85)
+    cfg = Ref(Cfg(0, 0, k, 1.0, tol, max_iter, min_iter, max_step, 2, 0, 0))
     fh = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ihtb_mvfit_create, LIB), Int32,
                 (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ref{Cfg}, Ref{Ptr{Cvoid}}),
@@ -173,28 +238,55 @@ function fit_iht(Y::AbstractMatrix{Float64}, xt::Transpose{Float64,B200SnpLinAlg
     end
 end
 
-"cv_iht (src/cross_validation.jl:60-131): one device workspace, the (fold, k) grid run back to back."
-function cv_iht(y::AbstractVector{Float64}, x::B200SnpLinAlg, z::AbstractVecOrMat{Float64};
+"""
+cv_iht (src/cross_validation.jl:60-131).  The plain grid is ONE library call: `ihtb_cv_run` on one GPU,
+`ihtb_mcv_run` over the replicas of a `B200MultiSnpLinAlg(...; mode = :replicate)` (shared work queue, largest k
+first).  Groups, `init_beta` and `est_r` take the per-fit loop on one device, where the NegativeBinomial estimate is
+carried from fit to fit like the reference's per-thread `IHTVariable` (src/cross_validation.jl:105).
+"""
+function cv_iht(y::AbstractVector{Float64}, x::AnyB200, z::AbstractVecOrMat{Float64};
                 d::Distribution=Normal(), l::Link=IdentityLink(), path::AbstractVector{<:Integer}=1:20, q::Int=5,
                 folds::AbstractVector{Int}=rand(1:q, size(x, 1)), zkeep::BitVector=trues(size(z, 2)),
                 J::Int=1, group::AbstractVector{Int}=Int[], weight::AbstractVector{Float64}=Float64[],
-                debias::Bool=false, max_iter::Int=100, min_iter::Int=5, kwargs...)
+                est_r::Symbol=:None, debias::Bool=false, init_beta::Bool=false, tol::Float64=1e-4,
+                max_iter::Int=100, min_iter::Int=5, max_step::Int=3, verbose::Bool=false, kwargs...)
+    reject_unknown(kwargs)
     maximum(path) > size(x, 2) && error("Sparsity level in `path` cannot be larger than total number of variables")
     zm = z isa AbstractVector ? reshape(z, :, 1) : Matrix(z)
     r = d isa NegativeBinomial ? d.r : 1.0
-    cfg = Ref(Cfg(distcode(d), linkcode(l), maximum(path), r, 1e-4, max_iter, min_iter, 3, 0, 0, debias))
+    est = est_r == :None ? Int32(0) : est_r == :MM ? Int32(1) : est_r == :Newton ? Int32(2) :
+          throw(ArgumentError("Only support method is Newton or MM, but got $est_r"))
+    cfg = Ref(Cfg(distcode(d), linkcode(l), maximum(path), r, tol, max_iter, min_iter, max_step, 0, est, debias))
+    combos = MendelIHT.allocate_fold_and_k(q, path)
+    mses = zeros(length(combos))
+    pathv = Int64.(collect(path)); foldv = Int32.(folds)
+    w = length(weight) > 0 ? weight : C_NULL
+    if length(group) == 0 && !init_beta
+        if x isa B200MultiSnpLinAlg
+            x.mode == :replicate || throw(ArgumentError("cv_iht over several GPUs needs mode = :replicate"))
+            check(ccall((:ihtb_mcv_run, LIB), Int32,
+                        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{UInt8}, Ref{Cfg}, Ptr{Int32}, Int32, Ptr{Int64},
+                         Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}),
+                        x.handle, y, zm, size(zm, 2), UInt8.(zkeep), cfg, foldv, q, pathv, length(pathv), w, mses, C_NULL, C_NULL))
+        else
+            check(ccall((:ihtb_cv_run, LIB), Int32,
+                        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{UInt8}, Ref{Cfg}, Ptr{Int32}, Int32, Ptr{Int64},
+                         Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                        x.handle, y, zm, size(zm, 2), UInt8.(zkeep), cfg, foldv, q, pathv, length(pathv), w, mses, C_NULL))
+        end
+        return MendelIHT.meanloss(mses, q, folds)
+    end
+    x isa B200SnpLinAlg || throw(ArgumentError("group / init_beta cross-validation runs on a single-device operator"))
     fh = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ihtb_fit_create, LIB), Int32,
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{UInt8}, Ref{Cfg}, Ref{Ptr{Cvoid}}),
                 x.handle, y, zm, size(zm, 2), UInt8.(zkeep), cfg, fh))
-    attach_options(fh[], x.p, maximum(path), J, group, weight)
-    combos = MendelIHT.allocate_fold_and_k(q, path)
-    mses = zeros(length(combos))
     try
+        attach_options(x, fh[], x.p, maximum(path), J, group, weight)
         for (i, (fold, k)) in enumerate(combos)
             test = UInt8.(folds .== fold); train = UInt8.(folds .!= fold)
             check(ccall((:ihtb_fit_set_k, LIB), Int32, (Ptr{Cvoid}, Int64), fh[], k))
-            check(ccall((:ihtb_fit_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), fh[], train))
+            fit_init(x, fh[], train, init_beta)
             check(ccall((:ihtb_fit_run, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64), fh[], C_NULL, C_NULL, 0))
             dev = Ref{Float64}(0.0)
             check(ccall((:ihtb_fit_predict, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Ref{Float64}), fh[], test, dev))

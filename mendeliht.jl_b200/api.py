@@ -574,7 +574,7 @@ def meanloss(fitloss, q: int, folds):
 
 
 def cv_run(y, x: B200SnpLinAlg, z, folds, q: int, path, d=NORMAL, l="IdentityLink", zkeep=None, nb_r=1.0, max_iter=100,
-           min_iter=5, sweep_mode=_lib.SWEEP_FAST, weight=None, debias=False):
+           min_iter=5, sweep_mode=_lib.SWEEP_FAST, weight=None, debias=False, est_r="None"):
     """The whole univariate (fold, k) grid in ONE library call (`ihtb_cv_run`); returns (mses, iters), fold-major."""
     y = f64(y)
     z = np.asarray(z, dtype=np.float64)
@@ -584,7 +584,7 @@ def cv_run(y, x: B200SnpLinAlg, z, folds, q: int, path, d=NORMAL, l="IdentityLin
     fl = np.ascontiguousarray(folds, dtype=np.int32)
     pa = np.ascontiguousarray(list(path), dtype=np.int64)
     cfg = Cfg(DIST_ID[d], LINK_ID[l], int(pa.max()), float(nb_r), 1e-4, int(max_iter), int(min_iter), 3,
-              int(sweep_mode), 0, 1 if debias else 0)
+              int(sweep_mode), EST_R_ID[est_r], 1 if debias else 0)
     mses = np.zeros(q * pa.shape[0]); iters = np.zeros(q * pa.shape[0], dtype=np.int64)
     w = None if weight is None else f64(weight)
     if isinstance(x, B200MultiSnpLinAlg):      # REPLICATE handle: the grid is farmed over the devices from a work queue
@@ -605,7 +605,7 @@ def cv_run(y, x: B200SnpLinAlg, z, folds, q: int, path, d=NORMAL, l="IdentityLin
 
 def cv_iht(y, x: B200SnpLinAlg, z=None, d=NORMAL, l=None, path=range(1, 21), q=5, folds=None, zkeep=None,
            nb_r=1.0, max_iter=100, min_iter=5, sweep_mode=_lib.SWEEP_FAST, combos=None, return_grid=False,
-           init_beta=False, weight=None, debias=False, J=1, group=None):
+           init_beta=False, weight=None, debias=False, J=1, group=None, est_r="None"):
     """`cv_iht` (src/cross_validation.jl:60-131).  `folds` in 1..q (drawn with numpy's default_rng if omitted).
     `combos`: optional subset of grid positions to run (used by the multi-GPU farm, parallel.py)."""
     path = [int(k) for k in path]
@@ -625,7 +625,7 @@ def cv_iht(y, x: B200SnpLinAlg, z=None, d=NORMAL, l=None, path=range(1, 21), q=5
         v = mIHTVariable(x, z, y, max(path), zkeep, 1e-4, max_iter, min_iter, 3, sweep_mode)
     else:
         v = IHTVariable(x, z, y, max(path), d, l, zkeep, nb_r, 1e-4, max_iter, min_iter, 3, sweep_mode,
-                        weight=weight, debias=debias, J=J, group=group)
+                        weight=weight, debias=debias, J=J, group=group, est_r=est_r)
     try:
         for i in todo:
             fold, k = grid[i]
@@ -643,9 +643,14 @@ def cv_iht(y, x: B200SnpLinAlg, z=None, d=NORMAL, l=None, path=range(1, 21), q=5
 
 
 # ---- file-level wrappers (reference src/wrapper.jl) ----------------------------------------------------------------
-def _read_fam_phenotype(path: str, col: int = 6) -> np.ndarray:
-    """`parse_phenotypes(x::SnpData, col, ::Normal)` (src/wrapper.jl:170-191): column `col` (1-based) of the .fam file,
-    "-9"/"NA" imputed with the mean of the observed phenotypes."""
+class MissingPhenotype(ValueError):
+    """The reference's MissingException for binary / count traits (src/wrapper.jl:193-207)."""
+
+
+def _read_fam_phenotype(path: str, col: int = 6, d: str = NORMAL) -> np.ndarray:
+    """`parse_phenotypes(x::SnpData, col, d)` (src/wrapper.jl:170-207): column `col` (1-based) of the .fam file.
+    "-9" / "NA" are missing: quantitative traits (Normal) are imputed with the mean of the observed phenotypes;
+    binary and count traits cannot be imputed and raise, like the reference."""
     vals, missing = [], []
     with open(path) as f:
         for i, line in enumerate(f):
@@ -656,8 +661,17 @@ def _read_fam_phenotype(path: str, col: int = 6) -> np.ndarray:
                 vals.append(float(tok))
     y = np.asarray(vals)
     if missing:
+        if d != NORMAL:
+            raise MissingPhenotype("Missing phenotype detected: automatic imputation is only possible for quantitative "
+                                   f"traits, but the trait is {d} (sample {missing[0] + 1} of {path})")
         y[missing] = (y.sum()) / (len(vals) - len(missing))
     return y
+
+
+def _read_fam_phenotypes_mv(path: str, cols) -> np.ndarray:
+    """`parse_phenotypes(x::SnpData, col::AbstractVector{Int}, ::MvNormal)` (src/wrapper.jl:136-162): r x n, every
+    trait imputed with its own observed mean."""
+    return np.vstack([_read_fam_phenotype(path, int(c), NORMAL) for c in cols])
 
 
 def parse_covariates(filename: str, exclude_std_idx=(), standardize: bool = True) -> np.ndarray:
@@ -682,12 +696,16 @@ def _load_plink(filename: str, phenotypes, d: str):
     fam = filename + ".fam"
     n = sum(1 for _ in open(fam))
     x = B200SnpLinAlg.from_bed_file(filename + ".bed", n)
-    if isinstance(phenotypes, int):
-        y = _read_fam_phenotype(fam, phenotypes)
-        if d != NORMAL and np.any(~np.isfinite(y)):
-            raise ValueError("Missing phenotype detected; automatic imputation is only possible for quantitative traits")
+    if isinstance(phenotypes, (int, np.integer)):
+        y = _read_fam_phenotype(fam, int(phenotypes), d)
+    elif isinstance(phenotypes, (list, tuple, np.ndarray)):          # phenotypes=[6, 7]: multivariate, r x n
+        y = _read_fam_phenotypes_mv(fam, phenotypes)
     else:
+        # comma-separated text file, one sample per row (src/wrapper.jl:209-217): several columns = several traits,
+        # returned r x n like the reference
         y = np.loadtxt(phenotypes, delimiter=",", dtype=np.float64)
+        if y.ndim == 2:
+            y = np.ascontiguousarray(y.T) if y.shape[1] > 1 else y[:, 0]
     return x, y
 
 
@@ -698,6 +716,9 @@ def iht(filename: str, k: int, d: str = NORMAL, phenotypes=6, covariates: str = 
     runs `fit_iht` with the canonical link (LogLink for NegativeBinomial).  Optional text outputs like the reference."""
     x, y = _load_plink(filename, phenotypes, d)
     z = np.ones(x.n) if covariates == "" else parse_covariates(covariates, exclude_std_idx)
+    if is_multivariate(y):          # src/wrapper.jl:80,84-85: z is transposed to q x n, no distribution / link
+        z = np.ones((1, x.n)) if covariates == "" else np.ascontiguousarray(np.asarray(z).reshape(x.n, -1).T)
+        return fit_iht(y, x, z, k=k, **kwargs)
     result = fit_iht(y, x, z, k=k, d=d, l=canonicallink(d), **kwargs)
     if summaryfile:
         with open(summaryfile, "w") as f:
@@ -718,7 +739,11 @@ def cross_validate(filename: str, d: str = NORMAL, path=range(1, 21), q: int = 5
     """`cross_validate(filename, d; path, q, ...)` (src/wrapper.jl:301-349) for binary PLINK input."""
     x, y = _load_plink(filename, phenotypes, d)
     z = np.ones(x.n) if covariates == "" else parse_covariates(covariates, exclude_std_idx)
-    mse = cv_iht(y, x, z, d=d, l=canonicallink(d), path=path, q=q, folds=folds, **kwargs)
+    if is_multivariate(y):
+        z = np.ones((1, x.n)) if covariates == "" else np.ascontiguousarray(np.asarray(z).reshape(x.n, -1).T)
+        mse = cv_iht(y, x, z, path=path, q=q, folds=folds, **kwargs)
+    else:
+        mse = cv_iht(y, x, z, d=d, l=canonicallink(d), path=path, q=q, folds=folds, **kwargs)
     if cv_summaryfile:
         with open(cv_summaryfile, "w") as f:
             f.write("k\tmse\n")

@@ -552,18 +552,45 @@ struct ihtb_fit {
             return x.a > y.a || (x.a == y.a && x.pos < y.pos);
         });
         idx.clear(); b.clear();
+        // project_k! (:553-559) zeroes the entries BELOW the k-th largest magnitude, so ties at it all survive ...
+        const double thr = project_threshold(items, k);
         std::vector<std::pair<int64_t, double>> keep;
         for (size_t t = 0; t < items.size(); ++t) {
-            bool kept = (int64_t)t < k;
+            const bool kept = items[t].a >= thr;
             if (items[t].pos >= p_global) {
                 if (!kept) c[items[t].pos - p_global] = 0.0;
             } else if (kept && items[t].v != 0.0) {
                 keep.push_back({items[t].pos, items[t].v});
             }
         }
+        for (int64_t l = 0; l < q; ++l) idc[l] = c[l] != 0.0;
+        // ... and _choose! (:444-458) prunes only what exceeds k + zkeepn entries
+        choose_prune(keep);
         std::sort(keep.begin(), keep.end());
         for (auto& kv : keep) { idx.push_back(kv.first); b.push_back(kv.second); }
-        for (int64_t l = 0; l < q; ++l) idc[l] = c[l] != 0.0;
+    }
+
+    // threshold of project_k!(x, k + zkeepn) over the candidate entries (kept covariates are +Inf in the reference's
+    // vector and never compete): the k-th largest magnitude, 0 when there are fewer than k entries, +Inf for k = 0
+    template <typename ItemT>
+    static double project_threshold(const std::vector<ItemT>& sorted_items, int64_t k) {
+        if (k <= 0) return INFINITY;
+        return (int64_t)sorted_items.size() >= k ? sorted_items[(size_t)k - 1].a : 0.0;
+    }
+    // _choose! (src/utilities.jl:444-458): when ties at the threshold leave more than k + zkeepn non-zero entries
+    // (SNPs + covariates, kept covariates counted once: nonzero = |idx| + |idc| - zkeepn), the reference zeroes
+    // randomly chosen SNP entries; here (and in the oracle) the smallest magnitudes go first, highest index first
+    void choose_prune(std::vector<std::pair<int64_t, double>>& keep) const {
+        int64_t nonzero = (int64_t)keep.size() - zkeepn;
+        for (int64_t l = 0; l < q; ++l) nonzero += idc[l] ? 1 : 0;
+        const int64_t limit = cfg.k + zkeepn;
+        if (nonzero <= limit) return;
+        std::vector<std::pair<int64_t, double>> byabs = keep;
+        std::sort(byabs.begin(), byabs.end(), [](const std::pair<int64_t, double>& x, const std::pair<int64_t, double>& y) {
+            return std::fabs(x.second) < std::fabs(y.second) || (std::fabs(x.second) == std::fabs(y.second) && x.first > y.first);
+        });
+        const size_t excess = std::min<size_t>((size_t)(nonzero - limit), byabs.size());
+        for (size_t t = 0; t < excess; ++t) keep.erase(std::find(keep.begin(), keep.end(), byabs[t]));
     }
 
     // ---- doubly sparse projection (keywords J / k / group; project_group_sparse!, src/utilities.jl:613-679) --------
@@ -892,9 +919,10 @@ struct ihtb_fit {
         std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) {
             return x.a > y.a || (x.a == y.a && x.pos < y.pos);
         });
+        const double thr = project_threshold(items, cfg.k);            // project_k!(v) keeps ties; no _choose! here (:412-414)
         std::vector<std::pair<int64_t, double>> keep;
         for (size_t t = 0; t < items.size(); ++t) {
-            bool kept = (int64_t)t < cfg.k;
+            const bool kept = items[t].a >= thr;
             if (items[t].pos >= p_global) {
                 if (!kept) c[items[t].pos - p_global] = 0.0;
             } else if (kept && items[t].v != 0.0) {
@@ -970,9 +998,10 @@ struct ihtb_fit {
         std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) {
             return x.a > y.a || (x.a == y.a && x.pos < y.pos);
         });
+        const double thr = project_threshold(items, cfg.k);            // ties at the k-th magnitude survive (:553-559)
         std::vector<std::pair<int64_t, double>> keep;
         for (size_t t = 0; t < items.size(); ++t) {
-            bool kept = (int64_t)t < cfg.k;
+            const bool kept = items[t].a >= thr;
             if (items[t].pos >= p_global) {
                 if (!kept) df2[items[t].pos - p_global] = 0.0;
             } else if (kept && items[t].v != 0.0) {
@@ -982,9 +1011,14 @@ struct ihtb_fit {
         std::sort(keep.begin(), keep.end());
         for (auto& kv : keep) { dfs_idx.push_back(kv.first); dfs_val.push_back(kv.second); }
         df_sparse = true;
-        idx = dfs_idx;
-        b.assign(idx.size(), 0.0);
         for (int64_t l = 0; l < q; ++l) idc[l] = zkeep[l];
+        // _choose!: surplus tied entries leave the SUPPORT, the projected gradient keeps them (:450-456 zeroes v.b, which
+        // is all zero here, and clears idx)
+        choose_prune(keep);
+        std::sort(keep.begin(), keep.end());
+        idx.clear();
+        for (auto& kv : keep) idx.push_back(kv.first);
+        b.assign(idx.size(), 0.0);
         inited = true;
     }
 
@@ -1241,7 +1275,6 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
         IHTB_CHECK(g && y && z && cfg && out, IHTB_EINVAL, "NULL argument");
         IHTB_CHECK(p_global >= g->p, IHTB_EDIM, "p_global is smaller than the local shard");
         geno_require_ready(g);
-        IHTB_CHECK(comm || (p_global == g->p && g->j0 == 0) || true, IHTB_EINVAL, "");
         IHTB_CHECK(q >= 1, IHTB_EDIM, "z must have at least the intercept column");
         IHTB_CHECK(cfg->k >= 0, IHTB_EINVAL, "Value of k (max predictors per group) must be nonnegative!");
         IHTB_CHECK(cfg->max_iter >= 0, IHTB_EINVAL, "Value of max_iter must be nonnegative!");

@@ -321,13 +321,19 @@ static int32_t cv_farm(const std::vector<ihtb_geno*>& parts, const std::vector<i
     static const int pair_env = [] { const char* e = getenv("IHTB_CV_PAIR"); return e ? atoi(e) : -1; }();
     const bool want_pair = pair_env == 1 || (pair_env != 0 && n <= 20000);
     // the pair sweep needs a tiled layout, FAST arithmetic and at least two fits to pair
-    const int per_dev = (want_pair && c.sweep_mode == IHTB_SWEEP_FAST && ngrid >= 2 && parts[0]->cs_j == 128) ? 2 : 1;
+    const int per_dev = (want_pair && c.sweep_mode == IHTB_SWEEP_FAST && c.est_r == 0 && ngrid >= 2 &&
+                         parts[0]->cs_j == 128) ? 2 : 1;
     std::vector<std::unique_ptr<SweepPairer>> pairers((size_t)nd);
     if (per_dev == 2) {
         rc = guard([&] { for (int d = 0; d < nd; ++d) pairers[(size_t)d].reset(new SweepPairer(devices[(size_t)d])); });
         if (rc != IHTB_OK) return rc;
     }
-    const int nworkers = nd * per_dev;
+    // est_r (NegativeBinomial nuisance parameter): the reference carries the estimate from one fit of a thread to the
+    // next (v.d = mle_for_r(v), src/fit.jl:235-237; one IHTVariable per thread, src/cross_validation.jl:105), so the
+    // result depends on the order of the fits.  Reproduce the single-thread order: one worker, fold-major.
+    const bool sequential = c.est_r != 0;
+    if (sequential) for (int64_t i = 0; i < ngrid; ++i) order[(size_t)i] = i;
+    const int nworkers = sequential ? 1 : nd * per_dev;
     std::vector<int> wdev((size_t)nworkers);
     for (int w = 0; w < nworkers; ++w) wdev[(size_t)w] = devices[(size_t)(w / per_dev)];
     std::vector<double> wbusy((size_t)nworkers, 0.0);

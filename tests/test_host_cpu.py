@@ -111,6 +111,13 @@ def test_wrapper_parsers_without_gpu(tmp_path):
     fam.write_text("f1 i1 0 0 1 1.5\nf2 i2 0 0 2 -9\nf3 i3 0 0 1 NA\nf4 i4 0 0 2 2.5\n")
     y = api._read_fam_phenotype(str(fam))
     np.testing.assert_allclose(y, [1.5, 2.0, 2.0, 2.5])          # missing -> mean of the observed
+    # binary / count traits cannot be imputed: the reference throws (src/wrapper.jl:193-207)
+    for d in ("Bernoulli", "Poisson", "NegativeBinomial"):
+        with pytest.raises(api.MissingPhenotype):
+            api._read_fam_phenotype(str(fam), 6, d)
+    fam2 = tmp_path / "t2.fam"
+    fam2.write_text("f1 i1 0 0 1 1.5 4\nf2 i2 0 0 2 -9 6\nf3 i3 0 0 1 0.5 NA\n")
+    np.testing.assert_allclose(api._read_fam_phenotypes_mv(str(fam2), [6, 7]), [[1.5, 1.0, 0.5], [4.0, 6.0, 5.0]])
     w = np.array([0.5, 0.1, 0.01])
     assert m.canonicallink("NegativeBinomial") == "LogLink" and m.canonicallink("Bernoulli") == "LogitLink"
     assert m.allocate_fold_and_k(2, [3, 5]) == [(1, 3), (1, 5), (2, 3), (2, 5)]
