@@ -64,8 +64,11 @@ __device__ __forceinline__ void consumer_bar() {
 }
 
 // 512 consumer threads: thread -> (nibble t, word w) pair and one half of the 16 values
+// cls selects what a 2-bit code contributes: 0 = the additive dosage (0, 0, 1, 2 for codes 00, 01, 10, 11; the X'v
+// sweep), 1 = the heterozygote indicator (code 10), 2 = the homozygote indicator (code 11) -- the class sums
+// sum_i v_i [g_ij = 1] and sum_i v_i [g_ij = 2] that initialize_beta! needs (src/utilities.jl:776-812)
 __device__ __forceinline__ void build64(uint32_t tab, const double* __restrict__ v, double vbar, int64_t n,
-                                        int64_t slab, int tid) {
+                                        int64_t slab, int tid, int cls) {
     const int pair = tid & 255, half = tid >> 8;
     const int t = pair >> 5, w = pair & 31;
     const int64_t i0 = slab * 512 + 16 * w + 2 * t;
@@ -76,8 +79,15 @@ __device__ __forceinline__ void build64(uint32_t tab, const double* __restrict__
     for (int e = 0; e < 8; ++e) {
         const int val = half * 8 + e;
         const int c0 = val & 3, c1 = val >> 2;
-        const double a0 = (c0 == 2) ? u0 : ((c0 == 3) ? __dadd_rn(u0, u0) : 0.0);
-        const double a1 = (c1 == 2) ? u1 : ((c1 == 3) ? __dadd_rn(u1, u1) : 0.0);
+        double a0, a1;
+        if (cls == 0) {
+            a0 = (c0 == 2) ? u0 : ((c0 == 3) ? __dadd_rn(u0, u0) : 0.0);
+            a1 = (c1 == 2) ? u1 : ((c1 == 3) ? __dadd_rn(u1, u1) : 0.0);
+        } else {
+            const int hit = cls == 1 ? 2 : 3;
+            a0 = (c0 == hit) ? u0 : 0.0;
+            a1 = (c1 == hit) ? u1 : 0.0;
+        }
         sts_f64(base + (uint32_t)val * 256u, __dadd_rn(a0, a1));
     }
 }
@@ -94,8 +104,8 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
 template <bool QUAD>
 __global__ void __launch_bounds__((X_CW + 1) * 32, 1)
 k_sweep_lut64(const uint8_t* __restrict__ bed, int64_t cs_s, int64_t p, int64_t p_out, int64_t n, int64_t n_slabs,
-              const double* __restrict__ v, const double* __restrict__ vbar_p, double* __restrict__ part) {
-    const double vbar = *vbar_p;
+              const double* __restrict__ v, const double* __restrict__ vbar_p, double* __restrict__ part, int cls) {
+    const double vbar = vbar_p ? *vbar_p : 0.0;         // class sums are taken of the vector itself
     constexpr int WPG = X_CW / X_G;                 // warps per group
     constexpr int CPW = X_STAGE_COLS / WPG;         // columns per warp per unit (16)
     constexpr int S = X_STAGES;
@@ -165,7 +175,7 @@ k_sweep_lut64(const uint8_t* __restrict__ bed, int64_t cs_s, int64_t p, int64_t 
             const int cb0 = (slab == slab_beg) ? (int)(u_beg - slab * n_cblocks) : 0;
             const int cb1 = (slab == slab_end) ? (int)(u_end - slab * n_cblocks) : ncb;
             consumer_bar();
-            build64(tab, v, vbar, n, slab, tid);
+            build64(tab, v, vbar, n, slab, tid, cls);
             consumer_bar();
             double* __restrict__ outp = part + slab * p_out + col;
             const int i_end = i_base + (cb1 - cb0);
@@ -223,7 +233,8 @@ k_sweep_lut64(const uint8_t* __restrict__ bed, int64_t cs_s, int64_t p, int64_t 
 }  // namespace
 
 // tiled layouts only (cs_j == 128, plain or quad-interleaved); d_part is [stride/128][p] doubles
-void sweep_exact_lut_partials(const ihtb_geno* g, const double* d_v, const double* d_vbar, double* d_part, cudaStream_t s) {
+void sweep_exact_lut_partials(const ihtb_geno* g, const double* d_v, const double* d_vbar, double* d_part, cudaStream_t s,
+                              int cls) {
     IHTB_CHECK(g->cs_j == 128, IHTB_EINVAL, "the table-driven exact sweep needs a tiled layout");
     IHTB_CHECK(g->p < (int64_t(1) << 31) - 256, IHTB_EDIM, "more than 2^31 SNP columns on one GPU");
     const int64_t n_slabs = g->stride / 128;
@@ -233,11 +244,11 @@ void sweep_exact_lut_partials(const ihtb_geno* g, const double* d_v, const doubl
     if (g->quad) {
         ensure_dynamic_smem(k_sweep_lut64<true>, X_SMEM_BYTES);
         IHTB_LAUNCH(k_sweep_lut64<true>, grid, (X_CW + 1) * 32, X_SMEM_BYTES, s, g->bed.p, g->cs_s, g->p4, g->p, g->n,
-                    n_slabs, d_v, d_vbar, d_part);
+                    n_slabs, d_v, d_vbar, d_part, cls);
     } else {
         ensure_dynamic_smem(k_sweep_lut64<false>, X_SMEM_BYTES);
         IHTB_LAUNCH(k_sweep_lut64<false>, grid, (X_CW + 1) * 32, X_SMEM_BYTES, s, g->bed.p, g->cs_s, g->p, g->p, g->n,
-                    n_slabs, d_v, d_vbar, d_part);
+                    n_slabs, d_v, d_vbar, d_part, cls);
     }
 }
 
