@@ -317,8 +317,7 @@ struct ihtb_fit {
     // The top-k of |b0 + eta*df| always lies in supp(b0) plus the k largest |df_j| outside it, for ANY eta, so the
     // gradient step and all its backtracks are then pure host work on ~2k exact values.
     void score_and_sweep() {
-        glm_score(glm, s);                                   // scal: sum r, sum |r|, df2[q]
-        glm_mean_from_sum(glm, d_vbar.p, s);                 // d_vbar[0] = scal[0] / n
+        glm_score(glm, s, d_vbar.p);                         // scal: sum r, sum |r|, df2[q]; d_vbar[0] = scal[0] / n
         IHTB_CUDA(cudaMemcpyAsync(h_scal.p, d_scal.p, (2 + q) * sizeof(double), cudaMemcpyDeviceToHost, s));
         IHTB_CUDA(cudaEventRecord(ev0, s));
         sweep_coef = cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound;
@@ -362,12 +361,10 @@ struct ihtb_fit {
                                   (paired && !rerun) ? pairer->d_l2 + pair_slot : nullptr);
             // slots re-scored without a second round trip; the looser bound of a PAIR sweep admits more near-threshold columns
             glaunch = (int)std::min<int64_t>(comm ? capx / 2 : cap, ksel + (sweep_coef == kPairBound ? 1024 : 64));
-            xt_gather(g, tk.cand, glaunch, d_r.p, 1, d_vbar.p, d_gout.p, s);      // slots beyond the count hold -1
         }
-        if (nsupp) {
-            upload(d_cols.p, supp_loc.data(), supp_loc.size());
-            xt_gather(g, d_cols.p, nsupp, d_r.p, 1, d_vbar.p, d_gout.p + glaunch, s);
-        }
+        if (nsupp) upload(d_cols.p, supp_loc.data(), supp_loc.size());
+        // candidates (slots beyond the count hold -1) and the current support re-scored exactly in ONE launch
+        xt_gather2(g, tk.cand, glaunch, d_cols.p, nsupp, d_r.p, 1, d_vbar.p, d_gout.p, s);
         // the next iteration's step-size denominator ||sqrt(W) (X[:,idx] df[idx] + Z[:,idc] df2[idc])||^2 needs nothing
         // from the host either: the support's exact df values are in d_gout, df2 is in d_scal (src/utilities.jl:728-756)
         denom_ready = false;
@@ -1254,7 +1251,7 @@ static ihtb_fit* fit_allocate(const ihtb_geno* g, int64_t q, int cap) {
     size_t cols_cap = 2 * (size_t)cap + 64;
     f->d_coef.alloc(cols_cap); f->d_gout.alloc(cols_cap); f->d_vbar.alloc(1);
     f->d_idx.alloc(cols_cap); f->d_cols.alloc(cols_cap);
-    f->d_keyL.alloc(p); f->d_keyU.alloc(p); f->d_hist.alloc(2048); f->d_sel.alloc(2 + cap);
+    f->d_keyL.alloc(p); f->d_keyU.alloc(p); f->d_hist.alloc(2 * 3 * 2048); f->d_sel.alloc(2 + cap);
     f->h_scal.alloc(2 + q + 8); f->h_gout.alloc(cols_cap); f->h_sel.alloc(2 + cap);
     f->sweep_scratch = sweep_scratch_create();
     f->d_hist.zero(f->s);
@@ -1326,6 +1323,7 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
         if (zkeep) for (int64_t l = 0; l < q; ++l) f->zkeep[l] = zkeep[l] ? 1 : 0;
         f->zkeepn = 0;
         for (auto v : f->zkeep) f->zkeepn += v;
+        f->d_hist.zero(f->s);          // both histogram sets of the candidate selection start clean (topk.cu)
         f->inited = false; f->sweep_pending = false; f->denom_ready = false;
         f->n_sweeps = 0; f->n_backtracks = 0; f->sweep_ms_total = 0.0;
         for (int i = 0; i < 4; ++i) f->phase[i] = 0.0;

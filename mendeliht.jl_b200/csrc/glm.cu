@@ -150,7 +150,9 @@ k_set_weights(int64_t n, const uint8_t* __restrict__ mask, const double* __restr
 }
 
 // out[v] = sum_b part[b*nv + v]: one warp per value, lanes stride over the blocks, fixed shuffle tree (deterministic)
-__global__ void k_finalize(const double* __restrict__ part, int nblocks, int nv, double* __restrict__ out) {
+// mean_out (optional): also writes out[0] / n, the mean the sweep centres the residual with (saves a launch)
+__global__ void k_finalize(const double* __restrict__ part, int nblocks, int nv, double* __restrict__ out,
+                           double* __restrict__ mean_out = nullptr, int64_t n = 1) {
     part += (int64_t)blockIdx.y * nblocks * nv; out += blockIdx.y * nv;       // batched: one row of sums per model
     int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -158,7 +160,10 @@ __global__ void k_finalize(const double* __restrict__ part, int nblocks, int nv,
     double a = 0.0;
     for (int b = lane; b < nblocks; b += 32) a += part[b * nv + v];
     a = warp_sum(a);
-    if (lane == 0) out[v] = a;
+    if (lane == 0) {
+        out[v] = a;
+        if (mean_out && v == 0 && blockIdx.y == 0) mean_out[0] = a / (double)n;
+    }
 }
 
 __global__ void k_mean_from_sum(const double* __restrict__ scal, int64_t n, double* __restrict__ out) {
@@ -256,12 +261,12 @@ void glm_mu_batched(GlmCtx& c, const double* d_cM, int M, double* xbM, double* z
                 c.nb_r, 1, d_partM);
     IHTB_LAUNCH(k_finalize, dim3(1, M), 96, 0, s, d_partM, grid, 3, d_scalM);
 }
-void glm_score(GlmCtx& c, cudaStream_t s) {
+void glm_score(GlmCtx& c, cudaStream_t s, double* d_mean) {
     int grid = glm_grid(c.n);
     int nv = 2 + (int)c.q;
     IHTB_LAUNCH(k_score, grid, GLM_THREADS, 0, s, c.n, c.q, c.Z, c.xb, c.zc, c.mu, c.y, c.w, c.dist, c.link, c.nb_r,
                 c.r, c.part);
-    IHTB_LAUNCH(k_finalize, (unsigned)ceil_div(nv, 4), 128, 0, s, c.part, grid, nv, c.scal);
+    IHTB_LAUNCH(k_finalize, (unsigned)ceil_div(nv, 4), 128, 0, s, c.part, grid, nv, c.scal, d_mean, c.n);
 }
 void glm_stepsize(GlmCtx& c, const double* d_d2, const double* d_xs, cudaStream_t s, const double* d_d2mask,
                   double* d_out) {

@@ -111,7 +111,8 @@ void glm_mu(GlmCtx& c, const double* d_c, int add_zc, cudaStream_t s);        //
 void glm_mu_batched(GlmCtx& c, const double* d_cM, int M, double* xbM, double* zcM, double* muM, double* d_partM,
                     double* d_scalM, cudaStream_t s);                           // d_scalM[3m..]: dev, lp, sum w of model m
 void glm_mean_from_sum(GlmCtx& c, double* d_mean, cudaStream_t s);             // d_mean[0] = scal[0] / n
-void glm_score(GlmCtx& c, cudaStream_t s);                                      // scal: sum r, sum |r|, df2[q]
+// r, sums [sum r, sum |r|, df2[q]]; d_mean (optional) receives mean(r) = sum r / n
+void glm_score(GlmCtx& c, cudaStream_t s, double* d_mean = nullptr);                                      // scal: sum r, sum |r|, df2[q]
 // scal[0] (or *d_out) = sum of squares of sqrt(W) (xs + Z (d2 .* d2mask)); d2mask may be NULL
 void glm_stepsize(GlmCtx& c, const double* d_d2, const double* d_xs, cudaStream_t s, const double* d_d2mask = nullptr,
                   double* d_out = nullptr);

@@ -746,7 +746,7 @@ int32_t ihtb_mvfit_create(const ihtb_geno* g, const double* Y, int64_t r, const 
         size_t cols_cap = 2 * (size_t)f->cap + 64;
         f->d_coef.alloc(cols_cap * r); f->d_gout.alloc(cols_cap * r); f->d_vbar.alloc(r); f->d_sval.alloc(cols_cap);
         f->d_idx.alloc(cols_cap); f->d_cols.alloc(cols_cap); f->d_sidx.alloc(cols_cap); f->d_bounds.alloc(r);
-        f->d_keyL.alloc(p * r); f->d_keyU.alloc(p * r); f->d_hist.alloc(2048); f->d_sel.alloc(2 + f->cap);
+        f->d_keyL.alloc(p * r); f->d_keyU.alloc(p * r); f->d_hist.alloc(2 * 3 * 2048); f->d_sel.alloc(2 + f->cap);
         f->h_scal.alloc(nvmax + 8); f->h_gout.alloc(cols_cap * r); f->h_sel.alloc(2 + f->cap);
         f->sweep_scratch = sweep_scratch_create();
         f->d_b0d.zero(f->s); f->d_hist.zero(f->s);

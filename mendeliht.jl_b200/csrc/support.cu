@@ -125,13 +125,14 @@ constexpr int XG_MAX_SPLIT = 64;
 
 template <int M>
 __global__ void __launch_bounds__(256)
-k_xt_gather(GenoView gv, const int64_t* __restrict__ cols, int64_t split_bytes, const double* __restrict__ v,
+k_xt_gather(GenoView gv, const int64_t* __restrict__ cols, int64_t n_a, const int64_t* __restrict__ cols_b,
+            int64_t split_bytes, const double* __restrict__ v,
             const double* __restrict__ vbar, double* __restrict__ part /*[ncols][nsplit][2M]*/) {
     __shared__ double sh[32];
     const int64_t nbytes = gv.nbytes, n = gv.n;
     const int64_t c = blockIdx.x, sp = blockIdx.y;
-    const int64_t j = cols[c];
-    if (j < 0) return;                       // column owned by another shard (block-uniform exit)
+    const int64_t j = c < n_a ? cols[c] : cols_b[c - n_a];      // two column lists, one launch (candidates | support)
+    if (j < 0) return;                       // unused slot / column owned by another shard (block-uniform exit)
     const int64_t b0 = sp * split_bytes;
     const int64_t b1 = (b0 + split_bytes < nbytes) ? b0 + split_bytes : nbytes;
     double a[M], mm[M], vb[M];
@@ -164,21 +165,23 @@ k_xt_gather(GenoView gv, const int64_t* __restrict__ cols, int64_t split_bytes, 
 }
 
 template <int M>
-__global__ void k_xt_gather_fin(GenoView gv, const int64_t* __restrict__ cols, int64_t ncols, int nsplit,
+__global__ void k_xt_gather_fin(GenoView gv, const int64_t* __restrict__ cols, int64_t n_a,
+                                const int64_t* __restrict__ cols_b, int64_t ncols, int nsplit,
                                 const double* __restrict__ vbar, const double* __restrict__ part,
                                 double* __restrict__ out) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= ncols * M) return;
     int64_t c = e / M;
     int t = (int)(e % M);
-    if (cols[c] < 0) { out[c + (int64_t)t * ncols] = 0.0; return; }
+    const int64_t jc = c < n_a ? cols[c] : cols_b[c - n_a];
+    if (jc < 0) { out[c + (int64_t)t * ncols] = 0.0; return; }
     double at = 0.0, mt = 0.0;
     for (int sp = 0; sp < nsplit; ++sp) {
         const double* o = part + (c * nsplit + sp) * (2 * M);
         at = __dadd_rn(at, o[2 * t]);
         mt = __dadd_rn(mt, o[2 * t + 1]);
     }
-    int64_t j = cols[c];
+    int64_t j = jc;
     double corr = gv.impute ? mt : __dmul_rn(-vbar[t], (double)gv.nmiss[j]);
     out[c + (int64_t)t * ncols] = __dmul_rn(gv.sinv[j], __dadd_rn(at, __dmul_rn(gv.mu[j], corr)));
 }
@@ -196,8 +199,8 @@ static DBuf<double>& gather_scratch(cudaStream_t s) {
 }
 
 template <int M>
-static void launch_xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t ncols, const double* d_v,
-                             const double* d_vbar, double* d_out, cudaStream_t s) {
+static void launch_xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t n_a, const int64_t* d_cols_b,
+                             int64_t ncols, const double* d_v, const double* d_vbar, double* d_out, cudaStream_t s) {
     int64_t split_bytes = ceil_div(ceil_div(g->nbytes, XG_MAX_SPLIT), 256) * 256;
     if (split_bytes < 1024) split_bytes = 1024;
     int nsplit = (int)ceil_div(g->nbytes, split_bytes);
@@ -208,24 +211,31 @@ static void launch_xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t 
         sc.alloc(need < 65536 ? 65536 : need);
     }
     dim3 grid((unsigned)ncols, (unsigned)nsplit);
-    IHTB_LAUNCH((k_xt_gather<M>), grid, 256, 0, s, geno_view(g), d_cols, split_bytes, d_v, d_vbar, sc.p);
-    IHTB_LAUNCH((k_xt_gather_fin<M>), (unsigned)ceil_div(ncols * M, 128), 128, 0, s, geno_view(g), d_cols, ncols,
-                nsplit, d_vbar, sc.p, d_out);
+    IHTB_LAUNCH((k_xt_gather<M>), grid, 256, 0, s, geno_view(g), d_cols, n_a, d_cols_b, split_bytes, d_v, d_vbar, sc.p);
+    IHTB_LAUNCH((k_xt_gather_fin<M>), (unsigned)ceil_div(ncols * M, 128), 128, 0, s, geno_view(g), d_cols, n_a, d_cols_b,
+                ncols, nsplit, d_vbar, sc.p, d_out);
 }
 
-void xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t ncols, const double* d_v, int64_t m,
-               const double* d_vbar, double* d_out, cudaStream_t s) {
+// two column lists in one launch: out[0 .. n_a) from d_cols_a, out[n_a .. n_a + n_b) from d_cols_b (either may be empty)
+void xt_gather2(const ihtb_geno* g, const int64_t* d_cols_a, int64_t n_a, const int64_t* d_cols_b, int64_t n_b,
+                const double* d_v, int64_t m, const double* d_vbar, double* d_out, cudaStream_t s) {
+    const int64_t ncols = n_a + n_b;
     if (ncols == 0) return;
     for (int64_t t0 = 0; t0 < m;) {
         int64_t mm = m - t0;
         const double* vv = d_v + t0 * g->n;
         const double* vb = d_vbar + t0;
         double* o = d_out + t0 * ncols;
-        if (mm >= 4) { launch_xt_gather<4>(g, d_cols, ncols, vv, vb, o, s); t0 += 4; }
-        else if (mm == 3) { launch_xt_gather<3>(g, d_cols, ncols, vv, vb, o, s); t0 += 3; }
-        else if (mm == 2) { launch_xt_gather<2>(g, d_cols, ncols, vv, vb, o, s); t0 += 2; }
-        else { launch_xt_gather<1>(g, d_cols, ncols, vv, vb, o, s); t0 += 1; }
+        if (mm >= 4) { launch_xt_gather<4>(g, d_cols_a, n_a, d_cols_b, ncols, vv, vb, o, s); t0 += 4; }
+        else if (mm == 3) { launch_xt_gather<3>(g, d_cols_a, n_a, d_cols_b, ncols, vv, vb, o, s); t0 += 3; }
+        else if (mm == 2) { launch_xt_gather<2>(g, d_cols_a, n_a, d_cols_b, ncols, vv, vb, o, s); t0 += 2; }
+        else { launch_xt_gather<1>(g, d_cols_a, n_a, d_cols_b, ncols, vv, vb, o, s); t0 += 1; }
     }
+}
+
+void xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t ncols, const double* d_v, int64_t m,
+               const double* d_vbar, double* d_out, cudaStream_t s) {
+    xt_gather2(g, d_cols, ncols, nullptr, 0, d_v, m, d_vbar, d_out, s);
 }
 
 }  // namespace ihtb

@@ -30,7 +30,16 @@ k_keys_hist0(int64_t p, const double* __restrict__ dfa, const double* __restrict
              const double* __restrict__ sinv, int64_t p_mod, const double* __restrict__ bounds, double eta,
              double bound, const double* __restrict__ scal, double bound_coef, const double* __restrict__ wt,
              uint32_t* __restrict__ keyL, uint32_t* __restrict__ keyU, int* __restrict__ hist,
-             const double* __restrict__ l2) {
+             const double* __restrict__ l2, int* __restrict__ hist_other, TopkState* __restrict__ st,
+             int64_t* __restrict__ cand, int cand_fill) {
+    // housekeeping of the fused chain: the other histogram set is cleared for the NEXT selection, the candidate count
+    // restarts, unused candidate slots read -1 (a gather launched over a fixed number of slots skips them)
+    if (blockIdx.x == 0) {
+        for (int b = threadIdx.x; b < 3 * TK_BINS; b += blockDim.x) hist_other[b] = 0;
+        if (threadIdx.x == 0) { st->prefix = 0; st->k_rem = 0; st->count = 0; st->pad = 0; }
+    }
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cand_fill; i += (int64_t)gridDim.x * blockDim.x)
+        cand[i] = -1;
     // scal != NULL: the bound comes from the score kernel's sums still on the device:
     // bound = coef * (sum|r| + |sum r|) >= coef * ||r - mean(r)||_1 (no host round trip between sweep and selection)
     // l2 != NULL (PAIR sweeps): bound = coef * ||r - mean(r)||_2, and `sinv` is the handle's sgn array
@@ -59,82 +68,111 @@ k_keys_hist0(int64_t p, const double* __restrict__ dfa, const double* __restrict
     hist_flush(sh, hist, TK_BINS);
 }
 
-// later passes: histogram of `bits` bits at `shift` among keys whose higher bits equal st->prefix
-__global__ void __launch_bounds__(TK_THREADS)
-k_hist(int64_t p, const uint32_t* __restrict__ keyL, const TopkState* __restrict__ st, int shift, int bits,
-       int* __restrict__ hist) {
-    __shared__ int sh[TK_BINS];
-    const int nb = 1 << bits;
-    for (int b = threadIdx.x; b < nb; b += blockDim.x) sh[b] = 0;
-    __syncthreads();
-    const uint32_t prefix = st->prefix;
-    const uint32_t himask = ~((1u << (shift + bits)) - 1u);   // bits above this digit
-    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p; j += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t k = keyL[j];
-        if ((k & himask) == (prefix & himask)) atomicAdd(&sh[(k >> shift) & (nb - 1)], 1);
-    }
-    __syncthreads();
-    hist_flush(sh, hist, nb);
-}
+// ---- fused digit picks -------------------------------------------------------------------------------------------
+// Round 1 ran the select as reset / keys+hist0 / pick / hist / pick / hist / pick / compact = 8 dependent launches of a
+// few microseconds each.  Every later pass now RE-DERIVES the digits of the earlier passes from their (finished,
+// read-only) histograms inside each CTA -- a 2048-bin suffix scan per pass and CTA, a microsecond of redundant work --
+// so the chain is keys+hist0 / hist1 / hist2 / compact.  Histograms are double-buffered between two consecutive selections
+// (`set`): the first kernel of a selection clears the other set for the next one, nobody ever clears what is being read.
+constexpr int TK_HIST_STRIDE = 3 * TK_BINS;        // ints per histogram set: hist0 | hist1 | hist2
 
-// one block of 1024 threads: find the digit whose suffix count crosses k_rem, then clear the histogram
-__global__ void __launch_bounds__(1024)
-k_pick(int* __restrict__ hist, TopkState* __restrict__ st, int shift, int bits) {
-    __shared__ int warp_tot[32];
-    const int nb = 1 << bits;
+// block-wide: digit of the bin (counted from the TOP) where the suffix count of `hist` crosses k; returns the bin and
+// the remaining rank inside it through shared memory.  All TK_THREADS threads must call it.
+__device__ __forceinline__ void block_pick(const int* __restrict__ hist, int nb, int k, int* sh_scan /*[32]*/,
+                                           int* sh_out /*[2]*/) {
+    constexpr int PER = TK_BINS / TK_THREADS;      // 8 reversed positions per thread
     const int t = threadIdx.x;
-    // reversed order: position r <-> bin nb-1-r, two positions per thread
-    const int r0 = 2 * t, r1 = 2 * t + 1;
-    const int c0 = (r0 < nb) ? hist[nb - 1 - r0] : 0;
-    const int c1 = (r1 < nb) ? hist[nb - 1 - r1] : 0;
-    int s = c0 + c1;
+    int c[PER];
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int r = t * PER + i;                 // reversed position: bin nb - 1 - r
+        c[i] = (r < nb) ? hist[nb - 1 - r] : 0;
+        s += c[i];
+    }
     int incl = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         int v = __shfl_up_sync(0xffffffffu, incl, o);
         if ((t & 31) >= o) incl += v;
     }
-    if ((t & 31) == 31) warp_tot[t >> 5] = incl;
+    if ((t & 31) == 31) sh_scan[t >> 5] = incl;
     __syncthreads();
     if (t < 32) {
-        int v = warp_tot[t];
+        int v = (t < TK_THREADS / 32) ? sh_scan[t] : 0;
         int sc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int u = __shfl_up_sync(0xffffffffu, sc, o);
             if (t >= o) sc += u;
         }
-        warp_tot[t] = sc - v;   // exclusive prefix of warp totals
+        if (t < TK_THREADS / 32) sh_scan[t] = sc - v;          // exclusive prefix of the warp totals
     }
     __syncthreads();
-    incl += warp_tot[t >> 5];
-    const int excl = incl - s;
-    const int k = st->k_rem;
-    __syncthreads();
-    if (excl < k && k <= incl) {
-        int bin, krem;
-        if (excl + c0 >= k) { bin = nb - 1 - r0; krem = k - excl; }
-        else { bin = nb - 1 - r1; krem = k - excl - c0; }
-        st->prefix |= (uint32_t)bin << shift;
-        st->k_rem = krem;
+    incl += sh_scan[t >> 5];
+    int excl = incl - s;
+    if (excl < k && k <= incl) {                                // exactly one thread: the crossing lies in its 8 bins
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            if (excl < k && k <= excl + c[i]) { sh_out[0] = nb - 1 - (t * PER + i); sh_out[1] = k - excl; }
+            excl += c[i];
+        }
     }
-    for (int b = t; b < TK_BINS; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
 }
 
+// pass 1 / 2: derive the digits of the earlier passes, then histogram the next digit among the keys that match
 __global__ void __launch_bounds__(TK_THREADS)
-k_compact(int64_t p, const uint32_t* __restrict__ keyU, TopkState* __restrict__ st, int64_t* __restrict__ cand,
-          int cap) {
-    const uint32_t tau = st->prefix;
+k_hist_fused(int64_t p, const uint32_t* __restrict__ keyL, const int* __restrict__ hists /*this set*/, int pass, int kk,
+             int* __restrict__ hist_out) {
+    __shared__ int sh[TK_BINS];
+    __shared__ int sh_scan[32];
+    __shared__ int sh_out[2];
+    block_pick(hists, TK_BINS, kk, sh_scan, sh_out);                           // digit 0: bits 31..21
+    uint32_t prefix = (uint32_t)sh_out[0] << 21;
+    int shift = 10, bits = 11;
+    uint32_t himask = 0xFFE00000u;
+    if (pass == 2) {
+        const int k1 = sh_out[1];
+        __syncthreads();
+        block_pick(hists + TK_BINS, TK_BINS, k1, sh_scan, sh_out);             // digit 1: bits 20..10
+        prefix |= (uint32_t)sh_out[0] << 10;
+        shift = 0; bits = 10; himask = 0xFFFFFC00u;
+    }
+    const int nb = 1 << bits;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p; j += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = keyL[j];
+        if ((k & himask) == prefix) atomicAdd(&sh[(k >> shift) & (nb - 1)], 1);
+    }
+    __syncthreads();
+    hist_flush(sh, hist_out, nb);
+}
+
+// last pass: derive all three digits (tau = the k-th largest lower-bound key), compact {j : keyU_j >= tau}
+__global__ void __launch_bounds__(TK_THREADS)
+k_compact_fused(int64_t p, const uint32_t* __restrict__ keyU, const int* __restrict__ hists, int kk,
+                TopkState* __restrict__ st, int64_t* __restrict__ cand, int cap) {
+    __shared__ int sh_scan[32];
+    __shared__ int sh_out[2];
+    block_pick(hists, TK_BINS, kk, sh_scan, sh_out);
+    uint32_t tau = (uint32_t)sh_out[0] << 21;
+    int k1 = sh_out[1];
+    __syncthreads();
+    block_pick(hists + TK_BINS, TK_BINS, k1, sh_scan, sh_out);
+    tau |= (uint32_t)sh_out[0] << 10;
+    k1 = sh_out[1];
+    __syncthreads();
+    block_pick(hists + 2 * TK_BINS, 1024, k1, sh_scan, sh_out);
+    tau |= (uint32_t)sh_out[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->prefix = tau; st->k_rem = sh_out[1]; }
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p; j += (int64_t)gridDim.x * blockDim.x) {
         if (keyU[j] >= tau) {
             int pos = atomicAdd(&st->count, 1);
             if (pos < cap) cand[pos] = j;
         }
     }
-}
-
-__global__ void k_topk_reset(TopkState* st, int k) {
-    st->prefix = 0; st->k_rem = k; st->count = 0; st->pad = 0;
 }
 
 // dense b0 maintenance: zero old support entries, write new ones
@@ -146,18 +184,18 @@ __global__ void k_scatter(double* __restrict__ dst, const int64_t* __restrict__ 
 
 static void topk_run(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, int64_t p_mod,
                      const double* d_bounds, double eta, double bound, int64_t k, cudaStream_t s,
-                     const double* d_scal = nullptr, double bound_coef = 0.0, const double* d_l2 = nullptr) {
+                     const double* d_scal = nullptr, double bound_coef = 0.0, const double* d_l2 = nullptr,
+                     bool fill_cand = false) {
     int grid = tk_grid(c.p);
     int kk = (int)(k < c.p ? k : c.p);
-    IHTB_LAUNCH(k_topk_reset, 1, 1, 0, s, c.st, kk);
+    int* hs = c.hist + (size_t)(c.set & 1) * TK_HIST_STRIDE;             // this selection's histograms (all zero)
+    int* ho = c.hist + (size_t)((c.set & 1) ^ 1) * TK_HIST_STRIDE;       // cleared now for the next selection
+    ++c.set;
     IHTB_LAUNCH(k_keys_hist0, grid, TK_THREADS, 0, s, c.p, d_dfa, d_b0d, d_sinv, p_mod, d_bounds, eta, bound, d_scal,
-                bound_coef, c.wt, c.keyL, c.keyU, c.hist, d_l2);
-    IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 21, 11);
-    IHTB_LAUNCH(k_hist, grid, TK_THREADS, 0, s, c.p, c.keyL, c.st, 10, 11, c.hist);
-    IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 10, 11);
-    IHTB_LAUNCH(k_hist, grid, TK_THREADS, 0, s, c.p, c.keyL, c.st, 0, 10, c.hist);
-    IHTB_LAUNCH(k_pick, 1, 1024, 0, s, c.hist, c.st, 0, 10);
-    IHTB_LAUNCH(k_compact, grid, TK_THREADS, 0, s, c.p, c.keyU, c.st, c.cand, c.cap);
+                bound_coef, c.wt, c.keyL, c.keyU, hs, d_l2, ho, c.st, c.cand, fill_cand ? c.cap : 0);
+    IHTB_LAUNCH(k_hist_fused, grid, TK_THREADS, 0, s, c.p, c.keyL, hs, 1, kk, hs + TK_BINS);
+    IHTB_LAUNCH(k_hist_fused, grid, TK_THREADS, 0, s, c.p, c.keyL, hs, 2, kk, hs + 2 * TK_BINS);
+    IHTB_LAUNCH(k_compact_fused, grid, TK_THREADS, 0, s, c.p, c.keyU, hs, kk, c.st, c.cand, c.cap);
 }
 
 void topk_candidates(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, double eta,
@@ -171,9 +209,8 @@ void topk_candidates(TopkCtx& c, const double* d_dfa, const double* d_b0d, const
 void topk_candidates_absdf(TopkCtx& c, const double* d_dfa, const double* d_sinv, const double* d_scal,
                            double bound_coef, int64_t k, cudaStream_t s, double host_bound, const double* d_l2) {
     // unused candidate slots stay -1 so that a gather launched over a fixed number of slots can skip them
-    IHTB_CUDA(cudaMemsetAsync(c.cand, 0xFF, (size_t)c.cap * sizeof(int64_t), s));
     topk_run(c, d_dfa, nullptr, d_sinv, c.p, nullptr, 1.0, (d_scal || d_l2) ? 0.0 : host_bound, k, s, d_scal, bound_coef,
-             d_l2);
+             d_l2, /*fill_cand=*/true);
 }
 
 __global__ void k_take(const double* __restrict__ src, const int64_t* __restrict__ idx, int64_t k,

@@ -14,11 +14,12 @@ struct TopkCtx {
     int64_t p;
     uint32_t* keyL;
     uint32_t* keyU;
-    int* hist;         // 2048 ints, zero on entry
+    int* hist;         // 2 sets x 3 x 2048 ints, zero at creation (double-buffered between selections, topk.cu)
     TopkState* st;
     int64_t* cand;
     int cap;
     const double* wt = nullptr;   // optional prior weights [p]: keys rank |v_j| * wt_j
+    unsigned set = 0;             // histogram set of the next selection
 };
 
 void topk_candidates(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, double eta,
