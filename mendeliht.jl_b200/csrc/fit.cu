@@ -80,6 +80,16 @@ struct ihtb_fit {
     void* sweep_scratch = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
     bool sweep_pending = false;
+    // one_step_fused: the score phase is enqueued before the host knows which candidate model won
+    struct FusedStep {
+        std::vector<int64_t> uni_loc;     // this rank's columns of the union of the candidate supports (local indices)
+        size_t maxsupp = 0;               // largest candidate support
+        int M = 0;
+        int winner = -1;
+    };
+    FusedStep* fz = nullptr;
+    DBuf<double> d_pick;
+    HBuf<double> h_pick;
     // cross-validation farm: two fits of one device share their sweeps (pairer.cuh); null = every sweep alone
     SweepPairer* pairer = nullptr;
     int pair_slot = 0;
@@ -348,31 +358,44 @@ struct ihtb_fit {
         df_exact.clear(); cand_cache.clear();
         df_sparse = false;
         const double coef = sweep_coef;
-        // this rank's part of the current support (local indices)
+        // this rank's part of the current support (local indices); fused step: of the union of the candidate models'
+        // supports (already on the device in d_idx), since the winner is only known after the read-back
+        const bool fused = fz != nullptr && !rerun;
         std::vector<int64_t> supp_loc;
-        for (int64_t j : idx)
-            if (is_local(j)) supp_loc.push_back(j - j0);
+        if (fused) supp_loc = fz->uni_loc;
+        else
+            for (int64_t j : idx)
+                if (is_local(j)) supp_loc.push_back(j - j0);
         const int nsupp = (int)supp_loc.size();
+        const int64_t* d_supp = fused ? d_idx.p : d_cols.p;
         int glaunch = 0;
         if (cfg.k > 0) {
-            const int64_t ksel = cfg.k + (int64_t)idx.size();
+            const int64_t ksel = cfg.k + (int64_t)(fused ? fz->maxsupp : idx.size());
             const bool paired = coef == kPairBound;        // L2 bound over the handle's sgn scale (see kPairBound)
             topk_candidates_absdf(tk, d_dfa.p, paired ? g->sgn.p : g->sinv.p, rerun ? nullptr : d_scal.p, coef, ksel, s, bound,
                                   (paired && !rerun) ? pairer->d_l2 + pair_slot : nullptr);
             // slots re-scored without a second round trip; the looser bound of a PAIR sweep admits more near-threshold columns
             glaunch = (int)std::min<int64_t>(comm ? capx / 2 : cap, ksel + (sweep_coef == kPairBound ? 1024 : 64));
         }
-        if (nsupp) upload(d_cols.p, supp_loc.data(), supp_loc.size());
+        if (nsupp && !fused) upload(d_cols.p, supp_loc.data(), supp_loc.size());
         // candidates (slots beyond the count hold -1) and the current support re-scored exactly in ONE launch
-        xt_gather2(g, tk.cand, glaunch, d_cols.p, nsupp, d_r.p, 1, d_vbar.p, d_gout.p, s);
+        xt_gather2(g, tk.cand, glaunch, d_supp, nsupp, d_r.p, 1, d_vbar.p, d_gout.p, s);
         // the next iteration's step-size denominator ||sqrt(W) (X[:,idx] df[idx] + Z[:,idc] df2[idc])||^2 needs nothing
         // from the host either: the support's exact df values are in d_gout, df2 is in d_scal (src/utilities.jl:728-756)
         denom_ready = false;
         if (!rerun) {
-            support_matvec_dev(d_cols.p, nsupp, d_gout.p + glaunch, d_xs.p);
-            std::vector<double> mask((size_t)q);
-            for (int64_t l = 0; l < q; ++l) mask[l] = idc[l] ? 1.0 : 0.0;
-            upload(d_small.p + q, mask.data(), (size_t)q);
+            if (fused) {
+                // the winner's support is a subset of the union: zero the other coefficients on the device
+                glm_winner_coef(d_pick.p, d_coefM.p, nsupp, d_gout.p + glaunch, d_coef.p, d_cM.p, q, d_small.p + q, s);
+                support_matvec_dev(d_supp, nsupp, d_coef.p, d_xs.p);
+                IHTB_CUDA(cudaMemcpyAsync(h_pick.p, d_pick.p, (size_t)(1 + fz->M) * sizeof(double), cudaMemcpyDeviceToHost, s));
+                IHTB_CUDA(cudaMemcpyAsync(h_scalM.p, d_scalM.p, (size_t)(3 * fz->M) * sizeof(double), cudaMemcpyDeviceToHost, s));
+            } else {
+                support_matvec_dev(d_supp, nsupp, d_gout.p + glaunch, d_xs.p);
+                std::vector<double> mask((size_t)q);
+                for (int64_t l = 0; l < q; ++l) mask[l] = idc[l] ? 1.0 : 0.0;
+                upload(d_small.p + q, mask.data(), (size_t)q);
+            }
             glm_stepsize(glm, d_scal.p + 2, d_xs.p, s, d_small.p + q, d_scal.p + 2 + q);
             IHTB_CUDA(cudaMemcpyAsync(h_scal.p + 2 + q, d_scal.p + 2 + q, sizeof(double), cudaMemcpyDeviceToHost, s));
             denom_ready = true;
@@ -381,6 +404,7 @@ struct ihtb_fit {
             IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + glaunch) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
             IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_gout.p, (glaunch + nsupp) * sizeof(double), cudaMemcpyDeviceToHost, s));
             sync();
+            if (fused) adopt_winner();
             const TopkState* st = reinterpret_cast<const TopkState*>(h_sel.p);
             const int count = cfg.k > 0 ? st->count : 0;
             if (count > cap && coef == kPairBound && !rerun) {
@@ -400,7 +424,7 @@ struct ihtb_fit {
                 df_exact[h_sel.p[2 + t]] = h_gout.p[t];
                 cand_cache.push_back(h_sel.p[2 + t]);
             }
-            for (int t = 0; t < nsupp; ++t) df_exact[supp_loc[t]] = h_gout.p[glaunch + t];
+            for (int t = 0; t < nsupp; ++t) df_exact[supp_loc[t] + j0] = h_gout.p[glaunch + t];
             if (count > glaunch) {                       // rare: many near-ties; fetch and re-score the remainder
                 IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + count) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
                 sync();
@@ -413,10 +437,11 @@ struct ihtb_fit {
             const size_t blk = 2 + 2 * (size_t)capx;
             IHTB_CHECK(nsupp <= capx / 2, IHTB_ENUMERIC, "support too large for the sharded candidate exchange");
             pack_sweep_candidates(d_pack.p, reinterpret_cast<const TopkState*>(d_sel.p), tk.cand, glaunch, d_gout.p,
-                                  d_cols.p, nsupp, d_gout.p + glaunch, j0, capx, s);
+                                  d_supp, nsupp, d_gout.p + glaunch, j0, capx, s);
             comm_allgather_i64(comm, d_pack.p, d_packall.p, blk, s);
             IHTB_CUDA(cudaMemcpyAsync(h_packall.p, d_packall.p, nr * blk * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
             sync();
+            if (fused) adopt_winner();
             for (int r = 0; r < nr; ++r) {
                 const int64_t* b_ = h_packall.p + (size_t)r * blk;
                 IHTB_CHECK(b_[0] <= glaunch, IHTB_ENUMERIC,
@@ -1039,79 +1064,93 @@ struct ihtb_fit {
         static const bool off = [] { const char* e = getenv("IHTB_NO_BATCH"); return e && *e == '1'; }();
         return !off && cfg.est_r == 0 && cfg.max_step >= 1 && cfg.max_step + 1 <= kMaxBatch;
     }
-    void one_step_batched(double old_logl, double& eta, int& eta_step, double& new_logl) {
+    struct StepModel { double eta; std::vector<int64_t> idx; std::vector<double> b, c; std::vector<uint8_t> idc; };
+    std::vector<StepModel> step_models;
+    void ensure_batch_buffers() {
         if (d_xbM.n < (size_t)(kMaxBatch * n)) {
             d_xbM.alloc((size_t)(kMaxBatch * n)); d_zcM.alloc((size_t)(kMaxBatch * n)); d_muM.alloc((size_t)(kMaxBatch * n));
             d_partM.alloc((size_t)kMaxBatch * GLM_MAX_BLOCKS * 3); d_scalM.alloc(kMaxBatch * 3); h_scalM.alloc(kMaxBatch * 3);
             d_cM.alloc((size_t)(kMaxBatch * q)); d_coefM.alloc((size_t)kMaxBatch * (size_t)cap);
+            d_pick.alloc(1 + kMaxBatch); h_pick.alloc(1 + kMaxBatch);
         }
-        double t0 = now();
-        const double eta0 = stepsize();
-        double t1 = now(); phase[0] += t1 - t0;
+    }
+    // host part shared by the batched and the fused step: the candidate models P_k(b0 + eta0 / 2^m df), m = 0..max_step,
+    // the union of their supports, and this rank's rows of the coefficient block (uploaded)
+    struct StepPlan { int M; std::vector<int64_t> uni, loc; size_t UL; };
+    StepPlan plan_step(double eta0) {
         const int M = cfg.max_step + 1;
-        struct Model { double eta; std::vector<int64_t> idx; std::vector<double> b, c; std::vector<uint8_t> idc; };
-        std::vector<Model> mods((size_t)M);
+        step_models.assign((size_t)M, StepModel{});
         double e = eta0;
         for (int m = 0; m < M; ++m) {
             if (m) { e /= 2; idx = idx0; b = b0; c = c0; }               // backtrack! (src/utilities.jl:959-973)
             gradstep(e);
-            mods[(size_t)m] = Model{e, idx, b, c, idc};
+            step_models[(size_t)m] = StepModel{e, idx, b, c, idc};
         }
-        std::vector<int64_t> uni;
-        for (const Model& md : mods) uni.insert(uni.end(), md.idx.begin(), md.idx.end());
-        std::sort(uni.begin(), uni.end());
-        uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
-        const size_t U = uni.size();
+        StepPlan pl; pl.M = M;
+        for (const StepModel& md : step_models) pl.uni.insert(pl.uni.end(), md.idx.begin(), md.idx.end());
+        std::sort(pl.uni.begin(), pl.uni.end());
+        pl.uni.erase(std::unique(pl.uni.begin(), pl.uni.end()), pl.uni.end());
+        const size_t U = pl.uni.size();
         IHTB_CHECK(U * (size_t)M <= d_coefM.n && U <= d_idx.n, IHTB_ENUMERIC, "support union too large for the batched step");
-        std::vector<double> coefM(U * (size_t)M, 0.0), cM((size_t)(M * q));
+        std::vector<size_t> keep_pos;
+        for (size_t t = 0; t < U; ++t)
+            if (is_local(pl.uni[t])) { pl.loc.push_back(pl.uni[t] - j0); keep_pos.push_back(t); }
+        pl.UL = pl.loc.size();
+        std::vector<double> coefL(pl.UL * (size_t)M, 0.0), cM((size_t)(M * q));
         for (int m = 0; m < M; ++m) {
-            const Model& md = mods[(size_t)m];
+            const StepModel& md = step_models[(size_t)m];
+            size_t u = 0;                               // both lists are sorted: one merge pass per model
             for (size_t t = 0; t < md.idx.size(); ++t) {
-                const size_t pos = (size_t)(std::lower_bound(uni.begin(), uni.end(), md.idx[t]) - uni.begin());
-                coefM[pos + (size_t)m * U] = md.b[t];
+                if (!is_local(md.idx[t])) continue;
+                const int64_t lj = md.idx[t] - j0;
+                while (pl.loc[u] != lj) ++u;
+                coefL[u + (size_t)m * pl.UL] = md.b[t];
             }
             for (int64_t l = 0; l < q; ++l) cM[(size_t)(m * q + l)] = md.c[(size_t)l];
         }
-        double t2 = now(); phase[1] += t2 - t1;
-        {
-            // this rank's columns of the union (all of them on a single GPU), local indices, same order
-            std::vector<int64_t> loc; std::vector<double> coefL;
-            loc.reserve(U);
-            std::vector<size_t> keep_pos;
-            for (size_t t = 0; t < U; ++t)
-                if (is_local(uni[t])) { loc.push_back(uni[t] - j0); keep_pos.push_back(t); }
-            const size_t UL = loc.size();
-            coefL.resize(UL * (size_t)M);
-            for (int m = 0; m < M; ++m)
-                for (size_t t = 0; t < UL; ++t) coefL[t + (size_t)m * UL] = coefM[keep_pos[t] + (size_t)m * U];
-            if (UL) {
-                upload(d_idx.p, loc.data(), UL);
-                upload(d_coefM.p, coefL.data(), coefL.size());
-            }
-            support_matvec_dev_m(UL ? d_idx.p : nullptr, (int64_t)UL, d_coefM.p, M, d_xbM.p);
+        if (pl.UL) {
+            upload(d_idx.p, pl.loc.data(), pl.UL);
+            upload(d_coefM.p, coefL.data(), coefL.size());
         }
         upload(d_cM.p, cM.data(), cM.size());
+        return pl;
+    }
+    void adopt_model(int m) {
+        const StepModel& win = step_models[(size_t)m];
+        idx = win.idx; b = win.b; c = win.c; idc = win.idc;
+    }
+    double logl_from_sums(const double* s3) const {
+        if (cfg.dist == IHTB_NORMAL) {
+            const double dev = s3[0], sw = s3[2], phi = dev / (double)n, sigma = std::sqrt(phi);
+            return -0.5 * (dev / phi) - sw * (0.5 * std::log(2.0 * M_PI) + std::log(sigma));
+        }
+        return s3[1];
+    }
+
+    void one_step_batched(double old_logl, double& eta, int& eta_step, double& new_logl) {
+        ensure_batch_buffers();
+        double t0 = now();
+        const double eta0 = stepsize();
+        double t1 = now(); phase[0] += t1 - t0;
+        const StepPlan pl = plan_step(eta0);
+        double t2 = now(); phase[1] += t2 - t1;
+        finish_batched(pl, t2, old_logl, eta, eta_step, new_logl);
+    }
+    void finish_batched(const StepPlan& pl, double t2, double old_logl, double& eta, int& eta_step, double& new_logl) {
+        const int M = pl.M;
+        support_matvec_dev_m(pl.UL ? d_idx.p : nullptr, (int64_t)pl.UL, d_coefM.p, M, d_xbM.p);
         glm_mu_batched(glm, d_cM.p, M, d_xbM.p, d_zcM.p, d_muM.p, d_partM.p, d_scalM.p, s);
         IHTB_CUDA(cudaMemcpyAsync(h_scalM.p, d_scalM.p, (size_t)(3 * M) * sizeof(double), cudaMemcpyDeviceToHost, s));
         sync();
-        auto logl_of = [&](int m) {
-            const double dev = h_scalM.p[3 * m], lp = h_scalM.p[3 * m + 1], sw = h_scalM.p[3 * m + 2];
-            if (cfg.dist == IHTB_NORMAL) {
-                const double phi = dev / (double)n, sigma = std::sqrt(phi);
-                return -0.5 * (dev / phi) - sw * (0.5 * std::log(2.0 * M_PI) + std::log(sigma));
-            }
-            return lp;
-        };
         int sidx = 0;
-        new_logl = logl_of(0);
+        new_logl = logl_from_sums(h_scalM.p);
         while (old_logl > new_logl && sidx < cfg.max_step) {                // _iht_backtrack_ (src/utilities.jl:484-486)
             ++sidx;
-            new_logl = logl_of(sidx);
+            new_logl = logl_from_sums(h_scalM.p + 3 * sidx);
             ++n_backtracks;
         }
-        const Model& win = mods[(size_t)sidx];
-        idx = win.idx; b = win.b; c = win.c; idc = win.idc;
-        eta = win.eta; eta_step = sidx;
+        adopt_model(sidx);
+        eta = step_models[(size_t)sidx].eta; eta_step = sidx;
         last_dev = h_scalM.p[3 * sidx];
         const size_t nb = (size_t)n * sizeof(double);
         IHTB_CUDA(cudaMemcpyAsync(d_xb.p, d_xbM.p + (size_t)sidx * n, nb, cudaMemcpyDeviceToDevice, s));
@@ -1124,8 +1163,65 @@ struct ihtb_fit {
         IHTB_CHECK(!std::isinf(new_logl), IHTB_ENUMERIC, "Loglikelihood function is Inf, aborting...");
     }
 
+    // The whole iteration behind ONE host round trip: the candidate models are evaluated, the backtracking winner is
+    // chosen ON THE DEVICE (k_pick_model: the reference's `while prev_logl > logl` walk over the M loglikelihoods), its
+    // xb / zc / mu are adopted, and the score phase (residual, sweep, candidate selection, exact re-scoring of the
+    // candidates and of the UNION of the candidate supports, next step-size denominator for the winner's support)
+    // follows on the stream; the host then reads everything back at once and learns which model won.
+    // Opt-in (IHTB_FUSE=1, read per step so that tests can switch it).  Measured at configs[1] on one B200: 694 vs 692
+    // it/s -- the saved synchronisation (~25 us) is paid back by three more tiny kernels and the larger union gather, so
+    // the default stays the two-round-trip batched step (profiles/r2_fused_step_ab.txt).
+    bool fuse_ok() const {
+        const char* e = getenv("IHTB_FUSE");
+        return e && *e == '1' && !grouped() && denom_ready && !df_sparse;
+    }
+    void adopt_winner() {
+        fz->winner = (int)h_pick.p[0];
+        adopt_model(fz->winner);
+    }
+    void one_step_fused(double old_logl, double& eta, int& eta_step, double& new_logl) {
+        ensure_batch_buffers();
+        double t0 = now();
+        const double eta0 = stepsize();                                  // host only: the denominator came back with the last sweep
+        double t1 = now(); phase[0] += t1 - t0;
+        const StepPlan pl = plan_step(eta0);
+        const int M = pl.M;
+        double t2 = now(); phase[1] += t2 - t1;
+        if (comm && pl.UL > (size_t)capx / 2) {       // the union does not fit the sharded candidate block: two round trips
+            finish_batched(pl, t2, old_logl, eta, eta_step, new_logl);
+            return;
+        }
+        support_matvec_dev_m(pl.UL ? d_idx.p : nullptr, (int64_t)pl.UL, d_coefM.p, M, d_xbM.p);
+        glm_mu_batched(glm, d_cM.p, M, d_xbM.p, d_zcM.p, d_muM.p, d_partM.p, d_scalM.p, s);
+        glm_pick_model(glm, d_scalM.p, M, old_logl, cfg.max_step, d_pick.p, d_xbM.p, d_zcM.p, d_muM.p, s);
+        FusedStep ctx;
+        ctx.uni_loc = pl.loc; ctx.M = M;
+        for (const StepModel& md : step_models) ctx.maxsupp = std::max(ctx.maxsupp, md.idx.size());
+        double t3 = now(); phase[2] += t3 - t2;
+        fz = &ctx;
+        try {
+            score_and_sweep();                                           // ends with the round trip and adopt_winner()
+        } catch (...) {
+            fz = nullptr;
+            throw;
+        }
+        fz = nullptr;
+        phase[3] += now() - t3;
+        const int w = ctx.winner;
+        n_backtracks += w;
+        eta = step_models[(size_t)w].eta; eta_step = w;
+        new_logl = h_pick.p[1 + w];
+        last_dev = h_scalM.p[3 * w];
+        IHTB_CHECK(!std::isnan(new_logl), IHTB_ENUMERIC, "Loglikelihood function is NaN, aborting...");
+        IHTB_CHECK(!std::isinf(new_logl), IHTB_ENUMERIC, "Loglikelihood function is Inf, aborting...");
+    }
+
     void one_step(double old_logl, double& eta, int& eta_step, double& new_logl) {
-        if (batch_ok()) { one_step_batched(old_logl, eta, eta_step, new_logl); return; }
+        if (batch_ok()) {
+            if (fuse_ok()) one_step_fused(old_logl, eta, eta_step, new_logl);
+            else one_step_batched(old_logl, eta, eta_step, new_logl);
+            return;
+        }
         double t0 = now();
         eta = stepsize();
         double t1 = now(); phase[0] += t1 - t0;

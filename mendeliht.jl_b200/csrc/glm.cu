@@ -261,6 +261,56 @@ void glm_mu_batched(GlmCtx& c, const double* d_cM, int M, double* xbM, double* z
                 c.nb_r, 1, d_partM);
     IHTB_LAUNCH(k_finalize, dim3(1, M), 96, 0, s, d_partM, grid, 3, d_scalM);
 }
+// ---- the gradient step and its backtracks decided on the device (fit.cu one_step_fused) ------------------------------
+// scalM[3m..] = deviance, sum of log-densities, sum of weights of candidate model m (eta / 2^m).  pick[1 + m] = its
+// loglikelihood (src/utilities.jl:9-20: Normal uses phi = deviance / length(y)), pick[0] = the model the reference's
+// loop `while prev_logl > logl && step < max_step` (src/utilities.jl:484-486) ends at.
+__global__ void k_pick_model(const double* __restrict__ scalM, int M, double old_logl, int max_step, int dist, int64_t n,
+                             double* __restrict__ pick) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int m = 0; m < M; ++m) {
+        const double dev = scalM[3 * m], lp = scalM[3 * m + 1], sw = scalM[3 * m + 2];
+        double l = lp;
+        if (dist == IHTB_NORMAL) {
+            const double phi = dev / (double)n, sigma = sqrt(phi);
+            l = -0.5 * (dev / phi) - sw * (0.5 * log(2.0 * 3.14159265358979323846) + log(sigma));
+        }
+        pick[1 + m] = l;
+    }
+    int w = 0;
+    while (old_logl > pick[1 + w] && w < max_step) ++w;
+    pick[0] = (double)w;
+}
+__global__ void k_take_model(const double* __restrict__ pick, int64_t n, const double* __restrict__ xbM,
+                             const double* __restrict__ zcM, const double* __restrict__ muM, double* __restrict__ xb,
+                             double* __restrict__ zc, double* __restrict__ mu) {
+    const int64_t off = (int64_t)pick[0] * n;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        xb[i] = xbM[off + i]; zc[i] = zcM[off + i]; mu[i] = muM[off + i];
+    }
+}
+// coefficients of the step-size product X[:, supp] df[supp] for the WINNER's support (a subset of the union the
+// exact gradient was gathered for), and its covariate mask
+__global__ void k_winner_coef(const double* __restrict__ pick, const double* __restrict__ coefM, int64_t U,
+                              const double* __restrict__ df_uni, double* __restrict__ coef_out,
+                              const double* __restrict__ cM, int64_t q, double* __restrict__ mask_out) {
+    const int64_t w = (int64_t)pick[0];
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < U) coef_out[t] = coefM[t + w * U] != 0.0 ? df_uni[t] : 0.0;
+    if (t < q) mask_out[t] = cM[t + w * q] != 0.0 ? 1.0 : 0.0;
+}
+void glm_pick_model(GlmCtx& c, const double* d_scalM, int M, double old_logl, int max_step, double* d_pick,
+                    const double* xbM, const double* zcM, const double* muM, cudaStream_t s) {
+    IHTB_LAUNCH(k_pick_model, 1, 32, 0, s, d_scalM, M, old_logl, max_step, c.dist, c.n, d_pick);
+    IHTB_LAUNCH(k_take_model, glm_grid(c.n), GLM_THREADS, 0, s, d_pick, c.n, xbM, zcM, muM, c.xb, c.zc, c.mu);
+}
+void glm_winner_coef(const double* d_pick, const double* d_coefM, int64_t U, const double* d_df_uni, double* d_coef_out,
+                     const double* d_cM, int64_t q, double* d_mask_out, cudaStream_t s) {
+    const int64_t m = U > q ? U : q;
+    IHTB_LAUNCH(k_winner_coef, (unsigned)ceil_div(m > 0 ? m : 1, 128), 128, 0, s, d_pick, d_coefM, U, d_df_uni, d_coef_out,
+                d_cM, q, d_mask_out);
+}
+
 void glm_score(GlmCtx& c, cudaStream_t s, double* d_mean) {
     int grid = glm_grid(c.n);
     int nv = 2 + (int)c.q;

@@ -110,7 +110,13 @@ struct GlmCtx {
 void glm_mu(GlmCtx& c, const double* d_c, int add_zc, cudaStream_t s);        // scal: dev, lp, sum w
 void glm_mu_batched(GlmCtx& c, const double* d_cM, int M, double* xbM, double* zcM, double* muM, double* d_partM,
                     double* d_scalM, cudaStream_t s);                           // d_scalM[3m..]: dev, lp, sum w of model m
-void glm_mean_from_sum(GlmCtx& c, double* d_mean, cudaStream_t s);             // d_mean[0] = scal[0] / n
+void glm_mean_from_sum(GlmCtx& c, double* d_mean, cudaStream_t s);
+// device-side choice among the M candidate models of a step (d_pick[0] = winner, d_pick[1 + m] = loglikelihoods) and
+// copy of the winner's xb / zc / mu into the fit's vectors; coefficients / covariate mask of the winner's support
+void glm_pick_model(GlmCtx& c, const double* d_scalM, int M, double old_logl, int max_step, double* d_pick,
+                    const double* xbM, const double* zcM, const double* muM, cudaStream_t s);
+void glm_winner_coef(const double* d_pick, const double* d_coefM, int64_t U, const double* d_df_uni, double* d_coef_out,
+                     const double* d_cM, int64_t q, double* d_mask_out, cudaStream_t s);             // d_mean[0] = scal[0] / n
 // r, sums [sum r, sum |r|, df2[q]]; d_mean (optional) receives mean(r) = sum r / n
 void glm_score(GlmCtx& c, cudaStream_t s, double* d_mean = nullptr);                                      // scal: sum r, sum |r|, df2[q]
 // scal[0] (or *d_out) = sum of squares of sqrt(W) (xs + Z (d2 .* d2mask)); d2mask may be NULL

@@ -561,3 +561,25 @@ def test_genuine_ties_at_the_kth_magnitude():
                 if kk == 1 and dup_src == 10:
                     assert res.beta[dup_src] != 0 and res.beta[dup_dst] != 0 and res.beta[dup_src] == res.beta[dup_dst]
         g.close()
+
+
+def test_device_side_backtracking_choice_matches_default():
+    """IHTB_FUSE=1: the backtracking winner is chosen on the device and the whole iteration needs one host round trip
+    (fit.cu one_step_fused).  Same support, iterations, backtracks and values as the default two-round-trip step."""
+    for d, l, n, p, k, ncov in [("Bernoulli", "LogitLink", 2000, 3000, 7, 1), ("Normal", "IdentityLink", 1200, 3000, 10, 2),
+                                ("Poisson", "LogLink", 1500, 2500, 8, 1)]:
+        seed = 100 + n + p
+        y, z, *_ = synth.simulate_response(seed, n, p, k - 2, d, n_cov=ncov)
+        g = m.B200SnpLinAlg.from_bed_columns(synth.packed_columns(seed, n, np.arange(p)), n)
+        ref = m.fit_iht(y, g, z, k=k, d=d, l=l)
+        os.environ["IHTB_FUSE"] = "1"
+        try:
+            res = m.fit_iht(y, g, z, k=k, d=d, l=l)
+        finally:
+            os.environ.pop("IHTB_FUSE", None)
+        assert res.iter == ref.iter and [t[1] for t in res.trace] == [t[1] for t in ref.trace]
+        assert np.array_equal(np.flatnonzero(res.beta), np.flatnonzero(ref.beta))
+        np.testing.assert_allclose(res.beta, ref.beta, rtol=1e-12, atol=0)
+        np.testing.assert_allclose([t[0] for t in res.trace], [t[0] for t in ref.trace], rtol=1e-12)
+        assert res.n_launches != ref.n_launches            # it really took the other path
+        g.close()
