@@ -127,6 +127,7 @@ struct ihtb_fit {
 
     // statistics
     int64_t n_sweeps = 0, n_backtracks = 0, n_cand_iter = 0, n_pair_overflow = 0;
+    int last_count = 0;                    // candidates the last selection found (sizes the next re-scoring launch)
     double sweep_ms_total = 0.0;
     double pve = 0.0;
 
@@ -358,6 +359,9 @@ struct ihtb_fit {
         df_exact.clear(); cand_cache.clear();
         df_sparse = false;
         const double coef = sweep_coef;
+        // (column, exact df) of every candidate; only the ones that survive the trim below enter df_exact -- a paired
+        // sweep may list thousands, and a hash-map insertion per candidate would cost more than the sweep saves
+        std::vector<std::pair<int64_t, double>> cvals;
         // this rank's part of the current support (local indices); fused step: of the union of the candidate models'
         // supports (already on the device in d_idx), since the winner is only known after the read-back
         const bool fused = fz != nullptr && !rerun;
@@ -375,7 +379,10 @@ struct ihtb_fit {
             topk_candidates_absdf(tk, d_dfa.p, paired ? g->sgn.p : g->sinv.p, rerun ? nullptr : d_scal.p, coef, ksel, s, bound,
                                   (paired && !rerun) ? pairer->d_l2 + pair_slot : nullptr);
             // slots re-scored without a second round trip; the looser bound of a PAIR sweep admits more near-threshold columns
-            glaunch = (int)std::min<int64_t>(comm ? capx / 2 : cap, ksel + (sweep_coef == kPairBound ? 1024 : 64));
+            // (sized from the previous iteration's count there)
+            const int64_t want = sweep_coef == kPairBound ? std::max<int64_t>(ksel + 1024, last_count + last_count / 4 + 256)
+                                                          : ksel + 64;
+            glaunch = (int)std::min<int64_t>(comm ? capx / 2 : cap, want);
         }
         if (nsupp && !fused) upload(d_cols.p, supp_loc.data(), supp_loc.size());
         // candidates (slots beyond the count hold -1) and the current support re-scored exactly in ONE launch
@@ -420,17 +427,16 @@ struct ihtb_fit {
             IHTB_CHECK(count <= cap, IHTB_ENUMERIC,
                        "degenerate projection: more than " + std::to_string(cap) +
                            " entries lie within the sweep error bound of the k-th largest |gradient|");
-            for (int t = 0; t < std::min(count, glaunch); ++t) {
-                df_exact[h_sel.p[2 + t]] = h_gout.p[t];
-                cand_cache.push_back(h_sel.p[2 + t]);
-            }
+            last_count = count;
+            cvals.reserve((size_t)count);
+            for (int t = 0; t < std::min(count, glaunch); ++t) cvals.push_back({h_sel.p[2 + t], h_gout.p[t]});
             for (int t = 0; t < nsupp; ++t) df_exact[supp_loc[t] + j0] = h_gout.p[glaunch + t];
             if (count > glaunch) {                       // rare: many near-ties; fetch and re-score the remainder
                 IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + count) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
                 sync();
                 std::vector<int64_t> rest(h_sel.p + 2 + glaunch, h_sel.p + 2 + count);
                 exact_df(rest);
-                cand_cache.insert(cand_cache.end(), rest.begin(), rest.end());
+                for (int64_t j : rest) cvals.push_back({j, df_exact.at(j)});
             }
         } else {
             const int nr = nranks();
@@ -452,38 +458,44 @@ struct ihtb_fit {
                     if (j < 0) return;
                     double v;
                     memcpy(&v, &b_[2 + capx + t], sizeof(double));
-                    df_exact[j] = v;
-                    if (is_cand) cand_cache.push_back(j);
+                    if (is_cand) cvals.push_back({j, v});
+                    else df_exact[j] = v;
                 };
                 for (int t = 0; t < (int)b_[0]; ++t) take(t, true);                 // rank r's candidates
                 for (int t = 0; t < (int)b_[1]; ++t) take(half + t, false);         // rank r's part of the support
             }
         }
-        std::sort(cand_cache.begin(), cand_cache.end());
-        cand_cache.erase(std::unique(cand_cache.begin(), cand_cache.end()), cand_cache.end());
-        n_cand_iter += (int64_t)cand_cache.size();
+        std::sort(cvals.begin(), cvals.end());
+        cvals.erase(std::unique(cvals.begin(), cvals.end(), [](const std::pair<int64_t, double>& x, const std::pair<int64_t, double>& y) {
+                        return x.first == y.first; }), cvals.end());
+        n_cand_iter += (int64_t)cvals.size();
         // Only the k largest exact |df| OUTSIDE the support can enter P_k(b0 + eta*df) for any eta (the support itself
         // is always a candidate); with R ranks the merged list holds R x (k + |supp|) entries, so trim it once here
         // instead of sorting it in every gradstep/backtrack.  Entries within a relative 1e-12 of the k-th value stay:
         // eta*df may round two nearly equal magnitudes to a tie, which is then broken by index.
-        if ((int64_t)cand_cache.size() > cfg.k) {
-            std::vector<std::pair<double, int64_t>> outside;
-            outside.reserve(cand_cache.size());
-            for (int64_t j : cand_cache)
-                if (!std::binary_search(idx.begin(), idx.end(), j))
-                    outside.push_back({std::fabs(df_exact.at(j)) * w_at(j), j});
+        std::vector<char> keep(cvals.size(), 1);
+        if ((int64_t)cvals.size() > cfg.k) {
+            std::vector<std::pair<double, size_t>> outside;
+            outside.reserve(cvals.size());
+            for (size_t t = 0; t < cvals.size(); ++t)
+                if (!std::binary_search(idx.begin(), idx.end(), cvals[t].first))
+                    outside.push_back({std::fabs(cvals[t].second) * w_at(cvals[t].first), t});
             if ((int64_t)outside.size() > cfg.k) {
                 std::nth_element(outside.begin(), outside.begin() + (cfg.k - 1), outside.end(),
-                                 [](const std::pair<double, int64_t>& x, const std::pair<double, int64_t>& y) {
+                                 [](const std::pair<double, size_t>& x, const std::pair<double, size_t>& y) {
                                      return x.first > y.first;
                                  });
                 const double thr = outside[(size_t)cfg.k - 1].first * (1.0 - 1e-12);
-                cand_cache.clear();
+                std::fill(keep.begin(), keep.end(), 0);
                 for (const auto& e : outside)
-                    if (e.first >= thr) cand_cache.push_back(e.second);
-                std::sort(cand_cache.begin(), cand_cache.end());
+                    if (e.first >= thr) keep[e.second] = 1;
             }
         }
+        for (size_t t = 0; t < cvals.size(); ++t)
+            if (keep[t]) {
+                cand_cache.push_back(cvals[t].first);             // cvals is sorted by column: so is cand_cache
+                df_exact[cvals[t].first] = cvals[t].second;
+            }
         if (rerun) return;
         finish_sweep_scalars(coef);
     }
@@ -1334,6 +1346,11 @@ void ihtb_internal_fit_cache_clear(int device) {
     for (ihtb_fit* f : drop) { cudaSetDevice(f->device); delete f; }
 }
 
+// (C linkage, internal: multi.cu) the NEXT ihtb_fit_create of this thread gets at least this candidate capacity: paired
+// cross-validation fits re-score thousands of columns per iteration
+static thread_local int t_min_cap = 0;
+void ihtb_internal_next_fit_min_cap(int cap) { t_min_cap = cap; }
+
 static ihtb_fit* fit_allocate(const ihtb_geno* g, int64_t q, int cap) {
     std::unique_ptr<ihtb_fit> f(new ihtb_fit());
     int64_t n = g->n, p = g->p;
@@ -1380,6 +1397,8 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
         IHTB_CHECK(cfg->k <= p_global, IHTB_EINVAL, "k cannot exceed the number of SNPs");
         IHTB_CUDA(cudaSetDevice(g->device));
         int cap = (int)std::max<int64_t>(4096, 4 * cfg->k + 1024);
+        if (t_min_cap > cap) cap = t_min_cap;
+        t_min_cap = 0;
         std::unique_ptr<ihtb_fit> f(cache_take(g->device, g->n, g->p, q, cap));
         if (!f) f.reset(fit_allocate(g, q, cap));
         int64_t n = g->n, p = g->p;

@@ -293,6 +293,7 @@ int32_t ihtb_mfit_destroy(ihtb_mfit* f) {
 // k first (more iterations), so the devices finish together.  mses / iters are fold-major, nfolds x npath; the caller
 // applies meanloss (:304-320).  IHTB_CV_PAIR=0 runs one fit at a time per device.
 extern "C" void ihtb_internal_fit_set_pairer(ihtb_fit* f, void* pairer, int slot);
+extern "C" void ihtb_internal_next_fit_min_cap(int cap);
 
 static int32_t cv_farm(const std::vector<ihtb_geno*>& parts, const std::vector<int>& devices, int64_t n, int64_t p,
                        const double* y, const double* z, int64_t q, const uint8_t* zkeep, const ihtb_cfg* cfg,
@@ -316,10 +317,11 @@ static int32_t cv_farm(const std::vector<ihtb_geno*>& parts, const std::vector<i
     c.k = *std::max_element(path, path + npath);
     const int nd = (int)devices.size();
     // Pairing pays while the PAIR sweep's looser error bound (3.1 * 2^-11 ||u||_2 sgn_j, about 0.0023 sqrt(n) null
-    // standard deviations of a gradient entry) keeps the list of columns to re-score short: on by default up to
-    // n = 20000 samples; IHTB_CV_PAIR=1 forces it (a fit whose list overflows re-sweeps alone), IHTB_CV_PAIR=0 disables it.
+    // standard deviations of a gradient entry) keeps the list of columns to re-score within a few thousand (they are
+    // re-scored by the blocked gather kernel, support.cu): on by default up to n = 131072 samples (0.8 standard
+    // deviations); IHTB_CV_PAIR=1 forces it (a fit whose list overflows re-sweeps alone), IHTB_CV_PAIR=0 disables it.
     static const int pair_env = [] { const char* e = getenv("IHTB_CV_PAIR"); return e ? atoi(e) : -1; }();
-    const bool want_pair = pair_env == 1 || (pair_env != 0 && n <= 20000);
+    const bool want_pair = pair_env == 1 || (pair_env != 0 && n <= 131072);
     // the pair sweep needs a tiled layout, FAST arithmetic and at least two fits to pair
     const int per_dev = (want_pair && c.sweep_mode == IHTB_SWEEP_FAST && c.est_r == 0 && ngrid >= 2 &&
                          parts[0]->cs_j == 128) ? 2 : 1;
@@ -341,6 +343,7 @@ static int32_t cv_farm(const std::vector<ihtb_geno*>& parts, const std::vector<i
         const int d = w / per_dev, slot = w % per_dev;
         SweepPairer* pr = per_dev == 2 ? pairers[(size_t)d].get() : nullptr;
         ihtb_fit* f = nullptr;
+        if (pr) ihtb_internal_next_fit_min_cap(32768);       // room for the longer candidate lists of the PAIR sweep
         int32_t e = ihtb_fit_create(parts[(size_t)d], y, z, q, zkeep, &c, &f);
         if (e == IHTB_OK && weight) e = ihtb_fit_set_weights(f, weight);
         if (e == IHTB_OK && pr) ihtb_internal_fit_set_pairer(f, pr, slot);

@@ -4,6 +4,8 @@
 // re-score top-k candidates exactly (same value mul!(df, Transpose(x), r) gives for those columns).
 #include "common.cuh"
 #include "comm.cuh"
+#include <algorithm>
+#include <memory>
 #include <mutex>
 #include <unordered_map>
 
@@ -122,6 +124,7 @@ void x_support(const ihtb_geno* g, const int64_t* d_idx, int64_t k, const double
 // grid = (ncols, nsplit): each CTA reduces a contiguous byte range of one column with a fixed tree, a second tiny
 // kernel adds the splits in order (deterministic, no atomics).
 constexpr int XG_MAX_SPLIT = 64;
+constexpr int64_t XB_MIN_COLS = 512;          // column lists at least this long take the blocked kernel below
 
 template <int M>
 __global__ void __launch_bounds__(256)
@@ -186,6 +189,58 @@ __global__ void k_xt_gather_fin(GenoView gv, const int64_t* __restrict__ cols, i
     out[c + (int64_t)t * ncols] = __dmul_rn(gv.sinv[j], __dadd_rn(at, __dmul_rn(gv.mu[j], corr)));
 }
 
+// Blocked form for LONG column lists (thousands of candidates: lock-step paired cross-validation fits, whose PAIR sweep
+// has a looser error bound).  k_xt_gather reads the right-hand side once per column (8 bytes per sample against 0.25
+// bytes of genotype), which is what limits it beyond a few hundred columns.  Here a CTA stages the centred vector of one
+// 4096-sample chunk in shared memory once -- transposed, us[s][w] = u[16 w + s], so that the 32 lanes of a warp read
+// consecutive doubles -- and its 8 warps then walk the whole column list: per column and chunk a lane decodes 8 packed
+// words (128 genotypes) against the staged vector.  Same outputs as k_xt_gather (dosage dot, sum over missing samples)
+// per (column, chunk); k_xt_gather_fin adds the chunks in order.
+constexpr int XB_CHUNK = 4096;                 // samples per chunk: 1024 packed bytes = 256 words per column
+__global__ void __launch_bounds__(256)
+k_xt_gather_blocked(GenoView gv, const int64_t* __restrict__ cols, int64_t n_a, const int64_t* __restrict__ cols_b,
+                    int64_t ncols, const double* __restrict__ v, const double* __restrict__ vbar,
+                    double* __restrict__ part /*[ncols][nchunks][2]*/) {
+    __shared__ double us[16][XB_CHUNK / 16];                       // 32 KB
+    const int64_t n = gv.n;
+    const int64_t chunk = blockIdx.x, nchunks = gridDim.x;
+    const int64_t i0 = chunk * XB_CHUNK;
+    const double vb = vbar[0];
+    for (int e = threadIdx.x; e < XB_CHUNK; e += blockDim.x) {
+        const int64_t i = i0 + e;
+        us[e & 15][e >> 4] = (i < n) ? __dsub_rn(v[i], vb) : 0.0;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t w0 = chunk * (XB_CHUNK / 16);                     // first packed word of this chunk in a column
+    const int64_t nwords = (gv.nbytes + 3) >> 2;
+    for (int64_t c = (int64_t)blockIdx.y * 8 + warp; c < ncols; c += (int64_t)gridDim.y * 8) {
+        const int64_t j = c < n_a ? cols[c] : cols_b[c - n_a];
+        if (j < 0) continue;                                        // unused slot / column of another shard
+        double a = 0.0, mm = 0.0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int wl = lane + 32 * t;                           // word within the chunk
+            if (w0 + wl >= nwords) continue;
+            uint32_t x = *reinterpret_cast<const uint32_t*>(gv_ptr(gv, j, 4 * (w0 + wl)));
+            if (x == 0u) continue;
+#pragma unroll
+            for (int sgl = 0; sgl < 16; ++sgl) {
+                const uint32_t code = (x >> (2 * sgl)) & 3u;
+                if (code == 0u) continue;
+                const double u = us[sgl][wl];
+                if (code == 1u) mm = __dadd_rn(mm, u);
+                else a = __dadd_rn(a, (code == 3u) ? __dadd_rn(u, u) : u);
+            }
+        }
+        a = warp_sum(a); mm = warp_sum(mm);
+        if (lane == 0) {
+            double* o = part + (c * nchunks + chunk) * 2;
+            o[0] = a; o[1] = mm;
+        }
+    }
+}
+
 // split partial sums of the gather, one buffer per stream (a fit owns its stream; fits of several host threads and
 // devices run concurrently, and the threads of a multi-device call are short-lived, so neither a global nor a
 // thread-local buffer will do).  Buffers live until the process ends.
@@ -201,10 +256,25 @@ static DBuf<double>& gather_scratch(cudaStream_t s) {
 template <int M>
 static void launch_xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t n_a, const int64_t* d_cols_b,
                              int64_t ncols, const double* d_v, const double* d_vbar, double* d_out, cudaStream_t s) {
+    DBuf<double>& sc = gather_scratch(s);
+    if (M == 1 && ncols >= XB_MIN_COLS) {
+        // long lists: the blocked kernel (samples beyond the last byte of a column are zero padding: words are read whole)
+        const int nchunks = (int)ceil_div(g->n, XB_CHUNK);
+        const size_t need_b = (size_t)ncols * nchunks * 2;
+        if (sc.n < need_b) {
+            IHTB_CUDA(cudaStreamSynchronize(s));
+            sc.alloc(need_b);
+        }
+        int groups = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(ncols, 8), (4 * g->sm_count) / nchunks + 1));
+        IHTB_LAUNCH(k_xt_gather_blocked, dim3((unsigned)nchunks, (unsigned)groups), 256, 0, s, geno_view(g), d_cols, n_a,
+                    d_cols_b, ncols, d_v, d_vbar, sc.p);
+        IHTB_LAUNCH((k_xt_gather_fin<1>), (unsigned)ceil_div(ncols, 128), 128, 0, s, geno_view(g), d_cols, n_a, d_cols_b,
+                    ncols, nchunks, d_vbar, sc.p, d_out);
+        return;
+    }
     int64_t split_bytes = ceil_div(ceil_div(g->nbytes, XG_MAX_SPLIT), 256) * 256;
     if (split_bytes < 1024) split_bytes = 1024;
     int nsplit = (int)ceil_div(g->nbytes, split_bytes);
-    DBuf<double>& sc = gather_scratch(s);
     size_t need = (size_t)ncols * nsplit * 2 * M;
     if (sc.n < need) {
         IHTB_CUDA(cudaStreamSynchronize(s));

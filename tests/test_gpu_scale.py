@@ -62,6 +62,11 @@ def test_config2_poisson_cv_slice_100k_x_500k_matches_oracle():
                            return_grid=True)
     assert np.array_equal(iters[combos], ri[combos]), (iters[combos], ri[combos])
     np.testing.assert_allclose(mses[combos], rm[combos], rtol=RTOL)
+    # the whole 100-fit grid in ONE library call (ihtb_cv_run: work queue, two fits at a time sharing PAIR sweeps whose
+    # candidates are re-scored exactly) must reproduce the fit-by-fit loop bit for bit on the slice the oracle checked
+    gm, gi = m.cv_run(y, g, z, folds, q, path, d="Poisson", l="LogLink")
+    assert np.array_equal(gi[combos], iters[combos]) and np.array_equal(gm[combos], mses[combos])
+    assert np.all(gi > 0) and np.all(gm > 0)
     g.close()
 
 
