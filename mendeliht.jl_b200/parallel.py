@@ -313,8 +313,28 @@ def bench_sharded(args, rank, world, local_rank, G):
                            "(n <= 262144), two-phase all-reduce of the batched backtracking block, all-gather of top-k "
                            "candidates; NCCL only carries the rendezvous",
             "check": {"support_size": int(nz.size), "true_positives": int(np.intersect1d(nz, true_idx).size),
-                      "iterations": iters // args.steps},
+                      "iterations": iters // args.steps, "oracle_parity": None},
         }
+        # the CPU oracle's answer on this weak-scaling problem, computed offline (scripts/make_weakscale_golden.py)
+        gpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                             f"config1_weak_n{world}.json")
+        if os.path.exists(gpath):
+            gold = json.load(open(gpath))
+            gs = np.asarray(gold["support"], dtype=np.int64)
+            same = bool(np.array_equal(nz, gs))
+            berr = float(np.max(np.abs(r.beta[gs] - np.asarray(gold["beta"])) / np.abs(gold["beta"]))) if same else None
+            bt = [t[1] for t in r.trace]
+            # a fit that runs into max_iter (an oscillating logistic fit) is compared at 1e-4, like the reference's own
+            # mueta / glmvar loses digits at the +-20 clamp (tests/test_gpu_fit.py::test_oscillating_fit)
+            rtol = 1e-4 if gold.get("hit_max_iter") else 1e-6
+            lerr = float(abs(r.logl - gold["logl"]) / abs(gold["logl"]))
+            line["check"].update({
+                "oracle_parity": bool(same and int(r.iter) == int(gold["iter"]) and bt == list(gold["trace_backtracks"])
+                                      and berr is not None and berr <= rtol and lerr <= rtol),
+                "support_identical": same, "oracle_iterations": int(gold["iter"]), "backtracks_identical": bt == list(gold["trace_backtracks"]),
+                "max_rel_err_beta": berr, "rel_err_logl": lerr, "rtol": rtol, "oracle_hit_max_iter": bool(gold.get("hit_max_iter")),
+                "golden": f"tests/golden/config1_weak_n{world}.json ({gold['oracle']}, {gold['oracle_seconds']:.0f} s on "
+                          f"{gold['oracle_threads']} threads)"})
     # ---- the other multi-GPU configs of BASELINE.json, outside the timed region (world == 8, or IHTB_BENCH_EXTRA=1) ----
     extra = world == 8 or os.environ.get("IHTB_BENCH_EXTRA") == "1"
     if extra:

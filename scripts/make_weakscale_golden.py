@@ -1,0 +1,39 @@
+"""Oracle answers of the weak-scaling bench problems (bench.py --gpus N: configs[1] shape with p = N x 500k columns):
+the CPU oracle's fit on the same synthetic data, so that the N > 1 bench lines can report oracle parity too
+(round-1 verdict: the N = 2 fit stops at max_iter = 200 -- does the oracle?).  usage: make_weakscale_golden.py N [N ...]"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+from mendeliht_jl_b200 import synth
+from oracle import cpu as ocpu
+from oracle import glm, iht
+
+n, p1, k, seed = 50_000, 500_000, 20, 2024
+for N in [int(a) for a in sys.argv[1:]]:
+    p = p1 * N
+    t0 = time.time()
+    bed = ocpu.synth_columns(seed, n, 0, p)
+    x = ocpu.PackedSnpLinAlgCPU(bed, n)
+    y, z, true_idx, _, _ = synth.simulate_response(seed + 1, n, p, k, "Bernoulli", geno_seed=seed)
+    print(f"N={N}: data ready in {time.time() - t0:.0f}s", flush=True)
+    t0 = time.time()
+    res = iht.fit_iht(y, x, z, k=k, d=glm.BERNOULLI, l=glm.LOGIT)
+    dt = time.time() - t0
+    nz = np.flatnonzero(res.beta)
+    gold = {"config": f"bench.py --gpus {N}: synthetic PLINK n={n} p={p} Bernoulli/LogitLink k={k}", "n_gpus": N,
+            "oracle": "oracle.iht.fit_iht over oracle.cpu.PackedSnpLinAlgCPU (C+OpenMP)", "oracle_seconds": dt,
+            "oracle_threads": x.threads, "iter": int(res.iter), "logl": float(res.logl),
+            "support": [int(j) for j in nz], "beta": [float(res.beta[j]) for j in nz], "c": [float(v) for v in res.c],
+            "trace_backtracks": [int(b) for b in res.trace.backtracks],
+            "trace_logl_first_last": [float(res.trace.logl[0]), float(res.trace.logl[-1])],
+            "hit_max_iter": bool(res.iter >= 200), "true_positives": int(np.intersect1d(nz, true_idx).size)}
+    out = os.path.join(ROOT, "tests", "golden", f"config1_weak_n{N}.json")
+    json.dump(gold, open(out, "w"), indent=1)
+    print(f"N={N}: {res.iter} iterations in {dt:.0f}s -> {out}", flush=True)
+    del bed, x
