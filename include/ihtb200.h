@@ -240,6 +240,9 @@ int32_t ihtb_mcv_run(const ihtb_mgeno* g, const double* y, const double* z, int6
 int32_t ihtb_comm_unique_id(const char* nccl_lib_path, uint8_t* out128);
 int32_t ihtb_comm_create(const char* nccl_lib_path, const uint8_t* id128, int32_t rank, int32_t nranks, ihtb_comm** out);
 int32_t ihtb_comm_destroy(ihtb_comm* c);
+/* counters since creation: collectives served by the library's own peer-memory kernels / NCCL calls (rendezvous only,
+ * unless peer mapping is unavailable and NCCL carries the collectives) */
+int32_t ihtb_comm_stats(const ihtb_comm* c, int64_t* peer_memory_collectives, int64_t* nccl_calls);
 /* collective: average device time (us) of `reps` back-to-back all-reduces of n doubles.  use_p2p = 0: ncclAllReduce,
  * 1: the peer-memory path sharded fits take for this n (push-all up to 262144 elements, two-phase reduce-scatter +
  * all-gather above), 2: force push-all, 3: force two-phase (IHTB_EUNSUPPORTED when peer mapping is unavailable) */

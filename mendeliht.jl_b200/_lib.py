@@ -113,6 +113,7 @@ SIGNATURES = {
     "ihtb_comm_unique_id": [C.c_char_p, _u8],
     "ihtb_comm_create": [C.c_char_p, _u8, C.c_int32, C.c_int32, _pp],
     "ihtb_comm_destroy": [_p],
+    "ihtb_comm_stats": [_p, _i64, _i64],
     "ihtb_comm_allreduce_bench": [_p, C.c_int64, C.c_int32, C.c_int32, _f64],
     "ihtb_geno_set_offset": [_p, C.c_int64],
     "ihtb_mgeno_create": [_u8, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

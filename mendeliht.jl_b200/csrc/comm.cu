@@ -59,7 +59,7 @@ void nccl_allreduce_sum_f64(ihtb_comm* c, double* d_buf, size_t count, cudaStrea
     if (!c || c->nranks == 1 || count == 0) return;
     IHTB_CHECK(c->comm, IHTB_ECUDA, "this communicator has no NCCL backend and its peer memory is not mapped");
     nccl_check(g_nccl.AllReduce(d_buf, d_buf, count, kNcclFloat64, kNcclSum, c->comm, s), "ncclAllReduce");
-    ++c->n_collectives;
+    ++c->n_nccl_calls;
 }
 
 void nccl_allgather_i64(ihtb_comm* c, const int64_t* d_send, int64_t* d_recv, size_t count_per_rank,
@@ -71,7 +71,7 @@ void nccl_allgather_i64(ihtb_comm* c, const int64_t* d_send, int64_t* d_recv, si
     }
     IHTB_CHECK(c->comm, IHTB_ECUDA, "this communicator has no NCCL backend and its peer memory is not mapped");
     nccl_check(g_nccl.AllGather(d_send, d_recv, count_per_rank, kNcclInt64, c->comm, s), "ncclAllGather");
-    ++c->n_collectives;
+    ++c->n_nccl_calls;
 }
 
 }  // namespace ihtb
@@ -104,6 +104,16 @@ int32_t ihtb_comm_create(const char* nccl_lib_path, const uint8_t* id128, int32_
             nccl_check(g_nccl.CommInitRank(&c->comm, nranks, id, rank), "ncclCommInitRank");
         }
         *out = c.release();
+    });
+}
+
+// counters since creation: collectives served by the library's peer-memory kernels, and NCCL calls (the rendezvous of
+// the peer mappings, or every collective when peer mapping is unavailable)
+int32_t ihtb_comm_stats(const ihtb_comm* c, int64_t* peer_memory_collectives, int64_t* nccl_calls) {
+    return guard([&] {
+        IHTB_CHECK(c, IHTB_EINVAL, "NULL argument");
+        if (peer_memory_collectives) *peer_memory_collectives = c->n_collectives;
+        if (nccl_calls) *nccl_calls = c->n_nccl_calls;
     });
 }
 

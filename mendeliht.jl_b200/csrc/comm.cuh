@@ -35,7 +35,8 @@ struct LocalGroup {
 struct ihtb_comm {
     void* comm = nullptr;   // ncclComm_t (NULL when nranks == 1 or for in-process groups)
     int rank = 0, nranks = 1, device = 0;
-    int64_t n_collectives = 0;
+    int64_t n_collectives = 0;      // collectives served by the peer-memory kernels (p2p.cu)
+    int64_t n_nccl_calls = 0;       // ncclAllReduce / ncclAllGather calls (rendezvous, or fallback without peer mapping)
     std::shared_ptr<ihtb::LocalGroup> local;      // in-process group (multi.cu); null for NCCL communicators
     // symmetric peer-memory region (p2p.cu); sym_local == NULL -> NCCL only
     bool p2p_tried = false;

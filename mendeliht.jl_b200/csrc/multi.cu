@@ -320,7 +320,8 @@ static int32_t cv_farm(const std::vector<ihtb_geno*>& parts, const std::vector<i
     // standard deviations of a gradient entry) keeps the list of columns to re-score within a few thousand (they are
     // re-scored by the blocked gather kernel, support.cu): on by default up to n = 131072 samples (0.8 standard
     // deviations); IHTB_CV_PAIR=1 forces it (a fit whose list overflows re-sweeps alone), IHTB_CV_PAIR=0 disables it.
-    static const int pair_env = [] { const char* e = getenv("IHTB_CV_PAIR"); return e ? atoi(e) : -1; }();
+    const char* pe = getenv("IHTB_CV_PAIR");                  // read per call: tests switch it
+    const int pair_env = pe ? atoi(pe) : -1;
     const bool want_pair = pair_env == 1 || (pair_env != 0 && n <= 131072);
     // the pair sweep needs a tiled layout, FAST arithmetic and at least two fits to pair
     const int per_dev = (want_pair && c.sweep_mode == IHTB_SWEEP_FAST && c.est_r == 0 && ngrid >= 2 &&

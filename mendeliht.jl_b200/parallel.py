@@ -74,6 +74,12 @@ class Comm:
         check(load().ihtb_comm_allreduce_bench(self._h, n, reps, int(p2p), C.byref(out)))
         return out.value
 
+    def stats(self):
+        """(collectives served by the peer-memory kernels, NCCL calls) since creation."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(load().ihtb_comm_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def close(self):
         if getattr(self, "_h", None):
             load().ihtb_comm_destroy(self._h)
@@ -118,6 +124,7 @@ def north_star_run(rank, world, comm, dist, G, steps=3):
     v = api.IHTVariable(g, z, y, k, "Normal", "IdentityLink", comm=comm, p_global=p)
     v.init_iht_indices(None); v.fit(trace_cap=0)                       # warm-up fit
     dist.barrier(); torch.cuda.synchronize()
+    coll0 = comm.stats()
     v.timer(0)
     iters = sweeps = 0
     sweep_s = 0.0
@@ -126,6 +133,7 @@ def north_star_run(rank, world, comm, dist, G, steps=3):
         res, trace = v.fit()
         iters += int(res.iter); sweeps += int(res.n_sweeps); sweep_s += res.sweep_seconds
     ms = v.timer(1)
+    coll1 = comm.stats()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_fit = float(t.item()) * 1e-3
@@ -160,6 +168,7 @@ def north_star_run(rank, world, comm, dist, G, steps=3):
         "shard_generate_s": t_gen, "support_size": int(nz.size), "true_positives": int(np.intersect1d(nz, true_idx).size),
         "collectives": "X*beta partials: two-phase peer-memory all-reduce (reduce-scatter + all-gather kernels over "
                        "NVLink, n > 262144); candidates: peer-memory all-gather; no NCCL call inside the loop",
+        "collectives_in_timed_fits": {"peer_memory_kernels": coll1[0] - coll0[0], "nccl_calls": coll1[1] - coll0[1]},
         "oracle_parity": None,
     }
     gpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
@@ -246,6 +255,7 @@ def bench_sharded(args, rank, world, local_rank, G):
     if rank == 0:
         clocks.start()
     l0 = _lib.launch_count()
+    coll0 = comm.stats()
     ms = C.c_double(0.0)
     check(lib.ihtb_fit_timer(v._h, 0, None))
     iters = sweeps = 0
@@ -255,6 +265,7 @@ def bench_sharded(args, rank, world, local_rank, G):
         res, _ = v.fit(trace_cap=0)
         iters += int(res.iter); sweeps += int(res.n_sweeps); sweep_s += res.sweep_seconds
     check(lib.ihtb_fit_timer(v._h, 1, C.byref(ms)))
+    coll1 = comm.stats()
     dist.barrier(); torch.cuda.synchronize()
     launches = _lib.launch_count() - l0
     ph = (C.c_double * 4)()
@@ -309,6 +320,7 @@ def bench_sharded(args, rank, world, local_rank, G):
                     "note": "fit_iht(y, x_shard, z; comm) on every rank with host y/z, global beta copied back; "
                             "genotype shards generated on the device (host generation of N x 6.25 GB is skipped)"},
             "gpu_launches": int(launches), "clocks": clk, "cpu_baseline": None,
+            "collectives_in_timed_region": {"peer_memory_kernels": coll1[0] - coll0[0], "nccl_calls": coll1[1] - coll0[1]},
             "collectives": "peer-memory kernels over NVLink (CUDA IPC): fused X*beta producer + push-all all-reduce "
                            "(n <= 262144), two-phase all-reduce of the batched backtracking block, all-gather of top-k "
                            "candidates; NCCL only carries the rendezvous",

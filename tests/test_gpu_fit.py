@@ -583,3 +583,23 @@ def test_device_side_backtracking_choice_matches_default():
         np.testing.assert_allclose([t[0] for t in res.trace], [t[0] for t in ref.trace], rtol=1e-12)
         assert res.n_launches != ref.n_launches            # it really took the other path
         g.close()
+
+
+def test_cv_grid_does_not_depend_on_sweep_pairing():
+    """ihtb_cv_run runs two fits at a time per device and serves their sweeps with one PAIR pass (half2 tables, looser
+    error bound, more candidates re-scored exactly).  The grid must be bit-identical with pairing off -- plain, with
+    prior weights and debiasing, and with an odd number of fits (the last one sweeps alone)."""
+    n, p, q = 3000, 6000, 3
+    y, z, *_ = synth.simulate_response(31, n, p, 6, "Poisson", n_cov=1)
+    g = m.B200SnpLinAlg.synthetic(n, p, 31)
+    folds = synth.folds_for(31, n, q)
+    w = m.maf_weights(g, max_weight=3.0)
+    for path, kw in (([1, 3, 5, 8, 12], {}), ([2, 4, 7], {"weight": w}), ([3, 6, 9], {"debias": True})):
+        got = m.cv_run(y, g, z, folds, q, path, d="Poisson", l="LogLink", **kw)
+        os.environ["IHTB_CV_PAIR"] = "0"
+        try:
+            want = m.cv_run(y, g, z, folds, q, path, d="Poisson", l="LogLink", **kw)
+        finally:
+            os.environ.pop("IHTB_CV_PAIR", None)
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
+    g.close()
