@@ -121,6 +121,7 @@ def north_star_run(rank, world, comm, dist, G, steps=3):
     g = api.B200SnpLinAlg.synthetic(n, pl, c["seed"], 0.0, j0)
     t_gen = time.perf_counter() - t0
     y, z, true_idx, _, _ = synth.simulate_response(c["seed"], n, p, k, "Normal", n_cov=c["n_cov"], geno_seed=c["seed"])
+    z = np.asfortranarray(z)          # column-major like the Julia caller's matrix: the public call then passes it as is
     v = api.IHTVariable(g, z, y, k, "Normal", "IdentityLink", comm=comm, p_global=p)
     v.init_iht_indices(None); v.fit(trace_cap=0)                       # warm-up fit
     dist.barrier(); torch.cuda.synchronize()
