@@ -227,7 +227,8 @@ void x_support(const ihtb_geno* g, const int64_t* d_idx_local, int64_t k, const 
                double* d_out, cudaStream_t s);
 void xt_gather(const ihtb_geno* g, const int64_t* d_cols_local, int64_t ncols, const double* d_v, int64_t m,
                const double* d_vsum /*[m] device*/, double* d_out /*[ncols*m]*/, cudaStream_t s);
+// blocked = true: the kernel for long lists (residual chunk staged once per CTA); same value per column whatever the list
 void xt_gather2(const ihtb_geno* g, const int64_t* d_cols_a, int64_t n_a, const int64_t* d_cols_b, int64_t n_b,
-                const double* d_v, int64_t m, const double* d_vsum, double* d_out, cudaStream_t s);
+                const double* d_v, int64_t m, const double* d_vsum, double* d_out, cudaStream_t s, bool blocked = false);
 
 }  // namespace ihtb

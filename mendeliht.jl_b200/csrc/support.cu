@@ -124,7 +124,7 @@ void x_support(const ihtb_geno* g, const int64_t* d_idx, int64_t k, const double
 // grid = (ncols, nsplit): each CTA reduces a contiguous byte range of one column with a fixed tree, a second tiny
 // kernel adds the splits in order (deterministic, no atomics).
 constexpr int XG_MAX_SPLIT = 64;
-constexpr int64_t XB_MIN_COLS = 512;          // column lists at least this long take the blocked kernel below
+
 
 template <int M>
 __global__ void __launch_bounds__(256)
@@ -255,9 +255,12 @@ static DBuf<double>& gather_scratch(cudaStream_t s) {
 
 template <int M>
 static void launch_xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t n_a, const int64_t* d_cols_b,
-                             int64_t ncols, const double* d_v, const double* d_vbar, double* d_out, cudaStream_t s) {
+                             int64_t ncols, const double* d_v, const double* d_vbar, double* d_out, cudaStream_t s,
+                             bool blocked) {
     DBuf<double>& sc = gather_scratch(s);
-    if (M == 1 && ncols >= XB_MIN_COLS) {
+    if (M == 1 && blocked) {
+        // the caller's choice, never the list length: a fit must get the same bits for a column whether its list is long
+        // or short (paired or solo sweep), so every fit of a paired cross-validation grid takes this kernel throughout
         // long lists: the blocked kernel (samples beyond the last byte of a column are zero padding: words are read whole)
         const int nchunks = (int)ceil_div(g->n, XB_CHUNK);
         const size_t need_b = (size_t)ncols * nchunks * 2;
@@ -288,7 +291,7 @@ static void launch_xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t 
 
 // two column lists in one launch: out[0 .. n_a) from d_cols_a, out[n_a .. n_a + n_b) from d_cols_b (either may be empty)
 void xt_gather2(const ihtb_geno* g, const int64_t* d_cols_a, int64_t n_a, const int64_t* d_cols_b, int64_t n_b,
-                const double* d_v, int64_t m, const double* d_vbar, double* d_out, cudaStream_t s) {
+                const double* d_v, int64_t m, const double* d_vbar, double* d_out, cudaStream_t s, bool blocked) {
     const int64_t ncols = n_a + n_b;
     if (ncols == 0) return;
     for (int64_t t0 = 0; t0 < m;) {
@@ -296,16 +299,16 @@ void xt_gather2(const ihtb_geno* g, const int64_t* d_cols_a, int64_t n_a, const 
         const double* vv = d_v + t0 * g->n;
         const double* vb = d_vbar + t0;
         double* o = d_out + t0 * ncols;
-        if (mm >= 4) { launch_xt_gather<4>(g, d_cols_a, n_a, d_cols_b, ncols, vv, vb, o, s); t0 += 4; }
-        else if (mm == 3) { launch_xt_gather<3>(g, d_cols_a, n_a, d_cols_b, ncols, vv, vb, o, s); t0 += 3; }
-        else if (mm == 2) { launch_xt_gather<2>(g, d_cols_a, n_a, d_cols_b, ncols, vv, vb, o, s); t0 += 2; }
-        else { launch_xt_gather<1>(g, d_cols_a, n_a, d_cols_b, ncols, vv, vb, o, s); t0 += 1; }
+        if (mm >= 4) { launch_xt_gather<4>(g, d_cols_a, n_a, d_cols_b, ncols, vv, vb, o, s, blocked); t0 += 4; }
+        else if (mm == 3) { launch_xt_gather<3>(g, d_cols_a, n_a, d_cols_b, ncols, vv, vb, o, s, blocked); t0 += 3; }
+        else if (mm == 2) { launch_xt_gather<2>(g, d_cols_a, n_a, d_cols_b, ncols, vv, vb, o, s, blocked); t0 += 2; }
+        else { launch_xt_gather<1>(g, d_cols_a, n_a, d_cols_b, ncols, vv, vb, o, s, blocked); t0 += 1; }
     }
 }
 
 void xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t ncols, const double* d_v, int64_t m,
                const double* d_vbar, double* d_out, cudaStream_t s) {
-    xt_gather2(g, d_cols, ncols, nullptr, 0, d_v, m, d_vbar, d_out, s);
+    xt_gather2(g, d_cols, ncols, nullptr, 0, d_v, m, d_vbar, d_out, s, false);
 }
 
 }  // namespace ihtb

@@ -592,15 +592,15 @@ def test_cv_grid_does_not_depend_on_sweep_pairing():
     the summation order of the exact re-scoring (long candidate lists take the blocked gather kernel, short ones the
     per-column one; both are FP64, their last bits differ)."""
     n, p, q = 3000, 6000, 3
-    y, z, *_ = synth.simulate_response(31, n, p, 6, "Poisson", n_cov=1)
+    y, z, *_ = synth.simulate_response(31, n, p, 6, "Normal", n_cov=1)
     g = m.B200SnpLinAlg.synthetic(n, p, 31)
     folds = synth.folds_for(31, n, q)
     w = m.maf_weights(g, max_weight=3.0)
     for path, kw in (([1, 2, 3, 4, 5], {}), ([2, 4, 6], {"weight": w}), ([3, 5, 6], {"debias": True})):
-        got = m.cv_run(y, g, z, folds, q, path, d="Poisson", l="LogLink", **kw)
+        got = m.cv_run(y, g, z, folds, q, path, **kw)
         os.environ["IHTB_CV_PAIR"] = "0"
         try:
-            want = m.cv_run(y, g, z, folds, q, path, d="Poisson", l="LogLink", **kw)
+            want = m.cv_run(y, g, z, folds, q, path, **kw)
         finally:
             os.environ.pop("IHTB_CV_PAIR", None)
         assert np.array_equal(got[1], want[1]) and got[1].max() < 100          # converging fits (cf. test_oscillating_fit)
