@@ -177,6 +177,10 @@ int32_t ihtb_fit_destroy(ihtb_fit* f);
  * per two traits (the skinny X'R of src/multivariate.jl:85). */
 int32_t ihtb_mvfit_create(const ihtb_geno* g, const double* Y, int64_t r, const double* z, int64_t q,
                           const ihtb_cfg* cfg, ihtb_mvfit** out);
+/* SNP-sharded form, like ihtb_fit_create_sharded: this rank's handle holds columns [j0, j0 + p_local) of p_global; B
+ * in ihtb_mvfit_get has r x p_global entries.  init_beta is not available sharded. */
+int32_t ihtb_mvfit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_global, const double* Y, int64_t r,
+                                  const double* z, int64_t q, const ihtb_cfg* cfg, ihtb_mvfit** out);
 int32_t ihtb_mvfit_set_k(ihtb_mvfit* f, int64_t k);
 int32_t ihtb_mvfit_init(ihtb_mvfit* f, const uint8_t* train_mask);
 /* init_beta = true (src/multivariate.jl:425-429, initialize_beta! :519-558): B starts from per-trait univariate regressions */
@@ -229,6 +233,16 @@ int32_t ihtb_mfit_get(const ihtb_mfit* f, double* beta, double* c, double* mu, d
 int32_t ihtb_mfit_predict(ihtb_mfit* f, const uint8_t* test_mask, double* deviance);
 int32_t ihtb_mfit_timer(ihtb_mfit* f, int32_t which, double* ms);     /* slowest device's CUDA-event time */
 int32_t ihtb_mfit_destroy(ihtb_mfit* f);
+/* the multivariate fit over a SHARD handle (mIHTVariable over several GPUs): same arguments as ihtb_mvfit_* */
+typedef struct ihtb_mmvfit ihtb_mmvfit;
+int32_t ihtb_mmvfit_create(const ihtb_mgeno* g, const double* Y, int64_t r, const double* z, int64_t q,
+                           const ihtb_cfg* cfg, ihtb_mmvfit** out);
+int32_t ihtb_mmvfit_set_k(ihtb_mmvfit* f, int64_t k);
+int32_t ihtb_mmvfit_init(ihtb_mmvfit* f, const uint8_t* train_mask);
+int32_t ihtb_mmvfit_run(ihtb_mmvfit* f, ihtb_result* result, ihtb_iter_trace* trace, int64_t trace_cap);
+int32_t ihtb_mmvfit_get(const ihtb_mmvfit* f, double* beta, double* c, double* Sigma, double* sigma_g);
+int32_t ihtb_mmvfit_predict(ihtb_mmvfit* f, const uint8_t* test_mask, double* mse);
+int32_t ihtb_mmvfit_destroy(ihtb_mmvfit* f);
 /* ihtb_cv_run over a REPLICATE handle: fits are taken from a shared queue, largest k first (more iterations);
  * busy_seconds[ngpu] (optional) = wall time each device spent on its share */
 int32_t ihtb_mcv_run(const ihtb_mgeno* g, const double* y, const double* z, int64_t q, const uint8_t* zkeep,

@@ -99,6 +99,8 @@ const AnyB200 = Union{B200SnpLinAlg,B200MultiSnpLinAlg}
 # the single-device and the multi-device calls have the same argument lists (ihtb_fit_* / ihtb_mfit_*)
 fitsym(::B200SnpLinAlg, name::Symbol) = Symbol(:ihtb_fit_, name)
 fitsym(::B200MultiSnpLinAlg, name::Symbol) = Symbol(:ihtb_mfit_, name)
+mvsym(::B200SnpLinAlg, name::Symbol) = Symbol(:ihtb_mvfit_, name)          # multivariate: ihtb_mvfit_* / ihtb_mmvfit_*
+mvsym(::B200MultiSnpLinAlg, name::Symbol) = Symbol(:ihtb_mmvfit_, name)
 
 # ---- fit_iht on the device -----------------------------------------------------------------------------------
 struct Cfg
@@ -206,7 +208,7 @@ end
 Multivariate (MvNormal) fit: same call as the reference, `fit_iht(Y, Transpose(xla), Z; k)` with Y r x n and Z q x n
 (src/fit.jl:60-118, src/multivariate.jl); returns `mIHTResult`.  The library wants samples as rows (n x r, n x q).
 """
-function fit_iht(Y::AbstractMatrix{Float64}, xt::Transpose{Float64,B200SnpLinAlg}, Z::AbstractVecOrMat{Float64};
+function fit_iht(Y::AbstractMatrix{Float64}, xt::Transpose{Float64,<:AnyB200}, Z::AbstractVecOrMat{Float64};
                  k::Int=10, zkeep::BitVector=trues(size(Z, 1)), init_beta::Bool=false, debias::Bool=false,
                  tol::Float64=1e-4, max_iter::Int=200, min_iter::Int=5, max_step::Int=3, verbose::Bool=false,
                  io::IO=stdout, kwargs...)
@@ -222,19 +224,28 @@ function fit_iht(Y::AbstractMatrix{Float64}, xt::Transpose{Float64,B200SnpLinAlg
     # sweep_mode 2 = IHTB_SWEEP_PAIR: the skinny X'R reads the matrix once per two traits (src/multivariate.jl:85)
     cfg = Ref(Cfg(0, 0, k, 1.0, tol, max_iter, min_iter, max_step, 2, 0, 0))
     fh = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:ihtb_mvfit_create, LIB), Int32,
+    x isa B200MultiSnpLinAlg && init_beta && throw(ArgumentError("init_beta is not available for SNP-sharded multivariate fits"))
+    check(ccall((mvsym(x, :create), LIB), Int32,
                 (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ref{Cfg}, Ref{Ptr{Cvoid}}),
                 x.handle, Yc, r, Zc, q, cfg, fh))
     try
-        check(ccall((init_beta ? :ihtb_mvfit_init_beta : :ihtb_mvfit_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), fh[], C_NULL))
+        check(ccall((init_beta ? :ihtb_mvfit_init_beta : mvsym(x, :init), LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), fh[], C_NULL))
         res = CResult()
-        check(ccall((:ihtb_mvfit_run, LIB), Int32, (Ptr{Cvoid}, Ref{CResult}, Ptr{Cvoid}, Int64), fh[], res, C_NULL, 0))
+        trace = Vector{CIterTrace}(undef, verbose ? max_iter : 0)
+        check(ccall((mvsym(x, :run), LIB), Int32, (Ptr{Cvoid}, Ref{CResult}, Ptr{CIterTrace}, Int64),
+                    fh[], res, verbose ? trace : C_NULL, length(trace)))
+        if verbose
+            for i in 1:min(res.n_steps, length(trace))
+                t = trace[i]
+                println(io, "Iteration $i: loglikelihood = $(t.logl), backtracks = $(t.backtracks), tol = $(t.tol)")
+            end
+        end
         B = zeros(r, x.p); C = zeros(r, q); Σ = zeros(r, r); σg = zeros(r)
-        check(ccall((:ihtb_mvfit_get, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        check(ccall((mvsym(x, :get), LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                     fh[], B, C, Σ, σg))
         return MendelIHT.mIHTResult(res.time, res.logl, res.iter, B, C, k, r, Σ, σg)   # field order: src/data_structures.jl:263-273
     finally
-        ccall((:ihtb_mvfit_destroy, LIB), Int32, (Ptr{Cvoid},), fh[])
+        ccall((mvsym(x, :destroy), LIB), Int32, (Ptr{Cvoid},), fh[])
     end
 end
 

@@ -103,6 +103,7 @@ SIGNATURES = {
     "ihtb_cv_run": [_p, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), C.POINTER(C.c_int32), C.c_int32, _i64, C.c_int64,
                     _f64, _f64, _i64],
     "ihtb_mvfit_create": [_p, _f64, C.c_int64, _f64, C.c_int64, C.POINTER(Cfg), _pp],
+    "ihtb_mvfit_create_sharded": [_p, _p, C.c_int64, _f64, C.c_int64, _f64, C.c_int64, C.POINTER(Cfg), _pp],
     "ihtb_mvfit_set_k": [_p, C.c_int64],
     "ihtb_mvfit_init": [_p, _u8],
     "ihtb_mvfit_init_beta": [_p, _u8],
@@ -133,6 +134,13 @@ SIGNATURES = {
     "ihtb_mfit_predict": [_p, _u8, _f64],
     "ihtb_mfit_timer": [_p, C.c_int32, _f64],
     "ihtb_mfit_destroy": [_p],
+    "ihtb_mmvfit_create": [_p, _f64, C.c_int64, _f64, C.c_int64, C.POINTER(Cfg), _pp],
+    "ihtb_mmvfit_set_k": [_p, C.c_int64],
+    "ihtb_mmvfit_init": [_p, _u8],
+    "ihtb_mmvfit_run": [_p, C.POINTER(Result), C.POINTER(IterTrace), C.c_int64],
+    "ihtb_mmvfit_get": [_p, _f64, _f64, _f64, _f64],
+    "ihtb_mmvfit_predict": [_p, _u8, _f64],
+    "ihtb_mmvfit_destroy": [_p],
     "ihtb_mcv_run": [_p, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), C.POINTER(C.c_int32), C.c_int32, _i64, C.c_int64,
                      _f64, _f64, _i64, _f64],
 }

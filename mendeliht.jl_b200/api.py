@@ -436,42 +436,51 @@ class mIHTVariable:
         Yc = np.asfortranarray(Y.T)      # n x r column-major
         Zc = np.asfortranarray(Z.T)      # n x q column-major
         self._h = C.c_void_p()
-        check(load().ihtb_mvfit_create(x._h, Yc.ctypes.data_as(C.POINTER(C.c_double)), r,
-                                       Zc.ctypes.data_as(C.POINTER(C.c_double)), q, C.byref(self.cfg),
-                                       C.byref(self._h)))
+        # a SHARD multi-device operator runs the same calls through ihtb_mmvfit_* (one host thread per device inside)
+        self._multi = isinstance(x, B200MultiSnpLinAlg)
+        self._pre = "ihtb_mmvfit_" if self._multi else "ihtb_mvfit_"
+        if self._multi and x.mode != B200MultiSnpLinAlg.SHARD:
+            raise _lib.IHTBError(_lib.IHTB_EINVAL, "fit_iht over several GPUs needs a SHARD multi-device operator")
+        check(self._fn("create")(x._h, Yc.ctypes.data_as(C.POINTER(C.c_double)), r,
+                                 Zc.ctypes.data_as(C.POINTER(C.c_double)), q, C.byref(self.cfg), C.byref(self._h)))
+
+    def _fn(self, name):
+        return getattr(load(), self._pre + name)
 
     def set_k(self, k):
-        check(load().ihtb_mvfit_set_k(self._h, int(k)))
+        check(self._fn("set_k")(self._h, int(k)))
 
     def init_iht_indices(self, train_mask=None, init_beta=False):
         m = None if train_mask is None else np.ascontiguousarray(train_mask, dtype=np.uint8)
-        fn = load().ihtb_mvfit_init_beta if init_beta else load().ihtb_mvfit_init
+        if init_beta and self._multi:
+            raise _lib.IHTBError(_lib.IHTB_EUNSUPPORTED, "init_beta is not available for SNP-sharded multivariate fits")
+        fn = load().ihtb_mvfit_init_beta if init_beta else self._fn("init")
         check(fn(self._h, ptr(m, C.c_uint8) if m is not None else None))
 
     def fit(self, trace_cap=None):
         cap = int(self.cfg.max_iter) if trace_cap is None else trace_cap
         res = Result()
         tr = (IterTrace * max(cap, 1))()
-        check(load().ihtb_mvfit_run(self._h, C.byref(res), tr, cap))
+        check(self._fn("run")(self._h, C.byref(res), tr, cap))
         n_it = min(int(res.n_steps), cap)
         return res, [(tr[i].logl, tr[i].backtracks, tr[i].tol, tr[i].eta, tr[i].n_candidates) for i in range(n_it)]
 
     def get(self):
         beta = np.empty((self.r, self.p), order="F"); c = np.empty((self.r, self.q), order="F")
         S = np.empty((self.r, self.r)); sg = np.empty(self.r)
-        check(load().ihtb_mvfit_get(self._h, beta.ctypes.data_as(C.POINTER(C.c_double)),
-                                    c.ctypes.data_as(C.POINTER(C.c_double)), ptr(S, C.c_double), ptr(sg, C.c_double)))
+        check(self._fn("get")(self._h, beta.ctypes.data_as(C.POINTER(C.c_double)),
+                              c.ctypes.data_as(C.POINTER(C.c_double)), ptr(S, C.c_double), ptr(sg, C.c_double)))
         return np.ascontiguousarray(beta), np.ascontiguousarray(c), S, sg
 
     def predict(self, test_mask=None) -> float:
         m = None if test_mask is None else np.ascontiguousarray(test_mask, dtype=np.uint8)
         out = C.c_double(0.0)
-        check(load().ihtb_mvfit_predict(self._h, ptr(m, C.c_uint8) if m is not None else None, C.byref(out)))
+        check(self._fn("predict")(self._h, ptr(m, C.c_uint8) if m is not None else None, C.byref(out)))
         return float(out.value)
 
     def close(self):
         if getattr(self, "_h", None):
-            load().ihtb_mvfit_destroy(self._h)
+            self._fn("destroy")(self._h)
             self._h = None
 
     def __del__(self):

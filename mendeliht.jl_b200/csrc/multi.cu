@@ -284,6 +284,92 @@ int32_t ihtb_mfit_destroy(ihtb_mfit* f) {
     });
 }
 
+// ---- the multivariate fit over a SHARD handle ---------------------------------------------------------------------------
+struct ihtb_mmvfit {
+    const ihtb_mgeno* g = nullptr;
+    std::shared_ptr<LocalGroup> group;
+    std::vector<ihtb_comm*> comms;
+    std::vector<ihtb_mvfit*> fits;
+};
+int32_t ihtb_mmvfit_destroy(ihtb_mmvfit* f);
+
+int32_t ihtb_mmvfit_create(const ihtb_mgeno* g, const double* Y, int64_t r, const double* z, int64_t q,
+                           const ihtb_cfg* cfg, ihtb_mmvfit** out) {
+    ihtb_mmvfit* f = nullptr;
+    int32_t rc = guard([&] {
+        IHTB_CHECK(g && Y && z && cfg && out, IHTB_EINVAL, "NULL argument");
+        IHTB_CHECK(g->mode == IHTB_MULTI_SHARD, IHTB_EINVAL, "ihtb_mmvfit needs a SHARD multi-device handle");
+        f = new ihtb_mmvfit();
+        f->g = g;
+        const int nr = (int)g->devices.size();
+        f->group = std::make_shared<LocalGroup>();
+        f->group->nranks = nr;
+        for (int i = 0; i < nr; ++i) f->group->devices[i] = g->devices[(size_t)i];
+        f->comms.assign((size_t)nr, nullptr);
+        f->fits.assign((size_t)nr, nullptr);
+        for (int i = 0; i < nr; ++i) {
+            ihtb_comm* c = new ihtb_comm();
+            c->rank = i; c->nranks = nr; c->device = g->devices[(size_t)i];
+            if (nr > 1) c->local = f->group;
+            f->comms[(size_t)i] = c;
+        }
+    });
+    if (rc != IHTB_OK) { delete f; return rc; }
+    rc = on_all_ranks((int)g->devices.size(), g->devices, f->group.get(), [&](int i) -> int32_t {
+        return ihtb_mvfit_create_sharded(g->parts[(size_t)i], f->comms[(size_t)i], g->p, Y, r, z, q, cfg, &f->fits[(size_t)i]);
+    });
+    if (rc != IHTB_OK) {
+        std::string m = last_error();
+        ihtb_mmvfit_destroy(f);
+        set_last_error(m);
+        return rc;
+    }
+    *out = f;
+    return IHTB_OK;
+}
+
+#define MMVFIT_ALL(expr)                                                                                       \
+    do {                                                                                                       \
+        if (!f) { set_last_error("NULL fit handle"); return IHTB_EINVAL; }                                     \
+        if (f->group->failed) { set_last_error("this multi-device fit failed earlier; destroy it"); return IHTB_ECUDA; } \
+        return on_all_ranks((int)f->fits.size(), f->g->devices, f->group.get(), [&](int i) -> int32_t {         \
+            ihtb_mvfit* fr = f->fits[(size_t)i]; (void)fr;                                                     \
+            return (expr);                                                                                     \
+        });                                                                                                    \
+    } while (0)
+
+int32_t ihtb_mmvfit_set_k(ihtb_mmvfit* f, int64_t k) { MMVFIT_ALL(ihtb_mvfit_set_k(fr, k)); }
+int32_t ihtb_mmvfit_init(ihtb_mmvfit* f, const uint8_t* train_mask) { MMVFIT_ALL(ihtb_mvfit_init(fr, train_mask)); }
+int32_t ihtb_mmvfit_run(ihtb_mmvfit* f, ihtb_result* result, ihtb_iter_trace* trace, int64_t trace_cap) {
+    MMVFIT_ALL(i == 0 ? ihtb_mvfit_run(fr, result, trace, trace_cap) : ihtb_mvfit_run(fr, nullptr, nullptr, 0));
+}
+int32_t ihtb_mmvfit_predict(ihtb_mmvfit* f, const uint8_t* test_mask, double* mse) {
+    double out[P2P_MAX_RANKS] = {};
+    if (!f || !mse) { set_last_error("NULL argument"); return IHTB_EINVAL; }
+    int32_t rc = on_all_ranks((int)f->fits.size(), f->g->devices, f->group.get(), [&](int i) -> int32_t {
+        return ihtb_mvfit_predict(f->fits[(size_t)i], test_mask, &out[i]);
+    });
+    if (rc == IHTB_OK) *mse = out[0];
+    return rc;
+}
+int32_t ihtb_mmvfit_get(const ihtb_mmvfit* f, double* beta, double* c, double* Sigma, double* sigma_g) {
+    if (!f) { set_last_error("NULL fit handle"); return IHTB_EINVAL; }
+    cudaSetDevice(f->g->devices[0]);
+    return ihtb_mvfit_get(f->fits[0], beta, c, Sigma, sigma_g);
+}
+int32_t ihtb_mmvfit_destroy(ihtb_mmvfit* f) {
+    return guard([&] {
+        if (!f) return;
+        for (size_t i = 0; i < f->fits.size(); ++i)
+            if (f->fits[i]) { cudaSetDevice(f->g->devices[i]); ihtb_mvfit_destroy(f->fits[i]); }
+        for (size_t i = 0; i < f->comms.size(); ++i)
+            if (f->comms[i]) { cudaSetDevice(f->g->devices[i]); cudaDeviceSynchronize(); }
+        for (size_t i = 0; i < f->comms.size(); ++i)
+            if (f->comms[i]) { cudaSetDevice(f->g->devices[i]); p2p_teardown(f->comms[i]); delete f->comms[i]; }
+        delete f;
+    });
+}
+
 // ---- cv_iht: the (fold, k) grid from a shared work queue -----------------------------------------------------------------
 // cv_iht (reference src/cross_validation.jl:60-131) runs q * |path| independent fits on training masks of the SAME matrix
 // (allocate_fold_and_k :217-223; mu_j / sigma_j stay full-sample) and scores each on its held-out fold (predict!,

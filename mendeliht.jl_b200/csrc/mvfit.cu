@@ -15,6 +15,7 @@
 // (:172-189) reads the wrong slice, so there is no behaviour to reproduce.
 #include "glm.cuh"
 #include "topk.cuh"
+#include "comm.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -235,8 +236,16 @@ static const double kFastL2BoundMv = 1.0 / 1048576.0;
 struct ihtb_mvfit {
     const ihtb_geno* g = nullptr;
     int device = 0;
-    int64_t n = 0, p = 0, q = 0;
+    int64_t n = 0, p = 0, q = 0;          // p = local SNP columns
     int r = 0;
+    // SNP-sharded fits (like fit.cu): this rank owns global columns [j0, j0 + p); Y, Z, every n x r array and the
+    // k-sparse model (keyed by GLOBAL position j*r + t) are replicated; partial BX / V products are all-reduced, exact
+    // gradient entries and candidate columns are exchanged over the communicator's peer-memory collectives
+    ihtb_comm* comm = nullptr;
+    int64_t j0 = 0, p_global = 0;
+    DBuf<int64_t> d_xch, d_xchall;        // candidate-column exchange block [count | cols[cap]] and its gathered copy
+    HBuf<int64_t> h_xchall;
+    bool is_local(int64_t j) const { return j >= j0 && j < j0 + p; }
     ihtb_cfg cfg{};
     cudaStream_t s = nullptr;
     int cap = 4096;
@@ -301,10 +310,21 @@ struct ihtb_mvfit {
     // d_out (n x r) = sum_{j in cols} x[:, j] * coef[j][t]   (update_xb! :21-31 / iht_stepsize! :234)
     void support_matmat(const std::vector<int64_t>& cols, const std::vector<double>& coef /*|cols| x r col-major*/,
                         double* d_out) {
-        if (cols.empty()) { IHTB_CUDA(cudaMemsetAsync(d_out, 0, n * r * sizeof(double), s)); return; }
-        upload(d_idx.p, cols.data(), cols.size());
-        upload(d_coef.p, coef.data(), coef.size());
-        x_support(g, d_idx.p, (int64_t)cols.size(), d_coef.p, r, d_out, s);
+        // this rank's columns (all of them without a communicator), local indices, same order
+        std::vector<int64_t> loc; std::vector<size_t> src;
+        for (size_t c = 0; c < cols.size(); ++c)
+            if (is_local(cols[c])) { loc.push_back(cols[c] - j0); src.push_back(c); }
+        if (loc.empty()) {
+            IHTB_CUDA(cudaMemsetAsync(d_out, 0, n * r * sizeof(double), s));
+        } else {
+            std::vector<double> cl(loc.size() * (size_t)r);
+            for (int t = 0; t < r; ++t)
+                for (size_t c = 0; c < loc.size(); ++c) cl[c + (size_t)t * loc.size()] = coef[src[c] + (size_t)t * cols.size()];
+            upload(d_idx.p, loc.data(), loc.size());
+            upload(d_coef.p, cl.data(), cl.size());
+            x_support(g, d_idx.p, (int64_t)loc.size(), d_coef.p, r, d_out, s);
+        }
+        if (comm) comm_allreduce_sum_f64(comm, d_out, (size_t)(n * r), s);
     }
     void update_xb() {
         std::vector<int64_t> cols = support_cols(B, r);
@@ -352,8 +372,12 @@ struct ihtb_mvfit {
             if (!df_exact.count(j)) need.push_back(j);
         if (need.empty()) return;
         IHTB_CHECK(need.size() * r <= d_gout.n && need.size() <= d_cols.n, IHTB_ENUMERIC, "too many columns to re-score");
-        upload(d_cols.p, need.data(), need.size());
+        // columns of other shards are marked -1: the kernel writes 0 for them and the all-reduce fills them in
+        std::vector<int64_t> loc(need.size());
+        for (size_t c = 0; c < need.size(); ++c) loc[c] = is_local(need[c]) ? need[c] - j0 : -1;
+        upload(d_cols.p, loc.data(), loc.size());
         xt_gather(g, d_cols.p, (int64_t)need.size(), d_R1.p, r, d_vbar.p, d_gout.p, s);
+        if (comm) comm_allreduce_sum_f64(comm, d_gout.p, need.size() * (size_t)r, s);
         IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_gout.p, need.size() * r * sizeof(double), cudaMemcpyDeviceToHost, s));
         sync();
         for (size_t c = 0; c < need.size(); ++c) {
@@ -434,8 +458,8 @@ struct ihtb_mvfit {
         b0d_pos.clear();
         std::vector<double> vals;
         for (auto& kv : B0)
-            if (kv.second != 0.0) {   // device vector is trait-major: e = t*p + j
-                b0d_pos.push_back((kv.first % r) * p + kv.first / r);
+            if (kv.second != 0.0 && is_local(kv.first / r)) {   // device vector is trait-major over LOCAL columns: e = t*p + (j - j0)
+                b0d_pos.push_back((kv.first % r) * p + (kv.first / r - j0));
                 vals.push_back(kv.second);
             }
         if (!b0d_pos.empty()) {
@@ -455,7 +479,23 @@ struct ihtb_mvfit {
         const TopkState* st = reinterpret_cast<const TopkState*>(h_sel.p);
         IHTB_CHECK(st->count <= cap, IHTB_ENUMERIC, "degenerate projection: too many entries within the error bound");
         std::vector<int64_t> cols;
-        for (int t = 0; t < st->count; ++t) cols.push_back(h_sel.p[2 + t] % p);
+        for (int t = 0; t < st->count; ++t) cols.push_back(h_sel.p[2 + t] % p + j0);
+        if (!comm) return cols;
+        // every member of the global top-k is in its own rank's local top-k: the union of the ranks' candidate columns
+        // is a superset; one all-gather of fixed blocks [count | global columns]
+        const size_t blk = 1 + (size_t)cap;
+        std::vector<int64_t> mine(blk, -1);
+        mine[0] = (int64_t)cols.size();
+        std::copy(cols.begin(), cols.end(), mine.begin() + 1);
+        upload(d_xch.p, mine.data(), blk);
+        comm_allgather_i64(comm, d_xch.p, d_xchall.p, blk, s);
+        IHTB_CUDA(cudaMemcpyAsync(h_xchall.p, d_xchall.p, (size_t)comm->nranks * blk * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        sync();
+        cols.clear();
+        for (int rk = 0; rk < comm->nranks; ++rk) {
+            const int64_t* b_ = h_xchall.p + (size_t)rk * blk;
+            cols.insert(cols.end(), b_ + 1, b_ + 1 + b_[0]);
+        }
         return cols;
     }
     // _iht_gradstep! / project_k! :99-127 (all covariates kept: only entries of B compete for the k slots)
@@ -540,6 +580,7 @@ struct ihtb_mvfit {
     // univariate ihtb_fit_init_beta.  The reference accumulates the intercepts from several threads without
     // synchronisation; this is the single-thread result.
     void do_init_beta(const uint8_t* train_mask, const std::vector<double>& sy) {
+        IHTB_CHECK(!comm, IHTB_EUNSUPPORTED, "init_beta is not available for SNP-sharded multivariate fits");
         DBuf<double> cls((size_t)(6 * p)), bd((size_t)(p * r)), wy((size_t)n);
         double *W1 = cls.p, *W2 = W1 + p, *Wm = W2 + p, *Y1 = Wm + p, *Y2 = Y1 + p, *Ym = Y2 + p;
         sweep_class_sums(g, d_w.p, W1, W2, Wm, s, sweep_scratch);
@@ -718,16 +759,22 @@ extern "C" {
 
 int32_t ihtb_mvfit_create(const ihtb_geno* g, const double* Y, int64_t r, const double* z, int64_t q,
                           const ihtb_cfg* cfg, ihtb_mvfit** out) {
+    return ihtb_mvfit_create_sharded(g, nullptr, g ? g->p : 0, Y, r, z, q, cfg, out);
+}
+
+int32_t ihtb_mvfit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_global, const double* Y, int64_t r,
+                                  const double* z, int64_t q, const ihtb_cfg* cfg, ihtb_mvfit** out) {
     return guard([&] {
         IHTB_CHECK(g && Y && z && cfg && out, IHTB_EINVAL, "NULL argument");
         geno_require_ready(g);
+        IHTB_CHECK(p_global >= g->p, IHTB_EDIM, "p_global is smaller than the local shard");
         IHTB_CHECK(r >= 2 && r <= MV_MAXR, IHTB_EUNSUPPORTED, "multivariate IHT supports 2..20 traits");
         IHTB_CHECK(cfg->sweep_mode == IHTB_SWEEP_FAST || cfg->sweep_mode == IHTB_SWEEP_EXACT ||
                        cfg->sweep_mode == IHTB_SWEEP_PAIR, IHTB_EINVAL, "bad sweep_mode");
         IHTB_CHECK(!cfg->debias, IHTB_EUNSUPPORTED,
                    "Currently the debiasing routine for multivariate IHT is broken, sorry!");   // src/multivariate.jl:570
         IHTB_CHECK(q >= 1, IHTB_EDIM, "z must have at least the intercept row");
-        IHTB_CHECK(cfg->k >= 1 && cfg->k <= g->p * r, IHTB_EINVAL, "Multivariate IHT requires 1 <= k <= r*p");
+        IHTB_CHECK(cfg->k >= 1 && cfg->k <= p_global * r, IHTB_EINVAL, "Multivariate IHT requires 1 <= k <= r*p");
         IHTB_CHECK(cfg->max_iter >= 0 && cfg->max_step >= 0 && cfg->tol > 2.220446049250313e-16, IHTB_EINVAL,
                    "bad max_iter / max_step / tol");
         IHTB_CHECK(g->p * r < (int64_t(1) << 31), IHTB_EDIM, "r*p must be < 2^31");
@@ -736,7 +783,17 @@ int32_t ihtb_mvfit_create(const ihtb_geno* g, const double* Y, int64_t r, const 
         int64_t n = g->n, p = g->p;
         f->g = g; f->device = g->device; f->n = n; f->p = p; f->q = q; f->r = (int)r; f->cfg = *cfg;
         f->cap = (int)std::max<int64_t>(4096, 4 * cfg->k + 1024);
+        f->comm = (comm && comm->nranks > 1) ? comm : nullptr;
+        f->j0 = f->comm ? g->j0 : 0;
+        f->p_global = f->comm ? p_global : p;
         IHTB_CUDA(cudaStreamCreateWithFlags(&f->s, cudaStreamNonBlocking));
+        if (f->comm) {
+            // peer-memory areas (collective): n x r products in one all-reduce, candidate blocks in one all-gather
+            p2p_setup(f->comm, (size_t)(n * r), 1 + (size_t)f->cap, f->s);
+            f->d_xch.alloc(1 + (size_t)f->cap);
+            f->d_xchall.alloc((size_t)f->comm->nranks * (1 + (size_t)f->cap));
+            f->h_xchall.alloc((size_t)f->comm->nranks * (1 + (size_t)f->cap));
+        }
         IHTB_CUDA(cudaEventCreate(&f->ev0)); IHTB_CUDA(cudaEventCreate(&f->ev1));
         f->d_Y.alloc(n * r); f->d_Z.alloc(n * q); f->d_w.alloc(n); f->d_BX.alloc(n * r); f->d_mu.alloc(n * r);
         f->d_resid.alloc(n * r); f->d_R1.alloc(n * r); f->d_V.alloc(n * r); f->d_dfa.alloc(p * r);
@@ -795,7 +852,7 @@ int32_t ihtb_mvfit_get(const ihtb_mvfit* f, double* beta, double* c, double* Sig
         IHTB_CHECK(f, IHTB_EINVAL, "NULL fit handle");
         const int r = f->r;
         if (beta) {
-            std::fill(beta, beta + f->p * r, 0.0);
+            std::fill(beta, beta + f->p_global * r, 0.0);
             for (auto& kv : f->bestB) beta[kv.first] = kv.second;          // position j*r + t: r x p column-major
         }
         if (c)      // r x q column-major like Julia's best_C
