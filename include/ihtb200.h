@@ -178,7 +178,7 @@ int32_t ihtb_fit_destroy(ihtb_fit* f);
 int32_t ihtb_mvfit_create(const ihtb_geno* g, const double* Y, int64_t r, const double* z, int64_t q,
                           const ihtb_cfg* cfg, ihtb_mvfit** out);
 /* SNP-sharded form, like ihtb_fit_create_sharded: this rank's handle holds columns [j0, j0 + p_local) of p_global; B
- * in ihtb_mvfit_get has r x p_global entries.  init_beta is not available sharded. */
+ * in ihtb_mvfit_get has r x p_global entries. */
 int32_t ihtb_mvfit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_global, const double* Y, int64_t r,
                                   const double* z, int64_t q, const ihtb_cfg* cfg, ihtb_mvfit** out);
 int32_t ihtb_mvfit_set_k(ihtb_mvfit* f, int64_t k);
@@ -238,7 +238,7 @@ typedef struct ihtb_mmvfit ihtb_mmvfit;
 int32_t ihtb_mmvfit_create(const ihtb_mgeno* g, const double* Y, int64_t r, const double* z, int64_t q,
                            const ihtb_cfg* cfg, ihtb_mmvfit** out);
 int32_t ihtb_mmvfit_set_k(ihtb_mmvfit* f, int64_t k);
-int32_t ihtb_mmvfit_init(ihtb_mmvfit* f, const uint8_t* train_mask);
+int32_t ihtb_mmvfit_init(ihtb_mmvfit* f, const uint8_t* train_mask, int32_t init_beta);
 int32_t ihtb_mmvfit_run(ihtb_mmvfit* f, ihtb_result* result, ihtb_iter_trace* trace, int64_t trace_cap);
 int32_t ihtb_mmvfit_get(const ihtb_mmvfit* f, double* beta, double* c, double* Sigma, double* sigma_g);
 int32_t ihtb_mmvfit_predict(ihtb_mmvfit* f, const uint8_t* test_mask, double* mse);

@@ -224,12 +224,15 @@ function fit_iht(Y::AbstractMatrix{Float64}, xt::Transpose{Float64,<:AnyB200}, Z
     # sweep_mode 2 = IHTB_SWEEP_PAIR: the skinny X'R reads the matrix once per two traits (src/multivariate.jl:85)
     cfg = Ref(Cfg(0, 0, k, 1.0, tol, max_iter, min_iter, max_step, 2, 0, 0))
     fh = Ref{Ptr{Cvoid}}(C_NULL)
-    x isa B200MultiSnpLinAlg && init_beta && throw(ArgumentError("init_beta is not available for SNP-sharded multivariate fits"))
     check(ccall((mvsym(x, :create), LIB), Int32,
                 (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ref{Cfg}, Ref{Ptr{Cvoid}}),
                 x.handle, Yc, r, Zc, q, cfg, fh))
     try
-        check(ccall((init_beta ? :ihtb_mvfit_init_beta : mvsym(x, :init), LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), fh[], C_NULL))
+        if x isa B200MultiSnpLinAlg
+            check(ccall((:ihtb_mmvfit_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32), fh[], C_NULL, init_beta ? 1 : 0))
+        else
+            check(ccall((init_beta ? :ihtb_mvfit_init_beta : :ihtb_mvfit_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), fh[], C_NULL))
+        end
         res = CResult()
         trace = Vector{CIterTrace}(undef, verbose ? max_iter : 0)
         check(ccall((mvsym(x, :run), LIB), Int32, (Ptr{Cvoid}, Ref{CResult}, Ptr{CIterTrace}, Int64),

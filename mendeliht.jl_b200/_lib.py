@@ -136,7 +136,7 @@ SIGNATURES = {
     "ihtb_mfit_destroy": [_p],
     "ihtb_mmvfit_create": [_p, _f64, C.c_int64, _f64, C.c_int64, C.POINTER(Cfg), _pp],
     "ihtb_mmvfit_set_k": [_p, C.c_int64],
-    "ihtb_mmvfit_init": [_p, _u8],
+    "ihtb_mmvfit_init": [_p, _u8, C.c_int32],
     "ihtb_mmvfit_run": [_p, C.POINTER(Result), C.POINTER(IterTrace), C.c_int64],
     "ihtb_mmvfit_get": [_p, _f64, _f64, _f64, _f64],
     "ihtb_mmvfit_predict": [_p, _u8, _f64],

@@ -452,10 +452,11 @@ class mIHTVariable:
 
     def init_iht_indices(self, train_mask=None, init_beta=False):
         m = None if train_mask is None else np.ascontiguousarray(train_mask, dtype=np.uint8)
-        if init_beta and self._multi:
-            raise _lib.IHTBError(_lib.IHTB_EUNSUPPORTED, "init_beta is not available for SNP-sharded multivariate fits")
-        fn = load().ihtb_mvfit_init_beta if init_beta else self._fn("init")
-        check(fn(self._h, ptr(m, C.c_uint8) if m is not None else None))
+        mp = ptr(m, C.c_uint8) if m is not None else None
+        if self._multi:
+            check(load().ihtb_mmvfit_init(self._h, mp, 1 if init_beta else 0))
+        else:
+            check((load().ihtb_mvfit_init_beta if init_beta else load().ihtb_mvfit_init)(self._h, mp))
 
     def fit(self, trace_cap=None):
         cap = int(self.cfg.max_iter) if trace_cap is None else trace_cap

@@ -339,7 +339,9 @@ int32_t ihtb_mmvfit_create(const ihtb_mgeno* g, const double* Y, int64_t r, cons
     } while (0)
 
 int32_t ihtb_mmvfit_set_k(ihtb_mmvfit* f, int64_t k) { MMVFIT_ALL(ihtb_mvfit_set_k(fr, k)); }
-int32_t ihtb_mmvfit_init(ihtb_mmvfit* f, const uint8_t* train_mask) { MMVFIT_ALL(ihtb_mvfit_init(fr, train_mask)); }
+int32_t ihtb_mmvfit_init(ihtb_mmvfit* f, const uint8_t* train_mask, int32_t init_beta) {
+    MMVFIT_ALL(init_beta ? ihtb_mvfit_init_beta(fr, train_mask) : ihtb_mvfit_init(fr, train_mask));
+}
 int32_t ihtb_mmvfit_run(ihtb_mmvfit* f, ihtb_result* result, ihtb_iter_trace* trace, int64_t trace_cap) {
     MMVFIT_ALL(i == 0 ? ihtb_mvfit_run(fr, result, trace, trace_cap) : ihtb_mvfit_run(fr, nullptr, nullptr, 0));
 }

@@ -580,7 +580,8 @@ struct ihtb_mvfit {
     // univariate ihtb_fit_init_beta.  The reference accumulates the intercepts from several threads without
     // synchronisation; this is the single-thread result.
     void do_init_beta(const uint8_t* train_mask, const std::vector<double>& sy) {
-        IHTB_CHECK(!comm, IHTB_EUNSUPPORTED, "init_beta is not available for SNP-sharded multivariate fits");
+        // SNP-sharded fits: class sums and regressions are per column (no communication); the intercept sums are
+        // all-reduced and the ranks' local top-k entries of the initial B all-gathered for the global projection
         DBuf<double> cls((size_t)(6 * p)), bd((size_t)(p * r)), wy((size_t)n);
         double *W1 = cls.p, *W2 = W1 + p, *Wm = W2 + p, *Y1 = Wm + p, *Y2 = Y1 + p, *Ym = Y2 + p;
         sweep_class_sums(g, d_w.p, W1, W2, Wm, s, sweep_scratch);
@@ -596,6 +597,12 @@ struct ihtb_mvfit {
                             bd.p + (size_t)t * p, s);
             readback(1);
             c0sum[(size_t)t] = h_scal.p[0];
+        }
+        if (comm) {
+            upload(d_scal.p, c0sum.data(), (size_t)r);
+            comm_allreduce_sum_f64(comm, d_scal.p, (size_t)r, s);
+            readback(r);
+            std::copy(h_scal.p, h_scal.p + r, c0sum.begin());
         }
         // covariates 2..q: the same 2x2 regression on the host (r*q*n work)
         std::fill(C.begin(), C.end(), 0.0);
@@ -623,7 +630,7 @@ struct ihtb_mvfit {
                 }
         }
         for (int t = 0; t < r; ++t)
-            C[(size_t)(t * q)] = std::min(std::max(c0sum[(size_t)t] / (double)(p + q - 1), -2.0), 2.0);
+            C[(size_t)(t * q)] = std::min(std::max(c0sum[(size_t)t] / (double)(p_global + q - 1), -2.0), 2.0);
         // project_k!(v): the k largest |B| entries (ties: lowest position in vec(B)); covariates are all kept
         std::vector<double> zeros((size_t)r, 0.0);
         upload(d_bounds.p, zeros.data(), zeros.size());
@@ -640,8 +647,32 @@ struct ihtb_mvfit {
         struct Item { double a; int64_t pos; double v; };
         std::vector<Item> items;
         for (int e = 0; e < cnt; ++e) {
-            const int64_t pos_dev = h_sel.p[2 + e], t = pos_dev / p, j = pos_dev % p;
+            const int64_t pos_dev = h_sel.p[2 + e], t = pos_dev / p, j = pos_dev % p + j0;
             items.push_back({std::fabs(h_gout.p[e]), j * r + t, h_gout.p[e]});
+        }
+        if (comm) {        // two all-gathers of fixed blocks: [count | positions in vec(B)] and [count | value bits]
+            const size_t blk = 1 + (size_t)cap;
+            std::vector<int64_t> pos_blk(blk, -1), val_blk(blk, 0);
+            pos_blk[0] = val_blk[0] = (int64_t)items.size();
+            for (size_t e = 0; e < items.size(); ++e) {
+                pos_blk[1 + e] = items[e].pos;
+                memcpy(&val_blk[1 + e], &items[e].v, sizeof(double));
+            }
+            std::vector<int64_t> all_pos((size_t)comm->nranks * blk);
+            for (int pass = 0; pass < 2; ++pass) {
+                upload(d_xch.p, (pass == 0 ? pos_blk : val_blk).data(), blk);
+                comm_allgather_i64(comm, d_xch.p, d_xchall.p, blk, s);
+                IHTB_CUDA(cudaMemcpyAsync(h_xchall.p, d_xchall.p, all_pos.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+                sync();
+                if (pass == 0) std::copy(h_xchall.p, h_xchall.p + all_pos.size(), all_pos.begin());
+            }
+            items.clear();
+            for (int rk = 0; rk < comm->nranks; ++rk)
+                for (int64_t e = 0; e < all_pos[(size_t)rk * blk]; ++e) {
+                    double v;
+                    memcpy(&v, &h_xchall.p[(size_t)rk * blk + 1 + (size_t)e], sizeof(double));
+                    items.push_back({std::fabs(v), all_pos[(size_t)rk * blk + 1 + (size_t)e], v});
+                }
         }
         std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) {
             return x.a > y.a || (x.a == y.a && x.pos < y.pos);

@@ -346,6 +346,14 @@ def bench_sharded(args, rank, world, local_rank, G):
                 "rtol": 1e-6, "oracle_hit_max_iter": bool(gold.get("hit_max_iter")),
                 "golden": f"tests/golden/config1_weak_n{world}.json ({gold['oracle']}, {gold['oracle_seconds']:.0f} s on "
                           f"{gold['oracle_threads']} threads)"})
+            if "trace_logl" in gold:
+                # iteration-by-iteration comparison with the oracle's trace: how far the two runs agree to rtol
+                gl = np.asarray(gold["trace_logl"]); ml = np.asarray([t[0] for t in r.trace])
+                m = min(gl.size, ml.size)
+                rel = np.abs(ml[:m] - gl[:m]) / np.abs(gl[:m])
+                off = np.flatnonzero((rel > 1e-6) | (np.asarray(bt[:m]) != np.asarray(gold["trace_backtracks"][:m])))
+                line["check"]["trace_iterations_identical_to_oracle"] = int(off[0]) if off.size else int(m)
+                line["check"]["trace_max_rel_err_logl_all_iterations"] = float(rel.max()) if m else None
             if gold.get("hit_max_iter") and not strict:
                 # This problem (N = 2: 50k x 1M) is an oscillating logistic fit that never converges: the oracle also runs
                 # into max_iter = 200.  Over 200 iterations at the +-20 clamp, last-bit differences in summation order

@@ -32,6 +32,8 @@ for N in [int(a) for a in sys.argv[1:]]:
             "support": [int(j) for j in nz], "beta": [float(res.beta[j]) for j in nz], "c": [float(v) for v in res.c],
             "trace_backtracks": [int(b) for b in res.trace.backtracks],
             "trace_logl_first_last": [float(res.trace.logl[0]), float(res.trace.logl[-1])],
+            # whole trace: a fit that never converges is compared iteration by iteration until rounding decorrelates it
+            "trace_logl": [float(v) for v in res.trace.logl], "trace_tol": [float(v) for v in res.trace.tol],
             "hit_max_iter": bool(res.iter >= 200), "true_positives": int(np.intersect1d(nz, true_idx).size)}
     out = os.path.join(ROOT, "tests", "golden", f"config1_weak_n{N}.json")
     json.dump(gold, open(out, "w"), indent=1)

@@ -1,5 +1,5 @@
 """Runs the other BASELINE.json configs on one GPU (informational; bench.py's headline line is configs[1]).
-usage: python scripts/run_configs.py [cv|mv|ukb] ..."""
+usage: python scripts/run_configs.py [cv|mv|mvshard|ukb] ...   (mvshard: configs[3] with the SNP columns split over all visible GPUs)"""
 import json
 import os
 import sys
@@ -44,6 +44,38 @@ if "mv" in which:      # configs[3]: MvNormal r=5 traits n=100k p=500k k=50
                       "entries": int(np.count_nonzero(res.beta)), "true_cols_found": int(np.intersect1d(nz, idx).size),
                       "logl": res.logl}))
     g.close()
+
+if "mvshard" in which:      # configs[3] with the SNP columns split over every visible GPU, against the one-GPU fit
+    n, p, r, k = 100_000, 500_000, 5, 50
+    ngpu = m.device_count()
+    rng = np.random.default_rng(2026)
+    idx = np.sort(rng.permutation(p)[:k])
+    B = np.zeros((r, k))
+    for c in range(k):
+        B[rng.integers(0, r), c] = rng.normal()
+    A = rng.normal(size=(r, r)); cov = A @ A.T / r + 0.5 * np.eye(r)
+    Y = np.linalg.cholesky(cov) @ rng.normal(size=(r, n)) + 1.0
+    for s in range(0, k, 10):
+        Y += B[:, s:s + 10] @ synth.standardized_columns(2026, n, idx[s:s + 10]).T
+    out = {}
+    for name, make in (("one_gpu", lambda: m.B200SnpLinAlg.synthetic(n, p, 2026)),
+                       ("sharded", lambda: m.B200MultiSnpLinAlg.synthetic(n, p, 2026, 0.0, ngpu=ngpu,
+                                                                         mode=m.B200MultiSnpLinAlg.SHARD))):
+        g = make()
+        m.fit_iht(Y, g, None, k=k, sweep_mode=m.SWEEP_PAIR)                       # warm-up
+        best = None
+        for _ in range(3):
+            res = m.fit_iht(Y, g, None, k=k, sweep_mode=m.SWEEP_PAIR)
+            best = res if best is None or res.time < best.time else best
+        out[name] = best
+        g.close()
+    a, b_ = out["one_gpu"], out["sharded"]
+    print(json.dumps({"config": "configs[3] MvNormal r=5 n=100k p=500k k=50, PAIR sweep", "n_gpus": ngpu,
+                      "one_gpu_fit_seconds": a.time, "sharded_fit_seconds": b_.time, "speedup": a.time / b_.time,
+                      "iterations": [a.iter, b_.iter], "support_identical": bool(np.array_equal(a.beta != 0, b_.beta != 0)),
+                      "max_abs_diff_beta": float(np.max(np.abs(a.beta - b_.beta))),
+                      "rel_diff_logl": float(abs(a.logl - b_.logl) / abs(a.logl)),
+                      "sweep_seconds": [a.sweep_seconds, b_.sweep_seconds]}))
 
 if "cv" in which:      # configs[2]: Poisson CV q=5 path 1:20 n=100k p=500k (100 fits, one GPU here)
     n, p, q = 100_000, 500_000, 5

@@ -94,8 +94,14 @@ def test_one_process_sharded_multivariate_fit_matches_single_gpu(n, p, r, k):
         np.testing.assert_allclose(res.c, ref.c, rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(res.Sigma, ref.Sigma, rtol=1e-8, atol=1e-12)
         assert abs(res.logl - ref.logl) <= 1e-9 * abs(ref.logl)
-    with pytest.raises(m.IHTBError):
-        m.fit_iht(Y, gm, Z, k=k, init_beta=True)
+    # init_beta (initialize_beta!, src/multivariate.jl:519-558): per-shard regressions, intercept sums all-reduced, the
+    # ranks' top-k entries of the initial B all-gathered
+    res = m.fit_iht(Y, gm, Z, k=k + 2, init_beta=True)
+    ref = m.fit_iht(Y, g1, Z, k=k + 2, init_beta=True)
+    assert res.iter == ref.iter and np.array_equal(res.beta != 0, ref.beta != 0)
+    np.testing.assert_allclose(res.beta, ref.beta, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(res.c, ref.c, rtol=1e-9, atol=1e-12)
+    assert abs(res.logl - ref.logl) <= 1e-9 * abs(ref.logl)
     gm.close(); g1.close()
 
 
