@@ -53,12 +53,19 @@ void nccl_check(int rc, const char* what) {
 }
 }  // namespace
 
-constexpr int kNcclSum = 0, kNcclInt64 = 4, kNcclFloat64 = 8;
+constexpr int kNcclSum = 0, kNcclInt32 = 2, kNcclInt64 = 4, kNcclFloat64 = 8;
 
 void nccl_allreduce_sum_f64(ihtb_comm* c, double* d_buf, size_t count, cudaStream_t s) {
     if (!c || c->nranks == 1 || count == 0) return;
     IHTB_CHECK(c->comm, IHTB_ECUDA, "this communicator has no NCCL backend and its peer memory is not mapped");
     nccl_check(g_nccl.AllReduce(d_buf, d_buf, count, kNcclFloat64, kNcclSum, c->comm, s), "ncclAllReduce");
+    ++c->n_nccl_calls;
+}
+
+void nccl_allreduce_sum_i32(ihtb_comm* c, int* d_buf, size_t count, cudaStream_t s) {
+    if (!c || c->nranks == 1 || count == 0) return;
+    IHTB_CHECK(c->comm, IHTB_ECUDA, "this communicator has no NCCL backend and its peer memory is not mapped");
+    nccl_check(g_nccl.AllReduce(d_buf, d_buf, count, kNcclInt32, kNcclSum, c->comm, s), "ncclAllReduce");
     ++c->n_nccl_calls;
 }
 

@@ -57,6 +57,8 @@ struct NcclUniqueId { char internal[128]; };
 // generic collectives: peer memory when mapped (any size, chunked), NCCL otherwise
 void comm_allreduce_sum_f64(ihtb_comm* c, double* d_buf, size_t count, cudaStream_t s);
 void comm_allgather_i64(ihtb_comm* c, const int64_t* d_send, int64_t* d_recv, size_t count_per_rank, cudaStream_t s);
+void comm_allreduce_sum_i32(ihtb_comm* c, int* d_buf, size_t count, cudaStream_t s);      // counts (exact)
+void nccl_allreduce_sum_i32(ihtb_comm* c, int* d_buf, size_t count, cudaStream_t s);
 void nccl_allreduce_sum_f64(ihtb_comm* c, double* d_buf, size_t count, cudaStream_t s);
 void nccl_allgather_i64(ihtb_comm* c, const int64_t* d_send, int64_t* d_recv, size_t count_per_rank, cudaStream_t s);
 

@@ -294,6 +294,17 @@ struct ihtb_mvfit {
         IHTB_CUDA(cudaMemcpyAsync(h_scal.p, d_scal.p, nv * sizeof(double), cudaMemcpyDeviceToHost, s));
         sync();
     }
+    // host wall-clock per phase (every phase ends in a readback, so these are device-inclusive); IHTB_MV_TIMING=1 prints them
+    double phase_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 5..7: inside gradstep (top-k, exchange, exact re-scoring)
+    template <typename F>
+    auto timed(int ph, F&& fn) {
+        auto t0 = std::chrono::steady_clock::now();
+        struct Stop {
+            double& acc; std::chrono::steady_clock::time_point t0;
+            ~Stop() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+        } stop{phase_s[ph], t0};
+        return fn();
+    }
     static std::vector<int64_t> support_cols(const std::map<int64_t, double>& M, int r) {
         std::vector<int64_t> cols;
         for (auto& kv : M)
@@ -470,6 +481,11 @@ struct ihtb_mvfit {
     }
     // candidate columns of the top-k over the r*p entries |B0 + eta*df|
     std::vector<int64_t> device_candidate_cols(double eta) {
+        std::vector<int64_t> cols = timed(5, [&] { return local_candidate_cols(eta); });
+        if (!comm) return cols;
+        return timed(6, [&] { return exchange_candidate_cols(cols); });
+    }
+    std::vector<int64_t> local_candidate_cols(double eta) {
         upload(d_bounds.p, bounds.data(), (size_t)r);
         topk_candidates_blocked(tk, d_dfa.p, d_b0d.p,
                                 (cfg.sweep_mode == IHTB_SWEEP_PAIR && g->cs_j == 128) ? g->sgn.p : g->sinv.p, p,
@@ -480,9 +496,11 @@ struct ihtb_mvfit {
         IHTB_CHECK(st->count <= cap, IHTB_ENUMERIC, "degenerate projection: too many entries within the error bound");
         std::vector<int64_t> cols;
         for (int t = 0; t < st->count; ++t) cols.push_back(h_sel.p[2 + t] % p + j0);
-        if (!comm) return cols;
-        // every member of the global top-k is in its own rank's local top-k: the union of the ranks' candidate columns
-        // is a superset; one all-gather of fixed blocks [count | global columns]
+        return cols;
+    }
+    std::vector<int64_t> exchange_candidate_cols(std::vector<int64_t> cols) {
+        // the selection ran over all shards' entries (histograms all-reduced, topk.cu): every rank holds exactly its part
+        // of the candidate set a single device would find; one all-gather of fixed blocks [count | global columns]
         const size_t blk = 1 + (size_t)cap;
         std::vector<int64_t> mine(blk, -1);
         mine[0] = (int64_t)cols.size();
@@ -509,7 +527,7 @@ struct ihtb_mvfit {
         for (auto& kv : B0) cols.push_back(kv.first / r);
         std::sort(cols.begin(), cols.end());
         cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
-        if (!df_sparse) exact_df(cols);
+        if (!df_sparse) timed(7, [&] { exact_df(cols); return 0; });
         struct Item { double a; int64_t pos; double v; };
         std::vector<Item> items;
         for (int64_t j : cols)
@@ -733,20 +751,20 @@ struct ihtb_mvfit {
         inited = true;
     }
     void one_step(double old_logl, double& eta, int& eta_step, double& new_logl) {
-        eta = stepsize();
-        gradstep(eta);
-        update_xb();
-        new_logl = solve_sigma_and_logl();
+        eta = timed(0, [&] { return stepsize(); });
+        timed(1, [&] { gradstep(eta); return 0; });
+        timed(2, [&] { update_xb(); return 0; });
+        new_logl = timed(3, [&] { return solve_sigma_and_logl(); });
         eta_step = 0;
         while (old_logl > new_logl && eta_step < cfg.max_step) {
             eta /= 2;
             B = B0; C = C0; Gamma = Gamma0;
-            gradstep(eta);
-            update_xb();
-            new_logl = solve_sigma_and_logl();
+            timed(1, [&] { gradstep(eta); return 0; });
+            timed(2, [&] { update_xb(); return 0; });
+            new_logl = timed(3, [&] { return solve_sigma_and_logl(); });
             ++eta_step; ++n_backtracks;
         }
-        score_and_sweep();
+        timed(4, [&] { score_and_sweep(); return 0; });
         IHTB_CHECK(!std::isnan(new_logl), IHTB_ENUMERIC, "Loglikelihood function is NaN, aborting...");
         IHTB_CHECK(!std::isinf(new_logl), IHTB_ENUMERIC, "Loglikelihood function is Inf, aborting...");
     }
@@ -776,6 +794,11 @@ struct ihtb_mvfit {
         }
         compute_pve();
         inited = false;
+        if (getenv("IHTB_MV_TIMING") && (!comm || comm->rank == 0))
+            fprintf(stderr, "[mvfit] %lld steps: stepsize %.3f ms, gradstep %.3f ms, update_xb %.3f ms, sigma/logl %.3f ms, "
+                    "score+sweep %.3f ms (sweep kernels %.3f ms); inside gradstep: top-k %.3f, exchange %.3f, re-scoring %.3f ms\n",
+                    (long long)n_steps, phase_s[0] * 1e3, phase_s[1] * 1e3, phase_s[2] * 1e3, phase_s[3] * 1e3, phase_s[4] * 1e3,
+                    sweep_ms_total - ms0, phase_s[5] * 1e3, phase_s[6] * 1e3, phase_s[7] * 1e3);
         if (res) {
             res->time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             res->logl = best_logl; res->iter = mm_iter; res->sigma_g = pve.empty() ? 0.0 : pve[0];
@@ -842,6 +865,7 @@ int32_t ihtb_mvfit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p
         IHTB_CUDA(cudaMemcpyAsync(f->d_Z.p, z, n * q * sizeof(double), cudaMemcpyHostToDevice, f->s));
         f->tk = TopkCtx{p * r, f->d_keyL.p, f->d_keyU.p, f->d_hist.p, reinterpret_cast<TopkState*>(f->d_sel.p),
                         f->d_sel.p + 2, f->cap};
+        if (f->comm) { f->tk.comm = f->comm; f->tk.p_total = p_global * r; }     // one selection over all shards' entries
         f->sync();
         *out = f.release();
     });

@@ -107,8 +107,18 @@ __global__ void k_p2p_push(const double* __restrict__ src, int64_t n, P2PView v,
     p2p_publish(v, seq);
 }
 
+// counts (histograms of the distributed radix select, topk.cu): pushed as doubles -- sums of small integers are exact
+__global__ void k_p2p_push_i32(const int* __restrict__ src, int64_t n, P2PView v, unsigned long long seq) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = (double)src[i];
+        for (int r = 0; r < v.nranks; ++r) v.push_slot[r][i] = x;
+    }
+    p2p_publish(v, seq);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_p2p_reduce(double* __restrict__ out, int64_t n, P2PView v, unsigned long long seq, unsigned long long timeout_ns) {
+k_p2p_reduce(T* __restrict__ out, int64_t n, P2PView v, unsigned long long seq, unsigned long long timeout_ns) {
     if (threadIdx.x < v.nranks) {
         const volatile unsigned long long* f = v.local_flag + threadIdx.x;
         unsigned long long t0;
@@ -126,7 +136,7 @@ k_p2p_reduce(double* __restrict__ out, int64_t n, P2PView v, unsigned long long 
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double a = 0.0;
         for (int r = 0; r < v.nranks; ++r) a += __ldcv(v.local_slot[r] + i);
-        out[i] = a;
+        out[i] = (T)a;
     }
 }
 
@@ -386,7 +396,16 @@ void p2p_push(ihtb_comm* c, const double* d_src, size_t n, cudaStream_t s) {
 void p2p_reduce(ihtb_comm* c, double* d_out, size_t n, cudaStream_t s) {
     P2PView v = p2p_view(c);
     int grid = (int)std::min<size_t>(148, (n + 255) / 256);
-    IHTB_LAUNCH(k_p2p_reduce, grid, 256, 0, s, d_out, (int64_t)n, v, (unsigned long long)(c->seq[0] + 1), timeout_ns());
+    IHTB_LAUNCH(k_p2p_reduce<double>, grid, 256, 0, s, d_out, (int64_t)n, v, (unsigned long long)(c->seq[0] + 1), timeout_ns());
+    ++c->seq[0];
+    ++c->n_collectives;
+}
+
+static void p2p_allreduce_i32(ihtb_comm* c, int* d_buf, size_t n, cudaStream_t s) {
+    P2PView v = p2p_view(c);
+    int grid = (int)std::min<size_t>(148, (n + 255) / 256);
+    IHTB_LAUNCH(k_p2p_push_i32, grid, 256, 0, s, d_buf, (int64_t)n, v, (unsigned long long)(c->seq[0] + 1));
+    IHTB_LAUNCH(k_p2p_reduce<int>, grid, 256, 0, s, d_buf, (int64_t)n, v, (unsigned long long)(c->seq[0] + 1), timeout_ns());
     ++c->seq[0];
     ++c->n_collectives;
 }
@@ -454,6 +473,12 @@ void comm_allreduce_sum_f64(ihtb_comm* c, double* d_buf, size_t count, cudaStrea
             p2p_allreduce_2phase(c, m, d_buf + o, s);
         }
     }
+}
+
+void comm_allreduce_sum_i32(ihtb_comm* c, int* d_buf, size_t count, cudaStream_t s) {
+    if (!c || c->nranks == 1 || count == 0) return;
+    if (!p2p_mapped(c)) { nccl_allreduce_sum_i32(c, d_buf, count, s); return; }
+    for (size_t o = 0; o < count; o += c->pa_cap) p2p_allreduce_i32(c, d_buf + o, std::min(c->pa_cap, count - o), s);
 }
 
 void comm_allgather_i64(ihtb_comm* c, const int64_t* d_send, int64_t* d_recv, size_t count_per_rank, cudaStream_t s) {

@@ -8,6 +8,7 @@
 // re-scores those few columns exactly in FP64 and takes the top-k of the exact values, ties broken by lowest index,
 // so the selected support does not depend on the sweep arithmetic.  Only integer atomics: deterministic.
 #include "topk.cuh"
+#include "comm.cuh"
 
 namespace ihtb {
 
@@ -187,14 +188,18 @@ static void topk_run(TopkCtx& c, const double* d_dfa, const double* d_b0d, const
                      const double* d_scal = nullptr, double bound_coef = 0.0, const double* d_l2 = nullptr,
                      bool fill_cand = false) {
     int grid = tk_grid(c.p);
-    int kk = (int)(k < c.p ? k : c.p);
+    const int64_t total = c.comm ? c.p_total : c.p;
+    int kk = (int)(k < total ? k : total);
     int* hs = c.hist + (size_t)(c.set & 1) * TK_HIST_STRIDE;             // this selection's histograms (all zero)
     int* ho = c.hist + (size_t)((c.set & 1) ^ 1) * TK_HIST_STRIDE;       // cleared now for the next selection
     ++c.set;
     IHTB_LAUNCH(k_keys_hist0, grid, TK_THREADS, 0, s, c.p, d_dfa, d_b0d, d_sinv, p_mod, d_bounds, eta, bound, d_scal,
                 bound_coef, c.wt, c.keyL, c.keyU, hs, d_l2, ho, c.st, c.cand, fill_cand ? c.cap : 0);
+    if (c.comm) comm_allreduce_sum_i32(c.comm, hs, TK_BINS, s);
     IHTB_LAUNCH(k_hist_fused, grid, TK_THREADS, 0, s, c.p, c.keyL, hs, 1, kk, hs + TK_BINS);
+    if (c.comm) comm_allreduce_sum_i32(c.comm, hs + TK_BINS, TK_BINS, s);
     IHTB_LAUNCH(k_hist_fused, grid, TK_THREADS, 0, s, c.p, c.keyL, hs, 2, kk, hs + 2 * TK_BINS);
+    if (c.comm) comm_allreduce_sum_i32(c.comm, hs + 2 * TK_BINS, 1024, s);
     IHTB_LAUNCH(k_compact_fused, grid, TK_THREADS, 0, s, c.p, c.keyU, hs, kk, c.st, c.cand, c.cap);
 }
 

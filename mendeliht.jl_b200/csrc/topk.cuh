@@ -1,6 +1,8 @@
 #pragma once
 #include "common.cuh"
 
+struct ihtb_comm;
+
 namespace ihtb {
 
 struct TopkState {
@@ -20,6 +22,11 @@ struct TopkCtx {
     int cap;
     const double* wt = nullptr;   // optional prior weights [p]: keys rank |v_j| * wt_j
     unsigned set = 0;             // histogram set of the next selection
+    // Column-sharded selection over ALL shards' entries (mvfit.cu): the three digit histograms are all-reduced between
+    // the passes, so every rank derives the same tau (the k-th largest lower-bound key of the whole problem) and compacts
+    // only its own entries that can reach it.  p_total = entries over all shards.
+    ihtb_comm* comm = nullptr;
+    int64_t p_total = 0;
 };
 
 void topk_candidates(TopkCtx& c, const double* d_dfa, const double* d_b0d, const double* d_sinv, double eta,
