@@ -414,7 +414,7 @@ class mIHTVariable:
     (samples are columns); `x` is the n x p genotype operator whose transpose the reference passes."""
 
     def __init__(self, x: B200SnpLinAlg, z, y, k, zkeep=None, tol=1e-4, max_iter=200, min_iter=5, max_step=3,
-                 sweep_mode=_lib.SWEEP_FAST):
+                 sweep_mode=_lib.SWEEP_FAST, comm=None, p_global=None):
         Y = np.asarray(y, dtype=np.float64)
         Z = np.asarray(z, dtype=np.float64)
         if Z.ndim == 1:
@@ -441,8 +441,16 @@ class mIHTVariable:
         self._pre = "ihtb_mmvfit_" if self._multi else "ihtb_mvfit_"
         if self._multi and x.mode != B200MultiSnpLinAlg.SHARD:
             raise _lib.IHTBError(_lib.IHTB_EINVAL, "fit_iht over several GPUs needs a SHARD multi-device operator")
-        check(self._fn("create")(x._h, Yc.ctypes.data_as(C.POINTER(C.c_double)), r,
-                                 Zc.ctypes.data_as(C.POINTER(C.c_double)), q, C.byref(self.cfg), C.byref(self._h)))
+        self.p_global = int(p_global) if (comm is not None and p_global is not None) else x.p
+        if comm is not None:       # one process per GPU: this rank holds columns [x.j0, x.j0 + x.p) of p_global
+            if self._multi:
+                raise _lib.IHTBError(_lib.IHTB_EINVAL, "a multi-device operator already shards inside one process")
+            check(load().ihtb_mvfit_create_sharded(x._h, comm._h, self.p_global, Yc.ctypes.data_as(C.POINTER(C.c_double)),
+                                                   r, Zc.ctypes.data_as(C.POINTER(C.c_double)), q, C.byref(self.cfg),
+                                                   C.byref(self._h)))
+        else:
+            check(self._fn("create")(x._h, Yc.ctypes.data_as(C.POINTER(C.c_double)), r,
+                                     Zc.ctypes.data_as(C.POINTER(C.c_double)), q, C.byref(self.cfg), C.byref(self._h)))
 
     def _fn(self, name):
         return getattr(load(), self._pre + name)
@@ -467,7 +475,7 @@ class mIHTVariable:
         return res, [(tr[i].logl, tr[i].backtracks, tr[i].tol, tr[i].eta, tr[i].n_candidates) for i in range(n_it)]
 
     def get(self):
-        beta = np.empty((self.r, self.p), order="F"); c = np.empty((self.r, self.q), order="F")
+        beta = np.empty((self.r, self.p_global), order="F"); c = np.empty((self.r, self.q), order="F")
         S = np.empty((self.r, self.r)); sg = np.empty(self.r)
         check(self._fn("get")(self._h, beta.ctypes.data_as(C.POINTER(C.c_double)),
                               c.ctypes.data_as(C.POINTER(C.c_double)), ptr(S, C.c_double), ptr(sg, C.c_double)))
@@ -491,10 +499,11 @@ class mIHTVariable:
             pass
 
 
-def _fit_mv(y, x, z, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode, init_beta=False) -> mIHTResult:
+def _fit_mv(y, x, z, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode, init_beta=False, comm=None,
+            p_global=None) -> mIHTResult:
     if z is None:
         z = np.ones((1, x.n))
-    v = mIHTVariable(x, z, y, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode)
+    v = mIHTVariable(x, z, y, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode, comm, p_global)
     try:
         v.init_iht_indices(None, init_beta)
         res, trace = v.fit()
@@ -531,7 +540,7 @@ def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est
         if debias:
             raise _lib.IHTBError(_lib.IHTB_EUNSUPPORTED,
                                  "Currently the debiasing routine for multivariate IHT is broken, sorry!")
-        return _fit_mv(y, x, z, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode, init_beta)
+        return _fit_mv(y, x, z, k, zkeep, tol, max_iter, min_iter, max_step, sweep_mode, init_beta, comm, p_global)
     if not x.center:
         raise _lib.IHTBError(_lib.IHTB_EUNSUPPORTED, "x is not centered! Please construct SnpLinAlg{Float64}"
                                                      "(::SnpArray, center=true, scale=true)")

@@ -68,6 +68,23 @@ same = (res.iter == ref.iter and np.array_equal(np.flatnonzero(res.beta), np.fla
 ok = ok and same
 print(f"rank {rank} debias: sharded iter={res.iter} full iter={ref.iter} same={same} "
       f"max|dbeta|={np.abs(res.beta - ref.beta).max():.3e}", flush=True)
+# multivariate (MvNormal) fit with the columns split over the ranks: PAIR and FAST sweeps, init_beta
+r, kk = 3, 9
+rng = np.random.default_rng(57)
+idx = np.sort(rng.permutation(p)[:kk])
+Bt = np.zeros((r, kk))
+for cc in range(kk):
+    Bt[rng.integers(0, r), cc] = rng.normal() * 0.8
+Y = Bt @ synth.standardized_columns(55, n, idx).T + rng.normal(size=(r, n))
+Z = np.vstack([np.ones(n), rng.normal(size=n)])
+for kw in ({"sweep_mode": m.SWEEP_PAIR}, {"sweep_mode": m.SWEEP_FAST}, {"sweep_mode": m.SWEEP_PAIR, "init_beta": True}):
+    res = m.fit_iht(Y, g_loc, Z, k=kk + 2, comm=comm, p_global=p, **kw)
+    ref = m.fit_iht(Y, g_full, Z, k=kk + 2, **kw)
+    same = (res.iter == ref.iter and np.array_equal(res.beta != 0, ref.beta != 0)
+            and np.allclose(res.beta, ref.beta, rtol=1e-9, atol=1e-12) and np.allclose(res.c, ref.c, rtol=1e-9)
+            and abs(res.logl - ref.logl) < 1e-9 * abs(ref.logl))
+    ok = ok and same
+    print(f"rank {rank} MvNormal {kw}: sharded iter={res.iter} full iter={ref.iter} same={same}", flush=True)
 if os.environ.get("CHECK_SHARDED_SKIP_FULL") == "1":
     dist.barrier()
     comm.close()
