@@ -254,13 +254,17 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     abytes = sweep_bytes(n, p)
     achieved = abytes / (mk.value * 1e-3) / 1e9
+    # what the kernel physically streams: the handle's ternary copy packs five dosages per byte (p * ceil(n/640) * 128 B)
+    stream_b, ternary = g.sweep_stream_bytes()
+    sbytes = stream_b + 8 * n + 24 * p
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            traffic = tj.get("dram_bytes_per_launch")
-            traffic_src = "static: " + tj.get("source", "profiles/sweep_traffic.json") + " (ncu cannot run inside a timed bench)"
+            if bool(tj.get("ternary", False)) == ternary:       # an ncu capture of THIS kernel variant only
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = "static: " + tj.get("source", "profiles/sweep_traffic.json") + " (ncu cannot run inside a timed bench)"
         except Exception:
             traffic = None
 
@@ -286,6 +290,11 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "k_sweep_lut",
                      "algorithmic_bytes_per_launch": abytes, "kernel_ms": mk.value,
+                     "streamed_bytes_per_launch": sbytes, "streamed_gbs": sbytes / (mk.value * 1e-3) / 1e9,
+                     "streamed_frac": sbytes / (mk.value * 1e-3) / 1e9 / peak,
+                     "stream_encoding": ("ternary copy: 5 dosages per byte, lossless (missing -> CSR correction); `achieved` "
+                                         "counts the PLINK 2-bit bytes of SURVEY 8d, `streamed_*` what the kernel reads")
+                                        if ternary else "PLINK 2-bit tiles",
                      "sweep_with_epilogue_ms": mt.value, "sweep_with_epilogue_gbs": abytes / (mt.value * 1e-3) / 1e9},
         "e2e": {"value": e_iters / t_e2e, "unit": UNIT,
                 "h2d_bytes_per_step": int(y.nbytes + z.nbytes), "d2h_bytes_per_step": int(beta.nbytes + c.nbytes),

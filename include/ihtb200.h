@@ -132,6 +132,10 @@ int32_t ihtb_x_support(const ihtb_geno* g, const int64_t* idx, int64_t k, const 
  * ms_kernel = the dominant kernel, ms_total = kernel + epilogue, both averaged over `reps` launches */
 int32_t ihtb_sweep_bench(const ihtb_geno* g, int32_t sweep_mode, int32_t warmup, int32_t reps, double* ms_kernel,
                          double* ms_total);
+/* Bytes of packed genotypes one FAST / PAIR sweep streams from HBM for this handle: p * ceil(n/640) * 128 when the handle
+ * holds the ternary copy (five dosages per byte, built at creation when memory allows; IHTB_TERN=0/1 forces), else
+ * p * ceil(n/512) * 128 (the PLINK 2-bit tiles).  The algorithmic figure of SURVEY.md 8d stays p * ceil(n/4). */
+int32_t ihtb_geno_sweep_stream_bytes(const ihtb_geno* g, int64_t* bytes, int32_t* ternary);
 int32_t ihtb_geno_destroy(ihtb_geno* g);
 
 /* ---- univariate fit (fit_iht / fit_iht! / init_iht_indices!, src/fit.jl:60-207, src/utilities.jl:366-438) ---- */

@@ -95,6 +95,12 @@ class B200SnpLinAlg:
     def shape(self):
         return (self.n, self.p)
 
+    def sweep_stream_bytes(self):
+        """(bytes of packed genotypes one FAST / PAIR sweep reads from HBM, ternary copy in use?)"""
+        b, t = C.c_int64(0), C.c_int32(0)
+        check(load().ihtb_geno_sweep_stream_bytes(self._h, C.byref(b), C.byref(t)))
+        return int(b.value), bool(t.value)
+
     def size(self, dim=None):
         return self.shape if dim is None else self.shape[dim - 1]
 

@@ -201,9 +201,65 @@ __global__ void k_synth(GenoView g, int64_t j0, uint64_t seed, uint32_t miss_thr
     *reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(gv_ptr(g, j, 4 * w))) = out;
 }
 
+// Ternary copy of the quad-interleaved tiles (common.cuh ihtb_geno::tern): thread = one 32-bit word of the copy =
+// 20 samples of one column = 5 source bytes.  idx = ((slab * nquads + quad) * 32 + w) * 4 + cj, so stores are coalesced.
+__global__ void k_make_tern(GenoView g, int64_t p4, int64_t tern_slabs, uint32_t* __restrict__ out) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t total = tern_slabs * p4 * 32;
+    if (idx >= total) return;
+    const int cj = (int)(idx & 3), w = (int)((idx >> 2) & 31);
+    const int64_t sq = idx >> 7, nquads = p4 >> 2;
+    const int64_t slab = sq / nquads, j = (sq % nquads) * 4 + cj;
+    uint32_t word = 0;
+    if (j < g.p) {
+        const int64_t b0 = slab * 160 + 5 * w;                  // first of the 5 source bytes (20 samples)
+        uint32_t code[20];
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            const int64_t b = b0 + t;
+            const uint32_t byte = b < g.stride ? *gv_ptr(g, j, b) : 0u;      // bytes past nbytes are zero padding
+#pragma unroll
+            for (int s = 0; s < 4; ++s) code[4 * t + s] = (byte >> (2 * s)) & 3u;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int d = 4; d >= 0; --d) {
+                const uint32_t c = code[5 * t + d];
+                v = 3u * v + ((c >> 1) * (1u + (c & 1u)));       // 00 -> 0, 01 (missing) -> 0, 10 -> 1, 11 -> 2
+            }
+            word |= v << (8 * t);
+        }
+    }
+    out[idx] = word;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
+// IHTB_TERN=0 never builds the ternary copy, =1 always; default: when it takes at most half of the memory still free
+// (a 125 GB matrix on one GPU keeps the 2-bit sweep; its column shards on 8 GPUs get the copy)
+static void build_tern(ihtb_geno* g, cudaStream_t s) {
+    g->tern.release();
+    g->tern_slabs = 0;
+    if (!g->quad) return;
+    const char* e = getenv("IHTB_TERN");
+    if (e && *e == '0') return;
+    const int64_t slabs = ceil_div(g->n, 640);
+    const size_t bytes = (size_t)slabs * (size_t)g->p4 * 128;
+    if (!(e && *e == '1')) {
+        size_t free_b = 0, total_b = 0;
+        IHTB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (bytes > free_b / 2) return;
+    }
+    g->tern.alloc(bytes);
+    g->tern_slabs = slabs;
+    const int64_t words = slabs * g->p4 * 32;
+    IHTB_LAUNCH(k_make_tern, (unsigned)ceil_div(words, 256), 256, 0, s, geno_view(g), g->p4, slabs,
+                reinterpret_cast<uint32_t*>(g->tern.p));
+}
+
 static void finish_handle(ihtb_geno* g) {
     cudaStream_t s = 0;
     g->mu.alloc(g->p); g->sinv.alloc(g->p); g->nmiss.alloc(g->p); g->sgn.alloc(g->p);
@@ -226,6 +282,7 @@ static void finish_handle(ihtb_geno* g) {
         IHTB_LAUNCH(k_fill_missing, (unsigned)ceil_div(threads, 256), 256, 0, s, geno_view(g), g->miss_ptr.p,
                     g->miss_idx.p);
     }
+    build_tern(g, s);
     IHTB_CUDA(cudaStreamSynchronize(s));
 }
 
@@ -468,6 +525,16 @@ int32_t ihtb_synth_host(int64_t n, int64_t ncols, int64_t j0, uint64_t seed, dou
             });
         }
         for (auto& th : pool) th.join();
+    });
+}
+
+int32_t ihtb_geno_sweep_stream_bytes(const ihtb_geno* g, int64_t* bytes, int32_t* ternary) {
+    return guard([&] {
+        IHTB_CHECK(g, IHTB_EINVAL, "NULL genotype handle");
+        geno_require_ready(g);
+        const bool t = g->tern.p != nullptr;
+        if (bytes) *bytes = (t ? g->tern_slabs : g->stride / 128) * g->p4 * 128;
+        if (ternary) *ternary = t ? 1 : 0;
     });
 }
 

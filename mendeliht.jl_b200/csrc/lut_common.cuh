@@ -95,6 +95,80 @@ __device__ __forceinline__ void lut_build(uint32_t tab, const double* __restrict
     }
 }
 
+// Ternary tiles (ihtb_geno::tern): a byte is five base-3 dosages, a chunk covers 640 samples, word w holds samples
+// 20 w .. 20 w + 19 and byte t of it samples 20 w + 5 t .. + 4.  Same table addressing, 243 rows used.  Parts 0..2 take
+// one value of the top digit each (81 rows); a fourth part idles.
+template <int NT>
+__device__ __forceinline__ void lut_build_tern(uint32_t tab, const double* __restrict__ v, double vbar, int64_t n,
+                                               int64_t slab, int tid) {
+    static_assert(NT == 512, "ternary tables are built by 512 threads");
+    const int group = tid & 127, d4 = tid >> 7;
+    if (d4 > 2) return;
+    const int t = group >> 5, w = group & 31;
+    float u[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        int64_t i = slab * 640 + 20 * w + 5 * t + s;
+        u[s] = (i < n) ? __double2float_rn(__dsub_rn(v[i], vbar)) : 0.0f;
+    }
+    auto f = [&](int s, int d) -> float { return d == 1 ? u[s] : (d == 2 ? u[s] + u[s] : 0.0f); };
+    const uint32_t rowbase = tab + (uint32_t)(t >> 1) * 65536u + (uint32_t)(t & 1) * 128u + 4u * (uint32_t)w;
+    const float a4 = (d4 == 1) ? u[4] : ((d4 == 2) ? u[4] + u[4] : 0.0f);
+    const uint32_t base4 = rowbase + (uint32_t)d4 * (81u * 256u);
+#pragma unroll
+    for (int d3 = 0; d3 < 3; ++d3) {
+        const float a3 = a4 + f(3, d3);
+#pragma unroll
+        for (int d2 = 0; d2 < 3; ++d2) {
+            const float a2 = a3 + f(2, d2);
+#pragma unroll
+            for (int d1 = 0; d1 < 3; ++d1) {
+                const float a1 = a2 + f(1, d1);
+#pragma unroll
+                for (int d0 = 0; d0 < 3; ++d0)
+                    sts_f32(base4 + (uint32_t)(27 * d3 + 9 * d2 + 3 * d1 + d0) * 256u, a1 + f(0, d0));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void lut_build_h2_tern(uint32_t tab, const double* __restrict__ v0, const double* __restrict__ v1,
+                                                  double vbar0, double vbar1, float sc0, float sc1, int64_t n, int64_t slab,
+                                                  int tid) {
+    const int group = tid & 127, d4 = tid >> 7;
+    if (d4 > 2) return;
+    const int t = group >> 5, w = group & 31;
+    float a[5], b[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        int64_t i = slab * 640 + 20 * w + 5 * t + s;
+        a[s] = (i < n) ? __double2float_rn(__dsub_rn(v0[i], vbar0)) * sc0 : 0.0f;     // power-of-two scale: exact
+        b[s] = (i < n) ? __double2float_rn(__dsub_rn(v1[i], vbar1)) * sc1 : 0.0f;
+    }
+    auto fa = [&](int s, int d) -> float { return d == 1 ? a[s] : (d == 2 ? a[s] + a[s] : 0.0f); };
+    auto fb = [&](int s, int d) -> float { return d == 1 ? b[s] : (d == 2 ? b[s] + b[s] : 0.0f); };
+    const uint32_t rowbase = tab + (uint32_t)(t >> 1) * 65536u + (uint32_t)(t & 1) * 128u + 4u * (uint32_t)w;
+    const float a4 = fa(4, d4), b4 = fb(4, d4);
+    const uint32_t base4 = rowbase + (uint32_t)d4 * (81u * 256u);
+#pragma unroll
+    for (int d3 = 0; d3 < 3; ++d3) {
+        const float a3 = a4 + fa(3, d3), b3 = b4 + fb(3, d3);
+#pragma unroll
+        for (int d2 = 0; d2 < 3; ++d2) {
+            const float a2 = a3 + fa(2, d2), b2 = b3 + fb(2, d2);
+#pragma unroll
+            for (int d1 = 0; d1 < 3; ++d1) {
+                const float a1 = a2 + fa(1, d1), b1 = b2 + fb(1, d1);
+#pragma unroll
+                for (int d0 = 0; d0 < 3; ++d0) {
+                    const __half2 h = __floats2half2_rn(a1 + fa(0, d0), b1 + fb(0, d0));
+                    sts_u32(base4 + (uint32_t)(27 * d3 + 9 * d2 + 3 * d1 + d0) * 256u, *reinterpret_cast<const uint32_t*>(&h));
+                }
+            }
+        }
+    }
+}
+
 // half2 table of one slab for TWO right-hand sides (the pair sweep): entry = (v0 part | v1 part), each the FP32 sum of
 // up to four scaled values rounded once to FP16; same addressing as lut_build.  512 consumer threads.
 __device__ __forceinline__ void lut_build_h2(uint32_t tab, const double* __restrict__ v0, const double* __restrict__ v1,

@@ -181,7 +181,7 @@ void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* d
         double* out = dOut + t * g->p;
         if (mode == IHTB_SWEEP_PAIR && g->cs_j == 128 && t + 1 < m) {
             // two right-hand sides per pass over the matrix (half2 tables); an odd last one takes the FAST path below
-            const int64_t n_slabs = g->stride / 128;
+            const int64_t n_slabs = sweep_fast_num_slabs(g);
             if (sc->part32.n < (size_t)(2 * n_slabs * g->p)) sc->part32.alloc((size_t)(2 * n_slabs * g->p));
             if (sc->scale.n < 2) sc->scale.alloc(2);
             IHTB_LAUNCH(k_pair_scale, 1, 1024, 0, s, v, v + g->n, g->n, d_vbar + t, sc->scale.p);
@@ -268,7 +268,7 @@ bool SweepPairer::sweep(int slot, const ihtb_geno* g, const double* d_v, const d
             // second to arrive: launch one pass for both on this stream, behind the partner's producer kernels
             const Req a = req[0], b = req[1];
             SweepScratch* sc = reinterpret_cast<SweepScratch*>(scratch);
-            const int64_t n_slabs = g->stride / 128;
+            const int64_t n_slabs = sweep_fast_num_slabs(g);
             if (sc->part32.n < (size_t)(2 * n_slabs * g->p)) sc->part32.alloc((size_t)(2 * n_slabs * g->p));
             if (sc->scale.n < 2) sc->scale.alloc(2);
             IHTB_CUDA(cudaStreamWaitEvent(s, ready[other], 0));

@@ -76,7 +76,9 @@ __device__ __forceinline__ LutPlan lut_plan(uint32_t base, uint32_t bytes) {
 //       <= 2^14, no overflow); part is [2][n_slabs][p_out] floats of the SCALED sums.  Error bound, per column sum:
 //       one FP16 rounding per table entry + two levels of HADD2 on partial sums bounded by twice the absolute sum of
 //       the 16 samples of a word: 3 * 2^-11 * 2 ||u||_1 < 2^-8 ||u||_1 (FP32 and subnormal terms are below 1e-5 of that).
-template <int CW, int G, bool QUAD, bool H2>
+// TERN: the stream is the handle's ternary copy (common.cuh): five dosages per byte, 640 samples per chunk.  Bytes are
+//       opaque table keys to this kernel, so only the table builders differ.
+template <int CW, int G, bool QUAD, bool H2, bool TERN>
 __global__ void __launch_bounds__((CW + 1) * 32, 1)
 k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t p, int64_t p_out, int64_t n,
             int64_t n_slabs, const double* __restrict__ v, const double* __restrict__ v1,
@@ -166,7 +168,9 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
             const int cb0 = (slab == slab_beg) ? (int)(u_beg - slab * n_cblocks) : 0;
             const int cb1 = (slab == slab_end) ? (int)(u_end - slab * n_cblocks) : ncb;
             consumer_bar<CW * 32>();      // everyone finished looking up the previous slab's tables
-            if (H2) lut_build_h2(pl.tab, v, v1, vbar, vbar1, sc0, sc1, n, slab, tid);
+            if (H2 && TERN) lut_build_h2_tern(pl.tab, v, v1, vbar, vbar1, sc0, sc1, n, slab, tid);
+            else if (H2) lut_build_h2(pl.tab, v, v1, vbar, vbar1, sc0, sc1, n, slab, tid);
+            else if (TERN) lut_build_tern<CW * 32>(pl.tab, v, vbar, n, slab, tid);
             else lut_build<CW * 32>(pl.tab, v, vbar, n, slab, tid);
             consumer_bar<CW * 32>();
             float* __restrict__ outp = part + ((int64_t)(H2 ? vidx / CPW : 0) * n_slabs + slab) * p_out + col;
@@ -231,7 +235,10 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
     }
 }
 
-int64_t sweep_fast_num_slabs(const ihtb_geno* g) { return g->stride / 128; }
+// the FAST / PAIR sweeps stream the ternary copy when the handle has one (the TMEM variant reads the 2-bit tiles)
+bool sweep_tmem_enabled(const ihtb_geno* g);
+bool sweep_uses_tern(const ihtb_geno* g) { return g->tern.p != nullptr && g->quad && !sweep_tmem_enabled(g); }
+int64_t sweep_fast_num_slabs(const ihtb_geno* g) { return sweep_uses_tern(g) ? g->tern_slabs : g->stride / 128; }
 
 // sweep_tmem.cu: the same sweeps with the genotype stream staged through tensor memory (quad layout only)
 bool sweep_tmem_enabled(const ihtb_geno* g);
@@ -239,18 +246,18 @@ void sweep_tmem_partials(const ihtb_geno* g, const double* d_v, const double* d_
 void sweep_tmem_pair_partials(const ihtb_geno* g, const double* d_v0, const double* d_v1, const double* d_vbar,
                               const float* d_scale, float* d_part, cudaStream_t s);
 
-template <bool QUAD, bool H2>
+template <bool QUAD, bool H2, bool TERN = false>
 static void launch_lut(const ihtb_geno* g, const double* d_v, const double* d_v1, const double* d_vbar,
                        const float* d_scale, float* d_part, cudaStream_t s) {
-    ensure_dynamic_smem(k_sweep_lut<16, 2, QUAD, H2>, LUT_SMEM_BYTES);
-    const int64_t n_slabs = sweep_fast_num_slabs(g);
+    ensure_dynamic_smem(k_sweep_lut<16, 2, QUAD, H2, TERN>, LUT_SMEM_BYTES);
+    const int64_t n_slabs = TERN ? g->tern_slabs : g->stride / 128;
     const int64_t n_cblocks = ceil_div(g->p4, LUT_STAGE_COLS);
     int64_t units = n_slabs * n_cblocks;
     int grid = g->sm_count;
     if (units < grid) grid = (int)units;
     IHTB_CHECK(g->p < (int64_t(1) << 31) - 256, IHTB_EDIM, "more than 2^31 SNP columns on one GPU");
-    IHTB_LAUNCH((k_sweep_lut<16, 2, QUAD, H2>), grid, 17 * 32, LUT_SMEM_BYTES, s, g->bed.p, g->cs_j, g->cs_s, g->p4, g->p,
-                g->n, n_slabs, d_v, d_v1, d_vbar, d_scale, d_part, (uint32_t)LUT_SMEM_BYTES);
+    IHTB_LAUNCH((k_sweep_lut<16, 2, QUAD, H2, TERN>), grid, 17 * 32, LUT_SMEM_BYTES, s, TERN ? g->tern.p : g->bed.p, g->cs_j,
+                g->cs_s, g->p4, g->p, g->n, n_slabs, d_v, d_v1, d_vbar, d_scale, d_part, (uint32_t)LUT_SMEM_BYTES);
 }
 
 // FAST sweep, one right-hand side: d_part is [n_slabs][p] floats
@@ -258,7 +265,8 @@ void sweep_fast_partials(const ihtb_geno* g, const double* d_v, const double* d_
                          cudaStream_t s) {
     if (n_slabs_out) *n_slabs_out = sweep_fast_num_slabs(g);
     if (sweep_tmem_enabled(g)) { sweep_tmem_partials(g, d_v, d_vbar, d_part, s); return; }
-    if (g->quad) launch_lut<true, false>(g, d_v, nullptr, d_vbar, nullptr, d_part, s);
+    if (sweep_uses_tern(g)) launch_lut<true, false, true>(g, d_v, nullptr, d_vbar, nullptr, d_part, s);
+    else if (g->quad) launch_lut<true, false>(g, d_v, nullptr, d_vbar, nullptr, d_part, s);
     else launch_lut<false, false>(g, d_v, nullptr, d_vbar, nullptr, d_part, s);
 }
 
@@ -272,7 +280,8 @@ void sweep_pair_partials(const ihtb_geno* g, const double* d_v0, const double* d
                          const float* d_scale, float* d_part, cudaStream_t s) {
     IHTB_CHECK(g->cs_j == 128, IHTB_EUNSUPPORTED, "the pair sweep needs a tiled layout");
     if (sweep_tmem_enabled(g)) { sweep_tmem_pair_partials(g, d_v0, d_v1, d_vbar, d_scale, d_part, s); return; }
-    if (g->quad) launch_lut<true, true>(g, d_v0, d_v1, d_vbar, d_scale, d_part, s);
+    if (sweep_uses_tern(g)) launch_lut<true, true, true>(g, d_v0, d_v1, d_vbar, d_scale, d_part, s);
+    else if (g->quad) launch_lut<true, true>(g, d_v0, d_v1, d_vbar, d_scale, d_part, s);
     else launch_lut<false, true>(g, d_v0, d_v1, d_vbar, d_scale, d_part, s);
 }
 

@@ -299,6 +299,8 @@ def bench_sharded(args, rank, world, local_rank, G):
         peak, peak_src = G["measured_peak"]()
         abytes = G["sweep_bytes"](n, p_local)
         achieved = abytes / (float(tk.item()) * 1e-3) / 1e9
+        stream_b, ternary = g.sweep_stream_bytes()
+        sbytes = stream_b + 8 * n + 24 * p_local
         nz = np.flatnonzero(beta)
         line = {
             # weak scaling: every rank sweeps its own 500k-SNP shard each iteration, so the job processes
@@ -314,7 +316,10 @@ def bench_sharded(args, rank, world, local_rank, G):
             "packed_bytes_swept_per_sec_all_gpus": sweeps * G["sweep_bytes"](n, p) / t_value,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "k_sweep_lut (per GPU, slowest rank)",
-                         "algorithmic_bytes_per_launch": abytes, "kernel_ms": float(tk.item())},
+                         "algorithmic_bytes_per_launch": abytes, "kernel_ms": float(tk.item()),
+                         "streamed_bytes_per_launch": sbytes, "streamed_gbs": sbytes / (float(tk.item()) * 1e-3) / 1e9,
+                         "streamed_frac": sbytes / (float(tk.item()) * 1e-3) / 1e9 / peak,
+                         "stream_encoding": "ternary copy: 5 dosages per byte, lossless" if ternary else "PLINK 2-bit tiles"},
             "e2e": {"value": world * e_iters / t_e2e, "unit": G["UNIT"], "global_iterations_per_sec": e_iters / t_e2e,
                     "h2d_bytes_per_step": int(y.nbytes + z.nbytes),
                     "d2h_bytes_per_step": int(beta.nbytes + c.nbytes), "ms_per_step": t_e2e / args.steps * 1e3,

@@ -88,13 +88,57 @@ def test_xt_v_exact_and_fast(layout, n, p, miss):
         assert np.all(g.xt_v(zero, m.SWEEP_PAIR) == 0.0)
 
 
+@pytest.mark.parametrize("n,p,miss", [(1003, 513, 0.01), (640, 9, 0.0), (641, 130, 0.3), (3200, 257, 0.0), (50, 4, 0.0),
+                                      (12801, 1030, 0.002)])
+def test_ternary_copy_sweeps(n, p, miss):
+    """The FAST / PAIR sweeps stream a ternary copy of the tiles (five dosages per byte, 640 samples per 128-byte chunk,
+    common.cuh): same error bounds against the oracle as the 2-bit stream, everything else reads the PLINK codes."""
+    bed = synth.packed_columns(6, n, np.arange(p), miss)
+    o = snp.SnpLinAlgOracle(bed, n)
+    hs = {}
+    for flag in ("1", "0"):
+        os.environ["IHTB_TERN"] = flag
+        try:
+            hs[flag] = m.B200SnpLinAlg.from_bed_columns(bed, n)
+        finally:
+            os.environ.pop("IHTB_TERN", None)
+    p4 = (p + 3) // 4 * 4
+    assert hs["1"].sweep_stream_bytes() == (-(-n // 640) * 128 * p4, True)
+    assert hs["0"].sweep_stream_bytes() == (-(-n // 512) * 128 * p4, False)
+    rng = np.random.default_rng(1)
+    V = rng.normal(size=(n, 3)) * np.array([1.0, 40.0, 1e-3]) + np.array([0.3, -2.0, 0.0])
+    want = o.xt_v(V)
+    dos = snp.dosages(bed, n)
+    gn = np.maximum(np.sqrt((np.where(np.isnan(dos), 0.0, dos) ** 2).sum(axis=0)), 1.0)
+    for flag, g in hs.items():
+        assert np.array_equal(g.packed(), bed) and np.array_equal(g.decode(), o.dense())
+        for t in range(3):
+            u = V[:, t] - V[:, t].mean()
+            tiny = 1e-12 * np.abs(want[:, t]).max()
+            fa = g.xt_v(V[:, t], m.SWEEP_FAST)
+            assert np.all(np.abs(fa - want[:, t]) <= (2.0 ** -18) * np.abs(u).sum() * o.sigma_inv + tiny), (flag, t)
+            assert np.all(np.abs(fa - want[:, t]) <= (2.0 ** -20) * np.sqrt((u ** 2).sum()) * o.sigma_inv * gn + tiny), (flag, t)
+        got = g.xt_v(V, m.SWEEP_PAIR)
+        for t in range(3):
+            u = V[:, t] - V[:, t].mean()
+            bnd = (3.1 * 2.0 ** -11 if t < 2 else 2.0 ** -20) * np.sqrt((u ** 2).sum()) * o.sigma_inv * gn
+            assert np.all(np.abs(got[:, t] - want[:, t]) <= bnd + 1e-12 * np.abs(want[:, t]).max()), (flag, t)
+    assert np.array_equal(hs["1"].xt_v(V, m.SWEEP_EXACT), hs["0"].xt_v(V, m.SWEEP_EXACT))     # FP64 path: the PLINK tiles
+    for g in hs.values():
+        g.close()
+
+
 def test_tensor_memory_sweep_matches_stage_ring():
     """IHTB_SWEEP_TMEM=1: the genotype stream staged through tensor memory (tcgen05.cp / tcgen05.ld, sweep_tmem.cu).
     Same tables, same butterfly, same partial sums per slab: results identical to the default kernel, FAST and PAIR,
     including ragged n and a column count that is not a multiple of the 256-column unit."""
     for n, p, miss in [(1003, 513, 0.01), (5000, 3001, 0.0), (600, 7, 0.2)]:
         bed = synth.packed_columns(5, n, np.arange(p), miss)
-        g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+        os.environ["IHTB_TERN"] = "0"           # both kernels on the 2-bit tiles (the TMEM variant has no ternary form)
+        try:
+            g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+        finally:
+            os.environ.pop("IHTB_TERN", None)
         V = np.random.default_rng(2).normal(size=(n, 2)) * np.array([1.0, 30.0]) + 0.3
         want_f, want_p = g.xt_v(V[:, 0], m.SWEEP_FAST), g.xt_v(V, m.SWEEP_PAIR)
         os.environ["IHTB_SWEEP_TMEM"] = "1"
