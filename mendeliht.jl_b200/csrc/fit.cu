@@ -333,6 +333,7 @@ struct ihtb_fit {
         IHTB_CUDA(cudaMemcpyAsync(h_scal.p, d_scal.p, (2 + q) * sizeof(double), cudaMemcpyDeviceToHost, s));
         IHTB_CUDA(cudaEventRecord(ev0, s));
         sweep_coef = cfg.sweep_mode == IHTB_SWEEP_FAST ? kFastBound : kExactBound;
+        const double t_sw = now();
         if (pairer && cfg.sweep_mode == IHTB_SWEEP_FAST) {
             IHTB_CHECK(!grouped() && !comm, IHTB_EUNSUPPORTED, "paired sweeps serve plain single-device fits only");
             if (pairer->sweep(pair_slot, g, d_r.p, d_vbar.p, d_dfa.p, s, sweep_scratch)) {
@@ -345,7 +346,10 @@ struct ihtb_fit {
         }
         IHTB_CUDA(cudaEventRecord(ev1, s));
         ++n_sweeps;
+        const double t_sel = now();
+        dbg[0] += t_sel - t_sw;
         select_rescore(/*rerun=*/false);
+        dbg[1] += now() - t_sel;
     }
 
     // Candidate selection + exact re-scoring for the CURRENT idx against the last sweep's df (see score_and_sweep).
@@ -412,9 +416,12 @@ struct ihtb_fit {
             IHTB_CUDA(cudaMemcpyAsync(h_sel.p, d_sel.p, (2 + glaunch) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
             IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_gout.p, (glaunch + nsupp) * sizeof(double), cudaMemcpyDeviceToHost, s));
             sync();
+            const double t_host = now();
+            struct Acc { double& a; double t0; ~Acc() { a += now() - t0; } } acc_host{dbg[2], t_host};
             if (fused) adopt_winner();
             const TopkState* st = reinterpret_cast<const TopkState*>(h_sel.p);
             const int count = cfg.k > 0 ? st->count : 0;
+            dbg[3] += (double)std::min(count, glaunch);
             if (count > cap && coef == kPairBound && !rerun) {
                 // the looser bound of the PAIR sweep admits more columns than can be re-scored: sweep this residual
                 // alone with the FP32 tables and select again (results never depend on which sweep served them)
@@ -1060,6 +1067,9 @@ struct ihtb_fit {
     // ---- iht_one_step! (src/fit.jl:213-263) --------------------------------------------------------
     // host wall-clock per phase (seconds): stepsize, gradstep, xb + glm, score + sweep (ihtb_fit_phase_times)
     double phase[4] = {0, 0, 0, 0};
+    // finer split for IHTB_CV_TIMING (multi.cu): [0] inside the sweep call (pairing wait included), [1] select_rescore,
+    // [2] of that: host work after the read-back, [3] candidates re-scored, [4] init, [5] predict
+    double dbg[6] = {0, 0, 0, 0, 0, 0};
     static double now() {
         return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     }
@@ -1570,6 +1580,13 @@ int32_t ihtb_fit_phase_times(const ihtb_fit* f, double* out4) {
         IHTB_CHECK(f && out4, IHTB_EINVAL, "NULL argument");
         for (int i = 0; i < 4; ++i) out4[i] = f->phase[i];
     });
+}
+
+// (C linkage, internal: multi.cu) debug split of the score + sweep phase, see ihtb_fit::dbg
+void ihtb_internal_fit_debug(const ihtb_fit* f, double* out8) {
+    for (int i = 0; i < 6; ++i) out8[i] = f->dbg[i];
+    out8[6] = f->sweep_ms_total * 1e-3;
+    out8[7] = (double)f->n_sweeps;
 }
 
 // (C linkage, internal: multi.cu) two fits of one device share their sweeps; pairer == NULL detaches

@@ -9,6 +9,7 @@
 #include "comm.cuh"
 #include "pairer.cuh"
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <functional>
@@ -382,6 +383,7 @@ int32_t ihtb_mmvfit_destroy(ihtb_mmvfit* f) {
 // applies meanloss (:304-320).  IHTB_CV_PAIR=0 runs one fit at a time per device.
 extern "C" void ihtb_internal_fit_set_pairer(ihtb_fit* f, void* pairer, int slot);
 extern "C" void ihtb_internal_next_fit_min_cap(int cap);
+extern "C" void ihtb_internal_fit_debug(const ihtb_fit* f, double* out8);
 
 static int32_t cv_farm(const std::vector<ihtb_geno*>& parts, const std::vector<int>& devices, int64_t n, int64_t p,
                        const double* y, const double* z, int64_t q, const uint8_t* zkeep, const ihtb_cfg* cfg,
@@ -428,6 +430,8 @@ static int32_t cv_farm(const std::vector<ihtb_geno*>& parts, const std::vector<i
     std::vector<int> wdev((size_t)nworkers);
     for (int w = 0; w < nworkers; ++w) wdev[(size_t)w] = devices[(size_t)(w / per_dev)];
     std::vector<double> wbusy((size_t)nworkers, 0.0);
+    std::vector<std::array<double, 3>> wphase((size_t)nworkers, std::array<double, 3>{0, 0, 0});     // init, run, predict
+    const bool report = getenv("IHTB_CV_TIMING") != nullptr;
     rc = on_all_ranks(nworkers, wdev, nullptr, [&](int w) -> int32_t {
         const int d = w / per_dev, slot = w % per_dev;
         SweepPairer* pr = per_dev == 2 ? pairers[(size_t)d].get() : nullptr;
@@ -452,15 +456,33 @@ static int32_t cv_farm(const std::vector<ihtb_geno*>& parts, const std::vector<i
             ihtb_result res;
             double dev = 0.0;
             e = ihtb_fit_set_k(f, path[t]);
+            const auto ta = std::chrono::steady_clock::now();
             if (e == IHTB_OK) e = ihtb_fit_init(f, train.data());
+            const auto tb = std::chrono::steady_clock::now();
             if (e == IHTB_OK) e = ihtb_fit_run(f, &res, nullptr, 0);
+            const auto tc = std::chrono::steady_clock::now();
             if (e == IHTB_OK) e = ihtb_fit_predict(f, test.data(), &dev);
+            const auto td = std::chrono::steady_clock::now();
+            wphase[(size_t)w][0] += std::chrono::duration<double>(tb - ta).count();
+            wphase[(size_t)w][1] += std::chrono::duration<double>(tc - tb).count();
+            wphase[(size_t)w][2] += std::chrono::duration<double>(td - tc).count();
             if (e == IHTB_OK) {
                 mses[i] = dev;
                 if (iters) iters[i] = res.iter;
             }
         }
         wbusy[(size_t)w] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (report && f) {
+            double ph[4] = {0, 0, 0, 0}, dg[8] = {0};
+            ihtb_fit_phase_times(f, ph);
+            ihtb_internal_fit_debug(f, dg);
+            fprintf(stderr, "[cv worker %d] busy %.3f s: init %.3f run %.3f predict %.3f | run phases: stepsize %.3f gradstep %.3f "
+                    "xb+glm %.3f score+sweep %.3f | sweep call (incl. pairing wait) %.3f, select+rescore %.3f (host part %.3f), "
+                    "sweep kernels %.3f s over %.0f sweeps, %.0f candidates re-scored; pair sweeps %lld solo %lld\n",
+                    w, wbusy[(size_t)w], wphase[(size_t)w][0], wphase[(size_t)w][1], wphase[(size_t)w][2], ph[0], ph[1], ph[2],
+                    ph[3], dg[0], dg[1], dg[2], dg[6], dg[7], dg[3], pr ? (long long)pr->n_pair : 0LL,
+                    pr ? (long long)pr->n_solo : 0LL);
+        }
         if (pr) pr->leave();                          // the partner sweeps alone from now on (also on an error)
         if (e != IHTB_OK) {
             stop.store(true);
