@@ -167,6 +167,10 @@ int32_t ihtb_fit_init_beta(ihtb_fit* f, const uint8_t* train_mask);
 int32_t ihtb_fit_run(ihtb_fit* f, ihtb_result* result, ihtb_iter_trace* trace, int64_t trace_cap);   /* fit_iht! + pve */
 /* any pointer may be NULL; beta[p], c[q], mu[n], xb[n] */
 int32_t ihtb_fit_get(const ihtb_fit* f, double* beta, double* c, double* mu, double* xb);
+/* The same model as (global column, coefficient) pairs in column order: *nnz of them exist, at most cap are written
+ * (idx / val may be NULL to ask for the count).  For callers that hold a zero-initialised beta[p] (IHTResult.beta is dense,
+ * src/data_structures.jl:245-258): scattering k entries replaces writing p doubles. */
+int32_t ihtb_fit_get_sparse(const ihtb_fit* f, int64_t* idx, double* val, int64_t cap, int64_t* nnz);
 int32_t ihtb_fit_predict(ihtb_fit* f, const uint8_t* test_mask, double* deviance);   /* predict! (src/cross_validation.jl:279-286) */
 /* CUDA-event stopwatch on the fit's stream: which=0 start, which=1 stop (elapsed device milliseconds in *ms) */
 int32_t ihtb_fit_timer(ihtb_fit* f, int32_t which, double* ms);
@@ -234,6 +238,7 @@ int32_t ihtb_mfit_set_k(ihtb_mfit* f, int64_t k);
 int32_t ihtb_mfit_init(ihtb_mfit* f, const uint8_t* train_mask, int32_t init_beta);
 int32_t ihtb_mfit_run(ihtb_mfit* f, ihtb_result* result, ihtb_iter_trace* trace, int64_t trace_cap);
 int32_t ihtb_mfit_get(const ihtb_mfit* f, double* beta, double* c, double* mu, double* xb);
+int32_t ihtb_mfit_get_sparse(const ihtb_mfit* f, int64_t* idx, double* val, int64_t cap, int64_t* nnz);
 int32_t ihtb_mfit_predict(ihtb_mfit* f, const uint8_t* test_mask, double* deviance);
 int32_t ihtb_mfit_timer(ihtb_mfit* f, int32_t which, double* ms);     /* slowest device's CUDA-event time */
 int32_t ihtb_mfit_destroy(ihtb_mfit* f);

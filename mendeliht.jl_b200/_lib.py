@@ -97,6 +97,7 @@ SIGNATURES = {
     "ihtb_fit_init_beta": [_p, _u8],
     "ihtb_fit_run": [_p, C.POINTER(Result), C.POINTER(IterTrace), C.c_int64],
     "ihtb_fit_get": [_p, _f64, _f64, _f64, _f64],
+    "ihtb_fit_get_sparse": [_p, C.POINTER(C.c_int64), _f64, C.c_int64, C.POINTER(C.c_int64)],
     "ihtb_fit_predict": [_p, _u8, _f64],
     "ihtb_fit_timer": [_p, C.c_int32, _f64],
     "ihtb_fit_phase_times": [_p, _f64],
@@ -132,6 +133,7 @@ SIGNATURES = {
     "ihtb_mfit_init": [_p, _u8, C.c_int32],
     "ihtb_mfit_run": [_p, C.POINTER(Result), C.POINTER(IterTrace), C.c_int64],
     "ihtb_mfit_get": [_p, _f64, _f64, _f64, _f64],
+    "ihtb_mfit_get_sparse": [_p, C.POINTER(C.c_int64), _f64, C.c_int64, C.POINTER(C.c_int64)],
     "ihtb_mfit_predict": [_p, _u8, _f64],
     "ihtb_mfit_timer": [_p, C.c_int32, _f64],
     "ihtb_mfit_destroy": [_p],

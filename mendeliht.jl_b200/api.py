@@ -365,10 +365,17 @@ class IHTVariable:
         return res, trace
 
     def get(self, mu=False, xb=False):
-        beta = np.empty(self.p); c = np.empty(self.q)
+        # beta is dense like IHTResult.beta, but only its k entries are written: zero pages from calloc + a scatter
+        # (p = 4M at 8 GPUs would otherwise cost a 32 MB fill per fit)
+        nnz = C.c_int64(0)
+        check(self._fn("get_sparse")(self._h, None, None, 0, C.byref(nnz)))
+        idx = np.empty(max(nnz.value, 1), dtype=np.int64); val = np.empty(max(nnz.value, 1))
+        check(self._fn("get_sparse")(self._h, ptr(idx, C.c_int64), ptr(val, C.c_double), nnz.value, C.byref(nnz)))
+        beta = np.zeros(self.p); c = np.empty(self.q)
+        beta[idx[:nnz.value]] = val[:nnz.value]
         m = np.empty(self.n) if mu else None
         x = np.empty(self.n) if xb else None
-        check(self._fn("get")(self._h, ptr(beta, C.c_double), ptr(c, C.c_double),
+        check(self._fn("get")(self._h, None, ptr(c, C.c_double),
                               ptr(m, C.c_double) if mu else None, ptr(x, C.c_double) if xb else None))
         return beta, c, m, x
 

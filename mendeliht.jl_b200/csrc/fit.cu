@@ -1538,6 +1538,19 @@ int32_t ihtb_fit_get(const ihtb_fit* f, double* beta, double* c, double* mu, dou
     });
 }
 
+// The model as (global column, coefficient) pairs in column order: *nnz entries exist, at most cap are written.  A caller
+// holding a zeroed beta[p] (calloc) scatters them itself instead of having p doubles written (32 MB at p = 4M).
+int32_t ihtb_fit_get_sparse(const ihtb_fit* f, int64_t* idx, double* val, int64_t cap, int64_t* nnz) {
+    return guard([&] {
+        IHTB_CHECK(f && nnz, IHTB_EINVAL, "NULL argument");
+        *nnz = (int64_t)f->best_idx.size();
+        for (size_t t = 0; t < f->best_idx.size() && (int64_t)t < cap; ++t) {
+            if (idx) idx[t] = f->best_idx[t];
+            if (val) val[t] = f->best_b[t];
+        }
+    });
+}
+
 int32_t ihtb_fit_predict(ihtb_fit* f, const uint8_t* test_mask, double* deviance) {
     return guard([&] {
         IHTB_CHECK(f && deviance, IHTB_EINVAL, "NULL argument");

@@ -260,6 +260,10 @@ int32_t ihtb_mfit_get(const ihtb_mfit* f, double* beta, double* c, double* mu, d
     cudaSetDevice(f->g->devices[0]);
     return ihtb_fit_get(f->fits[0], beta, c, mu, xb);
 }
+int32_t ihtb_mfit_get_sparse(const ihtb_mfit* f, int64_t* idx, double* val, int64_t cap, int64_t* nnz) {
+    if (!f) { set_last_error("NULL fit handle"); return IHTB_EINVAL; }
+    return ihtb_fit_get_sparse(f->fits[0], idx, val, cap, nnz);
+}
 // device-time stopwatch around a group of calls: which = 0 starts on every rank, 1 stops; *ms = the slowest rank
 int32_t ihtb_mfit_timer(ihtb_mfit* f, int32_t which, double* ms) {
     double t[P2P_MAX_RANKS] = {};
