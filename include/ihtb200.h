@@ -136,6 +136,10 @@ int32_t ihtb_sweep_bench(const ihtb_geno* g, int32_t sweep_mode, int32_t warmup,
  * holds the ternary copy (five dosages per byte, built at creation when memory allows; IHTB_TERN=0/1 forces), else
  * p * ceil(n/512) * 128 (the PLINK 2-bit tiles).  The algorithmic figure of SURVEY.md 8d stays p * ceil(n/4). */
 int32_t ihtb_geno_sweep_stream_bytes(const ihtb_geno* g, int64_t* bytes, int32_t* ternary);
+/* Diagnostic / bench: exact FP64 column dots X[:, cols]' v (the re-scoring of top-k candidates) for ncols columns through
+ * the nibble-table kernel every univariate fit uses: average device time per call, and the largest difference to the
+ * per-column decode kernel relative to the largest value. */
+int32_t ihtb_gather_bench(const ihtb_geno* g, int64_t ncols, int32_t reps, double* ms_per_call, double* max_rel_diff);
 int32_t ihtb_geno_destroy(ihtb_geno* g);
 
 /* ---- univariate fit (fit_iht / fit_iht! / init_iht_indices!, src/fit.jl:60-207, src/utilities.jl:366-438) ---- */

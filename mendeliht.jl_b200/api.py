@@ -95,6 +95,12 @@ class B200SnpLinAlg:
     def shape(self):
         return (self.n, self.p)
 
+    def gather_bench(self, ncols: int, reps: int = 5):
+        """(ms per exact re-scoring of `ncols` columns, max difference to the per-column kernel / max |value|)"""
+        ms, err = C.c_double(0.0), C.c_double(0.0)
+        check(load().ihtb_gather_bench(self._h, int(ncols), int(reps), C.byref(ms), C.byref(err)))
+        return float(ms.value), float(err.value)
+
     def sweep_stream_bytes(self):
         """(bytes of packed genotypes one FAST / PAIR sweep reads from HBM, ternary copy in use?)"""
         b, t = C.c_int64(0), C.c_int32(0)

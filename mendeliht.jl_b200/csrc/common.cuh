@@ -234,7 +234,8 @@ void x_support(const ihtb_geno* g, const int64_t* d_idx_local, int64_t k, const 
                double* d_out, cudaStream_t s);
 void xt_gather(const ihtb_geno* g, const int64_t* d_cols_local, int64_t ncols, const double* d_v, int64_t m,
                const double* d_vsum /*[m] device*/, double* d_out /*[ncols*m]*/, cudaStream_t s);
-// blocked = true: the kernel for long lists (residual chunk staged once per CTA); same value per column whatever the list
+// m = 1 takes the nibble-table kernel whatever the list length (a column's value never depends on the list); `blocked`
+// is kept for source compatibility and ignored
 void xt_gather2(const ihtb_geno* g, const int64_t* d_cols_a, int64_t n_a, const int64_t* d_cols_b, int64_t n_b,
                 const double* d_v, int64_t m, const double* d_vsum, double* d_out, cudaStream_t s, bool blocked = false);
 

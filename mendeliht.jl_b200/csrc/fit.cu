@@ -313,7 +313,7 @@ struct ihtb_fit {
         for (size_t t = 0; t < need.size(); ++t) loc[t] = is_local(need[t]) ? need[t] - j0 : -1;
         upload(d_cols.p, loc.data(), loc.size());
         xt_gather2(g, d_cols.p, (int64_t)need.size(), nullptr, 0, d_r.p, 1, d_vbar.p, d_gout.p, s,
-                   /*blocked=*/pairer != nullptr);                              // d_vbar = mean(r), set by score
+                   false);                              // d_vbar = mean(r), set by score
         if (exchange) comm_allreduce_sum_f64(comm, d_gout.p, need.size(), s);
         IHTB_CUDA(cudaMemcpyAsync(h_gout.p, d_gout.p, need.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
         sync();
@@ -391,7 +391,7 @@ struct ihtb_fit {
         }
         if (nsupp && !fused) upload(d_cols.p, supp_loc.data(), supp_loc.size());
         // candidates (slots beyond the count hold -1) and the current support re-scored exactly in ONE launch
-        xt_gather2(g, tk.cand, glaunch, d_supp, nsupp, d_r.p, 1, d_vbar.p, d_gout.p, s, /*blocked=*/pairer != nullptr);
+        xt_gather2(g, tk.cand, glaunch, d_supp, nsupp, d_r.p, 1, d_vbar.p, d_gout.p, s);
         // the next iteration's step-size denominator ||sqrt(W) (X[:,idx] df[idx] + Z[:,idc] df2[idc])||^2 needs nothing
         // from the host either: the support's exact df values are in d_gout, df2 is in d_scal (src/utilities.jl:728-756)
         denom_ready = false;

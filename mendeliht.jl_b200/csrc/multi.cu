@@ -412,7 +412,7 @@ static int32_t cv_farm(const std::vector<ihtb_geno*>& parts, const std::vector<i
     const int nd = (int)devices.size();
     // Pairing pays while the PAIR sweep's looser error bound (3.1 * 2^-11 ||u||_2 sgn_j, about 0.0023 sqrt(n) null
     // standard deviations of a gradient entry) keeps the list of columns to re-score within a few thousand (they are
-    // re-scored by the blocked gather kernel, support.cu): on by default up to n = 131072 samples (0.8 standard
+    // re-scored by the nibble-table gather kernel, support.cu): on by default up to n = 131072 samples (0.8 standard
     // deviations); IHTB_CV_PAIR=1 forces it (a fit whose list overflows re-sweeps alone), IHTB_CV_PAIR=0 disables it.
     const char* pe = getenv("IHTB_CV_PAIR");                  // read per call: tests switch it
     const int pair_env = pe ? atoi(pe) : -1;

@@ -189,55 +189,70 @@ __global__ void k_xt_gather_fin(GenoView gv, const int64_t* __restrict__ cols, i
     out[c + (int64_t)t * ncols] = __dmul_rn(gv.sinv[j], __dadd_rn(at, __dmul_rn(gv.mu[j], corr)));
 }
 
-// Blocked form for LONG column lists (thousands of candidates: lock-step paired cross-validation fits, whose PAIR sweep
-// has a looser error bound).  k_xt_gather reads the right-hand side once per column (8 bytes per sample against 0.25
-// bytes of genotype), which is what limits it beyond a few hundred columns.  Here a CTA stages the centred vector of one
-// 4096-sample chunk in shared memory once -- transposed, us[s][w] = u[16 w + s], so that the 32 lanes of a warp read
-// consecutive doubles -- and its 8 warps then walk the whole column list: per column and chunk a lane decodes 8 packed
-// words (128 genotypes) against the staged vector.  Same outputs as k_xt_gather (dosage dot, sum over missing samples)
-// per (column, chunk); k_xt_gather_fin adds the chunks in order.
-constexpr int XB_CHUNK = 4096;                 // samples per chunk: 1024 packed bytes = 256 words per column
+// Single right-hand side (every univariate fit): nibble tables.  A CTA owns one 512-sample chunk (one packed word per lane
+// of a column) and builds, from the centred vector, T[k][nib][l] = dos(nib & 3) u[16 l + 2 k] + dos(nib >> 2) u[16 l + 2 k + 1]
+// (k-th pair of samples of word l; code 01 = missing counts 0 here) -- 8 x 16 x 32 doubles = 32 KB, lane l reads bank pair l
+// whatever the data.  Its 8 warps then walk the column list: per column and chunk a lane needs one 32-bit load, 8 table
+// lookups and 8 FP64 adds for 16 genotypes, against ~13 instructions per genotype for a decode-and-select loop (the
+// per-column kernel above also re-reads the vector for every column: 8 n bytes each from L2).  Measured at n = 500k,
+// ~300 columns: 122 us -> see profiles/r2_gather_nibble.txt.  The sum over a column's MISSING samples that imputation
+// needs comes from the handle's CSR list in the finalisation kernel, like in the sweep epilogue.
+// One kernel for every list length, paired or solo fit, any number of shards: a column's value never depends on them.
+constexpr int XN_CHUNK = 512;
 __global__ void __launch_bounds__(256)
-k_xt_gather_blocked(GenoView gv, const int64_t* __restrict__ cols, int64_t n_a, const int64_t* __restrict__ cols_b,
-                    int64_t ncols, const double* __restrict__ v, const double* __restrict__ vbar,
-                    double* __restrict__ part /*[ncols][nchunks][2]*/) {
-    __shared__ double us[16][XB_CHUNK / 16];                       // 32 KB
+k_xt_gather_nib(GenoView gv, const int64_t* __restrict__ cols, int64_t n_a, const int64_t* __restrict__ cols_b,
+                int64_t ncols, const double* __restrict__ v, const double* __restrict__ vbar,
+                double* __restrict__ part /*[ncols][nchunks]*/) {
+    __shared__ double T[8][16][32];                                 // 32 KB
     const int64_t n = gv.n;
     const int64_t chunk = blockIdx.x, nchunks = gridDim.x;
-    const int64_t i0 = chunk * XB_CHUNK;
-    const double vb = vbar[0];
-    for (int e = threadIdx.x; e < XB_CHUNK; e += blockDim.x) {
-        const int64_t i = i0 + e;
-        us[e & 15][e >> 4] = (i < n) ? __dsub_rn(v[i], vb) : 0.0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        const double vb = vbar[0];
+        const int64_t i0 = chunk * XN_CHUNK + 16 * lane + 2 * warp;             // thread (k = warp, l = lane) builds 16 rows
+        const double u0 = (i0 < n) ? __dsub_rn(v[i0], vb) : 0.0;
+        const double u1 = (i0 + 1 < n) ? __dsub_rn(v[i0 + 1], vb) : 0.0;
+        const double d0[4] = {0.0, 0.0, u0, __dadd_rn(u0, u0)};
+        const double d1[4] = {0.0, 0.0, u1, __dadd_rn(u1, u1)};
+#pragma unroll
+        for (int nib = 0; nib < 16; ++nib) T[warp][nib][lane] = __dadd_rn(d0[nib & 3], d1[nib >> 2]);
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t w0 = chunk * (XB_CHUNK / 16);                     // first packed word of this chunk in a column
-    const int64_t nwords = (gv.nbytes + 3) >> 2;
+    const int64_t w = chunk * (XN_CHUNK / 16) + lane;               // this lane's packed word of a column
+    const bool in_col = w < ((gv.nbytes + 3) >> 2);                 // bytes past nbytes inside a word are zero padding
     for (int64_t c = (int64_t)blockIdx.y * 8 + warp; c < ncols; c += (int64_t)gridDim.y * 8) {
         const int64_t j = c < n_a ? cols[c] : cols_b[c - n_a];
         if (j < 0) continue;                                        // unused slot / column of another shard
-        double a = 0.0, mm = 0.0;
+        const uint32_t x = in_col ? *reinterpret_cast<const uint32_t*>(gv_ptr(gv, j, 4 * w)) : 0u;
+        double a = 0.0;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int wl = lane + 32 * t;                           // word within the chunk
-            if (w0 + wl >= nwords) continue;
-            uint32_t x = *reinterpret_cast<const uint32_t*>(gv_ptr(gv, j, 4 * (w0 + wl)));
-            if (x == 0u) continue;
-#pragma unroll
-            for (int sgl = 0; sgl < 16; ++sgl) {
-                const uint32_t code = (x >> (2 * sgl)) & 3u;
-                if (code == 0u) continue;
-                const double u = us[sgl][wl];
-                if (code == 1u) mm = __dadd_rn(mm, u);
-                else a = __dadd_rn(a, (code == 3u) ? __dadd_rn(u, u) : u);
-            }
-        }
-        a = warp_sum(a); mm = warp_sum(mm);
-        if (lane == 0) {
-            double* o = part + (c * nchunks + chunk) * 2;
-            o[0] = a; o[1] = mm;
-        }
+        for (int k = 0; k < 8; ++k) a = __dadd_rn(a, T[k][(x >> (4 * k)) & 15u][lane]);
+        a = warp_sum(a);
+        if (lane == 0) part[c * nchunks + chunk] = a;
+    }
+}
+
+// one warp per column: lane l adds chunks l, l + 32, ... in order and its share of the column's missing samples (CSR),
+// the lanes are combined by a fixed butterfly
+__global__ void __launch_bounds__(128)
+k_xt_gather_fin_nib(GenoView gv, const int64_t* __restrict__ miss_ptr, const int32_t* __restrict__ miss_idx,
+                    const int64_t* __restrict__ cols, int64_t n_a, const int64_t* __restrict__ cols_b, int64_t ncols,
+                    int nchunks, const double* __restrict__ v, const double* __restrict__ vbar,
+                    const double* __restrict__ part, double* __restrict__ out) {
+    const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= ncols) return;
+    const int64_t jc = c < n_a ? cols[c] : cols_b[c - n_a];
+    if (jc < 0) { if (lane == 0) out[c] = 0.0; return; }
+    double at = 0.0, mt = 0.0;
+    for (int sp = lane; sp < nchunks; sp += 32) at = __dadd_rn(at, part[c * nchunks + sp]);
+    const double vb = vbar[0];
+    if (gv.impute)
+        for (int64_t e = miss_ptr[jc] + lane; e < miss_ptr[jc + 1]; e += 32) mt = __dadd_rn(mt, __dsub_rn(v[miss_idx[e]], vb));
+    at = warp_sum(at); mt = warp_sum(mt);
+    if (lane == 0) {
+        const double corr = gv.impute ? mt : __dmul_rn(-vb, (double)gv.nmiss[jc]);
+        out[c] = __dmul_rn(gv.sinv[jc], __dadd_rn(at, __dmul_rn(gv.mu[jc], corr)));
     }
 }
 
@@ -258,21 +273,19 @@ static void launch_xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t 
                              int64_t ncols, const double* d_v, const double* d_vbar, double* d_out, cudaStream_t s,
                              bool blocked) {
     DBuf<double>& sc = gather_scratch(s);
-    if (M == 1 && blocked) {
-        // the caller's choice, never the list length: a fit must get the same bits for a column whether its list is long
-        // or short (paired or solo sweep), so every fit of a paired cross-validation grid takes this kernel throughout
-        // long lists: the blocked kernel (samples beyond the last byte of a column are zero padding: words are read whole)
-        const int nchunks = (int)ceil_div(g->n, XB_CHUNK);
-        const size_t need_b = (size_t)ncols * nchunks * 2;
+    (void)blocked;
+    if (M == 1) {
+        const int nchunks = (int)ceil_div(g->n, XN_CHUNK);
+        const size_t need_b = (size_t)ncols * nchunks;
         if (sc.n < need_b) {
             IHTB_CUDA(cudaStreamSynchronize(s));
-            sc.alloc(need_b);
+            sc.alloc(need_b < 65536 ? 65536 : need_b);
         }
-        int groups = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(ncols, 8), (4 * g->sm_count) / nchunks + 1));
-        IHTB_LAUNCH(k_xt_gather_blocked, dim3((unsigned)nchunks, (unsigned)groups), 256, 0, s, geno_view(g), d_cols, n_a,
+        int groups = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(ncols, 8), (8 * g->sm_count) / nchunks + 1));
+        IHTB_LAUNCH(k_xt_gather_nib, dim3((unsigned)nchunks, (unsigned)groups), 256, 0, s, geno_view(g), d_cols, n_a,
                     d_cols_b, ncols, d_v, d_vbar, sc.p);
-        IHTB_LAUNCH((k_xt_gather_fin<1>), (unsigned)ceil_div(ncols, 128), 128, 0, s, geno_view(g), d_cols, n_a, d_cols_b,
-                    ncols, nchunks, d_vbar, sc.p, d_out);
+        IHTB_LAUNCH(k_xt_gather_fin_nib, (unsigned)ceil_div(ncols * 32, 128), 128, 0, s, geno_view(g), g->miss_ptr.p,
+                    g->miss_idx.p, d_cols, n_a, d_cols_b, ncols, nchunks, d_v, d_vbar, sc.p, d_out);
         return;
     }
     int64_t split_bytes = ceil_div(ceil_div(g->nbytes, XG_MAX_SPLIT), 256) * 256;
@@ -314,6 +327,57 @@ void xt_gather(const ihtb_geno* g, const int64_t* d_cols, int64_t ncols, const d
 }  // namespace ihtb
 
 using namespace ihtb;
+
+// Diagnostic / bench entry: exact column dots X[:, cols]' v for ncols columns (j_t = (t * 7919) mod p) through the
+// nibble-table kernel (what every univariate fit uses), timed, and checked against the per-column decode kernel
+// (run with two identical right-hand sides, which takes the other code path).  v is a fixed pseudo-random vector.
+__global__ void k_gb_fill(double* v, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        uint64_t h = (uint64_t)i * 0x9E3779B97F4A7C15ull + 12345ull;
+        h ^= h >> 31; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 29;
+        v[i] = (double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.4;
+        v[i + n] = v[i];
+    }
+}
+extern "C" int32_t ihtb_gather_bench(const ihtb_geno* g, int64_t ncols, int32_t reps, double* ms_per_call,
+                                     double* max_rel_diff) {
+    return guard([&] {
+        IHTB_CHECK(g && ncols >= 1 && reps >= 1, IHTB_EINVAL, "bad argument");
+        geno_require_ready(g);
+        IHTB_CUDA(cudaSetDevice(g->device));
+        cudaStream_t s;
+        IHTB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        std::vector<int64_t> hc((size_t)ncols);
+        for (int64_t t = 0; t < ncols; ++t) hc[(size_t)t] = (t * 7919) % g->p;
+        DBuf<int64_t> d_cols((size_t)ncols);
+        DBuf<double> d_v((size_t)(2 * g->n)), d_mean(2), d_a((size_t)ncols), d_b((size_t)(2 * ncols));
+        IHTB_CUDA(cudaMemcpyAsync(d_cols.p, hc.data(), (size_t)ncols * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        IHTB_LAUNCH(k_gb_fill, (unsigned)ceil_div(g->n, 256), 256, 0, s, d_v.p, g->n);
+        const double mean[2] = {0.1, 0.1};                       // any centring value: both kernels subtract the same one
+        IHTB_CUDA(cudaMemcpyAsync(d_mean.p, mean, sizeof(mean), cudaMemcpyHostToDevice, s));
+        xt_gather2(g, d_cols.p, ncols, nullptr, 0, d_v.p, 1, d_mean.p, d_a.p, s);            // warm-up (scratch)
+        cudaEvent_t e0, e1;
+        IHTB_CUDA(cudaEventCreate(&e0)); IHTB_CUDA(cudaEventCreate(&e1));
+        IHTB_CUDA(cudaEventRecord(e0, s));
+        for (int i = 0; i < reps; ++i) xt_gather2(g, d_cols.p, ncols, nullptr, 0, d_v.p, 1, d_mean.p, d_a.p, s);
+        IHTB_CUDA(cudaEventRecord(e1, s));
+        xt_gather2(g, d_cols.p, ncols, nullptr, 0, d_v.p, 2, d_mean.p, d_b.p, s);            // per-column decode kernel
+        std::vector<double> ha((size_t)ncols), hb((size_t)(2 * ncols));
+        IHTB_CUDA(cudaMemcpyAsync(ha.data(), d_a.p, ha.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        IHTB_CUDA(cudaMemcpyAsync(hb.data(), d_b.p, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        IHTB_CUDA(cudaStreamSynchronize(s));
+        float ms = 0.f;
+        IHTB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms_per_call) *ms_per_call = ms / reps;
+        double worst = 0.0, scale = 0.0;
+        for (int64_t t = 0; t < ncols; ++t) scale = std::max(scale, std::fabs(hb[(size_t)t]));
+        for (int64_t t = 0; t < ncols; ++t) worst = std::max(worst, std::fabs(ha[(size_t)t] - hb[(size_t)t]));
+        if (max_rel_diff) *max_rel_diff = scale > 0 ? worst / scale : worst;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        cudaStreamDestroy(s);
+    });
+}
 
 extern "C" int32_t ihtb_x_support(const ihtb_geno* g, const int64_t* idx, int64_t k, const double* coef, int64_t m,
                                   double* out) {

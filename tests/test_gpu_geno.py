@@ -254,3 +254,13 @@ def test_counts_maf_and_piecewise_ingest(tmp_path):
         bad = tmp_path / "bad.bed"
         bad.write_bytes(b"\x00\x00\x00" + bed[:2].tobytes())
         m.B200SnpLinAlg.from_bed_files([str(bad)], n)
+
+
+@pytest.mark.parametrize("n,p,miss,ncols", [(1003, 300, 0.05, 257), (5000, 64, 0.0, 64), (513, 40, 0.3, 9), (40000, 128, 0.001, 500)])
+def test_nibble_gather_matches_decode_kernel(n, p, miss, ncols):
+    """Exact re-scoring of candidate columns: the nibble-table kernel (one right-hand side, every univariate fit) against the
+    per-column decode kernel, with missing data (CSR imputation term) and ragged n."""
+    g = m.B200SnpLinAlg.synthetic(n, p, 77, miss)
+    ms, err = g.gather_bench(ncols, 1)
+    assert err <= 1e-13, err
+    g.close()
