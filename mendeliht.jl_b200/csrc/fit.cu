@@ -984,6 +984,7 @@ struct ihtb_fit {
         c.assign((size_t)q, 0.0); c0 = c; best_c = c; df2.assign((size_t)q, 0.0);
         idc.assign(zkeep.begin(), zkeep.end()); idc0 = idc;
         df_exact.clear(); dfs_idx.clear(); dfs_val.clear(); df_sparse = false;
+        last_bt = kMaxBatch;
         d_xb.zero(s);
         const uint8_t* dm = nullptr;
         if (train_mask) {
@@ -1081,6 +1082,8 @@ struct ihtb_fit {
     // coefficients add exact zeros; same blocks and reduction order), so results do not change -- only the number of
     // host<->device synchronisations per iteration (1 instead of 1 + #backtracks).
     static constexpr int kMaxBatch = 4;
+    static constexpr int64_t kAdaptiveBatchN = 131072;
+    int last_bt = kMaxBatch;                 // backtracks of the previous step (sizes the first batch at large n)
     DBuf<double> d_xbM, d_zcM, d_muM, d_partM, d_scalM, d_cM, d_coefM;
     HBuf<double> h_scalM;
     bool batch_ok() const {
@@ -1161,17 +1164,32 @@ struct ihtb_fit {
     }
     void finish_batched(const StepPlan& pl, double t2, double old_logl, double& eta, int& eta_step, double& new_logl) {
         const int M = pl.M;
-        support_matvec_dev_m(pl.UL ? d_idx.p : nullptr, (int64_t)pl.UL, d_coefM.p, M, d_xbM.p);
-        glm_mu_batched(glm, d_cM.p, M, d_xbM.p, d_zcM.p, d_muM.p, d_partM.p, d_scalM.p, s);
-        IHTB_CUDA(cudaMemcpyAsync(h_scalM.p, d_scalM.p, (size_t)(3 * M) * sizeof(double), cudaMemcpyDeviceToHost, s));
-        sync();
+        // models m0 .. m1-1 in one device round trip (per model the arithmetic does not depend on how many share a launch)
+        auto eval = [&](int m0, int m1) {
+            const int mm = m1 - m0;
+            support_matvec_dev_m(pl.UL ? d_idx.p : nullptr, (int64_t)pl.UL, d_coefM.p + (size_t)m0 * pl.UL, mm,
+                                 d_xbM.p + (size_t)m0 * n);
+            glm_mu_batched(glm, d_cM.p + (size_t)m0 * q, mm, d_xbM.p + (size_t)m0 * n, d_zcM.p + (size_t)m0 * n,
+                           d_muM.p + (size_t)m0 * n, d_partM.p, d_scalM.p + 3 * m0, s);
+            IHTB_CUDA(cudaMemcpyAsync(h_scalM.p + 3 * m0, d_scalM.p + 3 * m0, (size_t)(3 * mm) * sizeof(double),
+                                      cudaMemcpyDeviceToHost, s));
+            sync();
+        };
+        // Small n: all M at once -- the batch costs microseconds and saves a round trip whenever the step backtracks.
+        // Long vectors (n x M products, all-reduces of n x M doubles when sharded): as many as the last step needed plus
+        // one, the rest in a second round trip only if the walk below gets that far.  Same results either way.
+        int have = M;
+        if (n >= kAdaptiveBatchN) have = std::min(M, last_bt + 1 + (last_bt > 0 ? 1 : 0));
+        eval(0, have);
         int sidx = 0;
         new_logl = logl_from_sums(h_scalM.p);
         while (old_logl > new_logl && sidx < cfg.max_step) {                // _iht_backtrack_ (src/utilities.jl:484-486)
             ++sidx;
+            if (sidx >= have) { eval(have, M); have = M; }
             new_logl = logl_from_sums(h_scalM.p + 3 * sidx);
             ++n_backtracks;
         }
+        last_bt = sidx;
         adopt_model(sidx);
         eta = step_models[(size_t)sidx].eta; eta_step = sidx;
         last_dev = h_scalM.p[3 * sidx];

@@ -606,3 +606,20 @@ def test_cv_grid_does_not_depend_on_sweep_pairing():
         assert np.array_equal(got[1], want[1]) and got[1].max() < 100          # converging fits (cf. test_oscillating_fit)
         np.testing.assert_allclose(got[0], want[0], rtol=1e-10, atol=0)
     g.close()
+
+
+def test_long_vectors_adaptive_batch_matches_oracle():
+    """n >= 131072: the gradient step and its backtracks are evaluated in a first batch sized from the previous step's
+    backtracks, the remaining candidate models in a second round trip only when the walk needs them (fit.cu
+    finish_batched); candidates are re-scored by the nibble-table gather.  The oracle's fit on this problem takes
+    0, 1, 2 and 3 backtracks in turn, so every batch size and the second round trip are exercised."""
+    from oracle import cpu as ocpu
+    d, l, n, p, k, seed = "Bernoulli", "LogitLink", 140_000, 600, 5, 4243
+    bed = ocpu.synth_columns(seed, n, 0, p)
+    y, z, *_ = synth.simulate_response(seed + 1, n, p, k, d, geno_seed=seed)
+    g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    res = m.fit_iht(y, g, z, k=k + 1, d=d, l=l)
+    ref = iht.fit_iht(y, ocpu.PackedSnpLinAlgCPU(bed, n), z, k=k + 1, d=d, l=l)
+    assert ref.iter < 200 and set(ref.trace.backtracks) == {0, 1, 2, 3}
+    _compare(res, ref)
+    g.close()
