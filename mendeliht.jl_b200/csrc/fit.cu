@@ -1102,18 +1102,26 @@ struct ihtb_fit {
     }
     // host part shared by the batched and the fused step: the candidate models P_k(b0 + eta0 / 2^m df), m = 0..max_step,
     // the union of their supports, and this rank's rows of the coefficient block (uploaded)
-    struct StepPlan { int M; std::vector<int64_t> uni, loc; size_t UL; };
-    StepPlan plan_step(double eta0) {
-        const int M = cfg.max_step + 1;
-        step_models.assign((size_t)M, StepModel{});
-        double e = eta0;
-        for (int m = 0; m < M; ++m) {
-            if (m) { e /= 2; idx = idx0; b = b0; c = c0; }               // backtrack! (src/utilities.jl:959-973)
+    // models m0 .. m0 + M - 1 of the step (all of them by default): their union and coefficient block sit at offset 0 of
+    // d_idx / d_coefM / d_cM, their outputs go to slots m0 .. of the n x M buffers
+    struct StepPlan { int M; int m0; std::vector<int64_t> uni, loc; size_t UL; };
+    StepPlan plan_step(double eta0, int m0 = 0, int m1 = -1) {
+        const int Mtot = cfg.max_step + 1;
+        if (m1 < 0) m1 = Mtot;
+        if (m0 == 0) step_models.assign((size_t)Mtot, StepModel{});
+        for (int m = m0; m < m1; ++m) {
+            double e = eta0;
+            for (int i = 0; i < m; ++i) e /= 2;
+            if (m) { idx = idx0; b = b0; c = c0; }                       // backtrack! (src/utilities.jl:959-973)
             gradstep(e);
             step_models[(size_t)m] = StepModel{e, idx, b, c, idc};
         }
-        StepPlan pl; pl.M = M;
-        for (const StepModel& md : step_models) pl.uni.insert(pl.uni.end(), md.idx.begin(), md.idx.end());
+        const int M = m1 - m0;
+        StepPlan pl; pl.M = M; pl.m0 = m0;
+        for (int m = m0; m < m1; ++m) {
+            const StepModel& md = step_models[(size_t)m];
+            pl.uni.insert(pl.uni.end(), md.idx.begin(), md.idx.end());
+        }
         std::sort(pl.uni.begin(), pl.uni.end());
         pl.uni.erase(std::unique(pl.uni.begin(), pl.uni.end()), pl.uni.end());
         const size_t U = pl.uni.size();
@@ -1124,7 +1132,7 @@ struct ihtb_fit {
         pl.UL = pl.loc.size();
         std::vector<double> coefL(pl.UL * (size_t)M, 0.0), cM((size_t)(M * q));
         for (int m = 0; m < M; ++m) {
-            const StepModel& md = step_models[(size_t)m];
+            const StepModel& md = step_models[(size_t)(m0 + m)];
             size_t u = 0;                               // both lists are sorted: one merge pass per model
             for (size_t t = 0; t < md.idx.size(); ++t) {
                 if (!is_local(md.idx[t])) continue;
@@ -1158,34 +1166,36 @@ struct ihtb_fit {
         double t0 = now();
         const double eta0 = stepsize();
         double t1 = now(); phase[0] += t1 - t0;
-        const StepPlan pl = plan_step(eta0);
+        // Small n: all candidate models at once -- the batch costs microseconds and saves a round trip whenever the step
+        // backtracks.  Long vectors (n x M products, all-reduces of n x M doubles when sharded): as many as the last step
+        // needed plus one; the rest are planned and evaluated in a second round trip only if the walk in finish_batched
+        // gets that far.  Per model the arithmetic does not depend on how many share a launch: same results either way.
+        const int Mtot = cfg.max_step + 1;
+        int first = Mtot;
+        if (n >= kAdaptiveBatchN) first = std::min(Mtot, last_bt + 1 + (last_bt > 0 ? 1 : 0));
+        const StepPlan pl = plan_step(eta0, 0, first);
         double t2 = now(); phase[1] += t2 - t1;
-        finish_batched(pl, t2, old_logl, eta, eta_step, new_logl);
+        finish_batched(pl, eta0, t2, old_logl, eta, eta_step, new_logl);
     }
-    void finish_batched(const StepPlan& pl, double t2, double old_logl, double& eta, int& eta_step, double& new_logl) {
-        const int M = pl.M;
-        // models m0 .. m1-1 in one device round trip (per model the arithmetic does not depend on how many share a launch)
-        auto eval = [&](int m0, int m1) {
-            const int mm = m1 - m0;
-            support_matvec_dev_m(pl.UL ? d_idx.p : nullptr, (int64_t)pl.UL, d_coefM.p + (size_t)m0 * pl.UL, mm,
-                                 d_xbM.p + (size_t)m0 * n);
-            glm_mu_batched(glm, d_cM.p + (size_t)m0 * q, mm, d_xbM.p + (size_t)m0 * n, d_zcM.p + (size_t)m0 * n,
-                           d_muM.p + (size_t)m0 * n, d_partM.p, d_scalM.p + 3 * m0, s);
-            IHTB_CUDA(cudaMemcpyAsync(h_scalM.p + 3 * m0, d_scalM.p + 3 * m0, (size_t)(3 * mm) * sizeof(double),
+    // pl covers models 0 .. pl.M - 1 of the step
+    void finish_batched(const StepPlan& pl, double eta0, double t2, double old_logl, double& eta, int& eta_step,
+                        double& new_logl) {
+        const int Mtot = cfg.max_step + 1;
+        auto eval = [&](const StepPlan& P) {                      // one device round trip for the models of plan P
+            const size_t off = (size_t)P.m0 * (size_t)n;
+            support_matvec_dev_m(P.UL ? d_idx.p : nullptr, (int64_t)P.UL, d_coefM.p, P.M, d_xbM.p + off);
+            glm_mu_batched(glm, d_cM.p, P.M, d_xbM.p + off, d_zcM.p + off, d_muM.p + off, d_partM.p, d_scalM.p + 3 * P.m0, s);
+            IHTB_CUDA(cudaMemcpyAsync(h_scalM.p + 3 * P.m0, d_scalM.p + 3 * P.m0, (size_t)(3 * P.M) * sizeof(double),
                                       cudaMemcpyDeviceToHost, s));
             sync();
         };
-        // Small n: all M at once -- the batch costs microseconds and saves a round trip whenever the step backtracks.
-        // Long vectors (n x M products, all-reduces of n x M doubles when sharded): as many as the last step needed plus
-        // one, the rest in a second round trip only if the walk below gets that far.  Same results either way.
-        int have = M;
-        if (n >= kAdaptiveBatchN) have = std::min(M, last_bt + 1 + (last_bt > 0 ? 1 : 0));
-        eval(0, have);
+        int have = pl.M;
+        eval(pl);
         int sidx = 0;
         new_logl = logl_from_sums(h_scalM.p);
         while (old_logl > new_logl && sidx < cfg.max_step) {                // _iht_backtrack_ (src/utilities.jl:484-486)
             ++sidx;
-            if (sidx >= have) { eval(have, M); have = M; }
+            if (sidx >= have) { eval(plan_step(eta0, have, Mtot)); have = Mtot; }
             new_logl = logl_from_sums(h_scalM.p + 3 * sidx);
             ++n_backtracks;
         }
@@ -1229,7 +1239,7 @@ struct ihtb_fit {
         const int M = pl.M;
         double t2 = now(); phase[1] += t2 - t1;
         if (comm && pl.UL > (size_t)capx / 2) {       // the union does not fit the sharded candidate block: two round trips
-            finish_batched(pl, t2, old_logl, eta, eta_step, new_logl);
+            finish_batched(pl, eta0, t2, old_logl, eta, eta_step, new_logl);
             return;
         }
         support_matvec_dev_m(pl.UL ? d_idx.p : nullptr, (int64_t)pl.UL, d_coefM.p, M, d_xbM.p);
