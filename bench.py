@@ -297,9 +297,10 @@ def run_ours(args):
                                         if ternary else "PLINK 2-bit tiles",
                      "sweep_with_epilogue_ms": mt.value, "sweep_with_epilogue_gbs": abytes / (mt.value * 1e-3) / 1e9},
         "e2e": {"value": e_iters / t_e2e, "unit": UNIT,
-                "h2d_bytes_per_step": int(y.nbytes + z.nbytes), "d2h_bytes_per_step": int(beta.nbytes + c.nbytes),
+                "h2d_bytes_per_step": int(y.nbytes + z.nbytes), "d2h_bytes_per_step": int(16 * np.count_nonzero(beta) + c.nbytes + 8),
                 "ms_per_step": t_e2e / args.steps * 1e3,
-                "note": "fit_iht(y, x, z) with host y/z and beta copied back; x (genotype operator) built once from "
+                "note": "fit_iht(y, x, z) with host y/z; the model comes back as k (index, value) pairs + c + logl (the "
+                        "dense beta of IHTResult is built on first access); x (genotype operator) built once from "
                         "host .bed bytes before the timed region",
                 "geno_host_generate_s": t_gen, "geno_create_from_host_s": t_upload,
                 "geno_h2d_bytes": int(p * ((n + 3) // 4))},

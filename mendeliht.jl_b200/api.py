@@ -241,9 +241,23 @@ class B200MultiSnpLinAlg:
             pass
 
 
+class SparseCoef:
+    """The k non-zero coefficients of a fit as (global column, value) pairs; `dense()` is the length-p vector."""
+
+    def __init__(self, p: int, idx: np.ndarray, val: np.ndarray):
+        self.p, self.idx, self.val = int(p), idx, val
+
+    def dense(self) -> np.ndarray:
+        b = np.zeros(self.p)
+        b[self.idx] = self.val
+        return b
+
+
 @dataclass
 class IHTResult:
-    """`IHTResult` (src/data_structures.jl:245-258) + device-side counters."""
+    """`IHTResult` (src/data_structures.jl:245-258) + device-side counters.  `beta` is the dense length-p vector of the
+    reference; when the fit hands over a `SparseCoef` it is built on first access (zeroing p doubles per fit costs 5 ms at
+    p = 4M -- more than a tenth of an 8-GPU fit) and `beta_sparse` keeps the pairs."""
     time: float
     logl: float
     iter: int
@@ -259,6 +273,23 @@ class IHTResult:
     n_backtracks: int = 0
     sweep_seconds: float = 0.0
     n_launches: int = 0
+
+    def __post_init__(self):
+        sp = self.__dict__.get("beta")
+        if isinstance(sp, SparseCoef):
+            self.__dict__["beta_sparse"] = sp
+            del self.__dict__["beta"]                    # __getattr__ below builds the dense vector on first use
+        else:
+            self.__dict__["beta_sparse"] = None
+
+    def __getattr__(self, name):
+        if name == "beta":
+            sp = self.__dict__.get("beta_sparse")
+            if sp is not None:
+                dense = sp.dense()
+                self.__dict__["beta"] = dense
+                return dense
+        raise AttributeError(name)
 
 
 class IHTVariable:
@@ -370,15 +401,18 @@ class IHTVariable:
         trace = [(tr[i].logl, tr[i].backtracks, tr[i].tol, tr[i].eta, tr[i].n_candidates) for i in range(n_it)]
         return res, trace
 
-    def get(self, mu=False, xb=False):
-        # beta is dense like IHTResult.beta, but only its k entries are written: zero pages from calloc + a scatter
-        # (p = 4M at 8 GPUs would otherwise cost a 32 MB fill per fit)
+    def get_sparse(self) -> SparseCoef:
         nnz = C.c_int64(0)
         check(self._fn("get_sparse")(self._h, None, None, 0, C.byref(nnz)))
         idx = np.empty(max(nnz.value, 1), dtype=np.int64); val = np.empty(max(nnz.value, 1))
         check(self._fn("get_sparse")(self._h, ptr(idx, C.c_int64), ptr(val, C.c_double), nnz.value, C.byref(nnz)))
-        beta = np.zeros(self.p); c = np.empty(self.q)
-        beta[idx[:nnz.value]] = val[:nnz.value]
+        return SparseCoef(self.p, idx[:nnz.value], val[:nnz.value])
+
+    def get(self, mu=False, xb=False, sparse=False):
+        """(beta, c, mu, xb); sparse=True returns beta as a `SparseCoef` (no length-p vector is written)."""
+        sp = self.get_sparse()
+        beta = sp if sparse else sp.dense()
+        c = np.empty(self.q)
         m = np.empty(self.n) if mu else None
         x = np.empty(self.n) if xb else None
         check(self._fn("get")(self._h, None, ptr(c, C.c_double),
@@ -571,7 +605,7 @@ def fit_iht(y, x: B200SnpLinAlg, z=None, k=10, d=NORMAL, l=None, zkeep=None, est
     try:
         v.init_iht_indices(None, init_beta)
         res, trace = v.fit()
-        beta, c, _, _ = v.get()
+        beta, c, _, _ = v.get(sparse=True)              # IHTResult builds the dense vector on first access
     finally:
         v.close()
     if verbose:

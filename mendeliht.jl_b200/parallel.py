@@ -322,8 +322,9 @@ def bench_sharded(args, rank, world, local_rank, G):
                          "stream_encoding": "ternary copy: 5 dosages per byte, lossless" if ternary else "PLINK 2-bit tiles"},
             "e2e": {"value": world * e_iters / t_e2e, "unit": G["UNIT"], "global_iterations_per_sec": e_iters / t_e2e,
                     "h2d_bytes_per_step": int(y.nbytes + z.nbytes),
-                    "d2h_bytes_per_step": int(beta.nbytes + c.nbytes), "ms_per_step": t_e2e / args.steps * 1e3,
-                    "note": "fit_iht(y, x_shard, z; comm) on every rank with host y/z, global beta copied back; "
+                    "d2h_bytes_per_step": int(16 * np.count_nonzero(beta) + c.nbytes + 8), "ms_per_step": t_e2e / args.steps * 1e3,
+                    "note": "fit_iht(y, x_shard, z; comm) on every rank with host y/z, the global model returned as k "
+                            "(index, value) pairs + c + logl (dense beta built on first access); "
                             "genotype shards generated on the device (host generation of N x 6.25 GB is skipped)"},
             "gpu_launches": int(launches), "clocks": clk, "cpu_baseline": None,
             "collectives_in_timed_region": {"peer_memory_kernels": coll1[0] - coll0[0], "nccl_calls": coll1[1] - coll0[1]},
