@@ -203,13 +203,15 @@ __global__ void k_synth(GenoView g, int64_t j0, uint64_t seed, uint32_t miss_thr
 
 // Ternary copy of the quad-interleaved tiles (common.cuh ihtb_geno::tern): thread = one 32-bit word of the copy =
 // 20 samples of one column = 5 source bytes.  idx = ((slab * nquads + quad) * 32 + w) * 4 + cj, so stores are coalesced.
+// Component cj of the 16 bytes at word position w holds column 4 quad + (cj ^ (w & 3)): lane w of a sweep warp then finds
+// its accumulator slots already arranged for a select-free butterfly (sweep_lut.cu).  Only the sweeps read this copy.
 __global__ void k_make_tern(GenoView g, int64_t p4, int64_t tern_slabs, uint32_t* __restrict__ out) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t total = tern_slabs * p4 * 32;
     if (idx >= total) return;
     const int cj = (int)(idx & 3), w = (int)((idx >> 2) & 31);
     const int64_t sq = idx >> 7, nquads = p4 >> 2;
-    const int64_t slab = sq / nquads, j = (sq % nquads) * 4 + cj;
+    const int64_t slab = sq / nquads, j = (sq % nquads) * 4 + (cj ^ (w & 3));
     uint32_t word = 0;
     if (j < g.p) {
         const int64_t b0 = slab * 160 + 5 * w;                  // first of the 5 source bytes (20 samples)

@@ -142,8 +142,12 @@ __device__ __forceinline__ void lut_build_h2_tern(uint32_t tab, const double* __
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
         int64_t i = slab * 640 + 20 * w + 5 * t + s;
-        a[s] = (i < n) ? __double2float_rn(__dsub_rn(v0[i], vbar0)) * sc0 : 0.0f;     // power-of-two scale: exact
-        b[s] = (i < n) ? __double2float_rn(__dsub_rn(v1[i], vbar1)) * sc1 : 0.0f;
+        const float x0 = (i < n) ? __double2float_rn(__dsub_rn(v0[i], vbar0)) * sc0 : 0.0f;     // power-of-two scale: exact
+        const float x1 = (i < n) ? __double2float_rn(__dsub_rn(v1[i], vbar1)) * sc1 : 0.0f;
+        // word positions 16..31 keep the two right-hand sides in swapped halves: the first butterfly level of the sweep
+        // (lane l with l ^ 16) then separates them without a select
+        a[s] = (w & 16) ? x1 : x0;
+        b[s] = (w & 16) ? x0 : x1;
     }
     auto fa = [&](int s, int d) -> float { return d == 1 ? a[s] : (d == 2 ? a[s] + a[s] : 0.0f); };
     auto fb = [&](int s, int d) -> float { return d == 1 ? b[s] : (d == 2 ? b[s] + b[s] : 0.0f); };

@@ -91,6 +91,7 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
     constexpr int CPW = LUT_STAGE_COLS / WPG;        // columns per warp per unit
     static_assert(!QUAD || CPW % 4 == 0, "quad layout: a warp owns whole quads");
     static_assert(!H2 || (CW == 16 && CPW == 16), "pair sweep: 512 table builders, 16 columns per warp");
+    static_assert(!TERN || (QUAD && CPW == 16), "ternary tiles: quad layout, 16 columns per warp");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const LutPlan pl = lut_plan(smem_u32(smem_raw), dyn_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -155,9 +156,15 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
         constexpr int NACC = H2 ? 2 * CPW : CPW;      // values reduced per warp and unit
         constexpr int LPC = 32 / NACC > 0 ? 32 / NACC : 1;   // lanes holding the same value after the butterfly
         // after the butterfly lane l holds value index l / LPC: (rhs, column) = (idx / CPW, idx % CPW)
-        const int vidx = lane / LPC;
+        // TERN: accumulator slot c of lane l holds value c ^ (l & (NACC - 1)) -- the ternary tiles store component i of the
+        // quad word w as column i ^ (w & 3) (geno.cu), the lane reads quad q ^ ((l >> 2) & 3), and the pair tables of word
+        // positions >= 16 carry the right-hand sides in swapped halves -- so every butterfly level is "keep the low half,
+        // add the partner's high half": no selects (2 per value otherwise: 12 % of the FAST kernel's instructions, 18 % of
+        // the PAIR kernel's, which was issue-bound).  Lane l ends with value l & (NACC - 1).
+        const int vidx = TERN ? (lane & (NACC - 1)) : lane / LPC;
         const int col = wg * CPW + vidx % CPW;        // column (within a unit) this lane stores
-        const bool writer = (lane & (LPC - 1)) == 0;
+        const bool writer = TERN ? (lane < NACC) : (lane & (LPC - 1)) == 0;
+        const uint32_t lqs = TERN ? ((((uint32_t)lane >> 2) & 3u) << 9) : 0u;
         const uint32_t lane_off = (uint32_t)(wg * CPW) * 128u + (QUAD ? 16u : 4u) * (uint32_t)lane;
         // this group consumes local unit indices i = grp, grp+G, ...: stage i % S, full-barrier parity (i / period) & 1
         int st = grp % S, ip = grp % period; uint32_t ph = (uint32_t)((grp / period) & 1);
@@ -185,7 +192,7 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
                 for (int c = 0; c < CPW; ++c) {
                     uint32_t w;
                     if (QUAD) {
-                        if ((c & 3) == 0) q4 = lds_u128(colbase + 512u * (c >> 2));
+                        if ((c & 3) == 0) q4 = lds_u128(colbase + ((512u * (c >> 2)) ^ lqs));
                         w = (c & 3) == 0 ? q4.x : (c & 3) == 1 ? q4.y : (c & 3) == 2 ? q4.z : q4.w;
                     } else {
                         w = lds_u32(colbase + 128u * c);
@@ -211,20 +218,33 @@ k_sweep_lut(const uint8_t* __restrict__ bed, int64_t cs_j, int64_t cs_s, int64_t
                 // the stage's bytes are now in registers: hand the slot back to the producer
                 __syncwarp();
                 if (lane == 0) mbar_arrive(pl.bar_empty + 8u * st);
-                // butterfly: NACC sums per lane -> one per lane; the high lane bits select the value
-                int o = 16;
+                if (TERN) {
+                    // select-free butterfly (slots pre-arranged, see above): levels NACC/2 .. 1, then the lanes that hold the
+                    // same value (FAST: l and l ^ 16) are added
+                    int o = NACC / 2;
 #pragma unroll
-                for (int h = NACC / 2; h >= 1; h >>= 1, o >>= 1) {
-                    const bool upper = (lane & o) != 0;
+                    for (int h = NACC / 2; h >= 1; h >>= 1, o >>= 1) {
 #pragma unroll
-                    for (int c = 0; c < h; ++c) {
-                        const float send = upper ? acc[c] : acc[c + h];
-                        const float keep = upper ? acc[c + h] : acc[c];
-                        acc[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        for (int c = 0; c < h; ++c) acc[c] = acc[c] + __shfl_xor_sync(0xffffffffu, acc[c + h], o);
                     }
-                }
 #pragma unroll
-                for (int oo = 16 / NACC; oo >= 1; oo >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], oo);
+                    for (int oo = 16; oo >= NACC; oo >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], oo);
+                } else {
+                    // butterfly: NACC sums per lane -> one per lane; the high lane bits select the value
+                    int o = 16;
+#pragma unroll
+                    for (int h = NACC / 2; h >= 1; h >>= 1, o >>= 1) {
+                        const bool upper = (lane & o) != 0;
+#pragma unroll
+                        for (int c = 0; c < h; ++c) {
+                            const float send = upper ? acc[c] : acc[c + h];
+                            const float keep = upper ? acc[c + h] : acc[c];
+                            acc[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        }
+                    }
+#pragma unroll
+                    for (int oo = 16 / NACC; oo >= 1; oo >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], oo);
+                }
                 const int jj = cb * LUT_STAGE_COLS + col;
                 if (writer && jj < (int)p_out) outp[cb * LUT_STAGE_COLS] = acc[0];
                 st += G; if (st >= S) st -= S;
