@@ -136,6 +136,11 @@ int32_t ihtb_sweep_bench(const ihtb_geno* g, int32_t sweep_mode, int32_t warmup,
  * holds the ternary copy (five dosages per byte, built at creation when memory allows; IHTB_TERN=0/1 forces), else
  * p * ceil(n/512) * 128 (the PLINK 2-bit tiles).  The algorithmic figure of SURVEY.md 8d stays p * ceil(n/4). */
 int32_t ihtb_geno_sweep_stream_bytes(const ihtb_geno* g, int64_t* bytes, int32_t* ternary);
+/* The ternary copy as it lies in HBM (ihtb_geno_sweep_stream_bytes bytes): slab-major tiles of 640 samples; inside a slab
+ * the columns are grouped by four, and the 16 bytes at word position w (0..31) of a group hold the 32-bit words of its four
+ * columns, component i = column 4 q + (i ^ (w & 3)); a word packs samples 20 w .. 20 w + 19 of the slab, a byte five dosages
+ * in base 3 (d0 + 3 d1 + 9 d2 + 27 d3 + 81 d4, missing -> 0).  Fails with IHTB_EINVAL when the handle holds no copy. */
+int32_t ihtb_geno_ternary_tiles(const ihtb_geno* g, uint8_t* out, int64_t out_bytes);
 /* Diagnostic / bench: exact FP64 column dots X[:, cols]' v (the re-scoring of top-k candidates) for ncols columns through
  * the nibble-table kernel every univariate fit uses: average device time per call, and the largest difference to the
  * per-column decode kernel relative to the largest value. */

@@ -88,6 +88,7 @@ SIGNATURES = {
     "ihtb_sweep_bench": [_p, C.c_int32, C.c_int32, C.c_int32, _f64, _f64],
     "ihtb_geno_sweep_stream_bytes": [_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)],
     "ihtb_gather_bench": [_p, C.c_int64, C.c_int32, _f64, _f64],
+    "ihtb_geno_ternary_tiles": [_p, _u8, C.c_int64],
     "ihtb_geno_destroy": [_p],
     "ihtb_fit_create": [_p, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), _pp],
     "ihtb_fit_create_sharded": [_p, _p, C.c_int64, _f64, _f64, C.c_int64, _u8, C.POINTER(Cfg), _pp],

@@ -95,6 +95,15 @@ class B200SnpLinAlg:
     def shape(self):
         return (self.n, self.p)
 
+    def ternary_tiles(self) -> np.ndarray:
+        """Raw bytes of the ternary copy the FAST / PAIR sweeps stream (format: include/ihtb200.h, synth.ternary_tiles)."""
+        nbytes, tern = self.sweep_stream_bytes()
+        if not tern:
+            raise _lib.IHTBError(_lib.IHTB_EINVAL, "this handle holds no ternary copy")
+        out = np.empty(nbytes, dtype=np.uint8)
+        check(load().ihtb_geno_ternary_tiles(self._h, ptr(out, C.c_uint8), nbytes))
+        return out
+
     def gather_bench(self, ncols: int, reps: int = 5):
         """(ms per exact re-scoring of `ncols` columns, max difference to the per-column kernel / max |value|)"""
         ms, err = C.c_double(0.0), C.c_double(0.0)

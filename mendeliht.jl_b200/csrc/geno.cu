@@ -629,6 +629,19 @@ int32_t ihtb_geno_packed(const ihtb_geno* g, int64_t j0, int64_t j1, uint8_t* ou
     });
 }
 
+// raw bytes of the ternary copy, exactly as they lie in HBM (tests pin the format against a host twin, synth.ternary_tiles)
+int32_t ihtb_geno_ternary_tiles(const ihtb_geno* g, uint8_t* out, int64_t out_bytes) {
+    return guard([&] {
+        IHTB_CHECK(g && out, IHTB_EINVAL, "NULL argument");
+        geno_require_ready(g);
+        IHTB_CHECK(g->tern.p != nullptr, IHTB_EINVAL, "this handle holds no ternary copy");
+        const int64_t bytes = g->tern_slabs * g->p4 * 128;
+        IHTB_CHECK(out_bytes == bytes, IHTB_EDIM, "the ternary copy has " + std::to_string(bytes) + " bytes");
+        IHTB_CUDA(cudaSetDevice(g->device));
+        IHTB_CUDA(cudaMemcpy(out, g->tern.p, (size_t)bytes, cudaMemcpyDeviceToHost));
+    });
+}
+
 int32_t ihtb_geno_destroy(ihtb_geno* g) {
     return guard([&] {
         if (g) {

@@ -64,6 +64,28 @@ def packed_columns(seed: int, n: int, cols, missing_rate: float = 0.0) -> np.nda
     return (pad[:, :, 0] | (pad[:, :, 1] << 2) | (pad[:, :, 2] << 4) | (pad[:, :, 3] << 6)).astype(np.uint8)
 
 
+def ternary_tiles(bed: np.ndarray, n: int) -> np.ndarray:
+    """Host twin of the ternary copy of a genotype handle (geno.cu k_make_tern): the byte stream the FAST / PAIR sweeps read.
+    bed: packed PLINK columns [p, ceil(n/4)].  Slabs of 640 samples; per slab, columns in groups of four; the 16 bytes at word
+    position w of a group hold the words of its four columns, component i = column 4 q + (i ^ (w & 3)); a word packs samples
+    20 w .. 20 w + 19 of the slab, a byte five dosages in base 3 (missing counts as 0)."""
+    p = bed.shape[0]
+    p4 = (p + 3) // 4 * 4
+    slabs = -(-n // 640)
+    codes4 = np.stack([(bed >> (2 * s)) & 3 for s in range(4)], axis=2).reshape(p, -1)[:, :n]      # [p, n] PLINK codes
+    dos = np.array([0, 0, 1, 2], dtype=np.uint32)[codes4]                                          # 01 (missing) -> 0
+    pad = np.zeros((p4, slabs * 640), dtype=np.uint32)
+    pad[:p, :n] = dos
+    d = pad.reshape(p4, slabs, 32, 4, 5)                                                           # column, slab, w, byte, digit
+    byte = (d * np.array([1, 3, 9, 27, 81], dtype=np.uint32)).sum(axis=4).astype(np.uint8)         # [p4, slabs, 32, 4]
+    out = np.zeros((slabs, p4 // 4, 32, 4, 4), dtype=np.uint8)                                     # slab, quad, w, component, byte
+    for w in range(32):
+        for i in range(4):
+            cols = np.arange(p4 // 4) * 4 + (i ^ (w & 3))
+            out[:, :, w, i, :] = byte[cols, :, w, :].transpose(1, 0, 2)
+    return out.reshape(-1)
+
+
 def standardized_columns(seed: int, n: int, cols, missing_rate: float = 0.0) -> np.ndarray:
     """x[:, cols] with SnpLinAlg(center, scale, impute) semantics, float64 [n, len(cols)]."""
     c = codes(seed, n, cols, missing_rate)

@@ -264,3 +264,16 @@ def test_nibble_gather_matches_decode_kernel(n, p, miss, ncols):
     ms, err = g.gather_bench(ncols, 1)
     assert err <= 1e-13, err
     g.close()
+
+
+@pytest.mark.parametrize("n,p,miss", [(640, 8, 0.0), (1003, 13, 0.05), (2500, 130, 0.2)])
+def test_ternary_tiles_match_host_twin(n, p, miss):
+    """The ternary copy as it lies in HBM equals the numpy restatement of its format byte for byte."""
+    bed = synth.packed_columns(9, n, np.arange(p), miss)
+    os.environ["IHTB_TERN"] = "1"
+    try:
+        g = m.B200SnpLinAlg.from_bed_columns(bed, n)
+    finally:
+        os.environ.pop("IHTB_TERN", None)
+    assert np.array_equal(g.ternary_tiles(), synth.ternary_tiles(bed, n))
+    g.close()

@@ -123,3 +123,23 @@ def test_wrapper_parsers_without_gpu(tmp_path):
     assert m.allocate_fold_and_k(2, [3, 5]) == [(1, 3), (1, 5), (2, 3), (2, 5)]
     with pytest.raises(AssertionError):
         api._check_args(5, 10, 3, 0.0)
+
+
+def test_ternary_tile_format_round_trip():
+    """synth.ternary_tiles restates the byte stream the sweeps read (five base-3 dosages per byte, 640-sample slabs,
+    columns of a quad permuted by word position): every sample decodes back to its dosage, missing to 0."""
+    import numpy as np
+    from mendeliht_jl_b200 import synth
+    for n, p, miss in [(640, 8, 0.0), (1003, 13, 0.05), (1281, 5, 0.3)]:
+        bed = synth.packed_columns(9, n, np.arange(p), miss)
+        t = synth.ternary_tiles(bed, n)
+        slabs, p4 = -(-n // 640), (p + 3) // 4 * 4
+        assert t.dtype == np.uint8 and t.shape == (slabs * p4 * 128,) and t.max() <= 242
+        T = t.reshape(slabs, p4 // 4, 32, 4, 4)
+        dos = np.array([0, 0, 1, 2])[synth.codes(9, n, np.arange(p), miss)]              # [n, p]
+        i = np.arange(n)
+        s, r = np.divmod(i, 640); w, rr = np.divmod(r, 20); b, dg = np.divmod(rr, 5)
+        for j in range(p):
+            byte = T[s, j // 4, w, (j & 3) ^ (w & 3), b].astype(np.int64)
+            assert np.array_equal((byte // 3 ** dg) % 3, dos[:, j])
+        assert not T[:, :, :, :, :].reshape(slabs, p4 // 4, 32, 4, 4)[:, p // 4:, :, :, :].any() or p % 4      # padding columns are zero
