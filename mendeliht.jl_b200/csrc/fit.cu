@@ -68,6 +68,7 @@ struct ihtb_fit {
     int cap = 4096;
 
     // device state
+    DBuf<unsigned> d_done;
     DBuf<double> d_y, d_z, d_w, d_xb, d_zc, d_mu, d_r, d_xs, d_dfa, d_part, d_scal, d_small, d_coef, d_gout,
         d_vbar;
     DBuf<uint8_t> d_mask;
@@ -1490,6 +1491,9 @@ int32_t ihtb_fit_create_sharded(const ihtb_geno* g, ihtb_comm* comm, int64_t p_g
         f->d_xb.zero(f->s); f->d_zc.zero(f->s);
         f->glm = GlmCtx{n, q, f->d_z.p, f->d_y.p, f->d_w.p, f->d_xb.p, f->d_zc.p, f->d_mu.p, f->d_r.p, f->d_part.p,
                         f->d_scal.p, cfg->dist, cfg->link, cfg->nb_r};
+        if (f->d_done.n < 8) { f->d_done.alloc(8); }
+        IHTB_CUDA(cudaMemsetAsync(f->d_done.p, 0, 8 * sizeof(unsigned), f->s));
+        f->glm.done = f->d_done.p;                 // in-kernel finalisation of the score / glm / step-size sums (glm.cu)
         f->tk = TopkCtx{p, f->d_keyL.p, f->d_keyU.p, f->d_hist.p, reinterpret_cast<TopkState*>(f->d_sel.p),
                         f->d_sel.p + 2, f->cap};
         f->wt.clear();

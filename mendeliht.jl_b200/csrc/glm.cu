@@ -14,12 +14,41 @@ static inline int glm_grid(int64_t n) {
     return (int)(b < 1 ? 1 : (b > GLM_MAX_BLOCKS ? GLM_MAX_BLOCKS : b));
 }
 
+// In-kernel finalisation: every CTA calls this after thread 0 wrote the CTA's nv partial sums to part[blockIdx.x * nv ..].
+// The CTA that arrives last (ticket counter `done`, reset for the next launch) reduces all of them exactly like k_finalize:
+// one warp per value, lanes stride over the CTAs, fixed shuffle tree -- bit-identical sums, one launch less.
+__device__ __forceinline__ void cta_finalize(const double* part, int nv, double* out, unsigned* done,
+                                             double* mean_out = nullptr, int64_t n = 1) {
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // this CTA's partial sums before its ticket
+        const unsigned t = atomicAdd(done, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();                                       // the other CTAs' sums after the last ticket
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int nblocks = (int)gridDim.x;
+    for (int v = warp; v < nv; v += nw) {
+        double a = 0.0;
+        for (int b = lane; b < nblocks; b += 32) a += __ldcg(part + (int64_t)b * nv + v);
+        a = warp_sum(a);
+        if (lane == 0) {
+            out[v] = a;
+            if (mean_out && v == 0) mean_out[0] = a / (double)n;
+        }
+    }
+    if (threadIdx.x == 0) *done = 0u;
+}
+
 // xb (clamped in place unless Normal), zc = Z c (clamped), mu = linkinv(xb + zc) [or linkinv(xb) when !add_zc],
 // partial sums: [0] sum w*devresid, [1] sum w*logpdf (phi-free part; unused for Normal), [2] sum w
 __global__ void __launch_bounds__(GLM_THREADS)
 k_glm_mu(int64_t n, int64_t q, const double* __restrict__ Z, const double* __restrict__ c, double* __restrict__ xb,
          double* __restrict__ zc, double* __restrict__ mu, const double* __restrict__ y, const double* __restrict__ w,
-         int dist, int link, double nb_r, int add_zc, double* __restrict__ part) {
+         int dist, int link, double nb_r, int add_zc, double* __restrict__ part, double* __restrict__ out = nullptr,
+         unsigned* __restrict__ done = nullptr) {
     __shared__ double sh[32];
     // blockIdx.y = model of a batched evaluation (glm_mu_batched): every model has its own c, xb, zc, mu and partial
     // sums, laid out back to back, and is reduced exactly like a single model (same blocks, same order)
@@ -52,6 +81,7 @@ k_glm_mu(int64_t n, int64_t q, const double* __restrict__ Z, const double* __res
         part[blockIdx.x * 3 + 1] = a_lp;
         part[blockIdx.x * 3 + 2] = a_w;
     }
+    if (done) cta_finalize(part, 3, out + blockIdx.y * 3, done + blockIdx.y);
 }
 
 // r_i = mueta(eta_i)/glmvar(mu_i) * (y_i - mu_i) * w_i ; partials [0] sum r, [1] sum |r|, [2..2+q) Z'r
@@ -59,7 +89,8 @@ __global__ void __launch_bounds__(GLM_THREADS)
 k_score(int64_t n, int64_t q, const double* __restrict__ Z, const double* __restrict__ xb,
         const double* __restrict__ zc, const double* __restrict__ mu, const double* __restrict__ y,
         const double* __restrict__ w, int dist, int link, double nb_r, double* __restrict__ r,
-        double* __restrict__ part) {
+        double* __restrict__ part, double* __restrict__ out = nullptr, unsigned* __restrict__ done = nullptr,
+        double* __restrict__ mean_out = nullptr) {
     __shared__ double sh[32];
     const int nv = 2 + (int)q;
     double a_r = 0.0, a_abs = 0.0;
@@ -85,6 +116,7 @@ k_score(int64_t n, int64_t q, const double* __restrict__ Z, const double* __rest
         a = block_sum(a, sh);
         if (threadIdx.x == 0) part[blockIdx.x * nv + 2 + l] = a;
     }
+    if (done) cta_finalize(part, nv, out, done, mean_out, n);
 }
 
 // xgk_i = (xs_i + sum_l Z[i,l] d2_l) * sqrt(mueta^2 / glmvar) * w_i ; partial [0] = sum xgk_i^2
@@ -93,7 +125,7 @@ k_stepsize(int64_t n, int64_t q, const double* __restrict__ Z, const double* __r
            const double* __restrict__ d2mask, const double* __restrict__ xs, const double* __restrict__ xb,
            const double* __restrict__ zc,
            const double* __restrict__ mu, const double* __restrict__ w, int dist, int link, double nb_r,
-           double* __restrict__ part) {
+           double* __restrict__ part, double* __restrict__ out = nullptr, unsigned* __restrict__ done = nullptr) {
     __shared__ double sh[32];
     double a = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -106,6 +138,7 @@ k_stepsize(int64_t n, int64_t q, const double* __restrict__ Z, const double* __r
     }
     a = block_sum(a, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = a;
+    if (done) cta_finalize(part, 1, out, done);
 }
 
 // partials [0] sum a_i, [1] sum b_i   (means for pve)
@@ -249,8 +282,8 @@ void glm_mean_from_sum(GlmCtx& c, double* d_mean, cudaStream_t s) {
 void glm_mu(GlmCtx& c, const double* d_c, int add_zc, cudaStream_t s) {
     int grid = glm_grid(c.n);
     IHTB_LAUNCH(k_glm_mu, grid, GLM_THREADS, 0, s, c.n, c.q, c.Z, d_c, c.xb, c.zc, c.mu, c.y, c.w, c.dist, c.link,
-                c.nb_r, add_zc, c.part);
-    IHTB_LAUNCH(k_finalize, 1, 96, 0, s, c.part, grid, 3, c.scal);
+                c.nb_r, add_zc, c.part, c.scal, c.done);
+    if (!c.done) IHTB_LAUNCH(k_finalize, 1, 96, 0, s, c.part, grid, 3, c.scal);
 }
 // M models at once (the gradient step and its backtracks): xbM / zcM / muM are n x M, d_cM is q x M, d_scalM gets
 // [dev, lp, sum w] per model.  Per model the arithmetic is that of glm_mu.
@@ -258,8 +291,8 @@ void glm_mu_batched(GlmCtx& c, const double* d_cM, int M, double* xbM, double* z
                     double* d_scalM, cudaStream_t s) {
     int grid = glm_grid(c.n);
     IHTB_LAUNCH(k_glm_mu, dim3(grid, M), GLM_THREADS, 0, s, c.n, c.q, c.Z, d_cM, xbM, zcM, muM, c.y, c.w, c.dist, c.link,
-                c.nb_r, 1, d_partM);
-    IHTB_LAUNCH(k_finalize, dim3(1, M), 96, 0, s, d_partM, grid, 3, d_scalM);
+                c.nb_r, 1, d_partM, d_scalM, c.done);
+    if (!c.done) IHTB_LAUNCH(k_finalize, dim3(1, M), 96, 0, s, d_partM, grid, 3, d_scalM);
 }
 // ---- the gradient step and its backtracks decided on the device (fit.cu one_step_fused) ------------------------------
 // scalM[3m..] = deviance, sum of log-densities, sum of weights of candidate model m (eta / 2^m).  pick[1 + m] = its
@@ -315,15 +348,15 @@ void glm_score(GlmCtx& c, cudaStream_t s, double* d_mean) {
     int grid = glm_grid(c.n);
     int nv = 2 + (int)c.q;
     IHTB_LAUNCH(k_score, grid, GLM_THREADS, 0, s, c.n, c.q, c.Z, c.xb, c.zc, c.mu, c.y, c.w, c.dist, c.link, c.nb_r,
-                c.r, c.part);
-    IHTB_LAUNCH(k_finalize, (unsigned)ceil_div(nv, 4), 128, 0, s, c.part, grid, nv, c.scal, d_mean, c.n);
+                c.r, c.part, c.scal, c.done, d_mean);
+    if (!c.done) IHTB_LAUNCH(k_finalize, (unsigned)ceil_div(nv, 4), 128, 0, s, c.part, grid, nv, c.scal, d_mean, c.n);
 }
 void glm_stepsize(GlmCtx& c, const double* d_d2, const double* d_xs, cudaStream_t s, const double* d_d2mask,
                   double* d_out) {
     int grid = glm_grid(c.n);
     IHTB_LAUNCH(k_stepsize, grid, GLM_THREADS, 0, s, c.n, c.q, c.Z, d_d2, d_d2mask, d_xs, c.xb, c.zc, c.mu, c.w, c.dist,
-                c.link, c.nb_r, c.part);
-    IHTB_LAUNCH(k_finalize, 1, 32, 0, s, c.part, grid, 1, d_out ? d_out : c.scal);
+                c.link, c.nb_r, c.part, d_out ? d_out : c.scal, c.done);
+    if (!c.done) IHTB_LAUNCH(k_finalize, 1, 32, 0, s, c.part, grid, 1, d_out ? d_out : c.scal);
 }
 void glm_sum2(GlmCtx& c, const double* a, const double* b, cudaStream_t s) {
     int grid = glm_grid(c.n);

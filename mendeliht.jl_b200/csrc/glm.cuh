@@ -105,6 +105,10 @@ struct GlmCtx {
     double* scal;      // finalized sums
     int dist, link;
     double nb_r;
+    // Tickets of the in-kernel finalisation (one per model of a batched launch, zero between launches): the CTA that draws
+    // the last ticket adds the per-CTA partial sums itself -- same order as k_finalize -- instead of a second launch.
+    // NULL: separate k_finalize launches (contexts built ad hoc, e.g. mvfit.cu's init_beta).
+    unsigned* done = nullptr;
 };
 
 void glm_mu(GlmCtx& c, const double* d_c, int add_zc, cudaStream_t s);        // scal: dev, lp, sum w
