@@ -28,7 +28,8 @@
 
 namespace ihtb {
 void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* vbar_host, int64_t m, double* dOut,
-                           int mode, cudaStream_t s, void* scratch_any, float* sweep_ms, double* d_l2 = nullptr);
+                           int mode, cudaStream_t s, void* scratch_any, float* sweep_ms, double* d_l2 = nullptr,
+                           const TopkFuse* tf = nullptr);
 void* sweep_scratch_create();
 void sweep_scratch_destroy(void* p);
 void sweep_class_sums(const ihtb_geno* g, const double* d_v, double* d_w1, double* d_w2, double* d_wm, cudaStream_t s,
@@ -342,6 +343,11 @@ struct ihtb_fit {
                 // ||r - mean||_2 of this fit travels back with the other score sums
                 IHTB_CUDA(cudaMemcpyAsync(h_scal.p + 3 + q, pairer->d_l2 + pair_slot, sizeof(double), cudaMemcpyDeviceToHost, s));
             }
+        } else if (cfg.k > 0 && !(grouped() && !init_plain)) {
+            // the epilogue also runs the first stage of the candidate selection (keys of |df| with this sweep's error bound,
+            // first digit histogram); select_rescore continues with topk_candidates_absdf_finish
+            const TopkFuse tf = topk_absdf_fuse_begin(tk, g->sinv.p, d_scal.p, sweep_coef);
+            sweep_xt_v_with_means(g, d_r.p, d_vbar.p, 1, d_dfa.p, cfg.sweep_mode, s, sweep_scratch, nullptr, nullptr, &tf);
         } else {
             sweep_xt_v_with_means(g, d_r.p, d_vbar.p, 1, d_dfa.p, cfg.sweep_mode, s, sweep_scratch, nullptr);
         }
@@ -382,8 +388,10 @@ struct ihtb_fit {
         if (cfg.k > 0) {
             const int64_t ksel = cfg.k + (int64_t)(fused ? fz->maxsupp : idx.size());
             const bool paired = coef == kPairBound;        // L2 bound over the handle's sgn scale (see kPairBound)
-            topk_candidates_absdf(tk, d_dfa.p, paired ? g->sgn.p : g->sinv.p, rerun ? nullptr : d_scal.p, coef, ksel, s, bound,
-                                  (paired && !rerun) ? pairer->d_l2 + pair_slot : nullptr);
+            if (tk.fused_hist) topk_candidates_absdf_finish(tk, ksel, s);      // first stage done by the sweep epilogue
+            else
+                topk_candidates_absdf(tk, d_dfa.p, paired ? g->sgn.p : g->sinv.p, rerun ? nullptr : d_scal.p, coef, ksel, s,
+                                      bound, (paired && !rerun) ? pairer->d_l2 + pair_slot : nullptr);
             // slots re-scored without a second round trip; the looser bound of a PAIR sweep admits more near-threshold columns
             // (sized from the previous iteration's count there)
             const int64_t want = sweep_coef == kPairBound ? std::max<int64_t>(ksel + 1024, last_count + last_count / 4 + 256)

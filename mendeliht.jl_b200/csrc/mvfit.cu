@@ -24,7 +24,8 @@
 
 namespace ihtb {
 void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* vbar_host, int64_t m, double* dOut,
-                           int mode, cudaStream_t s, void* scratch_any, float* sweep_ms, double* d_l2 = nullptr);
+                           int mode, cudaStream_t s, void* scratch_any, float* sweep_ms, double* d_l2 = nullptr,
+                           const TopkFuse* tf = nullptr);
 void* sweep_scratch_create();
 void sweep_scratch_destroy(void* p);
 void sweep_class_sums(const ihtb_geno* g, const double* d_v, double* d_w1, double* d_w2, double* d_wm, cudaStream_t s,

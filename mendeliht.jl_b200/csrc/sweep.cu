@@ -12,6 +12,7 @@
 //  FAST : FP32 byte-indexed lookup tables in shared memory (sweep_lut.cu).
 #include "common.cuh"
 #include "pairer.cuh"
+#include "topk.cuh"
 #include <stdlib.h>
 
 namespace ihtb {
@@ -88,29 +89,57 @@ k_sweep_exact(GenoView gv, const double* __restrict__ v, const double* __restric
 }
 
 // out_j = sinv_j * (sum_s part[s][j] + mu_j * (impute ? sum_{i in miss_j} u_i : -vbar * nmiss_j))
+// tf (optional, tf.keyL != NULL): the first stage of the candidate selection that follows a univariate sweep (topk.cuh
+// TopkFuse) -- keys of |df_j| with the sweep's error bound and the first digit histogram -- computed here, where df_j is
+// produced, instead of in a kernel of its own.  256 threads per CTA.
 template <typename T>
-__global__ void k_sweep_epilogue(const T* __restrict__ part, int64_t n_slabs, int64_t p,
-                                 const double* __restrict__ mu, const double* __restrict__ sinv,
-                                 const int32_t* __restrict__ nmiss, const int64_t* __restrict__ miss_ptr,
-                                 const int32_t* __restrict__ miss_idx, const double* __restrict__ v,
-                                 const double* __restrict__ vbar_p,
-                                 int impute, double* __restrict__ out, const float* __restrict__ scale_p = nullptr) {
+__global__ void __launch_bounds__(256)
+k_sweep_epilogue(const T* __restrict__ part, int64_t n_slabs, int64_t p,
+                 const double* __restrict__ mu, const double* __restrict__ sinv,
+                 const int32_t* __restrict__ nmiss, const int64_t* __restrict__ miss_ptr,
+                 const int32_t* __restrict__ miss_idx, const double* __restrict__ v,
+                 const double* __restrict__ vbar_p,
+                 int impute, double* __restrict__ out, const float* __restrict__ scale_p = nullptr,
+                 TopkFuse tf = TopkFuse()) {
+    __shared__ int sh[TOPK_BINS];
+    const bool fuse = tf.keyL != nullptr;
+    if (fuse) {
+        topk_first_kernel_housekeeping(tf.hist_other, tf.st, tf.cand, tf.cand_fill);
+        for (int b = threadIdx.x; b < TOPK_BINS; b += blockDim.x) sh[b] = 0;
+        __syncthreads();
+    }
     int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (j >= p) return;
-    const double vbar = *vbar_p;
-    double a = 0.0;
-    for (int64_t s = 0; s < n_slabs; ++s) a += (double)part[s * p + j];
-    if (scale_p) a /= (double)*scale_p;            // pair sweep: sums of 2^e-scaled values (exact division)
-    double corr = 0.0;
-    int nm = nmiss[j];
-    if (nm) {
-        if (impute) {
-            for (int64_t e = miss_ptr[j]; e < miss_ptr[j + 1]; ++e) corr += v[miss_idx[e]] - vbar;
-        } else {
-            corr = -vbar * (double)nm;
+    if (j < p) {
+        const double vbar = *vbar_p;
+        double a = 0.0;
+        for (int64_t s = 0; s < n_slabs; ++s) a += (double)part[s * p + j];
+        if (scale_p) a /= (double)*scale_p;            // pair sweep: sums of 2^e-scaled values (exact division)
+        double corr = 0.0;
+        int nm = nmiss[j];
+        if (nm) {
+            if (impute) {
+                for (int64_t e = miss_ptr[j]; e < miss_ptr[j + 1]; ++e) corr += v[miss_idx[e]] - vbar;
+            } else {
+                corr = -vbar * (double)nm;
+            }
+        }
+        const double df = sinv[j] * (a + mu[j] * corr);
+        out[j] = df;
+        if (fuse) {
+            // k_keys_hist0's arithmetic for b0 = 0, eta = 1: bound = coef * (sum |r| + |sum r|) from the score sums
+            const double bound = tf.bound_coef * (tf.scal[1] + fabs(tf.scal[0]));
+            const double w = tf.wt ? tf.wt[j] : 1.0;
+            uint32_t kl, ku;
+            topk_make_keys(0.0 + 1.0 * df, w, fabs(1.0) * tf.scale[j] * bound * w, kl, ku);
+            tf.keyL[j] = kl; tf.keyU[j] = ku;
+            atomicAdd(&sh[kl >> 21], 1);
         }
     }
-    out[j] = sinv[j] * (a + mu[j] * corr);
+    if (fuse) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < TOPK_BINS; b += blockDim.x)
+            if (sh[b]) atomicAdd(&tf.hist[b], sh[b]);
+    }
 }
 
 __global__ void k_vec_mean(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
@@ -165,8 +194,12 @@ struct SweepScratch {
 // dV: n x m column-major device array; dOut: p x m. d_vbar[t] = mean of column t (DEVICE array, so a sweep can be
 // enqueued right behind the kernel that produced the mean without a host round trip).
 // d_l2 (optional, m doubles, PAIR mode): ||v_t - mean||_2 of every right-hand side, for the L2 error bounds.
+// tf (optional, single right-hand side): first stage of the |df| selection, run by the epilogue (topk.cuh TopkFuse).
 void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* d_vbar, int64_t m, double* dOut,
-                           int mode, cudaStream_t s, void* scratch_any, float* sweep_ms, double* d_l2) {
+                           int mode, cudaStream_t s, void* scratch_any, float* sweep_ms, double* d_l2 = nullptr,
+                           const TopkFuse* tf = nullptr) {
+    IHTB_CHECK(!tf || (m == 1 && mode != IHTB_SWEEP_PAIR), IHTB_EINVAL, "fused selection stage: one right-hand side");
+    const TopkFuse fuse = tf ? *tf : TopkFuse();
     SweepScratch local;
     SweepScratch* sc = scratch_any ? reinterpret_cast<SweepScratch*>(scratch_any) : &local;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -200,7 +233,7 @@ void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* d
             sweep_exact_lut_partials(g, v, d_vbar + t, sc->part64.p, s);
             IHTB_LAUNCH((k_sweep_epilogue<double>), (unsigned)ceil_div(g->p, 256), 256, 0, s, sc->part64.p, n_slabs,
                         g->p, g->mu.p, g->sinv.p, g->nmiss.p, g->miss_ptr.p, g->miss_idx.p, v, d_vbar + t,
-                        g->impute, out);
+                        g->impute, out, (const float*)nullptr, fuse);
         } else if (mode == IHTB_SWEEP_EXACT) {
             int64_t words = g->stride >> 2;
             int64_t n_slabs = ceil_div(words, EX_THREADS);
@@ -209,14 +242,14 @@ void sweep_xt_v_with_means(const ihtb_geno* g, const double* dV, const double* d
             IHTB_LAUNCH(k_sweep_exact, grid, EX_THREADS, 0, s, geno_view(g), v, d_vbar + t, sc->part64.p);
             IHTB_LAUNCH((k_sweep_epilogue<double>), (unsigned)ceil_div(g->p, 256), 256, 0, s, sc->part64.p, n_slabs,
                         g->p, g->mu.p, g->sinv.p, g->nmiss.p, g->miss_ptr.p, g->miss_idx.p, v, d_vbar + t,
-                        g->impute, out);
+                        g->impute, out, (const float*)nullptr, fuse);
         } else {
             int64_t n_slabs = sweep_fast_num_slabs(g);
             if (sc->part32.n < (size_t)(n_slabs * g->p)) sc->part32.alloc((size_t)(n_slabs * g->p));
             sweep_fast_partials(g, v, d_vbar + t, sc->part32.p, &n_slabs, s);
             IHTB_LAUNCH((k_sweep_epilogue<float>), (unsigned)ceil_div(g->p, 256), 256, 0, s, sc->part32.p, n_slabs,
                         g->p, g->mu.p, g->sinv.p, g->nmiss.p, g->miss_ptr.p, g->miss_idx.p, v, d_vbar + t,
-                        g->impute, out);
+                        g->impute, out, (const float*)nullptr, fuse);
         }
     }
     if (sweep_ms) {

@@ -3,8 +3,9 @@
 //
 // The sweep's df_j may carry an absolute error of at most e_j = eta * sinv_j * bound (FAST mode: FP32 partial sums).
 // With L_j = |v_j| - e_j and U_j = |v_j| + e_j, let tau be the k-th largest L.  The true k-th largest |v| is >= tau,
-// so every member of the true top-k has U_j >= tau.  This file finds tau with a 3-pass radix select on the
-// order-preserving uint32 image of L (rounded down to FP32), then compacts {j : U_j >= tau} (U rounded up).  The fit
+// so every member of the true top-k has U_j >= tau.  This file finds tau with a two-digit radix select on the
+// order-preserving uint32 image of L (rounded down to FP32; the top 22 bits, two 11-bit digits, decide), then compacts
+// {j : U_j >= tau} (U rounded up).  The fit
 // re-scores those few columns exactly in FP64 and takes the top-k of the exact values, ties broken by lowest index,
 // so the selected support does not depend on the sweep arithmetic.  Only integer atomics: deterministic.
 #include "topk.cuh"
@@ -33,14 +34,7 @@ k_keys_hist0(int64_t p, const double* __restrict__ dfa, const double* __restrict
              uint32_t* __restrict__ keyL, uint32_t* __restrict__ keyU, int* __restrict__ hist,
              const double* __restrict__ l2, int* __restrict__ hist_other, TopkState* __restrict__ st,
              int64_t* __restrict__ cand, int cand_fill) {
-    // housekeeping of the fused chain: the other histogram set is cleared for the NEXT selection, the candidate count
-    // restarts, unused candidate slots read -1 (a gather launched over a fixed number of slots skips them)
-    if (blockIdx.x == 0) {
-        for (int b = threadIdx.x; b < 3 * TK_BINS; b += blockDim.x) hist_other[b] = 0;
-        if (threadIdx.x == 0) { st->prefix = 0; st->k_rem = 0; st->count = 0; st->pad = 0; }
-    }
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cand_fill; i += (int64_t)gridDim.x * blockDim.x)
-        cand[i] = -1;
+    topk_first_kernel_housekeeping(hist_other, st, cand, cand_fill);
     // scal != NULL: the bound comes from the score kernel's sums still on the device:
     // bound = coef * (sum|r| + |sum r|) >= coef * ||r - mean(r)||_1 (no host round trip between sweep and selection)
     // l2 != NULL (PAIR sweeps): bound = coef * ||r - mean(r)||_2, and `sinv` is the handle's sgn array
@@ -53,15 +47,10 @@ k_keys_hist0(int64_t p, const double* __restrict__ dfa, const double* __restrict
         double v = (b0d ? b0d[j] : 0.0) + eta * dfa[j];
         // prior weights (src/utilities.jl:291-315): the projection ranks |v_j| * w_j, so magnitude and error scale by w_j
         const double w = wt ? wt[j] : 1.0;
-        double a = fabs(v) * w;
         // blocked form (multivariate: entry j = t*p_mod + column): per-block bound, sinv of the column
         const double bj = bounds ? bounds[j / p_mod] : bound;
-        double e = fabs(eta) * sinv[bounds ? (j % p_mod) : j] * bj * w + a * 4e-16;
-        double lo = a - e, up = a + e;
-        if (!(lo > 0.0)) lo = 0.0;          // also maps NaN to 0
-        if (!(up >= 0.0)) up = INFINITY;    // NaN: always a candidate
-        uint32_t kl = __float_as_uint(__double2float_rd(lo));
-        uint32_t ku = __float_as_uint(__double2float_ru(up));
+        uint32_t kl, ku;
+        topk_make_keys(v, w, fabs(eta) * sinv[bounds ? (j % p_mod) : j] * bj * w, kl, ku);
         keyL[j] = kl; keyU[j] = ku;
         atomicAdd(&sh[kl >> 21], 1);
     }
@@ -73,7 +62,7 @@ k_keys_hist0(int64_t p, const double* __restrict__ dfa, const double* __restrict
 // Round 1 ran the select as reset / keys+hist0 / pick / hist / pick / hist / pick / compact = 8 dependent launches of a
 // few microseconds each.  Every later pass now RE-DERIVES the digits of the earlier passes from their (finished,
 // read-only) histograms inside each CTA -- a 2048-bin suffix scan per pass and CTA, a microsecond of redundant work --
-// so the chain is keys+hist0 / hist1 / hist2 / compact.  Histograms are double-buffered between two consecutive selections
+// so the chain is keys+hist0 / hist1 / compact (a third digit pass existed until round 2b, see k_compact_fused).  Histograms are double-buffered between two consecutive selections
 // (`set`): the first kernel of a selection clears the other set for the next one, nobody ever clears what is being read.
 constexpr int TK_HIST_STRIDE = 3 * TK_BINS;        // ints per histogram set: hist0 | hist1 | hist2
 
@@ -151,7 +140,7 @@ k_hist_fused(int64_t p, const uint32_t* __restrict__ keyL, const int* __restrict
     hist_flush(sh, hist_out, nb);
 }
 
-// last pass: derive all three digits (tau = the k-th largest lower-bound key), compact {j : keyU_j >= tau}
+// last pass: derive both digits (tau = lower edge of the 22-bit bin of the k-th largest lower-bound key), compact {j : keyU_j >= tau}
 __global__ void __launch_bounds__(TK_THREADS)
 k_compact_fused(int64_t p, const uint32_t* __restrict__ keyU, const int* __restrict__ hists, int kk,
                 TopkState* __restrict__ st, int64_t* __restrict__ cand, int cap) {
@@ -163,10 +152,9 @@ k_compact_fused(int64_t p, const uint32_t* __restrict__ keyU, const int* __restr
     __syncthreads();
     block_pick(hists + TK_BINS, TK_BINS, k1, sh_scan, sh_out);
     tau |= (uint32_t)sh_out[0] << 10;
-    k1 = sh_out[1];
-    __syncthreads();
-    block_pick(hists + 2 * TK_BINS, 1024, k1, sh_scan, sh_out);
-    tau |= (uint32_t)sh_out[0];
+    // Two digits (22 of the 32 key bits: sign, exponent, 13 mantissa bits) are enough: tau is the LOWER edge of the bin that
+    // holds the k-th largest lower-bound key, so {keyU >= tau} is still a superset of the true top-k -- it admits the few
+    // extra entries within 2^-13 of the threshold (re-scored exactly like the rest) and saves the third histogram pass.
     if (blockIdx.x == 0 && threadIdx.x == 0) { st->prefix = tau; st->k_rem = sh_out[1]; }
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < p; j += (int64_t)gridDim.x * blockDim.x) {
         if (keyU[j] >= tau) {
@@ -188,6 +176,7 @@ static void topk_run(TopkCtx& c, const double* d_dfa, const double* d_b0d, const
                      const double* d_scal = nullptr, double bound_coef = 0.0, const double* d_l2 = nullptr,
                      bool fill_cand = false) {
     int grid = tk_grid(c.p);
+    c.fused_hist = nullptr;                 // a complete selection supersedes any first stage left pending
     const int64_t total = c.comm ? c.p_total : c.p;
     int kk = (int)(k < total ? k : total);
     int* hs = c.hist + (size_t)(c.set & 1) * TK_HIST_STRIDE;             // this selection's histograms (all zero)
@@ -198,8 +187,29 @@ static void topk_run(TopkCtx& c, const double* d_dfa, const double* d_b0d, const
     if (c.comm) comm_allreduce_sum_i32(c.comm, hs, TK_BINS, s);
     IHTB_LAUNCH(k_hist_fused, grid, TK_THREADS, 0, s, c.p, c.keyL, hs, 1, kk, hs + TK_BINS);
     if (c.comm) comm_allreduce_sum_i32(c.comm, hs + TK_BINS, TK_BINS, s);
-    IHTB_LAUNCH(k_hist_fused, grid, TK_THREADS, 0, s, c.p, c.keyL, hs, 2, kk, hs + 2 * TK_BINS);
-    if (c.comm) comm_allreduce_sum_i32(c.comm, hs + 2 * TK_BINS, 1024, s);
+    IHTB_LAUNCH(k_compact_fused, grid, TK_THREADS, 0, s, c.p, c.keyU, hs, kk, c.st, c.cand, c.cap);
+}
+
+// The selection by |df| with its first stage (keys, first digit histogram, housekeeping) run by the sweep epilogue:
+// begin() reserves the histogram set and describes the stage, finish() runs the second digit pass and the compaction.
+TopkFuse topk_absdf_fuse_begin(TopkCtx& c, const double* d_sinv, const double* d_scal, double bound_coef) {
+    static_assert(TOPK_BINS == TK_BINS, "one bin count");
+    int* hs = c.hist + (size_t)(c.set & 1) * TK_HIST_STRIDE;
+    int* ho = c.hist + (size_t)((c.set & 1) ^ 1) * TK_HIST_STRIDE;
+    ++c.set;
+    c.fused_hist = hs;
+    TopkFuse f;
+    f.keyL = c.keyL; f.keyU = c.keyU; f.hist = hs; f.hist_other = ho; f.st = c.st; f.cand = c.cand; f.cand_fill = c.cap;
+    f.scale = d_sinv; f.scal = d_scal; f.bound_coef = bound_coef; f.wt = c.wt;
+    return f;
+}
+void topk_candidates_absdf_finish(TopkCtx& c, int64_t k, cudaStream_t s) {
+    IHTB_CHECK(c.fused_hist != nullptr && !c.comm, IHTB_EINVAL, "no fused selection stage pending");
+    int* hs = c.fused_hist;
+    c.fused_hist = nullptr;
+    const int grid = tk_grid(c.p);
+    const int kk = (int)(k < c.p ? k : c.p);
+    IHTB_LAUNCH(k_hist_fused, grid, TK_THREADS, 0, s, c.p, c.keyL, hs, 1, kk, hs + TK_BINS);
     IHTB_LAUNCH(k_compact_fused, grid, TK_THREADS, 0, s, c.p, c.keyU, hs, kk, c.st, c.cand, c.cap);
 }
 
