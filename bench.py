@@ -35,7 +35,7 @@ K_SPARSITY = 20
 SEED = 2024
 DIST, LINK = "Bernoulli", "LogitLink"
 CPU_SAMPLE_COLS = 500_000     # the reference arm at N>1 samples the first 500k columns of the N x 500k problem
-DTYPE = "f64 (sweep: f32 LUT partials per 512-sample slab, f64 across slabs; top-k candidates re-scored in f64)"
+DTYPE = "f64 (sweep: f32 LUT partials per slab of 640 samples (512 without the ternary copy), f64 across slabs; top-k candidates re-scored in f64)"
 PARITY_RTOL = 1e-6
 # One unit of work = one IHT iteration over one 50k x 500k shard.  At N=1 that is an IHT iteration of configs[1]; at N>1
 # (weak scaling, one shard per GPU) the job performs N shard-iterations per global iteration.
