@@ -143,3 +143,24 @@ def test_ternary_tile_format_round_trip():
             byte = T[s, j // 4, w, (j & 3) ^ (w & 3), b].astype(np.int64)
             assert np.array_equal((byte // 3 ** dg) % 3, dos[:, j])
         assert not T[:, :, :, :, :].reshape(slabs, p4 // 4, 32, 4, 4)[:, p // 4:, :, :, :].any() or p % 4      # padding columns are zero
+
+
+def test_ihtresult_builds_dense_beta_on_first_access():
+    """The fit hands the model over as k (index, value) pairs; `IHTResult.beta` (the reference's dense vector,
+    src/data_structures.jl:245-258) is materialised on first access and cached; a dense array passed in is kept as is."""
+    import pickle
+    import numpy as np
+    from mendeliht_jl_b200.api import IHTResult, SparseCoef
+    sp = SparseCoef(10, np.array([2, 5]), np.array([1.5, -2.0]))
+    r = IHTResult(0.1, -1.0, 3, sp, np.ones(1), 1, 2, [], "Normal", 0.5)
+    assert "beta" not in r.__dict__ and r.beta_sparse is sp
+    want = np.zeros(10); want[[2, 5]] = [1.5, -2.0]
+    assert np.array_equal(r.beta, want) and r.beta is r.beta and "beta" in r.__dict__
+    assert np.array_equal(pickle.loads(pickle.dumps(r)).beta, want)
+    dense = IHTResult(0.1, -1.0, 3, want.copy(), np.ones(1), 1, 2, [], "Normal", 0.5)
+    assert dense.beta_sparse is None and np.array_equal(dense.beta, want)
+    try:
+        dense.no_such_field
+        raise AssertionError("AttributeError expected")
+    except AttributeError:
+        pass
