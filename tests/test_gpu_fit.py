@@ -588,9 +588,8 @@ def test_device_side_backtracking_choice_matches_default():
 def test_cv_grid_does_not_depend_on_sweep_pairing():
     """ihtb_cv_run runs two fits at a time per device and serves their sweeps with one PAIR pass (half2 tables, looser
     error bound, more candidates re-scored exactly).  The grid must not depend on it -- plain, with prior weights and
-    debiasing, and with an odd number of fits (the last one sweeps alone): same iteration counts, losses equal up to
-    the summation order of the exact re-scoring (long candidate lists take the blocked gather kernel, short ones the
-    per-column one; both are FP64, their last bits differ)."""
+    debiasing, and with an odd number of fits (the last one sweeps alone): same iteration counts, losses equal to 1e-10
+    (every candidate is re-scored exactly by the same nibble-table kernel whatever sweep screened it)."""
     n, p, q = 3000, 6000, 3
     y, z, *_ = synth.simulate_response(31, n, p, 6, "Normal", n_cov=1)
     g = m.B200SnpLinAlg.synthetic(n, p, 31)
